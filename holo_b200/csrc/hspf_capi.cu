@@ -1,0 +1,471 @@
+// hspf_capi.cu — C ABI of the batched SPF engine (include/holo_spf.h).
+//
+// Host side: CSR validation, transposition, device residency, batch launch.
+// There is no CPU compute path in this file: every result plane is produced by
+// spf_batch_kernel on the device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "holo_spf.h"
+#include "spf_kernel.cuh"
+
+using namespace hspf;
+
+struct hspf_graph {
+    DevGraph d{};
+    void *blob = nullptr;      // single device allocation holding every array
+    size_t blob_bytes = 0;
+    uint32_t max_indeg = 0;
+};
+
+struct hspf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t *d_counter = nullptr;
+    // grow-only scratch
+    void *ws = nullptr;      size_t ws_bytes = 0;       // global state workspace
+    void *stage = nullptr;   size_t stage_bytes = 0;    // device staging of results (host-pointer mode)
+    void *h_pin = nullptr;   size_t h_pin_bytes = 0;    // pinned bounce buffer
+    void *scratch = nullptr; size_t scratch_bytes = 0;  // planes the caller did not ask for
+};
+
+namespace {
+
+int fail(hspf_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int cuda_fail(hspf_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, HSPF_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+int grow(hspf_ctx *ctx, void **p, size_t *have, size_t need, bool pinned = false) {
+    if (*have >= need) return HSPF_OK;
+    if (*p) {
+        if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+        *p = nullptr; *have = 0;
+    }
+    size_t want = need + need / 4;
+    cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (e != cudaSuccess) { *p = nullptr; return cuda_fail(ctx, e, pinned ? "cudaMallocHost" : "cudaMalloc"); }
+    *have = want;
+    return HSPF_OK;
+}
+
+template <typename VT>
+int launch(hspf_ctx *ctx, const BatchArgs &args, size_t smem, int grid) {
+    if (smem > 0) {
+        CK(cudaFuncSetAttribute(spf_batch_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    spf_batch_kernel<VT><<<grid, kThreads, smem, ctx->stream>>>(args);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return HSPF_OK;
+}
+
+template <typename VT>
+int max_ctas_per_sm(size_t smem) {
+    int n = 0;
+    if (smem > 0)
+        cudaFuncSetAttribute(spf_batch_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spf_batch_kernel<VT>, kThreads, smem) != cudaSuccess) n = 1;
+    return n < 1 ? 1 : n;
+}
+
+// Enqueue one batch.  All pointers in `jobs`/`out` are device pointers here.
+int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+    const uint32_t V = g->d.V;
+    const bool q16 = V <= 0xFFFFu;
+    const size_t sb = state_bytes(V, q16 ? 2 : 4);
+    // static smem of the kernel (Small) is ~4.5 KB; leave headroom
+    const size_t smem_cap = ctx->smem_optin > 6144 ? ctx->smem_optin - 6144 : 0;
+    const bool in_smem = sb <= smem_cap;
+
+    BatchArgs a{};
+    a.g = g->d;
+    a.n_jobs = jobs->n_jobs;
+    a.roots = jobs->roots;
+    a.ov_off = jobs->ov_off;
+    a.ov_edge = jobs->ov_edge;
+    a.ov_cost = jobs->ov_cost;
+    a.out_dist = out->dist;
+    a.out_hops = out->hops;
+    a.out_fp = out->first_parent;
+    a.out_npar = out->n_parents;
+    a.out_nh = out->nh_mask;
+    a.out_status = out->job_status;
+    a.nhw = out->nh_words;
+    a.job_counter = ctx->d_counter;
+
+    int per_sm = in_smem ? (q16 ? max_ctas_per_sm<uint16_t>(sb) : max_ctas_per_sm<uint32_t>(sb))
+                         : (q16 ? max_ctas_per_sm<uint16_t>(0) : max_ctas_per_sm<uint32_t>(0));
+    int grid = ctx->sm_count * per_sm;
+    if ((uint32_t)grid > jobs->n_jobs) grid = (int)jobs->n_jobs;
+    if (grid < 1) grid = 1;
+
+    if (!in_smem) {
+        int rc = grow(ctx, &ctx->ws, &ctx->ws_bytes, sb * (size_t)grid);
+        if (rc) return rc;
+        a.ws = static_cast<uint8_t *>(ctx->ws);
+        a.ws_stride = sb;
+    }
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), ctx->stream));
+    return q16 ? launch<uint16_t>(ctx, a, in_smem ? sb : 0, grid)
+               : launch<uint32_t>(ctx, a, in_smem ? sb : 0, grid);
+}
+
+struct Planes {   // byte sizes of the result planes of a batch
+    size_t dist, hops, fp, npar, nh, status;
+    size_t total() const { return dist + hops + fp + npar + nh + status; }
+};
+
+Planes plane_sizes(uint32_t n_jobs, uint32_t V, uint32_t nhw) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t n = (size_t)n_jobs * V;
+    Planes p;
+    p.dist = al(n * 4); p.hops = al(n * 2); p.fp = al(n * 4); p.npar = al(n * 2);
+    p.nh = al(n * 8 * nhw); p.status = al((size_t)n_jobs * 4);
+    return p;
+}
+
+int check_result_args(hspf_ctx *ctx, const hspf_result *out) {
+    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
+    if (out->nh_words < 1 || out->nh_words > 4) return fail(ctx, HSPF_E_INVAL, "nh_words must be 1..4");
+    return HSPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hspf_version(void) { return "holo_spf 0.1 sm_100a"; }
+
+int hspf_ctx_create(int device, hspf_ctx **out) {
+    if (!out) return HSPF_E_INVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return HSPF_E_CUDA;
+    hspf_ctx *ctx = new (std::nothrow) hspf_ctx();
+    if (!ctx) return HSPF_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HSPF_E_CUDA; }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return HSPF_E_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HSPF_E_CUDA; }
+    if (cudaMalloc(&ctx->d_counter, sizeof(uint32_t)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream); delete ctx; return HSPF_E_CUDA;
+    }
+    *out = ctx;
+    return HSPF_OK;
+}
+
+void hspf_ctx_destroy(hspf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    delete ctx;
+}
+
+const char *hspf_last_error(const hspf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
+    if (!ctx || !g || !out) return HSPF_E_INVAL;
+    *out = nullptr;
+    try {
+        const uint32_t V = g->n_vertices, E = g->n_edges;
+        if (V == 0 || V >= 0xFFFFFFF0u) return fail(ctx, HSPF_E_INVAL, "n_vertices out of range");
+        if (!g->row_ptr || !g->vflags || (E && (!g->col || !g->cost))) return fail(ctx, HSPF_E_INVAL, "null CSR array");
+        if (g->row_ptr[0] != 0 || g->row_ptr[V] != E) return fail(ctx, HSPF_E_INVAL, "row_ptr[0]!=0 or row_ptr[V]!=E");
+        bool zero_cost_hop_tail = false;
+        uint64_t cost_sum = 0;
+        std::vector<uint32_t> indeg(V + 1, 0);
+        for (uint32_t u = 0; u < V; ++u) {
+            if (g->row_ptr[u + 1] < g->row_ptr[u]) return fail(ctx, HSPF_E_INVAL, "row_ptr not monotone");
+            const bool uh = g->vflags[u] & HSPF_VF_HOP;
+            for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e) {
+                const uint32_t v = g->col[e];
+                if (v >= V) return fail(ctx, HSPF_E_INVAL, "col out of range");
+                if (v == u) return fail(ctx, HSPF_E_INVAL, "self loop");
+                if (g->cost[e] == HSPF_COST_DISABLED) return fail(ctx, HSPF_E_INVAL, "cost 0xFFFFFFFF is reserved");
+                if (!uh && !(g->vflags[v] & HSPF_VF_HOP)) return fail(ctx, HSPF_E_INVAL, "edge joins two non-HOP vertices");
+                if (uh && g->cost[e] == 0) zero_cost_hop_tail = true;
+                cost_sum += g->cost[e];
+                indeg[v + 1]++;
+            }
+        }
+        if (zero_cost_hop_tail)
+            return fail(ctx, HSPF_E_NEEDS_ORACLE,
+                        "zero-cost link out of a hop-counting vertex: ECMP DAG depends on pop order");
+        uint32_t max_indeg = 0;
+        for (uint32_t v = 0; v < V; ++v) max_indeg = std::max(max_indeg, indeg[v + 1]);
+        if (max_indeg >= 0xFFFFu) return fail(ctx, HSPF_E_UNSUPPORTED, "in-degree >= 65535");
+
+        // transposed CSR: in-edges of v ordered by (source, forward edge index)
+        std::vector<uint32_t> irow(V + 1, 0);
+        for (uint32_t v = 0; v < V; ++v) irow[v + 1] = irow[v] + indeg[v + 1];
+        std::vector<uint32_t> fill(irow.begin(), irow.end() - 1);
+        std::vector<uint2> iedge(E);
+        std::vector<uint32_t> ieid(E);
+        std::vector<uint2> fedge(E);
+        for (uint32_t u = 0; u < V; ++u)
+            for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e) {
+                const uint32_t v = g->col[e];
+                const uint32_t k = fill[v]++;
+                iedge[k] = make_uint2(u, g->cost[e]);
+                ieid[k] = e;
+                fedge[e] = make_uint2(v, g->cost[e]);
+            }
+
+        auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+        const size_t o_row = 0;
+        const size_t o_edge = o_row + al((size_t)(V + 1) * 4);
+        const size_t o_irow = o_edge + al((size_t)E * 8);
+        const size_t o_iedge = o_irow + al((size_t)(V + 1) * 4);
+        const size_t o_ieid = o_iedge + al((size_t)E * 8);
+        const size_t o_vf = o_ieid + al((size_t)E * 4);
+        const size_t total = o_vf + al(V);
+
+        hspf_graph *G = new hspf_graph();
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess) e = cudaMalloc(&G->blob, total);
+        if (e != cudaSuccess) { delete G; return cuda_fail(ctx, e, "cudaMalloc(graph)"); }
+        G->blob_bytes = total;
+        uint8_t *b = static_cast<uint8_t *>(G->blob);
+        std::vector<uint8_t> host(total, 0);
+        std::memcpy(host.data() + o_row, g->row_ptr, (size_t)(V + 1) * 4);
+        if (E) {
+            std::memcpy(host.data() + o_edge, fedge.data(), (size_t)E * 8);
+            std::memcpy(host.data() + o_iedge, iedge.data(), (size_t)E * 8);
+            std::memcpy(host.data() + o_ieid, ieid.data(), (size_t)E * 4);
+        }
+        std::memcpy(host.data() + o_irow, irow.data(), (size_t)(V + 1) * 4);
+        std::memcpy(host.data() + o_vf, g->vflags, V);
+        e = cudaMemcpyAsync(b, host.data(), total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(G->blob); delete G; return cuda_fail(ctx, e, "graph H2D"); }
+
+        G->d.V = V; G->d.E = E;
+        G->d.row = reinterpret_cast<const uint32_t *>(b + o_row);
+        G->d.edge = reinterpret_cast<const uint2 *>(b + o_edge);
+        G->d.irow = reinterpret_cast<const uint32_t *>(b + o_irow);
+        G->d.iedge = reinterpret_cast<const uint2 *>(b + o_iedge);
+        G->d.ieid = reinterpret_cast<const uint32_t *>(b + o_ieid);
+        G->d.vflags = b + o_vf;
+        G->d.reject_above = g->reject_above;
+        G->d.saturate_at = g->saturate_at;
+        G->d.flags = g->flags;
+        uint32_t delta = g->delta;
+        if (delta == 0) {
+            uint64_t mean = E ? cost_sum / E : 1;
+            delta = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mean, 1), 0x7FFFFFFFu);
+        }
+        G->d.delta = delta;
+        G->max_indeg = max_indeg;
+        *out = G;
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+void hspf_graph_free(hspf_ctx *ctx, hspf_graph *g) {
+    if (!g) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (g->blob) cudaFree(g->blob);
+    delete g;
+}
+
+int hspf_sync(hspf_ctx *ctx) {
+    if (!ctx) return HSPF_E_INVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HSPF_OK;
+}
+
+int hspf_run_batch_async(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+    if (!ctx || !g || !jobs) return HSPF_E_INVAL;
+    int rc = check_result_args(ctx, out);
+    if (rc) return rc;
+    if (jobs->n_jobs == 0) return HSPF_OK;
+    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        // planes the caller skipped still have to exist on the device
+        hspf_result r = *out;
+        Planes ps = plane_sizes(jobs->n_jobs, g->d.V, r.nh_words);
+        size_t need = 0;
+        if (!r.dist) need += ps.dist;
+        if (!r.hops) need += ps.hops;
+        if (!r.first_parent) need += ps.fp;
+        if (!r.n_parents) need += ps.npar;
+        if (!r.nh_mask) need += ps.nh;
+        if (!r.job_status) need += ps.status;
+        if (need) {
+            rc = grow(ctx, &ctx->scratch, &ctx->scratch_bytes, need);
+            if (rc) return rc;
+            uint8_t *p = static_cast<uint8_t *>(ctx->scratch);
+            if (!r.dist) { r.dist = reinterpret_cast<uint32_t *>(p); p += ps.dist; }
+            if (!r.hops) { r.hops = reinterpret_cast<uint16_t *>(p); p += ps.hops; }
+            if (!r.first_parent) { r.first_parent = reinterpret_cast<uint32_t *>(p); p += ps.fp; }
+            if (!r.n_parents) { r.n_parents = reinterpret_cast<uint16_t *>(p); p += ps.npar; }
+            if (!r.nh_mask) { r.nh_mask = reinterpret_cast<uint64_t *>(p); p += ps.nh; }
+            if (!r.job_status) { r.job_status = reinterpret_cast<uint32_t *>(p); p += ps.status; }
+        }
+        return enqueue(ctx, g, jobs, &r);
+    } catch (...) {
+        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out, uint32_t flags) {
+    if (!ctx || !g || !jobs) return HSPF_E_INVAL;
+    int rc = check_result_args(ctx, out);
+    if (rc) return rc;
+    if (jobs->n_jobs == 0) return HSPF_OK;
+    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const uint32_t n = jobs->n_jobs, V = g->d.V;
+        if (flags & HSPF_RUN_DEVICE_PTRS) {
+            rc = hspf_run_batch_async(ctx, g, jobs, out);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+            return HSPF_OK;   // job_status stays on the device in this mode
+        }
+        // ---- host-pointer mode: validate, stage in, run, stage out --------------
+        uint32_t n_ov = 0;
+        for (uint32_t j = 0; j < n; ++j)
+            if (jobs->roots[j] >= V) return fail(ctx, HSPF_E_INVAL, "root out of range");
+        if (jobs->ov_off) {
+            if (!jobs->ov_edge || !jobs->ov_cost) {
+                if (jobs->ov_off[n] != 0) return fail(ctx, HSPF_E_INVAL, "null override arrays");
+            }
+            for (uint32_t j = 0; j < n; ++j) {
+                if (jobs->ov_off[j + 1] < jobs->ov_off[j]) return fail(ctx, HSPF_E_INVAL, "ov_off not monotone");
+                if (jobs->ov_off[j + 1] - jobs->ov_off[j] > HSPF_MAX_OVERRIDES)
+                    return fail(ctx, HSPF_E_UNSUPPORTED, "more than HSPF_MAX_OVERRIDES overrides in a job");
+            }
+            n_ov = jobs->ov_off[n];
+            for (uint32_t i = 0; i < n_ov; ++i)
+                if (jobs->ov_edge[i] >= g->d.E) return fail(ctx, HSPF_E_INVAL, "override edge out of range");
+        }
+        auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+        const size_t in_roots = al((size_t)n * 4);
+        const size_t in_off = jobs->ov_off ? al((size_t)(n + 1) * 4) : 0;
+        const size_t in_ove = al((size_t)n_ov * 4 + 4), in_ovc = al((size_t)n_ov * 4 + 4);
+        const size_t in_total = in_roots + in_off + in_ove + in_ovc;
+        Planes ps = plane_sizes(n, V, out->nh_words);
+        const size_t dev_total = in_total + ps.total();
+        rc = grow(ctx, &ctx->stage, &ctx->stage_bytes, dev_total);
+        if (rc) return rc;
+        rc = grow(ctx, &ctx->h_pin, &ctx->h_pin_bytes, in_total, true);
+        if (rc) return rc;
+        uint8_t *hp = static_cast<uint8_t *>(ctx->h_pin);
+        uint8_t *dp = static_cast<uint8_t *>(ctx->stage);
+        std::memcpy(hp, jobs->roots, (size_t)n * 4);
+        if (jobs->ov_off) {
+            std::memcpy(hp + in_roots, jobs->ov_off, (size_t)(n + 1) * 4);
+            if (n_ov) {
+                std::memcpy(hp + in_roots + in_off, jobs->ov_edge, (size_t)n_ov * 4);
+                std::memcpy(hp + in_roots + in_off + in_ove, jobs->ov_cost, (size_t)n_ov * 4);
+            }
+        }
+        CK(cudaMemcpyAsync(dp, hp, in_total, cudaMemcpyHostToDevice, ctx->stream));
+        hspf_jobs dj{};
+        dj.n_jobs = n;
+        dj.roots = reinterpret_cast<const uint32_t *>(dp);
+        dj.ov_off = jobs->ov_off ? reinterpret_cast<const uint32_t *>(dp + in_roots) : nullptr;
+        dj.ov_edge = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off);
+        dj.ov_cost = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off + in_ove);
+        uint8_t *rp = dp + in_total;
+        hspf_result dr{};
+        dr.nh_words = out->nh_words;
+        dr.dist = reinterpret_cast<uint32_t *>(rp); rp += ps.dist;
+        dr.hops = reinterpret_cast<uint16_t *>(rp); rp += ps.hops;
+        dr.first_parent = reinterpret_cast<uint32_t *>(rp); rp += ps.fp;
+        dr.n_parents = reinterpret_cast<uint16_t *>(rp); rp += ps.npar;
+        dr.nh_mask = reinterpret_cast<uint64_t *>(rp); rp += ps.nh;
+        dr.job_status = reinterpret_cast<uint32_t *>(rp); rp += ps.status;
+        rc = enqueue(ctx, g, &dj, &dr);
+        if (rc) return rc;
+        const size_t nv = (size_t)n * V;
+        if (out->dist) CK(cudaMemcpyAsync(out->dist, dr.dist, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->hops) CK(cudaMemcpyAsync(out->hops, dr.hops, nv * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->first_parent) CK(cudaMemcpyAsync(out->first_parent, dr.first_parent, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->n_parents) CK(cudaMemcpyAsync(out->n_parents, dr.n_parents, nv * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->nh_mask) CK(cudaMemcpyAsync(out->nh_mask, dr.nh_mask, nv * 8 * out->nh_words, cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<uint32_t> st(n);
+        CK(cudaMemcpyAsync(st.data(), dr.job_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool any = false;
+        for (uint32_t j = 0; j < n; ++j) any |= (st[j] != 0);
+        if (out->job_status) std::memcpy(out->job_status, st.data(), (size_t)n * 4);
+        if (any) return fail(ctx, HSPF_E_JOB_STATUS, "one or more jobs need the CPU path (see job_status)");
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+int hspf_atom_count(const hspf_csr *g, uint32_t root, uint32_t *n_atoms) {
+    if (!g || !n_atoms || root >= g->n_vertices) return HSPF_E_INVAL;
+    uint32_t rb = g->row_ptr[root], re = g->row_ptr[root + 1];
+    uint32_t n = re - rb;
+    for (uint32_t e = rb; e < re; ++e) {
+        uint32_t h = g->col[e];
+        if (!(g->vflags[h] & HSPF_VF_HOP)) n += g->row_ptr[h + 1] - g->row_ptr[h];
+    }
+    *n_atoms = n;
+    return HSPF_OK;
+}
+
+int hspf_atom_decode(const hspf_csr *g, uint32_t root, uint32_t atom, uint32_t *tail, uint32_t *edge) {
+    if (!g || !tail || !edge || root >= g->n_vertices) return HSPF_E_INVAL;
+    uint32_t rb = g->row_ptr[root], re = g->row_ptr[root + 1];
+    uint32_t deg = re - rb;
+    if (atom < deg) { *tail = root; *edge = rb + atom; return HSPF_OK; }
+    uint32_t base = deg;
+    for (uint32_t e = rb; e < re; ++e) {
+        uint32_t h = g->col[e];
+        if (g->vflags[h] & HSPF_VF_HOP) continue;
+        uint32_t d = g->row_ptr[h + 1] - g->row_ptr[h];
+        if (atom < base + d) { *tail = h; *edge = g->row_ptr[h] + (atom - base); return HSPF_OK; }
+        base += d;
+    }
+    return HSPF_E_INVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,415 @@
+// spf_kernel.cuh — device side of the batched SPF engine (sm_100a).
+//
+// One persistent CTA per SM slot; each CTA loops over jobs (roots / perturbed
+// topologies).  All per-job mutable state (tentative distances, frontier
+// queues, ECMP in-degree counters) lives in shared memory; the read-only CSR
+// (forward + transposed) is shared by every CTA of the launch and is served
+// from L1/L2 (a 10k-vertex LSDB is < 1 MB, the B200 L2 is 126 MB).
+//
+// Per job the kernel reproduces the result of the reference Dijkstra
+//   holo-ospf/src/spf.rs:587-729 (run_area) / holo-isis/src/spf.rs:525-707
+// under the static-order assumption of SURVEY.md §8a "semantics that bite" #1
+// (no zero-cost edge out of a hop-counting vertex, no saturation), in three
+// phases:
+//   1. SSSP   : near/far bucketed label-correcting relaxation, atomicMin on the
+//               shared-memory distance array (distances are order independent);
+//   2. parents: pull pass over the transposed CSR: ECMP in-degree and
+//               first parent = DAG parent with the smallest (distance, id),
+//               i.e. the vertex whose relaxation created the final candidate
+//               entry in the reference (spf.rs:700-703);
+//   3. Kahn   : topological push over DAG edges; hops follow the first parent
+//               (spf.rs:675-678), next-hop atom sets are OR-ed over all ECMP
+//               parents (spf.rs:747-766 / holo-isis spf.rs:678-702).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hspf {
+
+constexpr uint32_t kInf = 0xFFFFFFFFu;
+constexpr int kThreads = 512;
+constexpr int kMaxOv = 8;          // HSPF_MAX_OVERRIDES
+constexpr int kMaxRootDeg = 512;   // root-edge table entries kept in smem
+constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
+constexpr uint32_t kGfNoHopTargetNoNh = 1u;
+constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
+
+struct DevGraph {
+    uint32_t V, E;
+    const uint32_t *row;    // [V+1]
+    const uint2 *edge;      // [E] {col, cost}
+    const uint32_t *irow;   // [V+1] transposed
+    const uint2 *iedge;     // [E] {src, cost}
+    const uint32_t *ieid;   // [E] forward edge index of the in-edge
+    const uint8_t *vflags;  // [V]
+    uint32_t reject_above, saturate_at, flags, delta;
+};
+
+struct BatchArgs {
+    DevGraph g;
+    uint32_t n_jobs;
+    const uint32_t *roots;
+    const uint32_t *ov_off;   // may be null
+    const uint32_t *ov_edge;
+    const uint32_t *ov_cost;
+    uint32_t *out_dist;       // [n_jobs][V]
+    uint16_t *out_hops;
+    uint32_t *out_fp;
+    uint16_t *out_npar;
+    uint64_t *out_nh;         // [n_jobs][V][nhw]
+    uint32_t *out_status;     // [n_jobs]
+    uint32_t nhw;
+    uint8_t *ws;              // per-CTA global workspace when state does not fit smem
+    size_t ws_stride;         // bytes per CTA (0: state in smem)
+    uint32_t *job_counter;    // dynamic job fetch
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bytes of per-job mutable state for V vertices and queue entry size qsz.
+__host__ __device__ inline size_t state_bytes(uint32_t V, int qsz) {
+    size_t Vp = align_up(V, 4);
+    size_t b = 0;
+    b += Vp * 4;                      // dist
+    b += align_up(Vp * qsz, 16) * 2;  // qa, qb
+    b += align_up(Vp * 2, 16);        // pend (u16, packed pairs)
+    b += align_up((Vp + 31) / 32 * 4, 16) * 2;  // two frontier bitmaps
+    return align_up(b, 16);
+}
+
+struct Ov {   // overrides of the current job, in smem
+    uint32_t n;
+    uint32_t tail[kMaxOv], head[kMaxOv], edge[kMaxOv], cost[kMaxOv];
+};
+
+struct Small {  // small per-CTA control block in smem
+    Ov ov;
+    uint32_t cnt[2];      // alternating queue fill counters
+    uint32_t scan_min;
+    uint32_t status;
+    uint32_t job;
+    uint32_t root_deg, n_roottab;
+    uint32_t rt_target[kMaxRootDeg];  // non-HOP heads of root edges
+    uint32_t rt_base[kMaxRootDeg];
+};
+
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;
+    return s < a ? kInf : s;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// Warp-aggregated queue push (all currently converged lanes take part).
+template <typename VT>
+__device__ __forceinline__ void q_push(VT *q, uint32_t *counter, uint32_t v) {
+    unsigned active = __activemask();
+    int leader = __ffs(active) - 1;
+    unsigned rank = __popc(active & ((1u << lane_id()) - 1));
+    uint32_t base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, __popc(active));
+    base = __shfl_sync(active, base, leader);
+    q[base + rank] = (VT)v;
+}
+
+__device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) {
+    if (fl & kVfLeaf) return false;
+    if ((fl & kVfLeafUnlessRoot) && u != root) return false;
+    return true;
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ Small S;
+
+    const DevGraph &g = a.g;
+    const uint32_t V = g.V;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t Vp = (uint32_t)align_up(V, 4);
+    const uint32_t nbw = (Vp + 31) / 32;
+
+    uint8_t *base = a.ws_stride ? a.ws + (size_t)blockIdx.x * a.ws_stride : smem_raw;
+    uint32_t *dist = reinterpret_cast<uint32_t *>(base);
+    size_t off = (size_t)Vp * 4;
+    VT *qa = reinterpret_cast<VT *>(base + off);
+    off += align_up((size_t)Vp * sizeof(VT), 16);
+    VT *qb = reinterpret_cast<VT *>(base + off);
+    off += align_up((size_t)Vp * sizeof(VT), 16);
+    uint32_t *pend32 = reinterpret_cast<uint32_t *>(base + off);  // packed u16 pairs
+    uint16_t *pend = reinterpret_cast<uint16_t *>(base + off);
+    off += align_up((size_t)Vp * 2, 16);
+    uint32_t *bm0 = reinterpret_cast<uint32_t *>(base + off);
+    off += align_up((size_t)nbw * 4, 16);
+    uint32_t *bm1 = reinterpret_cast<uint32_t *>(base + off);
+
+    const uint32_t nhw = a.nhw;
+
+    for (;;) {
+        // ---- fetch next job -------------------------------------------------
+        __syncthreads();
+        if (tid == 0) S.job = atomicAdd(a.job_counter, 1u);
+        __syncthreads();
+        const uint32_t job = S.job;
+        if (job >= a.n_jobs) break;
+        const uint32_t root = a.roots[job];
+        const size_t jo = (size_t)job * V;
+        uint16_t *o_hops = a.out_hops + jo;
+        uint32_t *o_fp = a.out_fp + jo;
+        uint16_t *o_npar = a.out_npar + jo;
+        uint64_t *o_nh = a.out_nh + jo * nhw;
+        uint32_t *o_dist = a.out_dist + jo;
+
+        // ---- per-job init -----------------------------------------------------
+        for (uint32_t v = tid; v < Vp; v += kThreads) dist[v] = kInf;
+        for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
+        for (uint32_t v = tid; v < V; v += kThreads) o_hops[v] = 0;
+        for (size_t i = tid; i < (size_t)V * nhw; i += kThreads) o_nh[i] = 0ull;
+        if (tid == 0) {
+            S.status = 0;
+            S.cnt[0] = 1;
+            S.cnt[1] = 0;
+            S.scan_min = kInf;
+            uint32_t n = 0;
+            if (a.ov_off) n = a.ov_off[job + 1] - a.ov_off[job];
+            S.ov.n = n > kMaxOv ? kMaxOv : n;
+        }
+        __syncthreads();
+        if (tid < S.ov.n) {
+            uint32_t e = a.ov_edge[a.ov_off[job] + tid];
+            uint32_t c = a.ov_cost[a.ov_off[job] + tid];
+            // tail = last vertex with row[v] <= e
+            uint32_t lo = 0, hi = V;  // invariant row[lo] <= e < row[hi]
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (g.row[mid] <= e) lo = mid; else hi = mid;
+            }
+            S.ov.tail[tid] = lo;
+            S.ov.head[tid] = g.edge[e].x;
+            S.ov.edge[tid] = e;
+            S.ov.cost[tid] = c;
+            if (c == 0 && (g.vflags[lo] & kVfHop)) atomicOr(&S.status, kJsOrder);
+        }
+        if (tid == 0) {
+            dist[root] = 0;
+            qa[0] = (VT)root;
+        }
+        // root edge table: bases of first-hop atoms behind non-HOP heads
+        if (tid == 32) {
+            uint32_t rb = g.row[root], re = g.row[root + 1];
+            uint32_t deg = re - rb;
+            S.root_deg = deg;
+            uint32_t nt = 0, nextbase = deg;
+            for (uint32_t e = rb; e < re; ++e) {
+                uint32_t h = g.edge[e].x;
+                if (!(g.vflags[h] & kVfHop)) {
+                    if (nt < (uint32_t)kMaxRootDeg) {
+                        S.rt_target[nt] = h;
+                        S.rt_base[nt] = nextbase;
+                        ++nt;
+                    } else {
+                        atomicOr(&S.status, kJsTooManyAtoms);
+                    }
+                    nextbase += g.row[h + 1] - g.row[h];
+                }
+            }
+            S.n_roottab = nt;
+        }
+        __syncthreads();
+        const uint32_t n_ov = S.ov.n;
+
+        // ======================= phase 1: SSSP ==================================
+        const uint32_t delta = g.delta ? g.delta : 1u;
+        uint32_t hi_thr = delta;       // near bucket is [*, hi_thr)
+        uint32_t *bm_next = bm0, *bm_old = bm1;
+        VT *qcur = qa, *qnext = qb;
+        uint32_t p = 0;                // S.cnt[p] counts qcur, S.cnt[p^1] counts qnext
+        for (;;) {
+            for (;;) {
+                const uint32_t n_cur = S.cnt[p];
+                if (n_cur == 0) break;
+                for (uint32_t i = tid; i < n_cur; i += kThreads) {
+                    const uint32_t u = qcur[i];
+                    const uint32_t du = dist[u];
+                    const uint32_t fu = g.vflags[u];
+                    if (!expands(fu, u, root)) continue;
+                    bool uo = false;
+                    for (uint32_t k = 0; k < n_ov; ++k) uo |= (S.ov.tail[k] == u);
+                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
+                    for (uint32_t e = eb; e < ee; ++e) {
+                        uint2 ec = g.edge[e];
+                        uint32_t c = ec.y;
+                        if (uo) {
+                            for (uint32_t k = 0; k < n_ov; ++k)
+                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
+                            if (c == kInf) continue;
+                        }
+                        const uint32_t nd = sat_add(du, c);
+                        if (nd > g.reject_above) continue;
+                        const uint32_t v = ec.x;
+                        if (nd < dist[v]) {
+                            const uint32_t old = atomicMin(&dist[v], nd);
+                            if (nd < old && nd < hi_thr) {
+                                const uint32_t bit = 1u << (v & 31);
+                                const uint32_t ob = atomicOr(&bm_next[v >> 5], bit);
+                                if (!(ob & bit)) q_push(qnext, &S.cnt[p ^ 1], v);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // every thread has consumed S.cnt[p]; recycle it for the round after next
+                if (tid == 0) S.cnt[p] = 0;
+                // the bitmap that guarded this round's queue becomes the next guard
+                for (uint32_t w = tid; w < nbw; w += kThreads) bm_old[w] = 0;
+                { uint32_t *t = bm_next; bm_next = bm_old; bm_old = t; }
+                { VT *t = qcur; qcur = qnext; qnext = t; }
+                p ^= 1;
+                __syncthreads();
+            }
+            // near bucket exhausted (S.cnt[0] == S.cnt[1] == 0): everything below
+            // hi_thr is settled.  Collect the next bucket [m, m + delta) into qcur,
+            // where m = min unsettled distance.
+            uint32_t lo_thr = hi_thr;
+            bool done = false;
+            for (;;) {
+                if (tid == 0) { S.scan_min = kInf; S.cnt[p] = 0; }
+                __syncthreads();
+                const uint32_t hi2 = sat_add(lo_thr, delta);
+                uint32_t lmin = kInf;
+                for (uint32_t v = tid; v < V; v += kThreads) {
+                    const uint32_t d = dist[v];
+                    if (d >= lo_thr && d != kInf) {
+                        lmin = min(lmin, d);
+                        if (d < hi2) q_push(qcur, &S.cnt[p], v);
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+                if (lane_id() == 0 && lmin != kInf) atomicMin(&S.scan_min, lmin);
+                __syncthreads();
+                const uint32_t found = S.cnt[p];
+                const uint32_t m = S.scan_min;
+                __syncthreads();   // all reads done before a possible reset above
+                if (found > 0) { hi_thr = hi2; break; }
+                if (m == kInf) { done = true; break; }
+                lo_thr = m;   // jump over the empty gap and rescan
+            }
+            if (done) break;
+        }
+        __syncthreads();
+
+        // ======================= phase 2: ECMP parents (pull) ====================
+        uint32_t sat_flag = 0;
+        for (uint32_t v = tid; v < Vp; v += kThreads) {
+            uint32_t cnt = 0, bd = kInf, bu = kInf;
+            if (v < V) {
+                const uint32_t dv = dist[v];
+                if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
+                if (v != root && dv != kInf) {
+                    bool vo = false;
+                    for (uint32_t k = 0; k < n_ov; ++k) vo |= (S.ov.head[k] == v);
+                    const uint32_t ib = g.irow[v], ie = g.irow[v + 1];
+                    for (uint32_t i = ib; i < ie; ++i) {
+                        const uint2 sc = g.iedge[i];
+                        const uint32_t u = sc.x;
+                        const uint32_t du = dist[u];
+                        if (du == kInf) continue;
+                        if (!expands(g.vflags[u], u, root)) continue;
+                        uint32_t c = sc.y;
+                        if (vo) {
+                            const uint32_t e = g.ieid[i];
+                            for (uint32_t k = 0; k < n_ov; ++k)
+                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
+                            if (c == kInf) continue;
+                        }
+                        if (sat_add(du, c) != dv) continue;
+                        ++cnt;
+                        if (du < bd || (du == bd && u < bu)) { bd = du; bu = u; }
+                    }
+                }
+                o_fp[v] = bu;
+                o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
+            }
+            pend[v] = (uint16_t)min(cnt, 0xFFFFu);
+        }
+        if (sat_flag) atomicOr(&S.status, kJsSaturated);
+        if (tid == 0) { S.cnt[0] = 1; S.cnt[1] = 0; qa[0] = (VT)root; }
+        __syncthreads();
+
+        // ======================= phase 3: Kahn push over the ECMP DAG ============
+        qcur = qa; qnext = qb;
+        p = 0;
+        {
+            for (;;) {
+                const uint32_t n_cur = S.cnt[p];
+                if (n_cur == 0) break;
+                for (uint32_t i = tid; i < n_cur; i += kThreads) {
+                    const uint32_t u = qcur[i];
+                    const uint32_t fu = g.vflags[u];
+                    if (!expands(fu, u, root)) continue;
+                    const uint32_t du = dist[u];
+                    const uint32_t hu = __ldcg(&o_hops[u]);
+                    uint64_t nhu[4] = {0, 0, 0, 0};
+                    uint32_t abase = 0;
+                    bool atoms_ok = true;
+                    if (hu != 0) {
+                        for (uint32_t w = 0; w < nhw; ++w) nhu[w] = __ldcg(&o_nh[(size_t)u * nhw + w]);
+                    } else if (u != root) {
+                        // non-HOP vertex directly attached to the root
+                        atoms_ok = false;
+                        for (uint32_t k = 0; k < S.n_roottab; ++k)
+                            if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
+                        if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
+                    }
+                    bool uo = false;
+                    for (uint32_t k = 0; k < n_ov; ++k) uo |= (S.ov.tail[k] == u);
+                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
+                    for (uint32_t e = eb; e < ee; ++e) {
+                        const uint2 ec = g.edge[e];
+                        const uint32_t v = ec.x;
+                        if (v == root) continue;
+                        uint32_t c = ec.y;
+                        if (uo) {
+                            for (uint32_t k = 0; k < n_ov; ++k)
+                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
+                            if (c == kInf) continue;
+                        }
+                        if (sat_add(du, c) != dist[v]) continue;
+                        const uint32_t fv = g.vflags[v];
+                        if (hu == 0) {
+                            if (!((g.flags & kGfNoHopTargetNoNh) && !(fv & kVfHop)) && atoms_ok) {
+                                const uint32_t atom = abase + (e - eb);
+                                if (atom < 64u * nhw)
+                                    atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
+                                             1ull << (atom & 63));
+                                else
+                                    atomicOr(&S.status, kJsTooManyAtoms);
+                            }
+                        } else {
+                            for (uint32_t w = 0; w < nhw; ++w)
+                                if (nhu[w])
+                                    atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), nhu[w]);
+                        }
+                        if (__ldcg(&o_fp[v]) == u) o_hops[v] = (uint16_t)min(hu + (fv & kVfHop), 0xFFFFu);
+                        // packed u16 decrement; the thread that takes it to zero owns v
+                        const uint32_t sh = (v & 1) * 16;
+                        const uint32_t oldw = atomicSub(&pend32[v >> 1], 1u << sh);
+                        if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(qnext, &S.cnt[p ^ 1], v);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) S.cnt[p] = 0;
+                { VT *t = qcur; qcur = qnext; qnext = t; }
+                p ^= 1;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+
+        // ======================= write-back ======================================
+        for (uint32_t v = tid; v < V; v += kThreads) o_dist[v] = dist[v];
+        if (tid == 0) a.out_status[job] = S.status;
+    }
+}
+
+}  // namespace hspf

@@ -1,0 +1,85 @@
+"""ctypes access to oracle/_build/liboracle.so (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_u32p = C.POINTER(C.c_uint32)
+_u16p = C.POINTER(C.c_uint16)
+_u64p = C.POINTER(C.c_uint64)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        from holo_b200.build import ORACLE_LIB, build_oracle
+        if not ORACLE_LIB.exists():
+            build_oracle()
+        _lib = C.CDLL(str(ORACLE_LIB))
+    return _lib
+
+
+def _p(a, ty):
+    return C.cast(None, ty) if a is None else a.ctypes.data_as(ty)
+
+
+def csr_spf(csr, root: int, overrides=(), vec_mode: int = 0, nh_words: int = 1, want_lists: bool = False):
+    """Reference-faithful SPF over a flattened CSR.  Returns a dict of planes."""
+    L = lib()
+    V = csr.n_vertices
+    s = csr.as_struct()
+    ove = np.asarray([e for e, _ in overrides] or [0], dtype=np.uint32)
+    ovc = np.asarray([c for _, c in overrides] or [0], dtype=np.uint32)
+    dist = np.empty(V, np.uint32)
+    hops = np.empty(V, np.uint16)
+    fp = np.empty(V, np.uint32)
+    npar = np.empty(V, np.uint16)
+    nh = np.empty((V, nh_words), np.uint64)
+    order = np.empty(V, np.uint32)
+    n_popped = C.c_uint32()
+    status = C.c_uint32()
+    poff = parents = nvoff = nhvec = None
+    pcap = ncap = 0
+    if want_lists:
+        poff = np.empty(V + 1, np.uint32)
+        pcap = max(16, 4 * csr.n_edges)
+        parents = np.empty(pcap, np.uint32)
+        nvoff = np.empty(V + 1, np.uint32)
+        ncap = 1 << 22
+        nhvec = np.empty(ncap, np.uint32)
+    rc = L.oracle_csr_spf(C.byref(s), C.c_uint32(root), C.c_uint32(len(overrides)), _p(ove, _u32p), _p(ovc, _u32p),
+                          C.c_int(vec_mode), _p(dist, _u32p), _p(hops, _u16p), _p(fp, _u32p), _p(npar, _u16p),
+                          _p(nh, _u64p), C.c_uint32(nh_words), _p(poff, _u32p), _p(parents, _u32p), C.c_uint32(pcap),
+                          _p(nvoff, _u32p), _p(nhvec, _u32p), C.c_uint32(ncap), _p(order, _u32p),
+                          C.byref(n_popped), C.byref(status))
+    out = dict(dist=dist, hops=hops, first_parent=fp, n_parents=npar, nh_mask=nh, status=status.value,
+               pop_order=order[: n_popped.value].copy(), rc=rc)
+    if want_lists:
+        out["parents_off"] = poff
+        out["parents"] = parents[: poff[V]].copy()
+        out["nhvec_off"] = nvoff
+        out["nhvec"] = nhvec[: nvoff[V]].copy()
+    return out
+
+
+def csr_spf_heap(csr, root: int, overrides=(), nh_words: int = 1):
+    """Optimised CPU baseline (binary heap), same planes, static-order rules."""
+    L = lib()
+    V = csr.n_vertices
+    s = csr.as_struct()
+    ove = np.asarray([e for e, _ in overrides] or [0], dtype=np.uint32)
+    ovc = np.asarray([c for _, c in overrides] or [0], dtype=np.uint32)
+    dist = np.empty(V, np.uint32)
+    hops = np.empty(V, np.uint16)
+    fp = np.empty(V, np.uint32)
+    npar = np.empty(V, np.uint16)
+    nh = np.empty((V, nh_words), np.uint64)
+    status = C.c_uint32()
+    L.oracle_csr_spf_heap(C.byref(s), C.c_uint32(root), C.c_uint32(len(overrides)), _p(ove, _u32p), _p(ovc, _u32p),
+                          _p(dist, _u32p), _p(hops, _u16p), _p(fp, _u32p), _p(npar, _u16p), _p(nh, _u64p),
+                          C.c_uint32(nh_words), C.byref(status))
+    return dict(dist=dist, hops=hops, first_parent=fp, n_parents=npar, nh_mask=nh, status=status.value)

@@ -1,0 +1,187 @@
+"""GPU parity of the CSR-level engine (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+
+from holo_b200 import synth
+from holo_b200.capi import (COST_DISABLED, Csr, DIST_INF, HSPF_E_JOB_STATUS, HSPF_E_NEEDS_ORACLE,
+                            HspfError, JS_SATURATED, VF_HOP, VF_LEAF, VF_LEAF_UNLESS_ROOT)
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+PLANES = ["dist", "hops", "first_parent", "n_parents", "nh_mask"]
+
+
+def check(res, j, ref, nh_words=1):
+    for k in PLANES:
+        got = getattr(res, k)[j]
+        exp = ref[k]
+        if not np.array_equal(got, exp):
+            bad = np.nonzero((got != exp).reshape(len(exp), -1).any(axis=1))[0]
+            raise AssertionError(f"job {j} plane {k}: {len(bad)} mismatches, first v={bad[0]} "
+                                 f"got={got[bad[0]]} exp={exp[bad[0]]}")
+    assert res.job_status[j] == ref["status"]
+
+
+@pytest.mark.parametrize("V,E,seed,kw", [
+    (2, 2, 1, {}),
+    (5, 12, 2, {}),
+    (100, 400, 3, {}),
+    (100, 400, 4, dict(cost_choices=[10, 20])),
+    (300, 1400, 5, dict(lan_fraction=0.1)),
+    (300, 1400, 6, dict(cost_choices=[10, 20], lan_fraction=0.1)),
+    (2000, 8000, 7, dict(cost_lo=1, cost_hi=1000)),
+])
+@pytest.mark.parametrize("isis", [False, True])
+def test_small_all_roots_vs_faithful(ctx, V, E, seed, kw, isis):
+    t = synth.random_topology(V, E, synth.SEED_BASE + seed, **kw)
+    csr = synth.topology_csr(t, isis=isis)
+    g = ctx.upload(csr)
+    nv = csr.n_vertices
+    roots = np.arange(nv, dtype=np.uint32) if nv <= 300 else np.arange(0, nv, 97, dtype=np.uint32)
+    res = ctx.run(g, roots, nh_words=2)
+    for j, r in enumerate(roots):
+        ref = pyoracle.csr_spf(csr, int(r), vec_mode=int(isis), nh_words=2)
+        check(res, j, ref)
+    g.free()
+
+
+def test_c2_shape_1k_roots_vs_heap_and_sample_faithful(ctx):
+    t = synth.random_topology(10000, 40000, synth.SEED_BASE + 2)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    roots = np.arange(1000, dtype=np.uint32)
+    res = ctx.run(g, roots)
+    assert res.status == 0
+    for j, r in enumerate(roots):
+        check(res, j, pyoracle.csr_spf_heap(csr, int(r)))
+    for j in (0, 499, 999):
+        check(res, j, pyoracle.csr_spf(csr, int(roots[j])))
+    # size-independent properties on every job
+    assert (res.dist[np.arange(1000), roots] == 0).all()
+    row, col, cost = csr.row_ptr, csr.col, csr.cost
+    src = np.repeat(np.arange(csr.n_vertices), np.diff(row))
+    for j in range(0, 1000, 50):
+        d = res.dist[j].astype(np.int64)
+        assert (d[col] <= d[src] + cost).all()          # triangle inequality on every edge
+        fp = res.first_parent[j]
+        ok = fp != 0xFFFFFFFF
+        assert ok.sum() == csr.n_vertices - 1
+    g.free()
+
+
+def test_c5_shape_ecmp_lans(ctx):
+    t = synth.random_topology(10000, 40000, synth.SEED_BASE + 5, cost_choices=[10, 20], lan_fraction=0.05)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    L = len(t.lans)
+    roots = np.concatenate([np.arange(L, L + 64), np.asarray([m[0] + L for m, _ in t.lans[:64]])]).astype(np.uint32)
+    res = ctx.run(g, roots, nh_words=2)
+    for j, r in enumerate(roots):
+        check(res, j, pyoracle.csr_spf_heap(csr, int(r), nh_words=2))
+    for j in (0, 64, 100):
+        check(res, j, pyoracle.csr_spf(csr, int(roots[j]), nh_words=2))
+    g.free()
+
+
+def test_perturbations_isis_shape(ctx):
+    t = synth.random_topology(3000, 12000, synth.SEED_BASE + 3, cost_lo=1, cost_hi=1000)
+    csr = synth.topology_csr(t, isis=True, reject_above=0xFE000000)
+    g = ctx.upload(csr)
+    # adjacency k = forward edges (a->b, b->a): find CSR edge indices
+    row, col = csr.row_ptr, csr.col
+    L = len(t.lans)
+
+    def edge_index(u, v, nth):
+        idx = [e for e in range(row[u], row[u + 1]) if col[e] == v]
+        return idx[nth]
+
+    n_jobs = 200
+    overrides, seen = [], {}
+    for k in range(n_jobs):
+        a, b = int(t.p2p_a[k]) + L, int(t.p2p_b[k]) + L
+        # parallel adjacencies share endpoints: the n-th adjacency between {a, b}
+        # owns the n-th a->b and the n-th b->a CSR edge (edges keep adjacency order)
+        key = (min(a, b), max(a, b))
+        nth = seen.get(key, 0)
+        seen[key] = nth + 1
+        e1, e2 = edge_index(a, b, nth), edge_index(b, a, nth)
+        overrides.append([(e1, COST_DISABLED), (e2, COST_DISABLED)] if k % 3 else [(e1, 7), (e2, 9)])
+    roots = np.full(n_jobs, L, dtype=np.uint32)
+    res = ctx.run(g, roots, overrides=overrides)
+    for j in range(n_jobs):
+        check(res, j, pyoracle.csr_spf(csr, int(roots[j]), overrides=overrides[j], vec_mode=1))
+    g.free()
+
+
+def test_leaf_flags_and_reject(ctx):
+    t = synth.random_topology(400, 1800, synth.SEED_BASE + 9, cost_lo=1, cost_hi=63, lan_fraction=0.05)
+    csr = synth.topology_csr(t, isis=True, reject_above=300)
+    L = len(t.lans)
+    csr.vflags[L + 5] |= VF_LEAF
+    csr.vflags[L + 9] |= VF_LEAF_UNLESS_ROOT
+    csr.vflags[L + 17] |= VF_LEAF_UNLESS_ROOT
+    csr.vflags[L + 30] |= VF_LEAF
+    g = ctx.upload(csr)
+    roots = np.asarray([L, L + 5, L + 9, L + 17, L + 100], dtype=np.uint32)
+    res = ctx.run(g, roots)
+    for j, r in enumerate(roots):
+        ref = pyoracle.csr_spf(csr, int(r), vec_mode=1)
+        check(res, j, ref)
+    assert (res.dist[0] == DIST_INF).any()     # reject_above=300 leaves some vertices unreached
+    g.free()
+
+
+def test_disconnected_and_tiny(ctx):
+    # two components + an isolated vertex
+    row = np.asarray([0, 1, 2, 3, 4, 4], dtype=np.uint32)
+    col = np.asarray([1, 0, 3, 2], dtype=np.uint32)
+    cost = np.asarray([5, 6, 7, 8], dtype=np.uint32)
+    csr = Csr(row, col, cost, np.full(5, VF_HOP, np.uint8), saturate_at=0xFFFF)
+    g = ctx.upload(csr)
+    res = ctx.run(g, np.arange(5, dtype=np.uint32))
+    for j in range(5):
+        check(res, j, pyoracle.csr_spf(csr, j))
+    g.free()
+
+
+def test_zero_cost_router_link_is_refused(ctx):
+    row = np.asarray([0, 1, 2], dtype=np.uint32)
+    csr = Csr(row, np.asarray([1, 0], np.uint32), np.asarray([0, 3], np.uint32), np.full(2, VF_HOP, np.uint8))
+    with pytest.raises(HspfError) as ei:
+        ctx.upload(csr)
+    assert ei.value.code == HSPF_E_NEEDS_ORACLE
+
+
+def test_saturation_is_flagged(ctx):
+    # a chain whose far end exceeds 65535 in OSPF u16 arithmetic
+    n = 6
+    src = np.arange(n - 1)
+    row = np.zeros(n + 1, np.uint32)
+    col, cost = [], []
+    for v in range(n):
+        if v > 0:
+            col.append(v - 1); cost.append(20000)
+        if v < n - 1:
+            col.append(v + 1); cost.append(20000)
+        row[v + 1] = len(col)
+    csr = Csr(row, np.asarray(col, np.uint32), np.asarray(cost, np.uint32), np.full(n, VF_HOP, np.uint8),
+              saturate_at=0xFFFF)
+    g = ctx.upload(csr)
+    res = ctx.run(g, np.asarray([0], np.uint32))
+    assert res.status == HSPF_E_JOB_STATUS
+    assert res.job_status[0] & JS_SATURATED
+    ref = pyoracle.csr_spf(csr, 0)
+    assert ref["status"] & JS_SATURATED
+    g.free()
+
+
+def test_large_vertex_count_uses_global_state(ctx):
+    t = synth.random_topology(70000, 280000, synth.SEED_BASE + 4, cost_lo=1, cost_hi=100)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    roots = np.asarray([0, 12345, 69999], dtype=np.uint32)
+    res = ctx.run(g, roots)
+    for j, r in enumerate(roots):
+        check(res, j, pyoracle.csr_spf_heap(csr, int(r)))
+    g.free()
