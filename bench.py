@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — SPF recomputations/sec on the BASELINE.json C2 workload.
+
+A "step" is one pass of the hot path over one batch: 1000 SPF roots over the
+synthetic OSPFv2 10k-router / 40k-directed-link LSDB (seed 0x484F4C4F+2) on each
+GPU (weak scaling: every rank runs its own 1000 roots; at N>1 the per-rank result
+planes are all-gathered over NCCL/NVLink, the path's one exchange step,
+SURVEY.md §8e).
+
+  value      whole-job SPF/s with the graph, the root list and the result planes
+             resident in HBM (device-pointer C-ABI call), CUDA-event timed.
+  e2e        same metric through the host-pointer C-ABI call: H2D of the job list
+             from pinned memory, kernel, D2H of every result plane into pinned
+             host buffers, inside the timed region.
+  roofline   algorithmic bytes (12E+20V per SPF) / kernel time vs
+             the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline  the reference-faithful oracle (oracle/, "port") on the host cores,
+             bounded sample.
+
+`--impl reference` times the CPU oracle instead (all host threads), same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+V_ROUTERS = 10000
+E_DIRECTED = 40000
+JOBS_PER_GPU = 1000
+CONFIG_INDEX = 2
+METRIC = "SPF recomputations/sec (10k-node LSDB)"
+UNIT = "SPF/s"
+NH_WORDS = 1
+BYTES_PER_VERTEX_OUT = 4 + 2 + 4 + 2 + 8 * NH_WORDS   # dist, hops, first_parent, n_parents, nh_mask
+
+
+def workload():
+    from holo_b200 import synth
+    t = synth.random_topology(V_ROUTERS, E_DIRECTED, synth.SEED_BASE + CONFIG_INDEX)
+    csr = synth.topology_csr(t)
+    return t, csr
+
+
+def algorithmic_bytes(csr) -> int:
+    return 12 * csr.n_edges + 20 * csr.n_vertices
+
+
+def config_dict(n_gpus: int, csr, extra=None):
+    c = {
+        "workload": "C2: OSPFv2 single-area synthetic LSDB, 10000 routers / 40000 directed p2p links, "
+                    "cost U[1,100], 1000 SPF roots per GPU per step",
+        "V": int(csr.n_vertices), "E": int(csr.n_edges), "jobs_per_gpu": JOBS_PER_GPU,
+        "global_jobs_per_step": JOBS_PER_GPU * n_gpus,
+        "seed": hex(0x484F4C4F + CONFIG_INDEX),
+        "parallelism": f"roots sharded over {n_gpus} GPU(s), graph replicated",
+        "result_planes": "dist:u32 hops:u16 first_parent:u32 n_parents:u16 nh_mask:u64",
+        "l2": "flushed between timed steps (256 MiB memset, untimed); result planes are 200 MB/step/GPU > L2",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_oracle_rate(csr, roots, threads: int):
+    """Reference-faithful oracle (linear candidate scan + per-edge mutual check) on
+    `threads` host threads, one job per thread at a time.  Returns (SPF/s, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    pyoracle.lib()
+
+    def one(r):
+        pyoracle.csr_spf(csr, int(r))
+        return 1
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        n = sum(ex.map(one, roots))
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated in oracle/, the Rust
+    reference cannot be built in this image) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from holo_b200.build import build_oracle
+    build_oracle()
+    _, csr = workload()
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(csr, np.arange(min(cores, 8)), cores)
+    t_total = 0.0
+    for s in range(args.steps):
+        roots = (np.arange(per_step) + s * per_step) % V_ROUTERS
+        rate, dt = cpu_oracle_rate(csr, roots, cores)
+        rates.append(rate)
+        t_total += dt
+    value = per_step * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(args.gpus, csr, {"reference_sample": f"{per_step} roots per step"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step * args.steps} SPF roots of the C2 LSDB, one job per host thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from holo_b200.build import build_all
+    from holo_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if rank == 0:
+        build_all()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    t, csr = workload()
+    V, E = csr.n_vertices, csr.n_edges
+    ctx = capi.Context(local_rank)
+    g = ctx.upload(csr)
+    n = JOBS_PER_GPU
+    roots_np = ((np.arange(n) + rank * n) % V_ROUTERS + len(t.lans)).astype(np.uint32)
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---- device-resident planes (value path) ----------------------------------------
+    d_roots = torch.from_numpy(roots_np.astype(np.int32)).to(dev)
+    planes = {
+        "dist": torch.empty((n, V), dtype=torch.int32, device=dev),
+        "hops": torch.empty((n, V), dtype=torch.int16, device=dev),
+        "fp": torch.empty((n, V), dtype=torch.int32, device=dev),
+        "npar": torch.empty((n, V), dtype=torch.int16, device=dev),
+        "nh": torch.empty((n, V, NH_WORDS), dtype=torch.int64, device=dev),
+        "status": torch.zeros((n,), dtype=torch.int32, device=dev),
+    }
+    gathered = None
+    if world > 1:
+        gathered = {k: torch.empty((world,) + tuple(v.shape), dtype=v.dtype, device=dev) for k, v in planes.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    js = capi.JobsStruct()
+    js.n_jobs = n
+    js.roots = C.cast(d_roots.data_ptr(), C.POINTER(C.c_uint32))
+    rs = capi.ResultStruct()
+    rs.dist = C.cast(planes["dist"].data_ptr(), C.POINTER(C.c_uint32))
+    rs.hops = C.cast(planes["hops"].data_ptr(), C.POINTER(C.c_uint16))
+    rs.first_parent = C.cast(planes["fp"].data_ptr(), C.POINTER(C.c_uint32))
+    rs.n_parents = C.cast(planes["npar"].data_ptr(), C.POINTER(C.c_uint16))
+    rs.nh_mask = C.cast(planes["nh"].data_ptr(), C.POINTER(C.c_uint64))
+    rs.nh_words = NH_WORDS
+    rs.job_status = C.cast(planes["status"].data_ptr(), C.POINTER(C.c_uint32))
+
+    def step_device():
+        """kernel (+ all-gather of the result planes at N>1) on the ctx stream"""
+        ctx.run_device(g, js, rs, sync=False)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                for k in planes:
+                    dist.all_gather_into_tensor(gathered[k].view(-1), planes[k].view(-1))
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    for _ in range(args.warmup):
+        flush_l2()
+        step_device()
+    barrier()
+    assert int(planes["status"].abs().sum().item()) == 0, "job_status != 0"
+
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush_l2()
+        e0, ek, e1 = ev[s]
+        e0.record(stream)
+        ctx.run_device(g, js, rs, sync=False)
+        ek.record(stream)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                for k in planes:
+                    dist.all_gather_into_tensor(gathered[k].view(-1), planes[k].view(-1))
+        e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    step_ms = [e0.elapsed_time(e1) for e0, _, e1 in ev]
+    kern_ms = [e0.elapsed_time(ek) for e0, ek, _ in ev]
+    total_ms = float(sum(step_ms))
+    kernel_ms_avg = float(sum(kern_ms) / len(kern_ms))
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers --------------------------------
+    h = {
+        "dist": torch.empty((n, V), dtype=torch.int32).pin_memory(),
+        "hops": torch.empty((n, V), dtype=torch.int16).pin_memory(),
+        "fp": torch.empty((n, V), dtype=torch.int32).pin_memory(),
+        "npar": torch.empty((n, V), dtype=torch.int16).pin_memory(),
+        "nh": torch.empty((n, V, NH_WORDS), dtype=torch.int64).pin_memory(),
+        "status": torch.zeros((n,), dtype=torch.int32).pin_memory(),
+    }
+    h_roots = torch.from_numpy(roots_np.astype(np.int32)).pin_memory()
+    hjs = capi.JobsStruct()
+    hjs.n_jobs = n
+    hjs.roots = C.cast(h_roots.data_ptr(), C.POINTER(C.c_uint32))
+    hrs = capi.ResultStruct()
+    hrs.dist = C.cast(h["dist"].data_ptr(), C.POINTER(C.c_uint32))
+    hrs.hops = C.cast(h["hops"].data_ptr(), C.POINTER(C.c_uint16))
+    hrs.first_parent = C.cast(h["fp"].data_ptr(), C.POINTER(C.c_uint32))
+    hrs.n_parents = C.cast(h["npar"].data_ptr(), C.POINTER(C.c_uint16))
+    hrs.nh_mask = C.cast(h["nh"].data_ptr(), C.POINTER(C.c_uint64))
+    hrs.nh_words = NH_WORDS
+    hrs.job_status = C.cast(h["status"].data_ptr(), C.POINTER(C.c_uint32))
+
+    def step_e2e():
+        rc = ctx.lib.hspf_run_batch(ctx.handle, g.handle, C.byref(hjs), C.byref(hrs), 0)
+        if rc != 0:
+            raise RuntimeError(f"hspf_run_batch rc={rc}: {ctx.last_error()}")
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()       # blocking: returns when results are in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # the D2H'd planes must equal the device-resident ones
+    assert torch.equal(h["dist"], planes["dist"].cpu()) and torch.equal(h["nh"], planes["nh"].cpu())
+
+    # ---- max over ranks ----------------------------------------------------------------------
+    tm = torch.tensor([total_ms, kernel_ms_avg, e2e_s, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms_avg, e2e_s, wall = [float(x) for x in tm.tolist()]
+
+    if rank == 0:
+        jobs_total = n * world * args.steps
+        value = jobs_total / (total_ms * 1e-3)
+        e2e_value = n * world * e2e_steps / e2e_s
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        alg = algorithmic_bytes(csr) * n
+        achieved = alg / (kernel_ms_avg * 1e-3) / 1e9
+        traffic = None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            try:
+                traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        # CPU baseline: bounded sample of the same workload on the host cores
+        cores = os.cpu_count() or 1
+        sample = max(cores, 8) * 4
+        if args.no_cpu_baseline:
+            cpu = None
+        else:
+            rate, dt = cpu_oracle_rate(csr, roots_np[:sample], cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{sample} of the {n} roots of this step, reference-faithful oracle "
+                             f"(linear candidate scan + per-edge mutual check), {dt:.1f} s"}
+        h2d = int(h_roots.numel() * 4)
+        d2h = int(n * V * BYTES_PER_VERTEX_OUT + n * 4)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": config_dict(world, csr),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "spf_batch_kernel",
+                         "kernel_ms": kernel_ms_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+        }
+        print(json.dumps(line))
+    g.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

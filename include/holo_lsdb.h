@@ -1,0 +1,225 @@
+/*
+ * holo_lsdb.h — flat, plain-C images of the link-state databases the SPF path
+ * reads, and of the tables it writes.  These are the argument types of the
+ * LSDB-level entry points (hspf_ospfv2_run_area, hspf_isis_compute_spt, ...):
+ * what the reference's run_area()/compute_spt() take from `Area.state.lsdb` /
+ * `Lsdb` plus the local interface/neighbour state, restated as arrays so they
+ * can cross a C ABI.  The CPU oracle (oracle/*.cc, test infrastructure) consumes
+ * the same images, so parity tests feed both sides identical bytes.
+ *
+ * All addresses / router ids are IPv4 values in host byte order (u32), so
+ * numeric order == Ipv4Addr Ord.  Arrays that model a BTreeMap/BTreeSet are
+ * documented with the order the producer must supply.
+ */
+#ifndef HOLO_LSDB_H
+#define HOLO_LSDB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HL_LSA_MAX_AGE 3600u   /* holo-ospf/src/packet/lsa.rs:145-147 is_maxage */
+
+/* ------------------------------------------------------------------ OSPFv2 -- */
+
+/* Router-LSA link types (holo-ospf/src/ospfv2/packet/lsa.rs LsaRouterLinkType) */
+#define HL_LINK_P2P     1u
+#define HL_LINK_TRANSIT 2u
+#define HL_LINK_STUB    3u
+#define HL_LINK_VLINK   4u
+
+/* Router-LSA flags (LsaRouterFlags): B=0x01 E=0x02 V=0x04 */
+#define HL_RTR_FLAG_B 0x01u
+#define HL_RTR_FLAG_E 0x02u
+#define HL_RTR_FLAG_V 0x04u
+
+typedef struct hl_ospfv2_link {
+    uint32_t link_id;
+    uint32_t link_data;
+    uint16_t metric;
+    uint8_t  link_type;
+    uint8_t  _pad;
+} hl_ospfv2_link;
+
+/* Router-LSAs, in LsaKey order (adv_rtr, lsa_id) (packet/lsa.rs:44-56). */
+typedef struct hl_ospfv2_router_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint16_t age;
+    uint8_t  flags;
+    uint8_t  options;
+    uint32_t link_off;     /* into links[] */
+    uint32_t n_links;
+} hl_ospfv2_router_lsa;
+
+/* Network-LSAs, in LsaKey order (adv_rtr, lsa_id); attached routers ascending
+ * (BTreeSet, ospfv2/spf.rs:398-418). */
+typedef struct hl_ospfv2_network_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t mask;
+    uint16_t age;
+    uint16_t _pad;
+    uint32_t att_off;      /* into attached[] */
+    uint32_t n_att;
+} hl_ospfv2_network_lsa;
+
+/* Interface types (holo-ospf/src/interface.rs InterfaceType + loopback). */
+#define HL_IF_P2P       0u
+#define HL_IF_BROADCAST 1u
+#define HL_IF_NBMA      2u
+#define HL_IF_P2MP      3u
+#define HL_IF_VLINK     4u
+#define HL_IF_LOOPBACK  5u
+
+/* The area's interfaces in NAME order (collections.rs:592: `indexes()` walks
+ * name_tree), i.e. the order `nth(link_pos)` counts in (ospfv2/spf.rs:195-201). */
+typedef struct hl_ospf_iface {
+    uint32_t ifindex;      /* reported in next hops */
+    uint32_t sort_key;     /* generational-arena Index order == NexthopKey order
+                              (route.rs:92-98); unique per interface            */
+    uint8_t  if_type;
+    uint8_t  _pad[3];
+    uint32_t addr_off;     /* into iface_addrs[]: iface.system.addr_list        */
+    uint32_t n_addrs;
+    uint32_t nbr_off;      /* into nbrs[]: neighbours of this interface         */
+    uint32_t n_nbrs;
+} hl_ospf_iface;
+
+typedef struct hl_ipv4_net { uint32_t addr; uint32_t mask; } hl_ipv4_net;
+typedef struct hl_ospf_nbr { uint32_t router_id; uint32_t src; } hl_ospf_nbr;
+
+/* SR: Router-Information Opaque LSAs in LsaKey order (adv_rtr, lsa_id); the
+ * per-router aggregate follows ospfv2/spf.rs:617-654. */
+typedef struct hl_srgb { uint32_t first; uint32_t range; uint8_t first_is_index; uint8_t _pad[3]; } hl_srgb;
+typedef struct hl_ospfv2_ri_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint16_t age;
+    uint8_t  has_sr_algo;
+    uint8_t  sr_algo_has_spf;
+    uint32_t srgb_off;     /* into srgbs[] */
+    uint32_t n_srgb;
+} hl_ospfv2_ri_lsa;
+
+/* Prefix-SID flags (holo-ospf/src/packet/tlv.rs PrefixSidFlags) */
+#define HL_PSID_NP 0x40u
+#define HL_PSID_M  0x20u
+#define HL_PSID_E  0x10u
+#define HL_PSID_V  0x08u
+#define HL_PSID_L  0x04u
+
+/* Extended-Prefix TLVs of area-scope Extended Prefix Opaque LSAs, flattened in
+ * LSDB iteration order (LsaKey order, then TLV order inside the LSA); the first
+ * entry per (adv_rtr, prefix) wins (ospfv2/spf.rs:656-689). */
+typedef struct hl_ospfv2_ext_prefix {
+    uint32_t adv_rtr;
+    uint32_t prefix;       /* masked */
+    uint32_t mask;
+    uint16_t age;
+    uint8_t  route_type;   /* ExtPrefixRouteType: 0 unspecified, 1 intra, 3 inter ... */
+    uint8_t  has_sid;      /* carries a Prefix-SID for algo SPF */
+    uint8_t  sid_flags;
+    uint8_t  sid_is_label; /* Sid::Label vs Sid::Index */
+    uint8_t  _pad[2];
+    uint32_t sid_value;
+} hl_ospfv2_ext_prefix;
+
+typedef struct hl_ospfv2_area {
+    uint32_t router_id;    /* instance.state.router_id: the SPF root             */
+    uint32_t area_id;
+    uint16_t max_paths;    /* instance.config.max_paths (default 16)             */
+    uint8_t  sr_enabled;
+    uint8_t  _pad;
+    uint32_t n_router_lsas;  const hl_ospfv2_router_lsa *router_lsas;
+    uint32_t n_links;        const hl_ospfv2_link *links;
+    uint32_t n_network_lsas; const hl_ospfv2_network_lsa *network_lsas;
+    uint32_t n_attached;     const uint32_t *attached;
+    uint32_t n_ifaces;       const hl_ospf_iface *ifaces;
+    uint32_t n_iface_addrs;  const hl_ipv4_net *iface_addrs;
+    uint32_t n_nbrs;         const hl_ospf_nbr *nbrs;
+    uint32_t n_ri_lsas;      const hl_ospfv2_ri_lsa *ri_lsas;
+    uint32_t n_srgbs;        const hl_srgb *srgbs;
+    uint32_t n_ext_prefixes; const hl_ospfv2_ext_prefix *ext_prefixes;
+} hl_ospfv2_area;
+
+/* ---- outputs ----------------------------------------------------------------- */
+
+/* Nexthop (route.rs:100-115); `iface` indexes hl_ospfv2_area.ifaces.  Sets of
+ * next hops are emitted in NexthopKey order (iface sort_key, then addr with
+ * None first). */
+typedef struct hl_nexthop {
+    uint32_t iface;
+    uint32_t addr;
+    uint32_t nbr_router_id;
+    uint32_t sr_label;
+    uint8_t  has_addr;
+    uint8_t  has_nbr;
+    uint8_t  has_label;
+    uint8_t  _pad;
+} hl_nexthop;
+
+/* SPT vertex (spf.rs:38-46), emitted in VertexId order (Network < Router). */
+typedef struct hl_spt_vertex {
+    uint32_t id;           /* dr_addr (network) or router_id (router)            */
+    uint32_t distance;
+    uint16_t hops;
+    uint8_t  is_router;
+    uint8_t  _pad;
+    uint32_t nh_off;       /* into nexthops[]                                    */
+    uint32_t n_nh;
+} hl_spt_vertex;
+
+/* Area router table entry (RouteRtr, route.rs:57-66), in router-id order. */
+typedef struct hl_route_rtr {
+    uint32_t router_id;
+    uint32_t metric;
+    uint8_t  flags;
+    uint8_t  options;
+    uint8_t  _pad[2];
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_route_rtr;
+
+#define HL_ROUTE_CONNECTED 0x01u   /* RouteNetFlags::CONNECTED */
+
+/* Intra-area network route (RouteNet, route.rs:32-46), in prefix order
+ * (Ipv4Network Ord: address, then prefix length). */
+typedef struct hl_route_net {
+    uint32_t prefix;
+    uint32_t mask;
+    uint32_t metric;
+    uint8_t  flags;
+    uint8_t  origin_type;  /* LSA type code of the LS origin: 1 router, 2 network */
+    uint8_t  has_prefix_sid;
+    uint8_t  has_sr_label;
+    uint32_t origin_adv_rtr;
+    uint32_t origin_lsa_id;
+    uint32_t prefix_sid_value;
+    uint8_t  prefix_sid_flags;
+    uint8_t  prefix_sid_is_label;
+    uint8_t  _pad[2];
+    uint32_t sr_label;     /* input label */
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_route_net;
+
+/* Caller-allocated result of one run_area + update_rib_intra_area.  *_cap are
+ * capacities on input; n_* are the produced counts.  If a capacity is too small
+ * the call returns HSPF_E_NOMEM with the required counts filled in. */
+typedef struct hl_ospfv2_result {
+    uint32_t vertices_cap, n_vertices;   hl_spt_vertex *vertices;
+    uint32_t routers_cap,  n_routers;    hl_route_rtr  *routers;
+    uint32_t routes_cap,   n_routes;     hl_route_net  *routes;
+    uint32_t nexthops_cap, n_nexthops;   hl_nexthop    *nexthops;
+    uint8_t  transit_capability;         /* area.state.transit_capability        */
+    uint8_t  root_found;                 /* 0: SpfRootNotFound (spf.rs:605-610)  */
+    uint8_t  _pad[2];
+} hl_ospfv2_result;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLO_LSDB_H */

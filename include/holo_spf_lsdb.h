@@ -1,0 +1,63 @@
+/*
+ * holo_spf_lsdb.h — LSDB-level entry points of libholo_spf.so: the calls that
+ * replace whole reference functions rather than just their inner loop.
+ *
+ *   hspf_ospfv2_run_area   <->  run_area<Ospfv2>() + update_rib_intra_area()
+ *                               holo-ospf/src/spf.rs:587-729, route.rs:343-446,
+ *                               sr.rs:29-77 (as called from compute_spf,
+ *                               spf.rs:540-545)
+ *   hspf_ospfv2_flatten    <->  the LSDB walk of vertex_lsa_find/vertex_lsa_links
+ *                               (ospfv2/spf.rs:356-461) done once, for callers
+ *                               that batch many roots / what-if jobs through
+ *                               hspf_run_batch (holo_spf.h)
+ *
+ * The SPT itself (distance, hops, ECMP first-hop sets of every vertex) is always
+ * computed by the CUDA kernels; the host code here only flattens the LSDB and maps
+ * first-hop atoms back to interface/address next hops, routes and labels.
+ */
+#ifndef HOLO_SPF_LSDB_H
+#define HOLO_SPF_LSDB_H
+
+#include "holo_lsdb.h"
+#include "holo_spf.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Flattened OSPFv2 area: CSR + the tables needed to map results back. */
+typedef struct hspf_ospfv2_flat hspf_ospfv2_flat;
+
+/* Flatten `area` (host only, no device work).  The image is borrowed for the
+ * lifetime of the returned object. */
+int hspf_ospfv2_flatten(const hl_ospfv2_area *area, hspf_ospfv2_flat **out);
+void hspf_ospfv2_flat_free(hspf_ospfv2_flat *flat);
+/* CSR view (pointers owned by `flat`).  saturate_at = 0xFFFF, reject_above =
+ * 0xFFFFFFFE, flags = 0. */
+int hspf_ospfv2_flat_csr(const hspf_ospfv2_flat *flat, hspf_csr *out);
+/* Vertex table: vertex v is Router (is_router[v]=1) router_id / Network dr_addr
+ * ids[v].  Arrays of n_vertices entries owned by `flat`. */
+int hspf_ospfv2_flat_vertices(const hspf_ospfv2_flat *flat, const uint32_t **ids, const uint8_t **is_router,
+                              uint32_t *n_vertices);
+/* Per CSR edge: index of the Router-LSA link it came from (into area->links) or
+ * 0xFFFFFFFF for Network->Router edges, and the reference's link_pos
+ * (ospfv2/spf.rs:440). */
+int hspf_ospfv2_flat_edge_tags(const hspf_ospfv2_flat *flat, const uint32_t **link_index, const uint32_t **link_pos);
+/* Vertex index of a router id / DR address; 0xFFFFFFFF if it is not a vertex. */
+uint32_t hspf_ospfv2_flat_router_vertex(const hspf_ospfv2_flat *flat, uint32_t router_id);
+uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t dr_addr);
+
+/*
+ * Full SPF of one area for the local router (area->router_id): flatten, run the
+ * SPT on the device, rebuild Vertex.nexthops, the area router table,
+ * transit_capability and the intra-area routes (with SR labels when
+ * area->sr_enabled).  Returns HSPF_OK, HSPF_E_NOMEM (capacities too small, counts
+ * filled in), HSPF_E_NEEDS_ORACLE / HSPF_E_JOB_STATUS (caller must use its CPU
+ * path), or another HSPF_E_*.
+ */
+int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLO_SPF_LSDB_H */

@@ -116,7 +116,7 @@ def test_perturbations_isis_shape(ctx):
 
 def test_leaf_flags_and_reject(ctx):
     t = synth.random_topology(400, 1800, synth.SEED_BASE + 9, cost_lo=1, cost_hi=63, lan_fraction=0.05)
-    csr = synth.topology_csr(t, isis=True, reject_above=300)
+    csr = synth.topology_csr(t, isis=True, reject_above=90)
     L = len(t.lans)
     csr.vflags[L + 5] |= VF_LEAF
     csr.vflags[L + 9] |= VF_LEAF_UNLESS_ROOT
@@ -128,7 +128,7 @@ def test_leaf_flags_and_reject(ctx):
     for j, r in enumerate(roots):
         ref = pyoracle.csr_spf(csr, int(r), vec_mode=1)
         check(res, j, ref)
-    assert (res.dist[0] == DIST_INF).any()     # reject_above=300 leaves some vertices unreached
+    assert (res.dist[0] == DIST_INF).any()     # reject_above=90 leaves some vertices unreached
     g.free()
 
 
