@@ -1,0 +1,607 @@
+// ospfv2_host.cc — OSPFv2 host side of the engine: LSDB image -> CSR, and device
+// results -> Vertex.nexthops / area router table / intra-area routes.
+//
+// What the reference does inside its Dijkstra loop per visited link
+// (vertex_lsa_find + vertex_lsa_links + mutual-link re-iteration,
+// holo-ospf/src/ospfv2/spf.rs:356-461, spf.rs:654-664) is done here ONCE per
+// LSDB with sorted tables, so the device sees a clean CSR; the SPT itself comes
+// from spf_batch_kernel through hspf_run_batch.  After the kernel the first-hop
+// atoms are mapped to interface/address next hops following
+// Ospfv2::calc_nexthops (ospfv2/spf.rs:173-354), then the intra-area route table
+// is assembled per update_rib_intra_area / route_update (route.rs:343-446,
+// 895-942) with SR labels per sr.rs:29-77,127-255.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "holo_spf_lsdb.h"
+
+namespace {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct Nh {   // one next hop; ordering key = (iface sort_key, has_addr, addr)
+    uint32_t sort, iface, addr, nbr, label;
+    uint8_t has_addr, has_nbr, has_label;
+};
+inline bool nh_less(const Nh &a, const Nh &b) {
+    if (a.sort != b.sort) return a.sort < b.sort;
+    if (a.has_addr != b.has_addr) return a.has_addr < b.has_addr;
+    return a.addr < b.addr;
+}
+inline bool nh_same_key(const Nh &a, const Nh &b) { return a.sort == b.sort && a.has_addr == b.has_addr && a.addr == b.addr; }
+
+// sorted-unique insert; an existing key is overwritten (BTreeMap::insert/extend)
+void nh_insert(std::vector<Nh> &set, const Nh &x) {
+    auto it = std::lower_bound(set.begin(), set.end(), x, nh_less);
+    if (it != set.end() && nh_same_key(*it, x)) *it = x; else set.insert(it, x);
+}
+
+}  // namespace
+
+struct hspf_ospfv2_flat {
+    const hl_ospfv2_area *area = nullptr;
+    uint32_t n_net = 0, n_rtr = 0;
+    std::vector<uint32_t> ids;          // [V] dr_addr / router_id
+    std::vector<uint8_t> is_router;     // [V]
+    std::vector<uint32_t> lsa_of;       // [V] index into network_lsas / router_lsas
+    std::vector<uint32_t> row, col, cost, link_index, link_pos;
+    std::vector<uint8_t> vflags;
+    std::unordered_map<uint32_t, uint32_t> net_vertex, rtr_vertex;   // id -> vertex
+};
+
+namespace {
+
+int flatten(const hl_ospfv2_area *a, hspf_ospfv2_flat &f) {
+    f.area = a;
+    // ---- vertices ---------------------------------------------------------------
+    // Router vertex: LSA key (adv_rtr == lsa_id == router_id), not MaxAge.
+    std::vector<std::pair<uint32_t, uint32_t>> rtrs;   // (router_id, lsa index)
+    for (uint32_t i = 0; i < a->n_router_lsas; ++i) {
+        const auto &l = a->router_lsas[i];
+        if (l.adv_rtr == l.lsa_id && l.age != HL_LSA_MAX_AGE) rtrs.emplace_back(l.adv_rtr, i);
+    }
+    std::sort(rtrs.begin(), rtrs.end());
+    rtrs.erase(std::unique(rtrs.begin(), rtrs.end(), [](auto &x, auto &y) { return x.first == y.first; }), rtrs.end());
+    // Network vertex: the FIRST Network-LSA in LsaKey order with that LS-ID; if that
+    // one is MaxAge the vertex does not exist (find() before filter()).
+    std::vector<uint32_t> order(a->n_network_lsas);
+    for (uint32_t i = 0; i < a->n_network_lsas; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        const auto &p = a->network_lsas[x], &q = a->network_lsas[y];
+        return p.adv_rtr != q.adv_rtr ? p.adv_rtr < q.adv_rtr : p.lsa_id < q.lsa_id;
+    });
+    std::unordered_map<uint32_t, uint32_t> first_net;   // lsa_id -> lsa index
+    for (uint32_t i : order) first_net.emplace(a->network_lsas[i].lsa_id, i);
+    std::vector<std::pair<uint32_t, uint32_t>> nets;
+    for (auto &kv : first_net)
+        if (a->network_lsas[kv.second].age != HL_LSA_MAX_AGE) nets.emplace_back(kv.first, kv.second);
+    std::sort(nets.begin(), nets.end());
+
+    f.n_net = (uint32_t)nets.size();
+    f.n_rtr = (uint32_t)rtrs.size();
+    const uint32_t V = f.n_net + f.n_rtr;
+    f.ids.resize(V); f.is_router.resize(V); f.lsa_of.resize(V); f.vflags.resize(V);
+    for (uint32_t i = 0; i < f.n_net; ++i) {
+        f.ids[i] = nets[i].first; f.is_router[i] = 0; f.lsa_of[i] = nets[i].second; f.vflags[i] = 0;
+        f.net_vertex.emplace(nets[i].first, i);
+    }
+    for (uint32_t i = 0; i < f.n_rtr; ++i) {
+        const uint32_t v = f.n_net + i;
+        f.ids[v] = rtrs[i].first; f.is_router[v] = 1; f.lsa_of[v] = rtrs[i].second; f.vflags[v] = HSPF_VF_HOP;
+        f.rtr_vertex.emplace(rtrs[i].first, v);
+    }
+
+    // ---- raw links (before the mutual-link filter) ---------------------------------
+    struct Raw { uint32_t u, v, cost, link, pos; };
+    std::vector<Raw> raw;
+    raw.reserve(a->n_links + a->n_attached);
+    std::vector<uint32_t> att;
+    for (uint32_t v = 0; v < V; ++v) {
+        if (!f.is_router[v]) {
+            const auto &n = a->network_lsas[f.lsa_of[v]];
+            att.assign(a->attached + n.att_off, a->attached + n.att_off + n.n_att);
+            std::sort(att.begin(), att.end());
+            att.erase(std::unique(att.begin(), att.end()), att.end());
+            for (uint32_t rid : att) {
+                auto it = f.rtr_vertex.find(rid);
+                if (it == f.rtr_vertex.end()) continue;
+                raw.push_back({v, it->second, 0, kNone, 0});
+            }
+        } else {
+            const auto &r = a->router_lsas[f.lsa_of[v]];
+            uint32_t pos = 0;
+            for (uint32_t k = 0; k < r.n_links; ++k) {
+                const auto &l = a->links[r.link_off + k];
+                uint32_t tgt = kNone;
+                if (l.link_type == HL_LINK_P2P || l.link_type == HL_LINK_VLINK) {
+                    auto it = f.rtr_vertex.find(l.link_id);
+                    if (it != f.rtr_vertex.end()) tgt = it->second;
+                } else if (l.link_type == HL_LINK_TRANSIT) {
+                    auto it = f.net_vertex.find(l.link_id);
+                    if (it != f.net_vertex.end()) tgt = it->second;
+                } else {
+                    continue;   // stub links are dropped before enumerate()
+                }
+                const uint32_t p = pos++;
+                if (tgt == kNone) continue;
+                raw.push_back({v, tgt, l.metric, r.link_off + k, p});
+            }
+        }
+    }
+    // ---- mutual-link filter: keep u->v iff v has any raw link to u -----------------
+    std::unordered_set<uint64_t> have;
+    have.reserve(raw.size() * 2);
+    for (auto &e : raw) have.insert(((uint64_t)e.u << 32) | e.v);
+    f.row.assign(V + 1, 0);
+    for (auto &e : raw) {
+        if (e.u == e.v) continue;   // a link to oneself is skipped by `spt.contains_key`
+        if (!have.count(((uint64_t)e.v << 32) | e.u)) continue;
+        f.row[e.u + 1]++;
+    }
+    for (uint32_t v = 0; v < V; ++v) f.row[v + 1] += f.row[v];
+    const uint32_t E = f.row[V];
+    f.col.resize(E); f.cost.resize(E); f.link_index.resize(E); f.link_pos.resize(E);
+    std::vector<uint32_t> fill(f.row.begin(), f.row.end() - 1);
+    for (auto &e : raw) {   // raw is already grouped by u in link order
+        if (e.u == e.v) continue;
+        if (!have.count(((uint64_t)e.v << 32) | e.u)) continue;
+        const uint32_t k = fill[e.u]++;
+        f.col[k] = e.v; f.cost[k] = e.cost; f.link_index[k] = e.link; f.link_pos[k] = e.pos;
+    }
+    return HSPF_OK;
+}
+
+void fill_csr(const hspf_ospfv2_flat &f, hspf_csr *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->n_vertices = (uint32_t)f.ids.size();
+    c->n_edges = (uint32_t)f.col.size();
+    c->row_ptr = f.row.data();
+    c->col = f.col.data();
+    c->cost = f.cost.data();
+    c->vflags = f.vflags.data();
+    c->reject_above = 0xFFFFFFFEu;
+    c->saturate_at = 0xFFFFu;
+    c->flags = 0;
+    c->delta = 0;
+}
+
+// ---- first hops (Ospfv2::calc_nexthops) ------------------------------------------------
+struct Resolver {
+    const hspf_ospfv2_flat &f;
+    const hl_ospfv2_area *a;
+    uint32_t root;
+    const uint64_t *nh_mask;   // [V][nhw]
+    uint32_t nhw;
+    std::vector<std::vector<Nh>> atom_nh;   // per atom
+    std::vector<uint8_t> atom_done;
+    std::vector<int> ifaces_with_nbrs;      // nth(link_pos) table
+
+    // parent is the root (ospfv2/spf.rs:188-305)
+    void root_atom(uint32_t e, std::vector<Nh> &out) const {
+        const uint32_t pos = f.link_pos[e];
+        if (pos >= ifaces_with_nbrs.size()) return;                  // Err(SpfNexthopCalcError)
+        const uint32_t ii = (uint32_t)ifaces_with_nbrs[pos];
+        const hl_ospf_iface &iface = a->ifaces[ii];
+        if (iface.if_type == HL_IF_VLINK) return;                    // resolved later (RFC 2328 16.3)
+        const uint32_t dest = f.col[e];
+        if (f.is_router[dest]) {
+            const auto &dl = a->router_lsas[f.lsa_of[dest]];
+            if (iface.if_type == HL_IF_P2P || iface.if_type == HL_IF_VLINK) {
+                for (uint32_t k = 0; k < iface.n_nbrs; ++k) {
+                    const auto &nbr = a->nbrs[iface.nbr_off + k];
+                    if (nbr.router_id != dl.adv_rtr) continue;
+                    out.push_back(Nh{iface.sort_key, ii, nbr.src, dl.adv_rtr, 0, 1, 1, 0});
+                    break;
+                }
+            } else if (iface.if_type == HL_IF_P2MP) {
+                for (uint32_t k = 0; k < dl.n_links; ++k) {
+                    const auto &l = a->links[dl.link_off + k];
+                    bool in = false;
+                    for (uint32_t q = 0; q < iface.n_addrs && !in; ++q) {
+                        const auto &net = a->iface_addrs[iface.addr_off + q];
+                        in = (l.link_data & net.mask) == (net.addr & net.mask);
+                    }
+                    if (in) nh_insert(out, Nh{iface.sort_key, ii, l.link_data, dl.adv_rtr, 0, 1, 1, 0});
+                }
+            }
+        } else {
+            out.push_back(Nh{iface.sort_key, ii, 0, 0, 0, 0, 0, 0});
+        }
+    }
+
+    std::vector<Nh> vertex_nexthops(uint32_t v) {
+        std::vector<Nh> set;
+        for (uint32_t w = 0; w < nhw; ++w) {
+            uint64_t m = nh_mask[(size_t)v * nhw + w];
+            while (m) {
+                const uint32_t atom = w * 64 + (uint32_t)__builtin_ctzll(m);
+                m &= m - 1;
+                for (const Nh &x : resolve(atom)) nh_insert(set, x);
+            }
+        }
+        return set;
+    }
+
+    const std::vector<Nh> &resolve(uint32_t atom) {
+        if (atom_done[atom]) return atom_nh[atom];
+        atom_done[atom] = 1;   // (the DAG has no cycles; set first to be safe)
+        hspf_csr c;
+        fill_csr(f, &c);
+        uint32_t tail = 0, e = 0;
+        std::vector<Nh> out;
+        if (hspf_atom_decode(&c, root, atom, &tail, &e) == HSPF_OK) {
+            if (tail == root) {
+                root_atom(e, out);
+            } else {
+                // parent is a transit network attached to the root (ospfv2/spf.rs:306-350)
+                const auto &pl = a->network_lsas[f.lsa_of[tail]];
+                const uint32_t dest = f.col[e];
+                const auto &dl = a->router_lsas[f.lsa_of[dest]];
+                const hl_ospfv2_link *dest_link = nullptr;
+                for (uint32_t k = 0; k < dl.n_links; ++k) {
+                    const auto &l = a->links[dl.link_off + k];
+                    if ((l.link_data & pl.mask) == (pl.lsa_id & pl.mask)) { dest_link = &l; break; }
+                }
+                if (dest_link) {
+                    std::vector<Nh> pn = vertex_nexthops(tail);     // parent.nexthops, final when it is expanded
+                    if (!pn.empty()) {
+                        const Nh &p0 = pn.front();
+                        out.push_back(Nh{p0.sort, p0.iface, dest_link->link_data, dl.adv_rtr, 0, 1, 1, 0});
+                    }
+                }
+            }
+        }
+        atom_nh[atom] = std::move(out);
+        return atom_nh[atom];
+    }
+};
+
+struct RouterInfo { bool has_sr_algo = false; std::vector<const hl_srgb *> srgb; };
+
+RouterInfo router_info(const hl_ospfv2_area *a, uint32_t rid) {
+    RouterInfo ri;
+    for (uint32_t i = 0; i < a->n_ri_lsas; ++i) {
+        const auto &l = a->ri_lsas[i];
+        if (l.adv_rtr != rid || l.age == HL_LSA_MAX_AGE) continue;
+        if (l.has_sr_algo) ri.has_sr_algo = true;
+        for (uint32_t k = 0; k < l.n_srgb; ++k) ri.srgb.push_back(&a->srgbs[l.srgb_off + k]);
+    }
+    return ri;
+}
+
+bool index_to_label(uint32_t index, const std::vector<const hl_srgb *> &srgbs, uint32_t *label) {
+    for (auto *s : srgbs) {
+        if (s->first_is_index) continue;
+        if (index >= s->range) { index -= s->range; continue; }
+        *label = s->first + index;
+        return true;
+    }
+    return false;
+}
+
+struct Route {
+    uint32_t prefix, plen, metric;
+    uint8_t flags, origin_type;
+    uint32_t origin_adv, origin_id;
+    bool has_sid = false; uint32_t sid_value = 0; uint8_t sid_flags = 0; bool sid_is_label = false;
+    bool has_label = false; uint32_t label = 0;
+    std::vector<Nh> nh;
+};
+
+inline uint64_t pkey(uint32_t prefix, uint32_t plen) { return ((uint64_t)prefix << 8) | plen; }
+
+}  // namespace
+
+extern "C" {
+
+int hspf_ospfv2_flatten(const hl_ospfv2_area *area, hspf_ospfv2_flat **out) {
+    if (!area || !out) return HSPF_E_INVAL;
+    *out = nullptr;
+    try {
+        auto *f = new hspf_ospfv2_flat();
+        int rc = flatten(area, *f);
+        if (rc) { delete f; return rc; }
+        *out = f;
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
+
+void hspf_ospfv2_flat_free(hspf_ospfv2_flat *flat) { delete flat; }
+
+int hspf_ospfv2_flat_csr(const hspf_ospfv2_flat *flat, hspf_csr *out) {
+    if (!flat || !out) return HSPF_E_INVAL;
+    fill_csr(*flat, out);
+    return HSPF_OK;
+}
+
+int hspf_ospfv2_flat_vertices(const hspf_ospfv2_flat *flat, const uint32_t **ids, const uint8_t **is_router,
+                              uint32_t *n_vertices) {
+    if (!flat) return HSPF_E_INVAL;
+    if (ids) *ids = flat->ids.data();
+    if (is_router) *is_router = flat->is_router.data();
+    if (n_vertices) *n_vertices = (uint32_t)flat->ids.size();
+    return HSPF_OK;
+}
+
+int hspf_ospfv2_flat_edge_tags(const hspf_ospfv2_flat *flat, const uint32_t **link_index, const uint32_t **link_pos) {
+    if (!flat) return HSPF_E_INVAL;
+    if (link_index) *link_index = flat->link_index.data();
+    if (link_pos) *link_pos = flat->link_pos.data();
+    return HSPF_OK;
+}
+
+uint32_t hspf_ospfv2_flat_router_vertex(const hspf_ospfv2_flat *flat, uint32_t router_id) {
+    if (!flat) return kNone;
+    auto it = flat->rtr_vertex.find(router_id);
+    return it == flat->rtr_vertex.end() ? kNone : it->second;
+}
+
+uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t dr_addr) {
+    if (!flat) return kNone;
+    auto it = flat->net_vertex.find(dr_addr);
+    return it == flat->net_vertex.end() ? kNone : it->second;
+}
+
+/* sizeof() of every struct that crosses the ABI, for binding self-checks. */
+int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
+    const uint32_t v[] = {
+        (uint32_t)sizeof(hspf_csr), (uint32_t)sizeof(hspf_jobs), (uint32_t)sizeof(hspf_result),
+        (uint32_t)sizeof(hl_ospfv2_link), (uint32_t)sizeof(hl_ospfv2_router_lsa), (uint32_t)sizeof(hl_ospfv2_network_lsa),
+        (uint32_t)sizeof(hl_ospf_iface), (uint32_t)sizeof(hl_ipv4_net), (uint32_t)sizeof(hl_ospf_nbr),
+        (uint32_t)sizeof(hl_srgb), (uint32_t)sizeof(hl_ospfv2_ri_lsa), (uint32_t)sizeof(hl_ospfv2_ext_prefix),
+        (uint32_t)sizeof(hl_ospfv2_area), (uint32_t)sizeof(hl_nexthop), (uint32_t)sizeof(hl_spt_vertex),
+        (uint32_t)sizeof(hl_route_rtr), (uint32_t)sizeof(hl_route_net), (uint32_t)sizeof(hl_ospfv2_result),
+    };
+    const uint32_t n = sizeof(v) / sizeof(v[0]);
+    if (!out || cap < n) return (int)n;
+    for (uint32_t i = 0; i < n; ++i) out[i] = v[i];
+    return (int)n;
+}
+
+int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *a, hl_ospfv2_result *out) {
+    if (!ctx || !a || !out) return HSPF_E_INVAL;
+    try {
+        out->n_vertices = out->n_routers = out->n_routes = out->n_nexthops = 0;
+        out->transit_capability = 0;
+        out->root_found = 0;
+        hspf_ospfv2_flat f;
+        int rc = flatten(a, f);
+        if (rc) return rc;
+        auto rit = f.rtr_vertex.find(a->router_id);
+        if (rit == f.rtr_vertex.end()) return HSPF_OK;   // SpfRootNotFound: logged, nothing computed
+        out->root_found = 1;
+        const uint32_t root = rit->second;
+        const uint32_t V = (uint32_t)f.ids.size();
+
+        // ---- SPT on the device ---------------------------------------------------------
+        hspf_csr csr;
+        fill_csr(f, &csr);
+        uint32_t n_atoms = 0;
+        hspf_atom_count(&csr, root, &n_atoms);
+        const uint32_t nhw = std::max(1u, (n_atoms + 63) / 64);
+        if (nhw > 4) return HSPF_E_UNSUPPORTED;   // > 256 first-hop atoms: caller's CPU path
+        hspf_graph *g = nullptr;
+        rc = hspf_graph_upload(ctx, &csr, &g);
+        if (rc) return rc;
+        std::vector<uint32_t> dist(V);
+        std::vector<uint16_t> hops(V);
+        std::vector<uint64_t> nh((size_t)V * nhw);
+        uint32_t status = 0;
+        hspf_jobs jobs{};
+        jobs.n_jobs = 1;
+        jobs.roots = &root;
+        hspf_result res{};
+        res.dist = dist.data(); res.hops = hops.data(); res.nh_mask = nh.data(); res.nh_words = nhw;
+        res.job_status = &status;
+        rc = hspf_run_batch(ctx, g, &jobs, &res, 0);
+        hspf_graph_free(ctx, g);
+        if (rc) return rc;   // includes HSPF_E_JOB_STATUS (saturation): caller's CPU path
+
+        // ---- Vertex.nexthops --------------------------------------------------------------
+        Resolver rs{f, a, root, nh.data(), nhw, {}, {}, {}};
+        rs.atom_nh.resize((size_t)64 * nhw);
+        rs.atom_done.assign((size_t)64 * nhw, 0);
+        for (uint32_t i = 0; i < a->n_ifaces; ++i)
+            if (a->ifaces[i].n_nbrs > 0) rs.ifaces_with_nbrs.push_back((int)i);
+        std::vector<uint32_t> spt;            // vertices on the SPT, VertexId order
+        for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
+        std::vector<std::vector<Nh>> vnh(V);
+        for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
+
+        // ---- intra-area routes (update_rib_intra_area) ------------------------------------
+        std::unordered_map<uint64_t, const hl_ospfv2_ext_prefix *> extp;   // (adv_rtr, prefix/len) first wins
+        auto ekey = [](uint32_t adv, uint32_t prefix, uint32_t plen) {
+            return ((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen;
+        };
+        if (a->sr_enabled) {
+            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+                const auto &e = a->ext_prefixes[i];
+                if (e.age == HL_LSA_MAX_AGE) continue;
+                extp.emplace(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), &e);
+            }
+        }
+        auto ext_find = [&](uint32_t adv, uint32_t prefix, uint32_t plen) -> const hl_ospfv2_ext_prefix * {
+            auto it = extp.find(ekey(adv, prefix, plen));
+            if (it == extp.end()) return nullptr;
+            const auto *e = it->second;
+            if (e->adv_rtr == adv && e->prefix == prefix && (uint32_t)__builtin_popcount(e->mask) == plen) return e;
+            // hash-key collision: fall back to a scan (first match in LSDB order)
+            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+                const auto &x = a->ext_prefixes[i];
+                if (x.age != HL_LSA_MAX_AGE && x.adv_rtr == adv && x.prefix == prefix &&
+                    (uint32_t)__builtin_popcount(x.mask) == plen) return &x;
+            }
+            return nullptr;
+        };
+        std::unordered_map<uint64_t, uint32_t> rib_idx;
+        std::vector<Route> rib;
+        std::vector<uint8_t> rib_live;
+        RouterInfo local_ri; bool local_ri_loaded = false;
+        std::unordered_map<uint32_t, RouterInfo> ri_cache;
+        auto cached_ri = [&](uint32_t rid) -> const RouterInfo & {
+            auto it = ri_cache.find(rid);
+            if (it == ri_cache.end()) it = ri_cache.emplace(rid, router_info(a, rid)).first;
+            return it->second;
+        };
+
+        auto add_stub = [&](uint32_t v, uint32_t prefix, uint32_t plen, uint32_t stub_metric, uint32_t adv_rtr) {
+            uint32_t m = dist[v] + stub_metric;
+            if (m > 0xFFFF) m = 0xFFFF;
+            const uint64_t key = pkey(prefix, plen);
+            auto it = rib_idx.find(key);
+            Route *cur = (it != rib_idx.end() && rib_live[it->second]) ? &rib[it->second] : nullptr;
+            if (cur && m > cur->metric) return;
+            uint8_t otype; uint32_t oadv, oid;
+            if (f.is_router[v]) { const auto &l = a->router_lsas[f.lsa_of[v]]; otype = 1; oadv = l.adv_rtr; oid = l.lsa_id; }
+            else { const auto &l = a->network_lsas[f.lsa_of[v]]; otype = 2; oadv = l.adv_rtr; oid = l.lsa_id; }
+            if (!f.is_router[v] && cur) {
+                if (m > cur->metric || oid < cur->origin_id) return;
+                rib_live[it->second] = 0;   // o.remove()
+                cur = nullptr;
+            }
+            Route nr;
+            nr.prefix = prefix; nr.plen = plen; nr.metric = m;
+            nr.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
+            nr.origin_type = otype; nr.origin_adv = oadv; nr.origin_id = oid;
+            nr.nh = vnh[v];
+            if (a->sr_enabled) {
+                const hl_ospfv2_ext_prefix *ep = ext_find(adv_rtr, prefix, plen);
+                if (ep && ep->route_type == 1 && ep->has_sid && cached_ri(oadv).has_sr_algo) {
+                    const bool local = hops[v] == 0, last_hop = hops[v] == 1;
+                    nr.has_sid = true; nr.sid_value = ep->sid_value; nr.sid_flags = ep->sid_flags;
+                    nr.sid_is_label = ep->sid_is_label;
+                    if (!(local && (!(ep->sid_flags & HL_PSID_NP) || (ep->sid_flags & HL_PSID_E)))) {
+                        if (!ep->sid_is_label) {
+                            if (!local_ri_loaded) { local_ri = router_info(a, a->router_id); local_ri_loaded = true; }
+                            uint32_t lab;
+                            if (!local_ri.srgb.empty() && index_to_label(ep->sid_value, local_ri.srgb, &lab)) {
+                                nr.has_label = true; nr.label = lab;
+                            }
+                        } else {
+                            nr.has_label = true; nr.label = ep->sid_value;
+                        }
+                    }
+                    for (Nh &x : nr.nh) {
+                        if (!x.has_nbr) continue;
+                        uint32_t lab = 0; bool ok = false, decided = false;
+                        if (last_hop) {
+                            if (!(ep->sid_flags & HL_PSID_NP)) { lab = 3; ok = decided = true; }
+                            else if (ep->sid_flags & HL_PSID_E) { lab = 0; ok = decided = true; }
+                        }
+                        if (!decided) {
+                            if (!ep->sid_is_label) {
+                                const RouterInfo &nri = cached_ri(x.nbr);
+                                if (!nri.srgb.empty()) ok = index_to_label(ep->sid_value, nri.srgb, &lab);
+                            } else {
+                                lab = last_hop ? ep->sid_value : 3u; ok = true;
+                            }
+                        }
+                        if (ok) { x.has_label = 1; x.label = lab; }
+                    }
+                }
+            }
+            // route_update
+            Route *route;
+            if (cur) {
+                if (nr.metric < cur->metric) *cur = nr;
+                else if (nr.metric == cur->metric) for (const Nh &x : nr.nh) nh_insert(cur->nh, x);
+                route = cur;
+            } else {
+                if (it != rib_idx.end()) { rib[it->second] = nr; rib_live[it->second] = 1; route = &rib[it->second]; }
+                else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); rib_live.push_back(1); route = &rib.back(); }
+            }
+            if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
+        };
+        for (uint32_t v : spt) {
+            if (!f.is_router[v]) {
+                const auto &nl = a->network_lsas[f.lsa_of[v]];
+                add_stub(v, nl.lsa_id & nl.mask, (uint32_t)__builtin_popcount(nl.mask), 0, nl.adv_rtr);
+            } else {
+                const auto &rl = a->router_lsas[f.lsa_of[v]];
+                for (uint32_t k = 0; k < rl.n_links; ++k) {
+                    const auto &l = a->links[rl.link_off + k];
+                    if (l.link_type != HL_LINK_STUB) continue;
+                    add_stub(v, l.link_id & l.link_data, (uint32_t)__builtin_popcount(l.link_data), l.metric, rl.adv_rtr);
+                }
+            }
+        }
+
+        // ---- export ---------------------------------------------------------------------------
+        std::vector<uint32_t> live;
+        for (uint32_t i = 0; i < rib.size(); ++i) if (rib_live[i]) live.push_back(i);
+        std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
+            return rib[x].prefix != rib[y].prefix ? rib[x].prefix < rib[y].prefix : rib[x].plen < rib[y].plen;
+        });
+        uint32_t n_rtr_in_spt = 0, need_h = 0;
+        for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr_in_spt; need_h += (uint32_t)vnh[v].size(); } }
+        for (uint32_t i : live) need_h += (uint32_t)rib[i].nh.size();
+        out->n_vertices = (uint32_t)spt.size();
+        out->n_routers = n_rtr_in_spt;
+        out->n_routes = (uint32_t)live.size();
+        out->n_nexthops = need_h;
+        bool tc = false;
+        for (uint32_t v : spt)
+            if (f.is_router[v] && (a->router_lsas[f.lsa_of[v]].flags & HL_RTR_FLAG_V)) tc = true;
+        out->transit_capability = tc;
+        if (out->n_vertices > out->vertices_cap || out->n_routers > out->routers_cap ||
+            out->n_routes > out->routes_cap || out->n_nexthops > out->nexthops_cap)
+            return HSPF_E_NOMEM;
+        uint32_t h = 0;
+        auto put = [&](const std::vector<Nh> &s) {
+            for (const Nh &x : s) {
+                hl_nexthop o{};
+                o.iface = x.iface; o.addr = x.has_addr ? x.addr : 0; o.nbr_router_id = x.has_nbr ? x.nbr : 0;
+                o.sr_label = x.has_label ? x.label : 0;
+                o.has_addr = x.has_addr; o.has_nbr = x.has_nbr; o.has_label = x.has_label;
+                out->nexthops[h++] = o;
+            }
+        };
+        uint32_t i = 0;
+        for (uint32_t v : spt) {
+            hl_spt_vertex o{};
+            o.id = f.ids[v]; o.distance = dist[v]; o.hops = hops[v]; o.is_router = f.is_router[v];
+            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+            put(vnh[v]);
+            out->vertices[i++] = o;
+        }
+        i = 0;
+        for (uint32_t v : spt) {   // router vertices are already in router-id order
+            if (!f.is_router[v]) continue;
+            const auto &rl = a->router_lsas[f.lsa_of[v]];
+            hl_route_rtr o{};
+            o.router_id = rl.adv_rtr; o.metric = dist[v]; o.flags = rl.flags; o.options = rl.options;
+            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+            put(vnh[v]);
+            out->routers[i++] = o;
+        }
+        i = 0;
+        for (uint32_t k : live) {
+            const Route &r = rib[k];
+            hl_route_net o{};
+            o.prefix = r.prefix; o.mask = r.plen == 0 ? 0 : 0xFFFFFFFFu << (32 - r.plen);
+            o.metric = r.metric; o.flags = r.flags; o.origin_type = r.origin_type;
+            o.origin_adv_rtr = r.origin_adv; o.origin_lsa_id = r.origin_id;
+            o.has_prefix_sid = r.has_sid; o.prefix_sid_value = r.sid_value; o.prefix_sid_flags = r.sid_flags;
+            o.prefix_sid_is_label = r.sid_is_label;
+            o.has_sr_label = r.has_label; o.sr_label = r.has_label ? r.label : 0;
+            o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
+            put(r.nh);
+            out->routes[i++] = o;
+        }
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
+
+}  // extern "C"

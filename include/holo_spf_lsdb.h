@@ -57,6 +57,11 @@ uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t 
  */
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
 
+/* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
+ * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
+ * foreign binding verify its struct layouts at load time. */
+int hspf_abi_sizes(uint32_t *out, uint32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

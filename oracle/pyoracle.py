@@ -83,3 +83,11 @@ def csr_spf_heap(csr, root: int, overrides=(), nh_words: int = 1):
                           _p(dist, _u32p), _p(hops, _u16p), _p(fp, _u32p), _p(npar, _u16p), _p(nh, _u64p),
                           C.c_uint32(nh_words), C.byref(status))
     return dict(dist=dist, hops=hops, first_parent=fp, n_parents=npar, nh_mask=nh, status=status.value)
+
+
+def ospfv2_run_area(area):
+    """Reference-faithful run_area + update_rib_intra_area over an LSDB image."""
+    from holo_b200 import ospfv2
+    L = lib()
+    L.oracle_ospfv2_run_area.argtypes = [C.POINTER(ospfv2.AreaStruct), C.POINTER(ospfv2.ResultStruct)]
+    return ospfv2._call_run_area(L.oracle_ospfv2_run_area, area)

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Extract golden vectors for the SPF path from the reference's own conformance
+fixtures (run in the build container; /root/reference does not exist on the GPU
+box).  Source (read only):
+
+  holo-ospf/tests/conformance/ospfv2/topologies/<topo>/<rt>/output/northbound-state.json
+  holo-ospf/tests/conformance/ospfv2/topologies/<topo>/<rt>/events.jsonl (ifindex map)
+  holo-isis/tests/conformance/topologies/<topo>/<rt>/{config.json,output/northbound-state.json}
+
+Each snapshot holds BOTH the instance's converged LSDB (every Router/Network LSA,
+or LSP, with links and metrics), the local interface/neighbour state, and the
+`local-rib` the reference computed from it; so (LSDB, local state) -> local-rib is
+a known-answer test of run_area/compute_spt + the intra-area route stage
+(SURVEY.md §8c, Appendix A).  Output: tests/golden/ospfv2.json, tests/golden/isis.json.
+
+Usage: python tests/golden/make_golden.py [/root/reference]
+"""
+from __future__ import annotations
+
+import json
+import re
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+
+LINK_TYPES = {"point-to-point-link": 1, "transit-network-link": 2, "stub-network-link": 3, "virtual-link": 4}
+RTR_BITS = {"abr-bit": 0x01, "asbr-bit": 0x02, "vlink-end-bit": 0x04}
+
+
+def ospf_root(d):
+    return d["ietf-routing:routing"]["control-plane-protocols"]["control-plane-protocol"][0]["ietf-ospf:ospf"]
+
+
+def ifindex_map(events_path: Path):
+    m = {}
+    if not events_path.exists():
+        return m
+    for line in events_path.read_text().splitlines():
+        for mm in re.finditer(r'"InterfaceUpd":\{"ifname":"([^"]+)","ifindex":(\d+)', line):
+            m[mm.group(1)] = int(mm.group(2))
+    return m
+
+
+def extract_ospfv2(ref: Path):
+    base = ref / "holo-ospf/tests/conformance/ospfv2/topologies"
+    out = []
+    for topo in sorted(p for p in base.iterdir() if p.is_dir()):
+        for rt in sorted(p for p in topo.iterdir() if p.is_dir()):
+            st = rt / "output" / "northbound-state.json"
+            if not st.exists():
+                continue
+            o = ospf_root(json.loads(st.read_text()))
+            cfg = json.loads((rt / "config.json").read_text())
+            cfg_ospf = ospf_root(cfg)
+            iftype_cfg = {}
+            for a in cfg_ospf.get("areas", {}).get("area", []):
+                for i in a.get("interfaces", {}).get("interface", []):
+                    iftype_cfg[(a["area-id"], i["name"])] = i.get("interface-type", "broadcast")
+            snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"),
+                    "ifindex": ifindex_map(rt / "events.jsonl"), "areas": [], "local_rib": []}
+            for a in o.get("areas", {}).get("area", []):
+                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "interfaces": []}
+                for t in a.get("database", {}).get("area-scope-lsa-type", []):
+                    for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
+                        h = l["ospfv2"]["header"]
+                        b = l["ospfv2"].get("body", {})
+                        if t["lsa-type"] == 1 and "router" in b:
+                            r = b["router"]
+                            flags = 0
+                            for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
+                                flags |= RTR_BITS.get(bit, 0)
+                            links = [[LINK_TYPES[x["type"]], x["link-id"], x["link-data"],
+                                      x["topologies"]["topology"][0]["metric"]]
+                                     for x in r.get("links", {}).get("link", [])]
+                            area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
+                                                        "links": links})
+                        elif t["lsa-type"] == 2 and "network" in b:
+                            n = b["network"]
+                            area["network_lsas"].append({
+                                "adv": h["adv-router"], "id": h["lsa-id"], "mask": n["network-mask"],
+                                "attached": n.get("attached-routers", {}).get("attached-router", [])})
+                for i in a.get("interfaces", {}).get("interface", []):
+                    nb = [[x["neighbor-router-id"], x["address"]]
+                          for x in i.get("neighbors", {}).get("neighbor", [])]
+                    area["interfaces"].append({"name": i["name"], "state": i.get("state"),
+                                               "cfg_type": iftype_cfg.get((a["area-id"], i["name"]), "broadcast"),
+                                               "neighbors": nb})
+                for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
+                    nb = [[x["neighbor-router-id"], x["address"]]
+                          for x in v.get("neighbors", {}).get("neighbor", [])]
+                    # holo names it vlink-<transit-area>-<router-id>
+                    # (holo-ospf/src/northbound/configuration.rs:606)
+                    area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
+                                               "state": v.get("state"), "cfg_type": "virtual-link", "neighbors": nb})
+                snap["areas"].append(area)
+            for r in o.get("local-rib", {}).get("route", []):
+                nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
+                       for n in r.get("next-hops", {}).get("next-hop", [])]
+                snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
+                                          "type": r.get("route-type"), "nexthops": nhs})
+            out.append(snap)
+    return out
+
+
+def main():
+    ref = Path(sys.argv[1]) if len(sys.argv) > 1 else Path("/root/reference")
+    v2 = extract_ospfv2(ref)
+    (HERE / "ospfv2.json").write_text(json.dumps(v2, separators=(",", ":"), sort_keys=True))
+    print(f"ospfv2: {len(v2)} router snapshots -> {HERE / 'ospfv2.json'}")
+    try:
+        from make_golden_isis import extract_isis   # optional second extractor
+        isis = extract_isis(ref)
+        (HERE / "isis.json").write_text(json.dumps(isis, separators=(",", ":"), sort_keys=True))
+        print(f"isis: {len(isis)} router snapshots -> {HERE / 'isis.json'}")
+    except ImportError:
+        pass
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, str(HERE))
+    main()

@@ -1,0 +1,46 @@
+"""Pin the oracle to the reference: every OSPFv2 conformance topology snapshot of
+the reference (LSDB + local state -> local-rib) must be reproduced by the
+line-faithful restatement in oracle/spf_ospfv2.cc."""
+import pytest
+
+import golden_util as gu
+from oracle import pyoracle
+
+SNAPS = gu.load_ospfv2()
+
+
+def _ids():
+    return [f"{s['topo']}-{s['rt']}" for s in SNAPS]
+
+
+def _norm(nh):
+    return sorted(((a or ""), (b or "")) for a, b in nh)
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=_ids())
+def test_ospfv2_oracle_reproduces_reference_local_rib(snap):
+    want = gu.golden_intra(snap)
+    per_area = []
+    for area in snap["areas"]:
+        img = gu.ospfv2_area_image(snap, area)
+        res = pyoracle.ospfv2_run_area(img)
+        assert res.rc == 0
+        if not res.root_found:
+            continue
+        per_area.append(gu.routes_as_dict(res, img.ifnames))
+    got = gu.merge_area_routes(per_area)
+    has_vlink = any(i["cfg_type"] == "virtual-link" for a in snap["areas"] for i in a["interfaces"])
+    # every intra-area route the reference installed must be computed identically
+    n_checked = 0
+    for prefix, (metric, nh) in want.items():
+        assert prefix in got, f"missing {prefix}"
+        assert got[prefix][0] == metric, (prefix, got[prefix], metric)
+        if has_vlink and not got[prefix][1]:
+            # Paths whose first hop is a virtual link get an EMPTY next-hop set from
+            # run_area (ospfv2/spf.rs:203-208); the reference fills them in afterwards
+            # from the transit area (route.rs update_rib_transit_area, RFC 2328 16.3),
+            # which is SURVEY §8f f1 (out of scope).  Metric is still pinned above.
+            continue
+        assert _norm(got[prefix][1]) == _norm(nh), (prefix, got[prefix][1], nh)
+        n_checked += 1
+    assert n_checked > 0
