@@ -219,6 +219,86 @@ typedef struct hl_ospfv2_result {
     uint8_t  _pad[2];
 } hl_ospfv2_result;
 
+
+/* ------------------------------------------------------------------- IS-IS -- */
+
+/* LanId / VertexId key: (SystemId as 48-bit big-endian value << 8) | pseudonode.
+ * Numeric order == derived Ord of LanId (holo-isis/src/packet/mod.rs:57-67). */
+typedef uint64_t hl_lan_id;
+
+#define HL_ISIS_REACH_LEGACY 0u  /* TLV 2  IS reachability, u8 default metric (packet/tlv.rs:263-275)  */
+#define HL_ISIS_REACH_EXT    1u  /* TLV 22 extended IS reachability, u32 metric (tlv.rs:277-287)        */
+#define HL_ISIS_REACH_MT     2u  /* TLV 222 MT IS reachability, carries mt_id                            */
+
+typedef struct hl_isis_reach {
+    hl_lan_id neighbor;
+    uint32_t  metric;
+    uint16_t  mt_id;
+    uint8_t   kind;
+    uint8_t   _pad;
+} hl_isis_reach;
+
+/* LSP flags needed by the SPF gates (holo-isis/src/spf.rs:556-602) */
+#define HL_LSPF_OL             0x01u  /* LspFlags::OL                                            */
+#define HL_LSPF_HAS_PROTOCOLS  0x02u  /* Protocols-Supported TLV present                         */
+#define HL_LSPF_NLPID_IPV4     0x04u
+#define HL_LSPF_NLPID_IPV6     0x08u
+#define HL_LSPF_MT_IPV6_OL     0x10u  /* MT entry for topology 2 has MtFlags::OL (pdu.rs:1431-1445) */
+
+/* LSP fragments in LspId order (lan_id, fragment) (collections.rs:67-74).  Reach
+ * entries of a fragment keep TLV order within each kind. */
+typedef struct hl_isis_lsp {
+    hl_lan_id lan_id;
+    uint32_t  seqno;
+    uint16_t  rem_lifetime;
+    uint8_t   fragment;
+    uint8_t   flags;
+    uint32_t  reach_off;   /* into reaches[] */
+    uint32_t  n_reach;
+} hl_isis_lsp;
+
+#define HL_ISIS_METRIC_STANDARD 0u   /* MetricType::Standard (narrow) */
+#define HL_ISIS_METRIC_WIDE     1u
+#define HL_ISIS_METRIC_BOTH     2u
+#define HL_ISIS_MT_NONE      0xFFu   /* mt_id: None (flooding topology)  */
+#define HL_ISIS_MT_STANDARD  0u
+#define HL_ISIS_MT_IPV6      2u
+#define HL_ISIS_MODE_NORMAL   0u     /* MetricMode::Normal   */
+#define HL_ISIS_MODE_HOPCOUNT 1u     /* MetricMode::HopCount (flooding/manet.rs:59) */
+
+/* One level's LSDB plus the compute_spt() parameters (spf.rs:525-535). */
+typedef struct hl_isis_level {
+    uint8_t  metric_type;
+    uint8_t  mt_id;
+    uint8_t  metric_mode;
+    uint8_t  ipv4_enabled;   /* instance.config.is_af_enabled(Ipv4) */
+    uint8_t  ipv6_enabled;
+    uint8_t  _pad[3];
+    uint32_t n_lsps;     const hl_isis_lsp *lsps;
+    uint32_t n_reaches;  const hl_isis_reach *reaches;
+} hl_isis_level;
+
+/* SPT vertex (Vertex, spf.rs:76-86) in id_tree order (pseudonodes first).
+ * parents[] entries index vertices[] of the same result (arena indices in the
+ * reference); nexthops[] are the VertexNexthop.system_id values of a
+ * `local = false` run, as 48-bit system ids, duplicates and order preserved. */
+typedef struct hl_isis_vertex {
+    hl_lan_id lan_id;
+    uint32_t  distance;
+    uint16_t  hops;
+    uint16_t  _pad;
+    uint32_t  par_off, n_par;
+    uint32_t  nh_off,  n_nh;
+} hl_isis_vertex;
+
+typedef struct hl_isis_spt {
+    uint32_t vertices_cap, n_vertices;  hl_isis_vertex *vertices;
+    uint32_t parents_cap,  n_parents;   uint32_t *parents;
+    uint32_t nexthops_cap, n_nexthops;  uint64_t *nexthops;
+    uint32_t first_hops_cap,  n_first_hops;   uint32_t *first_hops;   /* Spt.first_hops (insertion order)  */
+    uint32_t second_hops_cap, n_second_hops;  uint32_t *second_hops;
+} hl_isis_spt;
+
 #ifdef __cplusplus
 }
 #endif
