@@ -45,10 +45,13 @@ NH_WORDS = 1
 BYTES_PER_VERTEX_OUT = 4 + 2 + 4 + 2 + 8 * NH_WORDS   # dist, hops, first_parent, n_parents, nh_mask
 
 
+DELTA = 0   # near/far bucket width override (0 = library default)
+
+
 def workload():
     from holo_b200 import synth
     t = synth.random_topology(V_ROUTERS, E_DIRECTED, synth.SEED_BASE + CONFIG_INDEX)
-    csr = synth.topology_csr(t)
+    csr = synth.topology_csr(t, delta=DELTA)
     return t, csr
 
 
@@ -385,7 +388,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
     args = ap.parse_args()
+    global DELTA
+    DELTA = args.delta
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -94,13 +94,15 @@ int max_ctas_per_sm(size_t smem) {
 int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
     const uint32_t V = g->d.V;
     const bool q16 = V <= 0xFFFFu;
-    const size_t sb = state_bytes(V, q16 ? 2 : 4);
+    const Layout lay = make_layout(V, g->d.E, q16 ? 2 : 4);
+    const size_t sb = lay.total;
     // static smem of the kernel (Small) is ~4.5 KB; leave headroom
     const size_t smem_cap = ctx->smem_optin > 6144 ? ctx->smem_optin - 6144 : 0;
     const bool in_smem = sb <= smem_cap;
 
     BatchArgs a{};
     a.g = g->d;
+    a.lay = lay;
     a.n_jobs = jobs->n_jobs;
     a.roots = jobs->roots;
     a.ov_off = jobs->ov_off;

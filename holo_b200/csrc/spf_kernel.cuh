@@ -2,9 +2,10 @@
 //
 // One persistent CTA per SM slot; each CTA loops over jobs (roots / perturbed
 // topologies).  All per-job mutable state (tentative distances, frontier
-// queues, ECMP in-degree counters) lives in shared memory; the read-only CSR
-// (forward + transposed) is shared by every CTA of the launch and is served
-// from L1/L2 (a 10k-vertex LSDB is < 1 MB, the B200 L2 is 126 MB).
+// queues, ECMP in-degree counters, hop counts, DAG-edge bitmaps) lives in shared
+// memory; the read-only CSR (forward + transposed) is shared by every CTA of the
+// launch and is served from L1/L2 (a 10k-vertex LSDB is < 1 MB, the B200 L2 is
+// 126 MB).
 //
 // Per job the kernel reproduces the result of the reference Dijkstra
 //   holo-ospf/src/spf.rs:587-729 (run_area) / holo-isis/src/spf.rs:525-707
@@ -13,13 +14,19 @@
 // phases:
 //   1. SSSP   : near/far bucketed label-correcting relaxation, atomicMin on the
 //               shared-memory distance array (distances are order independent);
-//   2. parents: pull pass over the transposed CSR: ECMP in-degree and
-//               first parent = DAG parent with the smallest (distance, id),
-//               i.e. the vertex whose relaxation created the final candidate
-//               entry in the reference (spf.rs:700-703);
-//   3. Kahn   : topological push over DAG edges; hops follow the first parent
-//               (spf.rs:675-678), next-hop atom sets are OR-ed over all ECMP
-//               parents (spf.rs:747-766 / holo-isis spf.rs:678-702).
+//   2. parents: pull pass over the transposed CSR: ECMP in-degree, first parent =
+//               DAG parent with the smallest (distance, id), i.e. the vertex whose
+//               relaxation created the final candidate entry in the reference
+//               (spf.rs:700-703); marks every ECMP-DAG edge and every first-parent
+//               edge in two E-bit shared-memory bitmaps;
+//   3. Kahn   : topological push over the marked DAG edges only; hops follow the
+//               first-parent edge (spf.rs:675-678), next-hop atom sets are OR-ed
+//               over all ECMP parents (spf.rs:747-766 / holo-isis spf.rs:678-702).
+//
+// Shared-memory plan (byte offsets computed on the host, see make_layout):
+//   SSSP   : dist[V] u32 | qa[V] | qb[V] | pend[V] u16 | bm0 | bm1
+//   parents: dist (read) | dagbit,fpbit -> qa region | hops[V] u16 -> qb region | pend
+//   Kahn   : kq0,kq1 -> dist region (dist is written back to HBM first) | bitmaps | hops | pend
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -29,7 +36,7 @@ namespace hspf {
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThreads = 512;
 constexpr int kMaxOv = 8;          // HSPF_MAX_OVERRIDES
-constexpr int kMaxRootDeg = 512;   // root-edge table entries kept in smem
+constexpr int kMaxRootDeg = 256;   // non-HOP root neighbours tracked in smem
 constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
 constexpr uint32_t kGfNoHopTargetNoNh = 1u;
 constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
@@ -45,8 +52,15 @@ struct DevGraph {
     uint32_t reject_above, saturate_at, flags, delta;
 };
 
+struct Layout {   // byte offsets into the per-CTA state block
+    uint32_t dist, qa, qb, pend, bm0, bm1;     // SSSP
+    uint32_t kq0, kq1, hops, dagbit, fpbit;    // parents + Kahn
+    uint32_t total;
+};
+
 struct BatchArgs {
     DevGraph g;
+    Layout lay;
     uint32_t n_jobs;
     const uint32_t *roots;
     const uint32_t *ov_off;   // may be null
@@ -66,15 +80,29 @@ struct BatchArgs {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Bytes of per-job mutable state for V vertices and queue entry size qsz.
-__host__ __device__ inline size_t state_bytes(uint32_t V, int qsz) {
-    size_t Vp = align_up(V, 4);
-    size_t b = 0;
-    b += Vp * 4;                      // dist
-    b += align_up(Vp * qsz, 16) * 2;  // qa, qb
-    b += align_up(Vp * 2, 16);        // pend (u16, packed pairs)
-    b += align_up((Vp + 31) / 32 * 4, 16) * 2;  // two frontier bitmaps
-    return align_up(b, 16);
+// Per-job state layout for V vertices, E edges and queue entry size qsz (2 or 4).
+inline Layout make_layout(uint32_t V, uint32_t E, int qsz) {
+    Layout L{};
+    const size_t Vp = align_up(V, 4);
+    const size_t nbw = (Vp + 31) / 32, nbe = ((size_t)E + 31) / 32;
+    const size_t sz_dist = Vp * 4, sz_q = align_up(Vp * qsz, 16), sz_pend = align_up(Vp * 2, 16);
+    const size_t sz_bm = align_up(nbw * 4, 16), sz_eb = align_up(nbe * 4, 16), sz_hops = align_up(Vp * 2, 16);
+    size_t o = 0;
+    L.dist = (uint32_t)o; o += sz_dist;
+    L.qa = (uint32_t)o; o += sz_q;
+    L.qb = (uint32_t)o; o += sz_q;
+    L.pend = (uint32_t)o; o += sz_pend;
+    L.bm0 = (uint32_t)o; o += sz_bm;
+    L.bm1 = (uint32_t)o; o += sz_bm;
+    // parents/Kahn arrays: alias onto SSSP arrays that are dead by then, else append
+    if (2 * sz_eb <= sz_q) { L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb; }
+    else { L.dagbit = (uint32_t)o; o += sz_eb; L.fpbit = (uint32_t)o; o += sz_eb; }
+    L.hops = L.qb;                                   // sz_hops <= sz_q always (qsz >= 2)
+    if (2 * sz_q <= sz_dist) { L.kq0 = L.dist; L.kq1 = L.dist + (uint32_t)sz_q; }
+    else { L.kq0 = (uint32_t)o; o += sz_q; L.kq1 = (uint32_t)o; o += sz_q; }
+    (void)sz_hops;
+    L.total = (uint32_t)align_up(o, 16);
+    return L;
 }
 
 struct Ov {   // overrides of the current job, in smem
@@ -88,9 +116,9 @@ struct Small {  // small per-CTA control block in smem
     uint32_t scan_min;
     uint32_t status;
     uint32_t job;
-    uint32_t root_deg, n_roottab;
+    uint32_t n_roottab;
     uint32_t rt_target[kMaxRootDeg];  // non-HOP heads of root edges
-    uint32_t rt_base[kMaxRootDeg];
+    uint32_t rt_base[kMaxRootDeg];    // first-hop atom base of that head
 };
 
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {
@@ -103,9 +131,9 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 // Warp-aggregated queue push (all currently converged lanes take part).
 template <typename VT>
 __device__ __forceinline__ void q_push(VT *q, uint32_t *counter, uint32_t v) {
-    unsigned active = __activemask();
-    int leader = __ffs(active) - 1;
-    unsigned rank = __popc(active & ((1u << lane_id()) - 1));
+    const unsigned active = __activemask();
+    const int leader = __ffs(active) - 1;
+    const unsigned rank = __popc(active & ((1u << lane_id()) - 1));
     uint32_t base = 0;
     if ((int)lane_id() == leader) base = atomicAdd(counter, __popc(active));
     base = __shfl_sync(active, base, leader);
@@ -113,9 +141,7 @@ __device__ __forceinline__ void q_push(VT *q, uint32_t *counter, uint32_t v) {
 }
 
 __device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) {
-    if (fl & kVfLeaf) return false;
-    if ((fl & kVfLeafUnlessRoot) && u != root) return false;
-    return true;
+    return !((fl & kVfLeaf) || ((fl & kVfLeafUnlessRoot) && u != root));
 }
 
 template <typename VT>
@@ -124,24 +150,26 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     __shared__ Small S;
 
     const DevGraph &g = a.g;
+    const Layout &L = a.lay;
     const uint32_t V = g.V;
     const uint32_t tid = threadIdx.x;
     const uint32_t Vp = (uint32_t)align_up(V, 4);
     const uint32_t nbw = (Vp + 31) / 32;
+    const uint32_t nbe = (g.E + 31) / 32;
 
     uint8_t *base = a.ws_stride ? a.ws + (size_t)blockIdx.x * a.ws_stride : smem_raw;
-    uint32_t *dist = reinterpret_cast<uint32_t *>(base);
-    size_t off = (size_t)Vp * 4;
-    VT *qa = reinterpret_cast<VT *>(base + off);
-    off += align_up((size_t)Vp * sizeof(VT), 16);
-    VT *qb = reinterpret_cast<VT *>(base + off);
-    off += align_up((size_t)Vp * sizeof(VT), 16);
-    uint32_t *pend32 = reinterpret_cast<uint32_t *>(base + off);  // packed u16 pairs
-    uint16_t *pend = reinterpret_cast<uint16_t *>(base + off);
-    off += align_up((size_t)Vp * 2, 16);
-    uint32_t *bm0 = reinterpret_cast<uint32_t *>(base + off);
-    off += align_up((size_t)nbw * 4, 16);
-    uint32_t *bm1 = reinterpret_cast<uint32_t *>(base + off);
+    uint32_t *dist = reinterpret_cast<uint32_t *>(base + L.dist);
+    VT *qa = reinterpret_cast<VT *>(base + L.qa);
+    VT *qb = reinterpret_cast<VT *>(base + L.qb);
+    uint32_t *pend32 = reinterpret_cast<uint32_t *>(base + L.pend);  // packed u16 pairs
+    uint16_t *pend = reinterpret_cast<uint16_t *>(base + L.pend);
+    uint32_t *bm0 = reinterpret_cast<uint32_t *>(base + L.bm0);
+    uint32_t *bm1 = reinterpret_cast<uint32_t *>(base + L.bm1);
+    VT *kq0 = reinterpret_cast<VT *>(base + L.kq0);
+    VT *kq1 = reinterpret_cast<VT *>(base + L.kq1);
+    uint16_t *hops_s = reinterpret_cast<uint16_t *>(base + L.hops);
+    uint32_t *dagbit = reinterpret_cast<uint32_t *>(base + L.dagbit);
+    uint32_t *fpbit = reinterpret_cast<uint32_t *>(base + L.fpbit);
 
     const uint32_t nhw = a.nhw;
 
@@ -163,8 +191,11 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // ---- per-job init -----------------------------------------------------
         for (uint32_t v = tid; v < Vp; v += kThreads) dist[v] = kInf;
         for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
-        for (uint32_t v = tid; v < V; v += kThreads) o_hops[v] = 0;
-        for (size_t i = tid; i < (size_t)V * nhw; i += kThreads) o_nh[i] = 0ull;
+        {   // zero the next-hop plane (it is accumulated with atomics later)
+            uint64_t *p = o_nh;
+            const size_t n = (size_t)V * nhw;
+            for (size_t i = tid; i < n; i += kThreads) p[i] = 0ull;
+        }
         if (tid == 0) {
             S.status = 0;
             S.cnt[0] = 1;
@@ -176,12 +207,11 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         }
         __syncthreads();
         if (tid < S.ov.n) {
-            uint32_t e = a.ov_edge[a.ov_off[job] + tid];
-            uint32_t c = a.ov_cost[a.ov_off[job] + tid];
-            // tail = last vertex with row[v] <= e
+            const uint32_t e = a.ov_edge[a.ov_off[job] + tid];
+            const uint32_t c = a.ov_cost[a.ov_off[job] + tid];
             uint32_t lo = 0, hi = V;  // invariant row[lo] <= e < row[hi]
             while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
+                const uint32_t mid = (lo + hi) >> 1;
                 if (g.row[mid] <= e) lo = mid; else hi = mid;
             }
             S.ov.tail[tid] = lo;
@@ -194,14 +224,14 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             dist[root] = 0;
             qa[0] = (VT)root;
         }
-        // root edge table: bases of first-hop atoms behind non-HOP heads
+        __syncthreads();
+        const uint32_t n_ov = S.ov.n;
+        // root edge table: first-hop atom bases behind the root's non-HOP neighbours
         if (tid == 32) {
-            uint32_t rb = g.row[root], re = g.row[root + 1];
-            uint32_t deg = re - rb;
-            S.root_deg = deg;
-            uint32_t nt = 0, nextbase = deg;
+            const uint32_t rb = g.row[root], re = g.row[root + 1];
+            uint32_t nt = 0, nextbase = re - rb;
             for (uint32_t e = rb; e < re; ++e) {
-                uint32_t h = g.edge[e].x;
+                const uint32_t h = g.edge[e].x;
                 if (!(g.vflags[h] & kVfHop)) {
                     if (nt < (uint32_t)kMaxRootDeg) {
                         S.rt_target[nt] = h;
@@ -216,7 +246,6 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             S.n_roottab = nt;
         }
         __syncthreads();
-        const uint32_t n_ov = S.ov.n;
 
         // ======================= phase 1: SSSP ==================================
         const uint32_t delta = g.delta ? g.delta : 1u;
@@ -231,23 +260,29 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 for (uint32_t i = tid; i < n_cur; i += kThreads) {
                     const uint32_t u = qcur[i];
                     const uint32_t du = dist[u];
-                    const uint32_t fu = g.vflags[u];
-                    if (!expands(fu, u, root)) continue;
+                    if (!expands(g.vflags[u], u, root)) continue;
                     bool uo = false;
                     for (uint32_t k = 0; k < n_ov; ++k) uo |= (S.ov.tail[k] == u);
                     const uint32_t eb = g.row[u], ee = g.row[u + 1];
-                    for (uint32_t e = eb; e < ee; ++e) {
-                        uint2 ec = g.edge[e];
-                        uint32_t c = ec.y;
-                        if (uo) {
-                            for (uint32_t k = 0; k < n_ov; ++k)
-                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
-                            if (c == kInf) continue;
-                        }
-                        const uint32_t nd = sat_add(du, c);
-                        if (nd > g.reject_above) continue;
-                        const uint32_t v = ec.x;
-                        if (nd < dist[v]) {
+                    for (uint32_t e0 = eb; e0 < ee; e0 += 4) {
+                        uint2 ec[4];
+                        uint32_t dv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ec[k] = (e0 + k < ee) ? g.edge[e0 + k] : make_uint2(u, kInf);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) dv[k] = dist[ec[k].x];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (e0 + k >= ee) break;
+                            uint32_t c = ec[k].y;
+                            if (uo) {
+                                for (uint32_t q = 0; q < n_ov; ++q)
+                                    if (S.ov.edge[q] == e0 + k) c = S.ov.cost[q];
+                                if (c == kInf) continue;
+                            }
+                            const uint32_t nd = sat_add(du, c);
+                            if (nd > g.reject_above || nd >= dv[k]) continue;
+                            const uint32_t v = ec[k].x;
                             const uint32_t old = atomicMin(&dist[v], nd);
                             if (nd < old && nd < hi_thr) {
                                 const uint32_t bit = 1u << (v & 31);
@@ -296,12 +331,15 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             }
             if (done) break;
         }
+        // SSSP done: qa/qb/bm0/bm1 are dead, dist is final.
+        for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
+        for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
         __syncthreads();
 
         // ======================= phase 2: ECMP parents (pull) ====================
         uint32_t sat_flag = 0;
         for (uint32_t v = tid; v < Vp; v += kThreads) {
-            uint32_t cnt = 0, bd = kInf, bu = kInf;
+            uint32_t cnt = 0, bd = kInf, bu = kInf, be = kInf;
             if (v < V) {
                 const uint32_t dv = dist[v];
                 if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
@@ -309,23 +347,35 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     bool vo = false;
                     for (uint32_t k = 0; k < n_ov; ++k) vo |= (S.ov.head[k] == v);
                     const uint32_t ib = g.irow[v], ie = g.irow[v + 1];
-                    for (uint32_t i = ib; i < ie; ++i) {
-                        const uint2 sc = g.iedge[i];
-                        const uint32_t u = sc.x;
-                        const uint32_t du = dist[u];
-                        if (du == kInf) continue;
-                        if (!expands(g.vflags[u], u, root)) continue;
-                        uint32_t c = sc.y;
-                        if (vo) {
-                            const uint32_t e = g.ieid[i];
-                            for (uint32_t k = 0; k < n_ov; ++k)
-                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
-                            if (c == kInf) continue;
+                    for (uint32_t i0 = ib; i0 < ie; i0 += 4) {
+                        uint2 sc[4];
+                        uint32_t du[4];
+                        uint32_t fl[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sc[k] = (i0 + k < ie) ? g.iedge[i0 + k] : make_uint2(v, kInf);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { du[k] = dist[sc[k].x]; fl[k] = g.vflags[sc[k].x]; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (i0 + k >= ie) break;
+                            const uint32_t u = sc[k].x;
+                            if (du[k] == kInf || !expands(fl[k], u, root)) continue;
+                            uint32_t c = sc[k].y;
+                            uint32_t e = kInf;
+                            if (vo) {
+                                e = g.ieid[i0 + k];
+                                for (uint32_t q = 0; q < n_ov; ++q)
+                                    if (S.ov.edge[q] == e) c = S.ov.cost[q];
+                                if (c == kInf) continue;
+                            }
+                            if (sat_add(du[k], c) != dv) continue;
+                            if (e == kInf) e = g.ieid[i0 + k];
+                            ++cnt;
+                            atomicOr(&dagbit[e >> 5], 1u << (e & 31));
+                            if (du[k] < bd || (du[k] == bd && u < bu)) { bd = du[k]; bu = u; be = e; }
                         }
-                        if (sat_add(du, c) != dv) continue;
-                        ++cnt;
-                        if (du < bd || (du == bd && u < bu)) { bd = du; bu = u; }
                     }
+                    if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
                 }
                 o_fp[v] = bu;
                 o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
@@ -333,22 +383,24 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             pend[v] = (uint16_t)min(cnt, 0xFFFFu);
         }
         if (sat_flag) atomicOr(&S.status, kJsSaturated);
-        if (tid == 0) { S.cnt[0] = 1; S.cnt[1] = 0; qa[0] = (VT)root; }
+        __syncthreads();
+        // distances are final: stream them out, then the region is reused by the Kahn queues
+        for (uint32_t v = tid; v < V; v += kThreads) o_dist[v] = dist[v];
+        __syncthreads();
+        if (tid == 0) { S.cnt[0] = 1; S.cnt[1] = 0; kq0[0] = (VT)root; }
         __syncthreads();
 
         // ======================= phase 3: Kahn push over the ECMP DAG ============
-        qcur = qa; qnext = qb;
-        p = 0;
         {
+            VT *kcur = kq0, *knext = kq1;
+            p = 0;
             for (;;) {
                 const uint32_t n_cur = S.cnt[p];
                 if (n_cur == 0) break;
                 for (uint32_t i = tid; i < n_cur; i += kThreads) {
-                    const uint32_t u = qcur[i];
-                    const uint32_t fu = g.vflags[u];
-                    if (!expands(fu, u, root)) continue;
-                    const uint32_t du = dist[u];
-                    const uint32_t hu = __ldcg(&o_hops[u]);
+                    const uint32_t u = kcur[i];
+                    const uint32_t hu = hops_s[u];
+                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
                     uint64_t nhu[4] = {0, 0, 0, 0};
                     uint32_t abase = 0;
                     bool atoms_ok = true;
@@ -361,22 +413,12 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                             if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
                         if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
                     }
-                    bool uo = false;
-                    for (uint32_t k = 0; k < n_ov; ++k) uo |= (S.ov.tail[k] == u);
-                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
                     for (uint32_t e = eb; e < ee; ++e) {
-                        const uint2 ec = g.edge[e];
-                        const uint32_t v = ec.x;
-                        if (v == root) continue;
-                        uint32_t c = ec.y;
-                        if (uo) {
-                            for (uint32_t k = 0; k < n_ov; ++k)
-                                if (S.ov.edge[k] == e) c = S.ov.cost[k];
-                            if (c == kInf) continue;
-                        }
-                        if (sat_add(du, c) != dist[v]) continue;
-                        const uint32_t fv = g.vflags[v];
+                        if (!((dagbit[e >> 5] >> (e & 31)) & 1u)) continue;
+                        const uint32_t v = g.edge[e].x;
+                        const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
                         if (hu == 0) {
+                            const uint32_t fv = g.vflags[v];
                             if (!((g.flags & kGfNoHopTargetNoNh) && !(fv & kVfHop)) && atoms_ok) {
                                 const uint32_t atom = abase + (e - eb);
                                 if (atom < 64u * nhw)
@@ -385,21 +427,22 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 else
                                     atomicOr(&S.status, kJsTooManyAtoms);
                             }
+                            if (is_fp) hops_s[v] = (uint16_t)(fv & kVfHop);
                         } else {
                             for (uint32_t w = 0; w < nhw; ++w)
                                 if (nhu[w])
                                     atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), nhu[w]);
+                            if (is_fp) hops_s[v] = (uint16_t)min(hu + (g.vflags[v] & kVfHop), 0xFFFFu);
                         }
-                        if (__ldcg(&o_fp[v]) == u) o_hops[v] = (uint16_t)min(hu + (fv & kVfHop), 0xFFFFu);
                         // packed u16 decrement; the thread that takes it to zero owns v
                         const uint32_t sh = (v & 1) * 16;
                         const uint32_t oldw = atomicSub(&pend32[v >> 1], 1u << sh);
-                        if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(qnext, &S.cnt[p ^ 1], v);
+                        if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(knext, &S.cnt[p ^ 1], v);
                     }
                 }
                 __syncthreads();
                 if (tid == 0) S.cnt[p] = 0;
-                { VT *t = qcur; qcur = qnext; qnext = t; }
+                { VT *t = kcur; kcur = knext; knext = t; }
                 p ^= 1;
                 __syncthreads();
             }
@@ -407,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         __syncthreads();
 
         // ======================= write-back ======================================
-        for (uint32_t v = tid; v < V; v += kThreads) o_dist[v] = dist[v];
+        for (uint32_t v = tid; v < V; v += kThreads) o_hops[v] = hops_s[v];
         if (tid == 0) a.out_status[job] = S.status;
     }
 }
