@@ -27,6 +27,7 @@ VF_HOP = 0x01
 VF_LEAF = 0x02
 VF_LEAF_UNLESS_ROOT = 0x04
 GF_NOHOP_TARGET_NO_NEXTHOP = 0x01
+GF_HOPCOUNT = 0x02
 COST_DISABLED = 0xFFFFFFFF
 DIST_INF = 0xFFFFFFFF
 NO_PARENT = 0xFFFFFFFF

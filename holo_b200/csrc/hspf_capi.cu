@@ -225,7 +225,14 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
                 indeg[v + 1]++;
             }
         }
-        if (zero_cost_hop_tail)
+        if (g->flags & HSPF_GF_HOPCOUNT) {
+            for (uint32_t u = 0; u < V; ++u)
+                for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e) {
+                    const bool zero = (g->vflags[u] & HSPF_VF_HOP) && !(g->vflags[g->col[e]] & HSPF_VF_HOP);
+                    if (g->cost[e] != (zero ? 0u : 1u))
+                        return fail(ctx, HSPF_E_INVAL, "HSPF_GF_HOPCOUNT: costs must be 0 (HOP->non-HOP) or 1");
+                }
+        } else if (zero_cost_hop_tail)
             return fail(ctx, HSPF_E_NEEDS_ORACLE,
                         "zero-cost link out of a hop-counting vertex: ECMP DAG depends on pop order");
         uint32_t max_indeg = 0;

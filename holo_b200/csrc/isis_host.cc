@@ -1,0 +1,352 @@
+// isis_host.cc — IS-IS host side of the engine: level LSDB image -> CSR, and device
+// result planes -> the reference's Spt (vertices with ordered ECMP parents, next-hop
+// Vecs, first/second hops).
+//
+// The LSDB walk the reference repeats for every visited edge (vertex_edges over up
+// to 256 fragments x 4 TLV kinds, plus the mutual-link re-iteration,
+// holo-isis/src/spf.rs:605-625,1005-1120) happens here once; the per-vertex transit
+// gates (missing zeroth LSP, overload bit, protocols-supported, spf.rs:556-602)
+// become vertex flags.  Distances / hops / first-hop sets come from the CUDA kernel
+// (hspf_run_batch); this file only orders what the kernel found the way the
+// reference's pop order would have (parents: spf.rs:675, nexthops: spf.rs:678-702).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "holo_spf_lsdb.h"
+
+namespace {
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kMaxWide = 0xFE000000u;
+inline bool is_pn(hl_lan_id id) { return (id & 0xFF) != 0; }
+}  // namespace
+
+struct hspf_isis_flat {
+    const hl_isis_level *lvl = nullptr;
+    std::vector<hl_lan_id> ids;                 // [V] in VertexId order
+    std::vector<uint32_t> row, col, cost;
+    std::vector<uint8_t> vflags;
+    std::vector<uint32_t> irow, isrc, ieid;     // transposed (host copy)
+    std::unordered_map<uint64_t, uint32_t> index;
+    uint32_t reject_above = 0, gflags = 0;
+};
+
+namespace {
+
+int flatten(const hl_isis_level *l, hspf_isis_flat &f) {
+    f.lvl = l;
+    const bool mt_none = l->mt_id == HL_ISIS_MT_NONE, mt_std = l->mt_id == HL_ISIS_MT_STANDARD;
+    const bool std_en = l->metric_type == HL_ISIS_METRIC_STANDARD || l->metric_type == HL_ISIS_METRIC_BOTH;
+    const bool wide_en = l->metric_type == HL_ISIS_METRIC_WIDE || l->metric_type == HL_ISIS_METRIC_BOTH;
+    const bool hopcount = l->metric_mode == HL_ISIS_MODE_HOPCOUNT;
+    auto valid = [&](const hl_isis_lsp &p) { return p.seqno != 0 && p.rem_lifetime != 0; };
+
+    // fragments in LspId order
+    std::vector<uint32_t> order(l->n_lsps);
+    for (uint32_t i = 0; i < l->n_lsps; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const auto &x = l->lsps[a], &y = l->lsps[b];
+        return x.lan_id != y.lan_id ? x.lan_id < y.lan_id : x.fragment < y.fragment;
+    });
+    // vertices: every LAN id owning at least one valid fragment
+    std::vector<hl_lan_id> pn, rt;
+    for (uint32_t i : order) {
+        const auto &p = l->lsps[i];
+        if (!valid(p)) continue;
+        auto &dst = is_pn(p.lan_id) ? pn : rt;
+        if (dst.empty() || dst.back() != p.lan_id) dst.push_back(p.lan_id);
+    }
+    f.ids = pn;
+    f.ids.insert(f.ids.end(), rt.begin(), rt.end());
+    const uint32_t V = (uint32_t)f.ids.size();
+    for (uint32_t v = 0; v < V; ++v) f.index.emplace(f.ids[v], v);
+    f.vflags.assign(V, 0);
+    std::vector<uint8_t> has_zeroth(V, 0);
+    for (uint32_t v = 0; v < V; ++v) if (!is_pn(f.ids[v])) f.vflags[v] |= HSPF_VF_HOP;
+
+    struct Raw { uint32_t u, v, cost; };
+    std::vector<Raw> raw;
+    raw.reserve(l->n_reaches);
+    auto ecost = [&](hl_lan_id nbr, uint32_t metric) { return hopcount ? (is_pn(nbr) ? 0u : 1u) : metric; };
+    for (uint32_t i : order) {
+        const auto &p = l->lsps[i];
+        if (!valid(p)) continue;
+        const uint32_t u = f.index[p.lan_id];
+        if (p.fragment == 0) {
+            has_zeroth[u] = 1;
+            if (!is_pn(p.lan_id)) {
+                // overload bit: skipped unless root (spf.rs:566-572), only with an MT id
+                if (!mt_none) {
+                    const bool ol = mt_std ? (p.flags & HL_LSPF_OL) : (p.flags & HL_LSPF_MT_IPV6_OL);
+                    if (ol) f.vflags[u] |= HSPF_VF_LEAF_UNLESS_ROOT;
+                }
+                // protocols-supported gate (spf.rs:580-602), standard topology only
+                if (mt_std) {
+                    bool ok = p.flags & HL_LSPF_HAS_PROTOCOLS;
+                    if (ok && l->ipv4_enabled && !(p.flags & HL_LSPF_NLPID_IPV4)) ok = false;
+                    if (ok && l->ipv6_enabled && !(p.flags & HL_LSPF_NLPID_IPV6)) ok = false;
+                    if (!ok) f.vflags[u] |= HSPF_VF_LEAF;
+                }
+            }
+        }
+        const hl_isis_reach *re = l->reaches + p.reach_off;
+        auto emit = [&](const hl_isis_reach &r) {
+            auto it = f.index.find(r.neighbor);
+            if (it == f.index.end()) return;       // no LSP: the mutual check can never pass
+            raw.push_back({u, it->second, ecost(r.neighbor, r.metric)});
+        };
+        if ((mt_none || mt_std) && std_en)
+            for (uint32_t k = 0; k < p.n_reach; ++k) if (re[k].kind == HL_ISIS_REACH_LEGACY) emit(re[k]);
+        if (((mt_none || mt_std) || is_pn(p.lan_id)) && wide_en)
+            for (uint32_t k = 0; k < p.n_reach; ++k)
+                if (re[k].kind == HL_ISIS_REACH_EXT && re[k].metric < kMaxWide) emit(re[k]);
+        if (!mt_none && !mt_std)
+            for (uint32_t k = 0; k < p.n_reach; ++k)
+                if (re[k].kind == HL_ISIS_REACH_MT && re[k].mt_id == l->mt_id && re[k].metric < kMaxWide) emit(re[k]);
+        if (mt_none)
+            for (uint32_t k = 0; k < p.n_reach; ++k)
+                if (re[k].kind == HL_ISIS_REACH_MT && re[k].metric < kMaxWide) emit(re[k]);
+    }
+    for (uint32_t v = 0; v < V; ++v) if (!has_zeroth[v]) f.vflags[v] |= HSPF_VF_LEAF;
+
+    // mutual-link filter; raw is grouped by u in iteration order (fragments of one
+    // LAN id are contiguous in LspId order)
+    std::unordered_set<uint64_t> have;
+    have.reserve(raw.size() * 2);
+    for (auto &e : raw) have.insert(((uint64_t)e.u << 32) | e.v);
+    auto keep = [&](const Raw &e) {
+        if (e.u == e.v) return false;
+        // a link between two pseudonodes can never be mutual-checked into the SPT in
+        // a sane LSDB; the engine's CSR forbids it, so drop it
+        if (!(f.vflags[e.u] & HSPF_VF_HOP) && !(f.vflags[e.v] & HSPF_VF_HOP)) return false;
+        return have.count(((uint64_t)e.v << 32) | e.u) != 0;
+    };
+    f.row.assign(V + 1, 0);
+    for (auto &e : raw) if (keep(e)) f.row[e.u + 1]++;
+    for (uint32_t v = 0; v < V; ++v) f.row[v + 1] += f.row[v];
+    const uint32_t E = f.row[V];
+    f.col.resize(E); f.cost.resize(E);
+    std::vector<uint32_t> fill(f.row.begin(), f.row.end() - 1);
+    for (auto &e : raw) if (keep(e)) { const uint32_t k = fill[e.u]++; f.col[k] = e.v; f.cost[k] = e.cost; }
+    // transposed copy for the host-side ordering passes
+    f.irow.assign(V + 1, 0);
+    for (uint32_t e = 0; e < E; ++e) f.irow[f.col[e] + 1]++;
+    for (uint32_t v = 0; v < V; ++v) f.irow[v + 1] += f.irow[v];
+    f.isrc.resize(E); f.ieid.resize(E);
+    std::vector<uint32_t> ifill(f.irow.begin(), f.irow.end() - 1);
+    for (uint32_t u = 0; u < V; ++u)
+        for (uint32_t e = f.row[u]; e < f.row[u + 1]; ++e) { const uint32_t k = ifill[f.col[e]]++; f.isrc[k] = u; f.ieid[k] = e; }
+    f.reject_above = l->metric_type == HL_ISIS_METRIC_STANDARD ? 1023u : kMaxWide;
+    f.gflags = HSPF_GF_NOHOP_TARGET_NO_NEXTHOP | (hopcount ? HSPF_GF_HOPCOUNT : 0u);
+    return HSPF_OK;
+}
+
+void fill_csr(const hspf_isis_flat &f, hspf_csr *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->n_vertices = (uint32_t)f.ids.size();
+    c->n_edges = (uint32_t)f.col.size();
+    c->row_ptr = f.row.data(); c->col = f.col.data(); c->cost = f.cost.data(); c->vflags = f.vflags.data();
+    c->reject_above = f.reject_above;
+    c->saturate_at = 0;
+    c->flags = f.gflags;
+    c->delta = 0;
+}
+
+inline bool expands(uint8_t fl, uint32_t u, uint32_t root) {
+    return !((fl & HSPF_VF_LEAF) || ((fl & HSPF_VF_LEAF_UNLESS_ROOT) && u != root));
+}
+
+int spt_from_planes(const hspf_isis_flat &f, uint32_t root, const uint32_t *dist, const uint16_t *hops,
+                    uint32_t n_ov, const uint32_t *ov_edge, const uint32_t *ov_cost, hl_isis_spt *out) {
+    const uint32_t V = (uint32_t)f.ids.size();
+    const bool hopcount = f.gflags & HSPF_GF_HOPCOUNT;
+    auto ecost = [&](uint32_t e) {
+        uint32_t c = f.cost[e];
+        for (uint32_t k = 0; k < n_ov; ++k) if (ov_edge[k] == e) c = ov_cost[k];
+        return c;
+    };
+    auto is_dag = [&](uint32_t u, uint32_t e, uint32_t v) {
+        if (v == root || dist[u] == HSPF_DIST_INF || dist[v] == HSPF_DIST_INF) return false;
+        if (!expands(f.vflags[u], u, root)) return false;
+        const uint32_t c = ecost(e);
+        if (c == HSPF_COST_DISABLED) return false;
+        const uint64_t s = (uint64_t)dist[u] + c;
+        return s == dist[v];
+    };
+    // hop-count mode: a pseudonode's only parent is its lowest-numbered router of the same level
+    std::vector<uint32_t> owner;
+    if (hopcount) {
+        owner.assign(V, kNone);
+        for (uint32_t v = 0; v < V; ++v) {
+            if ((f.vflags[v] & HSPF_VF_HOP) || dist[v] == HSPF_DIST_INF) continue;
+            for (uint32_t i = f.irow[v]; i < f.irow[v + 1]; ++i)
+                if (is_dag(f.isrc[i], f.ieid[i], v)) owner[v] = std::min(owner[v], f.isrc[i]);
+        }
+    }
+    // pop order
+    std::vector<uint32_t> spt;
+    for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
+    std::vector<uint32_t> pop = spt;
+    auto key = [&](uint32_t v) {
+        // (distance, tie): plain VertexId order, or the interleaved hop-count order
+        uint64_t tie = v;
+        if (hopcount) tie = (f.vflags[v] & HSPF_VF_HOP) ? ((uint64_t)v << 33) : (((uint64_t)owner[v] << 33) | (1ull << 32) | v);
+        return std::make_pair(dist[v], tie);
+    };
+    std::sort(pop.begin(), pop.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    std::vector<uint32_t> pos(V, kNone), rank(V, kNone);
+    for (uint32_t i = 0; i < pop.size(); ++i) pos[pop[i]] = i;
+    for (uint32_t i = 0; i < spt.size(); ++i) rank[spt[i]] = i;
+
+    // parents in push order: by (pop position of the tail, edge order of the tail)
+    std::vector<std::vector<uint32_t>> parents(V);
+    size_t n_par = 0;
+    std::vector<std::pair<uint64_t, uint32_t>> tmp;
+    for (uint32_t v : spt) {
+        tmp.clear();
+        for (uint32_t i = f.irow[v]; i < f.irow[v + 1]; ++i) {
+            const uint32_t u = f.isrc[i], e = f.ieid[i];
+            if (!is_dag(u, e, v)) continue;
+            if (hopcount && !(f.vflags[v] & HSPF_VF_HOP) && u != owner[v]) continue;
+            tmp.emplace_back(((uint64_t)pos[u] << 32) | e, u);
+        }
+        std::sort(tmp.begin(), tmp.end());
+        for (auto &t : tmp) parents[v].push_back(t.second);
+        n_par += tmp.size();
+    }
+    // next-hop Vecs in pop order
+    std::vector<std::vector<uint64_t>> nh(V);
+    size_t n_nh = 0;
+    const size_t cap = (size_t)1 << 22;
+    for (uint32_t v : pop) {
+        auto &dst = nh[v];
+        for (uint32_t p : parents[v]) {
+            if (hops[p] == 0) {
+                if (f.vflags[v] & HSPF_VF_HOP) dst.push_back(f.ids[v] >> 8);
+            } else {
+                if (n_nh + dst.size() + nh[p].size() > cap) return HSPF_E_UNSUPPORTED;
+                dst.insert(dst.end(), nh[p].begin(), nh[p].end());
+            }
+        }
+        n_nh += dst.size();
+    }
+    std::vector<uint32_t> fh, sh;
+    for (uint32_t v : pop) {
+        if (!(f.vflags[v] & HSPF_VF_HOP)) continue;
+        if (hops[v] == 1) fh.push_back(rank[v]);
+        if (hops[v] == 2) sh.push_back(rank[v]);
+    }
+    out->n_vertices = (uint32_t)spt.size();
+    out->n_parents = (uint32_t)n_par;
+    out->n_nexthops = (uint32_t)n_nh;
+    out->n_first_hops = (uint32_t)fh.size();
+    out->n_second_hops = (uint32_t)sh.size();
+    if (out->n_vertices > out->vertices_cap || out->n_parents > out->parents_cap ||
+        out->n_nexthops > out->nexthops_cap || out->n_first_hops > out->first_hops_cap ||
+        out->n_second_hops > out->second_hops_cap)
+        return HSPF_E_NOMEM;
+    uint32_t i = 0, p = 0, n = 0;
+    for (uint32_t v : spt) {
+        hl_isis_vertex o{};
+        o.lan_id = f.ids[v]; o.distance = dist[v]; o.hops = hops[v];
+        o.par_off = p; o.n_par = (uint32_t)parents[v].size();
+        o.nh_off = n; o.n_nh = (uint32_t)nh[v].size();
+        for (uint32_t u : parents[v]) out->parents[p++] = rank[u];
+        for (uint64_t x : nh[v]) out->nexthops[n++] = x;
+        out->vertices[i++] = o;
+    }
+    std::copy(fh.begin(), fh.end(), out->first_hops);
+    std::copy(sh.begin(), sh.end(), out->second_hops);
+    return HSPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hspf_isis_flatten(const hl_isis_level *lvl, hspf_isis_flat **out) {
+    if (!lvl || !out) return HSPF_E_INVAL;
+    *out = nullptr;
+    try {
+        auto *f = new hspf_isis_flat();
+        int rc = flatten(lvl, *f);
+        if (rc) { delete f; return rc; }
+        *out = f;
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
+void hspf_isis_flat_free(hspf_isis_flat *flat) { delete flat; }
+
+int hspf_isis_flat_csr(const hspf_isis_flat *flat, hspf_csr *out) {
+    if (!flat || !out) return HSPF_E_INVAL;
+    fill_csr(*flat, out);
+    return HSPF_OK;
+}
+
+int hspf_isis_flat_vertices(const hspf_isis_flat *flat, const uint64_t **lan_ids, uint32_t *n_vertices) {
+    if (!flat) return HSPF_E_INVAL;
+    if (lan_ids) *lan_ids = flat->ids.data();
+    if (n_vertices) *n_vertices = (uint32_t)flat->ids.size();
+    return HSPF_OK;
+}
+
+uint32_t hspf_isis_flat_vertex(const hspf_isis_flat *flat, uint64_t lan_id) {
+    if (!flat) return kNone;
+    auto it = flat->index.find(lan_id);
+    return it == flat->index.end() ? kNone : it->second;
+}
+
+int hspf_isis_spt_from_planes(const hspf_isis_flat *flat, uint32_t root_vertex, const uint32_t *dist,
+                              const uint16_t *hops, uint32_t n_ov, const uint32_t *ov_edge,
+                              const uint32_t *ov_cost, hl_isis_spt *out) {
+    if (!flat || !dist || !hops || !out || root_vertex >= flat->ids.size()) return HSPF_E_INVAL;
+    try {
+        return spt_from_planes(*flat, root_vertex, dist, hops, n_ov, ov_edge, ov_cost, out);
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
+int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root_system_id, hl_isis_spt *out) {
+    if (!ctx || !lvl || !out) return HSPF_E_INVAL;
+    try {
+        hspf_isis_flat f;
+        int rc = flatten(lvl, f);
+        if (rc) return rc;
+        const hl_lan_id root_id = (hl_lan_id)(root_system_id << 8);
+        auto it = f.index.find(root_id);
+        if (it == f.index.end()) {
+            // the root owns no LSP: the SPT is the root alone (popped, zeroth LSP missing)
+            out->n_vertices = 1; out->n_parents = out->n_nexthops = out->n_first_hops = out->n_second_hops = 0;
+            if (out->vertices_cap < 1) return HSPF_E_NOMEM;
+            hl_isis_vertex o{};
+            o.lan_id = root_id;
+            out->vertices[0] = o;
+            return HSPF_OK;
+        }
+        const uint32_t root = it->second;
+        const uint32_t V = (uint32_t)f.ids.size();
+        hspf_csr csr;
+        fill_csr(f, &csr);
+        hspf_graph *g = nullptr;
+        rc = hspf_graph_upload(ctx, &csr, &g);
+        if (rc) return rc;
+        std::vector<uint32_t> dist(V);
+        std::vector<uint16_t> hops(V);
+        uint32_t status = 0;
+        hspf_jobs jobs{};
+        jobs.n_jobs = 1; jobs.roots = &root;
+        hspf_result res{};
+        res.dist = dist.data(); res.hops = hops.data(); res.nh_words = 4; res.job_status = &status;
+        rc = hspf_run_batch(ctx, g, &jobs, &res, 0);
+        hspf_graph_free(ctx, g);
+        // first-hop atom overflow is irrelevant here: the Vec is rebuilt from parents
+        if (rc == HSPF_E_JOB_STATUS && !(status & ~HSPF_JS_TOO_MANY_ATOMS)) rc = HSPF_OK;
+        if (rc) return rc;
+        return spt_from_planes(f, root, dist.data(), hops.data(), 0, nullptr, nullptr, out);
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
+}  // extern "C"

@@ -38,7 +38,7 @@ constexpr int kThreads = 512;
 constexpr int kMaxOv = 8;          // HSPF_MAX_OVERRIDES
 constexpr int kMaxRootDeg = 256;   // non-HOP root neighbours tracked in smem
 constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
-constexpr uint32_t kGfNoHopTargetNoNh = 1u;
+constexpr uint32_t kGfNoHopTargetNoNh = 1u, kGfHopCount = 2u;
 constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
 
 struct DevGraph {
@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // ======================= phase 2: ECMP parents (pull) ====================
         uint32_t sat_flag = 0;
         for (uint32_t v = tid; v < Vp; v += kThreads) {
-            uint32_t cnt = 0, bd = kInf, bu = kInf, be = kInf;
+            uint32_t cnt = 0, bu = kInf, be = kInf;
+            unsigned long long bkey = ~0ull;   // (distance, id) of the best parent so far
             if (v < V) {
                 const uint32_t dv = dist[v];
                 if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
@@ -347,6 +348,25 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     bool vo = false;
                     for (uint32_t k = 0; k < n_ov; ++k) vo |= (S.ov.head[k] == v);
                     const uint32_t ib = g.irow[v], ie = g.irow[v + 1];
+                    // Hop-count mode: a pseudonode is parented only by the lowest-numbered
+                    // attached router of its level (see HSPF_GF_HOPCOUNT in holo_spf.h).
+                    uint32_t only_u = kInf;
+                    const bool hopcount = g.flags & kGfHopCount;
+                    if (hopcount && !(g.vflags[v] & kVfHop)) {
+                        for (uint32_t i = ib; i < ie; ++i) {
+                            const uint2 sc1 = g.iedge[i];
+                            const uint32_t u = sc1.x, d1 = dist[u];
+                            if (d1 == kInf || !expands(g.vflags[u], u, root)) continue;
+                            uint32_t c = sc1.y;
+                            if (vo) {
+                                const uint32_t e = g.ieid[i];
+                                for (uint32_t q = 0; q < n_ov; ++q)
+                                    if (S.ov.edge[q] == e) c = S.ov.cost[q];
+                                if (c == kInf) continue;
+                            }
+                            if (sat_add(d1, c) == dv) only_u = min(only_u, u);
+                        }
+                    }
                     for (uint32_t i0 = ib; i0 < ie; i0 += 4) {
                         uint2 sc[4];
                         uint32_t du[4];
@@ -360,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                             if (i0 + k >= ie) break;
                             const uint32_t u = sc[k].x;
                             if (du[k] == kInf || !expands(fl[k], u, root)) continue;
+                            if (only_u != kInf && u != only_u) continue;
                             uint32_t c = sc[k].y;
                             uint32_t e = kInf;
                             if (vo) {
@@ -372,7 +393,26 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                             if (e == kInf) e = g.ieid[i0 + k];
                             ++cnt;
                             atomicOr(&dagbit[e >> 5], 1u << (e & 31));
-                            if (du[k] < bd || (du[k] == bd && u < bu)) { bd = du[k]; bu = u; be = e; }
+                            unsigned long long key = ((unsigned long long)du[k] << 32) | u;
+                            if (hopcount && !(fl[k] & kVfHop)) {
+                                // pop order inside a hop-count level is R1, pseudonodes inserted by
+                                // R1, R2, ...: a pseudonode sorts right after its owner router
+                                uint32_t owner = kInf;
+                                for (uint32_t j = g.irow[u]; j < g.irow[u + 1]; ++j) {
+                                    const uint2 s2 = g.iedge[j];
+                                    if (dist[s2.x] != du[k] || !expands(g.vflags[s2.x], s2.x, root)) continue;
+                                    bool dis = false;
+                                    for (uint32_t q = 0; q < n_ov; ++q)
+                                        if (S.ov.edge[q] == g.ieid[j] && S.ov.cost[q] == kInf) dis = true;
+                                    if (!dis) owner = min(owner, s2.x);
+                                }
+                                key = ((unsigned long long)du[k] << 32) | ((unsigned long long)owner) ;
+                                key = (key << 1) | 1ull;           // after the owner router itself
+                                key = (key << 0);
+                            } else if (hopcount) {
+                                key = (key << 1);
+                            }
+                            if (key < bkey || (key == bkey && u < bu)) { bkey = key; bu = u; be = e; }
                         }
                     }
                     if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));

@@ -1,0 +1,237 @@
+"""IS-IS side of the engine from Python: level LSDB images (include/holo_lsdb.h), the
+compute_spt call (holo-isis/src/spf.rs:525-707 replaced by hspf_isis_compute_spt), the
+flattener for batched roots / perturbations, and a synthetic LSDB builder."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .synth import Topology
+
+REACH_LEGACY, REACH_EXT, REACH_MT = 0, 1, 2
+LSPF_OL, LSPF_HAS_PROTOCOLS, LSPF_NLPID_IPV4, LSPF_NLPID_IPV6, LSPF_MT_IPV6_OL = 0x01, 0x02, 0x04, 0x08, 0x10
+METRIC_STANDARD, METRIC_WIDE, METRIC_BOTH = 0, 1, 2
+MT_NONE, MT_STANDARD, MT_IPV6 = 0xFF, 0, 2
+MODE_NORMAL, MODE_HOPCOUNT = 0, 1
+
+REACH_DT = np.dtype([("neighbor", "<u8"), ("metric", "<u4"), ("mt_id", "<u2"), ("kind", "u1"), ("_pad", "u1")], align=True)
+LSP_DT = np.dtype([("lan_id", "<u8"), ("seqno", "<u4"), ("rem_lifetime", "<u2"), ("fragment", "u1"), ("flags", "u1"),
+                   ("reach_off", "<u4"), ("n_reach", "<u4")], align=True)
+VERTEX_DT = np.dtype([("lan_id", "<u8"), ("distance", "<u4"), ("hops", "<u2"), ("_pad", "<u2"), ("par_off", "<u4"),
+                      ("n_par", "<u4"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+
+
+class LevelStruct(C.Structure):
+    _fields_ = [("metric_type", C.c_uint8), ("mt_id", C.c_uint8), ("metric_mode", C.c_uint8),
+                ("ipv4_enabled", C.c_uint8), ("ipv6_enabled", C.c_uint8), ("_pad", C.c_uint8 * 3),
+                ("n_lsps", C.c_uint32), ("lsps", C.c_void_p), ("n_reaches", C.c_uint32), ("reaches", C.c_void_p)]
+
+
+class SptStruct(C.Structure):
+    _fields_ = [("vertices_cap", C.c_uint32), ("n_vertices", C.c_uint32), ("vertices", C.c_void_p),
+                ("parents_cap", C.c_uint32), ("n_parents", C.c_uint32), ("parents", C.c_void_p),
+                ("nexthops_cap", C.c_uint32), ("n_nexthops", C.c_uint32), ("nexthops", C.c_void_p),
+                ("first_hops_cap", C.c_uint32), ("n_first_hops", C.c_uint32), ("first_hops", C.c_void_p),
+                ("second_hops_cap", C.c_uint32), ("n_second_hops", C.c_uint32), ("second_hops", C.c_void_p)]
+
+
+ABI_SIZES = [REACH_DT.itemsize, LSP_DT.itemsize, C.sizeof(LevelStruct), VERTEX_DT.itemsize, C.sizeof(SptStruct)]
+
+
+@dataclass
+class IsisLevel:
+    metric_type: int = METRIC_WIDE
+    mt_id: int = MT_STANDARD
+    metric_mode: int = MODE_NORMAL
+    ipv4_enabled: bool = True
+    ipv6_enabled: bool = False
+    lsps: np.ndarray = field(default_factory=lambda: np.zeros(0, LSP_DT))
+    reaches: np.ndarray = field(default_factory=lambda: np.zeros(0, REACH_DT))
+
+    def as_struct(self) -> LevelStruct:
+        s = LevelStruct()
+        s.metric_type, s.mt_id, s.metric_mode = self.metric_type, self.mt_id, self.metric_mode
+        s.ipv4_enabled, s.ipv6_enabled = int(self.ipv4_enabled), int(self.ipv6_enabled)
+        self.lsps = np.ascontiguousarray(self.lsps, dtype=LSP_DT)
+        self.reaches = np.ascontiguousarray(self.reaches, dtype=REACH_DT)
+        s.n_lsps, s.lsps = len(self.lsps), (self.lsps.ctypes.data if len(self.lsps) else None)
+        s.n_reaches, s.reaches = len(self.reaches), (self.reaches.ctypes.data if len(self.reaches) else None)
+        return s
+
+
+@dataclass
+class IsisSpt:
+    vertices: np.ndarray
+    parents: np.ndarray
+    nexthops: np.ndarray
+    first_hops: np.ndarray
+    second_hops: np.ndarray
+    rc: int = 0
+
+
+def _call_spt(fn, n_vertices_hint: int, n_edges_hint: int, prefix_args):
+    caps = [n_vertices_hint + 1, 2 * n_edges_hint + 16, 1 << 16]
+    for _ in range(3):
+        verts = np.zeros(caps[0], VERTEX_DT)
+        par = np.zeros(caps[1], np.uint32)
+        nh = np.zeros(caps[2], np.uint64)
+        fh = np.zeros(caps[0], np.uint32)
+        sh = np.zeros(caps[0], np.uint32)
+        r = SptStruct()
+        r.vertices_cap, r.vertices = caps[0], verts.ctypes.data
+        r.parents_cap, r.parents = caps[1], par.ctypes.data
+        r.nexthops_cap, r.nexthops = caps[2], nh.ctypes.data
+        r.first_hops_cap, r.first_hops = caps[0], fh.ctypes.data
+        r.second_hops_cap, r.second_hops = caps[0], sh.ctypes.data
+        rc = fn(*prefix_args, C.byref(r))
+        if rc == capi.HSPF_E_NOMEM:
+            caps = [max(caps[0], r.n_vertices), max(caps[1], r.n_parents), max(caps[2], r.n_nexthops)]
+            continue
+        break
+    return IsisSpt(verts[: r.n_vertices].copy(), par[: r.n_parents].copy(), nh[: r.n_nexthops].copy(),
+                   fh[: r.n_first_hops].copy(), sh[: r.n_second_hops].copy(), rc)
+
+
+def _bind(lib):
+    lib.hspf_isis_flatten.argtypes = [C.POINTER(LevelStruct), C.POINTER(C.c_void_p)]
+    lib.hspf_isis_flat_free.argtypes = [C.c_void_p]
+    lib.hspf_isis_flat_free.restype = None
+    lib.hspf_isis_flat_csr.argtypes = [C.c_void_p, C.POINTER(capi.CsrStruct)]
+    lib.hspf_isis_flat_vertices.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint32)]
+    lib.hspf_isis_flat_vertex.argtypes = [C.c_void_p, C.c_uint64]
+    lib.hspf_isis_flat_vertex.restype = C.c_uint32
+    lib.hspf_isis_spt_from_planes.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.POINTER(SptStruct)]
+    lib.hspf_isis_compute_spt.argtypes = [C.c_void_p, C.POINTER(LevelStruct), C.c_uint64, C.POINTER(SptStruct)]
+    return lib
+
+
+def compute_spt(ctx: capi.Context, level: IsisLevel, root_system_id: int) -> IsisSpt:
+    lib = _bind(ctx.lib)
+    s = level.as_struct()
+    res = _call_spt(lib.hspf_isis_compute_spt, len(level.lsps), len(level.reaches),
+                    (ctx.handle, C.byref(s), C.c_uint64(root_system_id)))
+    if res.rc != capi.HSPF_OK:
+        raise capi.HspfError(res.rc, ctx.last_error())
+    return res
+
+
+class Flat:
+    def __init__(self, level: IsisLevel):
+        self.lib = _bind(capi.load_library())
+        self.level = level
+        self._s = level.as_struct()
+        h = C.c_void_p()
+        rc = self.lib.hspf_isis_flatten(C.byref(self._s), C.byref(h))
+        if rc != capi.HSPF_OK:
+            raise capi.HspfError(rc, "hspf_isis_flatten failed")
+        self.handle = h
+        cs = capi.CsrStruct()
+        self.lib.hspf_isis_flat_csr(h, C.byref(cs))
+        V, E = cs.n_vertices, cs.n_edges
+        as_np = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt).copy() if n else np.zeros(0, dt)
+        self.csr = capi.Csr(as_np(cs.row_ptr, V + 1, np.uint32), as_np(cs.col, E, np.uint32),
+                            as_np(cs.cost, E, np.uint32), as_np(cs.vflags, V, np.uint8),
+                            reject_above=cs.reject_above, saturate_at=cs.saturate_at, flags=cs.flags, delta=cs.delta)
+        ids, n = C.POINTER(C.c_uint64)(), C.c_uint32()
+        self.lib.hspf_isis_flat_vertices(h, C.byref(ids), C.byref(n))
+        self.ids = as_np(ids, n.value, np.uint64)
+
+    def vertex(self, lan_id: int) -> int:
+        return int(self.lib.hspf_isis_flat_vertex(self.handle, C.c_uint64(lan_id)))
+
+    def spt_from_planes(self, root_vertex: int, dist: np.ndarray, hops: np.ndarray, overrides=()) -> IsisSpt:
+        dist = np.ascontiguousarray(dist, np.uint32)
+        hops = np.ascontiguousarray(hops, np.uint16)
+        ove = np.asarray([e for e, _ in overrides] or [0], np.uint32)
+        ovc = np.asarray([c for _, c in overrides] or [0], np.uint32)
+        res = _call_spt(self.lib.hspf_isis_spt_from_planes, self.csr.n_vertices, self.csr.n_edges,
+                        (self.handle, C.c_uint32(root_vertex), dist.ctypes.data, hops.ctypes.data,
+                         C.c_uint32(len(overrides)), ove.ctypes.data, ovc.ctypes.data))
+        if res.rc != capi.HSPF_OK:
+            raise capi.HspfError(res.rc, "hspf_isis_spt_from_planes failed")
+        return res
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.hspf_isis_flat_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------ synthetic
+SYSID_BASE = 0x000000000001
+
+
+def sysid(i: int) -> int:
+    return SYSID_BASE + int(i)
+
+
+def synth_level(t: Topology, metric_type: int = METRIC_WIDE, mt_id: int = MT_STANDARD, metric_mode: int = MODE_NORMAL,
+                max_reach_per_fragment: int = 0, overload=(), no_protocols=()) -> IsisLevel:
+    """IS-IS level LSDB for topology `t`: router i has system id 1+i and one LSP (split
+    into fragments of `max_reach_per_fragment` entries when > 0); LAN k is a pseudonode
+    of its first member.  Wide metrics use TLV 22, standard TLV 2 (metric clipped to
+    63), METRIC_BOTH advertises both (parallel edges, spf.rs:1005-1120)."""
+    R = t.n_routers
+    per = [[] for _ in range(R)]
+    for k in range(t.n_p2p):
+        a, b = int(t.p2p_a[k]), int(t.p2p_b[k])
+        per[a].append((sysid(b) << 8, int(t.p2p_cost_ab[k])))
+        per[b].append((sysid(a) << 8, int(t.p2p_cost_ba[k])))
+    pn_lsps = []
+    n_pn = [0] * R
+    for members, costs in t.lans:
+        dr = members[0]
+        n_pn[dr] += 1
+        assert n_pn[dr] < 256
+        pn_id = (sysid(dr) << 8) | n_pn[dr]
+        for m, c in zip(members, costs):
+            per[m].append((pn_id, int(c)))
+        pn_lsps.append((pn_id, [(sysid(m) << 8, 0) for m in members]))
+    lsps, reaches = [], []
+
+    def add_reach(nbr, metric):
+        out = []
+        if metric_type in (METRIC_STANDARD, METRIC_BOTH):
+            out.append((nbr, min(metric, 63), 0, REACH_LEGACY, 0))
+        if metric_type in (METRIC_WIDE, METRIC_BOTH):
+            out.append((nbr, metric, 0, REACH_EXT, 0))
+        if mt_id == MT_IPV6:
+            out.append((nbr, metric, MT_IPV6, REACH_MT, 0))
+        return out
+
+    def emit(lan_id, entries, flags):
+        chunks = [entries]
+        if max_reach_per_fragment > 0:
+            chunks = [entries[i:i + max_reach_per_fragment] for i in range(0, len(entries), max_reach_per_fragment)] or [[]]
+        for frag, ch in enumerate(chunks):
+            rr = [x for (nbr, m) in ch for x in add_reach(nbr, m)]
+            lsps.append((lan_id, 1, 1200, frag, flags if frag == 0 else 0, len(reaches), len(rr)))
+            reaches.extend(rr)
+
+    for i in range(R):
+        fl = LSPF_HAS_PROTOCOLS | LSPF_NLPID_IPV4
+        if i in overload:
+            fl |= LSPF_OL | LSPF_MT_IPV6_OL
+        if i in no_protocols:
+            fl &= ~(LSPF_HAS_PROTOCOLS | LSPF_NLPID_IPV4)
+        emit(sysid(i) << 8, per[i], fl)
+    for pn_id, ent in pn_lsps:
+        emit(pn_id, ent, 0)
+    lv = IsisLevel(metric_type=metric_type, mt_id=mt_id, metric_mode=metric_mode)
+    la = np.zeros(len(lsps), LSP_DT)
+    for i, x in enumerate(lsps):
+        la[i] = x
+    order = np.lexsort((la["fragment"], la["lan_id"]))
+    lv.lsps = la[order]
+    ra = np.zeros(len(reaches), REACH_DT)
+    for i, x in enumerate(reaches):
+        ra[i] = x
+    lv.reaches = ra
+    return lv

@@ -83,6 +83,11 @@ ABI_SIZES = [
 ]
 
 
+def abi_sizes_expected():
+    from . import isis
+    return ABI_SIZES + isis.ABI_SIZES
+
+
 def abi_sizes_from_library():
     lib = capi.load_library()
     out = (C.c_uint32 * 64)()

@@ -68,6 +68,16 @@ extern "C" {
  * (root -> transit network yields (iface, None), ospfv2/spf.rs:297-303).      */
 #define HSPF_GF_NOHOP_TARGET_NO_NEXTHOP 0x01u
 
+/* Hop-count topology (holo-isis MetricMode::HopCount, flooding/manet.rs:59,
+ * spf.rs:1122-1138): every HOP -> non-HOP edge costs 0 and every other edge costs
+ * 1 (checked at upload).  Zero-cost links out of HOP vertices make the reference's
+ * result depend on pop order, but here in one simple way the device reproduces
+ * exactly: a pseudonode enters the candidate list when the lowest-numbered
+ * attached router of its distance level is expanded and is popped before the
+ * next router ((d, false, ..) < (d, true, ..)), so that router is its only ECMP
+ * parent.  Without this flag such graphs are refused (HSPF_E_NEEDS_ORACLE). */
+#define HSPF_GF_HOPCOUNT 0x02u
+
 #define HSPF_COST_DISABLED 0xFFFFFFFFu /* edge override: remove the edge       */
 #define HSPF_DIST_INF      0xFFFFFFFFu /* result: vertex is not on the SPT     */
 #define HSPF_NO_PARENT     0xFFFFFFFFu

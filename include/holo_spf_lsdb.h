@@ -57,6 +57,32 @@ uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t 
  */
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
 
+/* ---- IS-IS -------------------------------------------------------------------
+ *   hspf_isis_compute_spt  <->  compute_spt(level, root_system_id, local = false,
+ *                               mt_id, metric_mode, ..)  holo-isis/src/spf.rs:525-707,
+ *                               the call made per MT topology by compute_spf
+ *                               (spf.rs:742-757) and per adjacency by
+ *                               flooding::manet::init_cache (flooding/manet.rs:47-69)
+ *   hspf_isis_flatten + hspf_run_batch + hspf_isis_spt_from_planes: the same, for
+ *                               many roots / what-if perturbations per launch.
+ */
+typedef struct hspf_isis_flat hspf_isis_flat;
+
+int hspf_isis_flatten(const hl_isis_level *lvl, hspf_isis_flat **out);
+void hspf_isis_flat_free(hspf_isis_flat *flat);
+/* CSR view: reject_above = 1023 / 0xFE000000 by metric type, flags =
+ * HSPF_GF_NOHOP_TARGET_NO_NEXTHOP (| HSPF_GF_HOPCOUNT in hop-count mode). */
+int hspf_isis_flat_csr(const hspf_isis_flat *flat, hspf_csr *out);
+int hspf_isis_flat_vertices(const hspf_isis_flat *flat, const uint64_t **lan_ids, uint32_t *n_vertices);
+uint32_t hspf_isis_flat_vertex(const hspf_isis_flat *flat, uint64_t lan_id);
+/* Rebuild the reference's Spt (ordered ECMP parents, next-hop Vecs, first/second
+ * hops) for one job from its `dist` and `hops` result planes (host pointers). */
+int hspf_isis_spt_from_planes(const hspf_isis_flat *flat, uint32_t root_vertex, const uint32_t *dist,
+                              const uint16_t *hops, uint32_t n_ov, const uint32_t *ov_edge,
+                              const uint32_t *ov_cost, hl_isis_spt *out);
+/* One SPT for `root_system_id` (48-bit system id). */
+int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root_system_id, hl_isis_spt *out);
+
 /* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
  * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
  * foreign binding verify its struct layouts at load time. */

@@ -91,3 +91,13 @@ def ospfv2_run_area(area):
     L = lib()
     L.oracle_ospfv2_run_area.argtypes = [C.POINTER(ospfv2.AreaStruct), C.POINTER(ospfv2.ResultStruct)]
     return ospfv2._call_run_area(L.oracle_ospfv2_run_area, area)
+
+
+def isis_compute_spt(level, root_system_id: int):
+    """Reference-faithful compute_spt (local = false) over an IS-IS level image."""
+    from holo_b200 import isis
+    L = lib()
+    L.oracle_isis_compute_spt.argtypes = [C.POINTER(isis.LevelStruct), C.c_uint64, C.POINTER(isis.SptStruct)]
+    s = level.as_struct()
+    return isis._call_spt(L.oracle_isis_compute_spt, len(level.lsps), len(level.reaches),
+                          (C.byref(s), C.c_uint64(root_system_id)))
