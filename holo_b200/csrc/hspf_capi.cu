@@ -5,6 +5,7 @@
 // spf_batch_kernel on the device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -38,6 +39,8 @@ struct hspf_ctx {
     void *stage = nullptr;   size_t stage_bytes = 0;    // device staging of results (host-pointer mode)
     void *h_pin = nullptr;   size_t h_pin_bytes = 0;    // pinned bounce buffer
     void *scratch = nullptr; size_t scratch_bytes = 0;  // planes the caller did not ask for
+    unsigned long long *d_prof = nullptr; int prof_rows = 0;  // optional phase counters (debug)
+    bool prof_enabled = false;
 };
 
 namespace {
@@ -70,23 +73,26 @@ int grow(hspf_ctx *ctx, void **p, size_t *have, size_t need, bool pinned = false
     return HSPF_OK;
 }
 
-template <typename VT>
+template <typename VT, bool S>
 int launch(hspf_ctx *ctx, const BatchArgs &args, size_t smem, int grid) {
-    if (smem > 0) {
-        CK(cudaFuncSetAttribute(spf_batch_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char *co = getenv("HSPF_SMEM_CARVEOUT")) {   // tuning knob (experiments only)
+        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
     }
-    spf_batch_kernel<VT><<<grid, kThreads, smem, ctx->stream>>>(args);
+    if (smem > 0) {
+        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    spf_batch_kernel<VT, S><<<grid, kThreads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     ctx->launches++;
     return HSPF_OK;
 }
 
-template <typename VT>
+template <typename VT, bool S>
 int max_ctas_per_sm(size_t smem) {
     int n = 0;
     if (smem > 0)
-        cudaFuncSetAttribute(spf_batch_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spf_batch_kernel<VT>, kThreads, smem) != cudaSuccess) n = 1;
+        cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spf_batch_kernel<VT, S>, kThreads, smem) != cudaSuccess) n = 1;
     return n < 1 ? 1 : n;
 }
 
@@ -117,8 +123,12 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
     a.nhw = out->nh_words;
     a.job_counter = ctx->d_counter;
 
-    int per_sm = in_smem ? (q16 ? max_ctas_per_sm<uint16_t>(sb) : max_ctas_per_sm<uint32_t>(sb))
-                         : (q16 ? max_ctas_per_sm<uint16_t>(0) : max_ctas_per_sm<uint32_t>(0));
+    int per_sm = in_smem ? (q16 ? max_ctas_per_sm<uint16_t, true>(sb) : max_ctas_per_sm<uint32_t, true>(sb))
+                         : (q16 ? max_ctas_per_sm<uint16_t, false>(0) : max_ctas_per_sm<uint32_t, false>(0));
+    if (const char *lim = getenv("HSPF_CTAS_PER_SM")) {   // tuning knob (experiments only)
+        int v = atoi(lim);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     int grid = ctx->sm_count * per_sm;
     if ((uint32_t)grid > jobs->n_jobs) grid = (int)jobs->n_jobs;
     if (grid < 1) grid = 1;
@@ -129,9 +139,19 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         a.ws = static_cast<uint8_t *>(ctx->ws);
         a.ws_stride = sb;
     }
+    if (ctx->prof_enabled) {
+        if (ctx->prof_rows < grid) {
+            if (ctx->d_prof) cudaFree(ctx->d_prof);
+            CK(cudaMalloc(&ctx->d_prof, (size_t)grid * 8 * sizeof(unsigned long long)));
+            ctx->prof_rows = grid;
+        }
+        CK(cudaMemsetAsync(ctx->d_prof, 0, (size_t)ctx->prof_rows * 8 * sizeof(unsigned long long), ctx->stream));
+        a.prof = ctx->d_prof;
+    }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), ctx->stream));
-    return q16 ? launch<uint16_t>(ctx, a, in_smem ? sb : 0, grid)
-               : launch<uint32_t>(ctx, a, in_smem ? sb : 0, grid);
+    if (in_smem)
+        return q16 ? launch<uint16_t, true>(ctx, a, sb, grid) : launch<uint32_t, true>(ctx, a, sb, grid);
+    return q16 ? launch<uint16_t, false>(ctx, a, 0, grid) : launch<uint32_t, false>(ctx, a, 0, grid);
 }
 
 struct Planes {   // byte sizes of the result planes of a batch
@@ -187,6 +207,7 @@ void hspf_ctx_destroy(hspf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_prof) cudaFree(ctx->d_prof);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -199,6 +220,22 @@ const char *hspf_last_error(const hspf_ctx *ctx) { return ctx ? ctx->err.c_str()
 void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[8]) {
+    if (!ctx) return HSPF_E_INVAL;
+    if (out) {
+        for (int k = 0; k < 8; ++k) out[k] = 0;
+        if (ctx->d_prof && ctx->prof_rows > 0) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::vector<unsigned long long> h((size_t)ctx->prof_rows * 8);
+            CK(cudaMemcpy(h.data(), ctx->d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int r = 0; r < ctx->prof_rows; ++r)
+                for (int k = 0; k < 8; ++k) out[k] += h[(size_t)r * 8 + k];
+        }
+    }
+    ctx->prof_enabled = enable != 0;
+    return HSPF_OK;
+}
 
 int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
     if (!ctx || !g || !out) return HSPF_E_INVAL;

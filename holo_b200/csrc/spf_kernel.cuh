@@ -37,6 +37,8 @@ constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThreads = 512;
 constexpr int kMaxOv = 8;          // HSPF_MAX_OVERRIDES
 constexpr int kMaxRootDeg = 256;   // non-HOP root neighbours tracked in smem
+constexpr int kWarps = kThreads / 32;
+constexpr int kStage = 64;         // DAG edges staged per warp pass in the Kahn phase
 constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
 constexpr uint32_t kGfNoHopTargetNoNh = 1u, kGfHopCount = 2u;
 constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
@@ -54,7 +56,9 @@ struct DevGraph {
 
 struct Layout {   // byte offsets into the per-CTA state block
     uint32_t dist, qa, qb, pend, bm0, bm1;     // SSSP
+    uint32_t fl_hop, fl_leaf, fl_lur;          // vertex-flag bitmaps (whole kernel)
     uint32_t kq0, kq1, hops, dagbit, fpbit;    // parents + Kahn
+    uint32_t stage_e, stage_k;                 // Kahn per-warp staging [warps][kStage]
     uint32_t total;
 };
 
@@ -76,6 +80,7 @@ struct BatchArgs {
     uint8_t *ws;              // per-CTA global workspace when state does not fit smem
     size_t ws_stride;         // bytes per CTA (0: state in smem)
     uint32_t *job_counter;    // dynamic job fetch
+    unsigned long long *prof; // optional [gridDim][8] per-phase cycle counters (debug), may be null
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -94,9 +99,21 @@ inline Layout make_layout(uint32_t V, uint32_t E, int qsz) {
     L.pend = (uint32_t)o; o += sz_pend;
     L.bm0 = (uint32_t)o; o += sz_bm;
     L.bm1 = (uint32_t)o; o += sz_bm;
+    L.fl_hop = (uint32_t)o; o += sz_bm;
+    L.fl_leaf = (uint32_t)o; o += sz_bm;
+    L.fl_lur = (uint32_t)o; o += sz_bm;
     // parents/Kahn arrays: alias onto SSSP arrays that are dead by then, else append
-    if (2 * sz_eb <= sz_q) { L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb; }
-    else { L.dagbit = (uint32_t)o; o += sz_eb; L.fpbit = (uint32_t)o; o += sz_eb; }
+    const size_t sz_se = (size_t)kWarps * kStage * 4, sz_sk = align_up((size_t)kWarps * kStage, 16);
+    if (2 * sz_eb + sz_se + sz_sk <= sz_q) {
+        L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb;
+        L.stage_e = L.fpbit + (uint32_t)sz_eb; L.stage_k = L.stage_e + (uint32_t)sz_se;
+    } else if (2 * sz_eb <= sz_q) {
+        L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb;
+        L.stage_e = (uint32_t)o; o += sz_se; L.stage_k = (uint32_t)o; o += sz_sk;
+    } else {
+        L.dagbit = (uint32_t)o; o += sz_eb; L.fpbit = (uint32_t)o; o += sz_eb;
+        L.stage_e = (uint32_t)o; o += sz_se; L.stage_k = (uint32_t)o; o += sz_sk;
+    }
     L.hops = L.qb;                                   // sz_hops <= sz_q always (qsz >= 2)
     if (2 * sz_q <= sz_dist) { L.kq0 = L.dist; L.kq1 = L.dist + (uint32_t)sz_q; }
     else { L.kq0 = (uint32_t)o; o += sz_q; L.kq1 = (uint32_t)o; o += sz_q; }
@@ -144,7 +161,22 @@ __device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) 
     return !((fl & kVfLeaf) || ((fl & kVfLeafUnlessRoot) && u != root));
 }
 
-template <typename VT>
+// Phase timing (debug aid, enabled by passing BatchArgs.prof): thread 0 adds the
+// cycles since the previous mark to slot `k` of its CTA's row.
+#define HSPF_MARK(k)                                                             \
+    do {                                                                         \
+        if (a.prof && tid == 0) {                                                \
+            const long long now_ = clock64();                                    \
+            a.prof[(size_t)blockIdx.x * 8 + (k)] += (unsigned long long)(now_ - t_mark); \
+            t_mark = now_;                                                       \
+        }                                                                        \
+    } while (0)
+
+// kSmemState: the per-job state block lives in dynamic shared memory (the normal
+// case).  It is a template parameter, not a runtime select, so that the compiler
+// can prove the address space and emit LDS/STS/ATOMS instead of generic LD/ST/ATOM
+// (generic atomics that land in the shared window are an order of magnitude slower).
+template <typename VT, bool kSmemState>
 __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ Small S;
@@ -157,7 +189,9 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     const uint32_t nbw = (Vp + 31) / 32;
     const uint32_t nbe = (g.E + 31) / 32;
 
-    uint8_t *base = a.ws_stride ? a.ws + (size_t)blockIdx.x * a.ws_stride : smem_raw;
+    uint8_t *base;
+    if constexpr (kSmemState) base = smem_raw;
+    else base = a.ws + (size_t)blockIdx.x * a.ws_stride;
     uint32_t *dist = reinterpret_cast<uint32_t *>(base + L.dist);
     VT *qa = reinterpret_cast<VT *>(base + L.qa);
     VT *qb = reinterpret_cast<VT *>(base + L.qb);
@@ -165,6 +199,11 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     uint16_t *pend = reinterpret_cast<uint16_t *>(base + L.pend);
     uint32_t *bm0 = reinterpret_cast<uint32_t *>(base + L.bm0);
     uint32_t *bm1 = reinterpret_cast<uint32_t *>(base + L.bm1);
+    uint32_t *fl_hop = reinterpret_cast<uint32_t *>(base + L.fl_hop);
+    uint32_t *fl_leaf = reinterpret_cast<uint32_t *>(base + L.fl_leaf);
+    uint32_t *fl_lur = reinterpret_cast<uint32_t *>(base + L.fl_lur);
+    uint32_t *stage_e = reinterpret_cast<uint32_t *>(base + L.stage_e) + (threadIdx.x >> 5) * kStage;
+    uint8_t *stage_k = reinterpret_cast<uint8_t *>(base + L.stage_k) + (threadIdx.x >> 5) * kStage;
     VT *kq0 = reinterpret_cast<VT *>(base + L.kq0);
     VT *kq1 = reinterpret_cast<VT *>(base + L.kq1);
     uint16_t *hops_s = reinterpret_cast<uint16_t *>(base + L.hops);
@@ -172,6 +211,28 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     uint32_t *fpbit = reinterpret_cast<uint32_t *>(base + L.fpbit);
 
     const uint32_t nhw = a.nhw;
+    long long t_mark = clock64();
+    const uint32_t lane = threadIdx.x & 31;
+
+    // vertex flags as three V-bit bitmaps in shared memory (built once per CTA)
+    for (uint32_t w = tid; w < nbw; w += kThreads) {
+        uint32_t h = 0, l = 0, r = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t v = w * 32 + b;
+            if (v < V) {
+                const uint32_t f = g.vflags[v];
+                h |= ((f & kVfHop) ? 1u : 0u) << b;
+                l |= ((f & kVfLeaf) ? 1u : 0u) << b;
+                r |= ((f & kVfLeafUnlessRoot) ? 1u : 0u) << b;
+            }
+        }
+        fl_hop[w] = h; fl_leaf[w] = l; fl_lur[w] = r;
+    }
+    auto is_hop = [&](uint32_t v) -> bool { return (fl_hop[v >> 5] >> (v & 31)) & 1u; };
+    auto vexpands = [&](uint32_t u, uint32_t root_) -> bool {
+        const uint32_t b = 1u << (u & 31);
+        return !((fl_leaf[u >> 5] & b) || ((fl_lur[u >> 5] & b) && u != root_));
+    };
 
     for (;;) {
         // ---- fetch next job -------------------------------------------------
@@ -247,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         }
         __syncthreads();
 
+        HSPF_MARK(0);   // job fetch + init
         // ======================= phase 1: SSSP ==================================
         const uint32_t delta = g.delta ? g.delta : 1u;
         uint32_t hi_thr = delta;       // near bucket is [*, hi_thr)
@@ -257,42 +319,63 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             for (;;) {
                 const uint32_t n_cur = S.cnt[p];
                 if (n_cur == 0) break;
-                for (uint32_t i = tid; i < n_cur; i += kThreads) {
-                    const uint32_t u = qcur[i];
-                    const uint32_t du = dist[u];
-                    if (!expands(g.vflags[u], u, root)) continue;
-                    bool uo = false;
-                    for (uint32_t k = 0; k < n_ov; ++k) uo |= (S.ov.tail[k] == u);
-                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
-                    for (uint32_t e0 = eb; e0 < ee; e0 += 4) {
-                        uint2 ec[4];
-                        uint32_t dv[4];
+                // Warp-cooperative expansion: 32 frontier vertices per warp pass; their edge
+                // lists are concatenated and relaxed 32 edges at a time, one per lane, so a
+                // pass costs one row fetch + ceil(edges/32) edge fetches instead of
+                // max-degree sequential fetches with mostly idle lanes.
+                for (uint32_t i0 = (tid >> 5) * 32; i0 < n_cur; i0 += kThreads) {
+                    const uint32_t i = i0 + lane;
+                    uint32_t u = 0, du = 0, eb = 0, deg = 0;
+                    if (i < n_cur) {
+                        u = qcur[i];
+                        du = dist[u];
+                        if (vexpands(u, root)) { eb = g.row[u]; deg = g.row[u + 1] - eb; }
+                    }
+                    uint32_t incl = deg;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) ec[k] = (e0 + k < ee) ? g.edge[e0 + k] : make_uint2(u, kInf);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += t;
+                    }
+                    const uint32_t excl = incl - deg;
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        // owner lane k: the last lane whose exclusive prefix is <= j
+                        uint32_t k = 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) dv[k] = dist[ec[k].x];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (e0 + k >= ee) break;
-                            uint32_t c = ec[k].y;
-                            if (uo) {
-                                for (uint32_t q = 0; q < n_ov; ++q)
-                                    if (S.ov.edge[q] == e0 + k) c = S.ov.cost[q];
-                                if (c == kInf) continue;
-                            }
-                            const uint32_t nd = sat_add(du, c);
-                            if (nd > g.reject_above || nd >= dv[k]) continue;
-                            const uint32_t v = ec[k].x;
-                            const uint32_t old = atomicMin(&dist[v], nd);
-                            if (nd < old && nd < hi_thr) {
-                                const uint32_t bit = 1u << (v & 31);
-                                const uint32_t ob = atomicOr(&bm_next[v >> 5], bit);
-                                if (!(ob & bit)) q_push(qnext, &S.cnt[p ^ 1], v);
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const uint32_t cand = k + o;
+                            const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31);
+                            if (cand < 32 && ex <= j) k = cand;
+                        }
+                        const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
+                        const uint32_t k_ex = __shfl_sync(0xffffffffu, excl, k);
+                        const uint32_t k_du = __shfl_sync(0xffffffffu, du, k);
+                        const uint32_t k_u = __shfl_sync(0xffffffffu, u, k);
+                        if (j < total) {
+                            const uint32_t e = k_eb + (j - k_ex);
+                            const uint2 ec = g.edge[e];
+                            uint32_t c = ec.y;
+                            for (uint32_t q = 0; q < n_ov; ++q)
+                                if (S.ov.tail[q] == k_u && S.ov.edge[q] == e) c = S.ov.cost[q];
+                            if (c != kInf) {
+                                const uint32_t nd = sat_add(k_du, c);
+                                const uint32_t v = ec.x;
+                                if (nd <= g.reject_above && nd < dist[v]) {
+                                    const uint32_t old = atomicMin(&dist[v], nd);
+                                    if (nd < old && nd < hi_thr) {
+                                        const uint32_t bit = 1u << (v & 31);
+                                        const uint32_t ob = atomicOr(&bm_next[v >> 5], bit);
+                                        if (!(ob & bit)) q_push(qnext, &S.cnt[p ^ 1], v);
+                                    }
+                                }
                             }
                         }
                     }
                 }
                 __syncthreads();
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 7] += 1;   // SSSP rounds
                 // every thread has consumed S.cnt[p]; recycle it for the round after next
                 if (tid == 0) S.cnt[p] = 0;
                 // the bitmap that guarded this round's queue becomes the next guard
@@ -331,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             }
             if (done) break;
         }
+        HSPF_MARK(1);   // SSSP
         // SSSP done: qa/qb/bm0/bm1 are dead, dist is final.
         for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
         for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
@@ -352,11 +436,11 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     // attached router of its level (see HSPF_GF_HOPCOUNT in holo_spf.h).
                     uint32_t only_u = kInf;
                     const bool hopcount = g.flags & kGfHopCount;
-                    if (hopcount && !(g.vflags[v] & kVfHop)) {
+                    if (hopcount && !is_hop(v)) {
                         for (uint32_t i = ib; i < ie; ++i) {
                             const uint2 sc1 = g.iedge[i];
                             const uint32_t u = sc1.x, d1 = dist[u];
-                            if (d1 == kInf || !expands(g.vflags[u], u, root)) continue;
+                            if (d1 == kInf || !vexpands(u, root)) continue;
                             uint32_t c = sc1.y;
                             if (vo) {
                                 const uint32_t e = g.ieid[i];
@@ -374,12 +458,12 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
 #pragma unroll
                         for (int k = 0; k < 4; ++k) sc[k] = (i0 + k < ie) ? g.iedge[i0 + k] : make_uint2(v, kInf);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { du[k] = dist[sc[k].x]; fl[k] = g.vflags[sc[k].x]; }
+                        for (int k = 0; k < 4; ++k) { du[k] = dist[sc[k].x]; fl[k] = is_hop(sc[k].x) ? kVfHop : 0u; }
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (i0 + k >= ie) break;
                             const uint32_t u = sc[k].x;
-                            if (du[k] == kInf || !expands(fl[k], u, root)) continue;
+                            if (du[k] == kInf || !vexpands(u, root)) continue;
                             if (only_u != kInf && u != only_u) continue;
                             uint32_t c = sc[k].y;
                             uint32_t e = kInf;
@@ -400,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 uint32_t owner = kInf;
                                 for (uint32_t j = g.irow[u]; j < g.irow[u + 1]; ++j) {
                                     const uint2 s2 = g.iedge[j];
-                                    if (dist[s2.x] != du[k] || !expands(g.vflags[s2.x], s2.x, root)) continue;
+                                    if (dist[s2.x] != du[k] || !vexpands(s2.x, root)) continue;
                                     bool dis = false;
                                     for (uint32_t q = 0; q < n_ov; ++q)
                                         if (S.ov.edge[q] == g.ieid[j] && S.ov.cost[q] == kInf) dis = true;
@@ -424,12 +508,14 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         }
         if (sat_flag) atomicOr(&S.status, kJsSaturated);
         __syncthreads();
+        HSPF_MARK(2);   // parents pull
         // distances are final: stream them out, then the region is reused by the Kahn queues
         for (uint32_t v = tid; v < V; v += kThreads) o_dist[v] = dist[v];
         __syncthreads();
         if (tid == 0) { S.cnt[0] = 1; S.cnt[1] = 0; kq0[0] = (VT)root; }
         __syncthreads();
 
+        HSPF_MARK(3);   // dist write-back
         // ======================= phase 3: Kahn push over the ECMP DAG ============
         {
             VT *kcur = kq0, *knext = kq1;
@@ -437,50 +523,86 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             for (;;) {
                 const uint32_t n_cur = S.cnt[p];
                 if (n_cur == 0) break;
-                for (uint32_t i = tid; i < n_cur; i += kThreads) {
-                    const uint32_t u = kcur[i];
-                    const uint32_t hu = hops_s[u];
-                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
-                    uint64_t nhu[4] = {0, 0, 0, 0};
-                    uint32_t abase = 0;
+                // Warp-cooperative: each lane owns one frontier vertex, finds its DAG out-edges
+                // with shared-memory bit tests only, the warp compacts them into its staging
+                // buffer, then relaxes them edge-parallel (one edge per lane).
+                for (uint32_t i0 = (tid >> 5) * 32; i0 < n_cur; i0 += kThreads) {
+                    const uint32_t i = i0 + lane;
+                    uint32_t u = 0, hu = 0, eb = 0, ee = 0, abase = 0;
                     bool atoms_ok = true;
-                    if (hu != 0) {
-                        for (uint32_t w = 0; w < nhw; ++w) nhu[w] = __ldcg(&o_nh[(size_t)u * nhw + w]);
-                    } else if (u != root) {
-                        // non-HOP vertex directly attached to the root
-                        atoms_ok = false;
-                        for (uint32_t k = 0; k < S.n_roottab; ++k)
-                            if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
-                        if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
-                    }
-                    for (uint32_t e = eb; e < ee; ++e) {
-                        if (!((dagbit[e >> 5] >> (e & 31)) & 1u)) continue;
-                        const uint32_t v = g.edge[e].x;
-                        const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
-                        if (hu == 0) {
-                            const uint32_t fv = g.vflags[v];
-                            if (!((g.flags & kGfNoHopTargetNoNh) && !(fv & kVfHop)) && atoms_ok) {
-                                const uint32_t atom = abase + (e - eb);
-                                if (atom < 64u * nhw)
-                                    atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
-                                             1ull << (atom & 63));
-                                else
-                                    atomicOr(&S.status, kJsTooManyAtoms);
-                            }
-                            if (is_fp) hops_s[v] = (uint16_t)(fv & kVfHop);
-                        } else {
-                            for (uint32_t w = 0; w < nhw; ++w)
-                                if (nhu[w])
-                                    atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), nhu[w]);
-                            if (is_fp) hops_s[v] = (uint16_t)min(hu + (g.vflags[v] & kVfHop), 0xFFFFu);
+                    if (i < n_cur) {
+                        u = kcur[i];
+                        hu = hops_s[u];
+                        eb = g.row[u]; ee = g.row[u + 1];
+                        if (hu == 0 && u != root) {
+                            atoms_ok = false;   // non-HOP vertex directly attached to the root
+                            for (uint32_t k = 0; k < S.n_roottab; ++k)
+                                if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
+                            if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
                         }
-                        // packed u16 decrement; the thread that takes it to zero owns v
-                        const uint32_t sh = (v & 1) * 16;
-                        const uint32_t oldw = atomicSub(&pend32[v >> 1], 1u << sh);
-                        if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(knext, &S.cnt[p ^ 1], v);
+                    }
+                    uint32_t nd_edges = 0;
+                    for (uint32_t e = eb; e < ee; ++e) nd_edges += (dagbit[e >> 5] >> (e & 31)) & 1u;
+                    uint32_t incl = nd_edges;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += t;
+                    }
+                    const uint32_t excl = incl - nd_edges;
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    for (uint32_t w0 = 0; w0 < total; w0 += kStage) {
+                        // stage the window [w0, w0 + kStage) of this warp's DAG edges
+                        uint32_t pos = excl;
+                        for (uint32_t e = eb; e < ee; ++e) {
+                            if (!((dagbit[e >> 5] >> (e & 31)) & 1u)) continue;
+                            if (pos >= w0 && pos < w0 + kStage) { stage_e[pos - w0] = e; stage_k[pos - w0] = (uint8_t)lane; }
+                            ++pos;
+                        }
+                        __syncwarp();
+                        const uint32_t wn = min((uint32_t)kStage, total - w0);
+                        for (uint32_t j0 = 0; j0 < wn; j0 += 32) {
+                            const uint32_t j = j0 + lane;
+                            const bool act = j < wn;
+                            const uint32_t e = act ? stage_e[j] : 0u;
+                            const uint32_t k = act ? stage_k[j] : 0u;
+                            const uint32_t k_u = __shfl_sync(0xffffffffu, u, k);
+                            const uint32_t k_hu = __shfl_sync(0xffffffffu, hu, k);
+                            const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
+                            const uint32_t k_ab = __shfl_sync(0xffffffffu, abase, k);
+                            const uint32_t k_ok = __shfl_sync(0xffffffffu, (uint32_t)atoms_ok, k);
+                            if (act) {
+                                const uint32_t v = g.edge[e].x;
+                                const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
+                                const uint32_t hv = is_hop(v) ? 1u : 0u;
+                                if (k_hu == 0) {
+                                    if (!((g.flags & kGfNoHopTargetNoNh) && !hv) && k_ok) {
+                                        const uint32_t atom = k_ab + (e - k_eb);
+                                        if (atom < 64u * nhw)
+                                            atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
+                                                     1ull << (atom & 63));
+                                        else
+                                            atomicOr(&S.status, kJsTooManyAtoms);
+                                    }
+                                    if (is_fp) hops_s[v] = (uint16_t)hv;
+                                } else {
+                                    for (uint32_t w = 0; w < nhw; ++w) {
+                                        const uint64_t x = __ldcg(&o_nh[(size_t)k_u * nhw + w]);
+                                        if (x) atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), x);
+                                    }
+                                    if (is_fp) hops_s[v] = (uint16_t)min(k_hu + hv, 0xFFFFu);
+                                }
+                                // packed u16 decrement; the thread that takes it to zero owns v
+                                const uint32_t sh = (v & 1) * 16;
+                                const uint32_t oldw = atomicSub(&pend32[v >> 1], 1u << sh);
+                                if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(knext, &S.cnt[p ^ 1], v);
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
                 __syncthreads();
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 6] += 1;   // Kahn rounds
                 if (tid == 0) S.cnt[p] = 0;
                 { VT *t = kcur; kcur = knext; knext = t; }
                 p ^= 1;
@@ -489,9 +611,11 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         }
         __syncthreads();
 
+        HSPF_MARK(4);   // Kahn
         // ======================= write-back ======================================
         for (uint32_t v = tid; v < V; v += kThreads) o_hops[v] = hops_s[v];
         if (tid == 0) a.out_status[job] = S.status;
+        HSPF_MARK(5);   // hops write-back
     }
 }
 

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Per-phase SM-cycle breakdown of spf_batch_kernel on the C2 workload (debug aid)."""
+import ctypes as C
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from holo_b200 import capi, synth  # noqa: E402
+
+delta = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+t = synth.random_topology(10000, 40000, synth.SEED_BASE + 2)
+csr = synth.topology_csr(t, delta=delta)
+ctx = capi.Context(0)
+g = ctx.upload(csr)
+lib = ctx.lib
+lib.hspf_debug_phase_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+roots = np.arange(1000, dtype=np.uint32)
+ctx.run(g, roots)
+lib.hspf_debug_phase_profile(ctx.handle, 1, None)
+ctx.run(g, roots)
+out = (C.c_uint64 * 8)()
+lib.hspf_debug_phase_profile(ctx.handle, 0, out)
+names = ["init", "sssp", "parents", "dist_wb", "kahn", "hops_wb"]
+tot = sum(out[k] for k in range(6))
+print("delta", delta, "total Mcycles", tot / 1e6, "per job kcycles", tot / 1000 / 1e3)
+print("  kahn rounds/job", out[6] / 1000, " sssp rounds/job", out[7] / 1000)
+for k, n in enumerate(names):
+    print(f"  {n:8s} {100 * out[k] / tot:5.1f}%  {out[k] / 1000 / 1e3:8.1f} kcycles/job")
