@@ -24,6 +24,7 @@ struct hspf_graph {
     void *blob = nullptr;      // single device allocation holding every array
     size_t blob_bytes = 0;
     uint32_t max_indeg = 0;
+    bool has_leaf = false;     // any HSPF_VF_LEAF / LEAF_UNLESS_ROOT vertex
 };
 
 struct hspf_ctx {
@@ -73,15 +74,15 @@ int grow(hspf_ctx *ctx, void **p, size_t *have, size_t need, bool pinned = false
     return HSPF_OK;
 }
 
-template <typename VT, bool S>
+template <typename VT, bool S, bool F>
 int launch(hspf_ctx *ctx, const BatchArgs &args, size_t smem, int grid) {
     if (const char *co = getenv("HSPF_SMEM_CARVEOUT")) {   // tuning knob (experiments only)
-        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
+        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S, F>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
     }
     if (smem > 0) {
-        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(spf_batch_kernel<VT, S, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    spf_batch_kernel<VT, S><<<grid, kThreads, smem, ctx->stream>>>(args);
+    spf_batch_kernel<VT, S, F><<<grid, kThreads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     ctx->launches++;
     return HSPF_OK;
@@ -91,8 +92,8 @@ template <typename VT, bool S>
 int max_ctas_per_sm(size_t smem) {
     int n = 0;
     if (smem > 0)
-        cudaFuncSetAttribute(spf_batch_kernel<VT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spf_batch_kernel<VT, S>, kThreads, smem) != cudaSuccess) n = 1;
+        cudaFuncSetAttribute(spf_batch_kernel<VT, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spf_batch_kernel<VT, S, false>, kThreads, smem) != cudaSuccess) n = 1;
     return n < 1 ? 1 : n;
 }
 
@@ -130,6 +131,10 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     int grid = ctx->sm_count * per_sm;
+    if (const char *mg = getenv("HSPF_MAX_GRID")) {   // tuning knob (experiments only)
+        int v = atoi(mg);
+        if (v >= 1 && v < grid) grid = v;
+    }
     if ((uint32_t)grid > jobs->n_jobs) grid = (int)jobs->n_jobs;
     if (grid < 1) grid = 1;
 
@@ -149,9 +154,12 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         a.prof = ctx->d_prof;
     }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), ctx->stream));
-    if (in_smem)
-        return q16 ? launch<uint16_t, true>(ctx, a, sb, grid) : launch<uint32_t, true>(ctx, a, sb, grid);
-    return q16 ? launch<uint16_t, false>(ctx, a, 0, grid) : launch<uint32_t, false>(ctx, a, 0, grid);
+    const bool fast = !jobs->ov_off && !(g->d.flags & HSPF_GF_HOPCOUNT) && !g->has_leaf && out->nh_words == 1;
+    if (in_smem) {
+        if (fast) return q16 ? launch<uint16_t, true, true>(ctx, a, sb, grid) : launch<uint32_t, true, true>(ctx, a, sb, grid);
+        return q16 ? launch<uint16_t, true, false>(ctx, a, sb, grid) : launch<uint32_t, true, false>(ctx, a, sb, grid);
+    }
+    return q16 ? launch<uint16_t, false, false>(ctx, a, 0, grid) : launch<uint32_t, false, false>(ctx, a, 0, grid);
 }
 
 struct Planes {   // byte sizes of the result planes of a batch
@@ -337,6 +345,8 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         }
         G->d.delta = delta;
         G->max_indeg = max_indeg;
+        for (uint32_t v = 0; v < V; ++v)
+            if (g->vflags[v] & (HSPF_VF_LEAF | HSPF_VF_LEAF_UNLESS_ROOT)) G->has_leaf = true;
         *out = G;
         return HSPF_OK;
     } catch (const std::bad_alloc &) {

@@ -172,11 +172,51 @@ __device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) 
         }                                                                        \
     } while (0)
 
+// Compact the set bits of a V-bit bitmap into queue `q` (vertex ids, any order),
+// clearing the bitmap; `keep(v)` filters.  One word per thread, warp-aggregated
+// reservation in *counter.  Call from all threads; the caller supplies the barriers.
+template <typename VT, typename Keep>
+__device__ __forceinline__ void bitmap_to_queue(uint32_t *bm, uint32_t nbw, VT *q, uint32_t *counter, Keep keep) {
+    for (uint32_t w0 = 0; w0 < nbw; w0 += kThreads) {
+        const uint32_t w = w0 + threadIdx.x;
+        uint32_t bits = 0;
+        if (w < nbw) {
+            bits = bm[w];
+            if (bits) {
+                bm[w] = 0;
+                uint32_t kept = 0;
+                for (uint32_t b = bits; b; b &= b - 1) {
+                    const uint32_t bit = __ffs(b) - 1;
+                    if (keep(w * 32 + bit)) kept |= 1u << bit;
+                }
+                bits = kept;
+            }
+        }
+        const uint32_t n = __popc(bits);
+        uint32_t incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)(threadIdx.x & 31) >= o) incl += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (tot) {
+            if ((threadIdx.x & 31) == 31) base = atomicAdd(counter, tot);
+            base = __shfl_sync(0xffffffffu, base, 31);
+        }
+        uint32_t pos = base + incl - n;
+        for (uint32_t b = bits; b; b &= b - 1) q[pos++] = (VT)(w * 32 + (__ffs(b) - 1));
+    }
+}
+
 // kSmemState: the per-job state block lives in dynamic shared memory (the normal
 // case).  It is a template parameter, not a runtime select, so that the compiler
 // can prove the address space and emit LDS/STS/ATOMS instead of generic LD/ST/ATOM
 // (generic atomics that land in the shared window are an order of magnitude slower).
-template <typename VT, bool kSmemState>
+// kFast: the common batch shape — no edge overrides, no hop-count mode, no LEAF
+// vertex flags, one next-hop word — with those branches compiled out.
+template <typename VT, bool kSmemState, bool kFast>
 __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ Small S;
@@ -210,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     uint32_t *dagbit = reinterpret_cast<uint32_t *>(base + L.dagbit);
     uint32_t *fpbit = reinterpret_cast<uint32_t *>(base + L.fpbit);
 
-    const uint32_t nhw = a.nhw;
+    const uint32_t nhw = kFast ? 1u : a.nhw;
     long long t_mark = clock64();
     const uint32_t lane = threadIdx.x & 31;
 
@@ -230,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     }
     auto is_hop = [&](uint32_t v) -> bool { return (fl_hop[v >> 5] >> (v & 31)) & 1u; };
     auto vexpands = [&](uint32_t u, uint32_t root_) -> bool {
+        if (kFast) return true;
         const uint32_t b = 1u << (u & 31);
         return !((fl_leaf[u >> 5] & b) || ((fl_lur[u >> 5] & b) && u != root_));
     };
@@ -286,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             qa[0] = (VT)root;
         }
         __syncthreads();
-        const uint32_t n_ov = S.ov.n;
+        const uint32_t n_ov = kFast ? 0u : S.ov.n;
         // root edge table: first-hop atom bases behind the root's non-HOP neighbours
         if (tid == 32) {
             const uint32_t rb = g.row[root], re = g.row[root + 1];
@@ -312,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // ======================= phase 1: SSSP ==================================
         const uint32_t delta = g.delta ? g.delta : 1u;
         uint32_t hi_thr = delta;       // near bucket is [*, hi_thr)
-        uint32_t *bm_next = bm0, *bm_old = bm1;
+        uint32_t *bm_next = bm0;
         VT *qcur = qa, *qnext = qb;
         uint32_t p = 0;                // S.cnt[p] counts qcur, S.cnt[p^1] counts qnext
         for (;;) {
@@ -363,12 +404,10 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 const uint32_t nd = sat_add(k_du, c);
                                 const uint32_t v = ec.x;
                                 if (nd <= g.reject_above && nd < dist[v]) {
-                                    const uint32_t old = atomicMin(&dist[v], nd);
-                                    if (nd < old && nd < hi_thr) {
-                                        const uint32_t bit = 1u << (v & 31);
-                                        const uint32_t ob = atomicOr(&bm_next[v >> 5], bit);
-                                        if (!(ob & bit)) q_push(qnext, &S.cnt[p ^ 1], v);
-                                    }
+                                    // fire-and-forget: nothing below waits on an atomic's result;
+                                    // the next frontier is compacted from the bitmap at round end
+                                    atomicMin(&dist[v], nd);
+                                    if (nd < hi_thr) atomicOr(&bm_next[v >> 5], 1u << (v & 31));
                                 }
                             }
                         }
@@ -378,9 +417,8 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 7] += 1;   // SSSP rounds
                 // every thread has consumed S.cnt[p]; recycle it for the round after next
                 if (tid == 0) S.cnt[p] = 0;
-                // the bitmap that guarded this round's queue becomes the next guard
-                for (uint32_t w = tid; w < nbw; w += kThreads) bm_old[w] = 0;
-                { uint32_t *t = bm_next; bm_next = bm_old; bm_old = t; }
+                // next frontier = vertices marked this round (each once, the bitmap dedups)
+                bitmap_to_queue(bm_next, nbw, qnext, &S.cnt[p ^ 1], [](uint32_t) { return true; });
                 { VT *t = qcur; qcur = qnext; qnext = t; }
                 p ^= 1;
                 __syncthreads();
@@ -417,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         HSPF_MARK(1);   // SSSP
         // SSSP done: qa/qb/bm0/bm1 are dead, dist is final.
         for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
+        for (uint32_t w = tid; w < nbw; w += kThreads) bm0[w] = 0;
         for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
         __syncthreads();
 
@@ -435,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     // Hop-count mode: a pseudonode is parented only by the lowest-numbered
                     // attached router of its level (see HSPF_GF_HOPCOUNT in holo_spf.h).
                     uint32_t only_u = kInf;
-                    const bool hopcount = g.flags & kGfHopCount;
+                    const bool hopcount = kFast ? false : (g.flags & kGfHopCount) != 0;
                     if (hopcount && !is_hop(v)) {
                         for (uint32_t i = ib; i < ie; ++i) {
                             const uint2 sc1 = g.iedge[i];
@@ -592,10 +631,10 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                     }
                                     if (is_fp) hops_s[v] = (uint16_t)min(k_hu + hv, 0xFFFFu);
                                 }
-                                // packed u16 decrement; the thread that takes it to zero owns v
-                                const uint32_t sh = (v & 1) * 16;
-                                const uint32_t oldw = atomicSub(&pend32[v >> 1], 1u << sh);
-                                if (((oldw >> sh) & 0xFFFFu) == 1u) q_push(knext, &S.cnt[p ^ 1], v);
+                                // packed u16 in-degree decrement + "touched" mark, both fire-and-forget;
+                                // vertices whose counter reached zero are collected at round end
+                                atomicSub(&pend32[v >> 1], 1u << ((v & 1) * 16));
+                                atomicOr(&bm0[v >> 5], 1u << (v & 31));
                             }
                         }
                         __syncwarp();
@@ -604,6 +643,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 __syncthreads();
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 6] += 1;   // Kahn rounds
                 if (tid == 0) S.cnt[p] = 0;
+                bitmap_to_queue(bm0, nbw, knext, &S.cnt[p ^ 1], [&](uint32_t v) { return pend[v] == 0; });
                 { VT *t = kcur; kcur = knext; knext = t; }
                 p ^= 1;
                 __syncthreads();
