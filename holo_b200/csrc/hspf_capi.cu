@@ -147,10 +147,10 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
     if (ctx->prof_enabled) {
         if (ctx->prof_rows < grid) {
             if (ctx->d_prof) cudaFree(ctx->d_prof);
-            CK(cudaMalloc(&ctx->d_prof, (size_t)grid * 8 * sizeof(unsigned long long)));
+            CK(cudaMalloc(&ctx->d_prof, (size_t)grid * 16 * sizeof(unsigned long long)));
             ctx->prof_rows = grid;
         }
-        CK(cudaMemsetAsync(ctx->d_prof, 0, (size_t)ctx->prof_rows * 8 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_prof, 0, (size_t)ctx->prof_rows * 16 * sizeof(unsigned long long), ctx->stream));
         a.prof = ctx->d_prof;
     }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), ctx->stream));
@@ -229,16 +229,16 @@ void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[8]) {
+int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]) {
     if (!ctx) return HSPF_E_INVAL;
     if (out) {
-        for (int k = 0; k < 8; ++k) out[k] = 0;
+        for (int k = 0; k < 16; ++k) out[k] = 0;
         if (ctx->d_prof && ctx->prof_rows > 0) {
             CK(cudaStreamSynchronize(ctx->stream));
-            std::vector<unsigned long long> h((size_t)ctx->prof_rows * 8);
+            std::vector<unsigned long long> h((size_t)ctx->prof_rows * 16);
             CK(cudaMemcpy(h.data(), ctx->d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             for (int r = 0; r < ctx->prof_rows; ++r)
-                for (int k = 0; k < 8; ++k) out[k] += h[(size_t)r * 8 + k];
+                for (int k = 0; k < 16; ++k) out[k] += h[(size_t)r * 16 + k];
         }
     }
     ctx->prof_enabled = enable != 0;
@@ -288,15 +288,13 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         std::vector<uint32_t> irow(V + 1, 0);
         for (uint32_t v = 0; v < V; ++v) irow[v + 1] = irow[v] + indeg[v + 1];
         std::vector<uint32_t> fill(irow.begin(), irow.end() - 1);
-        std::vector<uint2> iedge(E);
-        std::vector<uint32_t> ieid(E);
+        std::vector<uint4> iedge(E);
         std::vector<uint2> fedge(E);
         for (uint32_t u = 0; u < V; ++u)
             for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e) {
                 const uint32_t v = g->col[e];
                 const uint32_t k = fill[v]++;
-                iedge[k] = make_uint2(u, g->cost[e]);
-                ieid[k] = e;
+                iedge[k] = make_uint4(u, g->cost[e], e, 0u);
                 fedge[e] = make_uint2(v, g->cost[e]);
             }
 
@@ -305,8 +303,7 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         const size_t o_edge = o_row + al((size_t)(V + 1) * 4);
         const size_t o_irow = o_edge + al((size_t)E * 8);
         const size_t o_iedge = o_irow + al((size_t)(V + 1) * 4);
-        const size_t o_ieid = o_iedge + al((size_t)E * 8);
-        const size_t o_vf = o_ieid + al((size_t)E * 4);
+        const size_t o_vf = o_iedge + al((size_t)E * 16);
         const size_t total = o_vf + al(V);
 
         hspf_graph *G = new hspf_graph();
@@ -319,8 +316,7 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         std::memcpy(host.data() + o_row, g->row_ptr, (size_t)(V + 1) * 4);
         if (E) {
             std::memcpy(host.data() + o_edge, fedge.data(), (size_t)E * 8);
-            std::memcpy(host.data() + o_iedge, iedge.data(), (size_t)E * 8);
-            std::memcpy(host.data() + o_ieid, ieid.data(), (size_t)E * 4);
+            std::memcpy(host.data() + o_iedge, iedge.data(), (size_t)E * 16);
         }
         std::memcpy(host.data() + o_irow, irow.data(), (size_t)(V + 1) * 4);
         std::memcpy(host.data() + o_vf, g->vflags, V);
@@ -332,16 +328,17 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         G->d.row = reinterpret_cast<const uint32_t *>(b + o_row);
         G->d.edge = reinterpret_cast<const uint2 *>(b + o_edge);
         G->d.irow = reinterpret_cast<const uint32_t *>(b + o_irow);
-        G->d.iedge = reinterpret_cast<const uint2 *>(b + o_iedge);
-        G->d.ieid = reinterpret_cast<const uint32_t *>(b + o_ieid);
+        G->d.iedge = reinterpret_cast<const uint4 *>(b + o_iedge);
         G->d.vflags = b + o_vf;
         G->d.reject_above = g->reject_above;
         G->d.saturate_at = g->saturate_at;
         G->d.flags = g->flags;
         uint32_t delta = g->delta;
         if (delta == 0) {
+            // near/far bucket width: ~4x the mean link cost keeps the SSSP at a few buckets
+            // (fewer barrier rounds) with ~1.3x re-expansion on the BASELINE shapes
             uint64_t mean = E ? cost_sum / E : 1;
-            delta = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mean, 1), 0x7FFFFFFFu);
+            delta = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4 * mean, 1), 0x7FFFFFFFu);
         }
         G->d.delta = delta;
         G->max_indeg = max_indeg;

@@ -48,8 +48,7 @@ struct DevGraph {
     const uint32_t *row;    // [V+1]
     const uint2 *edge;      // [E] {col, cost}
     const uint32_t *irow;   // [V+1] transposed
-    const uint2 *iedge;     // [E] {src, cost}
-    const uint32_t *ieid;   // [E] forward edge index of the in-edge
+    const uint4 *iedge;     // [E] {src, cost, forward edge index, 0}: one 16 B load per in-edge
     const uint8_t *vflags;  // [V]
     uint32_t reject_above, saturate_at, flags, delta;
 };
@@ -80,7 +79,7 @@ struct BatchArgs {
     uint8_t *ws;              // per-CTA global workspace when state does not fit smem
     size_t ws_stride;         // bytes per CTA (0: state in smem)
     uint32_t *job_counter;    // dynamic job fetch
-    unsigned long long *prof; // optional [gridDim][8] per-phase cycle counters (debug), may be null
+    unsigned long long *prof; // optional [gridDim][16] per-phase cycle counters (debug), may be null
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -167,7 +166,7 @@ __device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) 
     do {                                                                         \
         if (a.prof && tid == 0) {                                                \
             const long long now_ = clock64();                                    \
-            a.prof[(size_t)blockIdx.x * 8 + (k)] += (unsigned long long)(now_ - t_mark); \
+            a.prof[(size_t)blockIdx.x * 16 + (k)] += (unsigned long long)(now_ - t_mark); \
             t_mark = now_;                                                       \
         }                                                                        \
     } while (0)
@@ -360,6 +359,8 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             for (;;) {
                 const uint32_t n_cur = S.cnt[p];
                 if (n_cur == 0) break;
+                long long t_sub = 0;
+                if (a.prof && tid == 0) { t_sub = clock64(); a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; }
                 // Warp-cooperative expansion: 32 frontier vertices per warp pass; their edge
                 // lists are concatenated and relaxed 32 edges at a time, one per lane, so a
                 // pass costs one row fetch + ceil(edges/32) edge fetches instead of
@@ -380,48 +381,61 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     }
                     const uint32_t excl = incl - deg;
                     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-                        const uint32_t j = j0 + lane;
-                        // owner lane k: the last lane whose exclusive prefix is <= j
-                        uint32_t k = 0;
+                    // up to kSB batches of 32 edges are fetched together (one L2 latency for
+                    // 128 edges), then relaxed
+                    constexpr int kSB = 4;
+                    for (uint32_t j0 = 0; j0 < total; j0 += 32 * kSB) {
+                        uint2 ec[kSB];
+                        uint32_t k_du[kSB], k_u[kSB], eidx[kSB];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const uint32_t cand = k + o;
-                            const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31);
-                            if (cand < 32 && ex <= j) k = cand;
+                        for (int b = 0; b < kSB; ++b) {
+                            const uint32_t j = j0 + b * 32 + lane;
+                            // owner lane k: the last lane whose exclusive prefix is <= j
+                            uint32_t k = 0;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const uint32_t cand = k + o;
+                                const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31);
+                                if (cand < 32 && ex <= j) k = cand;
+                            }
+                            const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
+                            const uint32_t k_ex = __shfl_sync(0xffffffffu, excl, k);
+                            k_du[b] = __shfl_sync(0xffffffffu, du, k);
+                            k_u[b] = __shfl_sync(0xffffffffu, u, k);
+                            eidx[b] = k_eb + (j - k_ex);
+                            ec[b] = (j < total) ? g.edge[eidx[b]] : make_uint2(0u, kInf);
                         }
-                        const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
-                        const uint32_t k_ex = __shfl_sync(0xffffffffu, excl, k);
-                        const uint32_t k_du = __shfl_sync(0xffffffffu, du, k);
-                        const uint32_t k_u = __shfl_sync(0xffffffffu, u, k);
-                        if (j < total) {
-                            const uint32_t e = k_eb + (j - k_ex);
-                            const uint2 ec = g.edge[e];
-                            uint32_t c = ec.y;
-                            for (uint32_t q = 0; q < n_ov; ++q)
-                                if (S.ov.tail[q] == k_u && S.ov.edge[q] == e) c = S.ov.cost[q];
-                            if (c != kInf) {
-                                const uint32_t nd = sat_add(k_du, c);
-                                const uint32_t v = ec.x;
-                                if (nd <= g.reject_above && nd < dist[v]) {
-                                    // fire-and-forget: nothing below waits on an atomic's result;
-                                    // the next frontier is compacted from the bitmap at round end
-                                    atomicMin(&dist[v], nd);
-                                    if (nd < hi_thr) atomicOr(&bm_next[v >> 5], 1u << (v & 31));
-                                }
+#pragma unroll
+                        for (int b = 0; b < kSB; ++b) {
+                            uint32_t c = ec[b].y;
+                            if (!kFast)
+                                for (uint32_t q = 0; q < n_ov; ++q)
+                                    if (S.ov.tail[q] == k_u[b] && S.ov.edge[q] == eidx[b] && c != kInf) c = S.ov.cost[q];
+                            if (c == kInf) continue;     // padding lane or disabled edge
+                            const uint32_t nd = sat_add(k_du[b], c);
+                            const uint32_t v = ec[b].x;
+                            if (nd <= g.reject_above && nd < dist[v]) {
+                                // fire-and-forget: nothing below waits on an atomic's result;
+                                // the next frontier is compacted from the bitmap at round end
+                                atomicMin(&dist[v], nd);
+                                if (nd < hi_thr) atomicOr(&bm_next[v >> 5], 1u << (v & 31));
                             }
                         }
                     }
                 }
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 8] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();
-                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 7] += 1;   // SSSP rounds
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;   // SSSP rounds
                 // every thread has consumed S.cnt[p]; recycle it for the round after next
                 if (tid == 0) S.cnt[p] = 0;
                 // next frontier = vertices marked this round (each once, the bitmap dedups)
                 bitmap_to_queue(bm_next, nbw, qnext, &S.cnt[p ^ 1], [](uint32_t) { return true; });
                 { VT *t = qcur; qcur = qnext; qnext = t; }
                 p ^= 1;
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 10] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 11] += n_ - t_sub; }
             }
             // near bucket exhausted (S.cnt[0] == S.cnt[1] == 0): everything below
             // hi_thr is settled.  Collect the next bucket [m, m + delta) into qcur,
@@ -461,89 +475,88 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
 
         // ======================= phase 2: ECMP parents (pull) ====================
         uint32_t sat_flag = 0;
-        for (uint32_t v = tid; v < Vp; v += kThreads) {
-            uint32_t cnt = 0, bu = kInf, be = kInf;
-            unsigned long long bkey = ~0ull;   // (distance, id) of the best parent so far
-            if (v < V) {
-                const uint32_t dv = dist[v];
-                if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
-                if (v != root && dv != kInf) {
-                    bool vo = false;
-                    for (uint32_t k = 0; k < n_ov; ++k) vo |= (S.ov.head[k] == v);
-                    const uint32_t ib = g.irow[v], ie = g.irow[v + 1];
-                    // Hop-count mode: a pseudonode is parented only by the lowest-numbered
-                    // attached router of its level (see HSPF_GF_HOPCOUNT in holo_spf.h).
-                    uint32_t only_u = kInf;
-                    const bool hopcount = kFast ? false : (g.flags & kGfHopCount) != 0;
-                    if (hopcount && !is_hop(v)) {
-                        for (uint32_t i = ib; i < ie; ++i) {
-                            const uint2 sc1 = g.iedge[i];
-                            const uint32_t u = sc1.x, d1 = dist[u];
-                            if (d1 == kInf || !vexpands(u, root)) continue;
-                            uint32_t c = sc1.y;
-                            if (vo) {
-                                const uint32_t e = g.ieid[i];
+        {
+            // in-edge range of the next vertex is fetched one iteration ahead
+            uint32_t ib_n = 0, ie_n = 0;
+            if (tid < V) { ib_n = g.irow[tid]; ie_n = g.irow[tid + 1]; }
+            for (uint32_t v = tid; v < Vp; v += kThreads) {
+                const uint32_t ib = ib_n, ie = ie_n;
+                if (v + kThreads < V) { ib_n = g.irow[v + kThreads]; ie_n = g.irow[v + kThreads + 1]; }
+                uint32_t cnt = 0, bu = kInf, be = kInf;
+                unsigned long long bkey = ~0ull;   // (distance, id) of the best parent so far
+                if (v < V) {
+                    const uint32_t dv = dist[v];
+                    if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
+                    if (v != root && dv != kInf) {
+                        // Hop-count mode: a pseudonode is parented only by the lowest-numbered
+                        // attached router of its level (see HSPF_GF_HOPCOUNT in holo_spf.h).
+                        uint32_t only_u = kInf;
+                        const bool hopcount = kFast ? false : (g.flags & kGfHopCount) != 0;
+                        if (hopcount && !is_hop(v)) {
+                            for (uint32_t i = ib; i < ie; ++i) {
+                                const uint4 sc1 = g.iedge[i];
+                                const uint32_t u = sc1.x, d1 = dist[u];
+                                if (d1 == kInf || !vexpands(u, root)) continue;
+                                uint32_t c = sc1.y;
                                 for (uint32_t q = 0; q < n_ov; ++q)
-                                    if (S.ov.edge[q] == e) c = S.ov.cost[q];
+                                    if (S.ov.edge[q] == sc1.z) c = S.ov.cost[q];
                                 if (c == kInf) continue;
+                                if (sat_add(d1, c) == dv) only_u = min(only_u, u);
                             }
-                            if (sat_add(d1, c) == dv) only_u = min(only_u, u);
                         }
-                    }
-                    for (uint32_t i0 = ib; i0 < ie; i0 += 4) {
-                        uint2 sc[4];
-                        uint32_t du[4];
-                        uint32_t fl[4];
+                        for (uint32_t i0 = ib; i0 < ie; i0 += 4) {
+                            uint4 sc[4];
+                            uint32_t du[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) sc[k] = (i0 + k < ie) ? g.iedge[i0 + k] : make_uint2(v, kInf);
+                            for (int k = 0; k < 4; ++k) sc[k] = (i0 + k < ie) ? g.iedge[i0 + k] : make_uint4(v, kInf, 0u, 0u);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { du[k] = dist[sc[k].x]; fl[k] = is_hop(sc[k].x) ? kVfHop : 0u; }
+                            for (int k = 0; k < 4; ++k) du[k] = dist[sc[k].x];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (i0 + k >= ie) break;
-                            const uint32_t u = sc[k].x;
-                            if (du[k] == kInf || !vexpands(u, root)) continue;
-                            if (only_u != kInf && u != only_u) continue;
-                            uint32_t c = sc[k].y;
-                            uint32_t e = kInf;
-                            if (vo) {
-                                e = g.ieid[i0 + k];
-                                for (uint32_t q = 0; q < n_ov; ++q)
-                                    if (S.ov.edge[q] == e) c = S.ov.cost[q];
-                                if (c == kInf) continue;
-                            }
-                            if (sat_add(du[k], c) != dv) continue;
-                            if (e == kInf) e = g.ieid[i0 + k];
-                            ++cnt;
-                            atomicOr(&dagbit[e >> 5], 1u << (e & 31));
-                            unsigned long long key = ((unsigned long long)du[k] << 32) | u;
-                            if (hopcount && !(fl[k] & kVfHop)) {
-                                // pop order inside a hop-count level is R1, pseudonodes inserted by
-                                // R1, R2, ...: a pseudonode sorts right after its owner router
-                                uint32_t owner = kInf;
-                                for (uint32_t j = g.irow[u]; j < g.irow[u + 1]; ++j) {
-                                    const uint2 s2 = g.iedge[j];
-                                    if (dist[s2.x] != du[k] || !vexpands(s2.x, root)) continue;
-                                    bool dis = false;
+                            for (int k = 0; k < 4; ++k) {
+                                if (i0 + k >= ie) break;
+                                const uint32_t u = sc[k].x;
+                                if (du[k] == kInf || !vexpands(u, root)) continue;
+                                if (only_u != kInf && u != only_u) continue;
+                                uint32_t c = sc[k].y;
+                                const uint32_t e = sc[k].z;
+                                if (!kFast) {
                                     for (uint32_t q = 0; q < n_ov; ++q)
-                                        if (S.ov.edge[q] == g.ieid[j] && S.ov.cost[q] == kInf) dis = true;
-                                    if (!dis) owner = min(owner, s2.x);
+                                        if (S.ov.edge[q] == e) c = S.ov.cost[q];
+                                    if (c == kInf) continue;
                                 }
-                                key = ((unsigned long long)du[k] << 32) | ((unsigned long long)owner) ;
-                                key = (key << 1) | 1ull;           // after the owner router itself
-                                key = (key << 0);
-                            } else if (hopcount) {
-                                key = (key << 1);
+                                if (sat_add(du[k], c) != dv) continue;
+                                ++cnt;
+                                atomicOr(&dagbit[e >> 5], 1u << (e & 31));
+                                unsigned long long key = ((unsigned long long)du[k] << 32) | u;
+                                if (hopcount) {
+                                    // pop order inside a hop-count level is R1, pseudonodes first
+                                    // reached from R1, R2, ...: a pseudonode sorts right after its
+                                    // owner router
+                                    if (!is_hop(u)) {
+                                        uint32_t owner = kInf;
+                                        for (uint32_t j = g.irow[u]; j < g.irow[u + 1]; ++j) {
+                                            const uint4 s2 = g.iedge[j];
+                                            if (dist[s2.x] != du[k] || !vexpands(s2.x, root)) continue;
+                                            bool dis = false;
+                                            for (uint32_t q = 0; q < n_ov; ++q)
+                                                if (S.ov.edge[q] == s2.z && S.ov.cost[q] == kInf) dis = true;
+                                            if (!dis) owner = min(owner, s2.x);
+                                        }
+                                        key = ((((unsigned long long)du[k] << 32) | owner) << 1) | 1ull;
+                                    } else {
+                                        key <<= 1;
+                                    }
+                                }
+                                if (key < bkey || (key == bkey && u < bu)) { bkey = key; bu = u; be = e; }
                             }
-                            if (key < bkey || (key == bkey && u < bu)) { bkey = key; bu = u; be = e; }
                         }
+                        if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
                     }
-                    if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
+                    o_fp[v] = bu;
+                    o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
                 }
-                o_fp[v] = bu;
-                o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
+                pend[v] = (uint16_t)min(cnt, 0xFFFFu);
             }
-            pend[v] = (uint16_t)min(cnt, 0xFFFFu);
         }
         if (sat_flag) atomicOr(&S.status, kJsSaturated);
         __syncthreads();
@@ -580,8 +593,16 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                             if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
                         }
                     }
+                    // DAG out-edges of this lane's vertex: word-level scans of the DAG bitmap
+                    auto range_mask = [&](uint32_t w) -> uint32_t {   // bits of word w inside [eb, ee)
+                        uint32_t m = 0xFFFFFFFFu;
+                        if (w == (eb >> 5)) m &= 0xFFFFFFFFu << (eb & 31);
+                        if (w == ((ee - 1) >> 5)) m &= 0xFFFFFFFFu >> (31 - ((ee - 1) & 31));
+                        return m;
+                    };
                     uint32_t nd_edges = 0;
-                    for (uint32_t e = eb; e < ee; ++e) nd_edges += (dagbit[e >> 5] >> (e & 31)) & 1u;
+                    if (ee > eb)
+                        for (uint32_t w = eb >> 5; w <= ((ee - 1) >> 5); ++w) nd_edges += __popc(dagbit[w] & range_mask(w));
                     uint32_t incl = nd_edges;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -592,56 +613,69 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                     for (uint32_t w0 = 0; w0 < total; w0 += kStage) {
                         // stage the window [w0, w0 + kStage) of this warp's DAG edges
-                        uint32_t pos = excl;
-                        for (uint32_t e = eb; e < ee; ++e) {
-                            if (!((dagbit[e >> 5] >> (e & 31)) & 1u)) continue;
-                            if (pos >= w0 && pos < w0 + kStage) { stage_e[pos - w0] = e; stage_k[pos - w0] = (uint8_t)lane; }
-                            ++pos;
+                        if (nd_edges) {
+                            uint32_t pos = excl;
+                            for (uint32_t w = eb >> 5; w <= ((ee - 1) >> 5); ++w) {
+                                for (uint32_t m = dagbit[w] & range_mask(w); m; m &= m - 1) {
+                                    if (pos >= w0 && pos < w0 + kStage) {
+                                        stage_e[pos - w0] = w * 32 + (__ffs(m) - 1);
+                                        stage_k[pos - w0] = (uint8_t)lane;
+                                    }
+                                    ++pos;
+                                }
+                            }
                         }
                         __syncwarp();
                         const uint32_t wn = min((uint32_t)kStage, total - w0);
-                        for (uint32_t j0 = 0; j0 < wn; j0 += 32) {
-                            const uint32_t j = j0 + lane;
+                        constexpr int kKB = kStage / 32;   // both batches of a window are fetched together
+                        uint32_t e_[kKB], v_[kKB], ku_[kKB], khu_[kKB], keb_[kKB], kab_[kKB], kok_[kKB];
+#pragma unroll
+                        for (int b = 0; b < kKB; ++b) {
+                            const uint32_t j = b * 32 + lane;
                             const bool act = j < wn;
-                            const uint32_t e = act ? stage_e[j] : 0u;
+                            e_[b] = act ? stage_e[j] : kInf;
                             const uint32_t k = act ? stage_k[j] : 0u;
-                            const uint32_t k_u = __shfl_sync(0xffffffffu, u, k);
-                            const uint32_t k_hu = __shfl_sync(0xffffffffu, hu, k);
-                            const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
-                            const uint32_t k_ab = __shfl_sync(0xffffffffu, abase, k);
-                            const uint32_t k_ok = __shfl_sync(0xffffffffu, (uint32_t)atoms_ok, k);
-                            if (act) {
-                                const uint32_t v = g.edge[e].x;
-                                const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
-                                const uint32_t hv = is_hop(v) ? 1u : 0u;
-                                if (k_hu == 0) {
-                                    if (!((g.flags & kGfNoHopTargetNoNh) && !hv) && k_ok) {
-                                        const uint32_t atom = k_ab + (e - k_eb);
-                                        if (atom < 64u * nhw)
-                                            atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
-                                                     1ull << (atom & 63));
-                                        else
-                                            atomicOr(&S.status, kJsTooManyAtoms);
-                                    }
-                                    if (is_fp) hops_s[v] = (uint16_t)hv;
-                                } else {
-                                    for (uint32_t w = 0; w < nhw; ++w) {
-                                        const uint64_t x = __ldcg(&o_nh[(size_t)k_u * nhw + w]);
-                                        if (x) atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), x);
-                                    }
-                                    if (is_fp) hops_s[v] = (uint16_t)min(k_hu + hv, 0xFFFFu);
+                            ku_[b] = __shfl_sync(0xffffffffu, u, k);
+                            khu_[b] = __shfl_sync(0xffffffffu, hu, k);
+                            keb_[b] = __shfl_sync(0xffffffffu, eb, k);
+                            kab_[b] = __shfl_sync(0xffffffffu, abase, k);
+                            kok_[b] = __shfl_sync(0xffffffffu, (uint32_t)atoms_ok, k);
+                            v_[b] = act ? g.edge[e_[b]].x : 0u;
+                        }
+#pragma unroll
+                        for (int b = 0; b < kKB; ++b) {
+                            const uint32_t e = e_[b];
+                            if (e == kInf) continue;
+                            const uint32_t v = v_[b];
+                            const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
+                            const uint32_t hv = is_hop(v) ? 1u : 0u;
+                            if (khu_[b] == 0) {
+                                if (!((g.flags & kGfNoHopTargetNoNh) && !hv) && kok_[b]) {
+                                    const uint32_t atom = kab_[b] + (e - keb_[b]);
+                                    if (atom < 64u * nhw)
+                                        atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
+                                                 1ull << (atom & 63));
+                                    else
+                                        atomicOr(&S.status, kJsTooManyAtoms);
                                 }
-                                // packed u16 in-degree decrement + "touched" mark, both fire-and-forget;
-                                // vertices whose counter reached zero are collected at round end
-                                atomicSub(&pend32[v >> 1], 1u << ((v & 1) * 16));
-                                atomicOr(&bm0[v >> 5], 1u << (v & 31));
+                                if (is_fp) hops_s[v] = (uint16_t)hv;
+                            } else {
+                                for (uint32_t w = 0; w < nhw; ++w) {
+                                    const uint64_t x = __ldcg(&o_nh[(size_t)ku_[b] * nhw + w]);
+                                    if (x) atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), x);
+                                }
+                                if (is_fp) hops_s[v] = (uint16_t)min(khu_[b] + hv, 0xFFFFu);
                             }
+                            // packed u16 in-degree decrement + "touched" mark, both fire-and-forget;
+                            // vertices whose counter reached zero are collected at round end
+                            atomicSub(&pend32[v >> 1], 1u << ((v & 1) * 16));
+                            atomicOr(&bm0[v >> 5], 1u << (v & 31));
                         }
                         __syncwarp();
                     }
                 }
                 __syncthreads();
-                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 6] += 1;   // Kahn rounds
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 6] += 1;   // Kahn rounds
                 if (tid == 0) S.cnt[p] = 0;
                 bitmap_to_queue(bm0, nbw, knext, &S.cnt[p ^ 1], [&](uint32_t v) { return pend[v] == 0; });
                 { VT *t = kcur; kcur = knext; knext = t; }

@@ -220,8 +220,9 @@ int hspf_atom_count(const hspf_csr *g, uint32_t root, uint32_t *n_atoms);
 
 /* Debug aid: enable/disable per-phase cycle counters of the batch kernel and read
  * the sums of the last launch (slots: 0 init, 1 SSSP, 2 parents, 3 dist write-back,
- * 4 Kahn, 5 hops write-back; SM cycles summed over CTAs).  `out` may be NULL. */
-int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[8]);
+ * 4 Kahn, 5 hops write-back, 6/7 Kahn/SSSP round counts, 8-12 SSSP round internals;
+ * SM cycles summed over CTAs).  `out` may be NULL. */
+int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]);
 
 /* Library build info, e.g. "holo_spf 0.1 sm_100a". */
 const char *hspf_version(void);
