@@ -237,7 +237,7 @@ def run_ours(args):
         if world > 1:
             with torch.cuda.stream(stream):
                 for k in planes:
-                    dist.all_gather_into_tensor(gathered[k].view(-1), planes[k].view(-1))
+                    dist.all_gather_into_tensor(gathered[k].view(torch.uint8).view(-1), planes[k].view(torch.uint8).view(-1))
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -271,7 +271,7 @@ def run_ours(args):
         if world > 1:
             with torch.cuda.stream(stream):
                 for k in planes:
-                    dist.all_gather_into_tensor(gathered[k].view(-1), planes[k].view(-1))
+                    dist.all_gather_into_tensor(gathered[k].view(torch.uint8).view(-1), planes[k].view(torch.uint8).view(-1))
         e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0

@@ -220,6 +220,149 @@ typedef struct hl_ospfv2_result {
 } hl_ospfv2_result;
 
 
+/* ------------------------------------------------------------------ OSPFv3 -- */
+
+/* Router-LSA link (holo-ospf/src/ospfv3/packet/lsa.rs LsaRouterLink); link_type uses
+ * HL_LINK_P2P / HL_LINK_TRANSIT / HL_LINK_VLINK (OSPFv3 Router-LSAs carry no stub links). */
+typedef struct hl_ospfv3_link {
+    uint32_t iface_id;
+    uint32_t nbr_iface_id;
+    uint32_t nbr_router_id;
+    uint16_t metric;
+    uint8_t  link_type;
+    uint8_t  _pad;
+} hl_ospfv3_link;
+
+#define HL_V3_OPT_R  0x01u   /* Options::R  */
+#define HL_V3_OPT_V6 0x02u   /* Options::V6 */
+
+/* Router-LSA fragments in LsaKey order (adv_rtr, lsa_id): all fragments of one
+ * advertising router form ONE vertex (RFC 5340 4.8.1, ospfv3/spf.rs:316-342). */
+typedef struct hl_ospfv3_router_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint16_t age;
+    uint8_t  flags;        /* HL_RTR_FLAG_* */
+    uint8_t  options;      /* HL_V3_OPT_*   */
+    uint32_t link_off;
+    uint32_t n_links;
+} hl_ospfv3_router_lsa;
+
+/* Network-LSAs keyed (adv_rtr, lsa_id = DR interface id); attached routers ascending. */
+typedef struct hl_ospfv3_network_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint16_t age;
+    uint16_t _pad;
+    uint32_t att_off;
+    uint32_t n_att;
+} hl_ospfv3_network_lsa;
+
+/* IP address / prefix of either family.  Order: IPv4 before IPv6 (IpAddr / IpNetwork
+ * derived Ord), then address bytes, then prefix length. */
+typedef struct hl_ip_addr { uint8_t bytes[16]; uint8_t is_v6; uint8_t _pad[3]; } hl_ip_addr;
+
+#define HL_PFX_OPT_NU 0x01u   /* PrefixOptions::NU: not used in the routing calculation */
+typedef struct hl_ospfv3_prefix {
+    hl_ip_addr addr;       /* already masked */
+    uint8_t  len;
+    uint8_t  options;
+    uint16_t metric;
+} hl_ospfv3_prefix;
+
+/* Intra-Area-Prefix-LSAs in LsaKey order (ospfv3/spf.rs:420-477). */
+#define HL_V3_REF_ROUTER  1u
+#define HL_V3_REF_NETWORK 2u
+typedef struct hl_ospfv3_iap_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint16_t age;
+    uint8_t  ref_type;     /* HL_V3_REF_*; 0 = something else (ignored) */
+    uint8_t  _pad;
+    uint32_t ref_lsa_id;
+    uint32_t ref_adv_rtr;
+    uint32_t prefix_off;   /* into prefixes[] */
+    uint32_t n_prefixes;
+} hl_ospfv3_iap_lsa;
+
+/* Link-LSAs of the local interfaces' link-scope LSDBs (ospfv3/spf.rs:592-611). */
+typedef struct hl_ospfv3_link_lsa {
+    uint32_t iface;        /* index into ifaces[]: whose link-scope LSDB holds it */
+    uint32_t adv_rtr;
+    uint32_t lsa_id;       /* the neighbour's interface id */
+    uint16_t age;
+    uint16_t _pad;
+    hl_ip_addr linklocal;
+} hl_ospfv3_link_lsa;
+
+/* Local interfaces of the area; next hops are found by system ifindex ==
+ * Router-LSA link iface_id (get_by_ifindex, ospfv3/spf.rs:187-190). */
+typedef struct hl_ospfv3_iface {
+    uint32_t ifindex;
+    uint32_t sort_key;     /* arena index order (NexthopKey order) */
+    uint8_t  if_type;      /* HL_IF_* */
+    uint8_t  _pad[3];
+} hl_ospfv3_iface;
+
+typedef struct hl_ospfv3_area {
+    uint32_t router_id;
+    uint32_t area_id;
+    uint16_t max_paths;
+    uint8_t  af_ipv6;      /* instance address family is IPv6 unicast: V6-bit required */
+    uint8_t  _pad;
+    uint32_t n_router_lsas;  const hl_ospfv3_router_lsa *router_lsas;
+    uint32_t n_links;        const hl_ospfv3_link *links;
+    uint32_t n_network_lsas; const hl_ospfv3_network_lsa *network_lsas;
+    uint32_t n_attached;     const uint32_t *attached;
+    uint32_t n_iap_lsas;     const hl_ospfv3_iap_lsa *iap_lsas;
+    uint32_t n_prefixes;     const hl_ospfv3_prefix *prefixes;
+    uint32_t n_ifaces;       const hl_ospfv3_iface *ifaces;
+    uint32_t n_link_lsas;    const hl_ospfv3_link_lsa *link_lsas;
+} hl_ospfv3_area;
+
+typedef struct hl_nexthop6 {
+    uint32_t iface;        /* index into hl_ospfv3_area.ifaces */
+    uint32_t nbr_router_id;
+    hl_ip_addr addr;
+    uint8_t  has_addr;
+    uint8_t  has_nbr;
+    uint8_t  _pad[2];
+} hl_nexthop6;
+
+typedef struct hl_spt_vertex6 {   /* VertexId::Network{router_id, iface_id} < Router{router_id} */
+    uint32_t router_id;
+    uint32_t iface_id;     /* networks only */
+    uint32_t distance;
+    uint16_t hops;
+    uint8_t  is_router;
+    uint8_t  _pad;
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_spt_vertex6;
+
+typedef struct hl_route_net6 {
+    hl_ip_addr prefix;
+    uint8_t  len;
+    uint8_t  flags;        /* HL_ROUTE_CONNECTED */
+    uint8_t  origin_type;  /* 1 router, 2 network */
+    uint8_t  prefix_options;
+    uint32_t metric;
+    uint32_t origin_adv_rtr;
+    uint32_t origin_lsa_id;
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_route_net6;
+
+typedef struct hl_ospfv3_result {
+    uint32_t vertices_cap, n_vertices;   hl_spt_vertex6 *vertices;
+    uint32_t routers_cap,  n_routers;    hl_route_rtr   *routers;
+    uint32_t routes_cap,   n_routes;     hl_route_net6  *routes;
+    uint32_t nexthops_cap, n_nexthops;   hl_nexthop6    *nexthops;
+    uint8_t  transit_capability;
+    uint8_t  root_found;
+    uint8_t  _pad[2];
+} hl_ospfv3_result;
+
 /* ------------------------------------------------------------------- IS-IS -- */
 
 /* LanId / VertexId key: (SystemId as 48-bit big-endian value << 8) | pseudonode.

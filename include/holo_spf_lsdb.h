@@ -57,6 +57,20 @@ uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t 
  */
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
 
+/* ---- OSPFv3 ----------------------------------------------------------------
+ *   hspf_ospfv3_run_area  <->  run_area<Ospfv3>() + update_rib_intra_area()
+ *                              (holo-ospf/src/spf.rs:587-729 with the SpfVersion hooks of
+ *                              holo-ospf/src/ospfv3/spf.rs:164-477, route.rs:343-446)
+ */
+typedef struct hspf_ospfv3_flat hspf_ospfv3_flat;
+int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out);
+void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat);
+int hspf_ospfv3_flat_csr(const hspf_ospfv3_flat *flat, hspf_csr *out);
+int hspf_ospfv3_flat_vertices(const hspf_ospfv3_flat *flat, const uint32_t **router_ids, const uint32_t **iface_ids,
+                              const uint8_t **is_router, uint32_t *n_vertices);
+uint32_t hspf_ospfv3_flat_router_vertex(const hspf_ospfv3_flat *flat, uint32_t router_id);
+int hspf_ospfv3_run_area(hspf_ctx *ctx, const hl_ospfv3_area *area, hl_ospfv3_result *out);
+
 /* ---- IS-IS -------------------------------------------------------------------
  *   hspf_isis_compute_spt  <->  compute_spt(level, root_system_id, local = false,
  *                               mt_id, metric_mode, ..)  holo-isis/src/spf.rs:525-707,

@@ -101,3 +101,11 @@ def isis_compute_spt(level, root_system_id: int):
     s = level.as_struct()
     return isis._call_spt(L.oracle_isis_compute_spt, len(level.lsps), len(level.reaches),
                           (C.byref(s), C.c_uint64(root_system_id)))
+
+
+def ospfv3_run_area(area):
+    """Reference-faithful OSPFv3 run_area + update_rib_intra_area over an LSDB image."""
+    from holo_b200 import ospfv3
+    L = lib()
+    L.oracle_ospfv3_run_area.argtypes = [C.POINTER(ospfv3.AreaStruct), C.POINTER(ospfv3.ResultStruct)]
+    return ospfv3._call_run_area(L.oracle_ospfv3_run_area, area)

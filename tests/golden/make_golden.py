@@ -103,11 +103,84 @@ def extract_ospfv2(ref: Path):
     return out
 
 
+V3_LINK_TYPES = {"point-to-point-link": 1, "transit-network-link": 2, "virtual-link": 4}
+V3_BITS = {"abr-bit": 0x01, "asbr-bit": 0x02, "vlink-end-bit": 0x04}
+
+
+def extract_ospfv3(ref: Path):
+    """OSPFv3 snapshots: Router/Network/Intra-Area-Prefix LSAs, the interfaces with their
+    interface ids, neighbours and link-scope Link-LSAs, and the golden local-rib."""
+    base = ref / "holo-ospf/tests/conformance/ospfv3/topologies"
+    out = []
+    for topo in sorted(p for p in base.iterdir() if p.is_dir()):
+        for rt in sorted(p for p in topo.iterdir() if p.is_dir()):
+            st = rt / "output" / "northbound-state.json"
+            if not st.exists():
+                continue
+            o = ospf_root(json.loads(st.read_text()))
+            snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"), "areas": [], "local_rib": []}
+            for a in o.get("areas", {}).get("area", []):
+                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "iap_lsas": [], "interfaces": []}
+                for t in a.get("database", {}).get("area-scope-lsa-type", []):
+                    for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
+                        h = l["ospfv3"]["header"]
+                        b = l["ospfv3"].get("body", {})
+                        if "router" in b:
+                            r = b["router"]
+                            flags = 0
+                            for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
+                                flags |= V3_BITS.get(bit, 0)
+                            opts = r.get("lsa-options", {}).get("lsa-options", [])
+                            links = [[V3_LINK_TYPES[x["type"]], x["interface-id"], x["neighbor-interface-id"],
+                                      x["neighbor-router-id"], x["metric"]] for x in r.get("links", {}).get("link", [])]
+                            area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
+                                                        "r": "r-bit" in opts, "v6": "v6-bit" in opts, "links": links})
+                        elif "network" in b:
+                            area["network_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
+                                                         "attached": b["network"].get("attached-routers", {}).get("attached-router", [])})
+                        elif "intra-area-prefix" in b:
+                            p = b["intra-area-prefix"]
+                            pf = [[x["prefix"], x.get("metric", 0), x.get("prefix-options", {}).get("prefix-options", [])]
+                                  for x in p.get("prefixes", {}).get("prefix", [])]
+                            area["iap_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
+                                                     "ref_type": p["referenced-ls-type"],
+                                                     "ref_id": p["referenced-link-state-id"],
+                                                     "ref_adv": p["referenced-adv-router"], "prefixes": pf})
+                for i in a.get("interfaces", {}).get("interface", []):
+                    llsas = []
+                    for t in i.get("database", {}).get("link-scope-lsa-type", []):
+                        for l in t.get("link-scope-lsas", {}).get("link-scope-lsa", []):
+                            b = l["ospfv3"].get("body", {})
+                            if "link" in b:
+                                llsas.append([l["adv-router"], l["ospfv3"]["header"]["lsa-id"],
+                                              b["link"]["link-local-interface-address"]])
+                    area["interfaces"].append({"name": i["name"], "state": i.get("state"),
+                                               "interface_id": i.get("interface-id"),
+                                               "neighbors": [[x["neighbor-router-id"], x["address"]]
+                                                             for x in i.get("neighbors", {}).get("neighbor", [])],
+                                               "link_lsas": llsas})
+                for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
+                    area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
+                                               "state": "virtual-link", "interface_id": v.get("interface-id"),
+                                               "neighbors": [], "link_lsas": []})
+                snap["areas"].append(area)
+            for r in o.get("local-rib", {}).get("route", []):
+                nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
+                       for n in r.get("next-hops", {}).get("next-hop", [])]
+                snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
+                                          "type": r.get("route-type"), "nexthops": nhs})
+            out.append(snap)
+    return out
+
+
 def main():
     ref = Path(sys.argv[1]) if len(sys.argv) > 1 else Path("/root/reference")
     v2 = extract_ospfv2(ref)
     (HERE / "ospfv2.json").write_text(json.dumps(v2, separators=(",", ":"), sort_keys=True))
     print(f"ospfv2: {len(v2)} router snapshots -> {HERE / 'ospfv2.json'}")
+    v3 = extract_ospfv3(ref)
+    (HERE / "ospfv3.json").write_text(json.dumps(v3, separators=(",", ":"), sort_keys=True))
+    print(f"ospfv3: {len(v3)} router snapshots -> {HERE / 'ospfv3.json'}")
     try:
         from make_golden_isis import extract_isis   # optional second extractor
         isis = extract_isis(ref)

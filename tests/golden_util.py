@@ -103,3 +103,73 @@ def golden_intra(snap):
         nh = sorted(((n[0], n[1]) for n in r["nexthops"]), key=lambda x: (x[0] or "", x[1] or ""))
         out[r["prefix"]] = (r["metric"], nh)
     return out
+
+
+# ------------------------------------------------------------------------------ OSPFv3
+def load_ospfv3():
+    return json.loads((GOLDEN / "ospfv3.json").read_text())
+
+
+def ospfv3_area_image(snap, area):
+    """hl_ospfv3_area for one area of a golden OSPFv3 snapshot."""
+    from holo_b200 import ospfv3
+    rl = sorted(area["router_lsas"], key=lambda l: (ip(l["adv"]), l["id"]))
+    links, rlsa = [], []
+    for l in rl:
+        rlsa.append((ip(l["adv"]), l["id"], 1, l["flags"], (ospfv3.OPT_R if l["r"] else 0) | (ospfv3.OPT_V6 if l["v6"] else 0),
+                     len(links), len(l["links"])))
+        links += [(ifid, nifid, ip(nrid), metric, ty, 0) for (ty, ifid, nifid, nrid, metric) in l["links"]]
+    nl = sorted(area["network_lsas"], key=lambda l: (ip(l["adv"]), l["id"]))
+    nlsa, att = [], []
+    for l in nl:
+        a = sorted(ip(x) for x in l["attached"])
+        nlsa.append((ip(l["adv"]), l["id"], 1, 0, len(att), len(a)))
+        att += a
+    il = sorted(area["iap_lsas"], key=lambda l: (ip(l["adv"]), l["id"]))
+    iaps, prefixes = [], []
+    for l in il:
+        ref = {"ospfv3-router-lsa": ospfv3.REF_ROUTER, "ospfv3-network-lsa": ospfv3.REF_NETWORK}.get(l["ref_type"], 0)
+        off = len(prefixes)
+        for (p, metric, opts) in l["prefixes"]:
+            net = ipaddress.ip_network(p, strict=False)
+            prefixes.append((ospfv3.ip_rec(net.network_address), net.prefixlen,
+                             ospfv3.PFX_NU if "nu-bit" in opts else 0, metric))
+        iaps.append((ip(l["adv"]), l["id"], 1, ref, 0, l["ref_id"], ip(l["ref_adv"]), off, len(prefixes) - off))
+    ifs = sorted(area["interfaces"], key=lambda i: i["name"].encode())
+    ifaces, llsas, names = [], [], []
+    for i, f in enumerate(ifs):
+        if f["state"] == "virtual-link":
+            ty = 4
+        elif f["state"] == "loopback":
+            ty = 5
+        elif f["state"] == "point-to-point":
+            ty = 0
+        else:
+            ty = 1
+        ifaces.append((f["interface_id"] or 0, i + 1, ty, (0, 0, 0)))
+        names.append(f["name"])
+        for (adv, lsid, ll) in f["link_lsas"]:
+            llsas.append((i, ip(adv), lsid, 1, 0, ospfv3.ip_rec(ll)))
+    img = ospfv3.Ospfv3Area(router_id=ip(snap["router_id"]), area_id=ip(area["area_id"]))
+    mk = lambda rows, dt: np.asarray(rows, dtype=dt) if rows else np.zeros(0, dt)
+    img.router_lsas, img.links = mk(rlsa, ospfv3.ROUTER_LSA_DT), mk(links, ospfv3.LINK_DT)
+    img.network_lsas, img.attached = mk(nlsa, ospfv3.NETWORK_LSA_DT), np.asarray(att, dtype=np.uint32)
+    img.ifaces = mk(ifaces, ospfv3.IFACE_DT)
+    for name, rows, dt in (("iap_lsas", iaps, ospfv3.IAP_LSA_DT), ("prefixes", prefixes, ospfv3.PREFIX_DT),
+                           ("link_lsas", llsas, ospfv3.LINK_LSA_DT)):
+        arr = np.zeros(len(rows), dt)
+        for k, r in enumerate(rows):
+            arr[k] = r
+        setattr(img, name, arr)
+    img.ifnames = names
+    return img
+
+
+def routes6_as_dict(res, names):
+    from holo_b200 import ospfv3
+    out = {}
+    for r in res.routes:
+        key = f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"
+        nh = sorted((names[i], a) for (i, a, _n) in res.nh(r))
+        out[key] = (int(r["metric"]), nh)
+    return out

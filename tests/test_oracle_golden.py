@@ -44,3 +44,29 @@ def test_ospfv2_oracle_reproduces_reference_local_rib(snap):
         assert _norm(got[prefix][1]) == _norm(nh), (prefix, got[prefix][1], nh)
         n_checked += 1
     assert n_checked > 0
+
+
+SNAPS_V3 = gu.load_ospfv3()
+
+
+@pytest.mark.parametrize("snap", SNAPS_V3, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_V3])
+def test_ospfv3_oracle_reproduces_reference_local_rib(snap):
+    want = gu.golden_intra(snap)
+    per_area = []
+    for area in snap["areas"]:
+        img = gu.ospfv3_area_image(snap, area)
+        res = pyoracle.ospfv3_run_area(img)
+        assert res.rc == 0
+        if res.root_found:
+            per_area.append(gu.routes6_as_dict(res, img.ifnames))
+    got = gu.merge_area_routes(per_area)
+    has_vlink = any(i["state"] == "virtual-link" for a in snap["areas"] for i in a["interfaces"])
+    n_checked = 0
+    for prefix, (metric, nh) in want.items():
+        assert prefix in got, f"missing {prefix}"
+        assert got[prefix][0] == metric, (prefix, got[prefix], metric)
+        if has_vlink and not got[prefix][1]:
+            continue    # virtual-link next hops are filled by update_rib_transit_area
+        assert _norm(got[prefix][1]) == _norm(nh), (prefix, got[prefix][1], nh)
+        n_checked += 1
+    assert n_checked > 0

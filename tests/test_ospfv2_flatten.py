@@ -53,3 +53,27 @@ def test_flatten_golden_snapshots():
     for snap in gu.load_ospfv2():
         for area in snap["areas"]:
             check_flat_against_lsdb_oracle(gu.ospfv2_area_image(snap, area))
+
+
+def test_ospfv3_flatten_agrees_with_lsdb_oracle():
+    from holo_b200 import ospfv3
+    for seed, kw, root, frag in [(1, {}, 0, 0), (6, dict(cost_choices=[10, 20], lan_fraction=0.1), 5, 3)]:
+        t = synth.random_topology(150, 700, synth.SEED_BASE + seed, **kw)
+        area = ospfv3.synth_area(t, root=root, max_links_per_fragment=frag)
+        ref = pyoracle.ospfv3_run_area(area)
+        f = ospfv3.Flat(area)
+        spt = pyoracle.csr_spf(f.csr, f.router_vertex(area.router_id), nh_words=4)
+        want = {(int(v["is_router"]), int(v["router_id"]), int(v["iface_id"])): (int(v["distance"]), int(v["hops"]))
+                for v in ref.vertices}
+        got = {(int(f.is_router[v]), int(f.router_ids[v]), int(f.iface_ids[v])): (int(spt["dist"][v]), int(spt["hops"][v]))
+               for v in range(f.csr.n_vertices) if spt["dist"][v] != 0xFFFFFFFF}
+        assert got == want
+    for snap in gu.load_ospfv3():
+        for area in snap["areas"]:
+            img = gu.ospfv3_area_image(snap, area)
+            ref = pyoracle.ospfv3_run_area(img)
+            f = ospfv3.Flat(img)
+            if not ref.root_found:
+                continue
+            spt = pyoracle.csr_spf(f.csr, f.router_vertex(img.router_id), nh_words=4)
+            assert (spt["dist"] != 0xFFFFFFFF).sum() == len(ref.vertices)
