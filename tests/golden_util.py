@@ -173,3 +173,82 @@ def routes6_as_dict(res, names):
         nh = sorted((names[i], a) for (i, a, _n) in res.nh(r))
         out[key] = (int(r["metric"]), nh)
     return out
+
+
+# ------------------------------------------------------------------------------ IS-IS
+def load_isis():
+    return json.loads((GOLDEN / "isis.json").read_text())
+
+
+def lan_id(s: str) -> int:
+    """'0000.0000.0003.01' -> (sysid << 8) | pseudonode"""
+    parts = s.split(".")
+    sysid = int("".join(parts[:3]), 16)
+    return (sysid << 8) | int(parts[3], 16)
+
+
+def isis_level_image(snap, level, mt_id=None):
+    from holo_b200 import isis
+    mtype = {"old-only": isis.METRIC_STANDARD, "wide-only": isis.METRIC_WIDE, "both": isis.METRIC_BOTH}[snap["metric_type"]]
+    lsps, reaches = [], []
+    for l in level["lsps"]:
+        lid, frag = l["id"].split("-")
+        flags = 0
+        if "lsp-overload-flag" in l["flags"]:
+            flags |= isis.LSPF_OL
+        if l["protocols"] is not None:
+            flags |= isis.LSPF_HAS_PROTOCOLS
+            if 204 in l["protocols"]:
+                flags |= isis.LSPF_NLPID_IPV4
+            if 142 in l["protocols"]:
+                flags |= isis.LSPF_NLPID_IPV6
+        rr = [(lan_id(n), m, 0, isis.REACH_LEGACY, 0) for (n, m, _mt) in l["is"]]
+        rr += [(lan_id(n), m, 0, isis.REACH_EXT, 0) for (n, m, _mt) in l["ext_is"]]
+        rr += [(lan_id(n), m, 2 if mt is None else mt, isis.REACH_MT, 0) for (n, m, mt) in l["mt_is"]]
+        lsps.append((lan_id(lid), 1, 1200, int(frag, 16), flags, len(reaches), len(rr)))
+        reaches += rr
+    lv = isis.IsisLevel(metric_type=mtype, mt_id=isis.MT_STANDARD if mt_id is None else mt_id,
+                        ipv4_enabled="ipv4" in snap["afs"], ipv6_enabled="ipv6" in snap["afs"])
+    la = np.zeros(len(lsps), isis.LSP_DT)
+    for i, x in enumerate(lsps):
+        la[i] = x
+    lv.lsps = la[np.lexsort((la["fragment"], la["lan_id"]))]
+    ra = np.zeros(len(reaches), isis.REACH_DT)
+    for i, x in enumerate(reaches):
+        ra[i] = x
+    # reach_off refers to the unsorted reach array, which is fine (offsets travel with the LSP)
+    lv.reaches = ra
+    return lv
+
+
+def isis_expected_ipv4_routes(snap, level, spt):
+    """IPv4 routes implied by an SPT: metric = dist + prefix metric (route.rs:97), next hops
+    = adjacencies of the next-hop systems of the best vertices (route.rs:105-139)."""
+    mtype = snap["metric_type"]
+    by_lan = {}
+    for l in level["lsps"]:
+        by_lan.setdefault(lan_id(l["id"].split("-")[0]), []).append(l)
+    adj = {}
+    for a in snap["adjacencies"]:
+        if a["state"] == "up" and a["ipv4"]:
+            adj.setdefault(int(a["sysid"].replace(".", ""), 16), []).append((a["iface"], a["ipv4"][0]))
+    best = {}
+    for v in spt.vertices:
+        nh = set()
+        for sid in spt.nexthops[int(v["nh_off"]): int(v["nh_off"]) + int(v["n_nh"])]:
+            for x in adj.get(int(sid), []):
+                nh.add(x)
+        for l in by_lan.get(int(v["lan_id"]), []):
+            pf = []
+            if mtype in ("old-only", "both"):
+                pf += l["ipv4_int"] + l["ipv4_ext"]
+            if mtype in ("wide-only", "both"):
+                pf += l["ext_ipv4"]
+            for (p, m, _mt) in pf:
+                tot = int(v["distance"]) + m
+                cur = best.get(p)
+                if cur is None or tot < cur[0]:
+                    best[p] = (tot, set(nh))
+                elif tot == cur[0]:
+                    cur[1].update(nh)
+    return best

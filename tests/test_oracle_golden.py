@@ -70,3 +70,29 @@ def test_ospfv3_oracle_reproduces_reference_local_rib(snap):
         assert _norm(got[prefix][1]) == _norm(nh), (prefix, got[prefix][1], nh)
         n_checked += 1
     assert n_checked > 0
+
+
+SNAPS_ISIS = gu.load_isis()
+
+
+@pytest.mark.parametrize("snap", SNAPS_ISIS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_ISIS])
+def test_isis_oracle_reproduces_reference_local_rib(snap):
+    """compute_spt restatement vs the reference's golden IS-IS local-rib: IPv4 route metrics
+    (= SPT distances + prefix metrics) and next hops (= first-hop systems' adjacencies)."""
+    import ipaddress
+    n_checked = 0
+    root = int(snap["system_id"].replace(".", ""), 16)
+    for level in snap["levels"]:
+        lv = gu.isis_level_image(snap, level)
+        spt = pyoracle.isis_compute_spt(lv, root)
+        assert spt.rc == 0
+        got = gu.isis_expected_ipv4_routes(snap, level, spt)
+        for r in snap["local_rib"]:
+            if r["level"] != level["level"] or ":" in r["prefix"] or r["prefix"] == "0.0.0.0/0":
+                continue
+            assert r["prefix"] in got, r["prefix"]
+            metric, nh = got[r["prefix"]]
+            assert metric == r["metric"], (r["prefix"], metric, r["metric"])
+            assert sorted(nh) == sorted((a, b) for a, b in r["nexthops"]), (r["prefix"], nh, r["nexthops"])
+            n_checked += 1
+    assert n_checked > 0
