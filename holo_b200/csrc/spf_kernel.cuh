@@ -38,7 +38,6 @@ constexpr int kThreads = 512;
 constexpr int kMaxOv = 8;          // HSPF_MAX_OVERRIDES
 constexpr int kMaxRootDeg = 256;   // non-HOP root neighbours tracked in smem
 constexpr int kWarps = kThreads / 32;
-constexpr int kStage = 64;         // DAG edges staged per warp pass in the Kahn phase
 constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
 constexpr uint32_t kGfNoHopTargetNoNh = 1u, kGfHopCount = 2u;
 constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
@@ -57,7 +56,6 @@ struct Layout {   // byte offsets into the per-CTA state block
     uint32_t dist, qa, qb, pend, bm0, bm1;     // SSSP
     uint32_t fl_hop, fl_leaf, fl_lur;          // vertex-flag bitmaps (whole kernel)
     uint32_t kq0, kq1, hops, dagbit, fpbit;    // parents + Kahn
-    uint32_t stage_e, stage_k;                 // Kahn per-warp staging [warps][kStage]
     uint32_t total;
 };
 
@@ -102,17 +100,8 @@ inline Layout make_layout(uint32_t V, uint32_t E, int qsz) {
     L.fl_leaf = (uint32_t)o; o += sz_bm;
     L.fl_lur = (uint32_t)o; o += sz_bm;
     // parents/Kahn arrays: alias onto SSSP arrays that are dead by then, else append
-    const size_t sz_se = (size_t)kWarps * kStage * 4, sz_sk = align_up((size_t)kWarps * kStage, 16);
-    if (2 * sz_eb + sz_se + sz_sk <= sz_q) {
-        L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb;
-        L.stage_e = L.fpbit + (uint32_t)sz_eb; L.stage_k = L.stage_e + (uint32_t)sz_se;
-    } else if (2 * sz_eb <= sz_q) {
-        L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb;
-        L.stage_e = (uint32_t)o; o += sz_se; L.stage_k = (uint32_t)o; o += sz_sk;
-    } else {
-        L.dagbit = (uint32_t)o; o += sz_eb; L.fpbit = (uint32_t)o; o += sz_eb;
-        L.stage_e = (uint32_t)o; o += sz_se; L.stage_k = (uint32_t)o; o += sz_sk;
-    }
+    if (2 * sz_eb <= sz_q) { L.dagbit = L.qa; L.fpbit = L.qa + (uint32_t)sz_eb; }
+    else { L.dagbit = (uint32_t)o; o += sz_eb; L.fpbit = (uint32_t)o; o += sz_eb; }
     L.hops = L.qb;                                   // sz_hops <= sz_q always (qsz >= 2)
     if (2 * sz_q <= sz_dist) { L.kq0 = L.dist; L.kq1 = L.dist + (uint32_t)sz_q; }
     else { L.kq0 = (uint32_t)o; o += sz_q; L.kq1 = (uint32_t)o; o += sz_q; }
@@ -174,7 +163,7 @@ __device__ __forceinline__ bool expands(uint32_t fl, uint32_t u, uint32_t root) 
 // Compact the set bits of a V-bit bitmap into queue `q` (vertex ids, any order),
 // clearing the bitmap; `keep(v)` filters.  One word per thread, warp-aggregated
 // reservation in *counter.  Call from all threads; the caller supplies the barriers.
-template <typename VT, typename Keep>
+template <bool kFilter, typename VT, typename Keep>
 __device__ __forceinline__ void bitmap_to_queue(uint32_t *bm, uint32_t nbw, VT *q, uint32_t *counter, Keep keep) {
     for (uint32_t w0 = 0; w0 < nbw; w0 += kThreads) {
         const uint32_t w = w0 + threadIdx.x;
@@ -183,12 +172,14 @@ __device__ __forceinline__ void bitmap_to_queue(uint32_t *bm, uint32_t nbw, VT *
             bits = bm[w];
             if (bits) {
                 bm[w] = 0;
-                uint32_t kept = 0;
-                for (uint32_t b = bits; b; b &= b - 1) {
-                    const uint32_t bit = __ffs(b) - 1;
-                    if (keep(w * 32 + bit)) kept |= 1u << bit;
+                if (kFilter) {
+                    uint32_t kept = 0;
+                    for (uint32_t b = bits; b; b &= b - 1) {
+                        const uint32_t bit = __ffs(b) - 1;
+                        if (keep(w * 32 + bit)) kept |= 1u << bit;
+                    }
+                    bits = kept;
                 }
-                bits = kept;
             }
         }
         const uint32_t n = __popc(bits);
@@ -241,8 +232,6 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
     uint32_t *fl_hop = reinterpret_cast<uint32_t *>(base + L.fl_hop);
     uint32_t *fl_leaf = reinterpret_cast<uint32_t *>(base + L.fl_leaf);
     uint32_t *fl_lur = reinterpret_cast<uint32_t *>(base + L.fl_lur);
-    uint32_t *stage_e = reinterpret_cast<uint32_t *>(base + L.stage_e) + (threadIdx.x >> 5) * kStage;
-    uint8_t *stage_k = reinterpret_cast<uint8_t *>(base + L.stage_k) + (threadIdx.x >> 5) * kStage;
     VT *kq0 = reinterpret_cast<VT *>(base + L.kq0);
     VT *kq1 = reinterpret_cast<VT *>(base + L.kq1);
     uint16_t *hops_s = reinterpret_cast<uint16_t *>(base + L.hops);
@@ -361,59 +350,50 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 if (n_cur == 0) break;
                 long long t_sub = 0;
                 if (a.prof && tid == 0) { t_sub = clock64(); a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; }
-                // Warp-cooperative expansion: 32 frontier vertices per warp pass; their edge
-                // lists are concatenated and relaxed 32 edges at a time, one per lane, so a
-                // pass costs one row fetch + ceil(edges/32) edge fetches instead of
-                // max-degree sequential fetches with mostly idle lanes.
+                // Team expansion: a warp pass covers 32 frontier vertices as 4 independent
+                // streams of 8 vertices; each vertex is served by a team of 4 lanes that
+                // strides over its edge list.  No prefix sums or owner searches, the four
+                // streams give the scheduler independent work, and an edge fetch covers
+                // 4 x 32 edges per iteration.
                 for (uint32_t i0 = (tid >> 5) * 32; i0 < n_cur; i0 += kThreads) {
-                    const uint32_t i = i0 + lane;
-                    uint32_t u = 0, du = 0, eb = 0, deg = 0;
-                    if (i < n_cur) {
-                        u = qcur[i];
-                        du = dist[u];
-                        if (vexpands(u, root)) { eb = g.row[u]; deg = g.row[u + 1] - eb; }
+                    const uint32_t sub = lane & 3, tv = lane >> 2;
+                    uint32_t du[4], eb[4], ee[4], uu[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        const uint32_t i = i0 + st * 8 + tv;
+                        uu[st] = (i < n_cur) ? (uint32_t)qcur[i] : kInf;
                     }
-                    uint32_t incl = deg;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ((int)lane >= o) incl += t;
+                    for (int st = 0; st < 4; ++st) {
+                        du[st] = 0; eb[st] = 0; ee[st] = 0;
+                        if (uu[st] != kInf && vexpands(uu[st], root)) {
+                            du[st] = dist[uu[st]];
+                            eb[st] = g.row[uu[st]];
+                            ee[st] = g.row[uu[st] + 1];
+                        }
                     }
-                    const uint32_t excl = incl - deg;
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    // up to kSB batches of 32 edges are fetched together (one L2 latency for
-                    // 128 edges), then relaxed
-                    constexpr int kSB = 4;
-                    for (uint32_t j0 = 0; j0 < total; j0 += 32 * kSB) {
-                        uint2 ec[kSB];
-                        uint32_t k_du[kSB], k_u[kSB], eidx[kSB];
+                    uint32_t maxdeg = 0;
 #pragma unroll
-                        for (int b = 0; b < kSB; ++b) {
-                            const uint32_t j = j0 + b * 32 + lane;
-                            // owner lane k: the last lane whose exclusive prefix is <= j
-                            uint32_t k = 0;
+                    for (int st = 0; st < 4; ++st) maxdeg = max(maxdeg, ee[st] - eb[st]);
+                    maxdeg = __reduce_max_sync(0xffffffffu, maxdeg);
+                    for (uint32_t k = 0; k < maxdeg; k += 4) {
+                        uint2 ec[4];
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const uint32_t cand = k + o;
-                                const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31);
-                                if (cand < 32 && ex <= j) k = cand;
-                            }
-                            const uint32_t k_eb = __shfl_sync(0xffffffffu, eb, k);
-                            const uint32_t k_ex = __shfl_sync(0xffffffffu, excl, k);
-                            k_du[b] = __shfl_sync(0xffffffffu, du, k);
-                            k_u[b] = __shfl_sync(0xffffffffu, u, k);
-                            eidx[b] = k_eb + (j - k_ex);
-                            ec[b] = (j < total) ? g.edge[eidx[b]] : make_uint2(0u, kInf);
+                        for (int st = 0; st < 4; ++st) {
+                            const uint32_t e = eb[st] + k + sub;
+                            ec[st] = (e < ee[st]) ? g.edge[e] : make_uint2(0u, kInf);
                         }
 #pragma unroll
-                        for (int b = 0; b < kSB; ++b) {
-                            uint32_t c = ec[b].y;
-                            if (!kFast)
+                        for (int st = 0; st < 4; ++st) {
+                            uint32_t c = ec[st].y;
+                            if (!kFast) {
+                                const uint32_t e = eb[st] + k + sub;
                                 for (uint32_t q = 0; q < n_ov; ++q)
-                                    if (S.ov.tail[q] == k_u[b] && S.ov.edge[q] == eidx[b] && c != kInf) c = S.ov.cost[q];
+                                    if (S.ov.tail[q] == uu[st] && S.ov.edge[q] == e && c != kInf) c = S.ov.cost[q];
+                            }
                             if (c == kInf) continue;     // padding lane or disabled edge
-                            const uint32_t nd = sat_add(k_du[b], c);
-                            const uint32_t v = ec[b].x;
+                            const uint32_t nd = sat_add(du[st], c);
+                            const uint32_t v = ec[st].x;
                             if (nd <= g.reject_above && nd < dist[v]) {
                                 // fire-and-forget: nothing below waits on an atomic's result;
                                 // the next frontier is compacted from the bitmap at round end
@@ -430,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 // every thread has consumed S.cnt[p]; recycle it for the round after next
                 if (tid == 0) S.cnt[p] = 0;
                 // next frontier = vertices marked this round (each once, the bitmap dedups)
-                bitmap_to_queue(bm_next, nbw, qnext, &S.cnt[p ^ 1], [](uint32_t) { return true; });
+                bitmap_to_queue<false>(bm_next, nbw, qnext, &S.cnt[p ^ 1], [](uint32_t) { return true; });
                 { VT *t = qcur; qcur = qnext; qnext = t; }
                 p ^= 1;
                 if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 10] += n_ - t_sub; t_sub = n_; }
@@ -575,83 +555,63 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             for (;;) {
                 const uint32_t n_cur = S.cnt[p];
                 if (n_cur == 0) break;
-                // Warp-cooperative: each lane owns one frontier vertex, finds its DAG out-edges
-                // with shared-memory bit tests only, the warp compacts them into its staging
-                // buffer, then relaxes them edge-parallel (one edge per lane).
-                for (uint32_t i0 = (tid >> 5) * 32; i0 < n_cur; i0 += kThreads) {
-                    const uint32_t i = i0 + lane;
-                    uint32_t u = 0, hu = 0, eb = 0, ee = 0, abase = 0;
+                long long t_sub = 0;
+                if (a.prof && tid == 0) t_sub = clock64();
+                // One frontier vertex per lane.  Its DAG out-edges are found with word-level
+                // scans of the shared DAG bitmap (no memory traffic), collected four at a
+                // time, and their heads fetched back to back (one L2 latency for up to four
+                // children, together with the parent's next-hop words).  The ECMP DAG is
+                // tree-like (~1.1 children per vertex), so one group is the common case.
+                for (uint32_t i = tid; i < n_cur; i += kThreads) {
+                    const uint32_t u = kcur[i];
+                    const uint32_t hu = hops_s[u];
+                    const uint32_t eb = g.row[u], ee = g.row[u + 1];
+                    if (ee == eb) continue;
+                    uint32_t abase = 0;
                     bool atoms_ok = true;
-                    if (i < n_cur) {
-                        u = kcur[i];
-                        hu = hops_s[u];
-                        eb = g.row[u]; ee = g.row[u + 1];
-                        if (hu == 0 && u != root) {
-                            atoms_ok = false;   // non-HOP vertex directly attached to the root
-                            for (uint32_t k = 0; k < S.n_roottab; ++k)
-                                if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
-                            if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
-                        }
+                    if (hu == 0 && u != root) {
+                        atoms_ok = false;   // non-HOP vertex directly attached to the root
+                        for (uint32_t k = 0; k < S.n_roottab; ++k)
+                            if (S.rt_target[k] == u) { abase = S.rt_base[k]; atoms_ok = true; break; }
+                        if (!atoms_ok) atomicOr(&S.status, kJsTooManyAtoms);
                     }
-                    // DAG out-edges of this lane's vertex: word-level scans of the DAG bitmap
-                    auto range_mask = [&](uint32_t w) -> uint32_t {   // bits of word w inside [eb, ee)
-                        uint32_t m = 0xFFFFFFFFu;
-                        if (w == (eb >> 5)) m &= 0xFFFFFFFFu << (eb & 31);
-                        if (w == ((ee - 1) >> 5)) m &= 0xFFFFFFFFu >> (31 - ((ee - 1) & 31));
-                        return m;
-                    };
-                    uint32_t nd_edges = 0;
-                    if (ee > eb)
-                        for (uint32_t w = eb >> 5; w <= ((ee - 1) >> 5); ++w) nd_edges += __popc(dagbit[w] & range_mask(w));
-                    uint32_t incl = nd_edges;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ((int)lane >= o) incl += t;
-                    }
-                    const uint32_t excl = incl - nd_edges;
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    for (uint32_t w0 = 0; w0 < total; w0 += kStage) {
-                        // stage the window [w0, w0 + kStage) of this warp's DAG edges
-                        if (nd_edges) {
-                            uint32_t pos = excl;
-                            for (uint32_t w = eb >> 5; w <= ((ee - 1) >> 5); ++w) {
-                                for (uint32_t m = dagbit[w] & range_mask(w); m; m &= m - 1) {
-                                    if (pos >= w0 && pos < w0 + kStage) {
-                                        stage_e[pos - w0] = w * 32 + (__ffs(m) - 1);
-                                        stage_k[pos - w0] = (uint8_t)lane;
-                                    }
-                                    ++pos;
-                                }
+                    uint64_t nhu[4] = {0, 0, 0, 0};
+                    bool nh_loaded = false;
+                    const uint32_t wlast = (ee - 1) >> 5;
+                    uint32_t w = eb >> 5;
+                    uint32_t m = dagbit[w] & (0xFFFFFFFFu << (eb & 31));
+                    if (w == wlast) m &= 0xFFFFFFFFu >> (31 - ((ee - 1) & 31));
+                    for (;;) {
+                        // collect up to 4 DAG edges
+                        uint32_t e_[4], v_[4];
+                        int n = 0;
+                        while (n < 4) {
+                            if (m == 0) {
+                                if (w == wlast) break;
+                                ++w;
+                                m = dagbit[w];
+                                if (w == wlast) m &= 0xFFFFFFFFu >> (31 - ((ee - 1) & 31));
+                                continue;
                             }
+                            e_[n++] = w * 32 + (__ffs(m) - 1);
+                            m &= m - 1;
                         }
-                        __syncwarp();
-                        const uint32_t wn = min((uint32_t)kStage, total - w0);
-                        constexpr int kKB = kStage / 32;   // both batches of a window are fetched together
-                        uint32_t e_[kKB], v_[kKB], ku_[kKB], khu_[kKB], keb_[kKB], kab_[kKB], kok_[kKB];
+                        if (n == 0) break;
 #pragma unroll
-                        for (int b = 0; b < kKB; ++b) {
-                            const uint32_t j = b * 32 + lane;
-                            const bool act = j < wn;
-                            e_[b] = act ? stage_e[j] : kInf;
-                            const uint32_t k = act ? stage_k[j] : 0u;
-                            ku_[b] = __shfl_sync(0xffffffffu, u, k);
-                            khu_[b] = __shfl_sync(0xffffffffu, hu, k);
-                            keb_[b] = __shfl_sync(0xffffffffu, eb, k);
-                            kab_[b] = __shfl_sync(0xffffffffu, abase, k);
-                            kok_[b] = __shfl_sync(0xffffffffu, (uint32_t)atoms_ok, k);
-                            v_[b] = act ? g.edge[e_[b]].x : 0u;
+                        for (int k = 0; k < 4; ++k) if (k < n) v_[k] = g.edge[e_[k]].x;
+                        if (hu != 0 && !nh_loaded) {
+                            for (uint32_t x = 0; x < nhw; ++x) nhu[x] = __ldcg(&o_nh[(size_t)u * nhw + x]);
+                            nh_loaded = true;
                         }
 #pragma unroll
-                        for (int b = 0; b < kKB; ++b) {
-                            const uint32_t e = e_[b];
-                            if (e == kInf) continue;
-                            const uint32_t v = v_[b];
+                        for (int k = 0; k < 4; ++k) {
+                            if (k >= n) break;
+                            const uint32_t e = e_[k], v = v_[k];
                             const bool is_fp = (fpbit[e >> 5] >> (e & 31)) & 1u;
                             const uint32_t hv = is_hop(v) ? 1u : 0u;
-                            if (khu_[b] == 0) {
-                                if (!((g.flags & kGfNoHopTargetNoNh) && !hv) && kok_[b]) {
-                                    const uint32_t atom = kab_[b] + (e - keb_[b]);
+                            if (hu == 0) {
+                                if (!((g.flags & kGfNoHopTargetNoNh) && !hv) && atoms_ok) {
+                                    const uint32_t atom = abase + (e - eb);
                                     if (atom < 64u * nhw)
                                         atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + (atom >> 6)]),
                                                  1ull << (atom & 63));
@@ -660,27 +620,28 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 }
                                 if (is_fp) hops_s[v] = (uint16_t)hv;
                             } else {
-                                for (uint32_t w = 0; w < nhw; ++w) {
-                                    const uint64_t x = __ldcg(&o_nh[(size_t)ku_[b] * nhw + w]);
-                                    if (x) atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + w]), x);
-                                }
-                                if (is_fp) hops_s[v] = (uint16_t)min(khu_[b] + hv, 0xFFFFu);
+                                for (uint32_t x = 0; x < nhw; ++x)
+                                    if (nhu[x]) atomicOr(reinterpret_cast<unsigned long long *>(&o_nh[(size_t)v * nhw + x]), nhu[x]);
+                                if (is_fp) hops_s[v] = (uint16_t)min(hu + hv, 0xFFFFu);
                             }
                             // packed u16 in-degree decrement + "touched" mark, both fire-and-forget;
                             // vertices whose counter reached zero are collected at round end
                             atomicSub(&pend32[v >> 1], 1u << ((v & 1) * 16));
                             atomicOr(&bm0[v >> 5], 1u << (v & 31));
                         }
-                        __syncwarp();
+                        if (n < 4) break;
                     }
                 }
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 13] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 14] += n_ - t_sub; t_sub = n_; }
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 6] += 1;   // Kahn rounds
                 if (tid == 0) S.cnt[p] = 0;
-                bitmap_to_queue(bm0, nbw, knext, &S.cnt[p ^ 1], [&](uint32_t v) { return pend[v] == 0; });
+                bitmap_to_queue<true>(bm0, nbw, knext, &S.cnt[p ^ 1], [&](uint32_t v) { return pend[v] == 0; });
                 { VT *t = kcur; kcur = knext; knext = t; }
                 p ^= 1;
                 __syncthreads();
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 15] += n_ - t_sub; }
             }
         }
         __syncthreads();

@@ -27,5 +27,6 @@ print("delta", delta, "total Mcycles", tot / 1e6, "per job kcycles", tot / 1000 
 print("  kahn rounds/job", out[6] / 1000, " sssp rounds/job", out[7] / 1000)
 print("  sssp per job: frontier entries", out[12] / 1000, " kcycles: expand(t0)", out[8] / 1e6, " barrier1", out[9] / 1e6,
       " compact", out[10] / 1e6, " barrier2", out[11] / 1e6)
+print("  kahn per job kcycles: expand(t0)", out[13] / 1e6, " barrier1", out[14] / 1e6, " compact+barrier2", out[15] / 1e6)
 for k, n in enumerate(names):
     print(f"  {n:8s} {100 * out[k] / tot:5.1f}%  {out[k] / 1000 / 1e3:8.1f} kcycles/job")
