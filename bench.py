@@ -68,7 +68,12 @@ def config_dict(n_gpus: int, csr, extra=None):
         "seed": hex(0x484F4C4F + CONFIG_INDEX),
         "parallelism": f"roots sharded over {n_gpus} GPU(s), graph replicated",
         "result_planes": "dist:u32 hops:u16 first_parent:u32 n_parents:u16 nh_mask:u64",
-        "l2": "flushed between timed steps (256 MiB memset, untimed); result planes are 200 MB/step/GPU > L2",
+        "l2": ("flushed between timed steps (256 MiB memset, untimed); result planes are 200 MB/step/GPU > L2"
+               if n_gpus == 1 else
+               "no explicit flush: each step writes 200 MB of result planes per GPU and receives n_gpus x 200 MB "
+               "of gathered planes (> 126 MB L2); the 0.9 MB graph is cache-resident by design"),
+        "exchange": ("none" if n_gpus == 1 else
+                     "one NCCL all-gather of the step's result planes per step, overlapped with the next step's kernel"),
     }
     if extra:
         c.update(extra)
@@ -197,6 +202,8 @@ def run_ours(args):
     t, csr = workload()
     V, E = csr.n_vertices, csr.n_edges
     ctx = capi.Context(local_rank)
+    if world > 1:
+        ctx.reserve_sms(args.reserve_sms)   # room for the NCCL all-gather beside the persistent kernel
     g = ctx.upload(csr)
     n = JOBS_PER_GPU
     roots_np = ((np.arange(n) + rank * n) % V_ROUTERS + len(t.lans)).astype(np.uint32)
@@ -204,40 +211,45 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     # ---- device-resident planes (value path) ----------------------------------------
+    # All planes of a step live in ONE byte buffer per rank so that the multi-GPU exchange
+    # is a single all-gather; two buffers so that the all-gather of step s (NCCL stream)
+    # overlaps the kernel of step s+1 (engine stream).
     d_roots = torch.from_numpy(roots_np.astype(np.int32)).to(dev)
-    planes = {
-        "dist": torch.empty((n, V), dtype=torch.int32, device=dev),
-        "hops": torch.empty((n, V), dtype=torch.int16, device=dev),
-        "fp": torch.empty((n, V), dtype=torch.int32, device=dev),
-        "npar": torch.empty((n, V), dtype=torch.int16, device=dev),
-        "nh": torch.empty((n, V, NH_WORDS), dtype=torch.int64, device=dev),
-        "status": torch.zeros((n,), dtype=torch.int32, device=dev),
-    }
-    gathered = None
-    if world > 1:
-        gathered = {k: torch.empty((world,) + tuple(v.shape), dtype=v.dtype, device=dev) for k, v in planes.items()}
+    al = lambda x: (x + 255) // 256 * 256
+    sizes = {"dist": n * V * 4, "hops": n * V * 2, "fp": n * V * 4, "npar": n * V * 2, "nh": n * V * 8 * NH_WORDS,
+             "status": n * 4}
+    offs, tot = {}, 0
+    for k, sz in sizes.items():
+        offs[k] = tot
+        tot += al(sz)
+    n_buf = 2 if world > 1 else 1
+    bufs = [torch.empty(tot, dtype=torch.uint8, device=dev) for _ in range(n_buf)]
+    gathered = torch.empty((world, tot), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
     js = capi.JobsStruct()
     js.n_jobs = n
     js.roots = C.cast(d_roots.data_ptr(), C.POINTER(C.c_uint32))
-    rs = capi.ResultStruct()
-    rs.dist = C.cast(planes["dist"].data_ptr(), C.POINTER(C.c_uint32))
-    rs.hops = C.cast(planes["hops"].data_ptr(), C.POINTER(C.c_uint16))
-    rs.first_parent = C.cast(planes["fp"].data_ptr(), C.POINTER(C.c_uint32))
-    rs.n_parents = C.cast(planes["npar"].data_ptr(), C.POINTER(C.c_uint16))
-    rs.nh_mask = C.cast(planes["nh"].data_ptr(), C.POINTER(C.c_uint64))
-    rs.nh_words = NH_WORDS
-    rs.job_status = C.cast(planes["status"].data_ptr(), C.POINTER(C.c_uint32))
 
-    def step_device():
-        """kernel (+ all-gather of the result planes at N>1) on the ctx stream"""
-        ctx.run_device(g, js, rs, sync=False)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                for k in planes:
-                    dist.all_gather_into_tensor(gathered[k].view(torch.uint8).view(-1), planes[k].view(torch.uint8).view(-1))
+    def result_struct(buf):
+        base = buf.data_ptr()
+        rs_ = capi.ResultStruct()
+        rs_.dist = C.cast(base + offs["dist"], C.POINTER(C.c_uint32))
+        rs_.hops = C.cast(base + offs["hops"], C.POINTER(C.c_uint16))
+        rs_.first_parent = C.cast(base + offs["fp"], C.POINTER(C.c_uint32))
+        rs_.n_parents = C.cast(base + offs["npar"], C.POINTER(C.c_uint16))
+        rs_.nh_mask = C.cast(base + offs["nh"], C.POINTER(C.c_uint64))
+        rs_.nh_words = NH_WORDS
+        rs_.job_status = C.cast(base + offs["status"], C.POINTER(C.c_uint32))
+        return rs_
+
+    rss = [result_struct(b) for b in bufs]
+
+    def plane(buf, k, dtype, shape):
+        return buf[offs[k]: offs[k] + sizes[k]].view(dtype).view(shape)
+
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -248,38 +260,59 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(n_steps, timed):
+        """Enqueue n_steps steps.  N=1: [flush, kernel] per step, per-step events.  N>1:
+        kernel(s) on the engine stream, all-gather(s) on the NCCL stream, double buffered."""
+        evs, k_done, ag_done = [], [None] * n_buf, [None] * n_buf
+        for s in range(n_steps):
+            b = s % n_buf
+            if world == 1:
+                flush_l2()
+            elif ag_done[b] is not None:
+                stream.wait_event(ag_done[b])          # buffer b is free again
+            e0 = torch.cuda.Event(enable_timing=True)
+            ek = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.run_device(g, js, rss[b], sync=False)
+            ek.record(stream)
+            if world > 1:
+                comm_stream.wait_event(ek)
+                with torch.cuda.stream(comm_stream):
+                    dist.all_gather_into_tensor(gathered.view(-1), bufs[b])
+                    ag_done[b] = torch.cuda.Event()
+                    ag_done[b].record(comm_stream)
+            evs.append((e0, ek))
+        if world > 1:
+            for e in ag_done:
+                if e is not None:
+                    stream.wait_event(e)
+        return evs
+
     # warm-up
-    for _ in range(args.warmup):
-        flush_l2()
-        step_device()
+    run_steps(args.warmup, False)
     barrier()
-    assert int(planes["status"].abs().sum().item()) == 0, "job_status != 0"
+    st = plane(bufs[0], "status", torch.int32, (n,))
+    assert int(st.abs().sum().item()) == 0, "job_status != 0"
 
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush_l2()
-        e0, ek, e1 = ev[s]
-        e0.record(stream)
-        ctx.run_device(g, js, rs, sync=False)
-        ek.record(stream)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                for k in planes:
-                    dist.all_gather_into_tensor(gathered[k].view(torch.uint8).view(-1), planes[k].view(torch.uint8).view(-1))
-        e1.record(stream)
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    ev = run_steps(args.steps, True)
+    t_end.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count - launches0
-    step_ms = [e0.elapsed_time(e1) for e0, _, e1 in ev]
-    kern_ms = [e0.elapsed_time(ek) for e0, ek, _ in ev]
-    total_ms = float(sum(step_ms))
+    kern_ms = [e0.elapsed_time(ek) for e0, ek in ev]
     kernel_ms_avg = float(sum(kern_ms) / len(kern_ms))
+    # N=1: the L2 flush between steps is untimed (sum of per-step kernel events); N>1: the
+    # whole pipelined region (kernels + exchanges), no flush needed (see config.l2)
+    total_ms = float(sum(kern_ms)) if world == 1 else float(t_begin.elapsed_time(t_end))
+    planes = {"dist": plane(bufs[0], "dist", torch.int32, (n, V)), "nh": plane(bufs[0], "nh", torch.int64, (n, V, NH_WORDS))}
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers --------------------------------
     h = {
@@ -388,6 +421,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=12,
+                    help="N>1 only: SMs left to the overlapped NCCL all-gather")
     ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
     args = ap.parse_args()
     global DELTA

@@ -84,6 +84,7 @@ EXPORTS = [
     "hspf_version", "hspf_ctx_create", "hspf_ctx_destroy", "hspf_last_error",
     "hspf_graph_upload", "hspf_graph_free", "hspf_run_batch", "hspf_run_batch_async",
     "hspf_sync", "hspf_stream", "hspf_launch_count", "hspf_atom_decode", "hspf_atom_count",
+    "hspf_ctx_reserve_sms",
 ]
 
 
@@ -123,6 +124,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.hspf_stream.restype = C.c_void_p
     lib.hspf_launch_count.argtypes = [C.c_void_p]
     lib.hspf_launch_count.restype = C.c_uint64
+    lib.hspf_ctx_reserve_sms.argtypes = [C.c_void_p, C.c_int]
     lib.hspf_atom_decode.argtypes = [C.POINTER(CsrStruct), C.c_uint32, C.c_uint32, _u32p, _u32p]
     lib.hspf_atom_count.argtypes = [C.POINTER(CsrStruct), C.c_uint32, _u32p]
     if path is None:
@@ -298,6 +300,9 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hspf_sync(self.handle))
+
+    def reserve_sms(self, n_sms: int):
+        self._check(self.lib.hspf_ctx_reserve_sms(self.handle, n_sms))
 
     @property
     def stream(self) -> int:

@@ -30,6 +30,8 @@ struct hspf_graph {
 struct hspf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // D2H of finished chunks (host-pointer mode)
+    cudaEvent_t chunk_done = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
     std::string err;
@@ -42,6 +44,7 @@ struct hspf_ctx {
     void *scratch = nullptr; size_t scratch_bytes = 0;  // planes the caller did not ask for
     unsigned long long *d_prof = nullptr; int prof_rows = 0;  // optional phase counters (debug)
     bool prof_enabled = false;
+    int reserved_sms = 0;     // SMs left free for concurrent kernels (e.g. NCCL), see hspf_ctx_reserve_sms
 };
 
 namespace {
@@ -130,7 +133,9 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         int v = atoi(lim);
         if (v >= 1 && v < per_sm) per_sm = v;
     }
-    int grid = ctx->sm_count * per_sm;
+    int sms = ctx->sm_count - ctx->reserved_sms;
+    if (sms < 1) sms = 1;
+    int grid = sms * per_sm;
     if (const char *mg = getenv("HSPF_MAX_GRID")) {   // tuning knob (experiments only)
         int v = atoi(mg);
         if (v >= 1 && v < grid) grid = v;
@@ -203,7 +208,11 @@ int hspf_ctx_create(int device, hspf_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HSPF_E_CUDA; }
-    if (cudaMalloc(&ctx->d_counter, sizeof(uint32_t)) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counter, sizeof(uint32_t)) != cudaSuccess) {
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
         cudaStreamDestroy(ctx->stream); delete ctx; return HSPF_E_CUDA;
     }
     *out = ctx;
@@ -214,6 +223,8 @@ void hspf_ctx_destroy(hspf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_prof) cudaFree(ctx->d_prof);
     if (ctx->ws) cudaFree(ctx->ws);
@@ -228,6 +239,12 @@ const char *hspf_last_error(const hspf_ctx *ctx) { return ctx ? ctx->err.c_str()
 void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms) {
+    if (!ctx || n_sms < 0 || n_sms >= ctx->sm_count) return HSPF_E_INVAL;
+    ctx->reserved_sms = n_sms;
+    return HSPF_OK;
+}
 
 int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]) {
     if (!ctx) return HSPF_E_INVAL;
@@ -470,16 +487,38 @@ int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, co
         dr.n_parents = reinterpret_cast<uint16_t *>(rp); rp += ps.npar;
         dr.nh_mask = reinterpret_cast<uint64_t *>(rp); rp += ps.nh;
         dr.job_status = reinterpret_cast<uint32_t *>(rp); rp += ps.status;
-        rc = enqueue(ctx, g, &dj, &dr);
-        if (rc) return rc;
-        const size_t nv = (size_t)n * V;
-        if (out->dist) CK(cudaMemcpyAsync(out->dist, dr.dist, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->hops) CK(cudaMemcpyAsync(out->hops, dr.hops, nv * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->first_parent) CK(cudaMemcpyAsync(out->first_parent, dr.first_parent, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->n_parents) CK(cudaMemcpyAsync(out->n_parents, dr.n_parents, nv * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->nh_mask) CK(cudaMemcpyAsync(out->nh_mask, dr.nh_mask, nv * 8 * out->nh_words, cudaMemcpyDeviceToHost, ctx->stream));
+        // Launch the batch in chunks of about one wave of CTAs and copy each chunk's planes
+        // back on a second stream while the next chunk computes (D2H is the e2e bound).
+        int per_sm_hint = 2;
+        uint32_t chunk = (uint32_t)std::max(1, ctx->sm_count * per_sm_hint);
+        if (const char *cs = getenv("HSPF_E2E_CHUNK")) { int v = atoi(cs); if (v > 0) chunk = (uint32_t)v; }
         std::vector<uint32_t> st(n);
-        CK(cudaMemcpyAsync(st.data(), dr.job_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint32_t cn = std::min(chunk, n - c0);
+            hspf_jobs cj = dj;
+            cj.n_jobs = cn;
+            cj.roots = dj.roots + c0;
+            if (dj.ov_off) cj.ov_off = dj.ov_off + c0;    // offsets stay absolute into ov_edge/ov_cost
+            hspf_result cr = dr;
+            const size_t o = (size_t)c0 * V;
+            cr.dist = dr.dist + o; cr.hops = dr.hops + o; cr.first_parent = dr.first_parent + o;
+            cr.n_parents = dr.n_parents + o; cr.nh_mask = dr.nh_mask + o * out->nh_words;
+            cr.job_status = dr.job_status + c0;
+            rc = enqueue(ctx, g, &cj, &cr);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->chunk_done, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
+            const size_t cv = (size_t)cn * V;
+            cudaStream_t cs = ctx->copy_stream;
+            if (out->dist) CK(cudaMemcpyAsync(out->dist + o, cr.dist, cv * 4, cudaMemcpyDeviceToHost, cs));
+            if (out->hops) CK(cudaMemcpyAsync(out->hops + o, cr.hops, cv * 2, cudaMemcpyDeviceToHost, cs));
+            if (out->first_parent) CK(cudaMemcpyAsync(out->first_parent + o, cr.first_parent, cv * 4, cudaMemcpyDeviceToHost, cs));
+            if (out->n_parents) CK(cudaMemcpyAsync(out->n_parents + o, cr.n_parents, cv * 2, cudaMemcpyDeviceToHost, cs));
+            if (out->nh_mask)
+                CK(cudaMemcpyAsync(out->nh_mask + o * out->nh_words, cr.nh_mask, cv * 8 * out->nh_words, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(st.data() + c0, cr.job_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+        }
+        CK(cudaStreamSynchronize(ctx->copy_stream));
         CK(cudaStreamSynchronize(ctx->stream));
         bool any = false;
         for (uint32_t j = 0; j < n; ++j) any |= (st[j] != 0);

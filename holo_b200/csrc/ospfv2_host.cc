@@ -361,6 +361,9 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
         (uint32_t)sizeof(hl_route_rtr), (uint32_t)sizeof(hl_route_net), (uint32_t)sizeof(hl_ospfv2_result),
         (uint32_t)sizeof(hl_isis_reach), (uint32_t)sizeof(hl_isis_lsp), (uint32_t)sizeof(hl_isis_level),
         (uint32_t)sizeof(hl_isis_vertex), (uint32_t)sizeof(hl_isis_spt),
+        (uint32_t)sizeof(hl_isis_ipreach), (uint32_t)sizeof(hl_isis_adj), (uint32_t)sizeof(hl_isis_iface),
+        (uint32_t)sizeof(hl_isis_instance), (uint32_t)sizeof(hl_isis_nexthop), (uint32_t)sizeof(hl_isis_route),
+        (uint32_t)sizeof(hl_isis_rib),
         (uint32_t)sizeof(hl_ospfv3_link), (uint32_t)sizeof(hl_ospfv3_router_lsa), (uint32_t)sizeof(hl_ospfv3_network_lsa),
         (uint32_t)sizeof(hl_ip_addr), (uint32_t)sizeof(hl_ospfv3_prefix), (uint32_t)sizeof(hl_ospfv3_iap_lsa),
         (uint32_t)sizeof(hl_ospfv3_link_lsa), (uint32_t)sizeof(hl_ospfv3_iface), (uint32_t)sizeof(hl_ospfv3_area),

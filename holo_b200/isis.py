@@ -19,7 +19,20 @@ MODE_NORMAL, MODE_HOPCOUNT = 0, 1
 
 REACH_DT = np.dtype([("neighbor", "<u8"), ("metric", "<u4"), ("mt_id", "<u2"), ("kind", "u1"), ("_pad", "u1")], align=True)
 LSP_DT = np.dtype([("lan_id", "<u8"), ("seqno", "<u4"), ("rem_lifetime", "<u2"), ("fragment", "u1"), ("flags", "u1"),
-                   ("reach_off", "<u4"), ("n_reach", "<u4")], align=True)
+                   ("reach_off", "<u4"), ("n_reach", "<u4"), ("ipreach_off", "<u4"), ("n_ipreach", "<u4")], align=True)
+IP_DT = np.dtype([("bytes", "u1", (16,)), ("is_v6", "u1"), ("_pad", "u1", (3,))], align=True)
+IPREACH_DT = np.dtype([("prefix", IP_DT), ("metric", "<u4"), ("mt_id", "<u2"), ("len", "u1"), ("kind", "u1"),
+                       ("external", "u1"), ("_pad", "u1", (3,))], align=True)
+ADJ_DT = np.dtype([("system_id", "<u8"), ("snpa", "u1", (6,)), ("up", "u1"), ("level_usage", "u1"), ("topo_std", "u1"),
+                   ("topo_ipv6", "u1"), ("has_ipv4", "u1"), ("has_ipv6", "u1"), ("area_disjoint", "u1"),
+                   ("_pad", "u1", (3,)), ("ipv4", "<u4"), ("ipv6", IP_DT)], align=True)
+IFACE_DT = np.dtype([("ifindex", "<u4"), ("metric", "<u4"), ("is_broadcast", "u1"), ("_pad", "u1", (3,)),
+                     ("adj_off", "<u4"), ("n_adj", "<u4")], align=True)
+NEXTHOP_DT = np.dtype([("system_id", "<u8"), ("iface", "<u4"), ("_pad", "<u4"), ("addr", IP_DT)], align=True)
+ROUTE_DT = np.dtype([("prefix", IP_DT), ("metric", "<u4"), ("len", "u1"), ("route_type", "u1"), ("flags", "u1"),
+                     ("_pad", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+IP_V4_INTERNAL, IP_V4_EXTERNAL, IP_V4_EXT, IP_V6, IP_MT_V6 = range(5)
+LSPF_ATT, LSPF_MT_IPV6_ATT = 0x20, 0x40
 VERTEX_DT = np.dtype([("lan_id", "<u8"), ("distance", "<u4"), ("hops", "<u2"), ("_pad", "<u2"), ("par_off", "<u4"),
                       ("n_par", "<u4"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
 
@@ -27,7 +40,20 @@ VERTEX_DT = np.dtype([("lan_id", "<u8"), ("distance", "<u4"), ("hops", "<u2"), (
 class LevelStruct(C.Structure):
     _fields_ = [("metric_type", C.c_uint8), ("mt_id", C.c_uint8), ("metric_mode", C.c_uint8),
                 ("ipv4_enabled", C.c_uint8), ("ipv6_enabled", C.c_uint8), ("_pad", C.c_uint8 * 3),
-                ("n_lsps", C.c_uint32), ("lsps", C.c_void_p), ("n_reaches", C.c_uint32), ("reaches", C.c_void_p)]
+                ("n_lsps", C.c_uint32), ("lsps", C.c_void_p), ("n_reaches", C.c_uint32), ("reaches", C.c_void_p),
+                ("n_ipreaches", C.c_uint32), ("ipreaches", C.c_void_p)]
+
+
+class InstanceStruct(C.Structure):
+    _fields_ = [("lvl", LevelStruct), ("system_id", C.c_uint64), ("max_paths", C.c_uint16), ("level", C.c_uint8),
+                ("level_type", C.c_uint8), ("att_ignore", C.c_uint8), ("mt_ipv6_enabled", C.c_uint8),
+                ("_pad", C.c_uint8 * 2), ("n_ifaces", C.c_uint32), ("ifaces", C.c_void_p),
+                ("n_adjs", C.c_uint32), ("adjs", C.c_void_p)]
+
+
+class RibStruct(C.Structure):
+    _fields_ = [("routes_cap", C.c_uint32), ("n_routes", C.c_uint32), ("routes", C.c_void_p),
+                ("nexthops_cap", C.c_uint32), ("n_nexthops", C.c_uint32), ("nexthops", C.c_void_p)]
 
 
 class SptStruct(C.Structure):
@@ -38,7 +64,9 @@ class SptStruct(C.Structure):
                 ("second_hops_cap", C.c_uint32), ("n_second_hops", C.c_uint32), ("second_hops", C.c_void_p)]
 
 
-ABI_SIZES = [REACH_DT.itemsize, LSP_DT.itemsize, C.sizeof(LevelStruct), VERTEX_DT.itemsize, C.sizeof(SptStruct)]
+ABI_SIZES = [REACH_DT.itemsize, LSP_DT.itemsize, C.sizeof(LevelStruct), VERTEX_DT.itemsize, C.sizeof(SptStruct),
+             IPREACH_DT.itemsize, ADJ_DT.itemsize, IFACE_DT.itemsize, C.sizeof(InstanceStruct), NEXTHOP_DT.itemsize,
+             ROUTE_DT.itemsize, C.sizeof(RibStruct)]
 
 
 @dataclass
@@ -50,6 +78,7 @@ class IsisLevel:
     ipv6_enabled: bool = False
     lsps: np.ndarray = field(default_factory=lambda: np.zeros(0, LSP_DT))
     reaches: np.ndarray = field(default_factory=lambda: np.zeros(0, REACH_DT))
+    ipreaches: np.ndarray = field(default_factory=lambda: np.zeros(0, IPREACH_DT))
 
     def as_struct(self) -> LevelStruct:
         s = LevelStruct()
@@ -59,6 +88,9 @@ class IsisLevel:
         self.reaches = np.ascontiguousarray(self.reaches, dtype=REACH_DT)
         s.n_lsps, s.lsps = len(self.lsps), (self.lsps.ctypes.data if len(self.lsps) else None)
         s.n_reaches, s.reaches = len(self.reaches), (self.reaches.ctypes.data if len(self.reaches) else None)
+        self.ipreaches = np.ascontiguousarray(self.ipreaches, dtype=IPREACH_DT)
+        s.n_ipreaches = len(self.ipreaches)
+        s.ipreaches = self.ipreaches.ctypes.data if len(self.ipreaches) else None
         return s
 
 
@@ -212,7 +244,7 @@ def synth_level(t: Topology, metric_type: int = METRIC_WIDE, mt_id: int = MT_STA
             chunks = [entries[i:i + max_reach_per_fragment] for i in range(0, len(entries), max_reach_per_fragment)] or [[]]
         for frag, ch in enumerate(chunks):
             rr = [x for (nbr, m) in ch for x in add_reach(nbr, m)]
-            lsps.append((lan_id, 1, 1200, frag, flags if frag == 0 else 0, len(reaches), len(rr)))
+            lsps.append((lan_id, 1, 1200, frag, flags if frag == 0 else 0, len(reaches), len(rr), 0, 0))
             reaches.extend(rr)
 
     for i in range(R):
@@ -235,3 +267,58 @@ def synth_level(t: Topology, metric_type: int = METRIC_WIDE, mt_id: int = MT_STA
         ra[i] = x
     lv.reaches = ra
     return lv
+
+
+# ------------------------------------------------------------------------------ route stage
+def instance_struct(inst: dict) -> InstanceStruct:
+    """hl_isis_instance from the dict produced by the image builders (keeps arrays alive
+    through the dict)."""
+    s = InstanceStruct()
+    s.lvl = inst["level"].as_struct()
+    s.system_id, s.max_paths = inst["system_id"], inst["max_paths"]
+    s.level, s.level_type = inst["level_no"], inst["level_type"]
+    s.att_ignore, s.mt_ipv6_enabled = inst["att_ignore"], inst["mt_ipv6"]
+    inst["ifaces"] = np.ascontiguousarray(inst["ifaces"], dtype=IFACE_DT)
+    inst["adjs"] = np.ascontiguousarray(inst["adjs"], dtype=ADJ_DT)
+    s.n_ifaces, s.ifaces = len(inst["ifaces"]), (inst["ifaces"].ctypes.data if len(inst["ifaces"]) else None)
+    s.n_adjs, s.adjs = len(inst["adjs"]), (inst["adjs"].ctypes.data if len(inst["adjs"]) else None)
+    return s
+
+
+@dataclass
+class IsisRib:
+    routes: np.ndarray
+    nexthops: np.ndarray
+    rc: int = 0
+
+    def nh(self, rec):
+        from .ospfv3 import ip_str
+        return [(int(x["iface"]), ip_str(x["addr"]), int(x["system_id"]))
+                for x in self.nexthops[int(rec["nh_off"]): int(rec["nh_off"]) + int(rec["n_nh"])]]
+
+
+def _call_rib(fn, inst: dict, prefix_args=()):
+    s = instance_struct(inst)
+    caps = [len(inst["level"].ipreaches) + 8, 16 * (len(inst["level"].ipreaches) + 8)]
+    for _ in range(2):
+        routes = np.zeros(caps[0], ROUTE_DT)
+        nhs = np.zeros(caps[1], NEXTHOP_DT)
+        r = RibStruct()
+        r.routes_cap, r.routes = caps[0], routes.ctypes.data
+        r.nexthops_cap, r.nexthops = caps[1], nhs.ctypes.data
+        rc = fn(*prefix_args, C.byref(s), C.byref(r))
+        if rc == capi.HSPF_E_NOMEM:
+            caps = [max(caps[0], r.n_routes), max(caps[1], r.n_nexthops)]
+            continue
+        break
+    return IsisRib(routes[: r.n_routes].copy(), nhs[: r.n_nexthops].copy(), rc)
+
+
+def compute_routes(ctx: capi.Context, inst: dict) -> IsisRib:
+    """compute_spt(local = true) per enabled topology + compute_routes on the GPU engine."""
+    lib = ctx.lib
+    lib.hspf_isis_compute_routes.argtypes = [C.c_void_p, C.POINTER(InstanceStruct), C.POINTER(RibStruct)]
+    res = _call_rib(lib.hspf_isis_compute_routes, inst, (ctx.handle,))
+    if res.rc != capi.HSPF_OK:
+        raise capi.HspfError(res.rc, ctx.last_error())
+    return res

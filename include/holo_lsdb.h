@@ -387,6 +387,8 @@ typedef struct hl_isis_reach {
 #define HL_LSPF_NLPID_IPV4     0x04u
 #define HL_LSPF_NLPID_IPV6     0x08u
 #define HL_LSPF_MT_IPV6_OL     0x10u  /* MT entry for topology 2 has MtFlags::OL (pdu.rs:1431-1445) */
+#define HL_LSPF_ATT            0x20u  /* LspFlags::ATT (pdu.rs:1414-1428)                        */
+#define HL_LSPF_MT_IPV6_ATT    0x40u  /* MT entry for topology 2 has MtFlags::ATT                */
 
 /* LSP fragments in LspId order (lan_id, fragment) (collections.rs:67-74).  Reach
  * entries of a fragment keep TLV order within each kind. */
@@ -398,7 +400,26 @@ typedef struct hl_isis_lsp {
     uint8_t   flags;
     uint32_t  reach_off;   /* into reaches[] */
     uint32_t  n_reach;
+    uint32_t  ipreach_off; /* into ipreaches[] (route stage only) */
+    uint32_t  n_ipreach;
 } hl_isis_lsp;
+
+/* IP reachability entry of an LSP fragment, TLV order kept within each kind
+ * (vertex_networks, holo-isis/src/spf.rs:1141-1281). */
+#define HL_ISIS_IP_V4_INTERNAL 0u   /* TLV 128 */
+#define HL_ISIS_IP_V4_EXTERNAL 1u   /* TLV 130 */
+#define HL_ISIS_IP_V4_EXT      2u   /* TLV 135 extended IPv4 reachability */
+#define HL_ISIS_IP_V6          3u   /* TLV 236 */
+#define HL_ISIS_IP_MT_V6       4u   /* TLV 237 (mt_id) */
+typedef struct hl_isis_ipreach {
+    hl_ip_addr prefix;
+    uint32_t metric;
+    uint16_t mt_id;
+    uint8_t  len;
+    uint8_t  kind;
+    uint8_t  external;     /* TLV 135: prefix-attr X flag; TLV 236/237: external bit */
+    uint8_t  _pad[3];
+} hl_isis_ipreach;
 
 #define HL_ISIS_METRIC_STANDARD 0u   /* MetricType::Standard (narrow) */
 #define HL_ISIS_METRIC_WIDE     1u
@@ -419,6 +440,7 @@ typedef struct hl_isis_level {
     uint8_t  _pad[3];
     uint32_t n_lsps;     const hl_isis_lsp *lsps;
     uint32_t n_reaches;  const hl_isis_reach *reaches;
+    uint32_t n_ipreaches; const hl_isis_ipreach *ipreaches;   /* may be 0/NULL for SPT-only calls */
 } hl_isis_level;
 
 /* SPT vertex (Vertex, spf.rs:76-86) in id_tree order (pseudonodes first).
@@ -433,6 +455,79 @@ typedef struct hl_isis_vertex {
     uint32_t  par_off, n_par;
     uint32_t  nh_off,  n_nh;
 } hl_isis_vertex;
+
+/* ---- IS-IS local state and the route stage --------------------------------------
+ * compute_spt(local = true) resolves first hops through the adjacency arena
+ * (resolve_nexthop, spf.rs:948-1002) and compute_routes (spf.rs:838-941) joins the SPT
+ * with the IP reachability of every vertex. */
+typedef struct hl_isis_adj {
+    uint64_t system_id;
+    uint8_t  snpa[6];
+    uint8_t  up;            /* AdjacencyState::Up */
+    uint8_t  level_usage;   /* bit0 L1, bit1 L2 */
+    uint8_t  topo_std;      /* adj.topologies contains 0 */
+    uint8_t  topo_ipv6;     /* adj.topologies contains 2 */
+    uint8_t  has_ipv4;
+    uint8_t  has_ipv6;
+    uint8_t  area_disjoint; /* adj.area_addrs disjoint from the local ones (instance.rs:575-589) */
+    uint8_t  _pad[3];
+    uint32_t ipv4;          /* first IPv4 address from the Hello */
+    hl_ip_addr ipv6;        /* first IPv6 address */
+} hl_isis_adj;
+
+/* Interfaces in NAME order (collections.rs:156-160).  Broadcast interfaces list their LAN
+ * adjacencies of the computed level (one per system id); p2p interfaces 0 or 1. */
+typedef struct hl_isis_iface {
+    uint32_t ifindex;
+    uint32_t metric;        /* iface.config.metric.get(level) */
+    uint8_t  is_broadcast;
+    uint8_t  _pad[3];
+    uint32_t adj_off;       /* into adjs[] */
+    uint32_t n_adj;
+} hl_isis_iface;
+
+typedef struct hl_isis_instance {
+    hl_isis_level lvl;      /* lvl.mt_id / lvl.metric_mode are ignored: set per topology */
+    uint64_t system_id;     /* instance.config.system_id: the root */
+    uint16_t max_paths;
+    uint8_t  level;         /* 1 or 2 */
+    uint8_t  level_type;    /* 1 = L1 only, 2 = L2 only, 3 = L1/L2 */
+    uint8_t  att_ignore;
+    uint8_t  mt_ipv6_enabled; /* is_topology_enabled(Ipv6Unicast) */
+    uint8_t  _pad[2];
+    uint32_t n_ifaces;  const hl_isis_iface *ifaces;
+    uint32_t n_adjs;    const hl_isis_adj *adjs;
+} hl_isis_instance;
+
+/* Route nexthop (route.rs:50-61), emitted in BTreeMap<IpAddr, _> order. */
+typedef struct hl_isis_nexthop {
+    uint64_t system_id;
+    uint32_t iface;         /* index into ifaces[] */
+    uint32_t _pad;
+    hl_ip_addr addr;
+} hl_isis_nexthop;
+
+#define HL_ISIS_RT_L2_INTRA 0u   /* IsisRouteType order (holo-utils/src/southbound.rs:99-106) */
+#define HL_ISIS_RT_L1_INTRA 1u
+#define HL_ISIS_RT_L2_EXT   2u
+#define HL_ISIS_RT_L1_EXT   3u
+
+/* Route (route.rs:27-37) in BTreeMap<IpNetwork, Route> order. */
+typedef struct hl_isis_route {
+    hl_ip_addr prefix;
+    uint32_t metric;
+    uint8_t  len;
+    uint8_t  route_type;
+    uint8_t  flags;         /* HL_ROUTE_CONNECTED */
+    uint8_t  _pad;
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_isis_route;
+
+typedef struct hl_isis_rib {
+    uint32_t routes_cap,   n_routes;    hl_isis_route *routes;
+    uint32_t nexthops_cap, n_nexthops;  hl_isis_nexthop *nexthops;
+} hl_isis_rib;
 
 typedef struct hl_isis_spt {
     uint32_t vertices_cap, n_vertices;  hl_isis_vertex *vertices;

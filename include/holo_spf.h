@@ -218,6 +218,11 @@ int hspf_atom_decode(const hspf_csr *g, uint32_t root, uint32_t atom,
                      uint32_t *tail, uint32_t *edge);
 int hspf_atom_count(const hspf_csr *g, uint32_t root, uint32_t *n_atoms);
 
+/* Leave `n_sms` SMs free in every batch launch of this ctx so that a concurrent kernel on
+ * another stream (the NCCL all-gather of the previous batch's results) can run beside
+ * the persistent batch kernel.  Default 0. */
+int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms);
+
 /* Debug aid: enable/disable per-phase cycle counters of the batch kernel and read
  * the sums of the last launch (slots: 0 init, 1 SSSP, 2 parents, 3 dist write-back,
  * 4 Kahn, 5 hops write-back, 6/7 Kahn/SSSP round counts, 8-12 SSSP round internals;

@@ -109,3 +109,11 @@ def ospfv3_run_area(area):
     L = lib()
     L.oracle_ospfv3_run_area.argtypes = [C.POINTER(ospfv3.AreaStruct), C.POINTER(ospfv3.ResultStruct)]
     return ospfv3._call_run_area(L.oracle_ospfv3_run_area, area)
+
+
+def isis_compute_routes(inst):
+    """Reference-faithful compute_spt(local = true) + compute_routes for one level."""
+    from holo_b200 import isis
+    L = lib()
+    L.oracle_isis_compute_routes.argtypes = [C.POINTER(isis.InstanceStruct), C.POINTER(isis.RibStruct)]
+    return isis._call_rib(L.oracle_isis_compute_routes, inst)

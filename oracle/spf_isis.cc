@@ -19,8 +19,11 @@
 // (tests/golden/isis.json).  Vertex.parents order and Vertex.hops are not exported
 // by the reference's tests: "parity unpinned" beyond this restatement.
 #include <algorithm>
+#include <array>
 #include <cstdint>
+#include <cstring>
 #include <functional>
+#include <set>
 #include <map>
 #include <tuple>
 #include <utility>
@@ -212,5 +215,268 @@ extern "C" int oracle_isis_compute_spt(const hl_isis_level *l, uint64_t root_sys
     }
     for (uint32_t k = 0; k < first_hops.size(); ++k) out->first_hops[k] = pos[first_hops[k]];
     for (uint32_t k = 0; k < second_hops.size(); ++k) out->second_hops[k] = pos[second_hops[k]];
+    return 0;
+}
+
+// =====================================================================================
+// compute_spf's route path: compute_spt(local = true) per enabled topology with
+// resolve_nexthop (holo-isis/src/spf.rs:948-1002), then compute_routes
+// (spf.rs:838-941) with vertex_networks (spf.rs:1141-1281), Route::new /
+// merge_nexthops / build_nexthops (holo-isis/src/route.rs:79-139) and the max_paths cut.
+// SR prefix-SID labels (sr.rs) are not restated.
+// =====================================================================================
+namespace {
+
+struct LocalNexthop { uint64_t system_id; bool has_iface; uint32_t iface; bool has4; uint32_t ipv4; bool has6; hl_ip_addr ipv6; };
+struct LVertex { VertexId id; uint32_t distance; uint16_t hops; std::vector<LocalNexthop> nexthops; };
+
+struct SnpaLess { bool operator()(const std::array<uint8_t, 6> &a, const std::array<uint8_t, 6> &b) const { return a < b; } };
+
+struct IpKey {
+    hl_ip_addr a;
+    bool operator<(const IpKey &o) const {
+        if (a.is_v6 != o.a.is_v6) return a.is_v6 < o.a.is_v6;
+        return std::memcmp(a.bytes, o.a.bytes, 16) < 0;
+    }
+};
+struct NetKey {
+    hl_ip_addr a; uint8_t len;
+    bool operator<(const NetKey &o) const {
+        if (a.is_v6 != o.a.is_v6) return a.is_v6 < o.a.is_v6;
+        int c = std::memcmp(a.bytes, o.a.bytes, 16);
+        if (c) return c < 0;
+        return len < o.len;
+    }
+};
+struct RNexthop { uint64_t system_id; uint32_t iface; hl_ip_addr addr; };
+struct Route { uint8_t route_type; uint32_t metric; uint8_t flags; std::map<IpKey, RNexthop> nexthops; };
+struct VNet { hl_ip_addr prefix; uint8_t len; uint32_t metric; bool external; };
+
+// one compute_spt(local = true) run; returns vertices in id_tree order
+std::vector<LVertex> local_spt(const hl_isis_instance *in, uint8_t mt_id) {
+    hl_isis_level l = in->lvl;
+    l.mt_id = mt_id;
+    l.metric_mode = HL_ISIS_MODE_NORMAL;
+    Lsdb lsdb{&l};
+    std::vector<LVertex> arena;
+    std::map<VertexId, uint32_t> id_tree;
+    std::map<std::pair<uint32_t, VertexId>, LVertex> cand_list;
+    std::set<std::array<uint8_t, 6>> used_adjs;
+    VertexId root_vid = vid((hl_lan_id)(in->system_id << 8));
+    cand_list.emplace(std::make_pair(0u, root_vid), LVertex{root_vid, 0, 0, {}});
+    const uint32_t max_path_metric = l.metric_type == HL_ISIS_METRIC_STANDARD ? MAX_PATH_METRIC_STANDARD : MAX_PATH_METRIC_WIDE;
+    const uint8_t level_bit = in->level == 1 ? 1 : 2;
+
+    auto resolve_nexthop = [&](LocalNexthop &nh, const LVertex &vertex, const Edge &link) {
+        const bool want_bcast = is_pseudonode(vertex.id.lan_id);
+        for (uint32_t i = 0; i < in->n_ifaces; ++i) {
+            const auto &iface = in->ifaces[i];
+            if ((bool)iface.is_broadcast != want_bcast) continue;
+            const hl_isis_adj *adj = nullptr;
+            if (iface.is_broadcast) {
+                for (uint32_t k = 0; k < iface.n_adj; ++k) {
+                    const auto &a = in->adjs[iface.adj_off + k];
+                    if (a.system_id == (link.id.lan_id >> 8)) { adj = &a; break; }   // get_by_system_id
+                }
+                if (adj && !(mt_id == HL_ISIS_MT_STANDARD ? adj->topo_std : adj->topo_ipv6)) adj = nullptr;
+                if (adj && !adj->up) adj = nullptr;
+            } else {
+                if (iface.metric != link.cost) continue;
+                if (iface.n_adj) {
+                    const auto &a = in->adjs[iface.adj_off];
+                    if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && (a.level_usage & level_bit) &&
+                        a.system_id == (link.id.lan_id >> 8) && a.up)
+                        adj = &a;
+                }
+            }
+            if (!adj) continue;
+            std::array<uint8_t, 6> snpa;
+            std::memcpy(snpa.data(), adj->snpa, 6);
+            if (!used_adjs.insert(snpa).second) continue;     // .find(|..| used_adjs.insert(adj.snpa))
+            nh.has_iface = true; nh.iface = i;
+            nh.has4 = adj->has_ipv4; nh.ipv4 = adj->ipv4;
+            nh.has6 = adj->has_ipv6; nh.ipv6 = adj->ipv6;
+            return;
+        }
+    };
+
+    while (!cand_list.empty()) {
+        auto first = cand_list.begin();
+        LVertex cand = std::move(first->second);
+        cand_list.erase(first);
+        const uint32_t vertex_idx = (uint32_t)arena.size();
+        arena.push_back(std::move(cand));
+        id_tree[arena[vertex_idx].id] = vertex_idx;
+        const VertexId vertex_id = arena[vertex_idx].id;
+        const uint32_t vertex_distance = arena[vertex_idx].distance;
+        const uint16_t vertex_hops = arena[vertex_idx].hops;
+        const hl_isis_lsp *z = lsdb.zeroth(vertex_id.lan_id);
+        if (!z) continue;
+        if (vertex_hops != 0 && !is_pseudonode(z->lan_id)) {
+            bool ol = mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_OL) : (z->flags & HL_LSPF_MT_IPV6_OL);
+            if (ol) continue;
+        }
+        if (mt_id == HL_ISIS_MT_STANDARD && !is_pseudonode(z->lan_id)) {
+            if (!(z->flags & HL_LSPF_HAS_PROTOCOLS)) continue;
+            if (l.ipv4_enabled && !(z->flags & HL_LSPF_NLPID_IPV4)) continue;
+            if (l.ipv6_enabled && !(z->flags & HL_LSPF_NLPID_IPV6)) continue;
+        }
+        lsdb.vertex_edges(vertex_id, [&](const Edge &link) {
+            bool back = false;
+            lsdb.vertex_edges(link.id, [&](const Edge &l2) { if (l2.id == vertex_id) { back = true; return false; } return true; });
+            if (!back) return true;
+            if (id_tree.count(link.id)) return true;
+            uint64_t s = (uint64_t)vertex_distance + link.cost;
+            uint32_t distance = s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s;
+            if (distance > max_path_metric) return true;
+            uint16_t hops = vertex_hops;
+            if (!is_pseudonode(link.id.lan_id)) hops = hops == 0xFFFF ? 0xFFFF : hops + 1;
+            auto it = cand_list.begin();
+            for (; it != cand_list.end(); ++it) if (it->second.id == link.id) break;
+            if (it != cand_list.end()) {
+                if (distance < it->second.distance) cand_list.erase(it);
+                else if (distance > it->second.distance) return true;
+            }
+            auto key = std::make_pair(distance, link.id);
+            auto ce = cand_list.find(key);
+            if (ce == cand_list.end()) ce = cand_list.emplace(key, LVertex{link.id, distance, hops, {}}).first;
+            LVertex &cand_v = ce->second;
+            if (vertex_hops == 0) {
+                if (!is_pseudonode(link.id.lan_id)) {
+                    LocalNexthop nh{link.id.lan_id >> 8, false, 0, false, 0, false, hl_ip_addr{}};
+                    resolve_nexthop(nh, arena[vertex_idx], link);
+                    cand_v.nexthops.push_back(nh);
+                }
+            } else {
+                const auto &src = arena[vertex_idx].nexthops;
+                cand_v.nexthops.insert(cand_v.nexthops.end(), src.begin(), src.end());
+            }
+            return true;
+        });
+    }
+    std::vector<LVertex> out;
+    for (auto &kv : id_tree) out.push_back(arena[kv.second]);
+    return out;
+}
+
+}  // namespace
+
+extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_rib *out) {
+    const hl_isis_level &l = in->lvl;
+    const bool std_en = l.metric_type == HL_ISIS_METRIC_STANDARD || l.metric_type == HL_ISIS_METRIC_BOTH;
+    const bool wide_en = l.metric_type == HL_ISIS_METRIC_WIDE || l.metric_type == HL_ISIS_METRIC_BOTH;
+    std::map<NetKey, Route> rib;
+    const uint8_t mts[2] = {HL_ISIS_MT_STANDARD, HL_ISIS_MT_IPV6};
+    for (uint8_t mt_id : mts) {
+        if (mt_id == HL_ISIS_MT_IPV6 && !in->mt_ipv6_enabled) continue;
+        std::vector<LVertex> spt = local_spt(in, mt_id);
+        hl_isis_level lm = l;
+        lm.mt_id = mt_id;
+        Lsdb lsdb{&lm};
+        // is_l2_attached_to_backbone (instance.rs:575-589)
+        bool attached = false;
+        for (uint32_t i = 0; i < in->n_adjs; ++i) {
+            const auto &a = in->adjs[i];
+            if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && a.up && (a.level_usage & 2) && a.area_disjoint) attached = true;
+        }
+        const bool ipv4_enabled = l.ipv4_enabled && mt_id == HL_ISIS_MT_STANDARD;
+        const bool ipv6_enabled = l.ipv6_enabled && (mt_id == HL_ISIS_MT_STANDARD ? !in->mt_ipv6_enabled : true);
+        for (const LVertex &vertex : spt) {
+            const hl_isis_lsp *z = lsdb.zeroth(vertex.id.lan_id);
+            if (!z) continue;
+            const bool att_bit = !in->att_ignore && (mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_ATT) : (z->flags & HL_LSPF_MT_IPV6_ATT));
+            // vertex_networks: per valid fragment, in LspId order
+            std::vector<VNet> nets;
+            auto r = lsdb.range(vertex.id.lan_id);
+            for (uint32_t i = r.first; i < r.second; ++i) {
+                const auto &lsp = l.lsps[i];
+                if (lsp.seqno == 0 || lsp.rem_lifetime == 0) continue;
+                if (att_bit && in->level == 1 && (in->level_type == 1 || !attached)) {
+                    if (ipv4_enabled) nets.push_back(VNet{hl_ip_addr{}, 0, 0, false});
+                    if (ipv6_enabled) { hl_ip_addr z6{}; z6.is_v6 = 1; nets.push_back(VNet{z6, 0, 0, false}); }
+                }
+                const hl_isis_ipreach *ip = l.ipreaches + lsp.ipreach_off;
+                if (mt_id == HL_ISIS_MT_STANDARD && ipv4_enabled) {
+                    if (std_en) {
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_INTERNAL) nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, false});
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_EXTERNAL) nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, true});
+                    }
+                    if (wide_en)
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= MAX_PATH_METRIC_WIDE)
+                                nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external});
+                }
+                if (ipv6_enabled) {
+                    for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
+                        const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
+                                                                   : (ip[k].kind == HL_ISIS_IP_V6);
+                        if (take) nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external});
+                    }
+                }
+            }
+            for (const VNet &network : nets) {
+                auto build = [&]() {
+                    std::map<IpKey, RNexthop> m;
+                    for (const auto &nh : vertex.nexthops) {
+                        hl_ip_addr addr{};
+                        if (!network.prefix.is_v6) {
+                            if (!nh.has4) continue;
+                            addr.bytes[0] = nh.ipv4 >> 24; addr.bytes[1] = nh.ipv4 >> 16; addr.bytes[2] = nh.ipv4 >> 8; addr.bytes[3] = nh.ipv4;
+                        } else {
+                            if (!nh.has6) continue;
+                            addr = nh.ipv6; addr.is_v6 = 1;
+                        }
+                        m[IpKey{addr}] = RNexthop{nh.system_id, nh.iface, addr};   // iface_idx.unwrap()
+                    }
+                    return m;
+                };
+                auto mk = [&]() {
+                    Route rt;
+                    rt.flags = vertex.hops == 0 ? HL_ROUTE_CONNECTED : 0;
+                    rt.route_type = in->level == 1 ? (network.external ? HL_ISIS_RT_L1_EXT : HL_ISIS_RT_L1_INTRA)
+                                                   : (network.external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
+                    rt.metric = vertex.distance + network.metric;
+                    rt.nexthops = build();
+                    return rt;
+                };
+                NetKey key{network.prefix, network.len};
+                auto it = rib.find(key);
+                Route *route;
+                if (it == rib.end()) {
+                    route = &rib.emplace(key, mk()).first->second;
+                } else {
+                    Route &cur = it->second;
+                    const uint32_t route_metric = vertex.distance + network.metric;
+                    if (route_metric < cur.metric) cur = mk();
+                    else if (route_metric == cur.metric) { for (auto &kv : build()) cur.nexthops[kv.first] = kv.second; }
+                    else continue;
+                    route = &cur;
+                }
+                if (route->nexthops.size() > in->max_paths) {
+                    std::map<IpKey, RNexthop> cut; uint32_t n = 0;
+                    for (auto &kv : route->nexthops) { if (n++ >= in->max_paths) break; cut.insert(kv); }
+                    route->nexthops = std::move(cut);
+                }
+            }
+        }
+    }
+    uint32_t need_h = 0;
+    for (auto &kv : rib) need_h += (uint32_t)kv.second.nexthops.size();
+    out->n_routes = (uint32_t)rib.size(); out->n_nexthops = need_h;
+    if (out->n_routes > out->routes_cap || need_h > out->nexthops_cap) return HSPF_E_NOMEM;
+    uint32_t i = 0, h = 0;
+    for (auto &kv : rib) {
+        hl_isis_route o{};
+        o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.route_type;
+        o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nexthops.size();
+        for (auto &nk : kv.second.nexthops) {
+            hl_isis_nexthop x{};
+            x.system_id = nk.second.system_id; x.iface = nk.second.iface; x.addr = nk.second.addr;
+            out->nexthops[h++] = x;
+        }
+        out->routes[i++] = o;
+    }
     return 0;
 }

@@ -42,6 +42,11 @@ def extract_isis(ref: Path):
             snap = {"topo": topo.name, "rt": rt.name, "system_id": cfg["system-id"],
                     "metric_type": (cfg.get("metric-type") or {}).get("value", "wide-only"),
                     "afs": afs, "mt_ipv6": bool(cfg.get("topologies")), "levels": [], "adjacencies": [],
+                    "level_type": cfg.get("level-type", "level-all"), "areas": cfg.get("area-address", []),
+                    "max_paths": (cfg.get("spf-control") or {}).get("paths", 16),
+                    "interfaces": [{"name": i["name"], "type": i.get("interface-type", "broadcast"),
+                                    "metric": (i.get("metric") or {}).get("value", 10)}
+                                   for i in cfg.get("interfaces", {}).get("interface", [])],
                     "local_rib": []}
             for lv in o.get("database", {}).get("levels", []):
                 lsps = []
@@ -50,6 +55,8 @@ def extract_isis(ref: Path):
                     lsps.append({
                         "id": l["lsp-id"], "flags": l.get("attributes", {}).get("lsp-flags", []),
                         "protocols": l.get("protocol-supported"),
+                        "mt_flags": {str(t["mt-id"]): t.get("attributes", {}).get("flags", [])
+                                     for t in (l.get("mt-entries") or {}).get("topology", [])},
                         "is": _reach(l, "is-neighbor", dm),
                         "ext_is": _reach(l, "extended-is-neighbor", lambda x: x["metric"]),
                         "mt_is": _reach(l, "mt-is-neighbor", lambda x: x["metric"]),
@@ -65,6 +72,7 @@ def extract_isis(ref: Path):
                     snap["adjacencies"].append({"iface": i["name"], "sysid": a["neighbor-sysid"], "state": a.get("state"),
                                                 "usage": a.get("usage"), "ipv4": a.get("holo-isis:ipv4-addresses", []),
                                                 "ipv6": a.get("holo-isis:ipv6-addresses", []),
+                                                "areas": a.get("holo-isis:area-addresses", []),
                                                 "topologies": a.get("holo-isis:topologies", [])})
             for r in o.get("local-rib", {}).get("route", []):
                 nhs = [[n.get("outgoing-interface"), n.get("next-hop")]

@@ -205,7 +205,7 @@ def isis_level_image(snap, level, mt_id=None):
         rr = [(lan_id(n), m, 0, isis.REACH_LEGACY, 0) for (n, m, _mt) in l["is"]]
         rr += [(lan_id(n), m, 0, isis.REACH_EXT, 0) for (n, m, _mt) in l["ext_is"]]
         rr += [(lan_id(n), m, 2 if mt is None else mt, isis.REACH_MT, 0) for (n, m, mt) in l["mt_is"]]
-        lsps.append((lan_id(lid), 1, 1200, int(frag, 16), flags, len(reaches), len(rr)))
+        lsps.append((lan_id(lid), 1, 1200, int(frag, 16), flags, len(reaches), len(rr), 0, 0))
         reaches += rr
     lv = isis.IsisLevel(metric_type=mtype, mt_id=isis.MT_STANDARD if mt_id is None else mt_id,
                         ipv4_enabled="ipv4" in snap["afs"], ipv6_enabled="ipv6" in snap["afs"])
@@ -252,3 +252,72 @@ def isis_expected_ipv4_routes(snap, level, spt):
                 elif tot == cur[0]:
                     cur[1].update(nh)
     return best
+
+
+def isis_instance_image(snap, level):
+    """hl_isis_instance (LSDB with IP reachability + local interfaces/adjacencies) for one
+    level of a golden IS-IS snapshot.  SNPAs are synthesised (the fixtures do not export
+    them): one distinct MAC per adjacency, as on a real network."""
+    import ipaddress
+    from holo_b200 import isis, ospfv3
+    lv = isis_level_image(snap, level)
+    # IP reachability per fragment, aligned with lv.lsps order
+    by_id = {}
+    for l in level["lsps"]:
+        lid, frag = l["id"].split("-")
+        by_id[(lan_id(lid), int(frag, 16))] = l
+    ipr = []
+    lsps = lv.lsps.copy()
+    for i in range(len(lsps)):
+        l = by_id[(int(lsps["lan_id"][i]), int(lsps["fragment"][i]))]
+        off = len(ipr)
+        def add(items, kind, ext=0):
+            for (p, m, mt) in items:
+                net = ipaddress.ip_network(p, strict=False)
+                ipr.append((ospfv3.ip_rec(net.network_address), m, 2 if (mt is None and kind == isis.IP_MT_V6) else (mt or 0),
+                            net.prefixlen, kind, ext, (0, 0, 0)))
+        add(l["ipv4_int"], isis.IP_V4_INTERNAL)
+        add(l["ipv4_ext"], isis.IP_V4_EXTERNAL, 1)
+        add(l["ext_ipv4"], isis.IP_V4_EXT)
+        add(l["ipv6"], isis.IP_V6)
+        add(l["mt_ipv6"], isis.IP_MT_V6)
+        lsps["ipreach_off"][i] = off
+        lsps["n_ipreach"][i] = len(ipr) - off
+        if "lsp-attached-default-metric-flag" in l["flags"]:
+            lsps["flags"][i] |= isis.LSPF_ATT
+        mtf = l.get("mt_flags", {}).get("2", [])
+        if "tlv229-attached-flag" in mtf:
+            lsps["flags"][i] |= isis.LSPF_MT_IPV6_ATT
+        if "tlv229-overload-flag" in mtf:
+            lsps["flags"][i] |= isis.LSPF_MT_IPV6_OL
+    lv.lsps = lsps
+    arr = np.zeros(len(ipr), isis.IPREACH_DT)
+    for k, r in enumerate(ipr):
+        arr[k] = r
+    lv.ipreaches = arr
+    lvl_no = level["level"]
+    ifs = sorted(snap["interfaces"], key=lambda i: i["name"].encode())
+    ifaces, adjs, names = [], [], []
+    n_adj = 0
+    for idx, f in enumerate(ifs):
+        mine = [a for a in snap["adjacencies"] if a["iface"] == f["name"]]
+        if f["type"] != "point-to-point":
+            want = "level-1" if lvl_no == 1 else "level-2"
+            mine = sorted([a for a in mine if a["usage"] in (want, "level-all")], key=lambda a: a["sysid"])
+        off = len(adjs)
+        for a in mine:
+            n_adj += 1
+            usage = {"level-1": 1, "level-2": 2, "level-all": 3}.get(a["usage"], 3)
+            v6 = ospfv3.ip_rec(a["ipv6"][0]) if a["ipv6"] else ospfv3.ip_rec("::")
+            adjs.append((int(a["sysid"].replace(".", ""), 16), (2, 0, 0, 0, n_adj >> 8, n_adj & 0xFF), int(a["state"] == "up"),
+                         usage, int(0 in a["topologies"]), int(2 in a["topologies"]), int(bool(a["ipv4"])),
+                         int(bool(a["ipv6"])), int(not (set(a["areas"]) & set(snap["areas"]))), (0, 0, 0),
+                         ip(a["ipv4"][0]) if a["ipv4"] else 0, v6))
+        ifaces.append((idx + 1, f["metric"], int(f["type"] != "point-to-point"), (0, 0, 0), off, len(adjs) - off))
+        names.append(f["name"])
+    inst = dict(level=lv, system_id=int(snap["system_id"].replace(".", ""), 16), max_paths=snap.get("max_paths", 16),
+                level_no=lvl_no, level_type={"level-1": 1, "level-2": 2, "level-all": 3}[snap["level_type"]],
+                att_ignore=0, mt_ipv6=int(snap["mt_ipv6"]),
+                ifaces=np.asarray(ifaces, dtype=isis.IFACE_DT) if ifaces else np.zeros(0, isis.IFACE_DT),
+                adjs=np.asarray(adjs, dtype=isis.ADJ_DT) if adjs else np.zeros(0, isis.ADJ_DT), ifnames=names)
+    return inst

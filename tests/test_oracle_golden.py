@@ -96,3 +96,28 @@ def test_isis_oracle_reproduces_reference_local_rib(snap):
             assert sorted(nh) == sorted((a, b) for a, b in r["nexthops"]), (r["prefix"], nh, r["nexthops"])
             n_checked += 1
     assert n_checked > 0
+
+
+@pytest.mark.parametrize("snap", SNAPS_ISIS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_ISIS])
+def test_isis_route_stage_oracle_reproduces_reference_local_rib(snap):
+    """Full IS-IS route path (compute_spt local=true per topology + compute_routes) vs the
+    golden local-rib: every prefix of every level, IPv4 and IPv6, metric and next hops."""
+    from holo_b200 import ospfv3
+    n_checked = 0
+    for level in snap["levels"]:
+        inst = gu.isis_instance_image(snap, level)
+        rib = pyoracle.isis_compute_routes(inst)
+        assert rib.rc == 0
+        got = {}
+        for r in rib.routes:
+            got[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (
+                int(r["metric"]), sorted((inst["ifnames"][i], a) for (i, a, _s) in rib.nh(r)))
+        for r in snap["local_rib"]:
+            if r["level"] != level["level"]:
+                continue
+            assert r["prefix"] in got, r["prefix"]
+            metric, nh = got[r["prefix"]]
+            assert metric == r["metric"], (r["prefix"], metric, r["metric"])
+            assert nh == sorted((a, b) for a, b in r["nexthops"]), (r["prefix"], nh, r["nexthops"])
+            n_checked += 1
+    assert n_checked > 0
