@@ -133,9 +133,8 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         int v = atoi(lim);
         if (v >= 1 && v < per_sm) per_sm = v;
     }
-    int sms = ctx->sm_count - ctx->reserved_sms;
-    if (sms < 1) sms = 1;
-    int grid = sms * per_sm;
+    int grid = ctx->sm_count * per_sm;
+    a.sm_limit = ctx->reserved_sms > 0 ? (uint32_t)(ctx->sm_count - ctx->reserved_sms) : 0u;
     if (const char *mg = getenv("HSPF_MAX_GRID")) {   // tuning knob (experiments only)
         int v = atoi(mg);
         if (v >= 1 && v < grid) grid = v;
@@ -487,10 +486,11 @@ int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, co
         dr.n_parents = reinterpret_cast<uint16_t *>(rp); rp += ps.npar;
         dr.nh_mask = reinterpret_cast<uint64_t *>(rp); rp += ps.nh;
         dr.job_status = reinterpret_cast<uint32_t *>(rp); rp += ps.status;
-        // Launch the batch in chunks of about one wave of CTAs and copy each chunk's planes
-        // back on a second stream while the next chunk computes (D2H is the e2e bound).
-        int per_sm_hint = 2;
-        uint32_t chunk = (uint32_t)std::max(1, ctx->sm_count * per_sm_hint);
+        // The batch can be launched in chunks, each chunk's planes copied back on a second
+        // stream while the next chunk computes.
+        // (measured on B200/PCIe5: the 200 MB D2H dominates and chunking buys nothing at the
+        // BASELINE batch size, so the default is one chunk; HSPF_E2E_CHUNK overrides)
+        uint32_t chunk = n;
         if (const char *cs = getenv("HSPF_E2E_CHUNK")) { int v = atoi(cs); if (v > 0) chunk = (uint32_t)v; }
         std::vector<uint32_t> st(n);
         for (uint32_t c0 = 0; c0 < n; c0 += chunk) {

@@ -350,3 +350,286 @@ int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root
 }
 
 }  // extern "C"
+
+// =====================================================================================
+// Route path of compute_spf (holo-isis/src/spf.rs:742-799): per enabled topology one
+// SPT with `local = true` next-hop resolution (resolve_nexthop, spf.rs:948-1002), then
+// compute_routes (spf.rs:838-941).  Distances/hops come from the device; the host
+// replays only the first-hop bookkeeping of the hops==0 vertices (root and the
+// pseudonodes attached to it) in pop order, because resolve_nexthop is stateful
+// ("the same adjacency shouldn't be used more than once", used_adjs).
+// =====================================================================================
+#include <array>
+#include <map>
+#include <set>
+
+namespace {
+
+struct LNh { uint64_t sysid; bool has_iface; uint32_t iface; bool has4; uint32_t ipv4; bool has6; hl_ip_addr ipv6; };
+
+struct IpLess {
+    bool operator()(const hl_ip_addr &a, const hl_ip_addr &b) const {
+        if (a.is_v6 != b.is_v6) return a.is_v6 < b.is_v6;
+        return std::memcmp(a.bytes, b.bytes, 16) < 0;
+    }
+};
+struct NetKey {
+    hl_ip_addr a; uint8_t len;
+    bool operator<(const NetKey &o) const {
+        if (a.is_v6 != o.a.is_v6) return a.is_v6 < o.a.is_v6;
+        int c = std::memcmp(a.bytes, o.a.bytes, 16);
+        return c ? c < 0 : len < o.len;
+    }
+};
+struct RNh { uint64_t sysid; uint32_t iface; hl_ip_addr addr; };
+struct RouteE { uint8_t type, flags; uint32_t metric; std::map<hl_ip_addr, RNh, IpLess> nh; };
+
+// Next-hop Vecs of a `local = true` SPT for every SPT vertex (indexed by vertex).
+int local_nexthops(const hspf_isis_flat &f, const hl_isis_instance *in, uint8_t mt_id, uint32_t root,
+                   const uint32_t *dist, const uint16_t *hops, std::vector<std::vector<LNh>> &out) {
+    const uint32_t V = (uint32_t)f.ids.size();
+    const uint8_t level_bit = in->level == 1 ? 1 : 2;
+    // pop order
+    std::vector<uint32_t> pop;
+    for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) pop.push_back(v);
+    std::sort(pop.begin(), pop.end(), [&](uint32_t a, uint32_t b) { return dist[a] != dist[b] ? dist[a] < dist[b] : a < b; });
+    std::vector<uint32_t> pos(V, kNone);
+    for (uint32_t i = 0; i < pop.size(); ++i) pos[pop[i]] = i;
+    auto relax_ok = [&](uint32_t u, uint32_t e) {     // would the reference relax this edge at all?
+        if (dist[u] == HSPF_DIST_INF || !expands(f.vflags[u], u, root)) return false;
+        return (uint64_t)dist[u] + f.cost[e] <= f.reject_above;
+    };
+    std::set<std::array<uint8_t, 6>> used;
+    auto resolve = [&](uint32_t P, uint32_t e, uint32_t R) {
+        LNh nh{f.ids[R] >> 8, false, 0, false, 0, false, hl_ip_addr{}};
+        const bool want_bcast = is_pn(f.ids[P]);
+        for (uint32_t i = 0; i < in->n_ifaces; ++i) {
+            const auto &iface = in->ifaces[i];
+            if ((bool)iface.is_broadcast != want_bcast) continue;
+            const hl_isis_adj *adj = nullptr;
+            if (iface.is_broadcast) {
+                for (uint32_t k = 0; k < iface.n_adj && !adj; ++k)
+                    if (in->adjs[iface.adj_off + k].system_id == nh.sysid) adj = &in->adjs[iface.adj_off + k];
+                if (adj && (!(mt_id == HL_ISIS_MT_STANDARD ? adj->topo_std : adj->topo_ipv6) || !adj->up)) adj = nullptr;
+            } else {
+                if (iface.metric != f.cost[e] || !iface.n_adj) continue;
+                const auto &a = in->adjs[iface.adj_off];
+                if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && (a.level_usage & level_bit) &&
+                    a.system_id == nh.sysid && a.up)
+                    adj = &a;
+            }
+            if (!adj) continue;
+            std::array<uint8_t, 6> snpa;
+            std::memcpy(snpa.data(), adj->snpa, 6);
+            if (!used.insert(snpa).second) continue;
+            nh.has_iface = true; nh.iface = i;
+            nh.has4 = adj->has_ipv4; nh.ipv4 = adj->ipv4;
+            nh.has6 = adj->has_ipv6; nh.ipv6 = adj->ipv6;
+            break;
+        }
+        return nh;
+    };
+    // replay the relaxations out of the hops==0 vertices, in pop order
+    std::map<uint32_t, LNh> first_hop;    // forward edge id -> resolved next hop (final DAG edges only)
+    for (uint32_t P : pop) {
+        if (hops[P] != 0 || !expands(f.vflags[P], P, root)) continue;
+        for (uint32_t e = f.row[P]; e < f.row[P + 1]; ++e) {
+            const uint32_t R = f.col[e];
+            if (pos[R] != kNone && pos[R] < pos[P]) continue;            // already on the SPT
+            const uint64_t d = (uint64_t)dist[P] + f.cost[e];
+            if (d > f.reject_above) continue;
+            // candidate distance of R at this moment
+            uint64_t cb = ~0ull;
+            for (uint32_t i = f.irow[R]; i < f.irow[R + 1]; ++i) {
+                const uint32_t u = f.isrc[i], e2 = f.ieid[i];
+                if (!relax_ok(u, e2)) continue;
+                const bool earlier = (u == P) ? (e2 < e) : (pos[u] < pos[P]);
+                if (earlier) cb = std::min<uint64_t>(cb, (uint64_t)dist[u] + f.cost[e2]);
+            }
+            if (d > cb) continue;
+            if (!(f.vflags[R] & HSPF_VF_HOP)) continue;                  // pseudonode: nothing is pushed
+            LNh nh = resolve(P, e, R);
+            if (d == dist[R]) first_hop[e] = nh;
+        }
+    }
+    // final Vecs in pop order: parents in (pop position, edge order)
+    out.assign(V, {});
+    std::vector<std::pair<uint64_t, uint32_t>> tmp;
+    for (uint32_t v : pop) {
+        if (v == root) continue;
+        tmp.clear();
+        for (uint32_t i = f.irow[v]; i < f.irow[v + 1]; ++i) {
+            const uint32_t u = f.isrc[i], e = f.ieid[i];
+            if (!relax_ok(u, e) || (uint64_t)dist[u] + f.cost[e] != dist[v]) continue;
+            tmp.emplace_back(((uint64_t)pos[u] << 32) | e, u);
+        }
+        std::sort(tmp.begin(), tmp.end());
+        for (auto &t : tmp) {
+            const uint32_t u = t.second, e = (uint32_t)(t.first & 0xFFFFFFFFu);
+            if (hops[u] == 0) {
+                if (f.vflags[v] & HSPF_VF_HOP) {
+                    auto it = first_hop.find(e);
+                    if (it != first_hop.end()) out[v].push_back(it->second);
+                }
+            } else {
+                if (out[v].size() + out[u].size() > ((size_t)1 << 22)) return HSPF_E_UNSUPPORTED;
+                out[v].insert(out[v].end(), out[u].begin(), out[u].end());
+            }
+        }
+    }
+    return HSPF_OK;
+}
+
+}  // namespace
+
+extern "C" int hspf_isis_compute_routes(hspf_ctx *ctx, const hl_isis_instance *in, hl_isis_rib *out) {
+    if (!ctx || !in || !out) return HSPF_E_INVAL;
+    try {
+        const hl_isis_level &l0 = in->lvl;
+        const bool std_en = l0.metric_type == HL_ISIS_METRIC_STANDARD || l0.metric_type == HL_ISIS_METRIC_BOTH;
+        const bool wide_en = l0.metric_type == HL_ISIS_METRIC_WIDE || l0.metric_type == HL_ISIS_METRIC_BOTH;
+        std::map<NetKey, RouteE> rib;
+        const uint8_t mts[2] = {HL_ISIS_MT_STANDARD, HL_ISIS_MT_IPV6};
+        for (uint8_t mt_id : mts) {
+            if (mt_id == HL_ISIS_MT_IPV6 && !in->mt_ipv6_enabled) continue;
+            hl_isis_level l = l0;
+            l.mt_id = mt_id;
+            l.metric_mode = HL_ISIS_MODE_NORMAL;
+            hspf_isis_flat f;
+            int rc = flatten(&l, f);
+            if (rc) return rc;
+            const hl_lan_id root_id = (hl_lan_id)(in->system_id << 8);
+            auto it = f.index.find(root_id);
+            if (it == f.index.end()) continue;      // root owns no LSP: nothing reachable, no routes
+            const uint32_t root = it->second;
+            const uint32_t V = (uint32_t)f.ids.size();
+            hspf_csr csr;
+            fill_csr(f, &csr);
+            hspf_graph *g = nullptr;
+            rc = hspf_graph_upload(ctx, &csr, &g);
+            if (rc) return rc;
+            std::vector<uint32_t> dist(V);
+            std::vector<uint16_t> hops(V);
+            uint32_t status = 0;
+            hspf_jobs jobs{};
+            jobs.n_jobs = 1; jobs.roots = &root;
+            hspf_result res{};
+            res.dist = dist.data(); res.hops = hops.data(); res.nh_words = 4; res.job_status = &status;
+            rc = hspf_run_batch(ctx, g, &jobs, &res, 0);
+            hspf_graph_free(ctx, g);
+            if (rc == HSPF_E_JOB_STATUS && !(status & ~HSPF_JS_TOO_MANY_ATOMS)) rc = HSPF_OK;
+            if (rc) return rc;
+            std::vector<std::vector<LNh>> vnh;
+            rc = local_nexthops(f, in, mt_id, root, dist.data(), hops.data(), vnh);
+            if (rc) return rc;
+
+            // ---- compute_routes over the SPT in id_tree (= vertex index) order -------------
+            bool attached = false;
+            for (uint32_t i = 0; i < in->n_adjs; ++i) {
+                const auto &a = in->adjs[i];
+                if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && a.up && (a.level_usage & 2) && a.area_disjoint) attached = true;
+            }
+            const bool ipv4_enabled = l0.ipv4_enabled && mt_id == HL_ISIS_MT_STANDARD;
+            const bool ipv6_enabled = l0.ipv6_enabled && (mt_id == HL_ISIS_MT_STANDARD ? !in->mt_ipv6_enabled : true);
+            // fragments per LAN id in LspId order
+            std::vector<uint32_t> order(l0.n_lsps);
+            for (uint32_t i = 0; i < l0.n_lsps; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const auto &x = l0.lsps[a], &y = l0.lsps[b];
+                return x.lan_id != y.lan_id ? x.lan_id < y.lan_id : x.fragment < y.fragment;
+            });
+            std::unordered_map<uint64_t, std::vector<uint32_t>> frags;
+            for (uint32_t i : order) frags[l0.lsps[i].lan_id].push_back(i);
+            for (uint32_t v = 0; v < V; ++v) {
+                if (dist[v] == HSPF_DIST_INF) continue;
+                const auto &fr = frags[f.ids[v]];
+                const hl_isis_lsp *z = nullptr;
+                for (uint32_t i : fr)
+                    if (l0.lsps[i].fragment == 0) { if (l0.lsps[i].seqno && l0.lsps[i].rem_lifetime) z = &l0.lsps[i]; break; }
+                if (!z) continue;
+                const bool att_bit = !in->att_ignore &&
+                                     (mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_ATT) : (z->flags & HL_LSPF_MT_IPV6_ATT));
+                auto add = [&](const hl_ip_addr &prefix, uint8_t len, uint32_t nmetric, bool external) {
+                    auto build = [&](std::map<hl_ip_addr, RNh, IpLess> &m) {
+                        for (const LNh &nh : vnh[v]) {
+                            hl_ip_addr addr{};
+                            if (!prefix.is_v6) {
+                                if (!nh.has4) continue;
+                                addr.bytes[0] = (uint8_t)(nh.ipv4 >> 24); addr.bytes[1] = (uint8_t)(nh.ipv4 >> 16);
+                                addr.bytes[2] = (uint8_t)(nh.ipv4 >> 8); addr.bytes[3] = (uint8_t)nh.ipv4;
+                            } else {
+                                if (!nh.has6) continue;
+                                addr = nh.ipv6; addr.is_v6 = 1;
+                            }
+                            m[addr] = RNh{nh.sysid, nh.iface, addr};
+                        }
+                    };
+                    const uint32_t metric = dist[v] + nmetric;
+                    NetKey key{prefix, len};
+                    auto rit = rib.find(key);
+                    RouteE *route;
+                    if (rit == rib.end() || metric < rit->second.metric) {
+                        RouteE r{};
+                        r.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
+                        r.type = in->level == 1 ? (external ? HL_ISIS_RT_L1_EXT : HL_ISIS_RT_L1_INTRA)
+                                                : (external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
+                        r.metric = metric;
+                        build(r.nh);
+                        if (rit == rib.end()) route = &rib.emplace(key, std::move(r)).first->second;
+                        else { rit->second = std::move(r); route = &rit->second; }
+                    } else if (metric == rit->second.metric) {
+                        build(rit->second.nh);
+                        route = &rit->second;
+                    } else {
+                        return;
+                    }
+                    while (route->nh.size() > in->max_paths) route->nh.erase(std::prev(route->nh.end()));
+                };
+                for (uint32_t i : fr) {
+                    const auto &lsp = l0.lsps[i];
+                    if (!lsp.seqno || !lsp.rem_lifetime) continue;
+                    if (att_bit && in->level == 1 && (in->level_type == 1 || !attached)) {
+                        if (ipv4_enabled) add(hl_ip_addr{}, 0, 0, false);
+                        if (ipv6_enabled) { hl_ip_addr z6{}; z6.is_v6 = 1; add(z6, 0, 0, false); }
+                    }
+                    const hl_isis_ipreach *ip = l0.ipreaches + lsp.ipreach_off;
+                    if (mt_id == HL_ISIS_MT_STANDARD && ipv4_enabled) {
+                        if (std_en) {
+                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                                if (ip[k].kind == HL_ISIS_IP_V4_INTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, false);
+                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                                if (ip[k].kind == HL_ISIS_IP_V4_EXTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, true);
+                        }
+                        if (wide_en)
+                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                                if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= kMaxWide)
+                                    add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                    }
+                    if (ipv6_enabled)
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
+                            const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
+                                                                       : (ip[k].kind == HL_ISIS_IP_V6);
+                            if (take) add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                        }
+                }
+            }
+        }
+        uint32_t need_h = 0;
+        for (auto &kv : rib) need_h += (uint32_t)kv.second.nh.size();
+        out->n_routes = (uint32_t)rib.size(); out->n_nexthops = need_h;
+        if (out->n_routes > out->routes_cap || need_h > out->nexthops_cap) return HSPF_E_NOMEM;
+        uint32_t i = 0, h = 0;
+        for (auto &kv : rib) {
+            hl_isis_route o{};
+            o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.type;
+            o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nh.size();
+            for (auto &nk : kv.second.nh) {
+                hl_isis_nexthop x{};
+                x.system_id = nk.second.sysid; x.iface = nk.second.iface; x.addr = nk.second.addr;
+                out->nexthops[h++] = x;
+            }
+            out->routes[i++] = o;
+        }
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}

@@ -97,6 +97,11 @@ int hspf_isis_spt_from_planes(const hspf_isis_flat *flat, uint32_t root_vertex, 
 /* One SPT for `root_system_id` (48-bit system id). */
 int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root_system_id, hl_isis_spt *out);
 
+/* Route path of one level (compute_spf, holo-isis/src/spf.rs:742-799): for every enabled
+ * topology an SPT with `local = true` next-hop resolution (spf.rs:948-1002), then
+ * compute_routes (spf.rs:838-941) into one RIB (prefix order). */
+int hspf_isis_compute_routes(hspf_ctx *ctx, const hl_isis_instance *inst, hl_isis_rib *out);
+
 /* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
  * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
  * foreign binding verify its struct layouts at load time. */
