@@ -206,7 +206,9 @@ def run_ours(args):
         ctx.reserve_sms(args.reserve_sms)   # room for the NCCL all-gather beside the persistent kernel
     g = ctx.upload(csr)
     n = JOBS_PER_GPU
-    roots_np = ((np.arange(n) + rank * n) % V_ROUTERS + len(t.lans)).astype(np.uint32)
+    from holo_b200 import shard
+    lo, hi = shard.job_range(n * world, rank, world)          # weak scaling: n jobs per rank
+    roots_np = (np.arange(lo, hi) % V_ROUTERS + len(t.lans)).astype(np.uint32)
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 

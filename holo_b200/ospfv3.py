@@ -209,14 +209,15 @@ class Flat:
 RID_BASE = 0x0A000001
 
 
-def synth_area(t: Topology, root: int = 0, max_links_per_fragment: int = 0, max_paths: int = 16) -> Ospfv3Area:
+def synth_area(t: Topology, root: int = 0, max_links_per_fragment: int = 0, max_paths: int = 16,
+               rids=None, area_id: int = 0) -> Ospfv3Area:
     """OSPFv3 area LSDB for topology `t` seen by router `root`.  Interface ids are
     per-router link ordinals (1-based); Router-LSAs are split into fragments of
     `max_links_per_fragment` links when > 0 (RFC 5340 4.8.1 aggregate); one
     Intra-Area-Prefix-LSA per router (a /128 loopback, metric 0, plus one /64 per
     p2p link) and one per LAN (referencing the Network-LSA)."""
     R = t.n_routers
-    rid = lambda i: RID_BASE + int(i)
+    rid = (lambda i: RID_BASE + int(i)) if rids is None else (lambda i: int(rids[int(i)]))
     per = [[] for _ in range(R)]          # (iface_id, nbr_iface_id, nbr_rid, metric, type)
     nif = [0] * R
     p2p_if = []
@@ -248,7 +249,8 @@ def synth_area(t: Topology, root: int = 0, max_links_per_fragment: int = 0, max_
         for frag, ch in enumerate(chunks):
             rl.append((rid(i), frag, 1, 0, OPT_R | OPT_V6, len(links), len(ch)))
             links += [(a, b, c, d, e, 0) for (a, b, c, d, e) in ch]
-    area = Ospfv3Area(router_id=rid(root), max_paths=max_paths)
+    area = Ospfv3Area(router_id=rid(root), max_paths=max_paths, area_id=area_id)
+    rl.sort(key=lambda x: (x[0], x[1]))          # LsaKey order (adv_rtr, lsa_id)
     area.router_lsas = np.asarray(rl, dtype=ROUTER_LSA_DT)
     area.links = np.asarray(links, dtype=LINK_DT) if links else np.zeros(0, LINK_DT)
     nl = np.zeros(len(net_lsas), NETWORK_LSA_DT)
