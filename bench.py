@@ -32,6 +32,12 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# Multi-GPU overlap: the NCCL all-gather of step s must be able to run beside the persistent
+# batch kernel of step s+1.  Give every stream its own hardware queue and let NCCL's stream
+# win the block scheduler (the batch kernel's CTAs fetch jobs dynamically, so they simply
+# take whatever SMs are left).  Must be set before CUDA / NCCL initialise.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
 
 import numpy as np  # noqa: E402
 
@@ -251,7 +257,7 @@ def run_ours(args):
     def plane(buf, k, dtype, shape):
         return buf[offs[k]: offs[k] + sizes[k]].view(dtype).view(shape)
 
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -423,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reserve-sms", type=int, default=12,
+    ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N>1 only: SMs left to the overlapped NCCL all-gather")
     ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
     args = ap.parse_args()

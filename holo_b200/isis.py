@@ -28,7 +28,8 @@ ADJ_DT = np.dtype([("system_id", "<u8"), ("snpa", "u1", (6,)), ("up", "u1"), ("l
                    ("_pad", "u1", (3,)), ("ipv4", "<u4"), ("ipv6", IP_DT)], align=True)
 IFACE_DT = np.dtype([("ifindex", "<u4"), ("metric", "<u4"), ("is_broadcast", "u1"), ("_pad", "u1", (3,)),
                      ("adj_off", "<u4"), ("n_adj", "<u4")], align=True)
-NEXTHOP_DT = np.dtype([("system_id", "<u8"), ("iface", "<u4"), ("_pad", "<u4"), ("addr", IP_DT)], align=True)
+NEXTHOP_DT = np.dtype([("system_id", "<u8"), ("iface", "<u4"), ("_pad", "<u4"), ("addr", IP_DT), ("_pad2", "<u4")],
+                      align=True)
 ROUTE_DT = np.dtype([("prefix", IP_DT), ("metric", "<u4"), ("len", "u1"), ("route_type", "u1"), ("flags", "u1"),
                      ("_pad", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
 IP_V4_INTERNAL, IP_V4_EXTERNAL, IP_V4_EXT, IP_V6, IP_MT_V6 = range(5)

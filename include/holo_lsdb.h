@@ -505,6 +505,7 @@ typedef struct hl_isis_nexthop {
     uint32_t iface;         /* index into ifaces[] */
     uint32_t _pad;
     hl_ip_addr addr;
+    uint32_t _pad2;         /* explicit tail padding: the struct has no hidden bytes */
 } hl_isis_nexthop;
 
 #define HL_ISIS_RT_L2_INTRA 0u   /* IsisRouteType order (holo-utils/src/southbound.rs:99-106) */
