@@ -87,6 +87,9 @@ extern "C" {
                                        OSPF u16 saturating_add (spf.rs:672) makes the
                                        ECMP DAG pop-order dependent; use the CPU path */
 #define HSPF_JS_TOO_MANY_ATOMS 0x2u /* first-hop atoms > 64*nh_words              */
+#define HSPF_JS_ORDER          0x4u /* an override put a zero cost on a link out of a
+                                       hop-counting vertex: pop-order dependent, use the
+                                       CPU path (same reason as HSPF_E_NEEDS_ORACLE)    */
 
 /*
  * Flattened link-state graph of one area / level / topology.

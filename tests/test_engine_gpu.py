@@ -185,3 +185,55 @@ def test_large_vertex_count_uses_global_state(ctx):
     for j, r in enumerate(roots):
         check(res, j, pyoracle.csr_spf_heap(csr, int(r)))
     g.free()
+
+
+def test_edge_cases_through_the_abi(ctx):
+    # single isolated vertex
+    csr = Csr(np.asarray([0, 0], np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32),
+              np.full(1, VF_HOP, np.uint8), saturate_at=0xFFFF)
+    g = ctx.upload(csr)
+    res = ctx.run(g, np.asarray([0], np.uint32))
+    assert res.dist[0, 0] == 0 and res.hops[0, 0] == 0 and res.first_parent[0, 0] == 0xFFFFFFFF
+    # empty job list is a no-op
+    res = ctx.run(g, np.zeros(0, np.uint32))
+    assert res.dist.shape == (0, 1) and res.status == 0
+    # root out of range is rejected on the host
+    with pytest.raises(HspfError):
+        ctx.run(g, np.asarray([5], np.uint32))
+    g.free()
+
+
+def test_override_limits(ctx):
+    t = synth.random_topology(50, 220, synth.SEED_BASE + 31)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    # 8 overrides in one job is the maximum, 9 is refused; results with 8 match the oracle
+    ov8 = [(e, 3 + e) for e in range(8)]
+    res = ctx.run(g, np.asarray([0], np.uint32), overrides=[ov8])
+    check(res, 0, pyoracle.csr_spf(csr, 0, overrides=ov8))
+    with pytest.raises(HspfError):
+        ctx.run(g, np.asarray([0], np.uint32), overrides=[[(e, 1) for e in range(9)]])
+    # a zero-cost override out of a router is order dependent: flagged, not computed silently
+    res = ctx.run(g, np.asarray([0], np.uint32), overrides=[[(0, 0)]])
+    assert res.status == HSPF_E_JOB_STATUS and res.job_status[0] & 0x4
+    g.free()
+
+
+def test_many_first_hop_atoms_need_more_words(ctx):
+    # a root on several large LANs has > 64 first-hop atoms
+    lans = [([0] + list(range(1 + 30 * k, 1 + 30 * (k + 1))), [10] * 31) for k in range(3)]
+    R = 100
+    a = np.arange(1, R, dtype=np.uint32)
+    t = synth.Topology(R, a, a - 1, np.full(R - 1, 7, np.uint32), np.full(R - 1, 9, np.uint32), lans)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    root = len(lans) + 0
+    from holo_b200.capi import atom_count, JS_TOO_MANY_ATOMS
+    n_atoms = atom_count(csr, root)
+    assert n_atoms > 64
+    res = ctx.run(g, np.asarray([root], np.uint32), nh_words=1)
+    assert res.job_status[0] & JS_TOO_MANY_ATOMS
+    res = ctx.run(g, np.asarray([root], np.uint32), nh_words=4)
+    assert res.status == 0
+    check(res, 0, pyoracle.csr_spf(csr, root, nh_words=4))
+    g.free()
