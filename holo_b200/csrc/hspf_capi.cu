@@ -126,6 +126,8 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
     a.out_status = out->job_status;
     a.nhw = out->nh_words;
     a.job_counter = ctx->d_counter;
+    // pointer-jumping next-hop phase: needs the aliased layout (dagbit in qa, words over dist)
+    a.jump_ok = (in_smem && q16 && lay.dagbit == lay.qa && lay.kq0 == lay.dist && !getenv("HSPF_NO_JUMP")) ? 1u : 0u;
 
     int per_sm = in_smem ? (q16 ? max_ctas_per_sm<uint16_t, true>(sb) : max_ctas_per_sm<uint32_t, true>(sb))
                          : (q16 ? max_ctas_per_sm<uint16_t, false>(0) : max_ctas_per_sm<uint32_t, false>(0));

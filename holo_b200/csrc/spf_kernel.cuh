@@ -77,6 +77,7 @@ struct BatchArgs {
     uint8_t *ws;              // per-CTA global workspace when state does not fit smem
     size_t ws_stride;         // bytes per CTA (0: state in smem)
     uint32_t *job_counter;    // dynamic job fetch
+    uint32_t jump_ok;         // layout allows the pointer-jumping next-hop phase (see phase 3J)
     uint32_t sm_limit;        // CTAs that land on an SM with %smid >= sm_limit exit at once (0 = no limit)
     unsigned long long *prof; // optional [gridDim][16] per-phase cycle counters (debug), may be null
 };
@@ -125,6 +126,9 @@ struct Small {  // small per-CTA control block in smem
     uint32_t n_roottab;
     uint32_t rt_target[kMaxRootDeg];  // non-HOP heads of root edges
     uint32_t rt_base[kMaxRootDeg];    // first-hop atom base of that head
+    uint32_t rt_cost[kMaxRootDeg];    // cost of that root edge
+    uint32_t root_rb;                 // row[root]
+    uint32_t n_atoms;                 // first-hop atoms of this root (root edges + edges of its non-HOP heads)
 };
 
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {
@@ -290,11 +294,6 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // ---- per-job init -----------------------------------------------------
         for (uint32_t v = tid; v < Vp; v += kThreads) dist[v] = kInf;
         for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
-        {   // zero the next-hop plane (it is accumulated with atomics later)
-            uint64_t *p = o_nh;
-            const size_t n = (size_t)V * nhw;
-            for (size_t i = tid; i < n; i += kThreads) p[i] = 0ull;
-        }
         if (tid == 0) {
             S.status = 0;
             S.cnt[0] = 1;
@@ -335,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     if (nt < (uint32_t)kMaxRootDeg) {
                         S.rt_target[nt] = h;
                         S.rt_base[nt] = nextbase;
+                        S.rt_cost[nt] = g.edge[e].y;
                         ++nt;
                     } else {
                         atomicOr(&S.status, kJsTooManyAtoms);
@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 }
             }
             S.n_roottab = nt;
+            S.root_rb = rb;
+            S.n_atoms = nextbase;
         }
         __syncthreads();
 
@@ -457,10 +459,33 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         }
         HSPF_MARK(1);   // SSSP
         // SSSP done: qa/qb/bm0/bm1 are dead, dist is final.
+        // Next hops are propagated either by pointer jumping over the first-parent tree
+        // (phase 3J: O(log depth) regular rounds) or by a Kahn push over the ECMP DAG
+        // (phase 3K: one round per DAG level; handles every case).
+        const bool use_jump = kFast && kSmemState && sizeof(VT) == 2 && a.jump_ok && S.n_atoms <= 16u;
+        uint16_t *fp16 = hops_s;          // jump path: first parent per vertex (0xFFFF: none)
+        uint32_t *h0bm = bm0;             // jump path: non-HOP heads of root edges that sit at hops 0
+        uint32_t *ecmpbm = bm1;           // jump path: vertices with two or more parents
         for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
-        for (uint32_t w = tid; w < nbw; w += kThreads) bm0[w] = 0;
-        for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
+        for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
+        if (!use_jump) {
+            for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
+            // zero the next-hop plane (the Kahn push accumulates it with atomics)
+            const size_t n = (size_t)V * nhw;
+            for (size_t i = tid; i < n; i += kThreads) o_nh[i] = 0ull;
+        }
         __syncthreads();
+        if (use_jump) {
+            if (tid < S.n_roottab) {
+                const uint32_t h = S.rt_target[tid];
+                if (dist[h] == S.rt_cost[tid]) atomicOr(&h0bm[h >> 5], 1u << (h & 31));
+            }
+            __syncthreads();
+        }
+        // u sits at hops 0: the root, or a non-HOP vertex whose first parent is the root
+        auto hops0 = [&](uint32_t u) -> bool {
+            return u == root || ((h0bm[u >> 5] >> (u & 31)) & 1u);
+        };
 
         // ======================= phase 2: ECMP parents (pull) ====================
         uint32_t sat_flag = 0;
@@ -539,12 +564,17 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 if (key < bkey || (key == bkey && u < bu)) { bkey = key; bu = u; be = e; }
                             }
                         }
-                        if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
+                        if (cnt && !use_jump) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
                     }
                     o_fp[v] = bu;
                     o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
                 }
-                pend[v] = (uint16_t)min(cnt, 0xFFFFu);
+                if (use_jump) {
+                    fp16[v] = (uint16_t)(cnt ? bu : 0xFFFFu);
+                    if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
+                } else {
+                    pend[v] = (uint16_t)min(cnt, 0xFFFFu);
+                }
             }
         }
         if (sat_flag) atomicOr(&S.status, kJsSaturated);
@@ -553,11 +583,134 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // distances are final: stream them out, then the region is reused by the Kahn queues
         for (uint32_t v = tid; v < V; v += kThreads) o_dist[v] = dist[v];
         __syncthreads();
+        HSPF_MARK(3);   // dist write-back
+        if (use_jump) {
+            // ======================= phase 3J: pointer jumping =======================
+            // Hops and next hops are path aggregates over the first-parent tree (sum of the
+            // HOP flags, OR of the first-hop atoms), so they are computed by pointer doubling
+            // in ceil(log2(depth)) rounds of perfectly regular work instead of one round per
+            // DAG level.  Each vertex is one 32-bit word (ancestor:16 | aggregate:16) that
+            // only its owner thread stores, so a reader always sees a consistent pair and the
+            // rounds can update in place without double buffering.
+            uint32_t *word = dist;
+            // -- hops: sum of HOP flags over (root, v]
+            for (uint32_t v = tid; v < Vp; v += kThreads) {
+                const uint32_t f = fp16[v];
+                word[v] = (f == 0xFFFFu) ? (v << 16) : ((f << 16) | (is_hop(v) ? 1u : 0u));
+            }
+            __syncthreads();
+            for (;;) {
+                int ch = 0;
+                for (uint32_t v = tid; v < Vp; v += kThreads) {
+                    const uint32_t w = word[v], A = w >> 16;
+                    if (A != root && A != v) {
+                        const uint32_t w2 = word[A];
+                        word[v] = (w2 & 0xFFFF0000u) | ((w + w2) & 0xFFFFu);
+                        ch |= (w2 >> 16) != root;
+                    }
+                }
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
+                if (!__syncthreads_or(ch)) break;
+            }
+            for (uint32_t v = tid; v < V; v += kThreads) {
+                const uint32_t w = word[v];
+                const uint32_t h = (w >> 16) == v ? 0u : (w & 0xFFFFu);
+                o_hops[v] = (uint16_t)h;
+                // a hops-0 vertex that is not a head of a root edge cannot own atoms
+                if (h == 0 && v != root && fp16[v] != 0xFFFFu && !hops0(v) && g.row[v + 1] != g.row[v])
+                    atomicOr(&S.status, kJsTooManyAtoms);
+            }
+            __syncthreads();
+            HSPF_MARK(5);   // jump path: hops
+            // -- next hops.  nh[v] = atoms entering v | U nh[p] over DAG parents p that are not
+            // at hops 0.  Between two ECMP vertices every vertex has one parent, so the tree is
+            // cut below hops-0 vertices and AT ECMP vertices (they are jump terminals):
+            //   word[v] = (top[v], atoms on the segment (top[v], v])
+            // then the few ECMP vertices are resolved among themselves (monotone sweeps to
+            // the fixpoint over a list of ~1 % of the vertices) and every vertex adds the
+            // final set of its top.
+            auto is_ecmp = [&](uint32_t v) -> bool { return (ecmpbm[v >> 5] >> (v & 31)) & 1u; };
+            for (uint32_t v = tid; v < Vp; v += kThreads) {
+                const uint32_t f = fp16[v];
+                word[v] = ((f == 0xFFFFu || hops0(f)) ? root : f) << 16;
+            }
+            __syncthreads();
+            if (tid < S.n_atoms) {   // one thread per first-hop atom: seed the head of its edge
+                const uint32_t atom = tid, rdeg = g.row[root + 1] - S.root_rb;
+                uint32_t e = kInf;
+                if (atom < rdeg) {
+                    e = S.root_rb + atom;
+                } else {
+                    for (uint32_t k = 0; k < S.n_roottab; ++k) {
+                        const uint32_t N = S.rt_target[k], nb = S.rt_base[k];
+                        if (atom < nb || atom >= nb + (g.row[N + 1] - g.row[N])) continue;
+                        bool first = true;   // parallel root edges: only the first one's range is used
+                        for (uint32_t q = 0; q < k; ++q) first = first && S.rt_target[q] != N;
+                        if (first && hops0(N)) e = g.row[N] + (atom - nb);
+                        break;
+                    }
+                }
+                if (e != kInf && ((dagbit[e >> 5] >> (e & 31)) & 1u)) {
+                    const uint32_t v = g.edge[e].x;
+                    if (!((g.flags & kGfNoHopTargetNoNh) && !is_hop(v))) atomicOr(&word[v], 1u << atom);
+                }
+            }
+            __syncthreads();
+            for (;;) {
+                int ch = 0;
+                for (uint32_t v = tid; v < Vp; v += kThreads) {
+                    const uint32_t w = word[v], A = w >> 16;
+                    if (A != root && !is_ecmp(A)) {
+                        const uint32_t w2 = word[A], A2 = w2 >> 16;
+                        word[v] = (w2 & 0xFFFF0000u) | ((w | w2) & 0xFFFFu);
+                        ch |= A2 != root && !is_ecmp(A2);
+                    }
+                }
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 14] += 1;
+                if (!__syncthreads_or(ch)) break;
+            }
+            // ECMP vertices: own segment | final set of own top | the same of every other parent
+            uint16_t *elist = pend;
+            if (tid == 0) S.cnt[0] = 0;
+            __syncthreads();
+            bitmap_to_queue<false>(ecmpbm, nbw, elist, &S.cnt[0], [](uint32_t) { return true; });
+            __syncthreads();
+            const uint32_t n_e = S.cnt[0];
+            if (n_e) {
+                for (;;) {
+                    int ch = 0;
+                    for (uint32_t i = tid; i < n_e; i += kThreads) {
+                        const uint32_t x = elist[i];
+                        const uint32_t w = word[x], T = w >> 16;
+                        uint32_t need = (T != root) ? word[T] : 0u;
+                        for (uint32_t j = g.irow[x]; j < g.irow[x + 1]; ++j) {
+                            const uint4 sc = g.iedge[j];
+                            if (!((dagbit[sc.z >> 5] >> (sc.z & 31)) & 1u) || hops0(sc.x)) continue;
+                            const uint32_t wp = word[sc.x], Tp = wp >> 16;
+                            need |= wp;
+                            if (Tp != root) need |= word[Tp];
+                        }
+                        need &= 0xFFFFu & ~w;
+                        if (need) { word[x] = w | need; ch = 1; }
+                    }
+                    if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 15] += 1;
+                    if (!__syncthreads_or(ch)) break;
+                }
+            }
+            for (uint32_t v = tid; v < V; v += kThreads) {
+                const uint32_t w = word[v], T = w >> 16;
+                uint32_t m = w;
+                if (T != root) m |= word[T];
+                o_nh[v] = (uint64_t)(m & 0xFFFFu);
+            }
+            if (tid == 0) a.out_status[job] = S.status;
+            HSPF_MARK(4);
+            continue;
+        }
         if (tid == 0) { S.cnt[0] = 1; S.cnt[1] = 0; kq0[0] = (VT)root; }
         __syncthreads();
 
-        HSPF_MARK(3);   // dist write-back
-        // ======================= phase 3: Kahn push over the ECMP DAG ============
+        // ======================= phase 3K: Kahn push over the ECMP DAG ===========
         {
             VT *kcur = kq0, *knext = kq1;
             p = 0;

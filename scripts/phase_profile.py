@@ -21,12 +21,17 @@ lib.hspf_debug_phase_profile(ctx.handle, 1, None)
 ctx.run(g, roots)
 out = (C.c_uint64 * 16)()
 lib.hspf_debug_phase_profile(ctx.handle, 0, out)
-names = ["init", "sssp", "parents", "dist_wb", "kahn", "hops_wb"]
+import os
+jump = not os.environ.get("HSPF_NO_JUMP")
+names = ["init", "sssp", "parents", "dist_wb", "jump_nh" if jump else "kahn", "jump_hops" if jump else "hops_wb"]
 tot = sum(out[k] for k in range(6))
 print("delta", delta, "total Mcycles", tot / 1e6, "per job kcycles", tot / 1000 / 1e3)
 print("  kahn rounds/job", out[6] / 1000, " sssp rounds/job", out[7] / 1000)
 print("  sssp per job: frontier entries", out[12] / 1000, " kcycles: expand(t0)", out[8] / 1e6, " barrier1", out[9] / 1e6,
       " compact", out[10] / 1e6, " barrier2", out[11] / 1e6)
-print("  kahn per job kcycles: expand(t0)", out[13] / 1e6, " barrier1", out[14] / 1e6, " compact+barrier2", out[15] / 1e6)
+if jump:
+    print("  jump per job: hop rounds", out[13] / 1000, " nh rounds", out[14] / 1000, " closure sweeps", out[15] / 1000)
+else:
+    print("  kahn per job kcycles: expand(t0)", out[13] / 1e6, " barrier1", out[14] / 1e6, " compact+barrier2", out[15] / 1e6)
 for k, n in enumerate(names):
     print(f"  {n:8s} {100 * out[k] / tot:5.1f}%  {out[k] / 1000 / 1e3:8.1f} kcycles/job")

@@ -237,3 +237,57 @@ def test_many_first_hop_atoms_need_more_words(ctx):
     assert res.status == 0
     check(res, 0, pyoracle.csr_spf(csr, root, nh_words=4))
     g.free()
+
+
+@pytest.mark.parametrize("V,E,seed,kw,isis", [
+    (100, 400, 3, {}, False),
+    (100, 400, 4, dict(cost_choices=[10, 20]), False),          # heavy ECMP
+    (300, 1400, 5, dict(lan_fraction=0.1), False),              # non-HOP vertices at hops 0
+    (300, 1400, 6, dict(cost_choices=[10, 20], lan_fraction=0.1), True),
+    (400, 1200, 8, dict(cost_choices=[5]), False),              # all-equal costs: ECMP under ECMP
+    (3000, 12000, 9, dict(cost_choices=[10, 20, 30], lan_fraction=0.05), False),
+])
+def test_jump_and_kahn_next_hop_phases_agree_with_oracle(ctx, monkeypatch, V, E, seed, kw, isis):
+    """One next-hop word, no overrides: the engine propagates next hops by pointer jumping
+    when the root has at most 32 first-hop atoms and by the Kahn push otherwise (or when
+    HSPF_NO_JUMP is set).  Both must give the oracle's planes."""
+    t = synth.random_topology(V, E, synth.SEED_BASE + seed, **kw)
+    csr = synth.topology_csr(t, isis=isis)
+    g = ctx.upload(csr)
+    nv = csr.n_vertices
+    roots = np.arange(nv, dtype=np.uint32) if nv <= 400 else np.arange(0, nv, 41, dtype=np.uint32)
+    refs = [pyoracle.csr_spf(csr, int(r), vec_mode=int(isis), nh_words=1) for r in roots]
+    ok = [j for j, ref in enumerate(refs) if ref["status"] == 0]
+    assert len(ok) > len(roots) // 2
+    for no_jump in (False, True):
+        if no_jump:
+            monkeypatch.setenv("HSPF_NO_JUMP", "1")
+        else:
+            monkeypatch.delenv("HSPF_NO_JUMP", raising=False)
+        res = ctx.run(g, roots, nh_words=1)   # a root that ran out of atoms only flags its own job
+        for j in ok:
+            check(res, j, refs[j])
+        for j, ref in enumerate(refs):
+            assert res.job_status[j] == ref["status"]
+    g.free()
+
+
+def test_atom_count_selects_the_next_hop_phase_per_job(ctx):
+    """One batch mixes roots below and above the 32-atom limit of the jump phase: a root on
+    two 20-router LANs (43 atoms, Kahn push) and ordinary routers (jump)."""
+    lans = [([0] + list(range(1 + 20 * k, 1 + 20 * (k + 1))), [10] * 21) for k in range(2)]
+    R = 120
+    a = np.arange(1, R, dtype=np.uint32)
+    t = synth.Topology(R, a, a - 1, np.full(R - 1, 7, np.uint32), np.full(R - 1, 9, np.uint32), lans)
+    csr = synth.topology_csr(t)
+    from holo_b200.capi import atom_count
+    L = len(lans)
+    roots = np.asarray([L + 0, L + 5, L + 60, L + 119, 0, 1], np.uint32)   # router 0, others, both LAN vertices
+    counts = [atom_count(csr, int(r)) for r in roots]
+    assert max(counts) > 32 and min(counts) <= 32 and max(counts) <= 64
+    g = ctx.upload(csr)
+    res = ctx.run(g, roots, nh_words=1)
+    assert res.status == 0
+    for j, r in enumerate(roots):
+        check(res, j, pyoracle.csr_spf(csr, int(r), nh_words=1))
+    g.free()
