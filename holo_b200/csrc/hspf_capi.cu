@@ -127,7 +127,8 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
     a.nhw = out->nh_words;
     a.job_counter = ctx->d_counter;
     // pointer-jumping next-hop phase: needs the aliased layout (dagbit in qa, words over dist)
-    a.jump_ok = (in_smem && q16 && lay.dagbit == lay.qa && lay.kq0 == lay.dist && !getenv("HSPF_NO_JUMP")) ? 1u : 0u;
+    a.jump_ok = (in_smem && q16 && g->d.iedge16 && g->d.edge16 && g->d.iquad && lay.dagbit == lay.qa && lay.kq0 == lay.dist && !getenv("HSPF_NO_JUMP")) ? 1u : 0u;
+    if (getenv("HSPF_NO_ROW16")) a.g.row16 = nullptr;   // tuning knob (experiments only)
 
     int per_sm = in_smem ? (q16 ? max_ctas_per_sm<uint16_t, true>(sb) : max_ctas_per_sm<uint32_t, true>(sb))
                          : (q16 ? max_ctas_per_sm<uint16_t, false>(0) : max_ctas_per_sm<uint32_t, false>(0));
@@ -316,13 +317,44 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
                 fedge[e] = make_uint2(v, g->cost[e]);
             }
 
+        // compact twins used by the jump phase when ids and costs fit 16 bits: row offsets
+        // (kept in shared memory during the SSSP) and in-edges as (source | cost << 16)
+        uint32_t max_cost = 0;
+        for (uint32_t e = 0; e < E; ++e) max_cost = std::max(max_cost, g->cost[e]);
+        const bool pack_rows = V <= 0xFFFFu && E <= 0xFFFFu;
+        const bool pack_in = V <= 0xFFFFu && max_cost <= 0xFFFFu;
+        std::vector<uint16_t> row16(pack_rows ? V : 0);
+        for (uint32_t v = 0; v < (uint32_t)row16.size(); ++v) row16[v] = (uint16_t)g->row_ptr[v];
+        std::vector<uint32_t> iedge16(pack_in ? E : 0);
+        for (uint32_t k = 0; k < (uint32_t)iedge16.size(); ++k) iedge16[k] = iedge[k].x | (iedge[k].y << 16);
+        // ... and the same in-edge records padded per vertex to whole 16-byte quads (pad record
+        // 0xFFFFFFFF: source 0xFFFF is never a vertex id), so the parents pass reads the usual
+        // four in-edges of a vertex with one 128-bit load
+        std::vector<uint32_t> iquad_row(pack_in ? V + 1 : 0);
+        std::vector<uint32_t> iquad;
+        if (pack_in) {
+            for (uint32_t v = 0; v < V; ++v) {
+                iquad_row[v] = (uint32_t)(iquad.size() / 4);
+                for (uint32_t k = irow[v]; k < irow[v + 1]; ++k) iquad.push_back(iedge16[k]);
+                while (iquad.size() % 4) iquad.push_back(0xFFFFFFFFu);
+            }
+            iquad_row[V] = (uint32_t)(iquad.size() / 4);
+        }
+        std::vector<uint32_t> edge16(pack_in ? E : 0);     // forward edges as (head | cost << 16)
+        for (uint32_t e = 0; e < (uint32_t)edge16.size(); ++e) edge16[e] = fedge[e].x | (fedge[e].y << 16);
+
         auto al = [](size_t x) { return (x + 255) / 256 * 256; };
         const size_t o_row = 0;
         const size_t o_edge = o_row + al((size_t)(V + 1) * 4);
         const size_t o_irow = o_edge + al((size_t)E * 8);
         const size_t o_iedge = o_irow + al((size_t)(V + 1) * 4);
         const size_t o_vf = o_iedge + al((size_t)E * 16);
-        const size_t total = o_vf + al(V);
+        const size_t o_row16 = o_vf + al(V);
+        const size_t o_iedge16 = o_row16 + al(row16.size() * 2);
+        const size_t o_edge16 = o_iedge16 + al(iedge16.size() * 4);
+        const size_t o_iqrow = o_edge16 + al(edge16.size() * 4);
+        const size_t o_iquad = o_iqrow + al(iquad_row.size() * 4);
+        const size_t total = o_iquad + al(iquad.size() * 4);
 
         hspf_graph *G = new hspf_graph();
         cudaError_t e = cudaSetDevice(ctx->device);
@@ -338,6 +370,11 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         }
         std::memcpy(host.data() + o_irow, irow.data(), (size_t)(V + 1) * 4);
         std::memcpy(host.data() + o_vf, g->vflags, V);
+        if (!row16.empty()) std::memcpy(host.data() + o_row16, row16.data(), row16.size() * 2);
+        if (!iedge16.empty()) std::memcpy(host.data() + o_iedge16, iedge16.data(), iedge16.size() * 4);
+        if (!edge16.empty()) std::memcpy(host.data() + o_edge16, edge16.data(), edge16.size() * 4);
+        if (!iquad_row.empty()) std::memcpy(host.data() + o_iqrow, iquad_row.data(), iquad_row.size() * 4);
+        if (!iquad.empty()) std::memcpy(host.data() + o_iquad, iquad.data(), iquad.size() * 4);
         e = cudaMemcpyAsync(b, host.data(), total, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { cudaFree(G->blob); delete G; return cuda_fail(ctx, e, "graph H2D"); }
@@ -348,6 +385,11 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         G->d.irow = reinterpret_cast<const uint32_t *>(b + o_irow);
         G->d.iedge = reinterpret_cast<const uint4 *>(b + o_iedge);
         G->d.vflags = b + o_vf;
+        G->d.row16 = row16.empty() ? nullptr : reinterpret_cast<const uint16_t *>(b + o_row16);
+        G->d.iedge16 = iedge16.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_iedge16);
+        G->d.edge16 = edge16.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_edge16);
+        G->d.iquad_row = iquad_row.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_iqrow);
+        G->d.iquad = iquad.empty() ? nullptr : reinterpret_cast<const uint4 *>(b + o_iquad);
         G->d.reject_above = g->reject_above;
         G->d.saturate_at = g->saturate_at;
         G->d.flags = g->flags;

@@ -49,6 +49,11 @@ struct DevGraph {
     const uint32_t *irow;   // [V+1] transposed
     const uint4 *iedge;     // [E] {src, cost, forward edge index, 0}: one 16 B load per in-edge
     const uint8_t *vflags;  // [V]
+    const uint16_t *row16;  // [V] row offsets as u16 (null unless V, E < 65536)
+    const uint32_t *iedge16;// [E] in-edges as (src | cost << 16) (null unless ids and costs fit 16 bits)
+    const uint32_t *edge16; // [E] forward edges as (head | cost << 16), same condition
+    const uint32_t *iquad_row; // [V+1] first quad of each vertex in iquad
+    const uint4 *iquad;     // in-edge records of iedge16, each vertex padded to whole quads with 0xFFFFFFFF
     uint32_t reject_above, saturate_at, flags, delta;
 };
 
@@ -276,6 +281,14 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         return !((fl_leaf[u >> 5] & b) || ((fl_lur[u >> 5] & b) && u != root_));
     };
 
+    // Jump-capable launch (see phase 3J): the `pend` block is not needed by the jump path,
+    // so it keeps the CSR row offsets (u16) across jobs and the SSSP reads them from
+    // shared memory instead of L2.
+    const bool jumpable = kFast && kSmemState && sizeof(VT) == 2 && a.jump_ok;
+    const bool use_row16 = jumpable && g.row16 != nullptr;
+    uint16_t *row_s = pend;
+    bool row_valid = false;
+
     for (;;) {
         // ---- fetch next job -------------------------------------------------
         __syncthreads();
@@ -294,6 +307,10 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // ---- per-job init -----------------------------------------------------
         for (uint32_t v = tid; v < Vp; v += kThreads) dist[v] = kInf;
         for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
+        if (use_row16 && !row_valid) {
+            for (uint32_t v = tid; v < V; v += kThreads) row_s[v] = g.row16[v];
+            row_valid = true;
+        }
         if (tid == 0) {
             S.status = 0;
             S.cnt[0] = 1;
@@ -379,14 +396,44 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                         du[st] = 0; eb[st] = 0; ee[st] = 0;
                         if (uu[st] != kInf && vexpands(uu[st], root)) {
                             du[st] = dist[uu[st]];
-                            eb[st] = g.row[uu[st]];
-                            ee[st] = g.row[uu[st] + 1];
+                            if (use_row16) {
+                                eb[st] = row_s[uu[st]];
+                                ee[st] = (uu[st] + 1 < V) ? (uint32_t)row_s[uu[st] + 1] : g.E;
+                            } else {
+                                eb[st] = g.row[uu[st]];
+                                ee[st] = g.row[uu[st] + 1];
+                            }
                         }
                     }
                     uint32_t maxdeg = 0;
 #pragma unroll
                     for (int st = 0; st < 4; ++st) maxdeg = max(maxdeg, ee[st] - eb[st]);
                     maxdeg = __reduce_max_sync(0xffffffffu, maxdeg);
+                    if (jumpable) {
+                        // packed edges (head | cost << 16): a team covers 8 edges of its vertex per
+                        // iteration with all 8 loads of the lane in flight together, so degrees up
+                        // to 8 cost one L2 round trip
+                        for (uint32_t k = 0; k < maxdeg; k += 8) {
+                            uint32_t r[8];
+#pragma unroll
+                            for (int st = 0; st < 4; ++st) {
+                                const uint32_t e = eb[st] + k + sub;
+                                r[st] = (e < ee[st]) ? g.edge16[e] : 0xFFFFFFFFu;
+                                r[st + 4] = (e + 4 < ee[st]) ? g.edge16[e + 4] : 0xFFFFFFFFu;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint32_t v = r[j] & 0xFFFFu;
+                                if (v == 0xFFFFu) continue;     // padding lane (ids are < 65535)
+                                const uint32_t nd = sat_add(du[j & 3], r[j] >> 16);
+                                if (nd <= g.reject_above && nd < dist[v]) {
+                                    atomicMin(&dist[v], nd);
+                                    if (nd < hi_thr) atomicOr(&bm_next[v >> 5], 1u << (v & 31));
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     for (uint32_t k = 0; k < maxdeg; k += 4) {
                         uint2 ec[4];
 #pragma unroll
@@ -438,15 +485,20 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 __syncthreads();
                 const uint32_t hi2 = sat_add(lo_thr, delta);
                 uint32_t lmin = kInf;
-                for (uint32_t v = tid; v < V; v += kThreads) {
-                    const uint32_t d = dist[v];
-                    if (d >= lo_thr && d != kInf) {
-                        lmin = min(lmin, d);
-                        if (d < hi2) q_push(qcur, &S.cnt[p], v);
-                    }
+                // a warp looks at 32 consecutive vertices per step, so the vertices that fall
+                // into the new bucket are one ballot = one word of the frontier bitmap
+                for (uint32_t v0 = tid & ~31u; v0 < V; v0 += kThreads) {
+                    const uint32_t v = v0 + lane;
+                    const uint32_t d = (v < V) ? dist[v] : kInf;
+                    const bool open = d >= lo_thr && d != kInf;
+                    if (open) lmin = min(lmin, d);
+                    const uint32_t b = __ballot_sync(0xffffffffu, open && d < hi2);
+                    if (lane == 0) bm_next[v0 >> 5] = b;
                 }
                 for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
                 if (lane_id() == 0 && lmin != kInf) atomicMin(&S.scan_min, lmin);
+                __syncthreads();
+                bitmap_to_queue<false>(bm_next, nbw, qcur, &S.cnt[p], [](uint32_t) { return true; });
                 __syncthreads();
                 const uint32_t found = S.cnt[p];
                 const uint32_t m = S.scan_min;
@@ -462,13 +514,14 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         // Next hops are propagated either by pointer jumping over the first-parent tree
         // (phase 3J: O(log depth) regular rounds) or by a Kahn push over the ECMP DAG
         // (phase 3K: one round per DAG level; handles every case).
-        const bool use_jump = kFast && kSmemState && sizeof(VT) == 2 && a.jump_ok && S.n_atoms <= 16u;
+        const bool use_jump = jumpable && S.n_atoms <= 16u;
         uint16_t *fp16 = hops_s;          // jump path: first parent per vertex (0xFFFF: none)
         uint32_t *h0bm = bm0;             // jump path: non-HOP heads of root edges that sit at hops 0
         uint32_t *ecmpbm = bm1;           // jump path: vertices with two or more parents
-        for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
         for (uint32_t w = tid; w < nbw; w += kThreads) { bm0[w] = 0; bm1[w] = 0; }
         if (!use_jump) {
+            row_valid = false;   // the Kahn path overwrites the pend block
+            for (uint32_t w = tid; w < nbe; w += kThreads) { dagbit[w] = 0; fpbit[w] = 0; }
             for (uint32_t v = tid; v < Vp; v += kThreads) hops_s[v] = 0;
             // zero the next-hop plane (the Kahn push accumulates it with atomics)
             const size_t n = (size_t)V * nhw;
@@ -489,7 +542,75 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
 
         // ======================= phase 2: ECMP parents (pull) ====================
         uint32_t sat_flag = 0;
-        {
+        uint32_t seed_v = kInf;   // jump path: head of this thread's first-hop atom edge
+        if (use_jump) {
+            // Packed in-edges (source | cost << 16), four per 16 bytes; no bitmaps and no
+            // atomics: the jump phase needs only the first parent and the ECMP flag.
+            // The quad range of the next vertex and its first quad are fetched one iteration ahead.
+            const uint4 kPad = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            uint32_t qb_n = 0, qe_n = 0;
+            uint4 r_n = kPad;
+            if (tid < V) {
+                qb_n = g.iquad_row[tid]; qe_n = g.iquad_row[tid + 1];
+                if (qb_n < qe_n) r_n = g.iquad[qb_n];
+            }
+            for (uint32_t v = tid; v < Vp; v += kThreads) {
+                const uint32_t qbeg = qb_n, qend = qe_n;
+                uint4 r4 = r_n;
+                qb_n = qe_n = 0; r_n = kPad;
+                if (v + kThreads < V) {
+                    qb_n = g.iquad_row[v + kThreads]; qe_n = g.iquad_row[v + kThreads + 1];
+                    if (qb_n < qe_n) r_n = g.iquad[qb_n];
+                }
+                uint32_t cnt = 0, bu = kInf, bd = kInf;
+                if (v < V) {
+                    const uint32_t dv = dist[v];
+                    if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
+                    if (v != root && dv != kInf) {
+                        for (uint32_t q = qbeg; q < qend; ++q) {
+                            if (q != qbeg) r4 = g.iquad[q];
+                            const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t u = r[k] & 0xFFFFu, c = r[k] >> 16;
+                                if (u == 0xFFFFu) continue;           // pad record
+                                const uint32_t du = dist[u];
+                                if (sat_add(du, c) != dv) continue;   // covers du == inf (dv is finite)
+                                ++cnt;
+                                if (du < bd || (du == bd && u < bu)) { bd = du; bu = u; }
+                            }
+                        }
+                    }
+                    o_fp[v] = bu;
+                    o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
+                }
+                fp16[v] = (uint16_t)(cnt ? bu : 0xFFFFu);
+                if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
+            }
+            if (tid < S.n_atoms) {   // one thread per first-hop atom: is its edge in the DAG?
+                const uint32_t atom = tid, rdeg = g.row[root + 1] - S.root_rb;
+                uint32_t e = kInf, u = root;
+                if (atom < rdeg) {
+                    e = S.root_rb + atom;
+                } else {
+                    for (uint32_t k = 0; k < S.n_roottab; ++k) {
+                        const uint32_t N = S.rt_target[k], nb = S.rt_base[k];
+                        if (atom < nb || atom >= nb + (g.row[N + 1] - g.row[N])) continue;
+                        bool first = true;   // parallel root edges: only the first one's range is used
+                        for (uint32_t q = 0; q < k; ++q) first = first && S.rt_target[q] != N;
+                        if (first && hops0(N)) { u = N; e = g.row[N] + (atom - nb); }
+                        break;
+                    }
+                }
+                if (e != kInf) {
+                    const uint2 ec = g.edge[e];
+                    const uint32_t du = dist[u], dh = dist[ec.x];
+                    if (du != kInf && dh != kInf && ec.y != kInf && sat_add(du, ec.y) == dh &&
+                        !((g.flags & kGfNoHopTargetNoNh) && !is_hop(ec.x)))
+                        seed_v = ec.x;
+                }
+            }
+        } else {
             // in-edge range of the next vertex is fetched one iteration ahead
             uint32_t ib_n = 0, ie_n = 0;
             if (tid < V) { ib_n = g.irow[tid]; ie_n = g.irow[tid + 1]; }
@@ -564,17 +685,12 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                                 if (key < bkey || (key == bkey && u < bu)) { bkey = key; bu = u; be = e; }
                             }
                         }
-                        if (cnt && !use_jump) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
+                        if (cnt) atomicOr(&fpbit[be >> 5], 1u << (be & 31));
                     }
                     o_fp[v] = bu;
                     o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
                 }
-                if (use_jump) {
-                    fp16[v] = (uint16_t)(cnt ? bu : 0xFFFFu);
-                    if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
-                } else {
-                    pend[v] = (uint16_t)min(cnt, 0xFFFFu);
-                }
+                pend[v] = (uint16_t)min(cnt, 0xFFFFu);
             }
         }
         if (sat_flag) atomicOr(&S.status, kJsSaturated);
@@ -635,26 +751,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 word[v] = ((f == 0xFFFFu || hops0(f)) ? root : f) << 16;
             }
             __syncthreads();
-            if (tid < S.n_atoms) {   // one thread per first-hop atom: seed the head of its edge
-                const uint32_t atom = tid, rdeg = g.row[root + 1] - S.root_rb;
-                uint32_t e = kInf;
-                if (atom < rdeg) {
-                    e = S.root_rb + atom;
-                } else {
-                    for (uint32_t k = 0; k < S.n_roottab; ++k) {
-                        const uint32_t N = S.rt_target[k], nb = S.rt_base[k];
-                        if (atom < nb || atom >= nb + (g.row[N + 1] - g.row[N])) continue;
-                        bool first = true;   // parallel root edges: only the first one's range is used
-                        for (uint32_t q = 0; q < k; ++q) first = first && S.rt_target[q] != N;
-                        if (first && hops0(N)) e = g.row[N] + (atom - nb);
-                        break;
-                    }
-                }
-                if (e != kInf && ((dagbit[e >> 5] >> (e & 31)) & 1u)) {
-                    const uint32_t v = g.edge[e].x;
-                    if (!((g.flags & kGfNoHopTargetNoNh) && !is_hop(v))) atomicOr(&word[v], 1u << atom);
-                }
-            }
+            if (seed_v != kInf) atomicOr(&word[seed_v], 1u << tid);   // first-hop atoms enter here
             __syncthreads();
             for (;;) {
                 int ch = 0;
@@ -670,25 +767,49 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                 if (!__syncthreads_or(ch)) break;
             }
             // ECMP vertices: own segment | final set of own top | the same of every other parent
-            uint16_t *elist = pend;
+            uint16_t *elist = fp16;   // (fp16 is dead once the words are initialised)
             if (tid == 0) S.cnt[0] = 0;
             __syncthreads();
             bitmap_to_queue<false>(ecmpbm, nbw, elist, &S.cnt[0], [](uint32_t) { return true; });
             __syncthreads();
             const uint32_t n_e = S.cnt[0];
             if (n_e) {
+                // DAG parents of an ECMP vertex are re-derived from the distance plane just
+                // written (L2); with one vertex per thread they are kept in registers.
+                auto parents = [&](uint32_t x, auto &&f) {
+                    const uint32_t dx = __ldcg(&o_dist[x]);
+                    for (uint32_t j = g.irow[x]; j < g.irow[x + 1]; ++j) {
+                        const uint32_t r = g.iedge16[j], u = r & 0xFFFFu;
+                        if (sat_add(__ldcg(&o_dist[u]), r >> 16) == dx && !hops0(u)) f(u);
+                    }
+                };
+                uint32_t pc[4] = {kInf, kInf, kInf, kInf};
+                bool cached = false;
+                if (n_e <= (uint32_t)kThreads && tid < n_e) {
+                    uint32_t n = 0;
+                    parents(elist[tid], [&](uint32_t u) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (n == (uint32_t)k) pc[k] = u;
+                        ++n;
+                    });
+                    cached = n <= 4;
+                }
                 for (;;) {
                     int ch = 0;
                     for (uint32_t i = tid; i < n_e; i += kThreads) {
                         const uint32_t x = elist[i];
                         const uint32_t w = word[x], T = w >> 16;
                         uint32_t need = (T != root) ? word[T] : 0u;
-                        for (uint32_t j = g.irow[x]; j < g.irow[x + 1]; ++j) {
-                            const uint4 sc = g.iedge[j];
-                            if (!((dagbit[sc.z >> 5] >> (sc.z & 31)) & 1u) || hops0(sc.x)) continue;
-                            const uint32_t wp = word[sc.x], Tp = wp >> 16;
+                        auto pull_parent = [&](uint32_t u) {
+                            const uint32_t wp = word[u], Tp = wp >> 16;
                             need |= wp;
                             if (Tp != root) need |= word[Tp];
+                        };
+                        if (cached) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (pc[k] != kInf) pull_parent(pc[k]);
+                        } else {
+                            parents(x, pull_parent);
                         }
                         need &= 0xFFFFu & ~w;
                         if (need) { word[x] = w | need; ch = 1; }
