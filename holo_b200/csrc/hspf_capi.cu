@@ -327,8 +327,8 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         for (uint32_t v = 0; v < (uint32_t)row16.size(); ++v) row16[v] = (uint16_t)g->row_ptr[v];
         std::vector<uint32_t> iedge16(pack_in ? E : 0);
         for (uint32_t k = 0; k < (uint32_t)iedge16.size(); ++k) iedge16[k] = iedge[k].x | (iedge[k].y << 16);
-        // ... and the same in-edge records padded per vertex to whole 16-byte quads (pad record
-        // 0xFFFFFFFF: source 0xFFFF is never a vertex id), so the parents pass reads the usual
+        // ... and the same in-edge records padded per vertex to whole 16-byte quads (pad record:
+        // the vertex itself with cost 0xFFFF, which can never be a parent), so the parents pass reads the usual
         // four in-edges of a vertex with one 128-bit load
         std::vector<uint32_t> iquad_row(pack_in ? V + 1 : 0);
         std::vector<uint32_t> iquad;
@@ -336,7 +336,7 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
             for (uint32_t v = 0; v < V; ++v) {
                 iquad_row[v] = (uint32_t)(iquad.size() / 4);
                 for (uint32_t k = irow[v]; k < irow[v + 1]; ++k) iquad.push_back(iedge16[k]);
-                while (iquad.size() % 4) iquad.push_back(0xFFFFFFFFu);
+                while (iquad.size() % 4) iquad.push_back(v | 0xFFFF0000u);   // pad: self-loop, never a parent
             }
             iquad_row[V] = (uint32_t)(iquad.size() / 4);
         }

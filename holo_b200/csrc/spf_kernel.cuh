@@ -413,20 +413,28 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                         // packed edges (head | cost << 16): a team covers 8 edges of its vertex per
                         // iteration with all 8 loads of the lane in flight together, so degrees up
                         // to 8 cost one L2 round trip
+                        // A padding lane relaxes the team's own vertex with cost 0xFFFF (never an
+                        // improvement), so the body needs no validity branch and the eight
+                        // distance reads go out together.  No overflow: a finite distance is at
+                        // most 65534 * 65535.
+                        uint32_t pad[4];
+#pragma unroll
+                        for (int st = 0; st < 4; ++st) pad[st] = ((uu[st] == kInf) ? root : uu[st]) | 0xFFFF0000u;
                         for (uint32_t k = 0; k < maxdeg; k += 8) {
-                            uint32_t r[8];
+                            uint32_t r[8], dh[8];
 #pragma unroll
                             for (int st = 0; st < 4; ++st) {
                                 const uint32_t e = eb[st] + k + sub;
-                                r[st] = (e < ee[st]) ? g.edge16[e] : 0xFFFFFFFFu;
-                                r[st + 4] = (e + 4 < ee[st]) ? g.edge16[e + 4] : 0xFFFFFFFFu;
+                                r[st] = (e < ee[st]) ? g.edge16[e] : pad[st];
+                                r[st + 4] = (e + 4 < ee[st]) ? g.edge16[e + 4] : pad[st];
                             }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) dh[j] = dist[r[j] & 0xFFFFu];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const uint32_t v = r[j] & 0xFFFFu;
-                                if (v == 0xFFFFu) continue;     // padding lane (ids are < 65535)
-                                const uint32_t nd = sat_add(du[j & 3], r[j] >> 16);
-                                if (nd <= g.reject_above && nd < dist[v]) {
+                                const uint32_t nd = du[j & 3] + (r[j] >> 16);
+                                if (nd <= g.reject_above && nd < dh[j]) {
                                     atomicMin(&dist[v], nd);
                                     if (nd < hi_thr) atomicOr(&bm_next[v >> 5], 1u << (v & 31));
                                 }
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
             // Packed in-edges (source | cost << 16), four per 16 bytes; no bitmaps and no
             // atomics: the jump phase needs only the first parent and the ECMP flag.
             // The quad range of the next vertex and its first quad are fetched one iteration ahead.
-            const uint4 kPad = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            const uint4 kPad = make_uint4(0u, 0u, 0u, 0u);   // placeholder, never examined (empty quad range)
             uint32_t qb_n = 0, qe_n = 0;
             uint4 r_n = kPad;
             if (tid < V) {
@@ -569,15 +577,20 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
                     if (v != root && dv != kInf) {
                         for (uint32_t q = qbeg; q < qend; ++q) {
                             if (q != qbeg) r4 = g.iquad[q];
+                            // branch-free: a pad record is (v | 0xFFFF << 16), which can never
+                            // satisfy dist[v] + 65535 == dist[v]
                             const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
+                            uint32_t du[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) du[k] = dist[r[k] & 0xFFFFu];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint32_t u = r[k] & 0xFFFFu, c = r[k] >> 16;
-                                if (u == 0xFFFFu) continue;           // pad record
-                                const uint32_t du = dist[u];
-                                if (sat_add(du, c) != dv) continue;   // covers du == inf (dv is finite)
-                                ++cnt;
-                                if (du < bd || (du == bd && u < bu)) { bd = du; bu = u; }
+                                const uint32_t u = r[k] & 0xFFFFu;
+                                const bool ok = du[k] != kInf && du[k] + (r[k] >> 16) == dv;
+                                const bool better = ok && (du[k] < bd || (du[k] == bd && u < bu));
+                                cnt += ok ? 1u : 0u;
+                                bd = better ? du[k] : bd;
+                                bu = better ? u : bu;
                             }
                         }
                     }

@@ -55,17 +55,17 @@ def find(t):
 
 marks = [("helpers", "__device__ __forceinline__ uint32_t sat_add"),
          ("prolog / job fetch / init", "spf_batch_kernel(const BatchArgs"),
-         ("sssp rounds", "phase 1: SSSP"),
+         ("sssp rounds", "= phase 1: SSSP ="),
          ("bucket scan", "near bucket exhausted"),
          ("h0 / zeroing", "SSSP done:"),
-         ("parents (packed, jump path)", "phase 2: ECMP parents"),
+         ("parents (packed, jump path)", "= phase 2: ECMP parents"),
          ("parents (general)", "in-edge range of the next vertex is fetched one iteration ahead"),
          ("dist write-back", "distances are final"),
-         ("jump: hops", "phase 3J"),
-         ("jump: next hops", "-- next hops."),
-         ("kahn", "phase 3K"),
-         ("write-back", "write-back ===")]
-pos = [(n, find(t)) for n, t in marks] + [("end", len(src) + 1)]
+         ("jump: hops", "= phase 3J: pointer jumping ="),
+         ("jump: next hops", "// -- next hops."),
+         ("kahn", "= phase 3K: Kahn push"),
+         ("write-back", "= write-back =")]
+pos = sorted([(n, find(t)) for n, t in marks], key=lambda x: x[1]) + [("end", len(src) + 1)]
 print("---- by phase")
 for (name, a), (_, b) in zip(pos, pos[1:]):
     s = [0, 0, 0]
