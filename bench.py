@@ -65,6 +65,15 @@ def algorithmic_bytes(csr) -> int:
     return 12 * csr.n_edges + 20 * csr.n_vertices
 
 
+EXCHANGE_TEXT = {
+    "none": "none",
+    "nccl": "one NCCL all-gather of the step's result planes per step, overlapped with the next step's kernel",
+    "p2p": "all-gather of the step's result planes per step by the copy engines over NVLink peer memory "
+           "(hspf_xchg_*: P2P copies + sequence flags, stream memory-op waits, no SM), overlapped with the next "
+           "step's kernel; checked once against an NCCL all-gather before the timed region",
+}
+
+
 def config_dict(n_gpus: int, csr, extra=None):
     c = {
         "workload": "C2: OSPFv2 single-area synthetic LSDB, 10000 routers / 40000 directed p2p links, "
@@ -231,8 +240,24 @@ def run_ours(args):
         offs[k] = tot
         tot += al(sz)
     n_buf = 2 if world > 1 else 1
-    bufs = [torch.empty(tot, dtype=torch.uint8, device=dev) for _ in range(n_buf)]
-    gathered = torch.empty((world, tot), dtype=torch.uint8, device=dev) if world > 1 else None
+    # N>1 exchange: "p2p" = copy-engine all-gather over NVLink peer memory (hspf_xchg_*, no SM
+    # used, overlaps the next step's kernel); "nccl" = one NCCL all-gather per step
+    exchange = args.exchange if world > 1 else "none"
+    xchg = None
+    if exchange == "p2p":
+        try:
+            xchg = shard.PeerExchange(ctx, local_rank, rank, world, tot, n_buf)
+        except RuntimeError as e:       # raised on every rank together
+            if rank == 0:
+                print(f"bench: peer exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+            exchange = "nccl"
+    if xchg is not None:
+        bufs = [shard.raw_cuda_tensor(xchg.slot_ptr(b, rank), tot, dev) for b in range(n_buf)]
+        gathered_p2p = [xchg.buffer_tensor(b, dev) for b in range(n_buf)]
+        gathered = None
+    else:
+        bufs = [torch.empty(tot, dtype=torch.uint8, device=dev) for _ in range(n_buf)]
+        gathered = torch.empty((world, tot), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
@@ -257,7 +282,8 @@ def run_ours(args):
     def plane(buf, k, dtype, shape):
         return buf[offs[k]: offs[k] + sizes[k]].view(dtype).view(shape)
 
-    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if (world > 1 and xchg is None) else None
+    cons_stream = torch.cuda.ExternalStream(xchg.consumer_stream, device=dev) if xchg is not None else None
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -276,6 +302,8 @@ def run_ours(args):
             b = s % n_buf
             if world == 1:
                 flush_l2()
+            elif xchg is not None:
+                xchg.acquire(b)                        # own slot of buffer b has left the device
             elif ag_done[b] is not None:
                 stream.wait_event(ag_done[b])          # buffer b is free again
             e0 = torch.cuda.Event(enable_timing=True)
@@ -283,14 +311,22 @@ def run_ours(args):
             e0.record(stream)
             ctx.run_device(g, js, rss[b], sync=False)
             ek.record(stream)
-            if world > 1:
+            if xchg is not None:
+                xchg.push(b)        # copy engines: slot -> every peer, flags behind the data
+                xchg.wait(b)        # consumer stream: all slots of buffer b have arrived
+                xchg.release(b)     # (no consumer work in the bench) peers may reuse buffer b
+            elif world > 1:
                 comm_stream.wait_event(ek)
                 with torch.cuda.stream(comm_stream):
                     dist.all_gather_into_tensor(gathered.view(-1), bufs[b])
                     ag_done[b] = torch.cuda.Event()
                     ag_done[b].record(comm_stream)
             evs.append((e0, ek))
-        if world > 1:
+        if xchg is not None:
+            done = torch.cuda.Event()
+            done.record(cons_stream)
+            stream.wait_event(done)                    # the timed region ends when every slot is in
+        elif world > 1:
             for e in ag_done:
                 if e is not None:
                     stream.wait_event(e)
@@ -299,6 +335,18 @@ def run_ours(args):
     # warm-up
     run_steps(args.warmup, False)
     barrier()
+    if xchg is not None:
+        # one-time check of the peer exchange against an NCCL all-gather of the same planes
+        xchg.sync()
+        b_last = (args.warmup - 1) % n_buf
+        ref = torch.empty((world, tot), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(ref.view(-1), bufs[b_last])
+        same = torch.tensor([1 if torch.equal(ref, gathered_p2p[b_last][:, :tot]) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) != 1:
+            raise SystemExit("bench: peer exchange delivered planes that differ from the NCCL all-gather")
+        del ref
+        barrier()
     st = plane(bufs[0], "status", torch.int32, (n,))
     assert int(st.abs().sum().item()) == 0, "job_status != 0"
 
@@ -403,7 +451,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": config_dict(world, csr),
+            "config": config_dict(world, csr, {"exchange": EXCHANGE_TEXT[exchange]}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
@@ -415,6 +463,10 @@ def run_ours(args):
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }
         print(json.dumps(line))
+    if xchg is not None:
+        xchg.sync()
+        barrier()          # nobody unmaps while a peer may still copy
+        xchg.close()
     g.free()
     ctx.close()
     if world > 1:
@@ -431,6 +483,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N>1 only: SMs left to the overlapped NCCL all-gather")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 only: how the result planes are all-gathered (p2p falls back to nccl if peer "
+                         "memory cannot be mapped)")
     ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
     args = ap.parse_args()
     global DELTA

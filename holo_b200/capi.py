@@ -85,6 +85,9 @@ EXPORTS = [
     "hspf_graph_upload", "hspf_graph_free", "hspf_run_batch", "hspf_run_batch_async",
     "hspf_sync", "hspf_stream", "hspf_launch_count", "hspf_atom_decode", "hspf_atom_count",
     "hspf_ctx_reserve_sms",
+    "hspf_xchg_create", "hspf_xchg_attach", "hspf_xchg_slot", "hspf_xchg_slot_bytes", "hspf_xchg_acquire",
+    "hspf_xchg_push", "hspf_xchg_wait", "hspf_xchg_release", "hspf_xchg_consumer_stream", "hspf_xchg_sync",
+    "hspf_xchg_last_error", "hspf_xchg_destroy",
 ]
 
 

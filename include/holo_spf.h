@@ -232,6 +232,43 @@ int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms);
  * SM cycles summed over CTAs).  `out` may be NULL. */
 int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]);
 
+/* ---- Multi-GPU result exchange over NVLink peer memory (one process per GPU) --------
+ * SURVEY.md §8e / BASELINE north_star: batches larger than one GPU are sharded by root and
+ * the per-partition SPT results are all-gathered over NVLink.  The reference has no
+ * counterpart (holo-ospf / holo-isis are single-process).
+ *
+ * Every rank owns `n_buffers` x `world` slots of `slot_bytes`; the batch kernel of rank r
+ * writes its result planes into slot r of its own buffer (hspf_xchg_slot), hspf_xchg_push
+ * copies that slot to slot r of the same buffer on every peer with the copy engines, and
+ * sequence flags travel behind the data.  Waiting and acknowledging use stream memory
+ * operations, so no step of the exchange needs an SM and the next batch kernel overlaps it.
+ *
+ * Per step on buffer k (all ranks, in lockstep):
+ *     hspf_xchg_acquire(x, k);            engine stream waits until push(k) two steps ago left
+ *     hspf_run_batch_async(... planes inside hspf_xchg_slot(x, k, rank) ...);
+ *     hspf_xchg_push(x, k);
+ *     hspf_xchg_wait(x, k);               consumer stream: all `world` slots of buffer k are in
+ *     ... consumer work on hspf_xchg_consumer_stream(x) ...
+ *     hspf_xchg_release(x, k);            peers may overwrite buffer k again
+ * Setup: create (returns this rank's IPC handle), exchange the 64-byte handles between the
+ * ranks by any means, attach every peer's handle.  Tear-down: make sure every rank has
+ * synced before any rank destroys its exchange (the allocations are mapped by the peers). */
+#define HSPF_IPC_HANDLE_BYTES 64
+typedef struct hspf_xchg hspf_xchg;
+int hspf_xchg_create(hspf_ctx *ctx, int device, uint32_t rank, uint32_t world, size_t slot_bytes,
+                     uint32_t n_buffers, hspf_xchg **out, uint8_t handle[HSPF_IPC_HANDLE_BYTES]);
+int hspf_xchg_attach(hspf_xchg *x, uint32_t peer_rank, const uint8_t handle[HSPF_IPC_HANDLE_BYTES]);
+void *hspf_xchg_slot(hspf_xchg *x, uint32_t buffer, uint32_t slot);   /* device pointer, local copy */
+size_t hspf_xchg_slot_bytes(const hspf_xchg *x);                      /* slot_bytes rounded up to 256 */
+int hspf_xchg_acquire(hspf_xchg *x, uint32_t buffer);
+int hspf_xchg_push(hspf_xchg *x, uint32_t buffer);
+int hspf_xchg_wait(hspf_xchg *x, uint32_t buffer);
+int hspf_xchg_release(hspf_xchg *x, uint32_t buffer);
+void *hspf_xchg_consumer_stream(hspf_xchg *x);                        /* cudaStream_t */
+int hspf_xchg_sync(hspf_xchg *x);                                     /* host blocks: pushes + consumer done */
+const char *hspf_xchg_last_error(const hspf_xchg *x);
+int hspf_xchg_destroy(hspf_xchg *x);
+
 /* Library build info, e.g. "holo_spf 0.1 sm_100a". */
 const char *hspf_version(void);
 
