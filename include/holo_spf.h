@@ -227,9 +227,11 @@ int hspf_atom_count(const hspf_csr *g, uint32_t root, uint32_t *n_atoms);
 int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms);
 
 /* Debug aid: enable/disable per-phase cycle counters of the batch kernel and read
- * the sums of the last launch (slots: 0 init, 1 SSSP, 2 parents, 3 dist write-back,
- * 4 Kahn, 5 hops write-back, 6/7 Kahn/SSSP round counts, 8-12 SSSP round internals;
- * SM cycles summed over CTAs).  `out` may be NULL. */
+ * the sums of the last launch (SM cycles summed over CTAs).  Slots: 0 init, 1 SSSP,
+ * 2 parents, 3 dist write-back, 4 next hops (jump phase) or Kahn push, 5 hops (jump phase) or
+ * hops write-back, 6 Kahn rounds, 7 SSSP rounds, 8-11 SSSP round internals (expand, barrier,
+ * compaction, barrier), 12 frontier entries, 13-15 jump phase: hop rounds, next-hop rounds,
+ * ECMP sweeps (Kahn path: round internals).  `out` may be NULL. */
 int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]);
 
 /* ---- Multi-GPU result exchange over NVLink peer memory (one process per GPU) --------
