@@ -8,7 +8,7 @@ markers (the library is built with -lineinfo).
   cuobjdump -xelf all holo_b200/lib/libholo_spf.so            # -> hspf_capi.sm_100a.cubin
   nvdisasm -g -c hspf_capi.sm_100a.cubin > dis.txt
   ncu -i gpurun_out/<tag>_full.ncu-rep --page source --csv > src.csv
-  python scripts/ncu_by_line.py dis.txt src.csv [kernel-substring]
+  python scripts/ncu_by_line.py dis.txt src.csv [kernel-substring [spf_kernel.cuh of that build]]
 """
 import collections
 import csv
@@ -18,7 +18,7 @@ from pathlib import Path
 
 dis_path, csv_path = sys.argv[1], sys.argv[2]
 kname = sys.argv[3] if len(sys.argv) > 3 else "spf_batch_kernelItLb1ELb1"
-SRC = Path(__file__).resolve().parent.parent / "holo_b200" / "csrc" / "spf_kernel.cuh"
+SRC = Path(sys.argv[4]) if len(sys.argv) > 4 else Path(__file__).resolve().parent.parent / "holo_b200" / "csrc" / "spf_kernel.cuh"
 
 cur, infunc, seq = None, False, []
 for l in open(dis_path).read().split("\n"):
