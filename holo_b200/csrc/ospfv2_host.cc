@@ -369,6 +369,8 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
         (uint32_t)sizeof(hl_ospfv3_link_lsa), (uint32_t)sizeof(hl_ospfv3_iface), (uint32_t)sizeof(hl_ospfv3_area),
         (uint32_t)sizeof(hl_nexthop6), (uint32_t)sizeof(hl_spt_vertex6), (uint32_t)sizeof(hl_route_net6),
         (uint32_t)sizeof(hl_ospfv3_result),
+        (uint32_t)sizeof(hl_ospfv2_summary_lsa), (uint32_t)sizeof(hl_ospfv2_external_lsa),
+        (uint32_t)sizeof(hl_ospfv2_rib_area), (uint32_t)sizeof(hl_rib_route), (uint32_t)sizeof(hl_ospfv2_rib),
     };
     const uint32_t n = sizeof(v) / sizeof(v[0]);
     if (!out || cap < n) return (int)n;

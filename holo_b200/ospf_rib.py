@@ -1,0 +1,123 @@
+"""OSPFv2 routing-table stages after the per-area SPFs, from Python: ctypes/numpy twins of
+hl_ospfv2_summary_lsa / hl_ospfv2_external_lsa / hl_ospfv2_rib_area / hl_rib_route /
+hl_ospfv2_rib (include/holo_lsdb.h) and the `hspf_ospfv2_update_rib_full` call
+(update_rib_full, holo-ospf/src/route.rs:146-193: inter-area networks and routers, transit
+areas, AS-external routes)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi, ospfv2
+
+PATH_INTRA, PATH_INTER, PATH_TYPE1, PATH_TYPE2 = 0, 1, 2, 3
+PATH_NAMES = {PATH_INTRA: "intra-area", PATH_INTER: "inter-area", PATH_TYPE1: "external-1", PATH_TYPE2: "external-2"}
+LSA_INFINITY = 0x00FFFFFF
+
+SUMMARY_LSA_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("mask", "<u4"), ("metric", "<u4"),
+                           ("lsa_type", "u1"), ("maxage", "u1"), ("_pad", "u1", (2,))], align=True)
+EXTERNAL_LSA_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("mask", "<u4"), ("metric", "<u4"),
+                            ("fwd_addr", "<u4"), ("tag", "<u4"), ("e_bit", "u1"), ("maxage", "u1"),
+                            ("_pad", "u1", (2,))], align=True)
+RIB_ROUTE_DT = np.dtype([("prefix", "<u4"), ("mask", "<u4"), ("metric", "<u4"), ("type2_metric", "<u4"),
+                         ("tag", "<u4"), ("area_id", "<u4"), ("path_type", "u1"), ("flags", "u1"), ("has_area", "u1"),
+                         ("has_type2", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+
+
+class RibAreaStruct(C.Structure):
+    _fields_ = [
+        ("area_id", C.c_uint32), ("n_summaries", C.c_uint32),
+        ("spf", C.c_void_p), ("ifaces", C.c_void_p), ("summaries", C.c_void_p),
+        ("n_ifaces", C.c_uint32), ("active", C.c_uint8), ("_pad", C.c_uint8 * 3),
+    ]
+
+
+class RibStruct(C.Structure):
+    _fields_ = [
+        ("routes_cap", C.c_uint32), ("n_routes", C.c_uint32), ("routes", C.c_void_p),
+        ("nexthops_cap", C.c_uint32), ("n_nexthops", C.c_uint32), ("nexthops", C.c_void_p),
+    ]
+
+
+# appended to hspf_abi_sizes() after the OSPFv3 block
+ABI_SIZES = [SUMMARY_LSA_DT.itemsize, EXTERNAL_LSA_DT.itemsize, C.sizeof(RibAreaStruct), RIB_ROUTE_DT.itemsize,
+             C.sizeof(RibStruct)]
+
+
+@dataclass
+class RibArea:
+    """One attached area: the result of run_area, the area's interfaces and Summary-LSAs."""
+    area_id: int
+    result: ospfv2.Ospfv2Result
+    ifaces: np.ndarray
+    summaries: np.ndarray
+    active: bool = True
+
+
+@dataclass
+class Rib:
+    routes: np.ndarray
+    nexthops: np.ndarray
+    rc: int = 0
+
+    def nh(self, rec):
+        return [tuple(int(x[k]) for k in ("iface", "has_addr", "addr", "has_nbr", "nbr_router_id", "has_label", "sr_label"))
+                for x in self.nexthops[int(rec["nh_off"]): int(rec["nh_off"]) + int(rec["n_nh"])]]
+
+
+def _result_struct(res: ospfv2.Ospfv2Result, keep: list) -> ospfv2.ResultStruct:
+    r = ospfv2.ResultStruct()
+    for name, dt in (("vertices", ospfv2.SPT_VERTEX_DT), ("routers", ospfv2.ROUTE_RTR_DT),
+                     ("routes", ospfv2.ROUTE_NET_DT), ("nexthops", ospfv2.NEXTHOP_DT)):
+        a = np.ascontiguousarray(getattr(res, name), dtype=dt)
+        keep.append(a)
+        setattr(r, name + "_cap", len(a))
+        setattr(r, "n_" + name, len(a))
+        setattr(r, name, a.ctypes.data if len(a) else None)
+    r.transit_capability = int(res.transit_capability)
+    r.root_found = int(res.root_found)
+    return r
+
+
+def call_update_rib_full(fn, router_id: int, max_paths: int, areas: list, externals=None) -> Rib:
+    """`fn` = hspf_ospfv2_update_rib_full of the product library or the oracle's twin."""
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(RibAreaStruct), C.c_uint32, C.c_void_p, C.c_uint32,
+                   C.POINTER(RibStruct)]
+    keep = []
+    arr = (RibAreaStruct * max(len(areas), 1))()
+    for i, a in enumerate(areas):
+        rs = _result_struct(a.result, keep)
+        keep.append(rs)
+        ifs = np.ascontiguousarray(a.ifaces, dtype=ospfv2.IFACE_DT)
+        sm = np.ascontiguousarray(a.summaries, dtype=SUMMARY_LSA_DT)
+        keep += [ifs, sm]
+        arr[i].area_id, arr[i].n_summaries = a.area_id, len(sm)
+        arr[i].spf = C.addressof(rs)
+        arr[i].ifaces = ifs.ctypes.data if len(ifs) else None
+        arr[i].summaries = sm.ctypes.data if len(sm) else None
+        arr[i].n_ifaces, arr[i].active = len(ifs), int(a.active)
+    ext = np.ascontiguousarray(externals if externals is not None else np.zeros(0, EXTERNAL_LSA_DT), dtype=EXTERNAL_LSA_DT)
+    caps = [256, 1024]
+    for _ in range(3):
+        routes = np.zeros(caps[0], RIB_ROUTE_DT)
+        nhs = np.zeros(caps[1], ospfv2.NEXTHOP_DT)
+        r = RibStruct()
+        r.routes_cap, r.routes = caps[0], routes.ctypes.data
+        r.nexthops_cap, r.nexthops = caps[1], nhs.ctypes.data
+        rc = fn(router_id, max_paths, arr, len(areas), ext.ctypes.data if len(ext) else None, len(ext), C.byref(r))
+        if rc == capi.HSPF_E_NOMEM:
+            caps = [max(caps[0], r.n_routes), max(caps[1], r.n_nexthops)]
+            continue
+        break
+    return Rib(routes[: r.n_routes].copy(), nhs[: r.n_nexthops].copy(), rc)
+
+
+def update_rib_full(router_id: int, max_paths: int, areas: list, externals=None) -> Rib:
+    """The product's host stage (libholo_spf.so); needs no device."""
+    lib = capi.load_library()
+    rib = call_update_rib_full(lib.hspf_ospfv2_update_rib_full, router_id, max_paths, areas, externals)
+    if rib.rc != capi.HSPF_OK:
+        raise capi.HspfError(rib.rc, "hspf_ospfv2_update_rib_full failed")
+    return rib

@@ -84,8 +84,8 @@ ABI_SIZES = [
 
 
 def abi_sizes_expected():
-    from . import isis, ospfv3
-    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES
+    from . import isis, ospf_rib, ospfv3
+    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES
 
 
 def abi_sizes_from_library():

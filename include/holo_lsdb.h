@@ -220,6 +220,77 @@ typedef struct hl_ospfv2_result {
 } hl_ospfv2_result;
 
 
+/* ------------------------------------------------ OSPFv2 full routing table -- */
+/* Inputs and output of update_rib_full (holo-ospf/src/route.rs:146-193): the stages that
+ * follow the per-area SPF — inter-area networks / routers from Summary-LSAs
+ * (route.rs:449-533, 653-714), transit areas (route.rs:535-650) and AS-external routes
+ * (route.rs:717-827). */
+#define HL_LSA_INFINITY 0x00FFFFFFu        /* lsdb.rs:46 */
+/* OspfRouteType (holo-utils/src/southbound.rs:86-94), in decreasing preference */
+#define HL_PATH_INTRA_AREA      0u
+#define HL_PATH_INTER_AREA      1u
+#define HL_PATH_TYPE1_EXTERNAL  2u
+#define HL_PATH_TYPE2_EXTERNAL  3u
+
+/* Type-3 / type-4 Summary-LSA (ospfv2/spf.rs:539-589), LSDB (LsaKey) order per area. */
+typedef struct hl_ospfv2_summary_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;       /* network address (type 3) or ASBR router id (type 4) */
+    uint32_t mask;         /* type 3                                               */
+    uint32_t metric;
+    uint8_t  lsa_type;     /* 3 or 4                                               */
+    uint8_t  maxage;
+    uint8_t  _pad[2];
+} hl_ospfv2_summary_lsa;
+
+/* AS-external-LSA (ospfv2/spf.rs:591-615), instance LSDB order. */
+typedef struct hl_ospfv2_external_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t mask;
+    uint32_t metric;
+    uint32_t fwd_addr;
+    uint32_t tag;
+    uint8_t  e_bit;        /* type-2 external metric                               */
+    uint8_t  maxage;
+    uint8_t  _pad[2];
+} hl_ospfv2_external_lsa;
+
+/* One attached area, in the order the instance iterates its areas. */
+typedef struct hl_ospfv2_rib_area {
+    uint32_t area_id;
+    uint32_t n_summaries;
+    const hl_ospfv2_result      *spf;        /* hspf_ospfv2_run_area output for this area       */
+    const hl_ospf_iface         *ifaces;     /* the area's interfaces (next hops index them)     */
+    const hl_ospfv2_summary_lsa *summaries;
+    uint32_t n_ifaces;
+    uint8_t  active;       /* Area::is_active (area.rs:150-156): an interface is not Down         */
+    uint8_t  _pad[3];
+} hl_ospfv2_rib_area;
+
+/* Route of the merged table, in prefix order.  Next hops are hl_nexthop with `iface` = the
+ * interface's sort_key (unique per instance, hl_ospf_iface), in NexthopKey order. */
+typedef struct hl_rib_route {
+    uint32_t prefix;
+    uint32_t mask;
+    uint32_t metric;
+    uint32_t type2_metric;
+    uint32_t tag;
+    uint32_t area_id;
+    uint8_t  path_type;    /* HL_PATH_*                                            */
+    uint8_t  flags;        /* HL_ROUTE_CONNECTED                                   */
+    uint8_t  has_area;
+    uint8_t  has_type2;
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_rib_route;
+
+typedef struct hl_ospfv2_rib {
+    uint32_t routes_cap,   n_routes;     hl_rib_route *routes;
+    uint32_t nexthops_cap, n_nexthops;   hl_nexthop   *nexthops;
+} hl_ospfv2_rib;
+
+
 /* ------------------------------------------------------------------ OSPFv3 -- */
 
 /* Router-LSA link (holo-ospf/src/ospfv3/packet/lsa.rs LsaRouterLink); link_type uses

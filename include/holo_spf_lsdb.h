@@ -6,6 +6,9 @@
  *                               holo-ospf/src/spf.rs:587-729, route.rs:343-446,
  *                               sr.rs:29-77 (as called from compute_spf,
  *                               spf.rs:540-545)
+ *   hspf_ospfv2_update_rib_full <-> the stages of update_rib_full() after the SPFs:
+ *                               inter-area networks/routers, transit areas, externals
+ *                               (route.rs:146-193, 449-827, 895-971); host only
  *   hspf_ospfv2_flatten    <->  the LSDB walk of vertex_lsa_find/vertex_lsa_links
  *                               (ospfv2/spf.rs:356-461) done once, for callers
  *                               that batch many roots / what-if jobs through
@@ -56,6 +59,20 @@ uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t 
  * path), or another HSPF_E_*.
  */
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
+
+/*
+ * The stages of update_rib_full that follow the per-area SPFs (holo-ospf/src/route.rs:146-193):
+ * merges the intra-area routes of the attached areas (route_update / route_compare,
+ * route.rs:895-971), adds inter-area network routes and inter-area router entries from the
+ * Summary-LSAs (only the backbone's when more than one area is active), re-examines transit
+ * areas, and adds AS-external routes through the best ASBR entry.  Pure host table joins over
+ * the results of hspf_ospfv2_run_area; no device work.  A prefix that is intra-area in two
+ * areas is merged by route_compare; the transit-network overwrite rule (route.rs:388-398)
+ * has already been applied inside each area.  Returns HSPF_OK or HSPF_E_NOMEM (counts filled in).
+ */
+int hspf_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv2_rib_area *areas,
+                                uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,
+                                hl_ospfv2_rib *out);
 
 /* ---- OSPFv3 ----------------------------------------------------------------
  *   hspf_ospfv3_run_area  <->  run_area<Ospfv3>() + update_rib_intra_area()

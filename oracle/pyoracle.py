@@ -93,6 +93,12 @@ def ospfv2_run_area(area):
     return ospfv2._call_run_area(L.oracle_ospfv2_run_area, area)
 
 
+def ospfv2_update_rib_full(router_id: int, max_paths: int, areas: list, externals=None):
+    """Reference-faithful update_rib_full stages after the per-area SPFs (oracle/rib_ospfv2.cc)."""
+    from holo_b200 import ospf_rib
+    return ospf_rib.call_update_rib_full(lib().oracle_ospfv2_update_rib_full, router_id, max_paths, areas, externals)
+
+
 def isis_compute_spt(level, root_system_id: int):
     """Reference-faithful compute_spt (local = false) over an IS-IS level image."""
     from holo_b200 import isis

@@ -60,7 +60,8 @@ def extract_ospfv2(ref: Path):
             snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"),
                     "ifindex": ifindex_map(rt / "events.jsonl"), "areas": [], "local_rib": []}
             for a in o.get("areas", {}).get("area", []):
-                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "interfaces": []}
+                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "summary_lsas": [],
+                        "interfaces": []}
                 for t in a.get("database", {}).get("area-scope-lsa-type", []):
                     for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
                         h = l["ospfv2"]["header"]
@@ -69,12 +70,19 @@ def extract_ospfv2(ref: Path):
                             r = b["router"]
                             flags = 0
                             for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
-                                flags |= RTR_BITS.get(bit, 0)
+                                flags |= RTR_BITS.get(bit.split(":")[-1], 0)    # some dumps prefix "ietf-ospf:"
                             links = [[LINK_TYPES[x["type"]], x["link-id"], x["link-data"],
                                       x["topologies"]["topology"][0]["metric"]]
                                      for x in r.get("links", {}).get("link", [])]
                             area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
                                                         "links": links})
+                        elif t["lsa-type"] in (3, 4) and "summary" in b:
+                            # Summary-LSAs (type 3 network / type 4 ASBR), inputs of the inter-area stage
+                            # (holo-ospf/src/ospfv2/spf.rs:539-589)
+                            sm = b["summary"]
+                            area["summary_lsas"].append({
+                                "type": t["lsa-type"], "adv": h["adv-router"], "id": h["lsa-id"],
+                                "mask": sm["network-mask"], "metric": sm["topologies"]["topology"][0]["metric"]})
                         elif t["lsa-type"] == 2 and "network" in b:
                             n = b["network"]
                             area["network_lsas"].append({
@@ -94,6 +102,18 @@ def extract_ospfv2(ref: Path):
                     area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
                                                "state": v.get("state"), "cfg_type": "virtual-link", "neighbors": nb})
                 snap["areas"].append(area)
+            # AS-external LSAs (type 5), inputs of update_rib_external (ospfv2/spf.rs:591-615)
+            snap["external_lsas"] = []
+            for t in o.get("database", {}).get("as-scope-lsa-type", []):
+                for l in t.get("as-scope-lsas", {}).get("as-scope-lsa", []):
+                    h = l["ospfv2"]["header"]
+                    ex = l["ospfv2"].get("body", {}).get("external")
+                    if t["lsa-type"] == 5 and ex:
+                        tp = ex["topologies"]["topology"][0]
+                        snap["external_lsas"].append({
+                            "adv": h["adv-router"], "id": h["lsa-id"], "mask": ex["network-mask"],
+                            "e_bit": "flags" in tp and "E" in str(tp.get("flags")), "metric": tp["metric"],
+                            "fwd": tp.get("forwarding-address", "0.0.0.0"), "tag": tp.get("external-route-tag", 0)})
             for r in o.get("local-rib", {}).get("route", []):
                 nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
                        for n in r.get("next-hops", {}).get("next-hop", [])]
@@ -129,7 +149,7 @@ def extract_ospfv3(ref: Path):
                             r = b["router"]
                             flags = 0
                             for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
-                                flags |= V3_BITS.get(bit, 0)
+                                flags |= V3_BITS.get(bit.split(":")[-1], 0)
                             opts = r.get("lsa-options", {}).get("lsa-options", [])
                             links = [[V3_LINK_TYPES[x["type"]], x["interface-id"], x["neighbor-interface-id"],
                                       x["neighbor-router-id"], x["metric"]] for x in r.get("links", {}).get("link", [])]

@@ -25,7 +25,14 @@ def load_ospfv2():
     return json.loads((GOLDEN / "ospfv2.json").read_text())
 
 
-def ospfv2_area_image(snap, area):
+def global_sort_keys(snap):
+    """One sort key per interface of the instance (hl_ospf_iface.sort_key must be unique per
+    instance for the multi-area table): rank in byte-wise name order over all areas."""
+    names = sorted({i["name"] for a in snap["areas"] for i in a["interfaces"]}, key=lambda n: n.encode())
+    return {n: k + 1 for k, n in enumerate(names)}
+
+
+def ospfv2_area_image(snap, area, sort_keys=None):
     """hl_ospfv2_area for one area of a golden snapshot."""
     rl = sorted(area["router_lsas"], key=lambda l: (ip(l["adv"]), ip(l["id"])))
     nlinks = sum(len(l["links"]) for l in rl)
@@ -60,7 +67,8 @@ def ospfv2_area_image(snap, area):
         else:
             ty = ospfv2.IF_BROADCAST
         nb = sorted((ip(r), ip(a)) for r, a in f["neighbors"])
-        ifaces[i] = (snap["ifindex"].get(f["name"], 0), i + 1, ty, (0, 0, 0), 0, 0, len(nbrs), len(nb))
+        sk = sort_keys[f["name"]] if sort_keys else i + 1
+        ifaces[i] = (snap["ifindex"].get(f["name"], 0), sk, ty, (0, 0, 0), 0, 0, len(nbrs), len(nb))
         nbrs += nb
         names.append(f["name"])
     img = ospfv2.Ospfv2Area(router_id=ip(snap["router_id"]), area_id=ip(area["area_id"]))
@@ -93,6 +101,52 @@ def merge_area_routes(dicts):
             elif m == rib[k][0]:
                 rib[k] = (m, sorted(set(rib[k][1]) | set(nh), key=lambda x: (x[0], x[1] or "")))
     return rib
+
+
+def ospfv2_summaries(area):
+    """hl_ospfv2_summary_lsa[] of one area of a golden snapshot, LsaKey order (type, adv_rtr, lsa_id)."""
+    from holo_b200 import ospf_rib
+    ls = sorted(area.get("summary_lsas", []), key=lambda l: (l["type"], ip(l["adv"]), ip(l["id"])))
+    out = np.zeros(len(ls), ospf_rib.SUMMARY_LSA_DT)
+    for i, l in enumerate(ls):
+        out[i] = (ip(l["adv"]), ip(l["id"]), ip(l["mask"]), l["metric"], l["type"], 0, (0, 0))
+    return out
+
+
+def ospfv2_full_rib(snap, run_area, update_rib_full):
+    """The whole OSPFv2 routing table of a golden snapshot: `run_area(img)` per attached area, then
+    `update_rib_full(router_id, max_paths, [RibArea...])`.  Returns {prefix: (metric, type, [(ifname, addr)])}
+    so that it compares directly with `golden_rib`."""
+    from holo_b200 import ospf_rib
+    keys = global_sort_keys(snap)
+    key_name = {v: k for k, v in keys.items()}
+    areas = []
+    for area in snap["areas"]:
+        img = ospfv2_area_image(snap, area, keys)
+        res = run_area(img)
+        assert res.rc == 0
+        if not res.root_found:
+            continue
+        active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+        areas.append(ospf_rib.RibArea(ip(area["area_id"]), res, img.ifaces, ospfv2_summaries(area), active))
+    rib = update_rib_full(ip(snap["router_id"]), 16, areas)
+    assert rib.rc == 0
+    out = {}
+    for r in rib.routes:
+        plen = bin(int(r["mask"])).count("1")
+        nh = sorted(((key_name.get(i, "?"), ipstr(a) if ha else None) for (i, ha, a, _hn, _n, _hl, _l) in rib.nh(r)),
+                    key=lambda x: (x[0] or "", x[1] or ""))
+        out[f"{ipstr(r['prefix'])}/{plen}"] = (int(r["metric"]), ospf_rib.PATH_NAMES[int(r["path_type"])], nh)
+    return out
+
+
+def golden_rib(snap):
+    """Every route of the reference's local-rib: {prefix: (metric, route-type, [(ifname, addr)])}."""
+    out = {}
+    for r in snap["local_rib"]:
+        nh = sorted(((n[0], n[1]) for n in r["nexthops"]), key=lambda x: (x[0] or "", x[1] or ""))
+        out[r["prefix"]] = (r["metric"], r["type"], nh)
+    return out
 
 
 def golden_intra(snap):

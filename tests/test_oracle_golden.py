@@ -46,6 +46,20 @@ def test_ospfv2_oracle_reproduces_reference_local_rib(snap):
     assert n_checked > 0
 
 
+@pytest.mark.parametrize("snap", SNAPS, ids=_ids())
+def test_ospfv2_oracle_reproduces_the_whole_reference_local_rib(snap):
+    """run_area per attached area + the update_rib_full stages (oracle/rib_ospfv2.cc): every
+    route of the reference's local-rib — intra-area and inter-area, with the next hops that
+    virtual-link end points obtain from their transit area — and nothing else."""
+    got = gu.ospfv2_full_rib(snap, pyoracle.ospfv2_run_area, pyoracle.ospfv2_update_rib_full)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want), (sorted(set(got) - set(want)), sorted(set(want) - set(got)))
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g, (metric, rtype))
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
+
+
 SNAPS_V3 = gu.load_ospfv3()
 
 

@@ -1,0 +1,128 @@
+"""Host stage hspf_ospfv2_update_rib_full (holo_b200/csrc/ospf_rib_host.cc) on the CPU:
+(1) fed with the per-area results of the oracle's run_area it must reproduce the whole
+local-rib of every golden OSPFv2 snapshot of the reference, byte-identical to the oracle's
+restatement (oracle/rib_ospfv2.cc); (2) on random multi-area tables with type-3/4/5 LSAs,
+ECMP and max_paths truncation it must agree with the restatement record for record."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from holo_b200 import ospf_rib, ospfv2
+from oracle import pyoracle
+
+SNAPS = gu.load_ospfv2()
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_product_rib_stage_reproduces_reference_local_rib(snap):
+    got = gu.ospfv2_full_rib(snap, pyoracle.ospfv2_run_area, ospf_rib.update_rib_full)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want)
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g)
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
+
+
+def random_instance(seed: int):
+    """Fabricated per-area SPF results (router tables with ABR/ASBR flags, intra-area routes,
+    ECMP next hops over globally unique interface sort keys) + summary and external LSAs."""
+    rng = np.random.default_rng(seed)
+    n_areas = int(rng.integers(1, 4))
+    area_ids = [0] + sorted(int(x) for x in rng.choice(np.arange(1, 9), n_areas - 1, replace=False))
+    rng.shuffle(area_ids)
+    router_id = 0x01010101
+    pool_prefixes = [(0x0A000000 + (i << 8), 0xFFFFFF00) for i in range(12)] + [(0x0A0A0A00 + i, 0xFFFFFFFF) for i in range(6)] + [(0, 0)]
+    rtr_ids = [0x02020200 + i for i in range(10)]
+    areas, sk = [], 1
+    for aid in area_ids:
+        n_if = int(rng.integers(1, 5))
+        ifaces = np.zeros(n_if, ospfv2.IFACE_DT)
+        for i in range(n_if):
+            ifaces[i] = (100 + sk, sk, ospfv2.IF_P2P, (0, 0, 0), 0, 0, 0, 0)
+            sk += 1
+        nhs = []
+
+        def hops():
+            k = int(rng.integers(0, 4))
+            off = len(nhs)
+            seen = set()
+            for _ in range(k):
+                i = int(rng.integers(0, n_if))
+                ha = int(rng.integers(0, 2))
+                addr = int(rng.integers(1, 5)) if ha else 0
+                if (i, ha, addr) in seen:
+                    continue
+                seen.add((i, ha, addr))
+                nhs.append((i, addr, int(rng.integers(1, 99)), 0, ha, 1, 0, 0))
+            sub = sorted(nhs[off:], key=lambda x: (ifaces[x[0]]["sort_key"], x[4], x[1]))
+            nhs[off:] = sub
+            return off, len(nhs) - off
+
+        routers = []
+        for rid in sorted(rng.choice(rtr_ids, int(rng.integers(1, 7)), replace=False)):
+            off, n = hops()
+            routers.append((int(rid), int(rng.integers(1, 60)), int(rng.integers(0, 4)), 2, (0, 0), off, n))
+        routes = []
+        for pi in sorted(rng.choice(len(pool_prefixes) - 1, int(rng.integers(1, 8)), replace=False)):
+            p, m = pool_prefixes[int(pi)]
+            off, n = hops()
+            routes.append((p, m, int(rng.integers(0, 40)), int(rng.integers(0, 2)), 1, 0, 0, 0, 0, 0, 0, 0, (0, 0), 0, off, n))
+        res = ospfv2.Ospfv2Result(np.zeros(0, ospfv2.SPT_VERTEX_DT), np.asarray(routers, ospfv2.ROUTE_RTR_DT),
+                                  np.asarray(routes, ospfv2.ROUTE_NET_DT), np.asarray(nhs, ospfv2.NEXTHOP_DT)
+                                  if nhs else np.zeros(0, ospfv2.NEXTHOP_DT), bool(rng.integers(0, 2)), True)
+        sums = []
+        for _ in range(int(rng.integers(0, 14))):
+            ty = 3 if rng.random() < 0.7 else 4
+            adv = int(rng.choice(rtr_ids + [router_id]))
+            if ty == 3:
+                p, m = pool_prefixes[int(rng.integers(0, len(pool_prefixes)))]
+                if rng.random() < 0.1:
+                    p |= 1                                     # host bits set: kept unmasked
+            else:
+                p, m = int(rng.choice(rtr_ids)), 0
+            metric = int(rng.choice([1, 5, 10, 10, 20, ospf_rib.LSA_INFINITY]))
+            sums.append((adv, p, m, metric, ty, int(rng.random() < 0.1), (0, 0)))
+        sums.sort(key=lambda x: (x[4], x[0], x[1]))
+        areas.append(ospf_rib.RibArea(aid, res, ifaces, np.asarray(sums, ospf_rib.SUMMARY_LSA_DT)
+                                      if sums else np.zeros(0, ospf_rib.SUMMARY_LSA_DT), bool(rng.random() < 0.8)))
+    ext = []
+    for _ in range(int(rng.integers(0, 10))):
+        p, m = pool_prefixes[int(rng.integers(0, len(pool_prefixes)))]
+        ext.append((int(rng.choice(rtr_ids)), p, m, int(rng.choice([1, 10, 20, ospf_rib.LSA_INFINITY])), 0,
+                    int(rng.integers(0, 5)), int(rng.integers(0, 2)), int(rng.random() < 0.1), (0, 0)))
+    ext.sort(key=lambda x: (x[0], x[1]))
+    ext = np.asarray(ext, ospf_rib.EXTERNAL_LSA_DT) if ext else np.zeros(0, ospf_rib.EXTERNAL_LSA_DT)
+    return router_id, int(rng.choice([1, 2, 16])), areas, ext
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_product_rib_stage_matches_restatement_on_random_tables(seed):
+    router_id, max_paths, areas, ext = random_instance(seed)
+    a = ospf_rib.update_rib_full(router_id, max_paths, areas, ext)
+    b = pyoracle.ospfv2_update_rib_full(router_id, max_paths, areas, ext)
+    assert b.rc == 0
+    assert a.routes.tobytes() == b.routes.tobytes(), (a.routes, b.routes)
+    assert a.nexthops.tobytes() == b.nexthops.tobytes()
+
+
+def test_random_tables_exercise_every_stage():
+    kinds = set()
+    n_multi = 0
+    for seed in range(200):
+        router_id, max_paths, areas, ext = random_instance(seed)
+        rib = ospf_rib.update_rib_full(router_id, max_paths, areas, ext)
+        kinds |= set(int(p) for p in rib.routes["path_type"])
+        n_multi += int((rib.routes["n_nh"] > 1).sum())
+    assert kinds == {0, 1, 2, 3} and n_multi > 20
+
+
+def test_rib_stage_argument_checks():
+    import ctypes as C
+    from holo_b200 import capi
+    lib = capi.load_library()
+    fn = lib.hspf_ospfv2_update_rib_full
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    assert fn(1, 16, None, 1, None, 0, None) == capi.HSPF_E_INVAL
+    r = ospf_rib.RibStruct()
+    assert fn(1, 16, None, 0, None, 0, C.byref(r)) == capi.HSPF_OK and r.n_routes == 0

@@ -106,3 +106,19 @@ def test_reference_golden_local_rib(ctx, snap):
         if has_vlink and not got[prefix][1]:
             continue   # virtual-link next hops: SURVEY §8f f1 (see test_oracle_golden.py)
         assert norm(got[prefix][1]) == norm(nh)
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_reference_golden_whole_local_rib(ctx, snap):
+    """LSDB -> full routing table through the product only: hspf_ospfv2_run_area on the GPU per
+    attached area, then hspf_ospfv2_update_rib_full (inter-area, transit areas, externals):
+    every route of the reference's local-rib, and nothing else (the same helper runs on the
+    CPU with the oracle in tests/test_ospf_rib.py and tests/test_oracle_golden.py)."""
+    from holo_b200 import ospf_rib
+    got = gu.ospfv2_full_rib(snap, lambda img: ospfv2.run_area(ctx, img), ospf_rib.update_rib_full)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want)
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g)
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
