@@ -19,14 +19,21 @@
 //               relaxation created the final candidate entry in the reference
 //               (spf.rs:700-703); marks every ECMP-DAG edge and every first-parent
 //               edge in two E-bit shared-memory bitmaps;
-//   3. Kahn   : topological push over the marked DAG edges only; hops follow the
-//               first-parent edge (spf.rs:675-678), next-hop atom sets are OR-ed
-//               over all ECMP parents (spf.rs:747-766 / holo-isis spf.rs:678-702).
+//   3. hops and next-hop atom sets (hops follow the first-parent edge, spf.rs:675-678; the
+//               sets are OR-ed over all ECMP parents, spf.rs:747-766 / holo-isis spf.rs:678-702):
+//      3J jump : common batch shape (kFast, packed CSR twins, <= 16 first-hop atoms): pointer
+//               doubling over the first-parent tree, ECMP vertices as jump terminals resolved
+//               by monotone sweeps — O(log depth) regular rounds;
+//      3K Kahn : every other case: topological push over the marked DAG edges only, one round
+//               per DAG level.
 //
 // Shared-memory plan (byte offsets computed on the host, see make_layout):
-//   SSSP   : dist[V] u32 | qa[V] | qb[V] | pend[V] u16 | bm0 | bm1
-//   parents: dist (read) | dagbit,fpbit -> qa region | hops[V] u16 -> qb region | pend
-//   Kahn   : kq0,kq1 -> dist region (dist is written back to HBM first) | bitmaps | hops | pend
+//   SSSP   : dist[V] u32 | qa[V] | qb[V] | pend[V] u16 (fast path: row16[V], kept across jobs) | bm0 | bm1
+//   parents: dist (read) | 3K: dagbit,fpbit -> qa region, pend = in-degrees | 3J: first_parent u16 -> qb region,
+//            bm0 = hops-0 heads of root edges, bm1 = ECMP vertices
+//   3J     : jump words (ancestor:16 | aggregate:16) -> dist region (dist is written back to HBM first),
+//            ECMP vertex list -> qb region
+//   3K     : kq0,kq1 -> dist region | bitmaps | hops[V] u16 -> qb region | pend
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
