@@ -1,16 +1,19 @@
-// OSPFv2 routing table after the per-area SPFs: hspf_ospfv2_update_rib_full
-// (include/holo_spf_lsdb.h).  Host-side table joins over the results of
-// hspf_ospfv2_run_area; replaces, for the stages after the SPT,
+// OSPF routing table after the per-area SPFs: hspf_ospfv2_update_rib_full /
+// hspf_ospfv3_update_rib_full (include/holo_spf_lsdb.h).  Host-side table joins over the
+// results of hspf_ospfv{2,3}_run_area; replaces, for the stages after the SPT,
 //   update_rib_full                  holo-ospf/src/route.rs:146-193
-//   update_rib_inter_area_networks   route.rs:449-533   (type-3 Summary-LSAs)
-//   update_rib_inter_area_routers    route.rs:653-714   (type-4 Summary-LSAs)
+//   update_rib_inter_area_networks   route.rs:449-533   (type-3 Summary / Inter-Area-Prefix LSAs)
+//   update_rib_inter_area_routers    route.rs:653-714   (type-4 Summary / Inter-Area-Router LSAs)
 //   update_rib_transit_area          route.rs:535-650   (RFC 2328 16.3, virtual links)
-//   update_rib_external              route.rs:717-827   (type-5 LSAs)
+//   update_rib_external              route.rs:717-827   (AS-external LSAs)
 //   route_update / route_compare     route.rs:895-971
-// Routes live in one flat vector with a hash index on (address, mask); next-hop sets are
-// small vectors kept sorted by NexthopKey (interface sort key, then address with None first),
-// merged like BTreeMap::extend (a later entry with the same key replaces the earlier one).
+// The reference is generic over the OSPF version; so is this file: one template, two small
+// trait structs for the address / record types.  Routes live in one flat vector with a hash
+// index on (address bytes, prefix length); next-hop sets are small vectors kept sorted by
+// NexthopKey (interface sort key, then address with None first), merged like
+// BTreeMap::extend (a later entry with the same key replaces the earlier one).
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -23,19 +26,33 @@
 
 namespace {
 
-struct Hop {
-    uint64_t ka;         // NexthopKey, major part: sort_key << 1 | has_addr   (None sorts first)
-    uint32_t kb;         // minor part: the address
-    hl_nexthop nh;
+// ---- prefix key: 16 address bytes (IPv4 in the first four, network byte order) + length ----
+struct PKey {
+    std::array<uint8_t, 17> b{};
+    bool operator==(const PKey &o) const { return b == o.b; }
+    bool operator<(const PKey &o) const { return b < o.b; }   // address, then prefix length
 };
-using Hops = std::vector<Hop>;   // ascending key, unique
+struct PKeyHash {
+    size_t operator()(const PKey &k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (uint8_t x : k.b) { h ^= x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
 
-inline bool key_less(const Hop &p, const Hop &q) { return p.ka != q.ka ? p.ka < q.ka : p.kb < q.kb; }
-inline bool key_same(const Hop &p, const Hop &q) { return p.ka == q.ka && p.kb == q.kb; }
+template <class Nh>
+struct HopT {
+    uint64_t ka;                      // NexthopKey, major: sort_key << 1 | has_addr (None first)
+    std::array<uint8_t, 16> kb;       // minor: the address
+    Nh nh;
+};
+template <class Nh> bool key_less(const HopT<Nh> &p, const HopT<Nh> &q) { return p.ka != q.ka ? p.ka < q.ka : p.kb < q.kb; }
+template <class Nh> bool key_same(const HopT<Nh> &p, const HopT<Nh> &q) { return p.ka == q.ka && p.kb == q.kb; }
 
 // dst <- dst extended with src (same key: src wins)
-void merge_hops(Hops &dst, const Hops &src) {
-    Hops out;
+template <class Nh>
+void merge_hops(std::vector<HopT<Nh>> &dst, const std::vector<HopT<Nh>> &src) {
+    std::vector<HopT<Nh>> out;
     out.reserve(dst.size() + src.size());
     size_t i = 0, j = 0;
     while (i < dst.size() || j < src.size()) {
@@ -46,49 +63,112 @@ void merge_hops(Hops &dst, const Hops &src) {
     dst.swap(out);
 }
 
-void clip(Hops &h, uint32_t max_paths) {
-    if (h.size() > max_paths) h.resize(max_paths);
-}
-
-struct Net {
-    uint32_t prefix, mask;
-    uint32_t metric, type2, tag, area;
-    uint8_t path, flags;
-    bool has_area, has_type2;
-    Hops hops;
-};
-
-struct Rtr {
-    uint32_t area, metric;
-    uint8_t path, flags;
-    Hops hops;
-};
-
-// negative: a preferred over b
-int prefer(const Net &a, const Net &b) {
-    if (a.path != b.path) return a.path < b.path ? -1 : 1;
-    if (a.path == HL_PATH_TYPE2_EXTERNAL) {
-        if (a.has_type2 != b.has_type2) return a.has_type2 ? 1 : -1;     // None < Some
-        if (a.type2 != b.type2) return a.type2 < b.type2 ? -1 : 1;
+// ---- version traits --------------------------------------------------------------------------
+struct V2 {
+    using Area = hl_ospfv2_rib_area;
+    using Sum = hl_ospfv2_summary_lsa;
+    using Ext = hl_ospfv2_external_lsa;
+    using Rib = hl_ospfv2_rib;
+    using NetIn = hl_route_net;
+    using Nh = hl_nexthop;
+    using Out = hl_rib_route;
+    static void put4(PKey &k, uint32_t a, uint32_t mask) {
+        k.b[0] = (uint8_t)(a >> 24); k.b[1] = (uint8_t)(a >> 16); k.b[2] = (uint8_t)(a >> 8); k.b[3] = (uint8_t)a;
+        k.b[16] = (uint8_t)__builtin_popcount(mask);
     }
-    if (a.metric != b.metric) return a.metric < b.metric ? -1 : 1;
-    return 0;
-}
+    static PKey key(const NetIn &r) { PKey k; put4(k, r.prefix, r.mask); return k; }
+    // with_netmask(lsa_id, mask) without apply_mask (ospfv2/spf.rs:552,602): host bits are kept
+    static PKey key(const Sum &l) { PKey k; put4(k, l.lsa_id, l.mask); return k; }
+    static PKey key(const Ext &l) { PKey k; put4(k, l.lsa_id, l.mask); return k; }
+    static bool skip(const Sum &) { return false; }
+    static bool skip(const Ext &) { return false; }
+    static uint32_t asbr_id(const Sum &l) { return l.lsa_id; }
+    static uint8_t options(const NetIn &) { return 0; }
+    static uint8_t options(const Sum &) { return 0; }
+    static uint8_t options(const Ext &) { return 0; }
+    static void addr_key(const Nh &n, std::array<uint8_t, 16> &kb) {
+        kb.fill(0);
+        if (n.has_addr) { kb[0] = (uint8_t)(n.addr >> 24); kb[1] = (uint8_t)(n.addr >> 16); kb[2] = (uint8_t)(n.addr >> 8); kb[3] = (uint8_t)n.addr; }
+    }
+    static void emit(Out &o, const PKey &k, uint8_t /*options*/) {
+        o.prefix = ((uint32_t)k.b[0] << 24) | ((uint32_t)k.b[1] << 16) | ((uint32_t)k.b[2] << 8) | k.b[3];
+        o.mask = k.b[16] ? 0xFFFFFFFFu << (32 - k.b[16]) : 0u;
+    }
+};
 
-struct Table {
+struct V3 {
+    using Area = hl_ospfv3_rib_area;
+    using Sum = hl_ospfv3_inter_area_lsa;
+    using Ext = hl_ospfv3_external_lsa;
+    using Rib = hl_ospfv3_rib;
+    using NetIn = hl_route_net6;
+    using Nh = hl_nexthop6;
+    using Out = hl_rib_route6;
+    static PKey mk(const hl_ip_addr &a, uint8_t len) { PKey k; std::memcpy(k.b.data(), a.bytes, 16); k.b[16] = len; return k; }
+    static PKey key(const NetIn &r) { return mk(r.prefix, r.len); }
+    static PKey key(const Sum &l) { return mk(l.prefix, l.len); }
+    static PKey key(const Ext &l) { return mk(l.prefix, l.len); }
+    static bool skip(const Sum &l) { return l.lsa_type == 3 && (l.prefix_options & HL_PFX_OPT_NU); }   // ospfv3/spf.rs:494
+    static bool skip(const Ext &l) { return (l.prefix_options & HL_PFX_OPT_NU) != 0; }                   // ospfv3/spf.rs:538
+    static uint32_t asbr_id(const Sum &l) { return l.router_id; }
+    static uint8_t options(const NetIn &r) { return r.prefix_options; }
+    static uint8_t options(const Sum &l) { return l.prefix_options; }
+    static uint8_t options(const Ext &l) { return l.prefix_options; }
+    static void addr_key(const Nh &n, std::array<uint8_t, 16> &kb) {
+        kb.fill(0);
+        if (n.has_addr) std::memcpy(kb.data(), n.addr.bytes, 16);
+    }
+    static void emit(Out &o, const PKey &k, uint8_t options) {
+        std::memcpy(o.prefix.bytes, k.b.data(), 16);
+        o.prefix.is_v6 = 1;
+        o.len = k.b[16];
+        o.prefix_options = options;
+    }
+};
+
+// ---- the stages ------------------------------------------------------------------------------
+template <class T>
+int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *areas, uint32_t n_areas,
+             const typename T::Ext *ext, uint32_t n_ext, typename T::Rib *out) {
+    using Hop = HopT<typename T::Nh>;
+    using Hops = std::vector<Hop>;
+    struct Net {
+        PKey key;
+        uint32_t metric, type2, tag, area;
+        uint8_t path, flags, options;
+        bool has_area, has_type2;
+        Hops hops;
+    };
+    struct Rtr {
+        uint32_t area, metric;
+        uint8_t path, flags;
+        Hops hops;
+    };
+    if ((!areas && n_areas) || (!ext && n_ext) || !out) return HSPF_E_INVAL;
+    for (uint32_t ai = 0; ai < n_areas; ++ai) {
+        const auto &a = areas[ai];
+        if (!a.spf || (a.n_ifaces && !a.ifaces) || (a.n_summaries && !a.summaries)) return HSPF_E_INVAL;
+    }
+    auto clip = [&](Hops &h) { if (h.size() > max_paths) h.resize(max_paths); };
+    auto prefer = [](const Net &a, const Net &b) -> int {      // route_compare; negative: a wins
+        if (a.path != b.path) return a.path < b.path ? -1 : 1;
+        if (a.path == HL_PATH_TYPE2_EXTERNAL) {
+            if (a.has_type2 != b.has_type2) return a.has_type2 ? 1 : -1;     // None < Some
+            if (a.type2 != b.type2) return a.type2 < b.type2 ? -1 : 1;
+        }
+        if (a.metric != b.metric) return a.metric < b.metric ? -1 : 1;
+        return 0;
+    };
     std::vector<Net> nets;
-    std::unordered_map<uint64_t, uint32_t> index;
-    uint32_t max_paths;
-
-    static uint64_t k(uint32_t prefix, uint32_t mask) { return ((uint64_t)prefix << 32) | mask; }
-    Net *find(uint32_t prefix, uint32_t mask) {
-        auto it = index.find(k(prefix, mask));
+    std::unordered_map<PKey, uint32_t, PKeyHash> index;
+    auto find = [&](const PKey &k) -> Net * {
+        auto it = index.find(k);
         return it == index.end() ? nullptr : &nets[it->second];
-    }
-    void offer(Net &&n) {          // route_update
-        Net *cur = find(n.prefix, n.mask);
+    };
+    auto offer = [&](Net &&n) {                                 // route_update
+        Net *cur = find(n.key);
         if (!cur) {
-            index.emplace(k(n.prefix, n.mask), (uint32_t)nets.size());
+            index.emplace(n.key, (uint32_t)nets.size());
             nets.push_back(std::move(n));
             cur = &nets.back();
         } else {
@@ -96,33 +176,159 @@ struct Table {
             if (c < 0) *cur = std::move(n);
             else if (c == 0) merge_hops(cur->hops, n.hops);
         }
-        clip(cur->hops, max_paths);
-    }
-};
+        clip(cur->hops);
+    };
+    auto hops_of = [&](const typename T::Area &a, uint32_t off, uint32_t n) {
+        Hops h;
+        h.reserve(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            Hop x;
+            x.nh = a.spf->nexthops[off + i];
+            const uint32_t sk = x.nh.iface < a.n_ifaces ? a.ifaces[x.nh.iface].sort_key : 0xFFFFFFFFu;
+            x.nh.iface = sk;                   // the merged table names interfaces by sort key
+            x.ka = ((uint64_t)sk << 1) | (x.nh.has_addr ? 1u : 0u);
+            T::addr_key(x.nh, x.kb);
+            h.push_back(x);
+        }
+        std::stable_sort(h.begin(), h.end(), key_less<typename T::Nh>);
+        Hops u;                                // same key twice: the later one stays
+        for (const Hop &x : h) {
+            if (!u.empty() && key_same(u.back(), x)) u.back() = x;
+            else u.push_back(x);
+        }
+        return u;
+    };
+    auto usable = [&](const typename T::Sum &l) {
+        return !l.maxage && l.metric < HL_LSA_INFINITY && l.adv_rtr != router_id && !T::skip(l);
+    };
+    std::vector<std::unordered_map<uint32_t, Rtr>> rtrs(n_areas);
 
-Hops hops_of(const hl_ospfv2_rib_area &a, uint32_t off, uint32_t n) {
-    Hops h;
-    h.reserve(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        Hop x;
-        x.nh = a.spf->nexthops[off + i];
-        const uint32_t sk = x.nh.iface < a.n_ifaces ? a.ifaces[x.nh.iface].sort_key : 0xFFFFFFFFu;
-        x.nh.iface = sk;                       // the merged table names interfaces by sort key
-        x.ka = ((uint64_t)sk << 1) | (x.nh.has_addr ? 1u : 0u);
-        x.kb = x.nh.has_addr ? x.nh.addr : 0u;
-        h.push_back(x);
+    // 1. per-area router tables; intra-area routes of all areas into one table
+    for (uint32_t ai = 0; ai < n_areas; ++ai) {
+        const auto &a = areas[ai];
+        for (uint32_t i = 0; i < a.spf->n_routers; ++i) {
+            const hl_route_rtr &r = a.spf->routers[i];
+            rtrs[ai][r.router_id] = Rtr{a.area_id, r.metric, HL_PATH_INTRA_AREA, r.flags, hops_of(a, r.nh_off, r.n_nh)};
+        }
+        for (uint32_t i = 0; i < a.spf->n_routes; ++i) {
+            const auto &r = a.spf->routes[i];
+            const PKey k = T::key(r);
+            if (const Net *cur = find(k))
+                if (r.metric > cur->metric) continue;
+            offer(Net{k, r.metric, 0, 0, a.area_id, HL_PATH_INTRA_AREA, r.flags, T::options(r), true, false,
+                      hops_of(a, r.nh_off, r.n_nh)});
+        }
     }
-    std::stable_sort(h.begin(), h.end(), key_less);
-    Hops u;                                    // same key twice: the later one stays
-    for (const Hop &x : h) {
-        if (!u.empty() && key_same(u.back(), x)) u.back() = x;
-        else u.push_back(x);
+
+    // 2. summaries: only the backbone's when more than one area is active
+    uint32_t n_active = 0;
+    for (uint32_t ai = 0; ai < n_areas; ++ai) n_active += areas[ai].active ? 1u : 0u;
+    auto abr = [&](uint32_t ai, uint32_t adv) -> const Rtr * {
+        auto it = rtrs[ai].find(adv);
+        return (it != rtrs[ai].end() && (it->second.flags & HL_RTR_FLAG_B)) ? &it->second : nullptr;
+    };
+    for (uint32_t ai = 0; ai < n_areas; ++ai) {
+        const auto &a = areas[ai];
+        if (n_active > 1 && a.area_id != 0) continue;
+        for (uint32_t i = 0; i < a.n_summaries; ++i) {            // networks
+            const auto &l = a.summaries[i];
+            if (l.lsa_type != 3 || !usable(l)) continue;
+            const Rtr *br = abr(ai, l.adv_rtr);
+            if (!br) continue;
+            offer(Net{T::key(l), br->metric + l.metric, 0, 0, a.area_id, HL_PATH_INTER_AREA, 0, T::options(l), true,
+                      false, br->hops});
+        }
+        for (uint32_t i = 0; i < a.n_summaries; ++i) {            // ASBRs
+            const auto &l = a.summaries[i];
+            if (l.lsa_type != 4 || !usable(l)) continue;
+            const Rtr *br = abr(ai, l.adv_rtr);
+            if (!br) continue;
+            Rtr e{a.area_id, br->metric + l.metric, HL_PATH_INTER_AREA, HL_RTR_FLAG_E, br->hops};
+            rtrs[ai][T::asbr_id(l)] = std::move(e);               // replaces any earlier entry
+        }
     }
-    return u;
+
+    // 3. transit areas
+    for (uint32_t ai = 0; ai < n_areas; ++ai) {
+        const auto &a = areas[ai];
+        if (!a.spf->transit_capability) continue;
+        for (uint32_t i = 0; i < a.n_summaries; ++i) {
+            const auto &l = a.summaries[i];
+            if (l.lsa_type != 3 || !usable(l)) continue;
+            Net *cur = find(T::key(l));
+            if (!cur || cur->path > HL_PATH_INTER_AREA || !cur->has_area || cur->area != 0) continue;
+            const Rtr *br = abr(ai, l.adv_rtr);
+            if (!br) continue;
+            const uint32_t metric = br->metric + l.metric;
+            if (metric < cur->metric) {
+                const PKey k = cur->key;
+                *cur = Net{k, metric, 0, 0, a.area_id, HL_PATH_INTER_AREA, 0, T::options(l), true, false, br->hops};
+            } else if (metric == cur->metric) {
+                merge_hops(cur->hops, br->hops);
+            }
+            clip(cur->hops);
+        }
+    }
+
+    // 4. AS-external LSAs through the best ASBR entry (areas in area-id order)
+    std::vector<uint32_t> order(n_areas);
+    for (uint32_t i = 0; i < n_areas; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return areas[x].area_id < areas[y].area_id; });
+    for (uint32_t i = 0; i < n_ext; ++i) {
+        const auto &l = ext[i];
+        if (l.maxage || !(l.metric < HL_LSA_INFINITY) || l.adv_rtr == router_id || T::skip(l)) continue;
+        const Rtr *best = nullptr;
+        bool best_pref = false;          // intra-area through a non-backbone area
+        for (uint32_t ai : order) {
+            auto it = rtrs[ai].find(l.adv_rtr);
+            if (it == rtrs[ai].end() || !(it->second.flags & HL_RTR_FLAG_E)) continue;
+            const Rtr *r = &it->second;
+            const bool pref = r->path == HL_PATH_INTRA_AREA && r->area != 0;
+            if (!best || (pref && !best_pref)) { best = r; best_pref = pref; continue; }
+            if (pref != best_pref) continue;
+            if (r->metric < best->metric || (r->metric == best->metric && r->area > best->area)) best = r;
+        }
+        if (!best) continue;
+        Net n{T::key(l), 0, 0, l.tag, 0, 0, 0, T::options(l), false, false, best->hops};
+        if (l.e_bit) { n.path = HL_PATH_TYPE2_EXTERNAL; n.metric = best->metric; n.has_type2 = true; n.type2 = l.metric; }
+        else { n.path = HL_PATH_TYPE1_EXTERNAL; n.metric = best->metric + l.metric; }
+        offer(std::move(n));
+    }
+
+    // emit in IpNetwork order (address, then prefix length)
+    std::vector<uint32_t> idx(nets.size());
+    for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return nets[x].key < nets[y].key; });
+    uint32_t n_h = 0;
+    for (const Net &n : nets) n_h += (uint32_t)n.hops.size();
+    out->n_routes = (uint32_t)nets.size();
+    out->n_nexthops = n_h;
+    if (out->n_routes > out->routes_cap || n_h > out->nexthops_cap) return HSPF_E_NOMEM;
+    if ((out->n_routes && !out->routes) || (n_h && !out->nexthops)) return HSPF_E_INVAL;
+    uint32_t h = 0;
+    for (uint32_t r = 0; r < idx.size(); ++r) {
+        const Net &n = nets[idx[r]];
+        typename T::Out o;
+        std::memset(&o, 0, sizeof(o));
+        T::emit(o, n.key, n.options);
+        o.metric = n.metric; o.type2_metric = n.type2; o.tag = n.tag; o.area_id = n.area; o.path_type = n.path;
+        o.flags = n.flags; o.has_area = n.has_area ? 1 : 0; o.has_type2 = n.has_type2 ? 1 : 0;
+        o.nh_off = h; o.n_nh = (uint32_t)n.hops.size();
+        for (const Hop &x : n.hops) out->nexthops[h++] = x.nh;
+        out->routes[r] = o;
+    }
+    return HSPF_OK;
 }
 
-bool usable(const hl_ospfv2_summary_lsa &l, uint32_t router_id) {
-    return !l.maxage && l.metric < HL_LSA_INFINITY && l.adv_rtr != router_id;
+template <class T, class... A>
+int guarded(A... args) {
+    try {
+        return rib_full<T>(args...);
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
 }
 
 }  // namespace
@@ -130,137 +336,11 @@ bool usable(const hl_ospfv2_summary_lsa &l, uint32_t router_id) {
 extern "C" int hspf_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv2_rib_area *areas,
                                            uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,
                                            hl_ospfv2_rib *out) {
-    if ((!areas && n_areas) || (!ext && n_ext) || !out) return HSPF_E_INVAL;
-    try {
-        for (uint32_t ai = 0; ai < n_areas; ++ai) {
-            const hl_ospfv2_rib_area &a = areas[ai];
-            if (!a.spf || (a.n_ifaces && !a.ifaces) || (a.n_summaries && !a.summaries)) return HSPF_E_INVAL;
-        }
-        Table t;
-        t.max_paths = max_paths;
-        std::vector<std::unordered_map<uint32_t, Rtr>> rtrs(n_areas);
+    return guarded<V2>(router_id, max_paths, areas, n_areas, ext, n_ext, out);
+}
 
-        // 1. per-area router tables; intra-area routes of all areas into one table
-        for (uint32_t ai = 0; ai < n_areas; ++ai) {
-            const hl_ospfv2_rib_area &a = areas[ai];
-            for (uint32_t i = 0; i < a.spf->n_routers; ++i) {
-                const hl_route_rtr &r = a.spf->routers[i];
-                Rtr e{a.area_id, r.metric, HL_PATH_INTRA_AREA, r.flags, hops_of(a, r.nh_off, r.n_nh)};
-                rtrs[ai][r.router_id] = std::move(e);
-            }
-            for (uint32_t i = 0; i < a.spf->n_routes; ++i) {
-                const hl_route_net &r = a.spf->routes[i];
-                if (const Net *cur = t.find(r.prefix, r.mask))
-                    if (r.metric > cur->metric) continue;
-                Net n{r.prefix, r.mask, r.metric, 0, 0, a.area_id, HL_PATH_INTRA_AREA, r.flags, true, false,
-                      hops_of(a, r.nh_off, r.n_nh)};
-                t.offer(std::move(n));
-            }
-        }
-
-        // 2. Summary-LSAs: only the backbone's when more than one area is active
-        uint32_t n_active = 0;
-        for (uint32_t ai = 0; ai < n_areas; ++ai) n_active += areas[ai].active ? 1u : 0u;
-        auto abr = [&](uint32_t ai, uint32_t adv) -> const Rtr * {
-            auto it = rtrs[ai].find(adv);
-            return (it != rtrs[ai].end() && (it->second.flags & HL_RTR_FLAG_B)) ? &it->second : nullptr;
-        };
-        for (uint32_t ai = 0; ai < n_areas; ++ai) {
-            const hl_ospfv2_rib_area &a = areas[ai];
-            if (n_active > 1 && a.area_id != 0) continue;
-            for (uint32_t i = 0; i < a.n_summaries; ++i) {            // networks
-                const hl_ospfv2_summary_lsa &l = a.summaries[i];
-                if (l.lsa_type != 3 || !usable(l, router_id)) continue;
-                const Rtr *br = abr(ai, l.adv_rtr);
-                if (!br) continue;
-                Net n{l.lsa_id, l.mask, br->metric + l.metric, 0, 0, a.area_id, HL_PATH_INTER_AREA, 0, true, false, br->hops};
-                t.offer(std::move(n));
-            }
-            for (uint32_t i = 0; i < a.n_summaries; ++i) {            // ASBRs
-                const hl_ospfv2_summary_lsa &l = a.summaries[i];
-                if (l.lsa_type != 4 || !usable(l, router_id)) continue;
-                const Rtr *br = abr(ai, l.adv_rtr);
-                if (!br) continue;
-                Rtr e{a.area_id, br->metric + l.metric, HL_PATH_INTER_AREA, HL_RTR_FLAG_E, br->hops};
-                rtrs[ai][l.lsa_id] = std::move(e);                    // replaces any earlier entry
-            }
-        }
-
-        // 3. transit areas
-        for (uint32_t ai = 0; ai < n_areas; ++ai) {
-            const hl_ospfv2_rib_area &a = areas[ai];
-            if (!a.spf->transit_capability) continue;
-            for (uint32_t i = 0; i < a.n_summaries; ++i) {
-                const hl_ospfv2_summary_lsa &l = a.summaries[i];
-                if (l.lsa_type != 3 || !usable(l, router_id)) continue;
-                Net *cur = t.find(l.lsa_id, l.mask);
-                if (!cur || cur->path > HL_PATH_INTER_AREA || !cur->has_area || cur->area != 0) continue;
-                const Rtr *br = abr(ai, l.adv_rtr);
-                if (!br) continue;
-                const uint32_t metric = br->metric + l.metric;
-                if (metric < cur->metric) {
-                    const uint32_t p = cur->prefix, m = cur->mask;
-                    *cur = Net{p, m, metric, 0, 0, a.area_id, HL_PATH_INTER_AREA, 0, true, false, br->hops};
-                } else if (metric == cur->metric) {
-                    merge_hops(cur->hops, br->hops);
-                }
-                clip(cur->hops, max_paths);
-            }
-        }
-
-        // 4. AS-external LSAs through the best ASBR entry (areas in area-id order)
-        std::vector<uint32_t> order(n_areas);
-        for (uint32_t i = 0; i < n_areas; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return areas[x].area_id < areas[y].area_id; });
-        for (uint32_t i = 0; i < n_ext; ++i) {
-            const hl_ospfv2_external_lsa &l = ext[i];
-            if (l.maxage || !(l.metric < HL_LSA_INFINITY) || l.adv_rtr == router_id) continue;
-            const Rtr *best = nullptr;
-            bool best_pref = false;          // intra-area through a non-backbone area
-            for (uint32_t ai : order) {
-                auto it = rtrs[ai].find(l.adv_rtr);
-                if (it == rtrs[ai].end() || !(it->second.flags & HL_RTR_FLAG_E)) continue;
-                const Rtr *r = &it->second;
-                const bool pref = r->path == HL_PATH_INTRA_AREA && r->area != 0;
-                if (!best || (pref && !best_pref)) { best = r; best_pref = pref; continue; }
-                if (pref != best_pref) continue;
-                if (r->metric < best->metric || (r->metric == best->metric && r->area > best->area)) best = r;
-            }
-            if (!best) continue;
-            Net n{l.lsa_id, l.mask, 0, 0, l.tag, 0, 0, 0, false, false, best->hops};
-            if (l.e_bit) { n.path = HL_PATH_TYPE2_EXTERNAL; n.metric = best->metric; n.has_type2 = true; n.type2 = l.metric; }
-            else { n.path = HL_PATH_TYPE1_EXTERNAL; n.metric = best->metric + l.metric; }
-            t.offer(std::move(n));
-        }
-
-        // emit in Ipv4Network order (address, then prefix length)
-        std::vector<uint32_t> idx(t.nets.size());
-        for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
-        std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
-            const Net &p = t.nets[x], &q = t.nets[y];
-            return p.prefix != q.prefix ? p.prefix < q.prefix : p.mask < q.mask;
-        });
-        uint32_t n_h = 0;
-        for (const Net &n : t.nets) n_h += (uint32_t)n.hops.size();
-        out->n_routes = (uint32_t)t.nets.size();
-        out->n_nexthops = n_h;
-        if (out->n_routes > out->routes_cap || n_h > out->nexthops_cap) return HSPF_E_NOMEM;
-        if ((out->n_routes && !out->routes) || (n_h && !out->nexthops)) return HSPF_E_INVAL;
-        uint32_t h = 0;
-        for (uint32_t r = 0; r < idx.size(); ++r) {
-            const Net &n = t.nets[idx[r]];
-            hl_rib_route o;
-            std::memset(&o, 0, sizeof(o));
-            o.prefix = n.prefix; o.mask = n.mask; o.metric = n.metric; o.type2_metric = n.type2; o.tag = n.tag;
-            o.area_id = n.area; o.path_type = n.path; o.flags = n.flags; o.has_area = n.has_area ? 1 : 0;
-            o.has_type2 = n.has_type2 ? 1 : 0; o.nh_off = h; o.n_nh = (uint32_t)n.hops.size();
-            for (const Hop &x : n.hops) out->nexthops[h++] = x.nh;
-            out->routes[r] = o;
-        }
-        return HSPF_OK;
-    } catch (const std::bad_alloc &) {
-        return HSPF_E_NOMEM;
-    } catch (...) {
-        return HSPF_E_INVAL;
-    }
+extern "C" int hspf_ospfv3_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv3_rib_area *areas,
+                                           uint32_t n_areas, const hl_ospfv3_external_lsa *ext, uint32_t n_ext,
+                                           hl_ospfv3_rib *out) {
+    return guarded<V3>(router_id, max_paths, areas, n_areas, ext, n_ext, out);
 }

@@ -26,6 +26,24 @@ RIB_ROUTE_DT = np.dtype([("prefix", "<u4"), ("mask", "<u4"), ("metric", "<u4"), 
                          ("has_type2", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
 
 
+# OSPFv3 twins (hl_ospfv3_inter_area_lsa, hl_ospfv3_external_lsa, hl_rib_route6)
+def _ip_dt():
+    from . import ospfv3
+    return ospfv3.IP_DT
+
+
+INTER_AREA_LSA_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("metric", "<u4"), ("router_id", "<u4"),
+                              ("prefix", _ip_dt()), ("len", "u1"), ("prefix_options", "u1"), ("lsa_type", "u1"),
+                              ("maxage", "u1")], align=True)
+EXTERNAL6_LSA_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("metric", "<u4"), ("tag", "<u4"),
+                             ("prefix", _ip_dt()), ("len", "u1"), ("prefix_options", "u1"), ("e_bit", "u1"),
+                             ("maxage", "u1")], align=True)
+RIB_ROUTE6_DT = np.dtype([("prefix", _ip_dt()), ("len", "u1"), ("path_type", "u1"), ("flags", "u1"),
+                          ("prefix_options", "u1"), ("has_area", "u1"), ("has_type2", "u1"), ("_pad", "u1", (2,)),
+                          ("metric", "<u4"), ("type2_metric", "<u4"), ("tag", "<u4"), ("area_id", "<u4"),
+                          ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+
+
 class RibAreaStruct(C.Structure):
     _fields_ = [
         ("area_id", C.c_uint32), ("n_summaries", C.c_uint32),
@@ -43,7 +61,9 @@ class RibStruct(C.Structure):
 
 # appended to hspf_abi_sizes() after the OSPFv3 block
 ABI_SIZES = [SUMMARY_LSA_DT.itemsize, EXTERNAL_LSA_DT.itemsize, C.sizeof(RibAreaStruct), RIB_ROUTE_DT.itemsize,
-             C.sizeof(RibStruct)]
+             C.sizeof(RibStruct),
+             INTER_AREA_LSA_DT.itemsize, EXTERNAL6_LSA_DT.itemsize, C.sizeof(RibAreaStruct), RIB_ROUTE6_DT.itemsize,
+             C.sizeof(RibStruct)]       # hl_ospfv3_rib_area / hl_ospfv3_rib have the layouts of the v2 structs
 
 
 @dataclass
@@ -67,10 +87,24 @@ class Rib:
                 for x in self.nexthops[int(rec["nh_off"]): int(rec["nh_off"]) + int(rec["n_nh"])]]
 
 
-def _result_struct(res: ospfv2.Ospfv2Result, keep: list) -> ospfv2.ResultStruct:
-    r = ospfv2.ResultStruct()
-    for name, dt in (("vertices", ospfv2.SPT_VERTEX_DT), ("routers", ospfv2.ROUTE_RTR_DT),
-                     ("routes", ospfv2.ROUTE_NET_DT), ("nexthops", ospfv2.NEXTHOP_DT)):
+def _version(v3: bool):
+    """(result struct class, result dtypes, iface dtype, summary dtype, external dtype, route dtype, nexthop dtype)"""
+    if not v3:
+        return (ospfv2.ResultStruct,
+                (("vertices", ospfv2.SPT_VERTEX_DT), ("routers", ospfv2.ROUTE_RTR_DT), ("routes", ospfv2.ROUTE_NET_DT),
+                 ("nexthops", ospfv2.NEXTHOP_DT)),
+                ospfv2.IFACE_DT, SUMMARY_LSA_DT, EXTERNAL_LSA_DT, RIB_ROUTE_DT, ospfv2.NEXTHOP_DT)
+    from . import ospfv3
+    return (ospfv3.ResultStruct,
+            (("vertices", ospfv3.SPT_VERTEX6_DT), ("routers", ospfv2.ROUTE_RTR_DT), ("routes", ospfv3.ROUTE_NET6_DT),
+             ("nexthops", ospfv3.NEXTHOP6_DT)),
+            ospfv3.IFACE_DT, INTER_AREA_LSA_DT, EXTERNAL6_LSA_DT, RIB_ROUTE6_DT, ospfv3.NEXTHOP6_DT)
+
+
+def _result_struct(res, keep: list, v3: bool = False):
+    cls, fields = _version(v3)[:2]
+    r = cls()
+    for name, dt in fields:
         a = np.ascontiguousarray(getattr(res, name), dtype=dt)
         keep.append(a)
         setattr(r, name + "_cap", len(a))
@@ -81,28 +115,29 @@ def _result_struct(res: ospfv2.Ospfv2Result, keep: list) -> ospfv2.ResultStruct:
     return r
 
 
-def call_update_rib_full(fn, router_id: int, max_paths: int, areas: list, externals=None) -> Rib:
-    """`fn` = hspf_ospfv2_update_rib_full of the product library or the oracle's twin."""
+def call_update_rib_full(fn, router_id: int, max_paths: int, areas: list, externals=None, v3: bool = False) -> Rib:
+    """`fn` = hspf_ospfv{2,3}_update_rib_full of the product library or the oracle's twin."""
+    _cls, _fields, IFACE_DT_, SUM_DT_, EXT_DT_, ROUTE_DT_, NH_DT_ = _version(v3)
     fn.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(RibAreaStruct), C.c_uint32, C.c_void_p, C.c_uint32,
                    C.POINTER(RibStruct)]
     keep = []
     arr = (RibAreaStruct * max(len(areas), 1))()
     for i, a in enumerate(areas):
-        rs = _result_struct(a.result, keep)
+        rs = _result_struct(a.result, keep, v3)
         keep.append(rs)
-        ifs = np.ascontiguousarray(a.ifaces, dtype=ospfv2.IFACE_DT)
-        sm = np.ascontiguousarray(a.summaries, dtype=SUMMARY_LSA_DT)
+        ifs = np.ascontiguousarray(a.ifaces, dtype=IFACE_DT_)
+        sm = np.ascontiguousarray(a.summaries, dtype=SUM_DT_)
         keep += [ifs, sm]
         arr[i].area_id, arr[i].n_summaries = a.area_id, len(sm)
         arr[i].spf = C.addressof(rs)
         arr[i].ifaces = ifs.ctypes.data if len(ifs) else None
         arr[i].summaries = sm.ctypes.data if len(sm) else None
         arr[i].n_ifaces, arr[i].active = len(ifs), int(a.active)
-    ext = np.ascontiguousarray(externals if externals is not None else np.zeros(0, EXTERNAL_LSA_DT), dtype=EXTERNAL_LSA_DT)
+    ext = np.ascontiguousarray(externals if externals is not None else np.zeros(0, EXT_DT_), dtype=EXT_DT_)
     caps = [256, 1024]
     for _ in range(3):
-        routes = np.zeros(caps[0], RIB_ROUTE_DT)
-        nhs = np.zeros(caps[1], ospfv2.NEXTHOP_DT)
+        routes = np.zeros(caps[0], ROUTE_DT_)
+        nhs = np.zeros(caps[1], NH_DT_)
         r = RibStruct()
         r.routes_cap, r.routes = caps[0], routes.ctypes.data
         r.nexthops_cap, r.nexthops = caps[1], nhs.ctypes.data
@@ -120,4 +155,13 @@ def update_rib_full(router_id: int, max_paths: int, areas: list, externals=None)
     rib = call_update_rib_full(lib.hspf_ospfv2_update_rib_full, router_id, max_paths, areas, externals)
     if rib.rc != capi.HSPF_OK:
         raise capi.HspfError(rib.rc, "hspf_ospfv2_update_rib_full failed")
+    return rib
+
+
+def update_rib_full_v3(router_id: int, max_paths: int, areas: list, externals=None) -> Rib:
+    """OSPFv3 twin (hspf_ospfv3_update_rib_full); host only."""
+    lib = capi.load_library()
+    rib = call_update_rib_full(lib.hspf_ospfv3_update_rib_full, router_id, max_paths, areas, externals, v3=True)
+    if rib.rc != capi.HSPF_OK:
+        raise capi.HspfError(rib.rc, "hspf_ospfv3_update_rib_full failed")
     return rib

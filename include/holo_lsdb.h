@@ -424,6 +424,65 @@ typedef struct hl_route_net6 {
     uint32_t n_nh;
 } hl_route_net6;
 
+/* ---- OSPFv3 full routing table (the same generic stages, route.rs:146-193) ---- */
+/* Inter-Area-Prefix-LSA (type 3) / Inter-Area-Router-LSA (type 4), ospfv3/spf.rs:479-526,
+ * LSDB (LsaKey) order per area. */
+typedef struct hl_ospfv3_inter_area_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t metric;
+    uint32_t router_id;    /* type 4: the ASBR                                    */
+    hl_ip_addr prefix;     /* type 3                                               */
+    uint8_t  len;
+    uint8_t  prefix_options;   /* HL_PFX_OPT_NU: skipped (ospfv3/spf.rs:494)      */
+    uint8_t  lsa_type;     /* 3 or 4                                               */
+    uint8_t  maxage;
+} hl_ospfv3_inter_area_lsa;
+
+/* AS-External-LSA (ospfv3/spf.rs:528-560), instance LSDB order. */
+typedef struct hl_ospfv3_external_lsa {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t metric;
+    uint32_t tag;
+    hl_ip_addr prefix;
+    uint8_t  len;
+    uint8_t  prefix_options;
+    uint8_t  e_bit;
+    uint8_t  maxage;
+} hl_ospfv3_external_lsa;
+
+struct hl_ospfv3_result;
+typedef struct hl_ospfv3_rib_area {
+    uint32_t area_id;
+    uint32_t n_summaries;
+    const struct hl_ospfv3_result      *spf;      /* hspf_ospfv3_run_area output     */
+    const hl_ospfv3_iface              *ifaces;
+    const hl_ospfv3_inter_area_lsa     *summaries;
+    uint32_t n_ifaces;
+    uint8_t  active;
+    uint8_t  _pad[3];
+} hl_ospfv3_rib_area;
+
+/* Route of the merged table, in prefix order; next hops are hl_nexthop6 with `iface` = the
+ * interface's sort_key. */
+typedef struct hl_rib_route6 {
+    hl_ip_addr prefix;
+    uint8_t  len;
+    uint8_t  path_type;    /* HL_PATH_*                                            */
+    uint8_t  flags;        /* HL_ROUTE_CONNECTED                                   */
+    uint8_t  prefix_options;
+    uint8_t  has_area;
+    uint8_t  has_type2;
+    uint8_t  _pad[2];
+    uint32_t metric;
+    uint32_t type2_metric;
+    uint32_t tag;
+    uint32_t area_id;
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_rib_route6;
+
 typedef struct hl_ospfv3_result {
     uint32_t vertices_cap, n_vertices;   hl_spt_vertex6 *vertices;
     uint32_t routers_cap,  n_routers;    hl_route_rtr   *routers;
@@ -433,6 +492,11 @@ typedef struct hl_ospfv3_result {
     uint8_t  root_found;
     uint8_t  _pad[2];
 } hl_ospfv3_result;
+
+typedef struct hl_ospfv3_rib {
+    uint32_t routes_cap,   n_routes;     hl_rib_route6 *routes;
+    uint32_t nexthops_cap, n_nexthops;   hl_nexthop6   *nexthops;
+} hl_ospfv3_rib;
 
 /* ------------------------------------------------------------------- IS-IS -- */
 

@@ -74,6 +74,12 @@ int hspf_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl
                                 uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,
                                 hl_ospfv2_rib *out);
 
+/* The OSPFv3 twin (Inter-Area-Prefix / Inter-Area-Router / AS-External LSAs,
+ * holo-ospf/src/ospfv3/spf.rs:479-560; prefixes with the NU option are skipped). */
+int hspf_ospfv3_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv3_rib_area *areas,
+                                uint32_t n_areas, const hl_ospfv3_external_lsa *ext, uint32_t n_ext,
+                                hl_ospfv3_rib *out);
+
 /* ---- OSPFv3 ----------------------------------------------------------------
  *   hspf_ospfv3_run_area  <->  run_area<Ospfv3>() + update_rib_intra_area()
  *                              (holo-ospf/src/spf.rs:587-729 with the SpfVersion hooks of

@@ -99,6 +99,12 @@ def ospfv2_update_rib_full(router_id: int, max_paths: int, areas: list, external
     return ospf_rib.call_update_rib_full(lib().oracle_ospfv2_update_rib_full, router_id, max_paths, areas, externals)
 
 
+def ospfv3_update_rib_full(router_id: int, max_paths: int, areas: list, externals=None):
+    from holo_b200 import ospf_rib
+    return ospf_rib.call_update_rib_full(lib().oracle_ospfv3_update_rib_full, router_id, max_paths, areas, externals,
+                                         v3=True)
+
+
 def isis_compute_spt(level, root_system_id: int):
     """Reference-faithful compute_spt (local = false) over an IS-IS level image."""
     from holo_b200 import isis

@@ -140,7 +140,8 @@ def extract_ospfv3(ref: Path):
             o = ospf_root(json.loads(st.read_text()))
             snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"), "areas": [], "local_rib": []}
             for a in o.get("areas", {}).get("area", []):
-                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "iap_lsas": [], "interfaces": []}
+                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "iap_lsas": [],
+                        "inter_area_lsas": [], "interfaces": []}
                 for t in a.get("database", {}).get("area-scope-lsa-type", []):
                     for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
                         h = l["ospfv3"]["header"]
@@ -158,6 +159,18 @@ def extract_ospfv3(ref: Path):
                         elif "network" in b:
                             area["network_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
                                                          "attached": b["network"].get("attached-routers", {}).get("attached-router", [])})
+                        elif "inter-area-prefix" in b:
+                            # inputs of the inter-area stage (holo-ospf/src/ospfv3/spf.rs:479-503)
+                            p = b["inter-area-prefix"]
+                            area["inter_area_lsas"].append({
+                                "type": 3, "adv": h["adv-router"], "id": h["lsa-id"], "prefix": p["prefix"],
+                                "metric": p.get("metric", 0),
+                                "options": p.get("prefix-options", {}).get("prefix-options", [])})
+                        elif "inter-area-router" in b:
+                            p = b["inter-area-router"]
+                            area["inter_area_lsas"].append({
+                                "type": 4, "adv": h["adv-router"], "id": h["lsa-id"],
+                                "router_id": p.get("destination-router-id"), "metric": p.get("metric", 0)})
                         elif "intra-area-prefix" in b:
                             p = b["intra-area-prefix"]
                             pf = [[x["prefix"], x.get("metric", 0), x.get("prefix-options", {}).get("prefix-options", [])]

@@ -164,7 +164,7 @@ def load_ospfv3():
     return json.loads((GOLDEN / "ospfv3.json").read_text())
 
 
-def ospfv3_area_image(snap, area):
+def ospfv3_area_image(snap, area, sort_keys=None):
     """hl_ospfv3_area for one area of a golden OSPFv3 snapshot."""
     from holo_b200 import ospfv3
     rl = sorted(area["router_lsas"], key=lambda l: (ip(l["adv"]), l["id"]))
@@ -200,7 +200,7 @@ def ospfv3_area_image(snap, area):
             ty = 0
         else:
             ty = 1
-        ifaces.append((f["interface_id"] or 0, i + 1, ty, (0, 0, 0)))
+        ifaces.append((f["interface_id"] or 0, sort_keys[f["name"]] if sort_keys else i + 1, ty, (0, 0, 0)))
         names.append(f["name"])
         for (adv, lsid, ll) in f["link_lsas"]:
             llsas.append((i, ip(adv), lsid, 1, 0, ospfv3.ip_rec(ll)))
@@ -217,6 +217,46 @@ def ospfv3_area_image(snap, area):
         setattr(img, name, arr)
     img.ifnames = names
     return img
+
+
+def ospfv3_inter_area_lsas(area):
+    """hl_ospfv3_inter_area_lsa[] of one area of a golden OSPFv3 snapshot, LsaKey order."""
+    from holo_b200 import ospf_rib, ospfv3
+    ls = sorted(area.get("inter_area_lsas", []), key=lambda l: (l["type"], ip(l["adv"]), l["id"]))
+    out = np.zeros(len(ls), ospf_rib.INTER_AREA_LSA_DT)
+    for i, l in enumerate(ls):
+        if l["type"] == 3:
+            net = ipaddress.ip_network(l["prefix"], strict=False)
+            out[i] = (ip(l["adv"]), l["id"], l["metric"], 0, ospfv3.ip_rec(net.network_address), net.prefixlen,
+                      ospfv3.PFX_NU if "nu-bit" in l.get("options", []) else 0, 3, 0)
+        else:
+            out[i] = (ip(l["adv"]), l["id"], l["metric"], ip(l["router_id"]), ospfv3.ip_rec("::"), 0, 0, 4, 0)
+    return out
+
+
+def ospfv3_full_rib(snap, run_area, update_rib_full):
+    """The whole OSPFv3 routing table of a golden snapshot (see ospfv2_full_rib)."""
+    from holo_b200 import ospf_rib, ospfv3
+    keys = global_sort_keys(snap)
+    key_name = {v: k for k, v in keys.items()}
+    areas = []
+    for area in snap["areas"]:
+        img = ospfv3_area_image(snap, area, keys)
+        res = run_area(img)
+        assert res.rc == 0
+        if not res.root_found:
+            continue
+        active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+        areas.append(ospf_rib.RibArea(ip(area["area_id"]), res, img.ifaces, ospfv3_inter_area_lsas(area), active))
+    rib = update_rib_full(ip(snap["router_id"]), 16, areas)
+    assert rib.rc == 0
+    out = {}
+    for r in rib.routes:
+        hops = rib.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        nh = sorted(((key_name.get(int(x["iface"]), "?"), ospfv3.ip_str(x["addr"]) if x["has_addr"] else None) for x in hops),
+                    key=lambda x: (x[0] or "", x[1] or ""))
+        out[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (int(r["metric"]), ospf_rib.PATH_NAMES[int(r["path_type"])], nh)
+    return out
 
 
 def routes6_as_dict(res, names):

@@ -86,6 +86,18 @@ def test_ospfv3_oracle_reproduces_reference_local_rib(snap):
     assert n_checked > 0
 
 
+@pytest.mark.parametrize("snap", SNAPS_V3, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_V3])
+def test_ospfv3_oracle_reproduces_the_whole_reference_local_rib(snap):
+    """OSPFv3: run_area per attached area + the update_rib_full stages (oracle/rib_ospf.cc)."""
+    got = gu.ospfv3_full_rib(snap, pyoracle.ospfv3_run_area, pyoracle.ospfv3_update_rib_full)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want), (sorted(set(got) - set(want)), sorted(set(want) - set(got)))
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g, (metric, rtype))
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
+
+
 SNAPS_ISIS = gu.load_isis()
 
 

@@ -126,3 +126,110 @@ def test_rib_stage_argument_checks():
     assert fn(1, 16, None, 1, None, 0, None) == capi.HSPF_E_INVAL
     r = ospf_rib.RibStruct()
     assert fn(1, 16, None, 0, None, 0, C.byref(r)) == capi.HSPF_OK and r.n_routes == 0
+
+
+# ------------------------------------------------------------------------------ OSPFv3
+SNAPS_V3 = gu.load_ospfv3()
+
+
+@pytest.mark.parametrize("snap", SNAPS_V3, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_V3])
+def test_product_rib_stage_v3_reproduces_reference_local_rib(snap):
+    got = gu.ospfv3_full_rib(snap, pyoracle.ospfv3_run_area, ospf_rib.update_rib_full_v3)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want)
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g)
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
+
+
+def random_instance_v3(seed: int):
+    from holo_b200 import ospfv3
+    rng = np.random.default_rng(10_000 + seed)
+    n_areas = int(rng.integers(1, 4))
+    area_ids = [0] + sorted(int(x) for x in rng.choice(np.arange(1, 9), n_areas - 1, replace=False))
+    rng.shuffle(area_ids)
+    router_id = 0x01010101
+    pool = [(f"2001:db8:{i:x}::", 64) for i in range(12)] + [(f"2001:db8:ffff::{i:x}", 128) for i in range(1, 7)] + [("::", 0)]
+    rtr_ids = [0x02020200 + i for i in range(10)]
+    lla = [f"fe80::{i:x}" for i in range(1, 6)]
+    areas, sk = [], 1
+    for aid in area_ids:
+        n_if = int(rng.integers(1, 5))
+        ifaces = np.zeros(n_if, ospfv3.IFACE_DT)
+        for i in range(n_if):
+            ifaces[i] = (100 + sk, sk, 0, (0, 0, 0))
+            sk += 1
+        nhs = []
+
+        def hops():
+            k = int(rng.integers(0, 4))
+            off = len(nhs)
+            seen = set()
+            for _ in range(k):
+                i = int(rng.integers(0, n_if))
+                ha = int(rng.integers(0, 2))
+                addr = lla[int(rng.integers(0, len(lla)))] if ha else "::"
+                if (i, ha, addr) in seen:
+                    continue
+                seen.add((i, ha, addr))
+                nhs.append((i, int(rng.integers(1, 99)), ospfv3.ip_rec(addr), ha, 1, (0, 0)))
+            return off, len(nhs) - off
+
+        routers = []
+        for rid in sorted(rng.choice(rtr_ids, int(rng.integers(1, 7)), replace=False)):
+            off, n = hops()
+            routers.append((int(rid), int(rng.integers(1, 60)), int(rng.integers(0, 4)), 2, (0, 0), off, n))
+        routes = []
+        for pi in sorted(rng.choice(len(pool) - 1, int(rng.integers(1, 8)), replace=False)):
+            p, ln = pool[int(pi)]
+            off, n = hops()
+            routes.append((ospfv3.ip_rec(p), ln, int(rng.integers(0, 2)), 1, 0, int(rng.integers(0, 40)), 0, 0, off, n))
+        mk = lambda rows, dt: np.asarray(rows, dtype=dt) if rows else np.zeros(0, dt)
+        res = ospfv3.Ospfv3Result(np.zeros(0, ospfv3.SPT_VERTEX6_DT), mk(routers, ospfv2.ROUTE_RTR_DT),
+                                  mk(routes, ospfv3.ROUTE_NET6_DT), mk(nhs, ospfv3.NEXTHOP6_DT),
+                                  bool(rng.integers(0, 2)), True)
+        sums = []
+        for _ in range(int(rng.integers(0, 14))):
+            ty = 3 if rng.random() < 0.7 else 4
+            adv = int(rng.choice(rtr_ids + [router_id]))
+            metric = int(rng.choice([1, 5, 10, 10, 20, ospf_rib.LSA_INFINITY]))
+            if ty == 3:
+                p, ln = pool[int(rng.integers(0, len(pool)))]
+                sums.append((adv, len(sums) + 1, metric, 0, ospfv3.ip_rec(p), ln,
+                             ospfv3.PFX_NU if rng.random() < 0.1 else 0, 3, int(rng.random() < 0.1)))
+            else:
+                sums.append((adv, len(sums) + 1, metric, int(rng.choice(rtr_ids)), ospfv3.ip_rec("::"), 0, 0, 4,
+                             int(rng.random() < 0.1)))
+        sums.sort(key=lambda x: (x[7], x[0], x[1]))
+        areas.append(ospf_rib.RibArea(aid, res, ifaces, mk(sums, ospf_rib.INTER_AREA_LSA_DT), bool(rng.random() < 0.8)))
+    ext = []
+    for k in range(int(rng.integers(0, 10))):
+        p, ln = pool[int(rng.integers(0, len(pool)))]
+        ext.append((int(rng.choice(rtr_ids)), k + 1, int(rng.choice([1, 10, 20, ospf_rib.LSA_INFINITY])),
+                    int(rng.integers(0, 5)), ospfv3.ip_rec(p), ln, ospfv3.PFX_NU if rng.random() < 0.1 else 0,
+                    int(rng.integers(0, 2)), int(rng.random() < 0.1)))
+    ext.sort(key=lambda x: (x[0], x[1]))
+    ext = np.asarray(ext, ospf_rib.EXTERNAL6_LSA_DT) if ext else np.zeros(0, ospf_rib.EXTERNAL6_LSA_DT)
+    return router_id, int(rng.choice([1, 2, 16])), areas, ext
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_product_rib_stage_v3_matches_restatement_on_random_tables(seed):
+    router_id, max_paths, areas, ext = random_instance_v3(seed)
+    a = ospf_rib.update_rib_full_v3(router_id, max_paths, areas, ext)
+    b = pyoracle.ospfv3_update_rib_full(router_id, max_paths, areas, ext)
+    assert b.rc == 0
+    assert a.routes.tobytes() == b.routes.tobytes(), (a.routes, b.routes)
+    assert a.nexthops.tobytes() == b.nexthops.tobytes()
+
+
+def test_random_tables_v3_exercise_every_stage():
+    kinds = set()
+    n_multi = 0
+    for seed in range(200):
+        router_id, max_paths, areas, ext = random_instance_v3(seed)
+        rib = ospf_rib.update_rib_full_v3(router_id, max_paths, areas, ext)
+        kinds |= set(int(p) for p in rib.routes["path_type"])
+        n_multi += int((rib.routes["n_nh"] > 1).sum())
+    assert kinds == {0, 1, 2, 3} and n_multi > 20

@@ -64,3 +64,18 @@ def test_reference_golden_local_rib(ctx, snap):
         if has_vlink and not got[prefix][1]:
             continue
         assert norm(got[prefix][1]) == norm(nh)
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_reference_golden_whole_local_rib(ctx, snap):
+    """LSDB -> full OSPFv3 routing table through the product only: hspf_ospfv3_run_area on the GPU
+    per attached area, then hspf_ospfv3_update_rib_full (the same helper runs on the CPU with the
+    oracle in tests/test_ospf_rib.py and tests/test_oracle_golden.py)."""
+    from holo_b200 import ospf_rib
+    got = gu.ospfv3_full_rib(snap, lambda img: ospfv3.run_area(ctx, img), ospf_rib.update_rib_full_v3)
+    want = gu.golden_rib(snap)
+    assert set(got) == set(want)
+    for prefix, (metric, rtype, nh) in want.items():
+        g = got[prefix]
+        assert (g[0], g[1]) == (metric, rtype), (prefix, g)
+        assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
