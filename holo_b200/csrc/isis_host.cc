@@ -482,26 +482,166 @@ int local_nexthops(const hspf_isis_flat &f, const hl_isis_instance *in, uint8_t 
 
 }  // namespace
 
+namespace {
+
+// One topology of compute_spf's route path: flatten with the topology's edge rules and find
+// the root.  Returns HSPF_OK and `have_root`.
+int topology_flat(const hl_isis_instance *in, uint8_t mt_id, hspf_isis_flat &f, uint32_t &root, bool &have_root) {
+    hl_isis_level l = in->lvl;
+    l.mt_id = mt_id;
+    l.metric_mode = HL_ISIS_MODE_NORMAL;
+    int rc = flatten(&l, f);
+    if (rc) return rc;
+    const hl_lan_id root_id = (hl_lan_id)(in->system_id << 8);
+    auto it = f.index.find(root_id);
+    have_root = it != f.index.end();      // root owns no LSP: nothing reachable, no routes
+    root = have_root ? it->second : 0;
+    return HSPF_OK;
+}
+
+// compute_routes (spf.rs:838-941) for one topology, over that topology's SPT planes
+// (vertex order of `f`).
+int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t mt_id, uint32_t root,
+                    const uint32_t *dist_p, const uint16_t *hops_p, std::map<NetKey, RouteE> &rib) {
+    const hl_isis_level &l0 = in->lvl;
+    const bool std_en = l0.metric_type == HL_ISIS_METRIC_STANDARD || l0.metric_type == HL_ISIS_METRIC_BOTH;
+    const bool wide_en = l0.metric_type == HL_ISIS_METRIC_WIDE || l0.metric_type == HL_ISIS_METRIC_BOTH;
+    const uint32_t V = (uint32_t)f.ids.size();
+    const uint32_t *dist = dist_p;
+    const uint16_t *hops = hops_p;
+    int rc = HSPF_OK;
+        std::vector<std::vector<LNh>> vnh;
+        rc = local_nexthops(f, in, mt_id, root, dist, hops, vnh);
+        if (rc) return rc;
+
+        // ---- compute_routes over the SPT in id_tree (= vertex index) order -------------
+        bool attached = false;
+        for (uint32_t i = 0; i < in->n_adjs; ++i) {
+            const auto &a = in->adjs[i];
+            if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && a.up && (a.level_usage & 2) && a.area_disjoint) attached = true;
+        }
+        const bool ipv4_enabled = l0.ipv4_enabled && mt_id == HL_ISIS_MT_STANDARD;
+        const bool ipv6_enabled = l0.ipv6_enabled && (mt_id == HL_ISIS_MT_STANDARD ? !in->mt_ipv6_enabled : true);
+        // fragments per LAN id in LspId order
+        std::vector<uint32_t> order(l0.n_lsps);
+        for (uint32_t i = 0; i < l0.n_lsps; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const auto &x = l0.lsps[a], &y = l0.lsps[b];
+            return x.lan_id != y.lan_id ? x.lan_id < y.lan_id : x.fragment < y.fragment;
+        });
+        std::unordered_map<uint64_t, std::vector<uint32_t>> frags;
+        for (uint32_t i : order) frags[l0.lsps[i].lan_id].push_back(i);
+        for (uint32_t v = 0; v < V; ++v) {
+            if (dist[v] == HSPF_DIST_INF) continue;
+            const auto &fr = frags[f.ids[v]];
+            const hl_isis_lsp *z = nullptr;
+            for (uint32_t i : fr)
+                if (l0.lsps[i].fragment == 0) { if (l0.lsps[i].seqno && l0.lsps[i].rem_lifetime) z = &l0.lsps[i]; break; }
+            if (!z) continue;
+            const bool att_bit = !in->att_ignore &&
+                                 (mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_ATT) : (z->flags & HL_LSPF_MT_IPV6_ATT));
+            auto add = [&](const hl_ip_addr &prefix, uint8_t len, uint32_t nmetric, bool external) {
+                auto build = [&](std::map<hl_ip_addr, RNh, IpLess> &m) {
+                    for (const LNh &nh : vnh[v]) {
+                        hl_ip_addr addr{};
+                        if (!prefix.is_v6) {
+                            if (!nh.has4) continue;
+                            addr.bytes[0] = (uint8_t)(nh.ipv4 >> 24); addr.bytes[1] = (uint8_t)(nh.ipv4 >> 16);
+                            addr.bytes[2] = (uint8_t)(nh.ipv4 >> 8); addr.bytes[3] = (uint8_t)nh.ipv4;
+                        } else {
+                            if (!nh.has6) continue;
+                            addr = nh.ipv6; addr.is_v6 = 1;
+                        }
+                        m[addr] = RNh{nh.sysid, nh.iface, addr};
+                    }
+                };
+                const uint32_t metric = dist[v] + nmetric;
+                NetKey key{prefix, len};
+                auto rit = rib.find(key);
+                RouteE *route;
+                if (rit == rib.end() || metric < rit->second.metric) {
+                    RouteE r{};
+                    r.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
+                    r.type = in->level == 1 ? (external ? HL_ISIS_RT_L1_EXT : HL_ISIS_RT_L1_INTRA)
+                                            : (external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
+                    r.metric = metric;
+                    build(r.nh);
+                    if (rit == rib.end()) route = &rib.emplace(key, std::move(r)).first->second;
+                    else { rit->second = std::move(r); route = &rit->second; }
+                } else if (metric == rit->second.metric) {
+                    build(rit->second.nh);
+                    route = &rit->second;
+                } else {
+                    return;
+                }
+                while (route->nh.size() > in->max_paths) route->nh.erase(std::prev(route->nh.end()));
+            };
+            for (uint32_t i : fr) {
+                const auto &lsp = l0.lsps[i];
+                if (!lsp.seqno || !lsp.rem_lifetime) continue;
+                if (att_bit && in->level == 1 && (in->level_type == 1 || !attached)) {
+                    if (ipv4_enabled) add(hl_ip_addr{}, 0, 0, false);
+                    if (ipv6_enabled) { hl_ip_addr z6{}; z6.is_v6 = 1; add(z6, 0, 0, false); }
+                }
+                const hl_isis_ipreach *ip = l0.ipreaches + lsp.ipreach_off;
+                if (mt_id == HL_ISIS_MT_STANDARD && ipv4_enabled) {
+                    if (std_en) {
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_INTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, false);
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_EXTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, true);
+                    }
+                    if (wide_en)
+                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
+                            if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= kMaxWide)
+                                add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                }
+                if (ipv6_enabled)
+                    for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
+                        const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
+                                                                   : (ip[k].kind == HL_ISIS_IP_V6);
+                        if (take) add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                    }
+            }
+        }
+    return HSPF_OK;
+}
+
+int emit_rib(std::map<NetKey, RouteE> &rib, hl_isis_rib *out) {
+    uint32_t need_h = 0;
+    for (auto &kv : rib) need_h += (uint32_t)kv.second.nh.size();
+    out->n_routes = (uint32_t)rib.size(); out->n_nexthops = need_h;
+    if (out->n_routes > out->routes_cap || need_h > out->nexthops_cap) return HSPF_E_NOMEM;
+    uint32_t i = 0, h = 0;
+    for (auto &kv : rib) {
+        hl_isis_route o{};
+        o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.type;
+        o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nh.size();
+        for (auto &nk : kv.second.nh) {
+            hl_isis_nexthop x{};
+            x.system_id = nk.second.sysid; x.iface = nk.second.iface; x.addr = nk.second.addr;
+            out->nexthops[h++] = x;
+        }
+        out->routes[i++] = o;
+    }
+    return HSPF_OK;
+}
+
+}  // namespace
+
 extern "C" int hspf_isis_compute_routes(hspf_ctx *ctx, const hl_isis_instance *in, hl_isis_rib *out) {
     if (!ctx || !in || !out) return HSPF_E_INVAL;
     try {
-        const hl_isis_level &l0 = in->lvl;
-        const bool std_en = l0.metric_type == HL_ISIS_METRIC_STANDARD || l0.metric_type == HL_ISIS_METRIC_BOTH;
-        const bool wide_en = l0.metric_type == HL_ISIS_METRIC_WIDE || l0.metric_type == HL_ISIS_METRIC_BOTH;
         std::map<NetKey, RouteE> rib;
         const uint8_t mts[2] = {HL_ISIS_MT_STANDARD, HL_ISIS_MT_IPV6};
         for (uint8_t mt_id : mts) {
             if (mt_id == HL_ISIS_MT_IPV6 && !in->mt_ipv6_enabled) continue;
-            hl_isis_level l = l0;
-            l.mt_id = mt_id;
-            l.metric_mode = HL_ISIS_MODE_NORMAL;
             hspf_isis_flat f;
-            int rc = flatten(&l, f);
+            uint32_t root = 0;
+            bool have_root = false;
+            int rc = topology_flat(in, mt_id, f, root, have_root);
             if (rc) return rc;
-            const hl_lan_id root_id = (hl_lan_id)(in->system_id << 8);
-            auto it = f.index.find(root_id);
-            if (it == f.index.end()) continue;      // root owns no LSP: nothing reachable, no routes
-            const uint32_t root = it->second;
+            if (!have_root) continue;
             const uint32_t V = (uint32_t)f.ids.size();
             hspf_csr csr;
             fill_csr(f, &csr);
@@ -519,117 +659,38 @@ extern "C" int hspf_isis_compute_routes(hspf_ctx *ctx, const hl_isis_instance *i
             hspf_graph_free(ctx, g);
             if (rc == HSPF_E_JOB_STATUS && !(status & ~HSPF_JS_TOO_MANY_ATOMS)) rc = HSPF_OK;
             if (rc) return rc;
-            std::vector<std::vector<LNh>> vnh;
-            rc = local_nexthops(f, in, mt_id, root, dist.data(), hops.data(), vnh);
+            rc = topology_routes(in, f, mt_id, root, dist.data(), hops.data(), rib);
             if (rc) return rc;
+        }
+        return emit_rib(rib, out);
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
 
-            // ---- compute_routes over the SPT in id_tree (= vertex index) order -------------
-            bool attached = false;
-            for (uint32_t i = 0; i < in->n_adjs; ++i) {
-                const auto &a = in->adjs[i];
-                if ((mt_id == HL_ISIS_MT_STANDARD ? a.topo_std : a.topo_ipv6) && a.up && (a.level_usage & 2) && a.area_disjoint) attached = true;
-            }
-            const bool ipv4_enabled = l0.ipv4_enabled && mt_id == HL_ISIS_MT_STANDARD;
-            const bool ipv6_enabled = l0.ipv6_enabled && (mt_id == HL_ISIS_MT_STANDARD ? !in->mt_ipv6_enabled : true);
-            // fragments per LAN id in LspId order
-            std::vector<uint32_t> order(l0.n_lsps);
-            for (uint32_t i = 0; i < l0.n_lsps; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-                const auto &x = l0.lsps[a], &y = l0.lsps[b];
-                return x.lan_id != y.lan_id ? x.lan_id < y.lan_id : x.fragment < y.fragment;
-            });
-            std::unordered_map<uint64_t, std::vector<uint32_t>> frags;
-            for (uint32_t i : order) frags[l0.lsps[i].lan_id].push_back(i);
-            for (uint32_t v = 0; v < V; ++v) {
-                if (dist[v] == HSPF_DIST_INF) continue;
-                const auto &fr = frags[f.ids[v]];
-                const hl_isis_lsp *z = nullptr;
-                for (uint32_t i : fr)
-                    if (l0.lsps[i].fragment == 0) { if (l0.lsps[i].seqno && l0.lsps[i].rem_lifetime) z = &l0.lsps[i]; break; }
-                if (!z) continue;
-                const bool att_bit = !in->att_ignore &&
-                                     (mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_ATT) : (z->flags & HL_LSPF_MT_IPV6_ATT));
-                auto add = [&](const hl_ip_addr &prefix, uint8_t len, uint32_t nmetric, bool external) {
-                    auto build = [&](std::map<hl_ip_addr, RNh, IpLess> &m) {
-                        for (const LNh &nh : vnh[v]) {
-                            hl_ip_addr addr{};
-                            if (!prefix.is_v6) {
-                                if (!nh.has4) continue;
-                                addr.bytes[0] = (uint8_t)(nh.ipv4 >> 24); addr.bytes[1] = (uint8_t)(nh.ipv4 >> 16);
-                                addr.bytes[2] = (uint8_t)(nh.ipv4 >> 8); addr.bytes[3] = (uint8_t)nh.ipv4;
-                            } else {
-                                if (!nh.has6) continue;
-                                addr = nh.ipv6; addr.is_v6 = 1;
-                            }
-                            m[addr] = RNh{nh.sysid, nh.iface, addr};
-                        }
-                    };
-                    const uint32_t metric = dist[v] + nmetric;
-                    NetKey key{prefix, len};
-                    auto rit = rib.find(key);
-                    RouteE *route;
-                    if (rit == rib.end() || metric < rit->second.metric) {
-                        RouteE r{};
-                        r.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
-                        r.type = in->level == 1 ? (external ? HL_ISIS_RT_L1_EXT : HL_ISIS_RT_L1_INTRA)
-                                                : (external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
-                        r.metric = metric;
-                        build(r.nh);
-                        if (rit == rib.end()) route = &rib.emplace(key, std::move(r)).first->second;
-                        else { rit->second = std::move(r); route = &rit->second; }
-                    } else if (metric == rit->second.metric) {
-                        build(rit->second.nh);
-                        route = &rit->second;
-                    } else {
-                        return;
-                    }
-                    while (route->nh.size() > in->max_paths) route->nh.erase(std::prev(route->nh.end()));
-                };
-                for (uint32_t i : fr) {
-                    const auto &lsp = l0.lsps[i];
-                    if (!lsp.seqno || !lsp.rem_lifetime) continue;
-                    if (att_bit && in->level == 1 && (in->level_type == 1 || !attached)) {
-                        if (ipv4_enabled) add(hl_ip_addr{}, 0, 0, false);
-                        if (ipv6_enabled) { hl_ip_addr z6{}; z6.is_v6 = 1; add(z6, 0, 0, false); }
-                    }
-                    const hl_isis_ipreach *ip = l0.ipreaches + lsp.ipreach_off;
-                    if (mt_id == HL_ISIS_MT_STANDARD && ipv4_enabled) {
-                        if (std_en) {
-                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
-                                if (ip[k].kind == HL_ISIS_IP_V4_INTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, false);
-                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
-                                if (ip[k].kind == HL_ISIS_IP_V4_EXTERNAL) add(ip[k].prefix, ip[k].len, ip[k].metric, true);
-                        }
-                        if (wide_en)
-                            for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
-                                if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= kMaxWide)
-                                    add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
-                    }
-                    if (ipv6_enabled)
-                        for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
-                            const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
-                                                                       : (ip[k].kind == HL_ISIS_IP_V6);
-                            if (take) add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
-                        }
-                }
-            }
+/* The same route stage over SPT planes the caller already has (e.g. one job of a what-if batch
+ * run through hspf_isis_flatten + hspf_run_batch): `dist_*` / `hops_*` are indexed by the vertex
+ * order of hspf_isis_flatten for that topology (lvl.mt_id = HL_ISIS_MT_STANDARD / HL_ISIS_MT_IPV6,
+ * lvl.metric_mode = HL_ISIS_MODE_NORMAL); the IPv6-topology planes are ignored unless
+ * inst->mt_ipv6_enabled.  Host only. */
+extern "C" int hspf_isis_routes_from_planes(const hl_isis_instance *in, const uint32_t *dist_std, const uint16_t *hops_std,
+                                            const uint32_t *dist_mt6, const uint16_t *hops_mt6, hl_isis_rib *out) {
+    if (!in || !out) return HSPF_E_INVAL;
+    try {
+        std::map<NetKey, RouteE> rib;
+        const uint8_t mts[2] = {HL_ISIS_MT_STANDARD, HL_ISIS_MT_IPV6};
+        for (uint8_t mt_id : mts) {
+            if (mt_id == HL_ISIS_MT_IPV6 && !in->mt_ipv6_enabled) continue;
+            const uint32_t *dist = mt_id == HL_ISIS_MT_STANDARD ? dist_std : dist_mt6;
+            const uint16_t *hops = mt_id == HL_ISIS_MT_STANDARD ? hops_std : hops_mt6;
+            hspf_isis_flat f;
+            uint32_t root = 0;
+            bool have_root = false;
+            int rc = topology_flat(in, mt_id, f, root, have_root);
+            if (rc) return rc;
+            if (!have_root) continue;
+            if (!dist || !hops) return HSPF_E_INVAL;
+            rc = topology_routes(in, f, mt_id, root, dist, hops, rib);
+            if (rc) return rc;
         }
-        uint32_t need_h = 0;
-        for (auto &kv : rib) need_h += (uint32_t)kv.second.nh.size();
-        out->n_routes = (uint32_t)rib.size(); out->n_nexthops = need_h;
-        if (out->n_routes > out->routes_cap || need_h > out->nexthops_cap) return HSPF_E_NOMEM;
-        uint32_t i = 0, h = 0;
-        for (auto &kv : rib) {
-            hl_isis_route o{};
-            o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.type;
-            o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nh.size();
-            for (auto &nk : kv.second.nh) {
-                hl_isis_nexthop x{};
-                x.system_id = nk.second.sysid; x.iface = nk.second.iface; x.addr = nk.second.addr;
-                out->nexthops[h++] = x;
-            }
-            out->routes[i++] = o;
-        }
-        return HSPF_OK;
+        return emit_rib(rib, out);
     } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
 }

@@ -298,7 +298,7 @@ class IsisRib:
                 for x in self.nexthops[int(rec["nh_off"]): int(rec["nh_off"]) + int(rec["n_nh"])]]
 
 
-def _call_rib(fn, inst: dict, prefix_args=()):
+def _call_rib(fn, inst: dict, prefix_args=(), tail_args=()):
     s = instance_struct(inst)
     caps = [len(inst["level"].ipreaches) + 8, 16 * (len(inst["level"].ipreaches) + 8)]
     for _ in range(2):
@@ -307,7 +307,7 @@ def _call_rib(fn, inst: dict, prefix_args=()):
         r = RibStruct()
         r.routes_cap, r.routes = caps[0], routes.ctypes.data
         r.nexthops_cap, r.nexthops = caps[1], nhs.ctypes.data
-        rc = fn(*prefix_args, C.byref(s), C.byref(r))
+        rc = fn(*prefix_args, C.byref(s), *tail_args, C.byref(r))
         if rc == capi.HSPF_E_NOMEM:
             caps = [max(caps[0], r.n_routes), max(caps[1], r.n_nexthops)]
             continue
@@ -322,4 +322,33 @@ def compute_routes(ctx: capi.Context, inst: dict) -> IsisRib:
     res = _call_rib(lib.hspf_isis_compute_routes, inst, (ctx.handle,))
     if res.rc != capi.HSPF_OK:
         raise capi.HspfError(res.rc, ctx.last_error())
+    return res
+
+
+def routes_from_planes(inst: dict, spf) -> IsisRib:
+    """hspf_isis_routes_from_planes: the route stage over SPT planes supplied by `spf(csr, root_vertex)
+    -> (dist u32[V], hops u16[V])`, called once per enabled topology on that topology's flattened
+    CSR (host only; the planes may come from hspf_run_batch or, in tests, from the oracle)."""
+    import copy
+    lib = capi.load_library()
+    u32p, u16p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)
+    lib.hspf_isis_routes_from_planes.argtypes = [C.POINTER(InstanceStruct), u32p, u16p, u32p, u16p, C.POINTER(RibStruct)]
+    planes = {}
+    for mt in (MT_STANDARD, MT_IPV6):
+        if mt == MT_IPV6 and not inst.get("mt_ipv6"):
+            continue
+        lv = copy.copy(inst["level"])
+        lv.mt_id, lv.metric_mode = mt, MODE_NORMAL
+        f = Flat(lv)
+        root = f.vertex(inst["system_id"] << 8)
+        if root == 0xFFFFFFFF:
+            continue
+        d, h = spf(f.csr, root)
+        planes[mt] = (np.ascontiguousarray(d, np.uint32), np.ascontiguousarray(h, np.uint16))
+    ptr = lambda a, ty: a.ctypes.data_as(ty) if a is not None else C.cast(None, ty)
+    ds, hs = planes.get(MT_STANDARD, (None, None))
+    d6, h6 = planes.get(MT_IPV6, (None, None))
+    res = _call_rib(lib.hspf_isis_routes_from_planes, inst, (), tail_args=(ptr(ds, u32p), ptr(hs, u16p), ptr(d6, u32p), ptr(h6, u16p)))
+    if res.rc != capi.HSPF_OK:
+        raise capi.HspfError(res.rc, "hspf_isis_routes_from_planes failed")
     return res

@@ -125,6 +125,15 @@ int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root
  * compute_routes (spf.rs:838-941) into one RIB (prefix order). */
 int hspf_isis_compute_routes(hspf_ctx *ctx, const hl_isis_instance *inst, hl_isis_rib *out);
 
+/* The same route stage (local next-hop resolution + compute_routes, holo-isis/src/spf.rs:838-1002)
+ * over SPT planes the caller already has — e.g. one job of a what-if batch run through
+ * hspf_isis_flatten + hspf_run_batch.  `dist_*` / `hops_*` are indexed by the vertex order of
+ * hspf_isis_flatten for that topology (lvl.mt_id = HL_ISIS_MT_STANDARD / HL_ISIS_MT_IPV6,
+ * lvl.metric_mode = HL_ISIS_MODE_NORMAL) with the local system as root; the IPv6-topology
+ * planes are read only when inst->mt_ipv6_enabled.  Host only. */
+int hspf_isis_routes_from_planes(const hl_isis_instance *inst, const uint32_t *dist_std, const uint16_t *hops_std,
+                                 const uint32_t *dist_mt6, const uint16_t *hops_mt6, hl_isis_rib *out);
+
 /* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
  * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
  * foreign binding verify its struct layouts at load time. */

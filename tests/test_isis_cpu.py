@@ -68,3 +68,49 @@ def test_narrow_metric_path_limit():
     root = f.vertex(isis.sysid(0) << 8)
     c = pyoracle.csr_spf(f.csr, root, vec_mode=1)
     same_spt(f.spt_from_planes(root, c["dist"], c["hops"]), ref)
+
+
+# ---- route stage on the CPU: hspf_isis_routes_from_planes with the oracle's planes -----------
+import golden_util as gu  # noqa: E402
+from isis_synth import synth_instance  # noqa: E402
+
+SNAPS = gu.load_isis()
+
+
+def oracle_planes(csr, root):
+    c = pyoracle.csr_spf(csr, root, vec_mode=1, nh_words=4)
+    return c["dist"], c["hops"]
+
+
+def same_rib(a, b):
+    assert len(a.routes) == len(b.routes) and len(a.nexthops) == len(b.nexthops)
+    assert a.routes.tobytes() == b.routes.tobytes()
+    assert a.nexthops.tobytes() == b.nexthops.tobytes()
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_route_stage_from_planes_on_reference_goldens(snap):
+    """The product's route stage (local next hops + compute_routes, isis_host.cc) fed with the
+    oracle's SPT planes: bit-identical to the oracle's route path and equal to the golden
+    local-rib of every IS-IS conformance snapshot (CPU twin of the GPU test)."""
+    from holo_b200 import ospfv3
+    for level in snap["levels"]:
+        inst = gu.isis_instance_image(snap, level)
+        rib = isis.routes_from_planes(inst, oracle_planes)
+        same_rib(rib, pyoracle.isis_compute_routes(inst))
+        got = {f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}":
+               (int(r["metric"]), sorted((inst["ifnames"][i], a) for (i, a, _s) in rib.nh(r))) for r in rib.routes}
+        for r in snap["local_rib"]:
+            if r["level"] == level["level"]:
+                assert got[r["prefix"]] == (r["metric"], sorted((a, b) for a, b in r["nexthops"]))
+
+
+@pytest.mark.parametrize("seed,kw,root,mtype,frag", [
+    (3, dict(cost_lo=1, cost_hi=30, lan_fraction=0.15), 0, isis.METRIC_WIDE, 3),
+    (4, dict(cost_choices=[10], lan_fraction=0.2), 7, isis.METRIC_WIDE, 0),
+    (5, dict(cost_lo=1, cost_hi=20), 11, isis.METRIC_BOTH, 2),
+])
+def test_route_stage_from_planes_synthetic(seed, kw, root, mtype, frag):
+    t = synth.random_topology(300, 1300, synth.SEED_BASE + seed, **kw)
+    inst = synth_instance(t, root, mtype, frag)
+    same_rib(isis.routes_from_planes(inst, oracle_planes), pyoracle.isis_compute_routes(inst))
