@@ -381,8 +381,75 @@ struct NetKey {
         return c ? c < 0 : len < o.len;
     }
 };
-struct RNh { uint64_t sysid; uint32_t iface; hl_ip_addr addr; };
-struct RouteE { uint8_t type, flags; uint32_t metric; std::map<hl_ip_addr, RNh, IpLess> nh; };
+struct RNh { uint64_t sysid; uint32_t iface; hl_ip_addr addr; bool has_label = false; uint32_t label = 0; };
+struct PrefixSid { bool present = false; uint8_t flags = 0; bool is_label = false; uint32_t value = 0; };
+struct RouteE {
+    uint8_t type, flags; uint32_t metric; std::map<hl_ip_addr, RNh, IpLess> nh;
+    PrefixSid psid;                               // Route.prefix_sid (route.rs:100)
+    bool has_label = false; uint32_t label = 0;   // Route.sr_label
+};
+
+// SR view of one level's LSDB (holo-isis/src/sr.rs): per system the label blocks and address
+// family flags of its first valid SR-Capabilities sub-TLV, per LAN id whether a valid fragment
+// lists SPF in an SR-Algorithm sub-TLV.  Built once per route computation.
+struct SrView {
+    struct Cap { const hl_srgb *blocks; uint32_t n; uint8_t flags; };
+    std::unordered_map<uint64_t, Cap> cap;          // system id -> capabilities
+    std::unordered_map<uint64_t, bool> algo_spf;    // LAN id -> SR-Algorithm contains SPF
+    explicit SrView(const hl_isis_level &l) {
+        // LspId order: (lan_id, fragment); the first valid LSP with the sub-TLV wins
+        std::vector<uint32_t> order(l.n_lsps);
+        for (uint32_t i = 0; i < l.n_lsps; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const auto &x = l.lsps[a], &y = l.lsps[b];
+            return x.lan_id != y.lan_id ? x.lan_id < y.lan_id : x.fragment < y.fragment;
+        });
+        for (uint32_t i : order) {
+            const auto &p = l.lsps[i];
+            if (!p.seqno || !p.rem_lifetime) continue;
+            if (p.sr_flags & HL_LSP_SR_ALGO_SPF) algo_spf[p.lan_id] = true;
+            if ((p.sr_flags & HL_LSP_SR_HAS_CAP) && !cap.count(p.lan_id >> 8))
+                cap.emplace(p.lan_id >> 8, Cap{l.srgbs + p.srgb_off, p.n_srgb, p.sr_flags});
+        }
+    }
+    // index_to_label (sr.rs:268-300)
+    static bool label_of(const Cap &c, uint32_t index, uint32_t &label) {
+        for (uint32_t i = 0; i < c.n; ++i) {
+            if (c.blocks[i].first_is_index) continue;
+            if (index >= c.blocks[i].range) { index -= c.blocks[i].range; continue; }
+            label = c.blocks[i].first + index;
+            return true;
+        }
+        return false;
+    }
+    // prefix_sid_update (sr.rs:33-99) with prefix_sid_input_label / prefix_sid_output_label
+    void update(RouteE &r, uint64_t own_system, uint64_t adv_lan_id, bool v6, bool local, bool last_hop) const {
+        const PrefixSid &ps = r.psid;
+        auto al = algo_spf.find(adv_lan_id);
+        if (al == algo_spf.end()) return;                 // remote node does not run SPF for SR
+        const bool p_flag = ps.flags & HL_ISIS_PSID_P, e_flag = ps.flags & HL_ISIS_PSID_E;
+        if (local && (!p_flag || e_flag)) {
+            r.has_label = false;
+        } else if (ps.is_label) {
+            r.has_label = true; r.label = ps.value;
+        } else {
+            auto own = cap.find(own_system);
+            uint32_t lab;
+            if (own != cap.end() && label_of(own->second, ps.value, lab)) { r.has_label = true; r.label = lab; }
+        }
+        for (auto &kv : r.nh) {
+            RNh &nh = kv.second;
+            if (last_hop && !p_flag) { nh.has_label = true; nh.label = 3; continue; }                 // implicit null
+            auto c = cap.find(nh.sysid);
+            if (c == cap.end()) continue;
+            if (!(c->second.flags & (v6 ? HL_LSP_SR_CAP_V : HL_LSP_SR_CAP_I))) continue;
+            if (last_hop && e_flag) { nh.has_label = true; nh.label = v6 ? 2u : 0u; continue; }      // explicit null
+            uint32_t lab;
+            if (ps.is_label) { nh.has_label = true; nh.label = last_hop ? ps.value : 3u; }
+            else if (label_of(c->second, ps.value, lab)) { nh.has_label = true; nh.label = lab; }
+        }
+    }
+};
 
 // Next-hop Vecs of a `local = true` SPT for every SPT vertex (indexed by vertex).
 int local_nexthops(const hspf_isis_flat &f, const hl_isis_instance *in, uint8_t mt_id, uint32_t root,
@@ -510,6 +577,7 @@ int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t
     const uint32_t *dist = dist_p;
     const uint16_t *hops = hops_p;
     int rc = HSPF_OK;
+    const SrView sr(l0);
         std::vector<std::vector<LNh>> vnh;
         rc = local_nexthops(f, in, mt_id, root, dist, hops, vnh);
         if (rc) return rc;
@@ -540,7 +608,7 @@ int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t
             if (!z) continue;
             const bool att_bit = !in->att_ignore &&
                                  (mt_id == HL_ISIS_MT_STANDARD ? (z->flags & HL_LSPF_ATT) : (z->flags & HL_LSPF_MT_IPV6_ATT));
-            auto add = [&](const hl_ip_addr &prefix, uint8_t len, uint32_t nmetric, bool external) {
+            auto add = [&](const hl_ip_addr &prefix, uint8_t len, uint32_t nmetric, bool external, const hl_isis_ipreach *src = nullptr) {
                 auto build = [&](std::map<hl_ip_addr, RNh, IpLess> &m) {
                     for (const LNh &nh : vnh[v]) {
                         hl_ip_addr addr{};
@@ -566,6 +634,7 @@ int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t
                                             : (external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
                     r.metric = metric;
                     build(r.nh);
+                    if (src && src->has_psid) r.psid = PrefixSid{true, src->psid_flags, src->psid_is_label != 0, src->psid_value};
                     if (rit == rib.end()) route = &rib.emplace(key, std::move(r)).first->second;
                     else { rit->second = std::move(r); route = &rit->second; }
                 } else if (metric == rit->second.metric) {
@@ -575,6 +644,8 @@ int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t
                     return;
                 }
                 while (route->nh.size() > in->max_paths) route->nh.erase(std::prev(route->nh.end()));
+                if (in->sr_enabled && route->psid.present)      // spf.rs:923-939
+                    sr.update(*route, in->system_id, f.ids[v], prefix.is_v6 != 0, hops[v] == 0, hops[v] == 1);
             };
             for (uint32_t i : fr) {
                 const auto &lsp = l0.lsps[i];
@@ -594,13 +665,13 @@ int topology_routes(const hl_isis_instance *in, const hspf_isis_flat &f, uint8_t
                     if (wide_en)
                         for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
                             if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= kMaxWide)
-                                add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                                add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external, &ip[k]);
                 }
                 if (ipv6_enabled)
                     for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
                         const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
                                                                    : (ip[k].kind == HL_ISIS_IP_V6);
-                        if (take) add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external);
+                        if (take) add(ip[k].prefix, ip[k].len, ip[k].metric, ip[k].external, &ip[k]);
                     }
             }
         }
@@ -617,9 +688,11 @@ int emit_rib(std::map<NetKey, RouteE> &rib, hl_isis_rib *out) {
         hl_isis_route o{};
         o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.type;
         o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nh.size();
+        o.has_sr_label = kv.second.has_label ? 1 : 0; o.sr_label = kv.second.has_label ? kv.second.label : 0;
         for (auto &nk : kv.second.nh) {
             hl_isis_nexthop x{};
             x.system_id = nk.second.sysid; x.iface = nk.second.iface; x.addr = nk.second.addr;
+            x.has_label = nk.second.has_label ? 1 : 0; x.sr_label = nk.second.has_label ? nk.second.label : 0;
             out->nexthops[h++] = x;
         }
         out->routes[i++] = o;

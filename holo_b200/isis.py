@@ -19,19 +19,37 @@ MODE_NORMAL, MODE_HOPCOUNT = 0, 1
 
 REACH_DT = np.dtype([("neighbor", "<u8"), ("metric", "<u4"), ("mt_id", "<u2"), ("kind", "u1"), ("_pad", "u1")], align=True)
 LSP_DT = np.dtype([("lan_id", "<u8"), ("seqno", "<u4"), ("rem_lifetime", "<u2"), ("fragment", "u1"), ("flags", "u1"),
-                   ("reach_off", "<u4"), ("n_reach", "<u4"), ("ipreach_off", "<u4"), ("n_ipreach", "<u4")], align=True)
+                   ("reach_off", "<u4"), ("n_reach", "<u4"), ("ipreach_off", "<u4"), ("n_ipreach", "<u4"),
+                   ("srgb_off", "<u4"), ("n_srgb", "<u2"), ("sr_flags", "u1"), ("_pad2", "u1")], align=True)
+LSP_SR_HAS_CAP, LSP_SR_ALGO_SPF, LSP_SR_CAP_V, LSP_SR_CAP_I = 0x01, 0x02, 0x40, 0x80
+PSID_R, PSID_N, PSID_P, PSID_E, PSID_V, PSID_L = 0x80, 0x40, 0x20, 0x10, 0x08, 0x04
+SRGB_DT = np.dtype([("first", "<u4"), ("range", "<u4"), ("first_is_index", "u1"), ("_pad", "u1", (3,))], align=True)
+
+
+def lsp_rec(lan_id, seqno, rem_lifetime, fragment, flags, reach_off, n_reach, ipreach_off=0, n_ipreach=0,
+            srgb_off=0, n_srgb=0, sr_flags=0):
+    """One LSP_DT record as a tuple."""
+    return (lan_id, seqno, rem_lifetime, fragment, flags, reach_off, n_reach, ipreach_off, n_ipreach, srgb_off, n_srgb,
+            sr_flags, 0)
+
+
+def ipreach_rec(prefix, metric, mt_id, plen, kind, external=0, psid=None):
+    """One IPREACH_DT record; psid = (flags, is_label, value) of a Prefix-SID sub-TLV for algorithm SPF."""
+    has, fl, isl, val = (1, psid[0], int(psid[1]), psid[2]) if psid is not None else (0, 0, 0, 0)
+    return (prefix, metric, mt_id, plen, kind, external, has, fl, isl, val)
 IP_DT = np.dtype([("bytes", "u1", (16,)), ("is_v6", "u1"), ("_pad", "u1", (3,))], align=True)
 IPREACH_DT = np.dtype([("prefix", IP_DT), ("metric", "<u4"), ("mt_id", "<u2"), ("len", "u1"), ("kind", "u1"),
-                       ("external", "u1"), ("_pad", "u1", (3,))], align=True)
+                       ("external", "u1"), ("has_psid", "u1"), ("psid_flags", "u1"), ("psid_is_label", "u1"),
+                       ("psid_value", "<u4")], align=True)
 ADJ_DT = np.dtype([("system_id", "<u8"), ("snpa", "u1", (6,)), ("up", "u1"), ("level_usage", "u1"), ("topo_std", "u1"),
                    ("topo_ipv6", "u1"), ("has_ipv4", "u1"), ("has_ipv6", "u1"), ("area_disjoint", "u1"),
                    ("_pad", "u1", (3,)), ("ipv4", "<u4"), ("ipv6", IP_DT)], align=True)
 IFACE_DT = np.dtype([("ifindex", "<u4"), ("metric", "<u4"), ("is_broadcast", "u1"), ("_pad", "u1", (3,)),
                      ("adj_off", "<u4"), ("n_adj", "<u4")], align=True)
-NEXTHOP_DT = np.dtype([("system_id", "<u8"), ("iface", "<u4"), ("_pad", "<u4"), ("addr", IP_DT), ("_pad2", "<u4")],
+NEXTHOP_DT = np.dtype([("system_id", "<u8"), ("iface", "<u4"), ("sr_label", "<u4"), ("addr", IP_DT), ("has_label", "<u4")],
                       align=True)
 ROUTE_DT = np.dtype([("prefix", IP_DT), ("metric", "<u4"), ("len", "u1"), ("route_type", "u1"), ("flags", "u1"),
-                     ("_pad", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+                     ("has_sr_label", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4"), ("sr_label", "<u4")], align=True)
 IP_V4_INTERNAL, IP_V4_EXTERNAL, IP_V4_EXT, IP_V6, IP_MT_V6 = range(5)
 LSPF_ATT, LSPF_MT_IPV6_ATT = 0x20, 0x40
 VERTEX_DT = np.dtype([("lan_id", "<u8"), ("distance", "<u4"), ("hops", "<u2"), ("_pad", "<u2"), ("par_off", "<u4"),
@@ -42,13 +60,13 @@ class LevelStruct(C.Structure):
     _fields_ = [("metric_type", C.c_uint8), ("mt_id", C.c_uint8), ("metric_mode", C.c_uint8),
                 ("ipv4_enabled", C.c_uint8), ("ipv6_enabled", C.c_uint8), ("_pad", C.c_uint8 * 3),
                 ("n_lsps", C.c_uint32), ("lsps", C.c_void_p), ("n_reaches", C.c_uint32), ("reaches", C.c_void_p),
-                ("n_ipreaches", C.c_uint32), ("ipreaches", C.c_void_p)]
+                ("n_ipreaches", C.c_uint32), ("ipreaches", C.c_void_p), ("n_srgbs", C.c_uint32), ("srgbs", C.c_void_p)]
 
 
 class InstanceStruct(C.Structure):
     _fields_ = [("lvl", LevelStruct), ("system_id", C.c_uint64), ("max_paths", C.c_uint16), ("level", C.c_uint8),
                 ("level_type", C.c_uint8), ("att_ignore", C.c_uint8), ("mt_ipv6_enabled", C.c_uint8),
-                ("_pad", C.c_uint8 * 2), ("n_ifaces", C.c_uint32), ("ifaces", C.c_void_p),
+                ("sr_enabled", C.c_uint8), ("_pad", C.c_uint8), ("n_ifaces", C.c_uint32), ("ifaces", C.c_void_p),
                 ("n_adjs", C.c_uint32), ("adjs", C.c_void_p)]
 
 
@@ -80,6 +98,7 @@ class IsisLevel:
     lsps: np.ndarray = field(default_factory=lambda: np.zeros(0, LSP_DT))
     reaches: np.ndarray = field(default_factory=lambda: np.zeros(0, REACH_DT))
     ipreaches: np.ndarray = field(default_factory=lambda: np.zeros(0, IPREACH_DT))
+    srgbs: np.ndarray = field(default_factory=lambda: np.zeros(0, SRGB_DT))
 
     def as_struct(self) -> LevelStruct:
         s = LevelStruct()
@@ -92,6 +111,8 @@ class IsisLevel:
         self.ipreaches = np.ascontiguousarray(self.ipreaches, dtype=IPREACH_DT)
         s.n_ipreaches = len(self.ipreaches)
         s.ipreaches = self.ipreaches.ctypes.data if len(self.ipreaches) else None
+        self.srgbs = np.ascontiguousarray(self.srgbs, dtype=SRGB_DT)
+        s.n_srgbs, s.srgbs = len(self.srgbs), (self.srgbs.ctypes.data if len(self.srgbs) else None)
         return s
 
 
@@ -245,7 +266,7 @@ def synth_level(t: Topology, metric_type: int = METRIC_WIDE, mt_id: int = MT_STA
             chunks = [entries[i:i + max_reach_per_fragment] for i in range(0, len(entries), max_reach_per_fragment)] or [[]]
         for frag, ch in enumerate(chunks):
             rr = [x for (nbr, m) in ch for x in add_reach(nbr, m)]
-            lsps.append((lan_id, 1, 1200, frag, flags if frag == 0 else 0, len(reaches), len(rr), 0, 0))
+            lsps.append(lsp_rec(lan_id, 1, 1200, frag, flags if frag == 0 else 0, len(reaches), len(rr)))
             reaches.extend(rr)
 
     for i in range(R):
@@ -279,6 +300,7 @@ def instance_struct(inst: dict) -> InstanceStruct:
     s.system_id, s.max_paths = inst["system_id"], inst["max_paths"]
     s.level, s.level_type = inst["level_no"], inst["level_type"]
     s.att_ignore, s.mt_ipv6_enabled = inst["att_ignore"], inst["mt_ipv6"]
+    s.sr_enabled = int(inst.get("sr_enabled", 0))
     inst["ifaces"] = np.ascontiguousarray(inst["ifaces"], dtype=IFACE_DT)
     inst["adjs"] = np.ascontiguousarray(inst["adjs"], dtype=ADJ_DT)
     s.n_ifaces, s.ifaces = len(inst["ifaces"]), (inst["ifaces"].ctypes.data if len(inst["ifaces"]) else None)

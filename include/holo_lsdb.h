@@ -537,7 +537,18 @@ typedef struct hl_isis_lsp {
     uint32_t  n_reach;
     uint32_t  ipreach_off; /* into ipreaches[] (route stage only) */
     uint32_t  n_ipreach;
+    uint32_t  srgb_off;    /* into srgbs[]: label blocks of the SR-Capabilities sub-TLV (sr.rs:166-256) */
+    uint16_t  n_srgb;
+    uint8_t   sr_flags;    /* HL_LSP_SR_* */
+    uint8_t   _pad2;
 } hl_isis_lsp;
+
+/* hl_isis_lsp.sr_flags: first SR-Capabilities / SR-Algorithm sub-TLV of the LSP's Router
+ * Capability TLVs (packet/pdu.rs:1785-1797) */
+#define HL_LSP_SR_HAS_CAP   0x01u
+#define HL_LSP_SR_ALGO_SPF  0x02u  /* an SR-Algorithm sub-TLV is present and lists SPF          */
+#define HL_LSP_SR_CAP_V     0x40u  /* SrCapabilitiesFlags::V (MPLS IPv6)                        */
+#define HL_LSP_SR_CAP_I     0x80u  /* SrCapabilitiesFlags::I (MPLS IPv4)                        */
 
 /* IP reachability entry of an LSP fragment, TLV order kept within each kind
  * (vertex_networks, holo-isis/src/spf.rs:1141-1281). */
@@ -553,8 +564,18 @@ typedef struct hl_isis_ipreach {
     uint8_t  len;
     uint8_t  kind;
     uint8_t  external;     /* TLV 135: prefix-attr X flag; TLV 236/237: external bit */
-    uint8_t  _pad[3];
+    uint8_t  has_psid;     /* Prefix-SID sub-TLV for algorithm SPF (spf.rs:1241-1269); TLV 135/236/237 */
+    uint8_t  psid_flags;   /* PrefixSidFlags: HL_ISIS_PSID_* (packet/subtlvs/prefix.rs:56-63) */
+    uint8_t  psid_is_label;/* Sid::Label (V/L flags) instead of Sid::Index */
+    uint32_t psid_value;
 } hl_isis_ipreach;
+
+#define HL_ISIS_PSID_R 0x80u
+#define HL_ISIS_PSID_N 0x40u
+#define HL_ISIS_PSID_P 0x20u
+#define HL_ISIS_PSID_E 0x10u
+#define HL_ISIS_PSID_V 0x08u
+#define HL_ISIS_PSID_L 0x04u
 
 #define HL_ISIS_METRIC_STANDARD 0u   /* MetricType::Standard (narrow) */
 #define HL_ISIS_METRIC_WIDE     1u
@@ -576,6 +597,7 @@ typedef struct hl_isis_level {
     uint32_t n_lsps;     const hl_isis_lsp *lsps;
     uint32_t n_reaches;  const hl_isis_reach *reaches;
     uint32_t n_ipreaches; const hl_isis_ipreach *ipreaches;   /* may be 0/NULL for SPT-only calls */
+    uint32_t n_srgbs;     const hl_srgb *srgbs;               /* SR label blocks (route stage with SR) */
 } hl_isis_level;
 
 /* SPT vertex (Vertex, spf.rs:76-86) in id_tree order (pseudonodes first).
@@ -629,7 +651,8 @@ typedef struct hl_isis_instance {
     uint8_t  level_type;    /* 1 = L1 only, 2 = L2 only, 3 = L1/L2 */
     uint8_t  att_ignore;
     uint8_t  mt_ipv6_enabled; /* is_topology_enabled(Ipv6Unicast) */
-    uint8_t  _pad[2];
+    uint8_t  sr_enabled;    /* instance.config.sr.enabled: Prefix-SID labels (sr.rs:33-99) */
+    uint8_t  _pad;
     uint32_t n_ifaces;  const hl_isis_iface *ifaces;
     uint32_t n_adjs;    const hl_isis_adj *adjs;
 } hl_isis_instance;
@@ -638,9 +661,9 @@ typedef struct hl_isis_instance {
 typedef struct hl_isis_nexthop {
     uint64_t system_id;
     uint32_t iface;         /* index into ifaces[] */
-    uint32_t _pad;
+    uint32_t sr_label;      /* output label (Nexthop.sr_label) when has_label */
     hl_ip_addr addr;
-    uint32_t _pad2;         /* explicit tail padding: the struct has no hidden bytes */
+    uint32_t has_label;     /* 0/1 (a full word: the struct has no hidden bytes) */
 } hl_isis_nexthop;
 
 #define HL_ISIS_RT_L2_INTRA 0u   /* IsisRouteType order (holo-utils/src/southbound.rs:99-106) */
@@ -655,9 +678,10 @@ typedef struct hl_isis_route {
     uint8_t  len;
     uint8_t  route_type;
     uint8_t  flags;         /* HL_ROUTE_CONNECTED */
-    uint8_t  _pad;
+    uint8_t  has_sr_label;
     uint32_t nh_off;
     uint32_t n_nh;
+    uint32_t sr_label;      /* input label (Route.sr_label) when has_sr_label */
 } hl_isis_route;
 
 typedef struct hl_isis_rib {

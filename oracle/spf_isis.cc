@@ -65,6 +65,15 @@ struct Lsdb {
         while (lo < l->n_lsps && l->lsps[lo].lan_id == id) ++lo;
         return {b, lo};
     }
+    // iter_for_system_id (collections.rs:670-678): every LSP of a system, any pseudonode number
+    std::pair<uint32_t, uint32_t> range_system(uint64_t system_id) const {
+        const hl_lan_id first = (hl_lan_id)(system_id << 8), last = first | 0xFF;
+        uint32_t lo = 0, hi = l->n_lsps;
+        while (lo < hi) { uint32_t m = (lo + hi) / 2; if (l->lsps[m].lan_id < first) lo = m + 1; else hi = m; }
+        uint32_t b = lo;
+        while (lo < l->n_lsps && l->lsps[lo].lan_id <= last) ++lo;
+        return {b, lo};
+    }
     const hl_isis_lsp *zeroth(hl_lan_id id) const {
         auto r = range(id);
         for (uint32_t i = r.first; i < r.second; ++i) {
@@ -223,7 +232,8 @@ extern "C" int oracle_isis_compute_spt(const hl_isis_level *l, uint64_t root_sys
 // resolve_nexthop (holo-isis/src/spf.rs:948-1002), then compute_routes
 // (spf.rs:838-941) with vertex_networks (spf.rs:1141-1281), Route::new /
 // merge_nexthops / build_nexthops (holo-isis/src/route.rs:79-139) and the max_paths cut.
-// SR prefix-SID labels (sr.rs) are not restated.
+// SR Prefix-SID labels: prefix_sid_update and its helpers (holo-isis/src/sr.rs:33-99, 151-300);
+// PARITY UNPINNED — no golden of the reference carries an IS-IS Prefix-SID.
 // =====================================================================================
 namespace {
 
@@ -248,9 +258,80 @@ struct NetKey {
         return len < o.len;
     }
 };
-struct RNexthop { uint64_t system_id; uint32_t iface; hl_ip_addr addr; };
-struct Route { uint8_t route_type; uint32_t metric; uint8_t flags; std::map<IpKey, RNexthop> nexthops; };
-struct VNet { hl_ip_addr prefix; uint8_t len; uint32_t metric; bool external; };
+struct Psid { uint8_t flags; bool is_label; uint32_t value; };   // PrefixSidStlv (packet/subtlvs/prefix.rs:69-73)
+struct RNexthop { uint64_t system_id; uint32_t iface; hl_ip_addr addr; bool has_label = false; uint32_t label = 0; };
+struct Route {
+    uint8_t route_type; uint32_t metric; uint8_t flags; std::map<IpKey, RNexthop> nexthops;
+    bool has_psid = false; Psid psid{};          // Route.prefix_sid
+    bool has_label = false; uint32_t label = 0;  // Route.sr_label
+};
+struct VNet { hl_ip_addr prefix; uint8_t len; uint32_t metric; bool external; bool has_psid = false; Psid psid{}; };
+
+// ---- holo-isis/src/sr.rs:33-99, 151-300 --------------------------------------------------
+// index_to_label (sr.rs:268-300): walk the label blocks; Err = no label
+bool index_to_label(const hl_isis_level &l, const hl_isis_lsp &cap, uint32_t index, uint32_t &label) {
+    for (uint32_t i = 0; i < cap.n_srgb; ++i) {
+        const hl_srgb &b = l.srgbs[cap.srgb_off + i];
+        if (b.first_is_index) continue;               // "SID ranges are rather obscure"
+        if (index >= b.range) { index -= b.range; continue; }
+        label = b.first + index;
+        return true;
+    }
+    return false;
+}
+
+// first valid LSP of the system that carries an SR-Capabilities sub-TLV (sr.rs:176-184, 213-221)
+const hl_isis_lsp *sr_cap_of(const Lsdb &lsdb, uint64_t system_id) {
+    auto r = lsdb.range_system(system_id);
+    for (uint32_t i = r.first; i < r.second; ++i) {
+        const auto &p = lsdb.l->lsps[i];
+        if (p.rem_lifetime == 0 || p.seqno == 0) continue;
+        if (p.sr_flags & HL_LSP_SR_HAS_CAP) return &p;
+    }
+    return nullptr;
+}
+
+// prefix_sid_update (sr.rs:33-99)
+void prefix_sid_update(const hl_isis_instance *in, const Lsdb &lsdb, hl_lan_id adv_rtr, bool is_v6, Route &route,
+                       bool local, bool last_hop) {
+    if (!route.has_psid) return;
+    const Psid &ps = route.psid;
+    // the advertising node must list SPF in an SR-Algorithm sub-TLV (sr.rs:49-62)
+    bool algo = false;
+    auto r = lsdb.range(adv_rtr);
+    for (uint32_t i = r.first; i < r.second && !algo; ++i) {
+        const auto &p = lsdb.l->lsps[i];
+        if (p.rem_lifetime == 0 || p.seqno == 0) continue;
+        if (p.sr_flags & HL_LSP_SR_ALGO_SPF) algo = true;
+    }
+    if (!algo) return;
+    // input label (prefix_sid_input_label, sr.rs:151-195); Err leaves route.sr_label as it is
+    if (local && (!(ps.flags & HL_ISIS_PSID_P) || (ps.flags & HL_ISIS_PSID_E))) {
+        route.has_label = false;                                     // Ok(None)
+    } else if (!ps.is_label) {
+        const hl_isis_lsp *cap = sr_cap_of(lsdb, in->system_id);
+        uint32_t label = 0;
+        if (cap && index_to_label(*lsdb.l, *cap, ps.value, label)) { route.has_label = true; route.label = label; }
+    } else {
+        route.has_label = true; route.label = ps.value;
+    }
+    // output labels (prefix_sid_output_label, sr.rs:198-265); Err leaves the nexthop's label as it is
+    for (auto &kv : route.nexthops) {
+        RNexthop &nh = kv.second;
+        if (last_hop && !(ps.flags & HL_ISIS_PSID_P)) { nh.has_label = true; nh.label = 3; continue; }   // implicit null
+        const hl_isis_lsp *cap = sr_cap_of(lsdb, nh.system_id);
+        if (!cap) continue;                                                                           // SrCapNotFound
+        if (!(cap->sr_flags & (is_v6 ? HL_LSP_SR_CAP_V : HL_LSP_SR_CAP_I))) continue;                // SrCapUnsupportedAf
+        if (last_hop && (ps.flags & HL_ISIS_PSID_E)) { nh.has_label = true; nh.label = is_v6 ? 2 : 0; continue; }   // explicit null
+        if (!ps.is_label) {
+            uint32_t label = 0;
+            if (index_to_label(*lsdb.l, *cap, ps.value, label)) { nh.has_label = true; nh.label = label; }
+        } else {
+            // V/L SIDs have local significance: only adjacent routers can use them
+            nh.has_label = true; nh.label = last_hop ? ps.value : 3;
+        }
+    }
+}
 
 // one compute_spt(local = true) run; returns vertices in id_tree order
 std::vector<LVertex> local_spt(const hl_isis_instance *in, uint8_t mt_id) {
@@ -406,13 +487,15 @@ extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_ri
                     if (wide_en)
                         for (uint32_t k = 0; k < lsp.n_ipreach; ++k)
                             if (ip[k].kind == HL_ISIS_IP_V4_EXT && ip[k].metric <= MAX_PATH_METRIC_WIDE)
-                                nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external});
+                                nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external, (bool)ip[k].has_psid,
+                                                    Psid{ip[k].psid_flags, (bool)ip[k].psid_is_label, ip[k].psid_value}});
                 }
                 if (ipv6_enabled) {
                     for (uint32_t k = 0; k < lsp.n_ipreach; ++k) {
                         const bool take = mt_id == HL_ISIS_MT_IPV6 ? (ip[k].kind == HL_ISIS_IP_MT_V6 && ip[k].mt_id == HL_ISIS_MT_IPV6)
                                                                    : (ip[k].kind == HL_ISIS_IP_V6);
-                        if (take) nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external});
+                        if (take) nets.push_back(VNet{ip[k].prefix, ip[k].len, ip[k].metric, (bool)ip[k].external, (bool)ip[k].has_psid,
+                                                      Psid{ip[k].psid_flags, (bool)ip[k].psid_is_label, ip[k].psid_value}});
                     }
                 }
             }
@@ -439,6 +522,7 @@ extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_ri
                                                    : (network.external ? HL_ISIS_RT_L2_EXT : HL_ISIS_RT_L2_INTRA);
                     rt.metric = vertex.distance + network.metric;
                     rt.nexthops = build();
+                    rt.has_psid = network.has_psid; rt.psid = network.psid;      // route.rs:100
                     return rt;
                 };
                 NetKey key{network.prefix, network.len};
@@ -459,6 +543,9 @@ extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_ri
                     for (auto &kv : route->nexthops) { if (n++ >= in->max_paths) break; cut.insert(kv); }
                     route->nexthops = std::move(cut);
                 }
+                // Update route's Prefix-SID (spf.rs:923-939)
+                if (in->sr_enabled && route->has_psid)
+                    prefix_sid_update(in, lsdb, vertex.id.lan_id, network.prefix.is_v6, *route, vertex.hops == 0, vertex.hops == 1);
             }
         }
     }
@@ -471,9 +558,11 @@ extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_ri
         hl_isis_route o{};
         o.prefix = kv.first.a; o.len = kv.first.len; o.metric = kv.second.metric; o.route_type = kv.second.route_type;
         o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nexthops.size();
+        o.has_sr_label = kv.second.has_label; o.sr_label = kv.second.has_label ? kv.second.label : 0;
         for (auto &nk : kv.second.nexthops) {
             hl_isis_nexthop x{};
             x.system_id = nk.second.system_id; x.iface = nk.second.iface; x.addr = nk.second.addr;
+            x.has_label = nk.second.has_label; x.sr_label = nk.second.has_label ? nk.second.label : 0;
             out->nexthops[h++] = x;
         }
         out->routes[i++] = o;

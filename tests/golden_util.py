@@ -299,7 +299,7 @@ def isis_level_image(snap, level, mt_id=None):
         rr = [(lan_id(n), m, 0, isis.REACH_LEGACY, 0) for (n, m, _mt) in l["is"]]
         rr += [(lan_id(n), m, 0, isis.REACH_EXT, 0) for (n, m, _mt) in l["ext_is"]]
         rr += [(lan_id(n), m, 2 if mt is None else mt, isis.REACH_MT, 0) for (n, m, mt) in l["mt_is"]]
-        lsps.append((lan_id(lid), 1, 1200, int(frag, 16), flags, len(reaches), len(rr), 0, 0))
+        lsps.append(isis.lsp_rec(lan_id(lid), 1, 1200, int(frag, 16), flags, len(reaches), len(rr)))
         reaches += rr
     lv = isis.IsisLevel(metric_type=mtype, mt_id=isis.MT_STANDARD if mt_id is None else mt_id,
                         ipv4_enabled="ipv4" in snap["afs"], ipv6_enabled="ipv6" in snap["afs"])
@@ -368,8 +368,9 @@ def isis_instance_image(snap, level):
         def add(items, kind, ext=0):
             for (p, m, mt) in items:
                 net = ipaddress.ip_network(p, strict=False)
-                ipr.append((ospfv3.ip_rec(net.network_address), m, 2 if (mt is None and kind == isis.IP_MT_V6) else (mt or 0),
-                            net.prefixlen, kind, ext, (0, 0, 0)))
+                ipr.append(isis.ipreach_rec(ospfv3.ip_rec(net.network_address), m,
+                                            2 if (mt is None and kind == isis.IP_MT_V6) else (mt or 0),
+                                            net.prefixlen, kind, ext))
         add(l["ipv4_int"], isis.IP_V4_INTERNAL)
         add(l["ipv4_ext"], isis.IP_V4_EXTERNAL, 1)
         add(l["ext_ipv4"], isis.IP_V4_EXT)

@@ -114,3 +114,36 @@ def test_route_stage_from_planes_synthetic(seed, kw, root, mtype, frag):
     t = synth.random_topology(300, 1300, synth.SEED_BASE + seed, **kw)
     inst = synth_instance(t, root, mtype, frag)
     same_rib(isis.routes_from_planes(inst, oracle_planes), pyoracle.isis_compute_routes(inst))
+
+
+@pytest.mark.parametrize("seed,kw,root,mtype,frag", [
+    (3, dict(cost_lo=1, cost_hi=30, lan_fraction=0.15), 0, isis.METRIC_WIDE, 3),
+    (4, dict(cost_choices=[10], lan_fraction=0.2), 7, isis.METRIC_WIDE, 0),          # ECMP: merged next hops
+    (5, dict(cost_lo=1, cost_hi=20), 11, isis.METRIC_BOTH, 2),
+    (6, dict(cost_choices=[5, 10]), 4, isis.METRIC_WIDE, 2),
+    (7, dict(cost_lo=1, cost_hi=9, lan_fraction=0.3), 12, isis.METRIC_WIDE, 1),
+])
+def test_route_stage_sr_prefix_sid_labels(seed, kw, root, mtype, frag):
+    """IS-IS SR Prefix-SID labels (holo-isis/src/sr.rs:33-99): product route stage vs the restatement,
+    byte for byte, plus the rules that can be read off the result."""
+    t = synth.random_topology(200, 800, synth.SEED_BASE + seed, **kw)
+    inst = synth_instance(t, root, mtype, frag, sr=True)
+    got = isis.routes_from_planes(inst, oracle_planes)
+    same_rib(got, pyoracle.isis_compute_routes(inst))
+    assert int(got.routes["has_sr_label"].sum()) > 20 and int(got.nexthops["has_label"].sum()) > 20
+    labels = got.nexthops["sr_label"][got.nexthops["has_label"] == 1]
+    assert (labels == 3).any() and (labels >= 16000).any()            # implicit null and SRGB labels
+    # sr disabled: no label anywhere, everything else unchanged
+    inst_off = dict(inst, sr_enabled=0)
+    off = isis.routes_from_planes(inst_off, oracle_planes)
+    assert int(off.routes["has_sr_label"].sum()) == 0 and int(off.nexthops["has_label"].sum()) == 0
+    assert np.array_equal(off.routes[["metric", "len", "route_type", "flags", "nh_off", "n_nh"]],
+                          got.routes[["metric", "len", "route_type", "flags", "nh_off", "n_nh"]])
+    # the local prefixes (hops 0) carry an input label only with P set and E clear
+    from holo_b200 import ospfv3
+    me = root
+    own = {f"10.{(me >> 16) & 255}.{(me >> 8) & 255}.{me & 255}"}
+    for r in got.routes:
+        if ospfv3.ip_str(r["prefix"]) in own:
+            kind = me % 7
+            assert bool(r["has_sr_label"]) == (kind == 1)

@@ -112,3 +112,16 @@ def test_route_stage_synthetic(ctx, seed, kw, root, mtype, frag):
     t = synth.random_topology(300, 1300, synth.SEED_BASE + seed, **kw)
     inst = synth_instance(t, root, mtype, frag)
     same_rib(isis.compute_routes(ctx, inst), pyoracle.isis_compute_routes(inst))
+
+
+@pytest.mark.parametrize("seed,kw,root,frag", [
+    (3, dict(cost_lo=1, cost_hi=30, lan_fraction=0.15), 0, 3),
+    (4, dict(cost_choices=[10], lan_fraction=0.2), 7, 0),
+])
+def test_route_stage_sr_prefix_sid_labels(ctx, seed, kw, root, frag):
+    """SR Prefix-SID labels through the GPU route path (CPU twin: tests/test_isis_cpu.py)."""
+    t = synth.random_topology(200, 800, synth.SEED_BASE + seed, **kw)
+    inst = synth_instance(t, root, isis.METRIC_WIDE, frag, sr=True)
+    rib = isis.compute_routes(ctx, inst)
+    same_rib(rib, pyoracle.isis_compute_routes(inst))
+    assert int(rib.nexthops["has_label"].sum()) > 20
