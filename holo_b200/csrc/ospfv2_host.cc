@@ -380,6 +380,215 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
     return (int)n;
 }
 
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Everything run_area + update_rib_intra_area do after the SPT (holo-ospf/src/spf.rs:627-724,
+// route.rs:343-446, sr.rs): Vertex.nexthops from the atom sets, the area's router table,
+// transit_capability, intra-area routes with SR labels.  `dist` / `hops` / `nh` are the planes
+// of the root's job in the vertex order of `f`.
+int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_t root, const uint32_t *dist,
+                     const uint16_t *hops, const uint64_t *nh, uint32_t nhw, hl_ospfv2_result *out) {
+    const uint32_t V = (uint32_t)f.ids.size();
+    // ---- Vertex.nexthops --------------------------------------------------------------
+    Resolver rs{f, a, root, nh, nhw, {}, {}, {}};
+    rs.atom_nh.resize((size_t)64 * nhw);
+    rs.atom_done.assign((size_t)64 * nhw, 0);
+    for (uint32_t i = 0; i < a->n_ifaces; ++i)
+        if (a->ifaces[i].n_nbrs > 0) rs.ifaces_with_nbrs.push_back((int)i);
+    std::vector<uint32_t> spt;            // vertices on the SPT, VertexId order
+    for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
+    std::vector<std::vector<Nh>> vnh(V);
+    for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
+
+    // ---- intra-area routes (update_rib_intra_area) ------------------------------------
+    std::unordered_map<uint64_t, const hl_ospfv2_ext_prefix *> extp;   // (adv_rtr, prefix/len) first wins
+    auto ekey = [](uint32_t adv, uint32_t prefix, uint32_t plen) {
+        return ((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen;
+    };
+    if (a->sr_enabled) {
+        for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+            const auto &e = a->ext_prefixes[i];
+            if (e.age == HL_LSA_MAX_AGE) continue;
+            extp.emplace(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), &e);
+        }
+    }
+    auto ext_find = [&](uint32_t adv, uint32_t prefix, uint32_t plen) -> const hl_ospfv2_ext_prefix * {
+        auto it = extp.find(ekey(adv, prefix, plen));
+        if (it == extp.end()) return nullptr;
+        const auto *e = it->second;
+        if (e->adv_rtr == adv && e->prefix == prefix && (uint32_t)__builtin_popcount(e->mask) == plen) return e;
+        // hash-key collision: fall back to a scan (first match in LSDB order)
+        for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+            const auto &x = a->ext_prefixes[i];
+            if (x.age != HL_LSA_MAX_AGE && x.adv_rtr == adv && x.prefix == prefix &&
+                (uint32_t)__builtin_popcount(x.mask) == plen) return &x;
+        }
+        return nullptr;
+    };
+    std::unordered_map<uint64_t, uint32_t> rib_idx;
+    std::vector<Route> rib;
+    std::vector<uint8_t> rib_live;
+    RouterInfo local_ri; bool local_ri_loaded = false;
+    std::unordered_map<uint32_t, RouterInfo> ri_cache;
+    auto cached_ri = [&](uint32_t rid) -> const RouterInfo & {
+        auto it = ri_cache.find(rid);
+        if (it == ri_cache.end()) it = ri_cache.emplace(rid, router_info(a, rid)).first;
+        return it->second;
+    };
+
+    auto add_stub = [&](uint32_t v, uint32_t prefix, uint32_t plen, uint32_t stub_metric, uint32_t adv_rtr) {
+        uint32_t m = dist[v] + stub_metric;
+        if (m > 0xFFFF) m = 0xFFFF;
+        const uint64_t key = pkey(prefix, plen);
+        auto it = rib_idx.find(key);
+        Route *cur = (it != rib_idx.end() && rib_live[it->second]) ? &rib[it->second] : nullptr;
+        if (cur && m > cur->metric) return;
+        uint8_t otype; uint32_t oadv, oid;
+        if (f.is_router[v]) { const auto &l = a->router_lsas[f.lsa_of[v]]; otype = 1; oadv = l.adv_rtr; oid = l.lsa_id; }
+        else { const auto &l = a->network_lsas[f.lsa_of[v]]; otype = 2; oadv = l.adv_rtr; oid = l.lsa_id; }
+        if (!f.is_router[v] && cur) {
+            if (m > cur->metric || oid < cur->origin_id) return;
+            rib_live[it->second] = 0;   // o.remove()
+            cur = nullptr;
+        }
+        Route nr;
+        nr.prefix = prefix; nr.plen = plen; nr.metric = m;
+        nr.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
+        nr.origin_type = otype; nr.origin_adv = oadv; nr.origin_id = oid;
+        nr.nh = vnh[v];
+        if (a->sr_enabled) {
+            const hl_ospfv2_ext_prefix *ep = ext_find(adv_rtr, prefix, plen);
+            if (ep && ep->route_type == 1 && ep->has_sid && cached_ri(oadv).has_sr_algo) {
+                const bool local = hops[v] == 0, last_hop = hops[v] == 1;
+                nr.has_sid = true; nr.sid_value = ep->sid_value; nr.sid_flags = ep->sid_flags;
+                nr.sid_is_label = ep->sid_is_label;
+                if (!(local && (!(ep->sid_flags & HL_PSID_NP) || (ep->sid_flags & HL_PSID_E)))) {
+                    if (!ep->sid_is_label) {
+                        if (!local_ri_loaded) { local_ri = router_info(a, a->router_id); local_ri_loaded = true; }
+                        uint32_t lab;
+                        if (!local_ri.srgb.empty() && index_to_label(ep->sid_value, local_ri.srgb, &lab)) {
+                            nr.has_label = true; nr.label = lab;
+                        }
+                    } else {
+                        nr.has_label = true; nr.label = ep->sid_value;
+                    }
+                }
+                for (Nh &x : nr.nh) {
+                    if (!x.has_nbr) continue;
+                    uint32_t lab = 0; bool ok = false, decided = false;
+                    if (last_hop) {
+                        if (!(ep->sid_flags & HL_PSID_NP)) { lab = 3; ok = decided = true; }
+                        else if (ep->sid_flags & HL_PSID_E) { lab = 0; ok = decided = true; }
+                    }
+                    if (!decided) {
+                        if (!ep->sid_is_label) {
+                            const RouterInfo &nri = cached_ri(x.nbr);
+                            if (!nri.srgb.empty()) ok = index_to_label(ep->sid_value, nri.srgb, &lab);
+                        } else {
+                            lab = last_hop ? ep->sid_value : 3u; ok = true;
+                        }
+                    }
+                    if (ok) { x.has_label = 1; x.label = lab; }
+                }
+            }
+        }
+        // route_update
+        Route *route;
+        if (cur) {
+            if (nr.metric < cur->metric) *cur = nr;
+            else if (nr.metric == cur->metric) for (const Nh &x : nr.nh) nh_insert(cur->nh, x);
+            route = cur;
+        } else {
+            if (it != rib_idx.end()) { rib[it->second] = nr; rib_live[it->second] = 1; route = &rib[it->second]; }
+            else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); rib_live.push_back(1); route = &rib.back(); }
+        }
+        if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
+    };
+    for (uint32_t v : spt) {
+        if (!f.is_router[v]) {
+            const auto &nl = a->network_lsas[f.lsa_of[v]];
+            add_stub(v, nl.lsa_id & nl.mask, (uint32_t)__builtin_popcount(nl.mask), 0, nl.adv_rtr);
+        } else {
+            const auto &rl = a->router_lsas[f.lsa_of[v]];
+            for (uint32_t k = 0; k < rl.n_links; ++k) {
+                const auto &l = a->links[rl.link_off + k];
+                if (l.link_type != HL_LINK_STUB) continue;
+                add_stub(v, l.link_id & l.link_data, (uint32_t)__builtin_popcount(l.link_data), l.metric, rl.adv_rtr);
+            }
+        }
+    }
+
+    // ---- export ---------------------------------------------------------------------------
+    std::vector<uint32_t> live;
+    for (uint32_t i = 0; i < rib.size(); ++i) if (rib_live[i]) live.push_back(i);
+    std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
+        return rib[x].prefix != rib[y].prefix ? rib[x].prefix < rib[y].prefix : rib[x].plen < rib[y].plen;
+    });
+    uint32_t n_rtr_in_spt = 0, need_h = 0;
+    for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr_in_spt; need_h += (uint32_t)vnh[v].size(); } }
+    for (uint32_t i : live) need_h += (uint32_t)rib[i].nh.size();
+    out->n_vertices = (uint32_t)spt.size();
+    out->n_routers = n_rtr_in_spt;
+    out->n_routes = (uint32_t)live.size();
+    out->n_nexthops = need_h;
+    bool tc = false;
+    for (uint32_t v : spt)
+        if (f.is_router[v] && (a->router_lsas[f.lsa_of[v]].flags & HL_RTR_FLAG_V)) tc = true;
+    out->transit_capability = tc;
+    if (out->n_vertices > out->vertices_cap || out->n_routers > out->routers_cap ||
+        out->n_routes > out->routes_cap || out->n_nexthops > out->nexthops_cap)
+        return HSPF_E_NOMEM;
+    uint32_t h = 0;
+    auto put = [&](const std::vector<Nh> &s) {
+        for (const Nh &x : s) {
+            hl_nexthop o{};
+            o.iface = x.iface; o.addr = x.has_addr ? x.addr : 0; o.nbr_router_id = x.has_nbr ? x.nbr : 0;
+            o.sr_label = x.has_label ? x.label : 0;
+            o.has_addr = x.has_addr; o.has_nbr = x.has_nbr; o.has_label = x.has_label;
+            out->nexthops[h++] = o;
+        }
+    };
+    uint32_t i = 0;
+    for (uint32_t v : spt) {
+        hl_spt_vertex o{};
+        o.id = f.ids[v]; o.distance = dist[v]; o.hops = hops[v]; o.is_router = f.is_router[v];
+        o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+        put(vnh[v]);
+        out->vertices[i++] = o;
+    }
+    i = 0;
+    for (uint32_t v : spt) {   // router vertices are already in router-id order
+        if (!f.is_router[v]) continue;
+        const auto &rl = a->router_lsas[f.lsa_of[v]];
+        hl_route_rtr o{};
+        o.router_id = rl.adv_rtr; o.metric = dist[v]; o.flags = rl.flags; o.options = rl.options;
+        o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+        put(vnh[v]);
+        out->routers[i++] = o;
+    }
+    i = 0;
+    for (uint32_t k : live) {
+        const Route &r = rib[k];
+        hl_route_net o{};
+        o.prefix = r.prefix; o.mask = r.plen == 0 ? 0 : 0xFFFFFFFFu << (32 - r.plen);
+        o.metric = r.metric; o.flags = r.flags; o.origin_type = r.origin_type;
+        o.origin_adv_rtr = r.origin_adv; o.origin_lsa_id = r.origin_id;
+        o.has_prefix_sid = r.has_sid; o.prefix_sid_value = r.sid_value; o.prefix_sid_flags = r.sid_flags;
+        o.prefix_sid_is_label = r.sid_is_label;
+        o.has_sr_label = r.has_label; o.sr_label = r.has_label ? r.label : 0;
+        o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
+        put(r.nh);
+        out->routes[i++] = o;
+    }
+    return HSPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *a, hl_ospfv2_result *out) {
     if (!ctx || !a || !out) return HSPF_E_INVAL;
     try {
@@ -418,199 +627,32 @@ int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *a, hl_ospfv2_resul
         rc = hspf_run_batch(ctx, g, &jobs, &res, 0);
         hspf_graph_free(ctx, g);
         if (rc) return rc;   // includes HSPF_E_JOB_STATUS (saturation): caller's CPU path
+        return area_from_planes(f, a, root, dist.data(), hops.data(), nh.data(), nhw, out);
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
 
-        // ---- Vertex.nexthops --------------------------------------------------------------
-        Resolver rs{f, a, root, nh.data(), nhw, {}, {}, {}};
-        rs.atom_nh.resize((size_t)64 * nhw);
-        rs.atom_done.assign((size_t)64 * nhw, 0);
-        for (uint32_t i = 0; i < a->n_ifaces; ++i)
-            if (a->ifaces[i].n_nbrs > 0) rs.ifaces_with_nbrs.push_back((int)i);
-        std::vector<uint32_t> spt;            // vertices on the SPT, VertexId order
-        for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
-        std::vector<std::vector<Nh>> vnh(V);
-        for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
-
-        // ---- intra-area routes (update_rib_intra_area) ------------------------------------
-        std::unordered_map<uint64_t, const hl_ospfv2_ext_prefix *> extp;   // (adv_rtr, prefix/len) first wins
-        auto ekey = [](uint32_t adv, uint32_t prefix, uint32_t plen) {
-            return ((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen;
-        };
-        if (a->sr_enabled) {
-            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
-                const auto &e = a->ext_prefixes[i];
-                if (e.age == HL_LSA_MAX_AGE) continue;
-                extp.emplace(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), &e);
-            }
-        }
-        auto ext_find = [&](uint32_t adv, uint32_t prefix, uint32_t plen) -> const hl_ospfv2_ext_prefix * {
-            auto it = extp.find(ekey(adv, prefix, plen));
-            if (it == extp.end()) return nullptr;
-            const auto *e = it->second;
-            if (e->adv_rtr == adv && e->prefix == prefix && (uint32_t)__builtin_popcount(e->mask) == plen) return e;
-            // hash-key collision: fall back to a scan (first match in LSDB order)
-            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
-                const auto &x = a->ext_prefixes[i];
-                if (x.age != HL_LSA_MAX_AGE && x.adv_rtr == adv && x.prefix == prefix &&
-                    (uint32_t)__builtin_popcount(x.mask) == plen) return &x;
-            }
-            return nullptr;
-        };
-        std::unordered_map<uint64_t, uint32_t> rib_idx;
-        std::vector<Route> rib;
-        std::vector<uint8_t> rib_live;
-        RouterInfo local_ri; bool local_ri_loaded = false;
-        std::unordered_map<uint32_t, RouterInfo> ri_cache;
-        auto cached_ri = [&](uint32_t rid) -> const RouterInfo & {
-            auto it = ri_cache.find(rid);
-            if (it == ri_cache.end()) it = ri_cache.emplace(rid, router_info(a, rid)).first;
-            return it->second;
-        };
-
-        auto add_stub = [&](uint32_t v, uint32_t prefix, uint32_t plen, uint32_t stub_metric, uint32_t adv_rtr) {
-            uint32_t m = dist[v] + stub_metric;
-            if (m > 0xFFFF) m = 0xFFFF;
-            const uint64_t key = pkey(prefix, plen);
-            auto it = rib_idx.find(key);
-            Route *cur = (it != rib_idx.end() && rib_live[it->second]) ? &rib[it->second] : nullptr;
-            if (cur && m > cur->metric) return;
-            uint8_t otype; uint32_t oadv, oid;
-            if (f.is_router[v]) { const auto &l = a->router_lsas[f.lsa_of[v]]; otype = 1; oadv = l.adv_rtr; oid = l.lsa_id; }
-            else { const auto &l = a->network_lsas[f.lsa_of[v]]; otype = 2; oadv = l.adv_rtr; oid = l.lsa_id; }
-            if (!f.is_router[v] && cur) {
-                if (m > cur->metric || oid < cur->origin_id) return;
-                rib_live[it->second] = 0;   // o.remove()
-                cur = nullptr;
-            }
-            Route nr;
-            nr.prefix = prefix; nr.plen = plen; nr.metric = m;
-            nr.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
-            nr.origin_type = otype; nr.origin_adv = oadv; nr.origin_id = oid;
-            nr.nh = vnh[v];
-            if (a->sr_enabled) {
-                const hl_ospfv2_ext_prefix *ep = ext_find(adv_rtr, prefix, plen);
-                if (ep && ep->route_type == 1 && ep->has_sid && cached_ri(oadv).has_sr_algo) {
-                    const bool local = hops[v] == 0, last_hop = hops[v] == 1;
-                    nr.has_sid = true; nr.sid_value = ep->sid_value; nr.sid_flags = ep->sid_flags;
-                    nr.sid_is_label = ep->sid_is_label;
-                    if (!(local && (!(ep->sid_flags & HL_PSID_NP) || (ep->sid_flags & HL_PSID_E)))) {
-                        if (!ep->sid_is_label) {
-                            if (!local_ri_loaded) { local_ri = router_info(a, a->router_id); local_ri_loaded = true; }
-                            uint32_t lab;
-                            if (!local_ri.srgb.empty() && index_to_label(ep->sid_value, local_ri.srgb, &lab)) {
-                                nr.has_label = true; nr.label = lab;
-                            }
-                        } else {
-                            nr.has_label = true; nr.label = ep->sid_value;
-                        }
-                    }
-                    for (Nh &x : nr.nh) {
-                        if (!x.has_nbr) continue;
-                        uint32_t lab = 0; bool ok = false, decided = false;
-                        if (last_hop) {
-                            if (!(ep->sid_flags & HL_PSID_NP)) { lab = 3; ok = decided = true; }
-                            else if (ep->sid_flags & HL_PSID_E) { lab = 0; ok = decided = true; }
-                        }
-                        if (!decided) {
-                            if (!ep->sid_is_label) {
-                                const RouterInfo &nri = cached_ri(x.nbr);
-                                if (!nri.srgb.empty()) ok = index_to_label(ep->sid_value, nri.srgb, &lab);
-                            } else {
-                                lab = last_hop ? ep->sid_value : 3u; ok = true;
-                            }
-                        }
-                        if (ok) { x.has_label = 1; x.label = lab; }
-                    }
-                }
-            }
-            // route_update
-            Route *route;
-            if (cur) {
-                if (nr.metric < cur->metric) *cur = nr;
-                else if (nr.metric == cur->metric) for (const Nh &x : nr.nh) nh_insert(cur->nh, x);
-                route = cur;
-            } else {
-                if (it != rib_idx.end()) { rib[it->second] = nr; rib_live[it->second] = 1; route = &rib[it->second]; }
-                else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); rib_live.push_back(1); route = &rib.back(); }
-            }
-            if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
-        };
-        for (uint32_t v : spt) {
-            if (!f.is_router[v]) {
-                const auto &nl = a->network_lsas[f.lsa_of[v]];
-                add_stub(v, nl.lsa_id & nl.mask, (uint32_t)__builtin_popcount(nl.mask), 0, nl.adv_rtr);
-            } else {
-                const auto &rl = a->router_lsas[f.lsa_of[v]];
-                for (uint32_t k = 0; k < rl.n_links; ++k) {
-                    const auto &l = a->links[rl.link_off + k];
-                    if (l.link_type != HL_LINK_STUB) continue;
-                    add_stub(v, l.link_id & l.link_data, (uint32_t)__builtin_popcount(l.link_data), l.metric, rl.adv_rtr);
-                }
-            }
-        }
-
-        // ---- export ---------------------------------------------------------------------------
-        std::vector<uint32_t> live;
-        for (uint32_t i = 0; i < rib.size(); ++i) if (rib_live[i]) live.push_back(i);
-        std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
-            return rib[x].prefix != rib[y].prefix ? rib[x].prefix < rib[y].prefix : rib[x].plen < rib[y].plen;
-        });
-        uint32_t n_rtr_in_spt = 0, need_h = 0;
-        for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr_in_spt; need_h += (uint32_t)vnh[v].size(); } }
-        for (uint32_t i : live) need_h += (uint32_t)rib[i].nh.size();
-        out->n_vertices = (uint32_t)spt.size();
-        out->n_routers = n_rtr_in_spt;
-        out->n_routes = (uint32_t)live.size();
-        out->n_nexthops = need_h;
-        bool tc = false;
-        for (uint32_t v : spt)
-            if (f.is_router[v] && (a->router_lsas[f.lsa_of[v]].flags & HL_RTR_FLAG_V)) tc = true;
-        out->transit_capability = tc;
-        if (out->n_vertices > out->vertices_cap || out->n_routers > out->routers_cap ||
-            out->n_routes > out->routes_cap || out->n_nexthops > out->nexthops_cap)
-            return HSPF_E_NOMEM;
-        uint32_t h = 0;
-        auto put = [&](const std::vector<Nh> &s) {
-            for (const Nh &x : s) {
-                hl_nexthop o{};
-                o.iface = x.iface; o.addr = x.has_addr ? x.addr : 0; o.nbr_router_id = x.has_nbr ? x.nbr : 0;
-                o.sr_label = x.has_label ? x.label : 0;
-                o.has_addr = x.has_addr; o.has_nbr = x.has_nbr; o.has_label = x.has_label;
-                out->nexthops[h++] = o;
-            }
-        };
-        uint32_t i = 0;
-        for (uint32_t v : spt) {
-            hl_spt_vertex o{};
-            o.id = f.ids[v]; o.distance = dist[v]; o.hops = hops[v]; o.is_router = f.is_router[v];
-            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
-            put(vnh[v]);
-            out->vertices[i++] = o;
-        }
-        i = 0;
-        for (uint32_t v : spt) {   // router vertices are already in router-id order
-            if (!f.is_router[v]) continue;
-            const auto &rl = a->router_lsas[f.lsa_of[v]];
-            hl_route_rtr o{};
-            o.router_id = rl.adv_rtr; o.metric = dist[v]; o.flags = rl.flags; o.options = rl.options;
-            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
-            put(vnh[v]);
-            out->routers[i++] = o;
-        }
-        i = 0;
-        for (uint32_t k : live) {
-            const Route &r = rib[k];
-            hl_route_net o{};
-            o.prefix = r.prefix; o.mask = r.plen == 0 ? 0 : 0xFFFFFFFFu << (32 - r.plen);
-            o.metric = r.metric; o.flags = r.flags; o.origin_type = r.origin_type;
-            o.origin_adv_rtr = r.origin_adv; o.origin_lsa_id = r.origin_id;
-            o.has_prefix_sid = r.has_sid; o.prefix_sid_value = r.sid_value; o.prefix_sid_flags = r.sid_flags;
-            o.prefix_sid_is_label = r.sid_is_label;
-            o.has_sr_label = r.has_label; o.sr_label = r.has_label ? r.label : 0;
-            o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
-            put(r.nh);
-            out->routes[i++] = o;
-        }
-        return HSPF_OK;
+/* The post-SPT half of hspf_ospfv2_run_area over planes the caller already has (one job of a
+ * batch run through hspf_ospfv2_flatten + hspf_run_batch with the local router as root): planes
+ * are indexed by the vertex order of hspf_ospfv2_flatten; nh_words as passed to the engine.
+ * Host only. */
+int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *a, const uint32_t *dist, const uint16_t *hops,
+                                 const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv2_result *out) {
+    if (!a || !out || !dist || !hops || !nh_mask || nh_words < 1 || nh_words > 4) return HSPF_E_INVAL;
+    try {
+        out->n_vertices = out->n_routers = out->n_routes = out->n_nexthops = 0;
+        out->transit_capability = 0;
+        out->root_found = 0;
+        hspf_ospfv2_flat f;
+        int rc = flatten(a, f);
+        if (rc) return rc;
+        auto rit = f.rtr_vertex.find(a->router_id);
+        if (rit == f.rtr_vertex.end()) return HSPF_OK;
+        out->root_found = 1;
+        return area_from_planes(f, a, rit->second, dist, hops, nh_mask, nh_words, out);
     } catch (const std::bad_alloc &) {
         return HSPF_E_NOMEM;
     } catch (...) {

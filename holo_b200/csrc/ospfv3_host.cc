@@ -290,6 +290,134 @@ uint32_t hspf_ospfv3_flat_router_vertex(const hspf_ospfv3_flat *flat, uint32_t r
     return it == flat->rtr_vertex.end() ? kNone : it->second;
 }
 
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Everything run_area + update_rib_intra_area do after the SPT for OSPFv3 (spf.rs:627-724 with
+// the hooks of ospfv3/spf.rs:164-283, 420-477, 592-611; route.rs:343-446), over the planes of
+// the root's job in the vertex order of `f`.
+int area_from_planes(const hspf_ospfv3_flat &f, const hl_ospfv3_area *a, uint32_t root, const uint32_t *dist,
+                     const uint16_t *hops, const uint64_t *nh, uint32_t nhw, hl_ospfv3_result *out) {
+    const uint32_t V = (uint32_t)f.rid.size();
+    Resolver rs{f, a, root, nh, nhw, {}, {}};
+    rs.atom_nh.resize((size_t)64 * nhw);
+    rs.atom_done.assign((size_t)64 * nhw, 0);
+    std::vector<uint32_t> spt;
+    for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
+    std::vector<std::vector<Nh6>> vnh(V);
+    for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
+
+    // ---- intra-area routes from Intra-Area-Prefix-LSAs in LsaKey order ----------
+    std::vector<uint32_t> iord(a->n_iap_lsas);
+    for (uint32_t i = 0; i < a->n_iap_lsas; ++i) iord[i] = i;
+    std::stable_sort(iord.begin(), iord.end(), [&](uint32_t x, uint32_t y) {
+        const auto &p = a->iap_lsas[x], &q = a->iap_lsas[y];
+        return p.adv_rtr != q.adv_rtr ? p.adv_rtr < q.adv_rtr : p.lsa_id < q.lsa_id;
+    });
+    std::map<PKey, uint32_t> rib_idx;
+    std::vector<Route6> rib;
+    for (uint32_t i : iord) {
+        const auto &l = a->iap_lsas[i];
+        if (l.age == HL_LSA_MAX_AGE) continue;
+        uint32_t v = kNone;
+        if (l.ref_type == HL_V3_REF_ROUTER) {
+            if (l.ref_lsa_id != 0) continue;
+            auto it = f.rtr_vertex.find(l.ref_adv_rtr);
+            if (it != f.rtr_vertex.end()) v = it->second;
+        } else if (l.ref_type == HL_V3_REF_NETWORK) {
+            auto it = f.net_vertex.find(((uint64_t)l.ref_adv_rtr << 32) | l.ref_lsa_id);
+            if (it != f.net_vertex.end()) v = it->second;
+        }
+        if (v == kNone || dist[v] == HSPF_DIST_INF) continue;
+        for (uint32_t k = 0; k < l.n_prefixes; ++k) {
+            const auto &px = a->prefixes[l.prefix_off + k];
+            if (px.options & HL_PFX_OPT_NU) continue;
+            uint32_t m = dist[v] + px.metric;
+            if (m > 0xFFFF) m = 0xFFFF;
+            PKey key{px.addr, px.len};
+            auto it = rib_idx.find(key);
+            Route6 *cur = (it != rib_idx.end() && rib[it->second].live) ? &rib[it->second] : nullptr;
+            if (cur && m > cur->metric) continue;
+            uint8_t otype; uint32_t oadv, oid;
+            if (f.is_router[v]) { const auto &r = a->router_lsas[f.first_lsa[v]]; otype = 1; oadv = r.adv_rtr; oid = r.lsa_id; }
+            else { const auto &n = a->network_lsas[f.first_lsa[v]]; otype = 2; oadv = n.adv_rtr; oid = n.lsa_id; }
+            if (!f.is_router[v] && cur) {
+                if (m > cur->metric || oid < cur->oid) continue;
+                cur->live = false;
+                cur = nullptr;
+            }
+            Route6 nr{px.addr, px.len, (uint8_t)(hops[v] == 0 ? HL_ROUTE_CONNECTED : 0), otype, px.options, m, oadv, oid, vnh[v], true};
+            Route6 *route;
+            if (cur) {
+                if (nr.metric < cur->metric) *cur = nr;
+                else if (nr.metric == cur->metric) for (const Nh6 &x : nr.nh) nh_insert(cur->nh, x);
+                route = cur;
+            } else if (it != rib_idx.end()) {
+                rib[it->second] = nr; route = &rib[it->second];
+            } else {
+                rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); route = &rib.back();
+            }
+            if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
+        }
+    }
+
+    // ---- export --------------------------------------------------------------------
+    uint32_t n_rtr = 0, need_h = 0, n_routes = 0;
+    for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr; need_h += (uint32_t)vnh[v].size(); } }
+    for (auto &kv : rib_idx) if (rib[kv.second].live) { ++n_routes; need_h += (uint32_t)rib[kv.second].nh.size(); }
+    out->n_vertices = (uint32_t)spt.size(); out->n_routers = n_rtr; out->n_routes = n_routes; out->n_nexthops = need_h;
+    bool tc = false;
+    for (uint32_t v : spt) if (f.is_router[v] && (a->router_lsas[f.first_lsa[v]].flags & HL_RTR_FLAG_V)) tc = true;
+    out->transit_capability = tc;
+    if (out->n_vertices > out->vertices_cap || n_rtr > out->routers_cap || n_routes > out->routes_cap ||
+        need_h > out->nexthops_cap)
+        return HSPF_E_NOMEM;
+    uint32_t h = 0;
+    auto put = [&](const std::vector<Nh6> &s) {
+        for (const Nh6 &x : s) {
+            hl_nexthop6 o{};
+            o.iface = x.iface; o.nbr_router_id = x.has_nbr ? x.nbr : 0;
+            if (x.has_addr) o.addr = x.addr;
+            o.has_addr = x.has_addr; o.has_nbr = x.has_nbr;
+            out->nexthops[h++] = o;
+        }
+    };
+    uint32_t i = 0;
+    for (uint32_t v : spt) {
+        hl_spt_vertex6 o{};
+        o.router_id = f.rid[v]; o.iface_id = f.ifid[v]; o.distance = dist[v]; o.hops = hops[v]; o.is_router = f.is_router[v];
+        o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+        put(vnh[v]);
+        out->vertices[i++] = o;
+    }
+    i = 0;
+    for (uint32_t v : spt) {
+        if (!f.is_router[v]) continue;
+        const auto &r = a->router_lsas[f.first_lsa[v]];
+        hl_route_rtr o{};
+        o.router_id = r.adv_rtr; o.metric = dist[v]; o.flags = r.flags; o.options = r.options;
+        o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
+        put(vnh[v]);
+        out->routers[i++] = o;
+    }
+    i = 0;
+    for (auto &kv : rib_idx) {
+        const Route6 &r = rib[kv.second];
+        if (!r.live) continue;
+        hl_route_net6 o{};
+        o.prefix = r.prefix; o.len = r.len; o.flags = r.flags; o.origin_type = r.otype; o.prefix_options = r.options;
+        o.metric = r.metric; o.origin_adv_rtr = r.oadv; o.origin_lsa_id = r.oid; o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
+        put(r.nh);
+        out->routes[i++] = o;
+    }
+    return HSPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int hspf_ospfv3_run_area(hspf_ctx *ctx, const hl_ospfv3_area *a, hl_ospfv3_result *out) {
     if (!ctx || !a || !out) return HSPF_E_INVAL;
     try {
@@ -324,120 +452,35 @@ int hspf_ospfv3_run_area(hspf_ctx *ctx, const hl_ospfv3_area *a, hl_ospfv3_resul
         rc = hspf_run_batch(ctx, g, &jobs, &res, 0);
         hspf_graph_free(ctx, g);
         if (rc) return rc;
+        return area_from_planes(f, a, root, dist.data(), hops.data(), nh.data(), nhw, out);
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
 
-        Resolver rs{f, a, root, nh.data(), nhw, {}, {}};
-        rs.atom_nh.resize((size_t)64 * nhw);
-        rs.atom_done.assign((size_t)64 * nhw, 0);
-        std::vector<uint32_t> spt;
-        for (uint32_t v = 0; v < V; ++v) if (dist[v] != HSPF_DIST_INF) spt.push_back(v);
-        std::vector<std::vector<Nh6>> vnh(V);
-        for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
-
-        // ---- intra-area routes from Intra-Area-Prefix-LSAs in LsaKey order ----------
-        std::vector<uint32_t> iord(a->n_iap_lsas);
-        for (uint32_t i = 0; i < a->n_iap_lsas; ++i) iord[i] = i;
-        std::stable_sort(iord.begin(), iord.end(), [&](uint32_t x, uint32_t y) {
-            const auto &p = a->iap_lsas[x], &q = a->iap_lsas[y];
-            return p.adv_rtr != q.adv_rtr ? p.adv_rtr < q.adv_rtr : p.lsa_id < q.lsa_id;
-        });
-        std::map<PKey, uint32_t> rib_idx;
-        std::vector<Route6> rib;
-        for (uint32_t i : iord) {
-            const auto &l = a->iap_lsas[i];
-            if (l.age == HL_LSA_MAX_AGE) continue;
-            uint32_t v = kNone;
-            if (l.ref_type == HL_V3_REF_ROUTER) {
-                if (l.ref_lsa_id != 0) continue;
-                auto it = f.rtr_vertex.find(l.ref_adv_rtr);
-                if (it != f.rtr_vertex.end()) v = it->second;
-            } else if (l.ref_type == HL_V3_REF_NETWORK) {
-                auto it = f.net_vertex.find(((uint64_t)l.ref_adv_rtr << 32) | l.ref_lsa_id);
-                if (it != f.net_vertex.end()) v = it->second;
-            }
-            if (v == kNone || dist[v] == HSPF_DIST_INF) continue;
-            for (uint32_t k = 0; k < l.n_prefixes; ++k) {
-                const auto &px = a->prefixes[l.prefix_off + k];
-                if (px.options & HL_PFX_OPT_NU) continue;
-                uint32_t m = dist[v] + px.metric;
-                if (m > 0xFFFF) m = 0xFFFF;
-                PKey key{px.addr, px.len};
-                auto it = rib_idx.find(key);
-                Route6 *cur = (it != rib_idx.end() && rib[it->second].live) ? &rib[it->second] : nullptr;
-                if (cur && m > cur->metric) continue;
-                uint8_t otype; uint32_t oadv, oid;
-                if (f.is_router[v]) { const auto &r = a->router_lsas[f.first_lsa[v]]; otype = 1; oadv = r.adv_rtr; oid = r.lsa_id; }
-                else { const auto &n = a->network_lsas[f.first_lsa[v]]; otype = 2; oadv = n.adv_rtr; oid = n.lsa_id; }
-                if (!f.is_router[v] && cur) {
-                    if (m > cur->metric || oid < cur->oid) continue;
-                    cur->live = false;
-                    cur = nullptr;
-                }
-                Route6 nr{px.addr, px.len, (uint8_t)(hops[v] == 0 ? HL_ROUTE_CONNECTED : 0), otype, px.options, m, oadv, oid, vnh[v], true};
-                Route6 *route;
-                if (cur) {
-                    if (nr.metric < cur->metric) *cur = nr;
-                    else if (nr.metric == cur->metric) for (const Nh6 &x : nr.nh) nh_insert(cur->nh, x);
-                    route = cur;
-                } else if (it != rib_idx.end()) {
-                    rib[it->second] = nr; route = &rib[it->second];
-                } else {
-                    rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); route = &rib.back();
-                }
-                if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
-            }
-        }
-
-        // ---- export --------------------------------------------------------------------
-        uint32_t n_rtr = 0, need_h = 0, n_routes = 0;
-        for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr; need_h += (uint32_t)vnh[v].size(); } }
-        for (auto &kv : rib_idx) if (rib[kv.second].live) { ++n_routes; need_h += (uint32_t)rib[kv.second].nh.size(); }
-        out->n_vertices = (uint32_t)spt.size(); out->n_routers = n_rtr; out->n_routes = n_routes; out->n_nexthops = need_h;
-        bool tc = false;
-        for (uint32_t v : spt) if (f.is_router[v] && (a->router_lsas[f.first_lsa[v]].flags & HL_RTR_FLAG_V)) tc = true;
-        out->transit_capability = tc;
-        if (out->n_vertices > out->vertices_cap || n_rtr > out->routers_cap || n_routes > out->routes_cap ||
-            need_h > out->nexthops_cap)
-            return HSPF_E_NOMEM;
-        uint32_t h = 0;
-        auto put = [&](const std::vector<Nh6> &s) {
-            for (const Nh6 &x : s) {
-                hl_nexthop6 o{};
-                o.iface = x.iface; o.nbr_router_id = x.has_nbr ? x.nbr : 0;
-                if (x.has_addr) o.addr = x.addr;
-                o.has_addr = x.has_addr; o.has_nbr = x.has_nbr;
-                out->nexthops[h++] = o;
-            }
-        };
-        uint32_t i = 0;
-        for (uint32_t v : spt) {
-            hl_spt_vertex6 o{};
-            o.router_id = f.rid[v]; o.iface_id = f.ifid[v]; o.distance = dist[v]; o.hops = hops[v]; o.is_router = f.is_router[v];
-            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
-            put(vnh[v]);
-            out->vertices[i++] = o;
-        }
-        i = 0;
-        for (uint32_t v : spt) {
-            if (!f.is_router[v]) continue;
-            const auto &r = a->router_lsas[f.first_lsa[v]];
-            hl_route_rtr o{};
-            o.router_id = r.adv_rtr; o.metric = dist[v]; o.flags = r.flags; o.options = r.options;
-            o.nh_off = h; o.n_nh = (uint32_t)vnh[v].size();
-            put(vnh[v]);
-            out->routers[i++] = o;
-        }
-        i = 0;
-        for (auto &kv : rib_idx) {
-            const Route6 &r = rib[kv.second];
-            if (!r.live) continue;
-            hl_route_net6 o{};
-            o.prefix = r.prefix; o.len = r.len; o.flags = r.flags; o.origin_type = r.otype; o.prefix_options = r.options;
-            o.metric = r.metric; o.origin_adv_rtr = r.oadv; o.origin_lsa_id = r.oid; o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
-            put(r.nh);
-            out->routes[i++] = o;
-        }
-        return HSPF_OK;
-    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+/* The post-SPT half of hspf_ospfv3_run_area over planes the caller already has (vertex order of
+ * hspf_ospfv3_flatten, area->router_id as root).  Host only. */
+int hspf_ospfv3_area_from_planes(const hl_ospfv3_area *a, const uint32_t *dist, const uint16_t *hops,
+                                 const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv3_result *out) {
+    if (!a || !out || !dist || !hops || !nh_mask || nh_words < 1 || nh_words > 4) return HSPF_E_INVAL;
+    try {
+        out->n_vertices = out->n_routers = out->n_routes = out->n_nexthops = 0;
+        out->transit_capability = 0;
+        out->root_found = 0;
+        hspf_ospfv3_flat f;
+        int rc = flatten(a, f);
+        if (rc) return rc;
+        auto rit = f.rtr_vertex.find(a->router_id);
+        if (rit == f.rtr_vertex.end()) return HSPF_OK;
+        out->root_found = 1;
+        return area_from_planes(f, a, rit->second, dist, hops, nh_mask, nh_words, out);
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
 }
 
 }  // extern "C"

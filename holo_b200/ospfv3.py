@@ -127,7 +127,7 @@ class Ospfv3Result:
                 for x in self.nexthops[int(rec["nh_off"]): int(rec["nh_off"]) + int(rec["n_nh"])]]
 
 
-def _call_run_area(fn, area: Ospfv3Area, prefix_args=()):
+def _call_run_area(fn, area: Ospfv3Area, prefix_args=(), tail_args=()):
     s = area.as_struct()
     nv = len(area.router_lsas) + len(area.network_lsas) + 1
     n_routes = len(area.prefixes) + 1
@@ -142,7 +142,7 @@ def _call_run_area(fn, area: Ospfv3Area, prefix_args=()):
         r.routers_cap, r.routers = caps[1], rtrs.ctypes.data
         r.routes_cap, r.routes = caps[2], routes.ctypes.data
         r.nexthops_cap, r.nexthops = caps[3], nhs.ctypes.data
-        rc = fn(*prefix_args, C.byref(s), C.byref(r))
+        rc = fn(*prefix_args, C.byref(s), *tail_args, C.byref(r))
         if rc == capi.HSPF_E_NOMEM:
             caps = [max(caps[0], r.n_vertices), max(caps[1], r.n_routers), max(caps[2], r.n_routes),
                     max(caps[3], r.n_nexthops)]
@@ -158,6 +158,31 @@ def run_area(ctx: capi.Context, area: Ospfv3Area) -> Ospfv3Result:
     res = _call_run_area(lib.hspf_ospfv3_run_area, area, (ctx.handle,))
     if res.rc != capi.HSPF_OK:
         raise capi.HspfError(res.rc, ctx.last_error())
+    return res
+
+
+def area_from_planes(area: Ospfv3Area, spf) -> Ospfv3Result:
+    """hspf_ospfv3_area_from_planes over planes from `spf(csr, root_vertex, nh_words)` (host only;
+    see holo_b200.ospfv2.area_from_planes)."""
+    lib = capi.load_library()
+    lib.hspf_ospfv3_area_from_planes.argtypes = [C.POINTER(AreaStruct), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16),
+                                                 C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(ResultStruct)]
+    f = Flat(area)
+    root = f.router_vertex(area.router_id)
+    nhw = 4
+    if root == 0xFFFFFFFF:
+        V = f.csr.n_vertices
+        d, h, m = np.zeros(V, np.uint32), np.zeros(V, np.uint16), np.zeros((V, nhw), np.uint64)
+    else:
+        d, h, m = spf(f.csr, root, nhw)
+    d = np.ascontiguousarray(d, np.uint32)
+    h = np.ascontiguousarray(h, np.uint16)
+    m = np.ascontiguousarray(m, np.uint64)
+    tail = (d.ctypes.data_as(C.POINTER(C.c_uint32)), h.ctypes.data_as(C.POINTER(C.c_uint16)),
+            m.ctypes.data_as(C.POINTER(C.c_uint64)), nhw)
+    res = _call_run_area(lib.hspf_ospfv3_area_from_planes, area, (), tail)
+    if res.rc != capi.HSPF_OK:
+        raise capi.HspfError(res.rc, "hspf_ospfv3_area_from_planes failed")
     return res
 
 

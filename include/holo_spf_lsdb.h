@@ -60,6 +60,14 @@ uint32_t hspf_ospfv2_flat_network_vertex(const hspf_ospfv2_flat *flat, uint32_t 
  */
 int hspf_ospfv2_run_area(hspf_ctx *ctx, const hl_ospfv2_area *area, hl_ospfv2_result *out);
 
+/* The post-SPT half of hspf_ospfv2_run_area (Vertex.nexthops, router table, transit_capability,
+ * intra-area routes with SR labels) over planes the caller already has — e.g. one job of a
+ * what-if batch run through hspf_ospfv2_flatten + hspf_run_batch with area->router_id as root.
+ * Planes are indexed by the vertex order of hspf_ospfv2_flatten; nh_words as given to the engine
+ * (1..4).  Host only. */
+int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *area, const uint32_t *dist, const uint16_t *hops,
+                                 const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv2_result *out);
+
 /*
  * The stages of update_rib_full that follow the per-area SPFs (holo-ospf/src/route.rs:146-193):
  * merges the intra-area routes of the attached areas (route_update / route_compare,
@@ -93,6 +101,11 @@ int hspf_ospfv3_flat_vertices(const hspf_ospfv3_flat *flat, const uint32_t **rou
                               const uint8_t **is_router, uint32_t *n_vertices);
 uint32_t hspf_ospfv3_flat_router_vertex(const hspf_ospfv3_flat *flat, uint32_t router_id);
 int hspf_ospfv3_run_area(hspf_ctx *ctx, const hl_ospfv3_area *area, hl_ospfv3_result *out);
+
+/* The post-SPT half of hspf_ospfv3_run_area over caller-supplied planes (see
+ * hspf_ospfv2_area_from_planes).  Host only. */
+int hspf_ospfv3_area_from_planes(const hl_ospfv3_area *area, const uint32_t *dist, const uint16_t *hops,
+                                 const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv3_result *out);
 
 /* ---- IS-IS -------------------------------------------------------------------
  *   hspf_isis_compute_spt  <->  compute_spt(level, root_system_id, local = false,

@@ -233,3 +233,25 @@ def test_random_tables_v3_exercise_every_stage():
         kinds |= set(int(p) for p in rib.routes["path_type"])
         n_multi += int((rib.routes["n_nh"] > 1).sum())
     assert kinds == {0, 1, 2, 3} and n_multi > 20
+
+
+# ---- LSDB -> whole routing table through product host code only (SPT planes from the oracle) ----
+def _planes(csr, root, nh_words):
+    c = pyoracle.csr_spf(csr, root, nh_words=nh_words)
+    return c["dist"], c["hops"], c["nh_mask"]
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_product_host_pipeline_reproduces_reference_local_rib(snap):
+    got = gu.ospfv2_full_rib(snap, lambda img: ospfv2.area_from_planes(img, _planes), ospf_rib.update_rib_full)
+    assert got == {k: (m, t, [(a, b) for a, b in nh]) for k, (m, t, nh) in gu.golden_rib(snap).items()} or \
+        {k: (v[0], v[1], [(a or "", b or "") for a, b in v[2]]) for k, v in got.items()} == \
+        {k: (m, t, [(a or "", b or "") for a, b in nh]) for k, (m, t, nh) in gu.golden_rib(snap).items()}
+
+
+@pytest.mark.parametrize("snap", SNAPS_V3, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS_V3])
+def test_product_host_pipeline_v3_reproduces_reference_local_rib(snap):
+    from holo_b200 import ospfv3
+    got = gu.ospfv3_full_rib(snap, lambda img: ospfv3.area_from_planes(img, _planes), ospf_rib.update_rib_full_v3)
+    assert {k: (v[0], v[1], [(a or "", b or "") for a, b in v[2]]) for k, v in got.items()} == \
+        {k: (m, t, [(a or "", b or "") for a, b in nh]) for k, (m, t, nh) in gu.golden_rib(snap).items()}
