@@ -262,17 +262,6 @@ struct Resolver {
 
 struct RouterInfo { bool has_sr_algo = false; std::vector<const hl_srgb *> srgb; };
 
-RouterInfo router_info(const hl_ospfv2_area *a, uint32_t rid) {
-    RouterInfo ri;
-    for (uint32_t i = 0; i < a->n_ri_lsas; ++i) {
-        const auto &l = a->ri_lsas[i];
-        if (l.adv_rtr != rid || l.age == HL_LSA_MAX_AGE) continue;
-        if (l.has_sr_algo) ri.has_sr_algo = true;
-        for (uint32_t k = 0; k < l.n_srgb; ++k) ri.srgb.push_back(&a->srgbs[l.srgb_off + k]);
-    }
-    return ri;
-}
-
 bool index_to_label(uint32_t index, const std::vector<const hl_srgb *> &srgbs, uint32_t *label) {
     for (auto *s : srgbs) {
         if (s->first_is_index) continue;
@@ -430,11 +419,30 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
     std::unordered_map<uint64_t, uint32_t> rib_idx;
     std::vector<Route> rib;
     std::vector<uint8_t> rib_live;
+    {   // at most one entry per stub link / network vertex: no rehash, no vector regrowth
+        const size_t cap = (size_t)a->n_links + a->n_network_lsas + 1;
+        rib_idx.reserve(cap);
+        rib.reserve(cap);
+        rib_live.reserve(cap);
+    }
     RouterInfo local_ri; bool local_ri_loaded = false;
+    // per-router aggregate of the Router-Information LSAs (area_router_information,
+    // ospfv2/spf.rs:617-654), built in one pass over the LSDB-ordered array
     std::unordered_map<uint32_t, RouterInfo> ri_cache;
+    const RouterInfo no_ri;
+    if (a->sr_enabled) {
+        ri_cache.reserve(a->n_ri_lsas);
+        for (uint32_t i = 0; i < a->n_ri_lsas; ++i) {
+            const auto &l = a->ri_lsas[i];
+            if (l.age == HL_LSA_MAX_AGE) continue;
+            RouterInfo &ri = ri_cache[l.adv_rtr];
+            if (l.has_sr_algo) ri.has_sr_algo = true;
+            for (uint32_t k = 0; k < l.n_srgb; ++k) ri.srgb.push_back(&a->srgbs[l.srgb_off + k]);
+        }
+    }
     auto cached_ri = [&](uint32_t rid) -> const RouterInfo & {
         auto it = ri_cache.find(rid);
-        if (it == ri_cache.end()) it = ri_cache.emplace(rid, router_info(a, rid)).first;
+        if (it == ri_cache.end()) return no_ri;
         return it->second;
     };
 
@@ -466,7 +474,7 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
                 nr.sid_is_label = ep->sid_is_label;
                 if (!(local && (!(ep->sid_flags & HL_PSID_NP) || (ep->sid_flags & HL_PSID_E)))) {
                     if (!ep->sid_is_label) {
-                        if (!local_ri_loaded) { local_ri = router_info(a, a->router_id); local_ri_loaded = true; }
+                        if (!local_ri_loaded) { local_ri = cached_ri(a->router_id); local_ri_loaded = true; }
                         uint32_t lab;
                         if (!local_ri.srgb.empty() && index_to_label(ep->sid_value, local_ri.srgb, &lab)) {
                             nr.has_label = true; nr.label = lab;
@@ -497,12 +505,12 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
         // route_update
         Route *route;
         if (cur) {
-            if (nr.metric < cur->metric) *cur = nr;
+            if (nr.metric < cur->metric) *cur = std::move(nr);
             else if (nr.metric == cur->metric) for (const Nh &x : nr.nh) nh_insert(cur->nh, x);
             route = cur;
         } else {
-            if (it != rib_idx.end()) { rib[it->second] = nr; rib_live[it->second] = 1; route = &rib[it->second]; }
-            else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(nr); rib_live.push_back(1); route = &rib.back(); }
+            if (it != rib_idx.end()) { rib[it->second] = std::move(nr); rib_live[it->second] = 1; route = &rib[it->second]; }
+            else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(std::move(nr)); rib_live.push_back(1); route = &rib.back(); }
         }
         if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
     };
