@@ -20,7 +20,9 @@ MODE_NORMAL, MODE_HOPCOUNT = 0, 1
 REACH_DT = np.dtype([("neighbor", "<u8"), ("metric", "<u4"), ("mt_id", "<u2"), ("kind", "u1"), ("_pad", "u1")], align=True)
 LSP_DT = np.dtype([("lan_id", "<u8"), ("seqno", "<u4"), ("rem_lifetime", "<u2"), ("fragment", "u1"), ("flags", "u1"),
                    ("reach_off", "<u4"), ("n_reach", "<u4"), ("ipreach_off", "<u4"), ("n_ipreach", "<u4"),
-                   ("srgb_off", "<u4"), ("n_srgb", "<u2"), ("sr_flags", "u1"), ("_pad2", "u1")], align=True)
+                   ("srgb_off", "<u4"), ("n_srgb", "<u2"), ("sr_flags", "u1"), ("flood_algo", "u1")], align=True)
+FLOOD_ZERO_PRUNER, FLOOD_MODIFIED_MANET = 1, 2
+RNL_DT = np.dtype([("system_id", "<u8"), ("algo", "u1"), ("_pad", "u1", (7,))], align=True)
 LSP_SR_HAS_CAP, LSP_SR_ALGO_SPF, LSP_SR_CAP_V, LSP_SR_CAP_I = 0x01, 0x02, 0x40, 0x80
 PSID_R, PSID_N, PSID_P, PSID_E, PSID_V, PSID_L = 0x80, 0x40, 0x20, 0x10, 0x08, 0x04
 SRGB_DT = np.dtype([("first", "<u4"), ("range", "<u4"), ("first_is_index", "u1"), ("_pad", "u1", (3,))], align=True)
@@ -374,3 +376,57 @@ def routes_from_planes(inst: dict, spf) -> IsisRib:
     if res.rc != capi.HSPF_OK:
         raise capi.HspfError(res.rc, "hspf_isis_routes_from_planes failed")
     return res
+
+
+# ---- flooding reduction over hop-count SPTs (holo-isis/src/flooding/manet.rs) ------------------
+def _spt_struct(spt: IsisSpt, keep: list) -> SptStruct:
+    r = SptStruct()
+    for name, dt in (("vertices", VERTEX_DT), ("parents", np.uint32), ("nexthops", np.uint64),
+                     ("first_hops", np.uint32), ("second_hops", np.uint32)):
+        a = np.ascontiguousarray(getattr(spt, name), dtype=dt)
+        keep.append(a)
+        setattr(r, name + "_cap", len(a))
+        setattr(r, "n_" + name, len(a))
+        setattr(r, name, a.ctypes.data if len(a) else None)
+    return r
+
+
+def flood_reduction_hash(system_id: int, pseudonode: int, fragment: int, lib=None, name="hspf_isis_flood_reduction_hash") -> int:
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes, fn.restype = [C.c_uint64, C.c_uint8, C.c_uint8], C.c_uint16
+    return int(fn(system_id, pseudonode, fragment))
+
+
+def remote_neighbors(level: IsisLevel, spt: IsisSpt, lib=None, name="hspf_isis_remote_neighbors") -> np.ndarray:
+    """Remote Neighbor List of the neighbour whose hop-count SPT `spt` is (manet.rs:72-88)."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.POINTER(LevelStruct), C.POINTER(SptStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    ls, ss = level.as_struct(), _spt_struct(spt, keep)
+    out = np.zeros(max(len(spt.first_hops), 1), RNL_DT)
+    n = C.c_uint32()
+    rc = fn(C.byref(ls), C.byref(ss), out.ctypes.data, len(out), C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return out[: n.value].copy()
+
+
+def reflood_list(spt: IsisSpt, rnl: np.ndarray, local_system_id: int, lsp_system_id: int, lsp_pseudonode: int,
+                 lsp_fragment: int, lib=None, name="hspf_isis_reflood_list") -> list:
+    """reflood_list (manet.rs:99-173): the two-hop neighbours this router must reflood the LSP to."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.POINTER(SptStruct), C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint8, C.c_uint8,
+                   C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    ss = _spt_struct(spt, keep)
+    rnl = np.ascontiguousarray(rnl, dtype=RNL_DT)
+    out = np.zeros(max(len(spt.second_hops), 1), np.uint64)
+    n = C.c_uint32()
+    rc = fn(C.byref(ss), rnl.ctypes.data if len(rnl) else None, len(rnl), local_system_id, lsp_system_id, lsp_pseudonode,
+            lsp_fragment, out.ctypes.data, len(out), C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return [int(x) for x in out[: n.value]]

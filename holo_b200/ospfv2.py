@@ -85,7 +85,7 @@ ABI_SIZES = [
 
 def abi_sizes_expected():
     from . import isis, ospf_rib, ospfv3
-    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES
+    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES + [isis.RNL_DT.itemsize]
 
 
 def abi_sizes_from_library():

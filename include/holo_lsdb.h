@@ -540,8 +540,12 @@ typedef struct hl_isis_lsp {
     uint32_t  srgb_off;    /* into srgbs[]: label blocks of the SR-Capabilities sub-TLV (sr.rs:166-256) */
     uint16_t  n_srgb;
     uint8_t   sr_flags;    /* HL_LSP_SR_* */
-    uint8_t   _pad2;
+    uint8_t   flood_algo;  /* first Flooding-Algorithm sub-TLV of the Router Capability TLVs
+                              (packet/pdu.rs:1799-1805): 0 = absent, else the algorithm number */
 } hl_isis_lsp;
+
+#define HL_ISIS_FLOOD_ZERO_PRUNER    1u   /* FloodingAlgo (packet/iana.rs:249-253) */
+#define HL_ISIS_FLOOD_MODIFIED_MANET 2u
 
 /* hl_isis_lsp.sr_flags: first SR-Capabilities / SR-Algorithm sub-TLV of the LSP's Router
  * Capability TLVs (packet/pdu.rs:1785-1797) */
@@ -688,6 +692,14 @@ typedef struct hl_isis_rib {
     uint32_t routes_cap,   n_routes;    hl_isis_route *routes;
     uint32_t nexthops_cap, n_nexthops;  hl_isis_nexthop *nexthops;
 } hl_isis_rib;
+
+/* Remote Neighbor List entry of the modified-MANET flooding reduction (flooding/manet.rs:30-35):
+ * BTreeMap<SystemId, FloodingAlgo>, ascending system id. */
+typedef struct hl_isis_rnl_entry {
+    uint64_t system_id;
+    uint8_t  algo;          /* HL_ISIS_FLOOD_* */
+    uint8_t  _pad[7];
+} hl_isis_rnl_entry;
 
 typedef struct hl_isis_spt {
     uint32_t vertices_cap, n_vertices;  hl_isis_vertex *vertices;

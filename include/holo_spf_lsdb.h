@@ -150,6 +150,26 @@ int hspf_isis_routes_from_planes(const hl_isis_instance *inst, const uint32_t *d
 /* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
  * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
  * foreign binding verify its struct layouts at load time. */
+/* ---- IS-IS flooding reduction over the hop-count SPTs of the neighbour batch ------------
+ * (holo-isis/src/flooding/manet.rs).  manet::init_cache runs one hop-count
+ * compute_spt per up adjacency (row a16: one hspf_run_batch with HSPF_GF_HOPCOUNT), then per
+ * neighbour:
+ *   hspf_isis_remote_neighbors  <->  the Remote Neighbor List loop of init_cache (manet.rs:72-88):
+ *                                    first hops of the SPT with the flooding algorithm each
+ *                                    advertises (default ZeroPruner)
+ *   hspf_isis_reflood_list      <->  reflood_list (manet.rs:99-173) with Spt::is_on_path
+ *                                    (spf.rs:257-284) and second_hops
+ *   hspf_isis_flood_reduction_hash <-> flood_reduction_hash (manet.rs:189-193): Fletcher-16 of the
+ *                                    LSP id with fragment >> 3 (crate `fletcher` 1.0)
+ * `spt_hopcount` is the hl_isis_spt of the transmitting neighbour (hspf_isis_spt_from_planes /
+ * hspf_isis_compute_spt with HL_ISIS_MODE_HOPCOUNT).  Host only. */
+uint16_t hspf_isis_flood_reduction_hash(uint64_t lsp_system_id, uint8_t lsp_pseudonode, uint8_t lsp_fragment);
+int hspf_isis_remote_neighbors(const hl_isis_level *lvl, const hl_isis_spt *spt_hopcount,
+                               hl_isis_rnl_entry *out, uint32_t cap, uint32_t *n_out);
+int hspf_isis_reflood_list(const hl_isis_spt *spt_hopcount, const hl_isis_rnl_entry *rnl, uint32_t n_rnl,
+                           uint64_t local_system_id, uint64_t lsp_system_id, uint8_t lsp_pseudonode,
+                           uint8_t lsp_fragment, uint64_t *out, uint32_t cap, uint32_t *n_out);
+
 int hspf_abi_sizes(uint32_t *out, uint32_t cap);
 
 #ifdef __cplusplus
