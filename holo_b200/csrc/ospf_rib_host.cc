@@ -86,6 +86,19 @@ struct V2 {
     static uint8_t options(const NetIn &) { return 0; }
     static uint8_t options(const Sum &) { return 0; }
     static uint8_t options(const Ext &) { return 0; }
+    static void label_in(bool &has, uint32_t &label, const NetIn &r) { has = r.has_sr_label != 0; label = r.sr_label; }
+    static void label_out(Out &o, bool has, uint32_t label) { o.has_sr_label = has ? 1 : 0; o.sr_label = has ? label : 0; }
+    static bool same_label(const Out &a, const Out &b) {
+        return a.has_sr_label == b.has_sr_label && (!a.has_sr_label || a.sr_label == b.sr_label);
+    }
+    static void old_label(hl_rib_action &act, const Out &o) { act.has_old_sr_label = o.has_sr_label; act.old_sr_label = o.has_sr_label ? o.sr_label : 0; }
+    static bool same_prefix(const Out &a, const Out &b) { return a.prefix == b.prefix && a.mask == b.mask; }
+    static bool prefix_less(const Out &a, const Out &b) { return a.prefix != b.prefix ? a.prefix < b.prefix : a.mask < b.mask; }
+    static bool same_hop(const Nh &a, const Nh &b) {
+        return a.iface == b.iface && a.has_addr == b.has_addr && (!a.has_addr || a.addr == b.addr) && a.has_nbr == b.has_nbr &&
+               (!a.has_nbr || a.nbr_router_id == b.nbr_router_id) && a.has_label == b.has_label &&
+               (!a.has_label || a.sr_label == b.sr_label);
+    }
     static void addr_key(const Nh &n, std::array<uint8_t, 16> &kb) {
         kb.fill(0);
         if (n.has_addr) { kb[0] = (uint8_t)(n.addr >> 24); kb[1] = (uint8_t)(n.addr >> 16); kb[2] = (uint8_t)(n.addr >> 8); kb[3] = (uint8_t)n.addr; }
@@ -114,6 +127,19 @@ struct V3 {
     static uint8_t options(const NetIn &r) { return r.prefix_options; }
     static uint8_t options(const Sum &l) { return l.prefix_options; }
     static uint8_t options(const Ext &l) { return l.prefix_options; }
+    static void label_in(bool &, uint32_t &, const NetIn &) {}
+    static void label_out(Out &, bool, uint32_t) {}
+    static bool same_label(const Out &, const Out &) { return true; }
+    static void old_label(hl_rib_action &, const Out &) {}
+    static bool same_prefix(const Out &a, const Out &b) { return a.len == b.len && std::memcmp(a.prefix.bytes, b.prefix.bytes, 16) == 0; }
+    static bool prefix_less(const Out &a, const Out &b) {
+        const int c = std::memcmp(a.prefix.bytes, b.prefix.bytes, 16);
+        return c != 0 ? c < 0 : a.len < b.len;
+    }
+    static bool same_hop(const Nh &a, const Nh &b) {
+        return a.iface == b.iface && a.has_addr == b.has_addr && (!a.has_addr || std::memcmp(a.addr.bytes, b.addr.bytes, 16) == 0) &&
+               a.has_nbr == b.has_nbr && (!a.has_nbr || a.nbr_router_id == b.nbr_router_id);
+    }
     static void addr_key(const Nh &n, std::array<uint8_t, 16> &kb) {
         kb.fill(0);
         if (n.has_addr) std::memcpy(kb.data(), n.addr.bytes, 16);
@@ -138,6 +164,8 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
         uint8_t path, flags, options;
         bool has_area, has_type2;
         Hops hops;
+        bool has_label = false;
+        uint32_t label = 0;
     };
     struct Rtr {
         uint32_t area, metric;
@@ -215,8 +243,10 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
             const PKey k = T::key(r);
             if (const Net *cur = find(k))
                 if (r.metric > cur->metric) continue;
-            offer(Net{k, r.metric, 0, 0, a.area_id, HL_PATH_INTRA_AREA, r.flags, T::options(r), true, false,
-                      hops_of(a, r.nh_off, r.n_nh)});
+            Net n{k, r.metric, 0, 0, a.area_id, HL_PATH_INTRA_AREA, r.flags, T::options(r), true, false,
+                  hops_of(a, r.nh_off, r.n_nh)};
+            T::label_in(n.has_label, n.label, r);
+            offer(std::move(n));
         }
     }
 
@@ -314,9 +344,63 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
         o.metric = n.metric; o.type2_metric = n.type2; o.tag = n.tag; o.area_id = n.area; o.path_type = n.path;
         o.flags = n.flags; o.has_area = n.has_area ? 1 : 0; o.has_type2 = n.has_type2 ? 1 : 0;
         o.nh_off = h; o.n_nh = (uint32_t)n.hops.size();
+        T::label_out(o, n.has_label, n.label);
         for (const Hop &x : n.hops) out->nexthops[h++] = x.nh;
         out->routes[r] = o;
     }
+    return HSPF_OK;
+}
+
+// update_global_rib (route.rs:833-893): both tables are in prefix order, so one merge walk
+template <class T>
+int rib_diff(const typename T::Rib *old_rib, typename T::Rib *new_rib, hl_rib_action *out, uint32_t cap, uint32_t *n_out) {
+    if (!new_rib || !n_out || (cap && !out)) return HSPF_E_INVAL;
+    if ((new_rib->n_routes && !new_rib->routes) || (new_rib->n_nexthops && !new_rib->nexthops)) return HSPF_E_INVAL;
+    const uint32_t n_old = old_rib ? old_rib->n_routes : 0;
+    if (old_rib && ((n_old && !old_rib->routes) || (old_rib->n_nexthops && !old_rib->nexthops))) return HSPF_E_INVAL;
+    auto metric_of = [](const typename T::Out &r) { return r.path_type == HL_PATH_TYPE2_EXTERNAL ? r.type2_metric : r.metric; };
+    std::vector<hl_rib_action> acts;
+    auto push = [&](uint8_t kind, uint32_t route, const typename T::Out *replaced) {
+        hl_rib_action a;
+        std::memset(&a, 0, sizeof(a));
+        a.kind = kind; a.route = route;
+        if (replaced) T::old_label(a, *replaced);
+        acts.push_back(a);
+    };
+    std::vector<uint32_t> gone;       // old routes without a successor, installed
+    uint32_t io = 0;
+    for (uint32_t in = 0; in < new_rib->n_routes; ++in) {
+        typename T::Out &r = new_rib->routes[in];
+        while (io < n_old && T::prefix_less(old_rib->routes[io], r)) {
+            if (old_rib->routes[io].flags & HL_ROUTE_INSTALLED) gone.push_back(io);
+            ++io;
+        }
+        const typename T::Out *o = (io < n_old && T::same_prefix(old_rib->routes[io], r)) ? &old_rib->routes[io++] : nullptr;
+        if (o) {
+            bool same = metric_of(*o) == metric_of(r) && o->tag == r.tag && T::same_label(*o, r) && o->n_nh == r.n_nh;
+            for (uint32_t k = 0; same && k < r.n_nh; ++k)
+                same = T::same_hop(old_rib->nexthops[o->nh_off + k], new_rib->nexthops[r.nh_off + k]);
+            if (same) {
+                if (o->flags & HL_ROUTE_INSTALLED) r.flags |= HL_ROUTE_INSTALLED;
+                continue;
+            }
+        }
+        if (!(r.flags & HL_ROUTE_CONNECTED) && r.n_nh != 0) {
+            push(HL_RIB_INSTALL, in, o);
+            r.flags |= HL_ROUTE_INSTALLED;
+        } else if (r.flags & HL_ROUTE_INSTALLED) {
+            // only for tables a caller carries over: update_rib_full builds every route with
+            // empty or CONNECTED flags, so after a full run this branch is not taken
+            push(HL_RIB_UNINSTALL, in, nullptr);
+            r.flags &= (uint8_t)~HL_ROUTE_INSTALLED;
+        }
+    }
+    for (; io < n_old; ++io)
+        if (old_rib->routes[io].flags & HL_ROUTE_INSTALLED) gone.push_back(io);
+    for (uint32_t i : gone) push(HL_RIB_UNINSTALL_OLD, i, nullptr);
+    *n_out = (uint32_t)acts.size();
+    if (acts.size() > cap) return HSPF_E_NOMEM;
+    for (size_t i = 0; i < acts.size(); ++i) out[i] = acts[i];
     return HSPF_OK;
 }
 
@@ -343,4 +427,16 @@ extern "C" int hspf_ospfv3_update_rib_full(uint32_t router_id, uint32_t max_path
                                            uint32_t n_areas, const hl_ospfv3_external_lsa *ext, uint32_t n_ext,
                                            hl_ospfv3_rib *out) {
     return guarded<V3>(router_id, max_paths, areas, n_areas, ext, n_ext, out);
+}
+
+extern "C" int hspf_ospfv2_rib_diff(const hl_ospfv2_rib *old_rib, hl_ospfv2_rib *new_rib, hl_rib_action *out, uint32_t cap,
+                                    uint32_t *n_out) {
+    try { return rib_diff<V2>(old_rib, new_rib, out, cap, n_out); }
+    catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
+extern "C" int hspf_ospfv3_rib_diff(const hl_ospfv3_rib *old_rib, hl_ospfv3_rib *new_rib, hl_rib_action *out, uint32_t cap,
+                                    uint32_t *n_out) {
+    try { return rib_diff<V3>(old_rib, new_rib, out, cap, n_out); }
+    catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
 }

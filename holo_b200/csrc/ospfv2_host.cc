@@ -362,8 +362,10 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
         (uint32_t)sizeof(hl_ospfv2_rib_area), (uint32_t)sizeof(hl_rib_route), (uint32_t)sizeof(hl_ospfv2_rib),
         (uint32_t)sizeof(hl_ospfv3_inter_area_lsa), (uint32_t)sizeof(hl_ospfv3_external_lsa),
         (uint32_t)sizeof(hl_ospfv3_rib_area), (uint32_t)sizeof(hl_rib_route6), (uint32_t)sizeof(hl_ospfv3_rib),
+        (uint32_t)sizeof(hl_rib_action),
         (uint32_t)sizeof(hl_isis_rnl_entry),
     };
+    static_assert(sizeof(hl_rib_action) == 12, "hl_rib_action layout");
     const uint32_t n = sizeof(v) / sizeof(v[0]);
     if (!out || cap < n) return (int)n;
     for (uint32_t i = 0; i < n; ++i) out[i] = v[i];

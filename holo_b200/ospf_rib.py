@@ -23,7 +23,12 @@ EXTERNAL_LSA_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("mask", "<u4
                             ("_pad", "u1", (2,))], align=True)
 RIB_ROUTE_DT = np.dtype([("prefix", "<u4"), ("mask", "<u4"), ("metric", "<u4"), ("type2_metric", "<u4"),
                          ("tag", "<u4"), ("area_id", "<u4"), ("path_type", "u1"), ("flags", "u1"), ("has_area", "u1"),
-                         ("has_type2", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+                         ("has_type2", "u1"), ("nh_off", "<u4"), ("n_nh", "<u4"), ("sr_label", "<u4"),
+                         ("has_sr_label", "u1"), ("_pad", "u1", (3,))], align=True)
+ROUTE_CONNECTED, ROUTE_INSTALLED = 0x01, 0x02
+RIB_INSTALL, RIB_UNINSTALL, RIB_UNINSTALL_OLD = 1, 2, 3
+ACTION_DT = np.dtype([("route", "<u4"), ("old_sr_label", "<u4"), ("kind", "u1"), ("has_old_sr_label", "u1"),
+                      ("_pad", "u1", (2,))], align=True)
 
 
 # OSPFv3 twins (hl_ospfv3_inter_area_lsa, hl_ospfv3_external_lsa, hl_rib_route6)
@@ -63,7 +68,8 @@ class RibStruct(C.Structure):
 ABI_SIZES = [SUMMARY_LSA_DT.itemsize, EXTERNAL_LSA_DT.itemsize, C.sizeof(RibAreaStruct), RIB_ROUTE_DT.itemsize,
              C.sizeof(RibStruct),
              INTER_AREA_LSA_DT.itemsize, EXTERNAL6_LSA_DT.itemsize, C.sizeof(RibAreaStruct), RIB_ROUTE6_DT.itemsize,
-             C.sizeof(RibStruct)]       # hl_ospfv3_rib_area / hl_ospfv3_rib have the layouts of the v2 structs
+             C.sizeof(RibStruct),       # hl_ospfv3_rib_area / hl_ospfv3_rib have the layouts of the v2 structs
+             ACTION_DT.itemsize]
 
 
 @dataclass
@@ -165,3 +171,42 @@ def update_rib_full_v3(router_id: int, max_paths: int, areas: list, externals=No
     if rib.rc != capi.HSPF_OK:
         raise capi.HspfError(rib.rc, "hspf_ospfv3_update_rib_full failed")
     return rib
+
+
+def _rib_struct(rib: Rib, keep: list, route_dt, nh_dt) -> RibStruct:
+    r = RibStruct()
+    routes = np.ascontiguousarray(rib.routes, dtype=route_dt)
+    nhs = np.ascontiguousarray(rib.nexthops, dtype=nh_dt)
+    keep += [routes, nhs]
+    r.routes_cap = r.n_routes = len(routes)
+    r.nexthops_cap = r.n_nexthops = len(nhs)
+    r.routes = routes.ctypes.data if len(routes) else None
+    r.nexthops = nhs.ctypes.data if len(nhs) else None
+    return r
+
+
+def call_rib_diff(fn, old, new: Rib, v3: bool = False):
+    """update_global_rib: returns (actions ACTION_DT[], new routes with HL_ROUTE_INSTALLED set as the
+    reference would).  `fn` = hspf_ospfv{2,3}_rib_diff or the oracle's twin; `old` may be None."""
+    ROUTE_DT_, NH_DT_ = _version(v3)[5:7]
+    fn.argtypes = [C.c_void_p, C.POINTER(RibStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    ns = _rib_struct(new, keep, ROUTE_DT_, NH_DT_)
+    new_routes = keep[0]
+    if new_routes is new.routes:                  # never write into the caller's array
+        new_routes = new_routes.copy()
+        keep[0] = new_routes
+        ns.routes = new_routes.ctypes.data if len(new_routes) else None
+    os_ = _rib_struct(old, keep, ROUTE_DT_, NH_DT_) if old is not None else None
+    cap = len(new.routes) + (len(old.routes) if old is not None else 0) + 1
+    acts = np.zeros(cap, ACTION_DT)
+    n = C.c_uint32()
+    rc = fn(C.addressof(os_) if os_ is not None else None, C.byref(ns), acts.ctypes.data, cap, C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "rib_diff failed")
+    return acts[: n.value].copy(), new_routes
+
+
+def rib_diff(old, new: Rib, v3: bool = False):
+    lib = capi.load_library()
+    return call_rib_diff(lib.hspf_ospfv3_rib_diff if v3 else lib.hspf_ospfv2_rib_diff, old, new, v3)

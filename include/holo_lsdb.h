@@ -278,12 +278,29 @@ typedef struct hl_rib_route {
     uint32_t tag;
     uint32_t area_id;
     uint8_t  path_type;    /* HL_PATH_*                                            */
-    uint8_t  flags;        /* HL_ROUTE_CONNECTED                                   */
+    uint8_t  flags;        /* HL_ROUTE_CONNECTED | HL_ROUTE_INSTALLED              */
     uint8_t  has_area;
     uint8_t  has_type2;
     uint32_t nh_off;
     uint32_t n_nh;
+    uint32_t sr_label;     /* input label of an intra-area route (from hl_route_net)  */
+    uint8_t  has_sr_label;
+    uint8_t  _pad[3];
 } hl_rib_route;
+
+#define HL_ROUTE_INSTALLED 0x02u   /* RouteNetFlags::INSTALLED (route.rs:50-55) */
+
+/* One message to the RIB manager produced by update_global_rib (route.rs:833-893). */
+#define HL_RIB_INSTALL        1u   /* ibus route_install of new_rib.routes[route]                   */
+#define HL_RIB_UNINSTALL      2u   /* new_rib.routes[route] was installed and no longer can be       */
+#define HL_RIB_UNINSTALL_OLD  3u   /* old_rib.routes[route]: the prefix is gone from the table       */
+typedef struct hl_rib_action {
+    uint32_t route;
+    uint32_t old_sr_label; /* label of the replaced route (route_install's old_sr_label)             */
+    uint8_t  kind;
+    uint8_t  has_old_sr_label;
+    uint8_t  _pad[2];
+} hl_rib_action;
 
 typedef struct hl_ospfv2_rib {
     uint32_t routes_cap,   n_routes;     hl_rib_route *routes;

@@ -82,6 +82,21 @@ int hspf_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl
                                 uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,
                                 hl_ospfv2_rib *out);
 
+/*
+ * update_global_rib (holo-ospf/src/route.rs:833-893): compares the freshly computed table with
+ * the previous one and lists the installs / uninstalls the RIB manager has to see, in the
+ * reference's order (new table in prefix order, then vanished prefixes in prefix order).  A route
+ * is reinstalled unless metric(), tag, sr_label and the next-hop set are all unchanged; connected
+ * routes and routes without next hops are never installed.  `new_rib->routes[].flags` receive
+ * HL_ROUTE_INSTALLED as the reference sets it (the next call's `old_rib`).  `old_rib` may be NULL
+ * (first computation).  Inter-area routes carry no SR label here (the stage does not run
+ * prefix_sid_update for Summary-LSAs).  Host only.
+ */
+int hspf_ospfv2_rib_diff(const hl_ospfv2_rib *old_rib, hl_ospfv2_rib *new_rib, hl_rib_action *out, uint32_t cap,
+                         uint32_t *n_out);
+int hspf_ospfv3_rib_diff(const hl_ospfv3_rib *old_rib, hl_ospfv3_rib *new_rib, hl_rib_action *out, uint32_t cap,
+                         uint32_t *n_out);
+
 /* The OSPFv3 twin (Inter-Area-Prefix / Inter-Area-Router / AS-External LSAs,
  * holo-ospf/src/ospfv3/spf.rs:479-560; prefixes with the NU option are skipped). */
 int hspf_ospfv3_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv3_rib_area *areas,

@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE — CPU restatement of the OSPF routing-table stages that follow
 // the per-area SPFs in the reference (generic over the OSPF version there, a template here): update_rib_full (holo-ospf/src/route.rs:146-193) with
 // update_rib_inter_area_networks (:449-533), update_rib_inter_area_routers (:653-714),
-// update_rib_transit_area (:535-650), update_rib_external (:717-827), route_update (:895-942)
-// and route_compare (:944-971).  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs
+// update_rib_transit_area (:535-650), update_rib_external (:717-827), update_global_rib (:833-893),
+// route_update (:895-942) and route_compare (:944-971).  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs
 // may use anything under oracle/.
 //
 // Pinned by: the 63 golden OSPFv2 snapshots of the reference's conformance topologies
@@ -72,6 +72,18 @@ struct V2 {   // Ospfv2
     static uint8_t opts(const hl_route_net &) { return 0; }
     static uint8_t opts(const Sum &) { return 0; }
     static uint8_t opts(const Ext &) { return 0; }
+    static void label(bool &has, uint32_t &lab, const hl_route_net &r) { has = r.has_sr_label; lab = r.sr_label; }
+    static void put_label(Out &o, bool has, uint32_t lab) { o.has_sr_label = has; o.sr_label = has ? lab : 0; }
+    static bool label_eq(const Out &a, const Out &b) {          // Option<Label> ==
+        return a.has_sr_label == b.has_sr_label && (!a.has_sr_label || a.sr_label == b.sr_label);
+    }
+    static void old_label(hl_rib_action &x, const Out &o) { x.has_old_sr_label = o.has_sr_label; x.old_sr_label = o.has_sr_label ? o.sr_label : 0; }
+    static Prefix of(const Out &o) { return v4(o.prefix, o.mask); }
+    static bool nh_eq(const Nh &a, const Nh &b) {               // Nexthop ==, field by field
+        return a.iface == b.iface && a.has_addr == b.has_addr && (!a.has_addr || a.addr == b.addr) &&
+               a.has_nbr == b.has_nbr && (!a.has_nbr || a.nbr_router_id == b.nbr_router_id) &&
+               a.has_label == b.has_label && (!a.has_label || a.sr_label == b.sr_label);
+    }
     static NhKey key(uint32_t sk, const Nh &n) {
         NhKey k{};
         k.iface = sk; k.has_addr = n.has_addr;
@@ -97,6 +109,15 @@ struct V3 {   // Ospfv3
     static uint8_t opts(const hl_route_net6 &r) { return r.prefix_options; }
     static uint8_t opts(const Sum &l) { return l.prefix_options; }
     static uint8_t opts(const Ext &l) { return l.prefix_options; }
+    static void label(bool &, uint32_t &, const hl_route_net6 &) {}
+    static void put_label(Out &, bool, uint32_t) {}
+    static bool label_eq(const Out &, const Out &) { return true; }
+    static void old_label(hl_rib_action &, const Out &) {}
+    static Prefix of(const Out &o) { return v6(o.prefix, o.len); }
+    static bool nh_eq(const Nh &a, const Nh &b) {
+        return a.iface == b.iface && a.has_addr == b.has_addr && (!a.has_addr || std::memcmp(a.addr.bytes, b.addr.bytes, 16) == 0) &&
+               a.has_nbr == b.has_nbr && (!a.has_nbr || a.nbr_router_id == b.nbr_router_id);
+    }
     static NhKey key(uint32_t sk, const Nh &n) {
         NhKey k{};
         k.iface = sk; k.has_addr = n.has_addr;
@@ -123,6 +144,8 @@ struct Stage {
         uint32_t tag = 0;
         uint8_t flags = 0;
         uint8_t prefix_options = 0;
+        bool has_label = false;      // sr_label of an intra-area route
+        uint32_t label = 0;
         Nexthops nexthops;
     };
     struct RouteRtr {   // route.rs:57-66
@@ -199,6 +222,7 @@ struct Stage {
                 RouteNet n;
                 n.path_type = HL_PATH_INTRA_AREA; n.has_area = true; n.area_id = a.area_id; n.metric = r.metric;
                 n.flags = r.flags; n.prefix_options = V::opts(r); n.nexthops = lift(a, r.nh_off, r.n_nh);
+                V::label(n.has_label, n.label, r);
                 route_update(rib, p, std::move(n), max_paths);
             }
         }
@@ -310,6 +334,7 @@ struct Stage {
             o.type2_metric = kv.second.type2_metric; o.has_type2 = kv.second.has_type2; o.tag = kv.second.tag;
             o.area_id = kv.second.area_id; o.has_area = kv.second.has_area; o.path_type = kv.second.path_type;
             o.flags = kv.second.flags; o.nh_off = h; o.n_nh = (uint32_t)kv.second.nexthops.size();
+            V::put_label(o, kv.second.has_label, kv.second.label);
             for (auto &nk : kv.second.nexthops) out->nexthops[h++] = nk.second;
             out->routes[ri++] = o;
         }
@@ -317,7 +342,61 @@ struct Stage {
     }
 };
 
+// update_global_rib (route.rs:833-893): which installs / uninstalls the RIB manager sees
+template <class V>
+int global_rib(const typename V::Rib *old_rib, typename V::Rib *rib, hl_rib_action *out, uint32_t cap, uint32_t *n_out) {
+    std::map<Prefix, uint32_t> old;                       // mut old_rib
+    if (old_rib)
+        for (uint32_t i = 0; i < old_rib->n_routes; ++i) old[V::of(old_rib->routes[i])] = i;
+    std::vector<hl_rib_action> acts;
+    auto metric = [](const typename V::Out &r) { return r.path_type == HL_PATH_TYPE2_EXTERNAL ? r.type2_metric : r.metric; };
+    for (uint32_t i = 0; i < rib->n_routes; ++i) {        // the new table is in prefix order
+        typename V::Out &route = rib->routes[i];
+        hl_rib_action a{};
+        a.route = i;
+        auto it = old.find(V::of(route));
+        if (it != old.end()) {
+            const typename V::Out &o = old_rib->routes[it->second];
+            old.erase(it);                                 // old_rib.remove(prefix)
+            V::old_label(a, o);
+            bool same = metric(o) == metric(route) && o.tag == route.tag && V::label_eq(o, route) && o.n_nh == route.n_nh;
+            for (uint32_t k = 0; same && k < route.n_nh; ++k)
+                same = V::nh_eq(old_rib->nexthops[o.nh_off + k], rib->nexthops[route.nh_off + k]);
+            if (same) {                                    // skip reinstalling
+                if (o.flags & HL_ROUTE_INSTALLED) route.flags |= HL_ROUTE_INSTALLED;
+                continue;
+            }
+        }
+        if (!(route.flags & HL_ROUTE_CONNECTED) && route.n_nh != 0) {
+            a.kind = HL_RIB_INSTALL;
+            acts.push_back(a);
+            route.flags |= HL_ROUTE_INSTALLED;
+        } else if (route.flags & HL_ROUTE_INSTALLED) {
+            a.kind = HL_RIB_UNINSTALL; a.has_old_sr_label = 0; a.old_sr_label = 0;
+            acts.push_back(a);
+            route.flags &= (uint8_t)~HL_ROUTE_INSTALLED;
+        }
+    }
+    for (auto &kv : old) {                                 // routes that are no longer available
+        if (!(old_rib->routes[kv.second].flags & HL_ROUTE_INSTALLED)) continue;
+        hl_rib_action a{};
+        a.kind = HL_RIB_UNINSTALL_OLD; a.route = kv.second;
+        acts.push_back(a);
+    }
+    *n_out = (uint32_t)acts.size();
+    if (acts.size() > cap) return HSPF_E_NOMEM;
+    for (size_t i = 0; i < acts.size(); ++i) out[i] = acts[i];
+    return HSPF_OK;
+}
+
 }  // namespace
+
+extern "C" int oracle_ospfv2_rib_diff(const hl_ospfv2_rib *o, hl_ospfv2_rib *n, hl_rib_action *out, uint32_t cap, uint32_t *n_out) {
+    return global_rib<V2>(o, n, out, cap, n_out);
+}
+extern "C" int oracle_ospfv3_rib_diff(const hl_ospfv3_rib *o, hl_ospfv3_rib *n, hl_rib_action *out, uint32_t cap, uint32_t *n_out) {
+    return global_rib<V3>(o, n, out, cap, n_out);
+}
 
 extern "C" int oracle_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv2_rib_area *areas,
                                              uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,

@@ -42,6 +42,28 @@ def ifindex_map(events_path: Path):
     return m
 
 
+def ibus_routes(path: Path):
+    """Final state of the RouteIpAdd / RouteIpDel stream the instance sent to the RIB manager
+    (output/ibus.jsonl; produced by update_global_rib, holo-ospf/src/route.rs:833-893):
+    {prefix: {"metric", "distance", "nexthops": [[ifindex, addr, [labels]]]}}, or None without the file."""
+    if not path.exists():
+        return None
+    out = {}
+    for line in path.read_text().splitlines():
+        try:
+            msg = json.loads(line)
+        except json.JSONDecodeError:
+            continue
+        if "RouteIpAdd" in msg:
+            r = msg["RouteIpAdd"]
+            nh = [[n["Address"]["ifindex"], n["Address"].get("addr"), n["Address"].get("labels", [])]
+                  for n in r.get("nexthops", []) if "Address" in n]
+            out[r["prefix"]] = {"metric": r["metric"], "distance": r["distance"], "tag": r.get("tag"), "nexthops": nh}
+        elif "RouteIpDel" in msg:
+            out.pop(msg["RouteIpDel"]["prefix"], None)
+    return out
+
+
 def extract_ospfv2(ref: Path):
     base = ref / "holo-ospf/tests/conformance/ospfv2/topologies"
     out = []
@@ -119,6 +141,7 @@ def extract_ospfv2(ref: Path):
                        for n in r.get("next-hops", {}).get("next-hop", [])]
                 snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
                                           "type": r.get("route-type"), "nexthops": nhs})
+            snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
             out.append(snap)
     return out
 
@@ -202,6 +225,8 @@ def extract_ospfv3(ref: Path):
                        for n in r.get("next-hops", {}).get("next-hop", [])]
                 snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
                                           "type": r.get("route-type"), "nexthops": nhs})
+            snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
+            snap["ifindex"] = ifindex_map(rt / "events.jsonl")
             out.append(snap)
     return out
 

@@ -416,3 +416,38 @@ def isis_instance_image(snap, level):
                 ifaces=np.asarray(ifaces, dtype=isis.IFACE_DT) if ifaces else np.zeros(0, isis.IFACE_DT),
                 adjs=np.asarray(adjs, dtype=isis.ADJ_DT) if adjs else np.zeros(0, isis.ADJ_DT), ifnames=names)
     return inst
+
+
+# ------------------------------------------------------------------------------ RIB manager stream
+def installs_from_empty(snap, rib, diff, v3=False):
+    """{prefix: (metric, sorted [(ifindex, addr)])} of the routes update_global_rib installs when the
+    previous table is empty, with interfaces named by system ifindex like the RouteIpAdd messages
+    of the reference (output/ibus.jsonl)."""
+    from holo_b200 import ospf_rib, ospfv3
+    keys = global_sort_keys(snap)
+    key_name = {v: k for k, v in keys.items()}
+    acts, routes = diff(None, rib)
+    assert all(int(a["kind"]) == ospf_rib.RIB_INSTALL for a in acts)
+    out = {}
+    for a in acts:
+        r = rib.routes[int(a["route"])]
+        assert routes[int(a["route"])]["flags"] & ospf_rib.ROUTE_INSTALLED
+        hops = rib.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        if v3:
+            pfx = f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"
+            nh = sorted((snap["ifindex"].get(key_name[int(x["iface"])], 0), ospfv3.ip_str(x["addr"]) if x["has_addr"] else None)
+                        for x in hops)
+        else:
+            pfx = f"{ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}"
+            nh = sorted((snap["ifindex"].get(key_name[int(x["iface"])], 0), ipstr(x["addr"]) if x["has_addr"] else None)
+                        for x in hops)
+        out[pfx] = (int(r["type2_metric"] if int(r["path_type"]) == 3 else r["metric"]), nh)
+    # routes that are not installed: connected, or without next hops
+    for i, r in enumerate(rib.routes):
+        if not (routes[i]["flags"] & ospf_rib.ROUTE_INSTALLED):
+            assert (int(r["flags"]) & ospf_rib.ROUTE_CONNECTED) or int(r["n_nh"]) == 0
+    return out
+
+
+def golden_ibus(snap):
+    return {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in snap["ibus_routes"].items()}

@@ -255,3 +255,66 @@ def test_product_host_pipeline_v3_reproduces_reference_local_rib(snap):
     got = gu.ospfv3_full_rib(snap, lambda img: ospfv3.area_from_planes(img, _planes), ospf_rib.update_rib_full_v3)
     assert {k: (v[0], v[1], [(a or "", b or "") for a, b in v[2]]) for k, v in got.items()} == \
         {k: (m, t, [(a or "", b or "") for a, b in nh]) for k, (m, t, nh) in gu.golden_rib(snap).items()}
+
+
+# ---- update_global_rib: the messages to the RIB manager ------------------------------------------
+IBUS_V2 = [s for s in SNAPS if s.get("ibus_routes") is not None]
+IBUS_V3 = [s for s in SNAPS_V3 if s.get("ibus_routes") is not None]
+
+
+@pytest.mark.parametrize("snap", IBUS_V2, ids=[f"{s['topo']}-{s['rt']}" for s in IBUS_V2])
+def test_installs_equal_the_reference_ibus_stream(snap):
+    """LSDB -> routing table -> update_global_rib from an empty table, all through product host code
+    (SPT planes from the oracle): exactly the RouteIpAdd set the reference sent to the RIB manager
+    (output/ibus.jsonl), prefix by prefix with metric, ifindex and next-hop address."""
+    areas_rib = gu.ospfv2_full_rib  # noqa: F841  (same pipeline, kept as structured arrays below)
+    keys = gu.global_sort_keys(snap)
+    areas = []
+    for area in snap["areas"]:
+        img = gu.ospfv2_area_image(snap, area, keys)
+        res = ospfv2.area_from_planes(img, _planes)
+        if res.root_found:
+            active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+            areas.append(ospf_rib.RibArea(gu.ip(area["area_id"]), res, img.ifaces, gu.ospfv2_summaries(area), active))
+    rib = ospf_rib.update_rib_full(gu.ip(snap["router_id"]), 16, areas)
+    got = gu.installs_from_empty(snap, rib, ospf_rib.rib_diff)
+    assert got == gu.golden_ibus(snap)
+    # and the restatement says the same
+    want = gu.installs_from_empty(snap, rib, lambda o, n: ospf_rib.call_rib_diff(pyoracle.lib().oracle_ospfv2_rib_diff, o, n))
+    assert got == want
+
+
+@pytest.mark.parametrize("snap", IBUS_V3, ids=[f"{s['topo']}-{s['rt']}" for s in IBUS_V3])
+def test_installs_v3_equal_the_reference_ibus_stream(snap):
+    from holo_b200 import ospfv3
+    keys = gu.global_sort_keys(snap)
+    areas = []
+    for area in snap["areas"]:
+        img = gu.ospfv3_area_image(snap, area, keys)
+        res = ospfv3.area_from_planes(img, _planes)
+        if res.root_found:
+            active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+            areas.append(ospf_rib.RibArea(gu.ip(area["area_id"]), res, img.ifaces, gu.ospfv3_inter_area_lsas(area), active))
+    rib = ospf_rib.update_rib_full_v3(gu.ip(snap["router_id"]), 16, areas)
+    got = gu.installs_from_empty(snap, rib, lambda o, n: ospf_rib.rib_diff(o, n, v3=True), v3=True)
+    assert got == gu.golden_ibus(snap)
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_rib_diff_matches_restatement_on_random_table_pairs(seed):
+    """Two random tables of the same instance (the second one perturbed): product vs restatement,
+    action by action and flag by flag, then the second diff with the flags of the first."""
+    router_id, max_paths, areas, ext = random_instance(seed)
+    old = ospf_rib.update_rib_full(router_id, max_paths, areas, ext)
+    router_id2, max_paths2, areas2, ext2 = random_instance(seed + 1 if seed % 3 else seed)
+    new = ospf_rib.update_rib_full(router_id2, max_paths2, areas2, ext2)
+    olib = pyoracle.lib()
+    a0, f0 = ospf_rib.rib_diff(None, old)
+    b0, g0 = ospf_rib.call_rib_diff(olib.oracle_ospfv2_rib_diff, None, old)
+    assert a0.tobytes() == b0.tobytes() and f0.tobytes() == g0.tobytes()
+    old_inst = ospf_rib.Rib(f0, old.nexthops)
+    a1, f1 = ospf_rib.rib_diff(old_inst, new)
+    b1, g1 = ospf_rib.call_rib_diff(olib.oracle_ospfv2_rib_diff, old_inst, new)
+    assert a1.tobytes() == b1.tobytes() and f1.tobytes() == g1.tobytes()
+    if seed % 3 == 0:          # identical tables: nothing to tell the RIB manager, flags carried over
+        assert len(a1) == 0 and f1.tobytes() == f0.tobytes()
