@@ -430,3 +430,59 @@ def reflood_list(spt: IsisSpt, rnl: np.ndarray, local_system_id: int, lsp_system
     if rc != capi.HSPF_OK:
         raise capi.HspfError(rc, name + " failed")
     return [int(x) for x in out[: n.value]]
+
+
+# ---- end of update_rib: level merge + update_global_rib (holo-isis/src/route.rs:232-314) --------
+ROUTE_CONNECTED, ROUTE_INSTALLED = 0x01, 0x02
+ACTION_DT = np.dtype([("route", "<u4"), ("old_sr_label", "<u4"), ("kind", "u1"), ("has_old_sr_label", "u1"),
+                      ("_pad", "u1", (2,))], align=True)
+
+
+def _rib_struct(rib, keep: list) -> RibStruct:
+    r = RibStruct()
+    routes = np.ascontiguousarray(rib.routes, dtype=ROUTE_DT)
+    nhs = np.ascontiguousarray(rib.nexthops, dtype=NEXTHOP_DT)
+    keep += [routes, nhs]
+    r.routes_cap = r.n_routes = len(routes)
+    r.nexthops_cap = r.n_nexthops = len(nhs)
+    r.routes = routes.ctypes.data if len(routes) else None
+    r.nexthops = nhs.ctypes.data if len(nhs) else None
+    return r
+
+
+def rib_merge(l2, l1, lib=None, name="hspf_isis_rib_merge") -> IsisRib:
+    """Merged local table of an L1/L2 router: L1 routes preferred (route.rs:236-242)."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RibStruct)]
+    keep = []
+    s2 = _rib_struct(l2, keep) if l2 is not None else None
+    s1 = _rib_struct(l1, keep) if l1 is not None else None
+    n_r = sum(len(x.routes) for x in (l2, l1) if x is not None)
+    n_h = sum(len(x.nexthops) for x in (l2, l1) if x is not None)
+    routes, nhs = np.zeros(max(n_r, 1), ROUTE_DT), np.zeros(max(n_h, 1), NEXTHOP_DT)
+    r = RibStruct()
+    r.routes_cap, r.routes = len(routes), routes.ctypes.data
+    r.nexthops_cap, r.nexthops = len(nhs), nhs.ctypes.data
+    rc = fn(C.addressof(s2) if s2 is not None else None, C.addressof(s1) if s1 is not None else None, C.byref(r))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return IsisRib(routes[: r.n_routes].copy(), nhs[: r.n_nexthops].copy(), rc)
+
+
+def rib_diff(old, new: IsisRib, lib=None, name="hspf_isis_rib_diff"):
+    """update_global_rib: (actions ACTION_DT[], new routes with ROUTE_INSTALLED set as the reference would)."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.c_void_p, C.POINTER(RibStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    ns = _rib_struct(IsisRib(new.routes.copy(), new.nexthops), keep)
+    new_routes = keep[0]
+    os_ = _rib_struct(old, keep) if old is not None else None
+    cap = len(new.routes) + (len(old.routes) if old is not None else 0) + 1
+    acts = np.zeros(cap, ACTION_DT)
+    n = C.c_uint32()
+    rc = fn(C.addressof(os_) if os_ is not None else None, C.byref(ns), acts.ctypes.data, cap, C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return acts[: n.value].copy(), new_routes

@@ -165,6 +165,16 @@ int hspf_isis_routes_from_planes(const hl_isis_instance *inst, const uint32_t *d
 /* sizeof() of the ABI structs in declaration order (hspf_csr, hspf_jobs,
  * hspf_result, then every struct of holo_lsdb.h); returns the count.  Lets a
  * foreign binding verify its struct layouts at load time. */
+/* The end of holo-isis' update_rib (holo-isis/src/route.rs:232-300): the local tables of the two
+ * levels are merged, L1 routes preferred (route.rs:236-242), and update_global_rib lists the
+ * installs / uninstalls for the RIB manager (a route is reinstalled unless metric and the
+ * next-hop set — labels included — are unchanged; connected routes and routes without next hops
+ * are never installed; hl_isis_route.flags receive HL_ROUTE_INSTALLED).  Either level may be
+ * NULL; `old_rib` may be NULL.  Summary (blackhole) routes are not modelled.  Host only. */
+int hspf_isis_rib_merge(const hl_isis_rib *l2, const hl_isis_rib *l1, hl_isis_rib *out);
+int hspf_isis_rib_diff(const hl_isis_rib *old_rib, hl_isis_rib *new_rib, hl_rib_action *out, uint32_t cap,
+                       uint32_t *n_out);
+
 /* ---- IS-IS flooding reduction over the hop-count SPTs of the neighbour batch ------------
  * (holo-isis/src/flooding/manet.rs).  manet::init_cache runs one hop-count
  * compute_spt per up adjacency (row a16: one hspf_run_batch with HSPF_GF_HOPCOUNT), then per

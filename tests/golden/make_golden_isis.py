@@ -79,5 +79,9 @@ def extract_isis(ref: Path):
                        for n in r.get("next-hops", {}).get("next-hop", [])]
                 snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"), "level": r.get("level"),
                                           "nexthops": nhs})
+            # what the instance sent to the RIB manager (update_global_rib, holo-isis/src/route.rs:255-314)
+            from make_golden import ibus_routes, ifindex_map
+            snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
+            snap["ifindex"] = ifindex_map(rt / "events.jsonl")
             out.append(snap)
     return out

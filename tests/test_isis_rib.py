@@ -1,0 +1,78 @@
+"""End of holo-isis' update_rib on the CPU: both levels through the product's route stage
+(hspf_isis_routes_from_planes, SPT planes from the oracle), hspf_isis_rib_merge (L1 preferred)
+and hspf_isis_rib_diff (update_global_rib) from an empty table must give exactly the RouteIpAdd
+set the reference sent to the RIB manager (output/ibus.jsonl of its 38 IS-IS conformance
+snapshots: prefix, metric, ifindex, next-hop address); product == restatement
+(oracle/rib_isis.cc) on these and on perturbed table pairs."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from holo_b200 import isis, ospfv3
+from oracle import pyoracle
+
+SNAPS = [s for s in gu.load_isis() if s.get("ibus_routes") is not None]
+
+
+def planes(csr, root):
+    c = pyoracle.csr_spf(csr, root, vec_mode=1, nh_words=4)
+    return c["dist"], c["hops"]
+
+
+def level_ribs(snap):
+    out = {}
+    names = None
+    for level in snap["levels"]:
+        inst = gu.isis_instance_image(snap, level)
+        out[level["level"]] = isis.routes_from_planes(inst, planes)
+        names = inst["ifnames"]
+    return out, names
+
+
+@pytest.mark.parametrize("snap", SNAPS, ids=[f"{s['topo']}-{s['rt']}" for s in SNAPS])
+def test_installs_equal_the_reference_ibus_stream(snap):
+    ribs, names = level_ribs(snap)
+    merged = isis.rib_merge(ribs.get(2), ribs.get(1))
+    ref = isis.rib_merge(ribs.get(2), ribs.get(1), lib=pyoracle.lib(), name="oracle_isis_rib_merge")
+    assert merged.routes.tobytes() == ref.routes.tobytes() and merged.nexthops.tobytes() == ref.nexthops.tobytes()
+    acts, routes = isis.rib_diff(None, merged)
+    acts_o, routes_o = isis.rib_diff(None, merged, lib=pyoracle.lib(), name="oracle_isis_rib_diff")
+    assert acts.tobytes() == acts_o.tobytes() and routes.tobytes() == routes_o.tobytes()
+    got = {}
+    for a in acts:
+        assert int(a["kind"]) == 1
+        r = merged.routes[int(a["route"])]
+        hops = merged.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        got[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (
+            int(r["metric"]), sorted((snap["ifindex"].get(names[int(x["iface"])], 0), ospfv3.ip_str(x["addr"])) for x in hops))
+    want = {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in snap["ibus_routes"].items()}
+    assert got == want
+    # second run over the unchanged table: nothing to tell the RIB manager, flags carried over
+    again, routes2 = isis.rib_diff(isis.IsisRib(routes, merged.nexthops), merged)
+    assert len(again) == 0 and routes2.tobytes() == routes.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_rib_diff_matches_restatement_on_perturbed_tables(seed):
+    rng = np.random.default_rng(seed)
+    snap = SNAPS[seed % len(SNAPS)]
+    ribs, _ = level_ribs(snap)
+    merged = isis.rib_merge(ribs.get(2), ribs.get(1))
+    _acts, routes = isis.rib_diff(None, merged)
+    old = isis.IsisRib(routes, merged.nexthops)
+    # perturb: drop some routes, change metrics, change a next-hop label
+    keep = rng.random(len(merged.routes)) > 0.2
+    new_routes = merged.routes[keep].copy()
+    for i in range(len(new_routes)):
+        if rng.random() < 0.3:
+            new_routes["metric"][i] += 1
+    nh = merged.nexthops.copy()
+    if len(nh):
+        k = int(rng.integers(0, len(nh)))
+        nh["has_label"][k] = 1
+        nh["sr_label"][k] = 16000 + seed
+    new = isis.IsisRib(new_routes, nh)
+    a, f = isis.rib_diff(old, new)
+    b, g = isis.rib_diff(old, new, lib=pyoracle.lib(), name="oracle_isis_rib_diff")
+    assert a.tobytes() == b.tobytes() and f.tobytes() == g.tobytes()
+    assert {int(x) for x in a["kind"]} <= {1, 3}
