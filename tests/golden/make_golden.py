@@ -64,6 +64,26 @@ def ibus_routes(path: Path):
     return out
 
 
+# Step tests whose input is a pure recomputation parameter, so that their ibus output pins the
+# re-computation + update_global_rib without emulating the protocol machines
+# (holo-ospf/tests/conformance/ospfv2/mod.rs:494-499, holo-isis/tests/conformance/mod.rs:994-999).
+STEP_TESTS = {
+    "ospfv2": [("nb-config-iface-cost1", "topo1-1", "rt2", "02-output-ibus.jsonl",
+                {"area": "0.0.0.1", "iface": "eth-rt1", "cost": 50})],
+    "isis": [("nb-config-spf-paths1", "topo2-1", "rt1", "01-output-ibus.jsonl", {"max_paths": 1})],
+}
+
+
+def step_outputs(base: Path, proto: str, topo: str, rt: str):
+    out = {}
+    for (name, t, r, fn, change) in STEP_TESTS.get(proto, []):
+        if (t, r) == (topo, rt):
+            routes = ibus_routes(base / name / fn)
+            if routes is not None:
+                out[name] = {"change": change, "ibus_routes": routes}
+    return out
+
+
 def extract_ospfv2(ref: Path):
     base = ref / "holo-ospf/tests/conformance/ospfv2/topologies"
     out = []
@@ -142,6 +162,7 @@ def extract_ospfv2(ref: Path):
                 snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
                                           "type": r.get("route-type"), "nexthops": nhs})
             snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
+            snap["steps"] = step_outputs(ref / "holo-ospf/tests/conformance/ospfv2", "ospfv2", topo.name, rt.name)
             out.append(snap)
     return out
 

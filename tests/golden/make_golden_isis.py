@@ -80,7 +80,8 @@ def extract_isis(ref: Path):
                 snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"), "level": r.get("level"),
                                           "nexthops": nhs})
             # what the instance sent to the RIB manager (update_global_rib, holo-isis/src/route.rs:255-314)
-            from make_golden import ibus_routes, ifindex_map
+            from make_golden import ibus_routes, ifindex_map, step_outputs
+            snap["steps"] = step_outputs(ref / "holo-isis/tests/conformance", "isis", topo.name, rt.name)
             snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
             snap["ifindex"] = ifindex_map(rt / "events.jsonl")
             out.append(snap)

@@ -76,3 +76,35 @@ def test_rib_diff_matches_restatement_on_perturbed_tables(seed):
     b, g = isis.rib_diff(old, new, lib=pyoracle.lib(), name="oracle_isis_rib_diff")
     assert a.tobytes() == b.tobytes() and f.tobytes() == g.tobytes()
     assert {int(x) for x in a["kind"]} <= {1, 3}
+
+
+def test_step_max_paths_change_reinstalls_exactly_the_ecmp_routes():
+    """The reference's step test nb-config-spf-paths1 (holo-isis/tests/conformance/mod.rs:994-999,
+    topo2-1 rt1): `spf-control/paths` 16 -> 1 makes it reinstall exactly the ECMP routes, each with
+    the single next hop it keeps (01-output-ibus.jsonl).  Here: table with max_paths 16 (installed),
+    table with max_paths 1, hspf_isis_rib_diff between them."""
+    snap = [s for s in gu.load_isis() if s.get("steps", {}).get("nb-config-spf-paths1")][0]
+    step = snap["steps"]["nb-config-spf-paths1"]
+
+    def table(max_paths):
+        ribs, names = {}, None
+        for level in snap["levels"]:
+            inst = gu.isis_instance_image(snap, level)
+            inst["max_paths"] = max_paths
+            ribs[level["level"]] = isis.routes_from_planes(inst, planes)
+            names = inst["ifnames"]
+        return isis.rib_merge(ribs.get(2), ribs.get(1)), names
+
+    old, names = table(16)
+    _a, installed = isis.rib_diff(None, old)
+    new, _ = table(step["change"]["max_paths"])
+    acts, _f = isis.rib_diff(isis.IsisRib(installed, old.nexthops), new)
+    got = {}
+    for a in acts:
+        assert int(a["kind"]) == 1
+        r = new.routes[int(a["route"])]
+        hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        got[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (
+            int(r["metric"]), sorted((snap["ifindex"].get(names[int(x["iface"])], 0), ospfv3.ip_str(x["addr"])) for x in hops))
+    want = {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in step["ibus_routes"].items()}
+    assert got == want

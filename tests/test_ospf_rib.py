@@ -318,3 +318,52 @@ def test_rib_diff_matches_restatement_on_random_table_pairs(seed):
     assert a1.tobytes() == b1.tobytes() and f1.tobytes() == g1.tobytes()
     if seed % 3 == 0:          # identical tables: nothing to tell the RIB manager, flags carried over
         assert len(a1) == 0 and f1.tobytes() == f0.tobytes()
+
+
+def test_step_interface_cost_change_reinstalls_exactly_the_changed_route():
+    """The reference's step test nb-config-iface-cost1 (holo-ospf/tests/conformance/ospfv2/mod.rs:
+    494-499, topo1-1 rt2): the cost of eth-rt1 goes 10 -> 50, the router re-originates its
+    Router-LSA of area 0.0.0.1 with the new metric, and the only message to the RIB manager is the
+    reinstall of 1.1.1.1/32 with metric 50 (02-output-ibus.jsonl; 10.0.1.0/24 is connected)."""
+    snap = [s for s in SNAPS if s.get("steps", {}).get("nb-config-iface-cost1")][0]
+    step = snap["steps"]["nb-config-iface-cost1"]
+    keys = gu.global_sort_keys(snap)
+
+    def table(changed):
+        areas = []
+        for area in snap["areas"]:
+            img = gu.ospfv2_area_image(snap, area, keys)
+            if changed and area["area_id"] == step["change"]["area"]:
+                # own Router-LSA: the p2p link over that interface and its stub link take the new cost
+                nbr = [n for i in area["interfaces"] if i["name"] == step["change"]["iface"] for n in i["neighbors"]][0]
+                me = [k for k in range(len(img.router_lsas)) if int(img.router_lsas["adv_rtr"][k]) == gu.ip(snap["router_id"])][0]
+                off, n = int(img.router_lsas["link_off"][me]), int(img.router_lsas["n_links"][me])
+                nbr_net = gu.ip(nbr[1]) & 0xFFFFFF00
+                hit = 0
+                for k in range(off, off + n):
+                    l = img.links[k]
+                    if (int(l["link_type"]) == ospfv2.LINK_P2P and int(l["link_id"]) == gu.ip(nbr[0])) or \
+                            (int(l["link_type"]) == ospfv2.LINK_STUB and int(l["link_id"]) == nbr_net):
+                        img.links["metric"][k] = step["change"]["cost"]
+                        hit += 1
+                assert hit == 2
+            res = ospfv2.area_from_planes(img, _planes)
+            if res.root_found:
+                active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+                areas.append(ospf_rib.RibArea(gu.ip(area["area_id"]), res, img.ifaces, gu.ospfv2_summaries(area), active))
+        return ospf_rib.update_rib_full(gu.ip(snap["router_id"]), 16, areas)
+
+    old = table(False)
+    _a, installed = ospf_rib.rib_diff(None, old)
+    new = table(True)
+    acts, _f = ospf_rib.rib_diff(ospf_rib.Rib(installed, old.nexthops), new)
+    key_name = {v: k for k, v in keys.items()}
+    got = {}
+    for a in acts:
+        assert int(a["kind"]) == ospf_rib.RIB_INSTALL
+        r = new.routes[int(a["route"])]
+        hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        got[f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}"] = (
+            int(r["metric"]), sorted((snap["ifindex"].get(key_name[int(x["iface"])], 0), gu.ipstr(x["addr"])) for x in hops))
+    want = {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in step["ibus_routes"].items()}
+    assert got == want
