@@ -78,33 +78,62 @@ def test_rib_diff_matches_restatement_on_perturbed_tables(seed):
     assert {int(x) for x in a["kind"]} <= {1, 3}
 
 
-def test_step_max_paths_change_reinstalls_exactly_the_ecmp_routes():
-    """The reference's step test nb-config-spf-paths1 (holo-isis/tests/conformance/mod.rs:994-999,
-    topo2-1 rt1): `spf-control/paths` 16 -> 1 makes it reinstall exactly the ECMP routes, each with
-    the single next hop it keeps (01-output-ibus.jsonl).  Here: table with max_paths 16 (installed),
-    table with max_paths 1, hspf_isis_rib_diff between them."""
-    snap = [s for s in gu.load_isis() if s.get("steps", {}).get("nb-config-spf-paths1")][0]
-    step = snap["steps"]["nb-config-spf-paths1"]
+AFTER = [(s, name) for s in gu.load_isis() for name in s.get("after", {})]
 
-    def table(max_paths):
+
+@pytest.mark.parametrize("snap,name", AFTER, ids=[f"{n}-{s['topo']}-{s['rt']}" for s, n in AFTER])
+def test_step_recomputation_gives_the_reference_ibus_output(snap, name):
+    """Step tests of the reference (holo-isis/tests/conformance/mod.rs): the state it reached after
+    the step is one more snapshot.  Table of the topology snapshot (installed) vs table of the
+    after-state through product host code + hspf_isis_rib_diff == the step's ibus output, message
+    for message and in order — 20 cases: configuration changes (att-ignore, max_paths 16 -> 1, an
+    address family or an interface disabled / deleted / made passive, interface metric), RPCs
+    (clear adjacency / database), interface and adjacency events, and received LSPs (ATT bit,
+    overload bit, expiration)."""
+    after = dict(snap["after"][name])
+    after.setdefault("ifindex", snap["ifindex"])
+
+    def table(s):
         ribs, names = {}, None
-        for level in snap["levels"]:
-            inst = gu.isis_instance_image(snap, level)
-            inst["max_paths"] = max_paths
+        for level in s["levels"]:
+            inst = gu.isis_instance_image(s, level)
+            inst["att_ignore"] = int(bool(s.get("att_ignore", False)))
             ribs[level["level"]] = isis.routes_from_planes(inst, planes)
             names = inst["ifnames"]
         return isis.rib_merge(ribs.get(2), ribs.get(1)), names
 
-    old, names = table(16)
+    old, names = table(snap)
     _a, installed = isis.rib_diff(None, old)
-    new, _ = table(step["change"]["max_paths"])
-    acts, _f = isis.rib_diff(isis.IsisRib(installed, old.nexthops), new)
-    got = {}
+    old_inst = isis.IsisRib(installed, old.nexthops)
+    new, names2 = table(after)
+    names2 = names2 or []
+    gone = after.get("deleted_ifaces", [])
+    if gone:
+        # Deleting an interface is handled by the configuration code before the SPF runs: it removes
+        # the next hops over that interface from the local table without telling the RIB manager
+        # (holo-isis/src/northbound/configuration.rs:2193-2211), and the arena slot goes away.  The
+        # same on the installed table here: prune, and re-index the interfaces by name.
+        routes, nhs = old_inst.routes.copy(), []
+        for i, r in enumerate(routes):
+            hops = [x.copy() for x in old_inst.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+                    if names[int(x["iface"])] not in gone]
+            for x in hops:
+                x["iface"] = names2.index(names[int(x["iface"])])
+            routes["nh_off"][i], routes["n_nh"][i] = len(nhs), len(hops)
+            nhs += hops
+        old_inst = isis.IsisRib(routes, np.asarray(nhs, dtype=isis.NEXTHOP_DT) if nhs else np.zeros(0, isis.NEXTHOP_DT))
+    acts, _f = isis.rib_diff(old_inst, new)
+    got = []
     for a in acts:
-        assert int(a["kind"]) == 1
-        r = new.routes[int(a["route"])]
-        hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
-        got[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (
-            int(r["metric"]), sorted((snap["ifindex"].get(names[int(x["iface"])], 0), ospfv3.ip_str(x["addr"])) for x in hops))
-    want = {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in step["ibus_routes"].items()}
+        kind = int(a["kind"])
+        if kind == 1:
+            r = new.routes[int(a["route"])]
+            hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+            got.append(["add", f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}", int(r["metric"]),
+                        sorted([snap["ifindex"].get(names2[int(x["iface"])], 0), ospfv3.ip_str(x["addr"])] for x in hops)])
+        else:
+            assert kind == 3
+            r = old_inst.routes[int(a["route"])]
+            got.append(["del", f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}", None, []])
+    want = [[k, p, m, sorted(nh)] for (k, p, m, nh) in after["ibus"]]
     assert got == want
