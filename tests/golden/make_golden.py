@@ -84,6 +84,100 @@ def step_outputs(base: Path, proto: str, topo: str, rt: str):
     return out
 
 
+# Step tests of the reference whose ibus output carries route messages and whose after-state dump
+# is a complete snapshot (holo-ospf/tests/conformance/ospfv2/mod.rs: the cases named here): the
+# table computed from the after-state, diffed against the table of the topology snapshot, must
+# give the step's ibus output message for message.
+OSPFV2_STEPS = [
+    ("lsa-expiry1", "topo2-1", "rt2", "02"), ("lsa-expiry2", "topo2-1", "rt2", "02"),
+    ("nb-config-area1", "topo1-1", "rt2", "01"), ("nb-config-enable1", "topo1-1", "rt3", "01"),
+    ("nb-config-enable2", "topo1-1", "rt3", "01"), ("nb-config-iface1", "topo1-1", "rt2", "02"),
+    ("nb-config-iface-cost1", "topo1-1", "rt2", "02"), ("nb-config-router-id1", "topo1-1", "rt3", "01"),
+    ("nb-rpc-clear-neighbor1", "topo1-1", "rt6", "02"), ("nb-rpc-clear-neighbor2", "topo1-1", "rt6", "02"),
+    ("ibus-addr-add3", "topo2-1", "rt6", "02"), ("ibus-addr-del1", "topo2-1", "rt2", "02"),
+    ("ibus-iface-update1", "topo2-1", "rt2", "02"), ("ibus-iface-update2", "topo2-1", "rt2", "02"),
+    ("ibus-iface-update3", "topo2-1", "rt3", "02"), ("ibus-iface-update4", "topo2-1", "rt2", "02"),
+    ("ibus-iface-update6", "topo2-1", "rt2", "02"), ("timeout-nbr1", "topo1-2", "rt3", "02"),
+    ("timeout-nbr2", "topo1-2", "rt3", "02"),
+]
+
+
+def ospfv2_snapshot(rt: Path, state_path: Path):
+    """One OSPFv2 snapshot dict from a northbound-state dump, the router's config.json and events.jsonl."""
+    o = ospf_root(json.loads(state_path.read_text()))
+    cfg = json.loads((rt / "config.json").read_text())
+    cfg_ospf = ospf_root(cfg)
+    iftype_cfg = {}
+    for a in cfg_ospf.get("areas", {}).get("area", []):
+        for i in a.get("interfaces", {}).get("interface", []):
+            iftype_cfg[(a["area-id"], i["name"])] = i.get("interface-type", "broadcast")
+    snap = {"topo": rt.parent.name, "rt": rt.name, "router_id": o.get("router-id"),
+            "ifindex": ifindex_map(rt / "events.jsonl"), "areas": [], "local_rib": []}
+    for a in o.get("areas", {}).get("area", []):
+        area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "summary_lsas": [],
+                "interfaces": []}
+        for t in a.get("database", {}).get("area-scope-lsa-type", []):
+            for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
+                h = l["ospfv2"]["header"]
+                b = l["ospfv2"].get("body", {})
+                if t["lsa-type"] == 1 and "router" in b:
+                    r = b["router"]
+                    flags = 0
+                    for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
+                        flags |= RTR_BITS.get(bit.split(":")[-1], 0)    # some dumps prefix "ietf-ospf:"
+                    links = [[LINK_TYPES[x["type"]], x["link-id"], x["link-data"],
+                              x["topologies"]["topology"][0]["metric"]]
+                             for x in r.get("links", {}).get("link", [])]
+                    area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
+                                                "links": links, "maxage": "holo-ospf-dev:maxage" in h})
+                elif t["lsa-type"] in (3, 4) and "summary" in b:
+                    # Summary-LSAs (type 3 network / type 4 ASBR), inputs of the inter-area stage
+                    # (holo-ospf/src/ospfv2/spf.rs:539-589)
+                    sm = b["summary"]
+                    area["summary_lsas"].append({
+                        "type": t["lsa-type"], "adv": h["adv-router"], "id": h["lsa-id"],
+                        "mask": sm["network-mask"], "metric": sm["topologies"]["topology"][0]["metric"],
+                        "maxage": "holo-ospf-dev:maxage" in h})
+                elif t["lsa-type"] == 2 and "network" in b:
+                    n = b["network"]
+                    area["network_lsas"].append({
+                        "adv": h["adv-router"], "id": h["lsa-id"], "mask": n["network-mask"],
+                        "attached": n.get("attached-routers", {}).get("attached-router", []),
+                        "maxage": "holo-ospf-dev:maxage" in h})
+        for i in a.get("interfaces", {}).get("interface", []):
+            nb = [[x["neighbor-router-id"], x["address"]]
+                  for x in i.get("neighbors", {}).get("neighbor", [])]
+            area["interfaces"].append({"name": i["name"], "state": i.get("state"),
+                                       "cfg_type": iftype_cfg.get((a["area-id"], i["name"]), "broadcast"),
+                                       "neighbors": nb})
+        for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
+            nb = [[x["neighbor-router-id"], x["address"]]
+                  for x in v.get("neighbors", {}).get("neighbor", [])]
+            # holo names it vlink-<transit-area>-<router-id>
+            # (holo-ospf/src/northbound/configuration.rs:606)
+            area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
+                                       "state": v.get("state"), "cfg_type": "virtual-link", "neighbors": nb})
+        snap["areas"].append(area)
+    # AS-external LSAs (type 5), inputs of update_rib_external (ospfv2/spf.rs:591-615)
+    snap["external_lsas"] = []
+    for t in o.get("database", {}).get("as-scope-lsa-type", []):
+        for l in t.get("as-scope-lsas", {}).get("as-scope-lsa", []):
+            h = l["ospfv2"]["header"]
+            ex = l["ospfv2"].get("body", {}).get("external")
+            if t["lsa-type"] == 5 and ex:
+                tp = ex["topologies"]["topology"][0]
+                snap["external_lsas"].append({
+                    "adv": h["adv-router"], "id": h["lsa-id"], "mask": ex["network-mask"],
+                    "e_bit": "flags" in tp and "E" in str(tp.get("flags")), "metric": tp["metric"],
+                    "fwd": tp.get("forwarding-address", "0.0.0.0"), "tag": tp.get("external-route-tag", 0)})
+    for r in o.get("local-rib", {}).get("route", []):
+        nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
+               for n in r.get("next-hops", {}).get("next-hop", [])]
+        snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
+                                  "type": r.get("route-type"), "nexthops": nhs})
+    return snap
+
+
 def extract_ospfv2(ref: Path):
     base = ref / "holo-ospf/tests/conformance/ospfv2/topologies"
     out = []
@@ -92,77 +186,19 @@ def extract_ospfv2(ref: Path):
             st = rt / "output" / "northbound-state.json"
             if not st.exists():
                 continue
-            o = ospf_root(json.loads(st.read_text()))
-            cfg = json.loads((rt / "config.json").read_text())
-            cfg_ospf = ospf_root(cfg)
-            iftype_cfg = {}
-            for a in cfg_ospf.get("areas", {}).get("area", []):
-                for i in a.get("interfaces", {}).get("interface", []):
-                    iftype_cfg[(a["area-id"], i["name"])] = i.get("interface-type", "broadcast")
-            snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"),
-                    "ifindex": ifindex_map(rt / "events.jsonl"), "areas": [], "local_rib": []}
-            for a in o.get("areas", {}).get("area", []):
-                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "summary_lsas": [],
-                        "interfaces": []}
-                for t in a.get("database", {}).get("area-scope-lsa-type", []):
-                    for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
-                        h = l["ospfv2"]["header"]
-                        b = l["ospfv2"].get("body", {})
-                        if t["lsa-type"] == 1 and "router" in b:
-                            r = b["router"]
-                            flags = 0
-                            for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
-                                flags |= RTR_BITS.get(bit.split(":")[-1], 0)    # some dumps prefix "ietf-ospf:"
-                            links = [[LINK_TYPES[x["type"]], x["link-id"], x["link-data"],
-                                      x["topologies"]["topology"][0]["metric"]]
-                                     for x in r.get("links", {}).get("link", [])]
-                            area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
-                                                        "links": links})
-                        elif t["lsa-type"] in (3, 4) and "summary" in b:
-                            # Summary-LSAs (type 3 network / type 4 ASBR), inputs of the inter-area stage
-                            # (holo-ospf/src/ospfv2/spf.rs:539-589)
-                            sm = b["summary"]
-                            area["summary_lsas"].append({
-                                "type": t["lsa-type"], "adv": h["adv-router"], "id": h["lsa-id"],
-                                "mask": sm["network-mask"], "metric": sm["topologies"]["topology"][0]["metric"]})
-                        elif t["lsa-type"] == 2 and "network" in b:
-                            n = b["network"]
-                            area["network_lsas"].append({
-                                "adv": h["adv-router"], "id": h["lsa-id"], "mask": n["network-mask"],
-                                "attached": n.get("attached-routers", {}).get("attached-router", [])})
-                for i in a.get("interfaces", {}).get("interface", []):
-                    nb = [[x["neighbor-router-id"], x["address"]]
-                          for x in i.get("neighbors", {}).get("neighbor", [])]
-                    area["interfaces"].append({"name": i["name"], "state": i.get("state"),
-                                               "cfg_type": iftype_cfg.get((a["area-id"], i["name"]), "broadcast"),
-                                               "neighbors": nb})
-                for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
-                    nb = [[x["neighbor-router-id"], x["address"]]
-                          for x in v.get("neighbors", {}).get("neighbor", [])]
-                    # holo names it vlink-<transit-area>-<router-id>
-                    # (holo-ospf/src/northbound/configuration.rs:606)
-                    area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
-                                               "state": v.get("state"), "cfg_type": "virtual-link", "neighbors": nb})
-                snap["areas"].append(area)
-            # AS-external LSAs (type 5), inputs of update_rib_external (ospfv2/spf.rs:591-615)
-            snap["external_lsas"] = []
-            for t in o.get("database", {}).get("as-scope-lsa-type", []):
-                for l in t.get("as-scope-lsas", {}).get("as-scope-lsa", []):
-                    h = l["ospfv2"]["header"]
-                    ex = l["ospfv2"].get("body", {}).get("external")
-                    if t["lsa-type"] == 5 and ex:
-                        tp = ex["topologies"]["topology"][0]
-                        snap["external_lsas"].append({
-                            "adv": h["adv-router"], "id": h["lsa-id"], "mask": ex["network-mask"],
-                            "e_bit": "flags" in tp and "E" in str(tp.get("flags")), "metric": tp["metric"],
-                            "fwd": tp.get("forwarding-address", "0.0.0.0"), "tag": tp.get("external-route-tag", 0)})
-            for r in o.get("local-rib", {}).get("route", []):
-                nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
-                       for n in r.get("next-hops", {}).get("next-hop", [])]
-                snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
-                                          "type": r.get("route-type"), "nexthops": nhs})
+            snap = ospfv2_snapshot(rt, st)
             snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
             snap["steps"] = step_outputs(ref / "holo-ospf/tests/conformance/ospfv2", "ospfv2", topo.name, rt.name)
+            snap["after"] = {}
+            for (name, t, r, nn) in OSPFV2_STEPS:
+                if (t, r) != (topo.name, rt.name):
+                    continue
+                from make_golden_isis import ibus_stream
+                sd = ref / "holo-ospf/tests/conformance/ospfv2" / name
+                after = ospfv2_snapshot(rt, sd / f"{nn}-output-northbound-state.json")
+                after.pop("ifindex", None)          # the events of the topology replay name the interfaces
+                after["ibus"] = ibus_stream(sd / f"{nn}-output-ibus.jsonl")
+                snap["after"][name] = after
             out.append(snap)
     return out
 

@@ -40,7 +40,7 @@ def ospfv2_area_image(snap, area, sort_keys=None):
     rlsa = np.zeros(len(rl), ospfv2.ROUTER_LSA_DT)
     off = 0
     for i, l in enumerate(rl):
-        rlsa[i] = (ip(l["adv"]), ip(l["id"]), 1, l["flags"], 0x02, off, len(l["links"]))
+        rlsa[i] = (ip(l["adv"]), ip(l["id"]), ospfv2.MAX_AGE if l.get("maxage") else 1, l["flags"], 0x02, off, len(l["links"]))
         for (ty, lid, ld, m) in l["links"]:
             links[off] = (ip(lid), ip(ld), m, ty, 0)
             off += 1
@@ -49,7 +49,7 @@ def ospfv2_area_image(snap, area, sort_keys=None):
     att = []
     for i, l in enumerate(nl):
         a = sorted(ip(x) for x in l["attached"])
-        nlsa[i] = (ip(l["adv"]), ip(l["id"]), ip(l["mask"]), 1, 0, len(att), len(a))
+        nlsa[i] = (ip(l["adv"]), ip(l["id"]), ip(l["mask"]), ospfv2.MAX_AGE if l.get("maxage") else 1, 0, len(att), len(a))
         att += a
     # interfaces in name order (BTreeMap<String, _>: byte-wise string order)
     ifs = sorted(area["interfaces"], key=lambda i: i["name"].encode())
@@ -109,7 +109,7 @@ def ospfv2_summaries(area):
     ls = sorted(area.get("summary_lsas", []), key=lambda l: (l["type"], ip(l["adv"]), ip(l["id"])))
     out = np.zeros(len(ls), ospf_rib.SUMMARY_LSA_DT)
     for i, l in enumerate(ls):
-        out[i] = (ip(l["adv"]), ip(l["id"]), ip(l["mask"]), l["metric"], l["type"], 0, (0, 0))
+        out[i] = (ip(l["adv"]), ip(l["id"]), ip(l["mask"]), l["metric"], l["type"], int(bool(l.get("maxage"))), (0, 0))
     return out
 
 

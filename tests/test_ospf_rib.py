@@ -367,3 +367,54 @@ def test_step_interface_cost_change_reinstalls_exactly_the_changed_route():
             int(r["metric"]), sorted((snap["ifindex"].get(key_name[int(x["iface"])], 0), gu.ipstr(x["addr"])) for x in hops))
     want = {p: (v["metric"], sorted((n[0], n[1]) for n in v["nexthops"])) for p, v in step["ibus_routes"].items()}
     assert got == want
+
+
+AFTER_V2 = [(s, name) for s in SNAPS for name in s.get("after", {})]
+
+
+def _table_v2(snap, keys0):
+    """Whole table of a snapshot through product host code; interfaces keep the sort keys of the
+    topology snapshot (arena slots are stable across deletions), new ones are appended."""
+    keys = dict(keys0)
+    for n in sorted({i["name"] for a in snap["areas"] for i in a["interfaces"]}):
+        keys.setdefault(n, max(keys.values(), default=0) + 1)
+    key_name = {v: k for k, v in keys.items()}
+    if not snap.get("router_id"):            # instance disabled: no table
+        return ospf_rib.Rib(np.zeros(0, ospf_rib.RIB_ROUTE_DT), np.zeros(0, ospfv2.NEXTHOP_DT)), key_name
+    areas = []
+    for area in snap["areas"]:
+        img = gu.ospfv2_area_image(snap, area, keys)
+        res = ospfv2.area_from_planes(img, _planes)
+        if res.root_found:
+            active = any((i.get("state") or "down") != "down" for i in area["interfaces"])
+            areas.append(ospf_rib.RibArea(gu.ip(area["area_id"]), res, img.ifaces, gu.ospfv2_summaries(area), active))
+    return ospf_rib.update_rib_full(gu.ip(snap["router_id"]), 16, areas), key_name
+
+
+@pytest.mark.parametrize("snap,name", AFTER_V2, ids=[f"{n}-{s['topo']}-{s['rt']}" for s, n in AFTER_V2])
+def test_step_recomputation_gives_the_reference_ibus_output(snap, name):
+    """19 step tests of the reference (holo-ospf/tests/conformance/ospfv2/mod.rs): LSA expiry,
+    area / interface / instance configuration changes, router-id change, neighbour clearing and
+    time-outs, interface and address events.  The state the reference reached after the step is one
+    more snapshot; table of the topology snapshot (installed) vs table of the after-state, through
+    product host code + hspf_ospfv2_rib_diff, == the step's ibus output, message for message."""
+    after = dict(snap["after"][name], ifindex=snap["ifindex"])
+    keys0 = gu.global_sort_keys(snap)
+    old, _kn = _table_v2(snap, keys0)
+    _a, installed = ospf_rib.rib_diff(None, old)
+    old_inst = ospf_rib.Rib(installed, old.nexthops)
+    new, kn = _table_v2(after, keys0)
+    acts, _f = ospf_rib.rib_diff(old_inst, new)
+    got = []
+    for a in acts:
+        if int(a["kind"]) == ospf_rib.RIB_INSTALL:
+            r = new.routes[int(a["route"])]
+            hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+            got.append(["add", f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}", int(r["metric"]),
+                        sorted([snap["ifindex"].get(kn[int(x["iface"])], 0), gu.ipstr(x["addr"]) if x["has_addr"] else None]
+                               for x in hops)])
+        else:
+            assert int(a["kind"]) == ospf_rib.RIB_UNINSTALL_OLD
+            r = old_inst.routes[int(a["route"])]
+            got.append(["del", f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}", None, []])
+    assert got == [[k, p, m, sorted(nh)] for (k, p, m, nh) in after["ibus"]]
