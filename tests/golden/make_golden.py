@@ -207,6 +207,76 @@ V3_LINK_TYPES = {"point-to-point-link": 1, "transit-network-link": 2, "virtual-l
 V3_BITS = {"abr-bit": 0x01, "asbr-bit": 0x02, "vlink-end-bit": 0x04}
 
 
+def ospfv3_snapshot(rt: Path, state_path: Path):
+    """One OSPFv3 snapshot dict from a northbound-state dump."""
+    o = ospf_root(json.loads(state_path.read_text()))
+    snap = {"topo": rt.parent.name, "rt": rt.name, "router_id": o.get("router-id"), "areas": [], "local_rib": []}
+    for a in o.get("areas", {}).get("area", []):
+        area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "iap_lsas": [],
+                "inter_area_lsas": [], "interfaces": []}
+        for t in a.get("database", {}).get("area-scope-lsa-type", []):
+            for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
+                h = l["ospfv3"]["header"]
+                b = l["ospfv3"].get("body", {})
+                if "router" in b:
+                    r = b["router"]
+                    flags = 0
+                    for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
+                        flags |= V3_BITS.get(bit.split(":")[-1], 0)
+                    opts = r.get("lsa-options", {}).get("lsa-options", [])
+                    links = [[V3_LINK_TYPES[x["type"]], x["interface-id"], x["neighbor-interface-id"],
+                              x["neighbor-router-id"], x["metric"]] for x in r.get("links", {}).get("link", [])]
+                    area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
+                                                "r": "r-bit" in opts, "v6": "v6-bit" in opts, "links": links})
+                elif "network" in b:
+                    area["network_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
+                                                 "attached": b["network"].get("attached-routers", {}).get("attached-router", [])})
+                elif "inter-area-prefix" in b:
+                    # inputs of the inter-area stage (holo-ospf/src/ospfv3/spf.rs:479-503)
+                    p = b["inter-area-prefix"]
+                    area["inter_area_lsas"].append({
+                        "type": 3, "adv": h["adv-router"], "id": h["lsa-id"], "prefix": p["prefix"],
+                        "metric": p.get("metric", 0),
+                        "options": p.get("prefix-options", {}).get("prefix-options", [])})
+                elif "inter-area-router" in b:
+                    p = b["inter-area-router"]
+                    area["inter_area_lsas"].append({
+                        "type": 4, "adv": h["adv-router"], "id": h["lsa-id"],
+                        "router_id": p.get("destination-router-id"), "metric": p.get("metric", 0)})
+                elif "intra-area-prefix" in b:
+                    p = b["intra-area-prefix"]
+                    pf = [[x["prefix"], x.get("metric", 0), x.get("prefix-options", {}).get("prefix-options", [])]
+                          for x in p.get("prefixes", {}).get("prefix", [])]
+                    area["iap_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
+                                             "ref_type": p["referenced-ls-type"],
+                                             "ref_id": p["referenced-link-state-id"],
+                                             "ref_adv": p["referenced-adv-router"], "prefixes": pf})
+        for i in a.get("interfaces", {}).get("interface", []):
+            llsas = []
+            for t in i.get("database", {}).get("link-scope-lsa-type", []):
+                for l in t.get("link-scope-lsas", {}).get("link-scope-lsa", []):
+                    b = l["ospfv3"].get("body", {})
+                    if "link" in b:
+                        llsas.append([l["adv-router"], l["ospfv3"]["header"]["lsa-id"],
+                                      b["link"]["link-local-interface-address"]])
+            area["interfaces"].append({"name": i["name"], "state": i.get("state"),
+                                       "interface_id": i.get("interface-id"),
+                                       "neighbors": [[x["neighbor-router-id"], x["address"]]
+                                                     for x in i.get("neighbors", {}).get("neighbor", [])],
+                                       "link_lsas": llsas})
+        for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
+            area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
+                                       "state": "virtual-link", "interface_id": v.get("interface-id"),
+                                       "neighbors": [], "link_lsas": []})
+        snap["areas"].append(area)
+    for r in o.get("local-rib", {}).get("route", []):
+        nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
+               for n in r.get("next-hops", {}).get("next-hop", [])]
+        snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
+                                  "type": r.get("route-type"), "nexthops": nhs})
+    return snap
+
+
 def extract_ospfv3(ref: Path):
     """OSPFv3 snapshots: Router/Network/Intra-Area-Prefix LSAs, the interfaces with their
     interface ids, neighbours and link-scope Link-LSAs, and the golden local-rib."""
@@ -217,71 +287,7 @@ def extract_ospfv3(ref: Path):
             st = rt / "output" / "northbound-state.json"
             if not st.exists():
                 continue
-            o = ospf_root(json.loads(st.read_text()))
-            snap = {"topo": topo.name, "rt": rt.name, "router_id": o.get("router-id"), "areas": [], "local_rib": []}
-            for a in o.get("areas", {}).get("area", []):
-                area = {"area_id": a["area-id"], "router_lsas": [], "network_lsas": [], "iap_lsas": [],
-                        "inter_area_lsas": [], "interfaces": []}
-                for t in a.get("database", {}).get("area-scope-lsa-type", []):
-                    for l in t.get("area-scope-lsas", {}).get("area-scope-lsa", []):
-                        h = l["ospfv3"]["header"]
-                        b = l["ospfv3"].get("body", {})
-                        if "router" in b:
-                            r = b["router"]
-                            flags = 0
-                            for bit in r.get("router-bits", {}).get("rtr-lsa-bits", []):
-                                flags |= V3_BITS.get(bit.split(":")[-1], 0)
-                            opts = r.get("lsa-options", {}).get("lsa-options", [])
-                            links = [[V3_LINK_TYPES[x["type"]], x["interface-id"], x["neighbor-interface-id"],
-                                      x["neighbor-router-id"], x["metric"]] for x in r.get("links", {}).get("link", [])]
-                            area["router_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"], "flags": flags,
-                                                        "r": "r-bit" in opts, "v6": "v6-bit" in opts, "links": links})
-                        elif "network" in b:
-                            area["network_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
-                                                         "attached": b["network"].get("attached-routers", {}).get("attached-router", [])})
-                        elif "inter-area-prefix" in b:
-                            # inputs of the inter-area stage (holo-ospf/src/ospfv3/spf.rs:479-503)
-                            p = b["inter-area-prefix"]
-                            area["inter_area_lsas"].append({
-                                "type": 3, "adv": h["adv-router"], "id": h["lsa-id"], "prefix": p["prefix"],
-                                "metric": p.get("metric", 0),
-                                "options": p.get("prefix-options", {}).get("prefix-options", [])})
-                        elif "inter-area-router" in b:
-                            p = b["inter-area-router"]
-                            area["inter_area_lsas"].append({
-                                "type": 4, "adv": h["adv-router"], "id": h["lsa-id"],
-                                "router_id": p.get("destination-router-id"), "metric": p.get("metric", 0)})
-                        elif "intra-area-prefix" in b:
-                            p = b["intra-area-prefix"]
-                            pf = [[x["prefix"], x.get("metric", 0), x.get("prefix-options", {}).get("prefix-options", [])]
-                                  for x in p.get("prefixes", {}).get("prefix", [])]
-                            area["iap_lsas"].append({"adv": h["adv-router"], "id": h["lsa-id"],
-                                                     "ref_type": p["referenced-ls-type"],
-                                                     "ref_id": p["referenced-link-state-id"],
-                                                     "ref_adv": p["referenced-adv-router"], "prefixes": pf})
-                for i in a.get("interfaces", {}).get("interface", []):
-                    llsas = []
-                    for t in i.get("database", {}).get("link-scope-lsa-type", []):
-                        for l in t.get("link-scope-lsas", {}).get("link-scope-lsa", []):
-                            b = l["ospfv3"].get("body", {})
-                            if "link" in b:
-                                llsas.append([l["adv-router"], l["ospfv3"]["header"]["lsa-id"],
-                                              b["link"]["link-local-interface-address"]])
-                    area["interfaces"].append({"name": i["name"], "state": i.get("state"),
-                                               "interface_id": i.get("interface-id"),
-                                               "neighbors": [[x["neighbor-router-id"], x["address"]]
-                                                             for x in i.get("neighbors", {}).get("neighbor", [])],
-                                               "link_lsas": llsas})
-                for v in a.get("virtual-links", {}).get("virtual-link", []) if a.get("virtual-links") else []:
-                    area["interfaces"].append({"name": f"vlink-{v['transit-area-id']}-{v['router-id']}",
-                                               "state": "virtual-link", "interface_id": v.get("interface-id"),
-                                               "neighbors": [], "link_lsas": []})
-                snap["areas"].append(area)
-            for r in o.get("local-rib", {}).get("route", []):
-                nhs = [[n.get("outgoing-interface"), n.get("next-hop")]
-                       for n in r.get("next-hops", {}).get("next-hop", [])]
-                snap["local_rib"].append({"prefix": r["prefix"], "metric": r.get("metric"),
-                                          "type": r.get("route-type"), "nexthops": nhs})
+            snap = ospfv3_snapshot(rt, st)
             snap["ibus_routes"] = ibus_routes(rt / "output" / "ibus.jsonl")
             snap["ifindex"] = ifindex_map(rt / "events.jsonl")
             out.append(snap)
