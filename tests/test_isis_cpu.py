@@ -147,3 +147,17 @@ def test_route_stage_sr_prefix_sid_labels(seed, kw, root, mtype, frag):
         if ospfv3.ip_str(r["prefix"]) in own:
             kind = me % 7
             assert bool(r["has_sr_label"]) == (kind == 1)
+
+
+AFTER = [(s, n) for s in SNAPS for n in s.get("after", {})]
+
+
+@pytest.mark.parametrize("snap,name", AFTER, ids=[f"{n}-{s['topo']}-{s['rt']}" for s, n in AFTER])
+def test_route_stage_on_step_after_states(snap, name):
+    """The LSDBs the reference reached after its step tests (overload and ATT bits, expired LSPs,
+    removed adjacencies ...): product route stage == oracle route path on each."""
+    after = snap["after"][name]
+    for level in after["levels"]:
+        inst = gu.isis_instance_image(after, level)
+        inst["att_ignore"] = int(bool(after.get("att_ignore", False)))
+        same_rib(isis.routes_from_planes(inst, oracle_planes), pyoracle.isis_compute_routes(inst))

@@ -86,3 +86,17 @@ SNAPS = gu.load_ospfv2()
 def test_reference_golden_snapshots(snap):
     for area in snap["areas"]:
         twin(gu.ospfv2_area_image(snap, area))
+
+
+AFTER = [(s, n) for s in SNAPS for n in s.get("after", {})]
+
+
+@pytest.mark.parametrize("snap,name", AFTER, ids=[f"{n}-{s['topo']}-{s['rt']}" for s, n in AFTER])
+def test_step_after_state_snapshots(snap, name):
+    """The LSDBs the reference reached after its step tests (expired LSAs, removed areas and
+    interfaces, changed costs ...): product host stage == LSDB-level oracle on each."""
+    after = dict(snap["after"][name], ifindex=snap["ifindex"])
+    if not after.get("router_id"):
+        pytest.skip("instance disabled in this state")
+    for area in after["areas"]:
+        twin(gu.ospfv2_area_image(after, area))
