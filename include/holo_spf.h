@@ -246,7 +246,8 @@ int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]);
  * operations, so no step of the exchange needs an SM and the next batch kernel overlaps it.
  *
  * Per step on buffer k (all ranks, in lockstep):
- *     hspf_xchg_acquire(x, k);            engine stream waits until push(k) two steps ago left
+ *     hspf_xchg_acquire(x, k);            engine stream waits until the previous push(k) has left the
+ *                                         device and the local consumer has released buffer k
  *     hspf_run_batch_async(... planes inside hspf_xchg_slot(x, k, rank) ...);
  *     hspf_xchg_push(x, k);
  *     hspf_xchg_wait(x, k);               consumer stream: all `world` slots of buffer k are in
