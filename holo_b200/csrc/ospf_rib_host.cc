@@ -176,6 +176,12 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
     for (uint32_t ai = 0; ai < n_areas; ++ai) {
         const auto &a = areas[ai];
         if (!a.spf || (a.n_ifaces && !a.ifaces) || (a.n_summaries && !a.summaries)) return HSPF_E_INVAL;
+        const auto &r = *a.spf;
+        if ((r.n_routers && !r.routers) || (r.n_routes && !r.routes) || (r.n_nexthops && !r.nexthops)) return HSPF_E_INVAL;
+        for (uint32_t i = 0; i < r.n_routers; ++i)
+            if ((uint64_t)r.routers[i].nh_off + r.routers[i].n_nh > r.n_nexthops) return HSPF_E_INVAL;
+        for (uint32_t i = 0; i < r.n_routes; ++i)
+            if ((uint64_t)r.routes[i].nh_off + r.routes[i].n_nh > r.n_nexthops) return HSPF_E_INVAL;
     }
     auto clip = [&](Hops &h) { if (h.size() > max_paths) h.resize(max_paths); };
     auto prefer = [](const Net &a, const Net &b) -> int {      // route_compare; negative: a wins
@@ -358,6 +364,10 @@ int rib_diff(const typename T::Rib *old_rib, typename T::Rib *new_rib, hl_rib_ac
     if ((new_rib->n_routes && !new_rib->routes) || (new_rib->n_nexthops && !new_rib->nexthops)) return HSPF_E_INVAL;
     const uint32_t n_old = old_rib ? old_rib->n_routes : 0;
     if (old_rib && ((n_old && !old_rib->routes) || (old_rib->n_nexthops && !old_rib->nexthops))) return HSPF_E_INVAL;
+    for (uint32_t i = 0; i < new_rib->n_routes; ++i)
+        if ((uint64_t)new_rib->routes[i].nh_off + new_rib->routes[i].n_nh > new_rib->n_nexthops) return HSPF_E_INVAL;
+    for (uint32_t i = 0; i < n_old; ++i)
+        if ((uint64_t)old_rib->routes[i].nh_off + old_rib->routes[i].n_nh > old_rib->n_nexthops) return HSPF_E_INVAL;
     auto metric_of = [](const typename T::Out &r) { return r.path_type == HL_PATH_TYPE2_EXTERNAL ? r.type2_metric : r.metric; };
     std::vector<hl_rib_action> acts;
     auto push = [&](uint8_t kind, uint32_t route, const typename T::Out *replaced) {

@@ -418,3 +418,22 @@ def test_step_recomputation_gives_the_reference_ibus_output(snap, name):
             r = old_inst.routes[int(a["route"])]
             got.append(["del", f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}", None, []])
     assert got == [[k, p, m, sorted(nh)] for (k, p, m, nh) in after["ibus"]]
+
+
+def test_rib_stage_rejects_out_of_range_next_hop_slices():
+    from holo_b200 import capi
+    router_id, max_paths, areas, ext = random_instance(3)
+    bad = areas[0].result.routes.copy()
+    if len(bad) == 0:
+        pytest.skip("no routes in this instance")
+    bad["nh_off"][0] = 10_000_000
+    areas[0].result = ospfv2.Ospfv2Result(areas[0].result.vertices, areas[0].result.routers, bad, areas[0].result.nexthops,
+                                          areas[0].result.transit_capability, True)
+    with pytest.raises(capi.HspfError):
+        ospf_rib.update_rib_full(router_id, max_paths, areas, ext)
+    rib = ospf_rib.update_rib_full(*random_instance(4))
+    if len(rib.routes):
+        broken = ospf_rib.Rib(rib.routes.copy(), rib.nexthops)
+        broken.routes["n_nh"][0] = 1_000_000
+        with pytest.raises(capi.HspfError):
+            ospf_rib.rib_diff(None, broken)
