@@ -137,3 +137,12 @@ def test_step_recomputation_gives_the_reference_ibus_output(snap, name):
             got.append(["del", f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}", None, []])
     want = [[k, p, m, sorted(nh)] for (k, p, m, nh) in after["ibus"]]
     assert got == want
+    # and the whole table of the after-state is the local-rib the reference reports there
+    table = {}
+    for r in new.routes:
+        hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        table[f"{ospfv3.ip_str(r['prefix'])}/{int(r['len'])}"] = (
+            int(r["metric"]), sorted((names2[int(x["iface"])], ospfv3.ip_str(x["addr"])) for x in hops))
+    rib_want = {r["prefix"]: (r["metric"], sorted((a, b) for a, b in r["nexthops"])) for r in after["local_rib"]}
+    if rib_want:    # (empty right after the instance was disabled or its database cleared)
+        assert table == rib_want

@@ -418,6 +418,21 @@ def test_step_recomputation_gives_the_reference_ibus_output(snap, name):
             r = old_inst.routes[int(a["route"])]
             got.append(["del", f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}", None, []])
     assert got == [[k, p, m, sorted(nh)] for (k, p, m, nh) in after["ibus"]]
+    # and the whole table of the after-state is the local-rib the reference reports there
+    table = {}
+    for r in new.routes:
+        hops = new.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        table[f"{gu.ipstr(r['prefix'])}/{bin(int(r['mask'])).count('1')}"] = (
+            int(r["metric"]), ospf_rib.PATH_NAMES[int(r["path_type"])],
+            sorted(((kn[int(x["iface"])], gu.ipstr(x["addr"]) if x["has_addr"] else None) for x in hops),
+                   key=lambda x: (x[0] or "", x[1] or "")))
+    want = gu.golden_rib(after)
+    if not want:
+        return      # the instance has just restarted (router-id change, disable): no SPF has run yet
+    assert set(table) == set(want)
+    for pfx, (metric, rtype, nh) in want.items():
+        assert table[pfx][:2] == (metric, rtype), (pfx, table[pfx])
+        assert [(a or "", b or "") for a, b in table[pfx][2]] == [(a or "", b or "") for a, b in nh], pfx
 
 
 def test_rib_stage_rejects_out_of_range_next_hop_slices():
