@@ -200,7 +200,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": config_dict(args.gpus, csr, {"reference_sample": f"{per_step} roots per step"}),
+        "config": config_dict(args.gpus, csr, {
+            "reference_sample": f"{per_step} roots per step",
+            # same workload description as the GPU arm reports for this N
+            "exchange": EXCHANGE_TEXT["none" if args.gpus == 1 else
+                                      (args.exchange if args.exchange != "auto" else ("p2p" if args.gpus <= 4 else "nccl"))]}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step * args.steps} SPF roots of the C2 LSDB, one job per host thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
