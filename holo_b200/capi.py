@@ -34,6 +34,7 @@ NO_PARENT = 0xFFFFFFFF
 JS_SATURATED = 0x1
 JS_TOO_MANY_ATOMS = 0x2
 JS_ORDER = 0x4
+JS_INVALID = 0x8
 RUN_DEVICE_PTRS = 0x1
 MAX_OVERRIDES = 8
 
@@ -84,7 +85,7 @@ EXPORTS = [
     "hspf_version", "hspf_ctx_create", "hspf_ctx_destroy", "hspf_last_error",
     "hspf_graph_upload", "hspf_graph_free", "hspf_run_batch", "hspf_run_batch_async",
     "hspf_sync", "hspf_stream", "hspf_launch_count", "hspf_atom_decode", "hspf_atom_count",
-    "hspf_ctx_reserve_sms",
+    "hspf_ctx_reserve_sms", "hspf_debug_quad_image", "hspf_debug_phase_profile",
     "hspf_xchg_create", "hspf_xchg_attach", "hspf_xchg_slot", "hspf_xchg_slot_bytes", "hspf_xchg_acquire",
     "hspf_xchg_push", "hspf_xchg_wait", "hspf_xchg_release", "hspf_xchg_consumer_stream", "hspf_xchg_sync",
     "hspf_xchg_last_error", "hspf_xchg_destroy",
@@ -130,6 +131,9 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.hspf_ctx_reserve_sms.argtypes = [C.c_void_p, C.c_int]
     lib.hspf_atom_decode.argtypes = [C.POINTER(CsrStruct), C.c_uint32, C.c_uint32, _u32p, _u32p]
     lib.hspf_atom_count.argtypes = [C.POINTER(CsrStruct), C.c_uint32, _u32p]
+    lib.hspf_debug_quad_image.argtypes = [C.POINTER(CsrStruct), C.POINTER(C.c_uint32), _u32p, _u32p, _u16p, _u16p,
+                                          _u32p, _u32p, _u32p, _u32p]
+    lib.hspf_debug_phase_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     if path is None:
         _lib = lib
     return lib
@@ -314,6 +318,50 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.hspf_launch_count(self.handle))
+
+
+@dataclass
+class QuadImage:
+    """Host copy of the quad-space graph image (csrc/quad_layout.h), for tests."""
+    eligible: bool
+    NQ: int = 0
+    NIQ: int = 0
+    shift: int = 0
+    max_ichain: int = 1
+    max_atoms: int = 0
+    fq: np.ndarray | None = None       # [NQ, 4]
+    fcont: np.ndarray | None = None    # [NQ / 32]
+    slot_of: np.ndarray | None = None  # [V]
+    vert_of: np.ndarray | None = None  # [NQ]
+    iq: np.ndarray | None = None       # [NIQ, 4]
+    imeta: np.ndarray | None = None    # [NIQ, 2]
+    fpos: np.ndarray | None = None     # [E]
+    ipos: np.ndarray | None = None     # [E]
+
+
+def quad_image(csr: Csr) -> QuadImage:
+    """Build the quad-space image on the host (no CUDA call)."""
+    lib = load_library()
+    s = csr.as_struct()
+    hdr = (C.c_uint32 * 8)()
+    nul32, nul16 = C.cast(None, _u32p), C.cast(None, _u16p)
+    rc = lib.hspf_debug_quad_image(C.byref(s), hdr, nul32, nul32, nul16, nul16, nul32, nul32, nul32, nul32)
+    if rc != HSPF_OK:
+        raise HspfError(rc, "hspf_debug_quad_image")
+    if not hdr[0]:
+        return QuadImage(False)
+    NQ, NIQ, V, E = hdr[1], hdr[2], csr.n_vertices, csr.n_edges
+    q = QuadImage(True, NQ, NIQ, hdr[3], hdr[4], hdr[5],
+                  np.zeros((NQ, 4), np.uint32), np.zeros(NQ // 32, np.uint32), np.zeros(V, np.uint16),
+                  np.zeros(NQ, np.uint16), np.zeros((NIQ, 4), np.uint32), np.zeros((NIQ, 2), np.uint32),
+                  np.zeros(max(E, 1), np.uint32), np.zeros(max(E, 1), np.uint32))
+    rc = lib.hspf_debug_quad_image(C.byref(s), hdr, _ptr(q.fq, _u32p), _ptr(q.fcont, _u32p), _ptr(q.slot_of, _u16p),
+                                   _ptr(q.vert_of, _u16p), _ptr(q.iq, _u32p), _ptr(q.imeta, _u32p),
+                                   _ptr(q.fpos, _u32p), _ptr(q.ipos, _u32p))
+    if rc != HSPF_OK:
+        raise HspfError(rc, "hspf_debug_quad_image")
+    q.fpos, q.ipos = q.fpos[:E], q.ipos[:E]
+    return q
 
 
 def atom_decode(csr: Csr, root: int, atom: int):

@@ -15,7 +15,9 @@
 #include <cuda_runtime.h>
 
 #include "holo_spf.h"
+#include "quad_layout.h"
 #include "spf_kernel.cuh"
+#include "spf_quad.cuh"
 
 using namespace hspf;
 
@@ -25,6 +27,9 @@ struct hspf_graph {
     size_t blob_bytes = 0;
     uint32_t max_indeg = 0;
     bool has_leaf = false;     // any HSPF_VF_LEAF / LEAF_UNLESS_ROOT vertex
+    bool has_quads = false;    // quad-space image present (spf_quad_kernel eligible, see quad_layout.h)
+    QuadDev q{};
+    std::string quad_why;      // why the quad image was not built
 };
 
 struct hspf_ctx {
@@ -100,8 +105,72 @@ int max_ctas_per_sm(size_t smem) {
     return n < 1 ? 1 : n;
 }
 
+template <int T, bool O>
+int launch_quad(hspf_ctx *ctx, const QuadArgs &args, size_t smem, int per_sm_cap) {
+    CK(cudaFuncSetAttribute(spf_quad_kernel<T, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(spf_quad_kernel<T, O>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spf_quad_kernel<T, O>, T, smem));
+    if (per_sm < 1) return fail(ctx, HSPF_E_CUDA, "spf_quad_kernel does not fit an SM");
+    if (per_sm_cap > 0 && per_sm > per_sm_cap) per_sm = per_sm_cap;
+    int grid = (ctx->sm_count - ctx->reserved_sms) * per_sm;
+    if (const char *mg = getenv("HSPF_MAX_GRID")) {   // tuning knob (experiments only)
+        int v = atoi(mg);
+        if (v >= 1 && v < grid) grid = v;
+    }
+    if ((uint32_t)grid > args.n_jobs) grid = (int)args.n_jobs;
+    if (grid < 1) grid = 1;
+    QuadArgs a = args;
+    if (ctx->prof_enabled) {
+        if (ctx->prof_rows < grid) {
+            if (ctx->d_prof) cudaFree(ctx->d_prof);
+            ctx->d_prof = nullptr; ctx->prof_rows = 0;
+            CK(cudaMalloc(&ctx->d_prof, (size_t)grid * 16 * sizeof(unsigned long long)));
+            ctx->prof_rows = grid;
+        }
+        CK(cudaMemsetAsync(ctx->d_prof, 0, (size_t)ctx->prof_rows * 16 * sizeof(unsigned long long), ctx->stream));
+        a.prof = ctx->d_prof;
+    }
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), ctx->stream));
+    spf_quad_kernel<T, O><<<grid, T, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return HSPF_OK;
+}
+
+// The fast path: quad-space kernel (spf_quad.cuh).  Returns 1 if the batch is not eligible.
+int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+    if (!g->has_quads || g->has_leaf || (g->d.flags & HSPF_GF_HOPCOUNT) || out->nh_words != 1) return 1;
+    if (getenv("HSPF_NO_QUAD")) return 1;             // tuning knob (experiments only)
+    uint32_t qcap = 2048;
+    if (const char *qc = getenv("HSPF_QUAD_QCAP")) { int v = atoi(qc); if (v >= 64 && v <= 32768) qcap = (uint32_t)v; }
+    const QuadLayout lay = make_quad_layout(g->d.V, g->q.NQ, qcap);
+    if ((size_t)lay.total + 2048 > ctx->smem_optin) return 1;
+    QuadArgs a{};
+    a.g = g->d; a.q = g->q; a.lay = lay;
+    a.n_jobs = jobs->n_jobs; a.roots = jobs->roots;
+    a.ov_off = jobs->ov_off; a.ov_edge = jobs->ov_edge; a.ov_cost = jobs->ov_cost;
+    a.out_dist = out->dist; a.out_hops = out->hops; a.out_fp = out->first_parent; a.out_npar = out->n_parents;
+    a.out_nh = out->nh_mask; a.out_status = out->job_status;
+    a.job_counter = ctx->d_counter;
+    int T = 384, cap = 0;
+    if (const char *t = getenv("HSPF_QUAD_T")) T = atoi(t);                 // tuning knobs (experiments only)
+    if (const char *c = getenv("HSPF_CTAS_PER_SM")) cap = atoi(c);
+    const bool ov = jobs->ov_off != nullptr;
+    switch (T) {
+    case 128: return ov ? launch_quad<128, true>(ctx, a, lay.total, cap) : launch_quad<128, false>(ctx, a, lay.total, cap);
+    case 256: return ov ? launch_quad<256, true>(ctx, a, lay.total, cap) : launch_quad<256, false>(ctx, a, lay.total, cap);
+    case 512: return ov ? launch_quad<512, true>(ctx, a, lay.total, cap) : launch_quad<512, false>(ctx, a, lay.total, cap);
+    default: return ov ? launch_quad<384, true>(ctx, a, lay.total, cap) : launch_quad<384, false>(ctx, a, lay.total, cap);
+    }
+}
+
 // Enqueue one batch.  All pointers in `jobs`/`out` are device pointers here.
 int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+    {
+        const int rq = enqueue_quad(ctx, g, jobs, out);
+        if (rq != 1) return rq;
+    }
     const uint32_t V = g->d.V;
     const bool q16 = V <= 0xFFFFu;
     const Layout lay = make_layout(V, g->d.E, q16 ? 2 : 4);
@@ -136,8 +205,8 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
         int v = atoi(lim);
         if (v >= 1 && v < per_sm) per_sm = v;
     }
-    int grid = ctx->sm_count * per_sm;
-    a.sm_limit = ctx->reserved_sms > 0 ? (uint32_t)(ctx->sm_count - ctx->reserved_sms) : 0u;
+    // SMs reserved for a concurrent kernel: launch fewer persistent CTAs (job fetch is dynamic)
+    int grid = (ctx->sm_count - ctx->reserved_sms) * per_sm;
     if (const char *mg = getenv("HSPF_MAX_GRID")) {   // tuning knob (experiments only)
         int v = atoi(mg);
         if (v >= 1 && v < grid) grid = v;
@@ -343,6 +412,15 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         std::vector<uint32_t> edge16(pack_in ? E : 0);     // forward edges as (head | cost << 16)
         for (uint32_t e = 0; e < (uint32_t)edge16.size(); ++e) edge16[e] = fedge[e].x | (fedge[e].y << 16);
 
+        // quad-space image for spf_quad_kernel (quad_layout.h), when ids and costs pack
+        QuadHost QH;
+        {
+            std::vector<uint32_t> isrc(E), icost(E), ifwd(E);
+            for (uint32_t k = 0; k < E; ++k) { isrc[k] = iedge[k].x; icost[k] = iedge[k].y; ifwd[k] = iedge[k].z; }
+            QH = build_quads(V, E, g->row_ptr, g->col, g->cost, g->vflags, irow.data(), isrc.data(), icost.data(),
+                             ifwd.data(), g->delta);
+        }
+
         auto al = [](size_t x) { return (x + 255) / 256 * 256; };
         const size_t o_row = 0;
         const size_t o_edge = o_row + al((size_t)(V + 1) * 4);
@@ -354,7 +432,15 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         const size_t o_edge16 = o_iedge16 + al(iedge16.size() * 4);
         const size_t o_iqrow = o_edge16 + al(edge16.size() * 4);
         const size_t o_iquad = o_iqrow + al(iquad_row.size() * 4);
-        const size_t total = o_iquad + al(iquad.size() * 4);
+        const size_t o_fq = o_iquad + al(iquad.size() * 4);
+        const size_t o_fcont = o_fq + al(QH.fq.size() * 4);
+        const size_t o_slot = o_fcont + al(QH.fcont.size() * 4);
+        const size_t o_vert = o_slot + al(QH.slot_of.size() * 2);
+        const size_t o_iq = o_vert + al(QH.vert_of.size() * 2);
+        const size_t o_imeta = o_iq + al(QH.iq.size() * 4);
+        const size_t o_fpos = o_imeta + al(QH.imeta.size() * 4);
+        const size_t o_ipos = o_fpos + al(QH.fpos.size() * 4);
+        const size_t total = o_ipos + al(QH.ipos.size() * 4);
 
         hspf_graph *G = new hspf_graph();
         cudaError_t e = cudaSetDevice(ctx->device);
@@ -375,6 +461,18 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         if (!edge16.empty()) std::memcpy(host.data() + o_edge16, edge16.data(), edge16.size() * 4);
         if (!iquad_row.empty()) std::memcpy(host.data() + o_iqrow, iquad_row.data(), iquad_row.size() * 4);
         if (!iquad.empty()) std::memcpy(host.data() + o_iquad, iquad.data(), iquad.size() * 4);
+        if (QH.eligible) {
+            std::memcpy(host.data() + o_fq, QH.fq.data(), QH.fq.size() * 4);
+            std::memcpy(host.data() + o_fcont, QH.fcont.data(), QH.fcont.size() * 4);
+            std::memcpy(host.data() + o_slot, QH.slot_of.data(), QH.slot_of.size() * 2);
+            std::memcpy(host.data() + o_vert, QH.vert_of.data(), QH.vert_of.size() * 2);
+            std::memcpy(host.data() + o_iq, QH.iq.data(), QH.iq.size() * 4);
+            std::memcpy(host.data() + o_imeta, QH.imeta.data(), QH.imeta.size() * 4);
+            if (E) {
+                std::memcpy(host.data() + o_fpos, QH.fpos.data(), QH.fpos.size() * 4);
+                std::memcpy(host.data() + o_ipos, QH.ipos.data(), QH.ipos.size() * 4);
+            }
+        }
         e = cudaMemcpyAsync(b, host.data(), total, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { cudaFree(G->blob); delete G; return cuda_fail(ctx, e, "graph H2D"); }
@@ -390,6 +488,22 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         G->d.edge16 = edge16.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_edge16);
         G->d.iquad_row = iquad_row.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_iqrow);
         G->d.iquad = iquad.empty() ? nullptr : reinterpret_cast<const uint4 *>(b + o_iquad);
+        G->has_quads = QH.eligible && G->d.iedge16 != nullptr;
+        G->quad_why = QH.why;
+        if (G->has_quads) {
+            G->q.NQ = QH.NQ; G->q.NIQ = QH.NIQ; G->q.shift = QH.shift;
+            uint32_t st = 0;
+            while ((1u << st) < QH.max_ichain) ++st;
+            G->q.isteps = st;
+            G->q.fq = reinterpret_cast<const uint4 *>(b + o_fq);
+            G->q.fcont = reinterpret_cast<const uint32_t *>(b + o_fcont);
+            G->q.slot_of = reinterpret_cast<const uint16_t *>(b + o_slot);
+            G->q.vert_of = reinterpret_cast<const uint16_t *>(b + o_vert);
+            G->q.iq = reinterpret_cast<const uint4 *>(b + o_iq);
+            G->q.imeta = reinterpret_cast<const uint2 *>(b + o_imeta);
+            G->q.fpos = reinterpret_cast<const uint32_t *>(b + o_fpos);
+            G->q.ipos = reinterpret_cast<const uint32_t *>(b + o_ipos);
+        }
         G->d.reject_above = g->reject_above;
         G->d.saturate_at = g->saturate_at;
         G->d.flags = g->flags;
@@ -573,6 +687,37 @@ int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, co
         return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
     } catch (...) {
         return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+int hspf_debug_quad_image(const hspf_csr *g, uint32_t hdr[8], uint32_t *fq, uint32_t *fcont, uint16_t *slot_of,
+                          uint16_t *vert_of, uint32_t *iq, uint32_t *imeta, uint32_t *fpos, uint32_t *ipos) {
+    if (!g || !hdr) return HSPF_E_INVAL;
+    try {
+        const uint32_t V = g->n_vertices, E = g->n_edges;
+        std::vector<uint32_t> irow(V + 1, 0), isrc(E), icost(E), ifwd(E);
+        for (uint32_t e = 0; e < E; ++e) {
+            if (g->col[e] >= V) return HSPF_E_INVAL;
+            irow[g->col[e] + 1]++;
+        }
+        for (uint32_t v = 0; v < V; ++v) irow[v + 1] += irow[v];
+        std::vector<uint32_t> fill(irow.begin(), irow.end() - 1);
+        for (uint32_t u = 0; u < V; ++u)
+            for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e) {
+                const uint32_t k = fill[g->col[e]]++;
+                isrc[k] = u; icost[k] = g->cost[e]; ifwd[k] = e;
+            }
+        QuadHost Q = build_quads(V, E, g->row_ptr, g->col, g->cost, g->vflags, irow.data(), isrc.data(), icost.data(),
+                                 ifwd.data(), g->delta);
+        hdr[0] = Q.eligible ? 1u : 0u; hdr[1] = Q.NQ; hdr[2] = Q.NIQ; hdr[3] = Q.shift;
+        hdr[4] = Q.max_ichain; hdr[5] = Q.max_atoms; hdr[6] = 0; hdr[7] = 0;
+        if (!Q.eligible) return HSPF_OK;
+        auto cp = [](auto *dst, const auto &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+        cp(fq, Q.fq); cp(fcont, Q.fcont); cp(slot_of, Q.slot_of); cp(vert_of, Q.vert_of);
+        cp(iq, Q.iq); cp(imeta, Q.imeta); cp(fpos, Q.fpos); cp(ipos, Q.ipos);
+        return HSPF_OK;
+    } catch (...) {
+        return HSPF_E_NOMEM;
     }
 }
 

@@ -90,7 +90,6 @@ struct BatchArgs {
     size_t ws_stride;         // bytes per CTA (0: state in smem)
     uint32_t *job_counter;    // dynamic job fetch
     uint32_t jump_ok;         // layout allows the pointer-jumping next-hop phase (see phase 3J)
-    uint32_t sm_limit;        // CTAs that land on an SM with %smid >= sm_limit exit at once (0 = no limit)
     unsigned long long *prof; // optional [gridDim][16] per-phase cycle counters (debug), may be null
 };
 
@@ -227,14 +226,6 @@ template <typename VT, bool kSmemState, bool kFast>
 __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ Small S;
-
-    if (a.sm_limit) {
-        // leave the highest-numbered SMs to a concurrent kernel (the NCCL all-gather of the
-        // previous batch): job fetch is dynamic, so the other CTAs simply do all the work
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (smid >= a.sm_limit) return;
-    }
 
     const DevGraph &g = a.g;
     const Layout &L = a.lay;

@@ -1,0 +1,602 @@
+// spf_quad.cuh — the fast path of the batched SPF engine (sm_100a): one CTA per job,
+// three CTAs per SM, the whole per-job state in shared memory, the link-state graph
+// read as 16-byte QUADS from L2 (quad_layout.h).
+//
+// Same results as spf_batch_kernel (spf_kernel.cuh) and as the reference Dijkstra
+//   holo-ospf/src/spf.rs:587-729 (run_area) / holo-isis/src/spf.rs:525-707 (compute_spt)
+// under the static-order conditions of SURVEY.md §8a #1; what differs is the data
+// layout and the shape of the parallel work:
+//
+//   1. SSSP    label-correcting relaxation in QUAD SPACE: the frontier is a bitmap over
+//              forward quads, a work item is one quad (one 128-bit load, four branch-free
+//              relaxations, atomicMin on the slot-indexed distance array).  Buckets are a
+//              ring of four frontier bitmaps indexed by (distance >> shift) & 3, so moving
+//              to the next bucket is a bitmap switch, not a scan of the distance array.
+//              A round is: compact the current bucket's bitmap into a bounded queue
+//              (chains of a multi-quad vertex are spread with bit operations), barrier,
+//              expand, barrier.
+//   2. parents one thread per IN-quad (edge-uniform, no per-vertex degree loop): ECMP-DAG
+//              predicate dist[u] + c == dist[v] on four records, chain partials combined
+//              with warp shuffles; writes dist / first_parent / n_parents planes.
+//   3. hops and next hops: pointer jumping over the first-parent tree, ECMP vertices as
+//              jump terminals (the scheme of spf_kernel.cuh phase 3J), 16 first-hop atoms
+//              per pass, up to four passes (64 atoms).
+//
+// Eligibility (checked by the host, hspf_capi.cu): packed ids and costs (V, quads < 65535,
+// costs <= 65534, degrees <= 128), no LEAF vertex flags, no hop-count mode, one next-hop
+// word.  Everything else runs spf_batch_kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "spf_kernel.cuh"
+
+namespace hspf {
+
+constexpr uint32_t kJsInvalid = 8u;   // HSPF_JS_INVALID
+constexpr int kQMaxRoot = 64;         // non-HOP root neighbours tracked (>= 64 atoms is refused anyway)
+
+struct QuadDev {
+    uint32_t NQ, NIQ, shift, isteps;
+    const uint4 *fq;            // [NQ]
+    const uint32_t *fcont;      // [NQ/32]
+    const uint16_t *slot_of;    // [V]
+    const uint16_t *vert_of;    // [NQ]
+    const uint4 *iq;            // [NIQ]
+    const uint2 *imeta;         // [NIQ]
+    const uint32_t *fpos;       // [E]
+    const uint32_t *ipos;       // [E]
+};
+
+struct QuadLayout {   // byte offsets into dynamic shared memory
+    uint32_t dist, queue, ring, cont, fl_hop, h0, ecmp, elist, total;
+    uint32_t qcap;    // queue capacity (entries)
+};
+
+struct QuadArgs {
+    DevGraph g;
+    QuadDev q;
+    QuadLayout lay;
+    uint32_t n_jobs;
+    const uint32_t *roots;
+    const uint32_t *ov_off;
+    const uint32_t *ov_edge;
+    const uint32_t *ov_cost;
+    uint32_t *out_dist;
+    uint16_t *out_hops;
+    uint32_t *out_fp;
+    uint16_t *out_npar;
+    uint64_t *out_nh;
+    uint32_t *out_status;
+    uint32_t *job_counter;
+    unsigned long long *prof;   // optional [gridDim][16] cycle counters
+};
+
+inline QuadLayout make_quad_layout(uint32_t V, uint32_t NQ, uint32_t qcap) {
+    QuadLayout L{};
+    auto al = [](size_t x) { return (uint32_t)((x + 15) / 16 * 16); };
+    const uint32_t nbv = (V + 31) / 32, nbw = NQ / 32;
+    uint32_t o = 0;
+    L.dist = o; o += al((size_t)NQ * 4);
+    L.queue = o; o += al((size_t)qcap * 2);
+    // phase 3: jump words u32[V] over dist, ECMP vertex list u16[V] behind them
+    L.elist = al((size_t)V * 4);
+    if (L.elist + al((size_t)V * 2) > o) o = L.elist + al((size_t)V * 2);
+    L.ring = o; o += al((size_t)4 * nbw * 4);
+    L.cont = o; o += al((size_t)nbw * 4);
+    L.fl_hop = o; o += al((size_t)nbv * 4);
+    L.h0 = o; o += al((size_t)nbv * 4);
+    L.ecmp = o; o += al((size_t)nbv * 4);
+    L.total = o;
+    L.qcap = qcap;
+    return L;
+}
+
+struct QSmall {
+    uint32_t cnt[2];
+    uint32_t status;
+    uint32_t job;
+    uint32_t n_ov, sh;
+    uint32_t ov_edge[kMaxOv], ov_cost[kMaxOv];          // forward edge, new cost (kInf = disabled)
+    uint32_t ov_fq[kMaxOv], ov_iq[kMaxOv];              // quad * 4 + record in fq / iq
+    uint32_t n_roottab, root_rb, n_atoms;
+    uint32_t rt_target[kQMaxRoot], rt_base[kQMaxRoot], rt_cost[kQMaxRoot];
+};
+
+#define HSPF_QMARK(k)                                                            \
+    do {                                                                         \
+        if (a.prof && tid == 0) {                                                \
+            const long long now_ = clock64();                                    \
+            a.prof[(size_t)blockIdx.x * 16 + (k)] += (unsigned long long)(now_ - t_mark); \
+            t_mark = now_;                                                       \
+        }                                                                        \
+    } while (0)
+
+template <int T, bool kOv>
+__global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
+    extern __shared__ __align__(16) uint8_t qsm[];
+    __shared__ QSmall S;
+
+    const DevGraph &g = a.g;
+    const QuadDev &Q = a.q;
+    const QuadLayout &L = a.lay;
+    const uint32_t V = g.V, NQ = Q.NQ, NBW = NQ >> 5, nbv = (V + 31) >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t qcap = L.qcap;
+
+    uint32_t *dist = reinterpret_cast<uint32_t *>(qsm + L.dist);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(qsm + L.queue);
+    uint32_t *ring = reinterpret_cast<uint32_t *>(qsm + L.ring);
+    uint32_t *cont_s = reinterpret_cast<uint32_t *>(qsm + L.cont);
+    uint32_t *fl_hop = reinterpret_cast<uint32_t *>(qsm + L.fl_hop);
+    uint32_t *h0bm = reinterpret_cast<uint32_t *>(qsm + L.h0);
+    uint32_t *ecmpbm = reinterpret_cast<uint32_t *>(qsm + L.ecmp);
+    uint32_t *word = dist;                                   // phase 3
+    uint16_t *elist = reinterpret_cast<uint16_t *>(qsm + L.elist);
+
+    long long t_mark = clock64();
+
+    // once per CTA: chain-continuation bits and the HOP flags as bitmaps
+    for (uint32_t w = tid; w < NBW; w += T) cont_s[w] = Q.fcont[w];
+    for (uint32_t w = tid; w < nbv; w += T) {
+        uint32_t h = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t v = w * 32 + b;
+            if (v < V && (g.vflags[v] & kVfHop)) h |= 1u << b;
+        }
+        fl_hop[w] = h;
+    }
+    auto is_hop = [&](uint32_t v) -> bool { return (fl_hop[v >> 5] >> (v & 31)) & 1u; };
+
+    for (;;) {
+        // ---- fetch next job -------------------------------------------------------
+        __syncthreads();
+        if (tid == 0) S.job = atomicAdd(a.job_counter, 1u);
+        __syncthreads();
+        const uint32_t job = S.job;
+        if (job >= a.n_jobs) break;
+        const uint32_t root = a.roots[job];
+        uint32_t n_ov_raw = 0;
+        if (kOv && a.ov_off) n_ov_raw = a.ov_off[job + 1] - a.ov_off[job];
+        if (root >= V || n_ov_raw > (uint32_t)kMaxOv) {      // device-pointer callers are not validated on the host
+            if (tid == 0) a.out_status[job] = kJsInvalid;
+            continue;
+        }
+        const size_t jo = (size_t)job * V;
+        uint32_t *o_dist = a.out_dist + jo;
+        uint16_t *o_hops = a.out_hops + jo;
+        uint32_t *o_fp = a.out_fp + jo;
+        uint16_t *o_npar = a.out_npar + jo;
+        uint64_t *o_nh = a.out_nh + jo;
+
+        // ---- per-job init -----------------------------------------------------------
+        {
+            uint4 *d4 = reinterpret_cast<uint4 *>(dist);
+            const uint4 inf4 = make_uint4(kInf, kInf, kInf, kInf);
+            for (uint32_t i = tid; i < NQ / 4; i += T) d4[i] = inf4;
+            for (uint32_t i = tid; i < 4 * NBW; i += T) ring[i] = 0;
+            for (uint32_t w = tid; w < nbv; w += T) { h0bm[w] = 0; ecmpbm[w] = 0; }
+        }
+        if (tid == 0) {
+            S.status = 0;
+            S.cnt[0] = 0;
+            S.cnt[1] = 0;
+            S.n_ov = n_ov_raw;
+            S.sh = Q.shift;
+        }
+        __syncthreads();
+        if (kOv && tid < n_ov_raw) {
+            const uint32_t e = a.ov_edge[a.ov_off[job] + tid];
+            const uint32_t c = a.ov_cost[a.ov_off[job] + tid];
+            if (e >= g.E) {
+                atomicOr(&S.status, kJsInvalid);
+                S.ov_edge[tid] = kInf; S.ov_cost[tid] = kInf; S.ov_fq[tid] = kInf; S.ov_iq[tid] = kInf;
+            } else {
+                S.ov_edge[tid] = e;
+                S.ov_cost[tid] = c;
+                S.ov_fq[tid] = Q.fpos[e];
+                S.ov_iq[tid] = Q.ipos[e];
+                const uint32_t tail = Q.vert_of[Q.fpos[e] >> 2];
+                if (c == 0 && (g.vflags[tail] & kVfHop)) atomicOr(&S.status, kJsOrder);
+                if (c != kInf) {
+                    // a relaxation out of bucket b must land in b .. b+3 (ring of four bitmaps)
+                    uint32_t sh = Q.shift;
+                    while (sh < 31 && (3ull << sh) < (unsigned long long)c) ++sh;
+                    atomicMax(&S.sh, sh);
+                }
+            }
+        }
+        const uint32_t rs = Q.slot_of[root];
+        if (tid == 0) {
+            dist[rs] = 0;
+            ring[rs >> 5] = 1u << (rs & 31);     // bucket 0
+        }
+        __syncthreads();
+        const uint32_t n_ov = kOv ? S.n_ov : 0u;
+        auto ov_cost_of = [&](uint32_t e, uint32_t c) -> uint32_t {   // cost of forward edge e under this job's overrides
+            for (uint32_t k = 0; k < n_ov; ++k)
+                if (S.ov_edge[k] == e) c = S.ov_cost[k];
+            return c;
+        };
+        // root edge table: first-hop atom bases behind the root's non-HOP neighbours
+        if (tid == 32 % T) {
+            const uint32_t rb = g.row[root], re = g.row[root + 1];
+            uint32_t nt = 0, nextbase = re - rb;
+            for (uint32_t e = rb; e < re; ++e) {
+                const uint2 ec = g.edge[e];
+                const uint32_t h = ec.x;
+                if (!(g.vflags[h] & kVfHop)) {
+                    if (nt < (uint32_t)kQMaxRoot) {
+                        S.rt_target[nt] = h;
+                        S.rt_base[nt] = nextbase;
+                        S.rt_cost[nt] = ov_cost_of(e, ec.y);
+                        ++nt;
+                    } else {
+                        atomicOr(&S.status, kJsTooManyAtoms);
+                    }
+                    nextbase += g.row[h + 1] - g.row[h];
+                }
+            }
+            S.n_roottab = nt;
+            S.root_rb = rb;
+            if (nextbase > 64u) { atomicOr(&S.status, kJsTooManyAtoms); nextbase = 64u; }
+            S.n_atoms = nextbase;
+        }
+        __syncthreads();
+        HSPF_QMARK(0);   // job fetch + init
+
+        // ======================= phase 1: SSSP in quad space ===========================
+        const uint32_t sh = kOv ? S.sh : Q.shift;
+        const uint32_t rej = g.reject_above;
+        {
+            uint32_t cur = 0, empties = 0, p = 0;
+            for (;;) {
+                uint32_t *bm = ring + (cur & 3u) * NBW;
+                long long t_sub = 0;
+                if (a.prof && tid == 0) t_sub = clock64();
+                // ---- compact the current bucket's bitmap into the queue ------------------
+                for (uint32_t w0 = 0; w0 < NBW; w0 += T) {
+                    const uint32_t w = w0 + tid;
+                    const uint32_t bits = (w < NBW) ? bm[w] : 0u;
+                    if (!__any_sync(0xffffffffu, bits != 0)) continue;
+                    uint32_t all = bits, C = 0;
+                    if (bits) {
+                        C = cont_s[w];
+                        uint32_t m = bits;
+                        while ((m = (m << 1) & C) != 0) all |= m;    // the other quads of a multi-quad vertex
+                    }
+                    const uint32_t n = __popc(all);
+                    uint32_t incl = n;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += t;
+                    }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t base = 0;
+                    if (lane == 31) base = atomicAdd(&S.cnt[p], tot);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    uint32_t pos = base + incl - n;
+                    if (n) {
+                        if (pos + n <= qcap) {
+                            bm[w] = 0;
+                            for (uint32_t b = all; b; b &= b - 1) {
+                                const uint32_t bit = __ffs(b) - 1;
+                                const uint32_t q = w * 32 + bit;
+                                queue[pos++] = (uint16_t)q;
+                                if ((C >> bit) & 1u) dist[q] = dist[q - 1];   // continuation quad: owner's distance
+                            }
+                        } else {
+                            // queue full: these vertices stay in the bitmap for the next round
+                            for (uint32_t q = pos; q < qcap && q < pos + n; ++q) queue[q] = 0xFFFFu;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 8] += n_ - t_sub; t_sub = n_; }
+                const uint32_t n_cur = min(S.cnt[p], qcap);
+                if (n_cur == 0) {
+                    if (++empties == 4) break;
+                    ++cur;
+                    __syncthreads();     // every thread has read S.cnt[p] == 0; the counter is reused as is
+                    continue;
+                }
+                empties = 0;
+                if (tid == 0) { S.cnt[p ^ 1] = 0; if (a.prof) { a.prof[(size_t)blockIdx.x * 16 + 7] += 1; a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; } }
+                // ---- expand: one quad per lane ---------------------------------------------
+                for (uint32_t i = tid; i < n_cur; i += T) {
+                    const uint32_t q = queue[i];
+                    if (q == 0xFFFFu) continue;
+                    const uint32_t du = dist[q];
+                    if ((du >> sh) != cur) continue;          // stale mark: settled in an earlier bucket
+                    const uint4 r4 = __ldg(&Q.fq[q]);
+                    uint32_t hs[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
+                    uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
+                    if (kOv) {
+                        for (uint32_t k = 0; k < n_ov; ++k) {
+                            const uint32_t fp_ = S.ov_fq[k];
+                            if ((fp_ >> 2) != q) continue;
+                            const uint32_t c = S.ov_cost[k];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if ((fp_ & 3u) == (uint32_t)j) {
+                                    if (c == kInf) { hs[j] = q; cs[j] = 0xFFFFu; } else cs[j] = c;
+                                }
+                        }
+                    }
+                    uint32_t dh[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dh[j] = dist[hs[j]];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
+                        if (nd < dh[j] && nd <= rej) {
+                            // fire-and-forget: nothing below waits on an atomic's result
+                            atomicMin(&dist[hs[j]], nd);
+                            atomicOr(&ring[((nd >> sh) & 3u) * NBW + (hs[j] >> 5)], 1u << (hs[j] & 31));
+                        }
+                    }
+                }
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
+                __syncthreads();
+                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 10] += n_ - t_sub; }
+                p ^= 1;
+            }
+        }
+        HSPF_QMARK(1);   // SSSP
+
+        // hops-0 non-HOP heads of root edges (their out-edges carry first-hop atoms)
+        if (tid < S.n_roottab) {
+            const uint32_t h = S.rt_target[tid], c = S.rt_cost[tid];
+            if (c != kInf && dist[Q.slot_of[h]] == c) atomicOr(&h0bm[h >> 5], 1u << (h & 31));
+        }
+        __syncthreads();
+        auto hops0 = [&](uint32_t u) -> bool { return u == root || ((h0bm[u >> 5] >> (u & 31)) & 1u); };
+
+        // first-hop atom seeds: one thread per atom, is its edge in the DAG?
+        const uint32_t n_atoms = S.n_atoms;
+        uint32_t seed_v = kInf;
+        if (tid < n_atoms) {
+            const uint32_t atom = tid, rdeg = g.row[root + 1] - S.root_rb;
+            uint32_t e = kInf, u = root;
+            if (atom < rdeg) {
+                e = S.root_rb + atom;
+            } else {
+                for (uint32_t k = 0; k < S.n_roottab; ++k) {
+                    const uint32_t N = S.rt_target[k], nb = S.rt_base[k];
+                    if (atom < nb || atom >= nb + (g.row[N + 1] - g.row[N])) continue;
+                    bool first = true;   // parallel root edges: only the first one's range is used
+                    for (uint32_t q = 0; q < k; ++q) first = first && S.rt_target[q] != N;
+                    if (first && hops0(N)) { u = N; e = g.row[N] + (atom - nb); }
+                    break;
+                }
+            }
+            if (e != kInf) {
+                const uint2 ec = g.edge[e];
+                const uint32_t c = kOv ? ov_cost_of(e, ec.y) : ec.y;
+                const uint32_t du = dist[Q.slot_of[u]], dh = dist[Q.slot_of[ec.x]];
+                if (du != kInf && dh != kInf && c != kInf && sat_add(du, c) == dh &&
+                    !((g.flags & kGfNoHopTargetNoNh) && !is_hop(ec.x)))
+                    seed_v = ec.x;
+            }
+        }
+
+        // ======================= phase 2: ECMP parents, one thread per in-quad =============
+        {
+            uint32_t sat_flag = 0;
+            const uint32_t NIQ = Q.NIQ, isteps = Q.isteps;
+            for (uint32_t i0 = 0; i0 < NIQ; i0 += T) {
+                const uint32_t i = i0 + tid;
+                if (i0 + (tid & ~31u) >= NIQ) break;           // whole warp out of range (NIQ % 32 == 0)
+                const uint2 m = __ldg(&Q.imeta[i]);
+                const uint4 r4 = __ldg(&Q.iq[i]);
+                const bool valid = m.x != 0xFFFFFFFFu;
+                const uint32_t sv = valid ? (m.x & 0xFFFFu) : 0u, v = m.x >> 16;
+                const uint32_t rem = m.y & 0xFFu, cpos = (m.y >> 8) & 0xFFu;
+                const uint32_t dv = dist[sv];
+                uint32_t su[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
+                uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
+                if (kOv) {
+                    for (uint32_t k = 0; k < n_ov; ++k) {
+                        const uint32_t ip_ = S.ov_iq[k];
+                        if ((ip_ >> 2) != i) continue;
+                        const uint32_t c = S.ov_cost[k];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if ((ip_ & 3u) == (uint32_t)j) {
+                                if (c == kInf) { su[j] = sv; cs[j] = 0xFFFFu; } else cs[j] = c;
+                            }
+                    }
+                }
+                uint32_t du[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) du[j] = dist[su[j]];
+                uint32_t cnt = 0, bd = kInf, bs = kInf;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t nd = kOv ? sat_add(du[j], cs[j]) : du[j] + cs[j];
+                    const bool ok = du[j] != kInf && nd == dv;
+                    const bool better = ok && (du[j] < bd || (du[j] == bd && su[j] < bs));
+                    cnt += ok ? 1u : 0u;
+                    bd = better ? du[j] : bd;
+                    bs = better ? su[j] : bs;
+                }
+                // combine the partial results of a chain (the quads of one vertex are adjacent lanes)
+                for (uint32_t s = 0, d = 1; s < isteps; ++s, d <<= 1) {
+                    const uint32_t ocnt = __shfl_down_sync(0xffffffffu, cnt, d);
+                    const uint32_t obd = __shfl_down_sync(0xffffffffu, bd, d);
+                    const uint32_t obs = __shfl_down_sync(0xffffffffu, bs, d);
+                    if (d <= rem) {
+                        cnt += ocnt;
+                        if (obd < bd || (obd == bd && obs < bs)) { bd = obd; bs = obs; }
+                    }
+                }
+                if (valid && cpos == 0) {
+                    if (v == root || dv == kInf) { cnt = 0; bs = kInf; }
+                    if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
+                    o_dist[v] = dv;
+                    o_fp[v] = cnt ? (uint32_t)Q.vert_of[bs] : kInf;
+                    o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
+                    if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
+                }
+            }
+            if (sat_flag) atomicOr(&S.status, kJsSaturated);
+        }
+        __syncthreads();
+        HSPF_QMARK(2);   // parents
+
+        // ======================= phase 3: pointer jumping ===============================
+        // Hops and next hops are path aggregates over the first-parent tree (sum of the HOP
+        // flags, OR of the first-hop atoms): pointer doubling, one 32-bit word per vertex
+        // (ancestor:16 | aggregate:16) that only its owner thread stores, so the rounds update
+        // in place.  See spf_kernel.cuh phase 3J for the derivation; the first parents are
+        // read back from the plane just written.
+        // -- hops: sum of HOP flags over (root, v]
+        for (uint32_t v = tid; v < V; v += T) {
+            const uint32_t f = __ldcg(&o_fp[v]);
+            word[v] = (f == kInf) ? (v << 16) : ((f << 16) | (is_hop(v) ? 1u : 0u));
+        }
+        __syncthreads();
+        for (;;) {
+            int ch = 0;
+            for (uint32_t v = tid; v < V; v += T) {
+                const uint32_t w = word[v], A = w >> 16;
+                if (A != root && A != v) {
+                    const uint32_t w2 = word[A];
+                    word[v] = (w2 & 0xFFFF0000u) | ((w + w2) & 0xFFFFu);
+                    ch |= (w2 >> 16) != root;
+                }
+            }
+            if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
+            if (!__syncthreads_or(ch)) break;
+        }
+        for (uint32_t v = tid; v < V; v += T) {
+            const uint32_t w = word[v];
+            const uint32_t h = (w >> 16) == v ? 0u : (w & 0xFFFFu);
+            o_hops[v] = (uint16_t)h;
+            // a hops-0 vertex that is not a head of a root edge cannot own atoms
+            if (h == 0 && v != root && (w >> 16) != v && !hops0(v) && g.row[v + 1] != g.row[v])
+                atomicOr(&S.status, kJsTooManyAtoms);
+        }
+        __syncthreads();
+        HSPF_QMARK(5);   // hops
+
+        // -- next hops.  nh[v] = atoms entering v | U nh[p] over DAG parents p that are not at
+        // hops 0.  The tree is cut below hops-0 vertices and AT ECMP vertices (jump terminals):
+        //   word[v] = (top[v], atoms on the segment (top[v], v])
+        // then the ECMP vertices are resolved among themselves (monotone sweeps to the fixpoint)
+        // and every vertex adds the final set of its top.  16 atoms per pass.
+        auto is_ecmp = [&](uint32_t v) -> bool { return (ecmpbm[v >> 5] >> (v & 31)) & 1u; };
+        // ECMP vertex list (ascending ids), built once
+        if (tid == 0) S.cnt[0] = 0;
+        __syncthreads();
+        for (uint32_t w0 = 0; w0 < nbv; w0 += T) {
+            const uint32_t w = w0 + tid;
+            const uint32_t bits = (w < nbv) ? ecmpbm[w] : 0u;
+            if (!__any_sync(0xffffffffu, bits != 0)) continue;
+            const uint32_t n = __popc(bits);
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&S.cnt[0], tot);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + incl - n;
+            for (uint32_t b = bits; b; b &= b - 1) elist[pos++] = (uint16_t)(w * 32 + (__ffs(b) - 1));
+        }
+        __syncthreads();
+        const uint32_t n_e = S.cnt[0];
+        // DAG parents of an ECMP vertex are re-derived from the distance plane just written
+        auto parents = [&](uint32_t x, auto &&f) {
+            const uint32_t dx = __ldcg(&o_dist[x]);
+            for (uint32_t j = g.irow[x]; j < g.irow[x + 1]; ++j) {
+                uint32_t u, c;
+                if constexpr (kOv) {
+                    const uint4 r = g.iedge[j];
+                    u = r.x; c = ov_cost_of(r.z, r.y);
+                    if (c == kInf) continue;
+                } else {
+                    const uint32_t r = g.iedge16[j];
+                    u = r & 0xFFFFu; c = r >> 16;
+                }
+                const uint32_t du = __ldcg(&o_dist[u]);
+                if (du != kInf && sat_add(du, c) == dx && !hops0(u)) f(u);
+            }
+        };
+        uint32_t pc[4] = {kInf, kInf, kInf, kInf};
+        bool cached = false;
+        if (n_e <= (uint32_t)T && tid < n_e) {
+            uint32_t n = 0;
+            parents(elist[tid], [&](uint32_t u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (n == (uint32_t)k) pc[k] = u;
+                ++n;
+            });
+            cached = n <= 4;
+        }
+        for (uint32_t pass = 0; pass * 16u < n_atoms || pass == 0; ++pass) {
+            for (uint32_t v = tid; v < V; v += T) {
+                const uint32_t f = __ldcg(&o_fp[v]);
+                word[v] = ((f == kInf || hops0(f)) ? root : f) << 16;
+            }
+            __syncthreads();
+            if (seed_v != kInf && (tid >> 4) == pass) atomicOr(&word[seed_v], 1u << (tid & 15));
+            __syncthreads();
+            for (;;) {
+                int ch = 0;
+                for (uint32_t v = tid; v < V; v += T) {
+                    const uint32_t w = word[v], A = w >> 16;
+                    if (A != root && !is_ecmp(A)) {
+                        const uint32_t w2 = word[A], A2 = w2 >> 16;
+                        word[v] = (w2 & 0xFFFF0000u) | ((w | w2) & 0xFFFFu);
+                        ch |= A2 != root && !is_ecmp(A2);
+                    }
+                }
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 14] += 1;
+                if (!__syncthreads_or(ch)) break;
+            }
+            // ECMP vertices: own segment | final set of own top | the same of every other parent
+            if (n_e) {
+                for (;;) {
+                    int ch = 0;
+                    for (uint32_t i = tid; i < n_e; i += T) {
+                        const uint32_t x = elist[i];
+                        const uint32_t w = word[x], Tx = w >> 16;
+                        uint32_t need = (Tx != root) ? word[Tx] : 0u;
+                        auto pull_parent = [&](uint32_t u) {
+                            const uint32_t wp = word[u], Tp = wp >> 16;
+                            need |= wp;
+                            if (Tp != root) need |= word[Tp];
+                        };
+                        if (cached) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (pc[k] != kInf) pull_parent(pc[k]);
+                        } else {
+                            parents(x, pull_parent);
+                        }
+                        need &= 0xFFFFu & ~w;
+                        if (need) { word[x] = w | need; ch = 1; }
+                    }
+                    if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 15] += 1;
+                    if (!__syncthreads_or(ch)) break;
+                }
+            }
+            for (uint32_t v = tid; v < V; v += T) {
+                const uint32_t w = word[v], Tv = w >> 16;
+                uint32_t m = w;
+                if (Tv != root) m |= word[Tv];
+                const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
+                if (pass == 0) o_nh[v] = bits; else o_nh[v] |= bits;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) a.out_status[job] = S.status;
+        HSPF_QMARK(4);   // next hops
+    }
+}
+
+}  // namespace hspf

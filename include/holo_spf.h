@@ -90,6 +90,12 @@ extern "C" {
 #define HSPF_JS_ORDER          0x4u /* an override put a zero cost on a link out of a
                                        hop-counting vertex: pop-order dependent, use the
                                        CPU path (same reason as HSPF_E_NEEDS_ORACLE)    */
+#define HSPF_JS_INVALID        0x8u /* malformed job (root >= n_vertices, more than
+                                       HSPF_MAX_OVERRIDES overrides, override edge >= n_edges):
+                                       the job was skipped, its planes are not written.  Only
+                                       reachable with HSPF_RUN_DEVICE_PTRS / hspf_run_batch_async,
+                                       whose job arrays the host cannot see; host-pointer calls
+                                       fail with HSPF_E_INVAL before anything runs            */
 
 /*
  * Flattened link-state graph of one area / level / topology.
@@ -233,6 +239,14 @@ int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms);
  * compaction, barrier), 12 frontier entries, 13-15 jump phase: hop rounds, next-hop rounds,
  * ECMP sweeps (Kahn path: round internals).  `out` may be NULL. */
 int hspf_debug_phase_profile(hspf_ctx *ctx, int enable, uint64_t out[16]);
+
+/* Debug / test aid (host only, no CUDA call): build the quad-space image the fast-path kernel
+ * reads (holo_b200/csrc/quad_layout.h) and copy it out.  hdr = {eligible, n_fwd_quads, n_in_quads,
+ * bucket shift, longest in-quad chain, largest atom count, 0, 0}.  Call once with NULL arrays to
+ * get the sizes: fq/iq [4*quads], fcont [quads/32], slot_of [V], vert_of [fwd quads],
+ * imeta [2*in quads], fpos/ipos [E]. */
+int hspf_debug_quad_image(const hspf_csr *g, uint32_t hdr[8], uint32_t *fq, uint32_t *fcont, uint16_t *slot_of,
+                          uint16_t *vert_of, uint32_t *iq, uint32_t *imeta, uint32_t *fpos, uint32_t *ipos);
 
 /* ---- Multi-GPU result exchange over NVLink peer memory (one process per GPU) --------
  * SURVEY.md §8e / BASELINE north_star: batches larger than one GPU are sharded by root and

@@ -259,11 +259,14 @@ def test_jump_and_kahn_next_hop_phases_agree_with_oracle(ctx, monkeypatch, V, E,
     refs = [pyoracle.csr_spf(csr, int(r), vec_mode=int(isis), nh_words=1) for r in roots]
     ok = [j for j, ref in enumerate(refs) if ref["status"] == 0]
     assert len(ok) > len(roots) // 2
-    for no_jump in (False, True):
-        if no_jump:
-            monkeypatch.setenv("HSPF_NO_JUMP", "1")
-        else:
-            monkeypatch.delenv("HSPF_NO_JUMP", raising=False)
+    # three device paths: the quad-space kernel (default), and spf_batch_kernel with the
+    # pointer-jumping and the Kahn next-hop phase
+    for no_quad, no_jump in ((False, False), (True, False), (True, True)):
+        for name, on in (("HSPF_NO_QUAD", no_quad), ("HSPF_NO_JUMP", no_jump)):
+            if on:
+                monkeypatch.setenv(name, "1")
+            else:
+                monkeypatch.delenv(name, raising=False)
         res = ctx.run(g, roots, nh_words=1)   # a root that ran out of atoms only flags its own job
         for j in ok:
             check(res, j, refs[j])
