@@ -75,7 +75,7 @@ struct QuadArgs {
 inline QuadLayout make_quad_layout(uint32_t V, uint32_t NQ, uint32_t qcap) {
     QuadLayout L{};
     auto al = [](size_t x) { return (uint32_t)((x + 15) / 16 * 16); };
-    const uint32_t nbv = (V + 31) / 32, nbw = NQ / 32;
+    const uint32_t nbv = (V + 31) / 32, nbw = (NQ / 32 + 1u) & ~1u;   // bitmap rows: an even number of words
     uint32_t o = 0;
     L.dist = o; o += al((size_t)NQ * 4);
     L.queue = o; o += al((size_t)qcap * 2);
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
     const QuadDev &Q = a.q;
     const QuadLayout &L = a.lay;
     const uint32_t V = g.V, NQ = Q.NQ, NBW = NQ >> 5, nbv = (V + 31) >> 5;
+    const uint32_t NBWp = (NBW + 1u) & ~1u;     // bitmap row stride: an even number of words
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t qcap = L.qcap;
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
     long long t_mark = clock64();
 
     // once per CTA: chain-continuation bits and the HOP flags as bitmaps
-    for (uint32_t w = tid; w < NBW; w += T) cont_s[w] = Q.fcont[w];
+    for (uint32_t w = tid; w < NBWp; w += T) cont_s[w] = (w < NBW) ? Q.fcont[w] : 0u;
     for (uint32_t w = tid; w < nbv; w += T) {
         uint32_t h = 0;
         for (uint32_t b = 0; b < 32; ++b) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             uint4 *d4 = reinterpret_cast<uint4 *>(dist);
             const uint4 inf4 = make_uint4(kInf, kInf, kInf, kInf);
             for (uint32_t i = tid; i < NQ / 4; i += T) d4[i] = inf4;
-            for (uint32_t i = tid; i < 4 * NBW; i += T) ring[i] = 0;
+            for (uint32_t i = tid; i < 4 * NBWp; i += T) ring[i] = 0;
             for (uint32_t w = tid; w < nbv; w += T) { h0bm[w] = 0; ecmpbm[w] = 0; }
         }
         if (tid == 0) {
@@ -249,23 +250,76 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         const uint32_t sh = kOv ? S.sh : Q.shift;
         const uint32_t rej = g.reject_above;
         {
+            // one quad: four branch-free relaxations (pad records never improve anything)
+            auto relax = [&](uint32_t q, uint32_t du, const uint4 &r4) {
+                uint32_t hs[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
+                uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
+                if (kOv) {
+                    for (uint32_t k = 0; k < n_ov; ++k) {
+                        const uint32_t fp_ = S.ov_fq[k];
+                        if ((fp_ >> 2) != q) continue;
+                        const uint32_t c = S.ov_cost[k];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if ((fp_ & 3u) == (uint32_t)j) {
+                                if (c == kInf) { hs[j] = q; cs[j] = 0xFFFFu; } else cs[j] = c;
+                            }
+                    }
+                }
+                uint32_t dh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dh[j] = dist[hs[j]];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
+                    if (nd < dh[j] && nd <= rej) {
+                        // fire-and-forget: nothing below waits on an atomic's result
+                        atomicMin(&dist[hs[j]], nd);
+                        atomicOr(&ring[((nd >> sh) & 3u) * NBWp + (hs[j] >> 5)], 1u << (hs[j] & 31));
+                    }
+                }
+            };
+            // queue the set bits of one bitmap word (ascending); a continuation quad gets its
+            // owner's distance (the previous quad's: chains are consecutive and ascending)
+            auto emit = [&](uint32_t bits, uint32_t C, uint32_t qbase, uint32_t &pos) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (bits) {
+                        const uint32_t bit = __ffs(bits) - 1, q = qbase + bit;
+                        queue[pos++] = (uint16_t)q;
+                        if ((C >> bit) & 1u) dist[q] = dist[q - 1];
+                        bits &= bits - 1;
+                    }
+                }
+                while (bits) {
+                    const uint32_t bit = __ffs(bits) - 1, q = qbase + bit;
+                    queue[pos++] = (uint16_t)q;
+                    if ((C >> bit) & 1u) dist[q] = dist[q - 1];
+                    bits &= bits - 1;
+                }
+            };
+            const uint32_t ND = NBWp >> 1;     // bitmap rows as 64-bit words: two words per lane
             uint32_t cur = 0, empties = 0, p = 0;
             for (;;) {
-                uint32_t *bm = ring + (cur & 3u) * NBW;
+                uint2 *bm2 = reinterpret_cast<uint2 *>(ring + (cur & 3u) * NBWp);
                 long long t_sub = 0;
                 if (a.prof && tid == 0) t_sub = clock64();
                 // ---- compact the current bucket's bitmap into the queue ------------------
-                for (uint32_t w0 = 0; w0 < NBW; w0 += T) {
-                    const uint32_t w = w0 + tid;
-                    const uint32_t bits = (w < NBW) ? bm[w] : 0u;
-                    if (!__any_sync(0xffffffffu, bits != 0)) continue;
-                    uint32_t all = bits, C = 0;
-                    if (bits) {
-                        C = cont_s[w];
-                        uint32_t m = bits;
-                        while ((m = (m << 1) & C) != 0) all |= m;    // the other quads of a multi-quad vertex
+                for (uint32_t d0 = 0; d0 < ND; d0 += T) {
+                    const uint32_t d = d0 + tid;
+                    uint2 bb = make_uint2(0u, 0u);
+                    if (d < ND) bb = bm2[d];
+                    if (!__any_sync(0xffffffffu, (bb.x | bb.y) != 0)) continue;
+                    uint32_t a0 = bb.x, a1 = bb.y, C0 = 0, C1 = 0;
+                    if (bb.x | bb.y) {
+                        const uint2 cc = reinterpret_cast<const uint2 *>(cont_s)[d];
+                        C0 = cc.x; C1 = cc.y;
+                        uint32_t m = a0;
+                        while ((m = (m << 1) & C0) != 0) a0 |= m;    // the other quads of a multi-quad vertex
+                        m = a1;
+                        while ((m = (m << 1) & C1) != 0) a1 |= m;
                     }
-                    const uint32_t n = __popc(all);
+                    const uint32_t n = __popc(a0) + __popc(a1);
                     uint32_t incl = n;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -279,13 +333,9 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     uint32_t pos = base + incl - n;
                     if (n) {
                         if (pos + n <= qcap) {
-                            bm[w] = 0;
-                            for (uint32_t b = all; b; b &= b - 1) {
-                                const uint32_t bit = __ffs(b) - 1;
-                                const uint32_t q = w * 32 + bit;
-                                queue[pos++] = (uint16_t)q;
-                                if ((C >> bit) & 1u) dist[q] = dist[q - 1];   // continuation quad: owner's distance
-                            }
+                            bm2[d] = make_uint2(0u, 0u);
+                            emit(a0, C0, d * 64, pos);
+                            emit(a1, C1, d * 64 + 32, pos);
                         } else {
                             // queue full: these vertices stay in the bitmap for the next round
                             for (uint32_t q = pos; q < qcap && q < pos + n; ++q) queue[q] = 0xFFFFu;
@@ -303,39 +353,20 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 }
                 empties = 0;
                 if (tid == 0) { S.cnt[p ^ 1] = 0; if (a.prof) { a.prof[(size_t)blockIdx.x * 16 + 7] += 1; a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; } }
-                // ---- expand: one quad per lane ---------------------------------------------
-                for (uint32_t i = tid; i < n_cur; i += T) {
-                    const uint32_t q = queue[i];
-                    if (q == 0xFFFFu) continue;
-                    const uint32_t du = dist[q];
-                    if ((du >> sh) != cur) continue;          // stale mark: settled in an earlier bucket
-                    const uint4 r4 = __ldg(&Q.fq[q]);
-                    uint32_t hs[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
-                    uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
-                    if (kOv) {
-                        for (uint32_t k = 0; k < n_ov; ++k) {
-                            const uint32_t fp_ = S.ov_fq[k];
-                            if ((fp_ >> 2) != q) continue;
-                            const uint32_t c = S.ov_cost[k];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if ((fp_ & 3u) == (uint32_t)j) {
-                                    if (c == kInf) { hs[j] = q; cs[j] = 0xFFFFu; } else cs[j] = c;
-                                }
-                        }
-                    }
-                    uint32_t dh[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dh[j] = dist[hs[j]];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
-                        if (nd < dh[j] && nd <= rej) {
-                            // fire-and-forget: nothing below waits on an atomic's result
-                            atomicMin(&dist[hs[j]], nd);
-                            atomicOr(&ring[((nd >> sh) & 3u) * NBW + (hs[j] >> 5)], 1u << (hs[j] & 31));
-                        }
-                    }
+                // ---- expand: one quad per lane, two quads of a thread in flight -----------------
+                for (uint32_t i = tid; i < n_cur; i += 2 * T) {
+                    const uint32_t i1 = i + T;
+                    const uint32_t q0 = queue[i];
+                    const uint32_t q1 = (i1 < n_cur) ? (uint32_t)queue[i1] : 0xFFFFu;
+                    const uint32_t du0 = (q0 != 0xFFFFu) ? dist[q0] : kInf;
+                    const uint32_t du1 = (q1 != 0xFFFFu) ? dist[q1] : kInf;
+                    // a mark is stale when the vertex was settled in an earlier bucket
+                    const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
+                    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                    if (l0) r0 = __ldg(&Q.fq[q0]);
+                    if (l1) r1 = __ldg(&Q.fq[q1]);
+                    if (l0) relax(q0, du0, r0);
+                    if (l1) relax(q1, du1, r1);
                 }
                 if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();
@@ -385,15 +416,10 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         {
             uint32_t sat_flag = 0;
             const uint32_t NIQ = Q.NIQ, isteps = Q.isteps;
-            for (uint32_t i0 = 0; i0 < NIQ; i0 += T) {
-                const uint32_t i = i0 + tid;
-                if (i0 + (tid & ~31u) >= NIQ) break;           // whole warp out of range (NIQ % 32 == 0)
-                const uint2 m = __ldg(&Q.imeta[i]);
-                const uint4 r4 = __ldg(&Q.iq[i]);
-                const bool valid = m.x != 0xFFFFFFFFu;
-                const uint32_t sv = valid ? (m.x & 0xFFFFu) : 0u, v = m.x >> 16;
-                const uint32_t rem = m.y & 0xFFu, cpos = (m.y >> 8) & 0xFFu;
-                const uint32_t dv = dist[sv];
+            // DAG predicate on the four records of one in-quad -> (count, best (dist, slot) parent)
+            auto pull = [&](uint32_t i, const uint2 &m, const uint4 &r4, uint32_t &dv, uint32_t &cnt, uint32_t &bd, uint32_t &bs) {
+                const uint32_t sv = (m.x != 0xFFFFFFFFu) ? (m.x & 0xFFFFu) : 0u;
+                dv = dist[sv];
                 uint32_t su[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
                 uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
                 if (kOv) {
@@ -411,7 +437,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 uint32_t du[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) du[j] = dist[su[j]];
-                uint32_t cnt = 0, bd = kInf, bs = kInf;
+                cnt = 0; bd = kInf; bs = kInf;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du[j], cs[j]) : du[j] + cs[j];
@@ -421,7 +447,9 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     bd = better ? du[j] : bd;
                     bs = better ? su[j] : bs;
                 }
-                // combine the partial results of a chain (the quads of one vertex are adjacent lanes)
+            };
+            // combine the partial results of a chain (the quads of one vertex are adjacent lanes)
+            auto combine = [&](uint32_t rem, uint32_t &cnt, uint32_t &bd, uint32_t &bs) {
                 for (uint32_t s = 0, d = 1; s < isteps; ++s, d <<= 1) {
                     const uint32_t ocnt = __shfl_down_sync(0xffffffffu, cnt, d);
                     const uint32_t obd = __shfl_down_sync(0xffffffffu, bd, d);
@@ -431,14 +459,35 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                         if (obd < bd || (obd == bd && obs < bs)) { bd = obd; bs = obs; }
                     }
                 }
-                if (valid && cpos == 0) {
+            };
+            auto emit_v = [&](const uint2 &m, uint32_t dv, uint32_t cnt, uint32_t bs) {
+                if (m.x != 0xFFFFFFFFu && ((m.y >> 8) & 0xFFu) == 0) {      // first quad of a real vertex
+                    const uint32_t v = m.x >> 16;
                     if (v == root || dv == kInf) { cnt = 0; bs = kInf; }
                     if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
                     o_dist[v] = dv;
-                    o_fp[v] = cnt ? (uint32_t)Q.vert_of[bs] : kInf;
+                    o_fp[v] = cnt ? (uint32_t)__ldg(&Q.vert_of[bs]) : kInf;
                     o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
                     if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
                 }
+            };
+            // two in-quads of a thread in flight (NIQ % 32 == 0: a warp is in range as a whole)
+            const uint32_t wbase = tid & ~31u;
+            for (uint32_t i0 = 0; i0 + wbase < NIQ; i0 += 2 * T) {
+                const uint32_t ia = i0 + tid, ib = ia + T;
+                const bool hb = i0 + T + wbase < NIQ;                          // warp-uniform
+                const uint2 ma = __ldg(&Q.imeta[ia]);
+                const uint4 ra = __ldg(&Q.iq[ia]);
+                uint2 mb = make_uint2(0xFFFFFFFFu, 0u);
+                uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+                if (hb) { mb = __ldg(&Q.imeta[ib]); rb = __ldg(&Q.iq[ib]); }
+                uint32_t dva, ca, bda, bsa, dvb = kInf, cb = 0, bdb = kInf, bsb = kInf;
+                pull(ia, ma, ra, dva, ca, bda, bsa);
+                if (hb) pull(ib, mb, rb, dvb, cb, bdb, bsb);
+                combine(ma.y & 0xFFu, ca, bda, bsa);
+                if (hb) combine(mb.y & 0xFFu, cb, bdb, bsb);
+                emit_v(ma, dva, ca, bsa);
+                if (hb) emit_v(mb, dvb, cb, bsb);
             }
             if (sat_flag) atomicOr(&S.status, kJsSaturated);
         }
@@ -449,26 +498,37 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         // Hops and next hops are path aggregates over the first-parent tree (sum of the HOP
         // flags, OR of the first-hop atoms): pointer doubling, one 32-bit word per vertex
         // (ancestor:16 | aggregate:16) that only its owner thread stores, so the rounds update
-        // in place.  See spf_kernel.cuh phase 3J for the derivation; the first parents are
-        // read back from the plane just written.
-        // -- hops: sum of HOP flags over (root, v]
+        // in place (a reader sees the old or the new pair, both consistent).  Terminals point
+        // at themselves with an aggregate that is neutral under the update, so the update is
+        // unconditional: word[v] = (anc(word[A]), agg(v) (+) agg(word[A])).
+        // See spf_kernel.cuh phase 3J for the derivation; the first parents are read back
+        // from the plane just written.
+        // -- hops: sum of HOP flags over (root, v]; the root and unreached vertices are terminals
         for (uint32_t v = tid; v < V; v += T) {
             const uint32_t f = __ldcg(&o_fp[v]);
             word[v] = (f == kInf) ? (v << 16) : ((f << 16) | (is_hop(v) ? 1u : 0u));
         }
         __syncthreads();
+        uint32_t jump_rounds = 0;     // rounds in which some vertex still moved
         for (;;) {
             int ch = 0;
-            for (uint32_t v = tid; v < V; v += T) {
-                const uint32_t w = word[v], A = w >> 16;
-                if (A != root && A != v) {
-                    const uint32_t w2 = word[A];
-                    word[v] = (w2 & 0xFFFF0000u) | ((w + w2) & 0xFFFFu);
-                    ch |= (w2 >> 16) != root;
+            for (uint32_t v0 = tid; v0 < V; v0 += 4 * T) {
+                uint32_t w[4], w2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const uint32_t v = v0 + k * T; w[k] = (v < V) ? word[v] : 0u; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t v = v0 + k * T;
+                    // w2 is a terminal (points at itself, sum 0) or an ordinary vertex
+                    if (v < V) word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
+                    ch |= ((w2[k] ^ w[k]) >> 16) != 0;
                 }
             }
             if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
             if (!__syncthreads_or(ch)) break;
+            ++jump_rounds;
         }
         for (uint32_t v = tid; v < V; v += T) {
             const uint32_t w = word[v];
@@ -539,28 +599,49 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             cached = n <= 4;
         }
         for (uint32_t pass = 0; pass * 16u < n_atoms || pass == 0; ++pass) {
+            // terminals (the root, unreached vertices, ECMP vertices) point at themselves
             for (uint32_t v = tid; v < V; v += T) {
                 const uint32_t f = __ldcg(&o_fp[v]);
-                word[v] = ((f == kInf || hops0(f)) ? root : f) << 16;
+                uint32_t A = (f == kInf) ? v : (hops0(f) ? root : f);
+                if (is_ecmp(v)) A = v;
+                word[v] = A << 16;
             }
             __syncthreads();
             if (seed_v != kInf && (tid >> 4) == pass) atomicOr(&word[seed_v], 1u << (tid & 15));
             __syncthreads();
-            for (;;) {
-                int ch = 0;
-                for (uint32_t v = tid; v < V; v += T) {
-                    const uint32_t w = word[v], A = w >> 16;
-                    if (A != root && !is_ecmp(A)) {
-                        const uint32_t w2 = word[A], A2 = w2 >> 16;
-                        word[v] = (w2 & 0xFFFF0000u) | ((w | w2) & 0xFFFFu);
-                        ch |= A2 != root && !is_ecmp(A2);
+            // the cut tree is no deeper than the first-parent tree: the hop pass's round count suffices
+            for (uint32_t r = 0; r < jump_rounds; ++r) {
+                for (uint32_t v0 = tid; v0 < V; v0 += 4 * T) {
+                    uint32_t w[4], w2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const uint32_t v = v0 + k * T; w[k] = (v < V) ? word[v] : 0u; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t v = v0 + k * T;
+                        // OR-ing a terminal's own seeds again is harmless (every vertex ORs in its top's set below)
+                        if (v < V) word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] | w2[k]) & 0xFFFFu);
                     }
                 }
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 14] += 1;
-                if (!__syncthreads_or(ch)) break;
+                __syncthreads();
             }
-            // ECMP vertices: own segment | final set of own top | the same of every other parent
+            // ECMP vertices: from the self-pointing terminal form to (top, own segment) through the first parent
             if (n_e) {
+                for (uint32_t i = tid; i < n_e; i += T) {
+                    const uint32_t x = elist[i];
+                    const uint32_t seeds = word[x] & 0xFFFFu;
+                    const uint32_t f = __ldcg(&o_fp[x]);      // an ECMP vertex has parents
+                    uint32_t nw;
+                    if (hops0(f)) nw = (root << 16) | seeds;
+                    else if (is_ecmp(f)) nw = (f << 16) | seeds;
+                    else { const uint32_t wf = word[f]; nw = (wf & 0xFFFF0000u) | ((wf | seeds) & 0xFFFFu); }
+                    // (word[f] of a non-ECMP f is final and is not rewritten here)
+                    word[x] = nw;
+                }
+                __syncthreads();
+                // own segment | final set of own top | the same of every other parent
                 for (;;) {
                     int ch = 0;
                     for (uint32_t i = tid; i < n_e; i += T) {
@@ -570,7 +651,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                         auto pull_parent = [&](uint32_t u) {
                             const uint32_t wp = word[u], Tp = wp >> 16;
                             need |= wp;
-                            if (Tp != root) need |= word[Tp];
+                            if (Tp != root && Tp != u) need |= word[Tp];
                         };
                         if (cached) {
 #pragma unroll
@@ -588,7 +669,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             for (uint32_t v = tid; v < V; v += T) {
                 const uint32_t w = word[v], Tv = w >> 16;
                 uint32_t m = w;
-                if (Tv != root) m |= word[Tv];
+                if (Tv != root && Tv != v) m |= word[Tv];
                 const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
                 if (pass == 0) o_nh[v] = bits; else o_nh[v] |= bits;
             }
