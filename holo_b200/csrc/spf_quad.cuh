@@ -34,6 +34,7 @@
 namespace hspf {
 
 constexpr uint32_t kJsInvalid = 8u;   // HSPF_JS_INVALID
+constexpr uint32_t kJsInternal = 16u; // HSPF_JS_INTERNAL: a loop bound that cannot be reached was reached
 constexpr int kQMaxRoot = 64;         // non-HOP root neighbours tracked (>= 64 atoms is refused anyway)
 
 struct QuadDev {
@@ -300,7 +301,9 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             };
             const uint32_t ND = NBWp >> 1;     // bitmap rows as 64-bit words: two words per lane
             uint32_t cur = 0, empties = 0, p = 0;
-            for (;;) {
+            // defensive bound on the number of rounds (a hang would cost the caller its GPU)
+            for (uint32_t guard = 0;; ++guard) {
+                if (guard > NQ * 64u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }
                 uint2 *bm2 = reinterpret_cast<uint2 *>(ring + (cur & 3u) * NBWp);
                 long long t_sub = 0;
                 if (a.prof && tid == 0) t_sub = clock64();
@@ -522,13 +525,15 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t v = v0 + k * T;
                     // w2 is a terminal (points at itself, sum 0) or an ordinary vertex
-                    if (v < V) word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
-                    ch |= ((w2[k] ^ w[k]) >> 16) != 0;
+                    if (v < V) {
+                        word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
+                        ch |= ((w2[k] ^ w[k]) >> 16) != 0;
+                    }
                 }
             }
             if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
             if (!__syncthreads_or(ch)) break;
-            ++jump_rounds;
+            if (++jump_rounds > 32u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // depth < 2^32: cannot happen
         }
         for (uint32_t v = tid; v < V; v += T) {
             const uint32_t w = word[v];
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 }
                 __syncthreads();
                 // own segment | final set of own top | the same of every other parent
-                for (;;) {
+                for (uint32_t sweeps = 0;;) {
                     int ch = 0;
                     for (uint32_t i = tid; i < n_e; i += T) {
                         const uint32_t x = elist[i];
@@ -664,6 +669,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     }
                     if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 15] += 1;
                     if (!__syncthreads_or(ch)) break;
+                    if (++sweeps > 16u * n_e + 16u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // <= 16 bits per vertex
                 }
             }
             for (uint32_t v = tid; v < V; v += T) {

@@ -97,6 +97,9 @@ extern "C" {
                                        whose job arrays the host cannot see; host-pointer calls
                                        fail with HSPF_E_INVAL before anything runs            */
 
+#define HSPF_JS_INTERNAL       0x10u /* a device loop hit a bound that cannot be reached on a
+                                        valid graph (defensive; please report): planes undefined */
+
 /*
  * Flattened link-state graph of one area / level / topology.
  *
