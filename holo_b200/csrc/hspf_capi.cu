@@ -144,7 +144,11 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
     if (getenv("HSPF_NO_QUAD")) return 1;             // tuning knob (experiments only)
     uint32_t qcap = 2048;
     if (const char *qc = getenv("HSPF_QUAD_QCAP")) { int v = atoi(qc); if (v >= 64 && v <= 32768) qcap = (uint32_t)v; }
-    const QuadLayout lay = make_quad_layout(g->d.V, g->q.NQ, qcap);
+    int T = 512, cap = 0;
+    if (const char *t = getenv("HSPF_QUAD_T")) T = atoi(t);                 // tuning knobs (experiments only)
+    if (T != 128 && T != 256 && T != 384 && T != 512) T = 512;
+    if (const char *c = getenv("HSPF_CTAS_PER_SM")) cap = atoi(c);
+    const QuadLayout lay = make_quad_layout(g->d.V, g->q.NQ, qcap, (uint32_t)T);
     if ((size_t)lay.total + 2048 > ctx->smem_optin) return 1;
     QuadArgs a{};
     a.g = g->d; a.q = g->q; a.lay = lay;
@@ -153,9 +157,6 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
     a.out_dist = out->dist; a.out_hops = out->hops; a.out_fp = out->first_parent; a.out_npar = out->n_parents;
     a.out_nh = out->nh_mask; a.out_status = out->job_status;
     a.job_counter = ctx->d_counter;
-    int T = 384, cap = 0;
-    if (const char *t = getenv("HSPF_QUAD_T")) T = atoi(t);                 // tuning knobs (experiments only)
-    if (const char *c = getenv("HSPF_CTAS_PER_SM")) cap = atoi(c);
     const bool ov = jobs->ov_off != nullptr;
     switch (T) {
     case 128: return ov ? launch_quad<128, true>(ctx, a, lay.total, cap) : launch_quad<128, false>(ctx, a, lay.total, cap);

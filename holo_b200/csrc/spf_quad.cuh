@@ -50,7 +50,7 @@ struct QuadDev {
 };
 
 struct QuadLayout {   // byte offsets into dynamic shared memory
-    uint32_t dist, queue, ring, cont, fl_hop, h0, ecmp, elist, total;
+    uint32_t dist, queue, ring, cont, h0, ecmp, elist, total;
     uint32_t qcap;    // queue capacity (entries)
 };
 
@@ -73,19 +73,21 @@ struct QuadArgs {
     unsigned long long *prof;   // optional [gridDim][16] cycle counters
 };
 
-inline QuadLayout make_quad_layout(uint32_t V, uint32_t NQ, uint32_t qcap) {
+// `threads` = CTA size: the jump words are padded to a multiple of 4 * threads (unrolled rounds
+// without bounds checks).
+inline QuadLayout make_quad_layout(uint32_t V, uint32_t NQ, uint32_t qcap, uint32_t threads) {
     QuadLayout L{};
     auto al = [](size_t x) { return (uint32_t)((x + 15) / 16 * 16); };
     const uint32_t nbv = (V + 31) / 32, nbw = (NQ / 32 + 1u) & ~1u;   // bitmap rows: an even number of words
+    const uint32_t Vp = (V + 4 * threads - 1) / (4 * threads) * (4 * threads);
     uint32_t o = 0;
     L.dist = o; o += al((size_t)NQ * 4);
-    L.queue = o; o += al((size_t)qcap * 2);
-    // phase 3: jump words u32[V] over dist, ECMP vertex list u16[V] behind them
-    L.elist = al((size_t)V * 4);
+    L.queue = o; o += al((size_t)qcap * 4);
+    // phase 3: jump words u32[Vp] over dist, ECMP vertex list u16[V] behind them
+    L.elist = al((size_t)Vp * 4);
     if (L.elist + al((size_t)V * 2) > o) o = L.elist + al((size_t)V * 2);
-    L.ring = o; o += al((size_t)4 * nbw * 4);
+    L.ring = o; o += al((size_t)4 * nbw * 4);      // [word][bucket & 3]
     L.cont = o; o += al((size_t)nbw * 4);
-    L.fl_hop = o; o += al((size_t)nbv * 4);
     L.h0 = o; o += al((size_t)nbv * 4);
     L.ecmp = o; o += al((size_t)nbv * 4);
     L.total = o;
@@ -127,10 +129,9 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
     const uint32_t qcap = L.qcap;
 
     uint32_t *dist = reinterpret_cast<uint32_t *>(qsm + L.dist);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(qsm + L.queue);
-    uint32_t *ring = reinterpret_cast<uint32_t *>(qsm + L.ring);
+    uint32_t *queue = reinterpret_cast<uint32_t *>(qsm + L.queue);   // entries: quad | first quad of its chain << 16
+    uint32_t *ring = reinterpret_cast<uint32_t *>(qsm + L.ring);     // frontier bitmaps, word w of bucket b at [w * 4 + (b & 3)]
     uint32_t *cont_s = reinterpret_cast<uint32_t *>(qsm + L.cont);
-    uint32_t *fl_hop = reinterpret_cast<uint32_t *>(qsm + L.fl_hop);
     uint32_t *h0bm = reinterpret_cast<uint32_t *>(qsm + L.h0);
     uint32_t *ecmpbm = reinterpret_cast<uint32_t *>(qsm + L.ecmp);
     uint32_t *word = dist;                                   // phase 3
@@ -138,17 +139,14 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 
     long long t_mark = clock64();
 
-    // once per CTA: chain-continuation bits and the HOP flags as bitmaps
+    // once per CTA: chain-continuation bits
     for (uint32_t w = tid; w < NBWp; w += T) cont_s[w] = (w < NBW) ? Q.fcont[w] : 0u;
-    for (uint32_t w = tid; w < nbv; w += T) {
-        uint32_t h = 0;
-        for (uint32_t b = 0; b < 32; ++b) {
-            const uint32_t v = w * 32 + b;
-            if (v < V && (g.vflags[v] & kVfHop)) h |= 1u << b;
-        }
-        fl_hop[w] = h;
-    }
-    auto is_hop = [&](uint32_t v) -> bool { return (fl_hop[v >> 5] >> (v & 31)) & 1u; };
+    auto is_hop = [&](uint32_t v) -> bool { return (__ldg(&g.vflags[v]) & kVfHop) != 0; };
+    const uint32_t Vp = (V + 4 * T - 1) / (4 * T) * (4 * T);
+    // Unreached sentinel: a relaxed distance above reject_above must be rejected (IS-IS
+    // MAX_PATH_METRIC, holo-isis/src/spf.rs:636-645).  With every distance initialised to
+    // reject_above + 1 the improvement test nd < dist[head] does that by itself.
+    const uint32_t U = g.reject_above + 1u ? g.reject_above + 1u : kInf;
 
     for (;;) {
         // ---- fetch next job -------------------------------------------------------
@@ -174,7 +172,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         // ---- per-job init -----------------------------------------------------------
         {
             uint4 *d4 = reinterpret_cast<uint4 *>(dist);
-            const uint4 inf4 = make_uint4(kInf, kInf, kInf, kInf);
+            const uint4 inf4 = make_uint4(U, U, U, U);
             for (uint32_t i = tid; i < NQ / 4; i += T) d4[i] = inf4;
             for (uint32_t i = tid; i < 4 * NBWp; i += T) ring[i] = 0;
             for (uint32_t w = tid; w < nbv; w += T) { h0bm[w] = 0; ecmpbm[w] = 0; }
@@ -211,7 +209,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         const uint32_t rs = Q.slot_of[root];
         if (tid == 0) {
             dist[rs] = 0;
-            ring[rs >> 5] = 1u << (rs & 31);     // bucket 0
+            ring[(rs >> 5) << 2] = 1u << (rs & 31);     // bucket 0
         }
         __syncthreads();
         const uint32_t n_ov = kOv ? S.n_ov : 0u;
@@ -249,9 +247,8 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 
         // ======================= phase 1: SSSP in quad space ===========================
         const uint32_t sh = kOv ? S.sh : Q.shift;
-        const uint32_t rej = g.reject_above;
         {
-            // one quad: four branch-free relaxations (pad records never improve anything)
+            // one quad: four relaxations (pad records never improve anything)
             auto relax = [&](uint32_t q, uint32_t du, const uint4 &r4) {
                 uint32_t hs[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
                 uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
@@ -273,76 +270,64 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
-                    if (nd < dh[j] && nd <= rej) {
+                    if (nd < dh[j]) {      // also rejects nd > reject_above (see U)
                         // fire-and-forget: nothing below waits on an atomic's result
                         atomicMin(&dist[hs[j]], nd);
-                        atomicOr(&ring[((nd >> sh) & 3u) * NBWp + (hs[j] >> 5)], 1u << (hs[j] & 31));
+                        atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
                     }
                 }
             };
-            // queue the set bits of one bitmap word (ascending); a continuation quad gets its
-            // owner's distance (the previous quad's: chains are consecutive and ascending)
-            auto emit = [&](uint32_t bits, uint32_t C, uint32_t qbase, uint32_t &pos) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (bits) {
-                        const uint32_t bit = __ffs(bits) - 1, q = qbase + bit;
-                        queue[pos++] = (uint16_t)q;
-                        if ((C >> bit) & 1u) dist[q] = dist[q - 1];
-                        bits &= bits - 1;
-                    }
-                }
-                while (bits) {
-                    const uint32_t bit = __ffs(bits) - 1, q = qbase + bit;
-                    queue[pos++] = (uint16_t)q;
-                    if ((C >> bit) & 1u) dist[q] = dist[q - 1];
-                    bits &= bits - 1;
-                }
-            };
-            const uint32_t ND = NBWp >> 1;     // bitmap rows as 64-bit words: two words per lane
             uint32_t cur = 0, empties = 0, p = 0;
             // defensive bound on the number of rounds (a hang would cost the caller its GPU)
             for (uint32_t guard = 0;; ++guard) {
                 if (guard > NQ * 64u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }
-                uint2 *bm2 = reinterpret_cast<uint2 *>(ring + (cur & 3u) * NBWp);
+                uint32_t *bm = ring + (cur & 3u);
                 long long t_sub = 0;
                 if (a.prof && tid == 0) t_sub = clock64();
                 // ---- compact the current bucket's bitmap into the queue ------------------
-                for (uint32_t d0 = 0; d0 < ND; d0 += T) {
+                // A lane owns two bitmap words.  Emission is by rank: in pass r every lane that
+                // still has a bit queues its r-th one at base + (its rank among such lanes), so
+                // the passes are ballots and popcounts, no per-lane loop and no prefix scan.
+                for (uint32_t d0 = 0; d0 * 2 < NBWp; d0 += T) {
                     const uint32_t d = d0 + tid;
-                    uint2 bb = make_uint2(0u, 0u);
-                    if (d < ND) bb = bm2[d];
-                    if (!__any_sync(0xffffffffu, (bb.x | bb.y) != 0)) continue;
-                    uint32_t a0 = bb.x, a1 = bb.y, C0 = 0, C1 = 0;
-                    if (bb.x | bb.y) {
-                        const uint2 cc = reinterpret_cast<const uint2 *>(cont_s)[d];
-                        C0 = cc.x; C1 = cc.y;
+                    uint32_t a0 = 0, a1 = 0;
+                    if (d * 2 < NBWp) { a0 = bm[(d * 2) << 2]; a1 = bm[(d * 2 + 1) << 2]; }
+                    if (!__any_sync(0xffffffffu, (a0 | a1) != 0)) continue;
+                    const uint32_t b0 = a0, b1 = a1;
+                    uint32_t C0 = 0, C1 = 0;
+                    if (a0 | a1) {
+                        C0 = cont_s[d * 2]; C1 = cont_s[d * 2 + 1];
                         uint32_t m = a0;
                         while ((m = (m << 1) & C0) != 0) a0 |= m;    // the other quads of a multi-quad vertex
                         m = a1;
                         while ((m = (m << 1) & C1) != 0) a1 |= m;
                     }
-                    const uint32_t n = __popc(a0) + __popc(a1);
-                    uint32_t incl = n;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ((int)lane >= o) incl += t;
-                    }
-                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const uint32_t n = __reduce_add_sync(0xffffffffu, __popc(a0) + __popc(a1));
                     uint32_t base = 0;
-                    if (lane == 31) base = atomicAdd(&S.cnt[p], tot);
-                    base = __shfl_sync(0xffffffffu, base, 31);
-                    uint32_t pos = base + incl - n;
-                    if (n) {
-                        if (pos + n <= qcap) {
-                            bm2[d] = make_uint2(0u, 0u);
-                            emit(a0, C0, d * 64, pos);
-                            emit(a1, C1, d * 64 + 32, pos);
-                        } else {
-                            // queue full: these vertices stay in the bitmap for the next round
-                            for (uint32_t q = pos; q < qcap && q < pos + n; ++q) queue[q] = 0xFFFFu;
+                    if (lane == 0) base = atomicAdd(&S.cnt[p], n);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base + n > qcap) {
+                        // queue full: these vertices stay in the bitmap for the next round
+                        for (uint32_t i = base + lane; i < qcap; i += 32) queue[i] = 0xFFFFFFFFu;
+                        continue;
+                    }
+                    if (b0) bm[(d * 2) << 2] = 0;
+                    if (b1) bm[(d * 2 + 1) << 2] = 0;
+                    uint32_t first = 0;
+                    const uint32_t qb = d * 64;
+                    for (;;) {
+                        const bool has = (a0 | a1) != 0;
+                        const uint32_t mk = __ballot_sync(0xffffffffu, has);
+                        if (mk == 0) break;
+                        if (has) {
+                            uint32_t bit, q;
+                            bool isc;
+                            if (a0) { bit = __ffs(a0) - 1; a0 &= a0 - 1; q = qb + bit; isc = (C0 >> bit) & 1u; }
+                            else { bit = __ffs(a1) - 1; a1 &= a1 - 1; q = qb + 32 + bit; isc = (C1 >> bit) & 1u; }
+                            if (!isc) first = q;          // bits come in ascending order: a chain's first quad precedes it
+                            queue[base + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
                         }
+                        base += __popc(mk);
                     }
                 }
                 __syncthreads();
@@ -359,17 +344,17 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 // ---- expand: one quad per lane, two quads of a thread in flight -----------------
                 for (uint32_t i = tid; i < n_cur; i += 2 * T) {
                     const uint32_t i1 = i + T;
-                    const uint32_t q0 = queue[i];
-                    const uint32_t q1 = (i1 < n_cur) ? (uint32_t)queue[i1] : 0xFFFFu;
-                    const uint32_t du0 = (q0 != 0xFFFFu) ? dist[q0] : kInf;
-                    const uint32_t du1 = (q1 != 0xFFFFu) ? dist[q1] : kInf;
+                    const uint32_t e0 = queue[i];
+                    const uint32_t e1 = (i1 < n_cur) ? queue[i1] : 0xFFFFFFFFu;
+                    const uint32_t du0 = (e0 != 0xFFFFFFFFu) ? dist[e0 >> 16] : kInf;     // the chain owner's distance
+                    const uint32_t du1 = (e1 != 0xFFFFFFFFu) ? dist[e1 >> 16] : kInf;
                     // a mark is stale when the vertex was settled in an earlier bucket
                     const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
                     uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                    if (l0) r0 = __ldg(&Q.fq[q0]);
-                    if (l1) r1 = __ldg(&Q.fq[q1]);
-                    if (l0) relax(q0, du0, r0);
-                    if (l1) relax(q1, du1, r1);
+                    if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
+                    if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
+                    if (l0) relax(e0 & 0xFFFFu, du0, r0);
+                    if (l1) relax(e1 & 0xFFFFu, du1, r1);
                 }
                 if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();
@@ -382,7 +367,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         // hops-0 non-HOP heads of root edges (their out-edges carry first-hop atoms)
         if (tid < S.n_roottab) {
             const uint32_t h = S.rt_target[tid], c = S.rt_cost[tid];
-            if (c != kInf && dist[Q.slot_of[h]] == c) atomicOr(&h0bm[h >> 5], 1u << (h & 31));
+            if (c < U && dist[Q.slot_of[h]] == c) atomicOr(&h0bm[h >> 5], 1u << (h & 31));
         }
         __syncthreads();
         auto hops0 = [&](uint32_t u) -> bool { return u == root || ((h0bm[u >> 5] >> (u & 31)) & 1u); };
@@ -409,7 +394,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 const uint2 ec = g.edge[e];
                 const uint32_t c = kOv ? ov_cost_of(e, ec.y) : ec.y;
                 const uint32_t du = dist[Q.slot_of[u]], dh = dist[Q.slot_of[ec.x]];
-                if (du != kInf && dh != kInf && c != kInf && sat_add(du, c) == dh &&
+                if (du < U && dh < U && c != kInf && sat_add(du, c) == dh &&
                     !((g.flags & kGfNoHopTargetNoNh) && !is_hop(ec.x)))
                     seed_v = ec.x;
             }
@@ -444,7 +429,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du[j], cs[j]) : du[j] + cs[j];
-                    const bool ok = du[j] != kInf && nd == dv;
+                    const bool ok = du[j] < U && nd == dv;
                     const bool better = ok && (du[j] < bd || (du[j] == bd && su[j] < bs));
                     cnt += ok ? 1u : 0u;
                     bd = better ? du[j] : bd;
@@ -466,6 +451,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             auto emit_v = [&](const uint2 &m, uint32_t dv, uint32_t cnt, uint32_t bs) {
                 if (m.x != 0xFFFFFFFFu && ((m.y >> 8) & 0xFFu) == 0) {      // first quad of a real vertex
                     const uint32_t v = m.x >> 16;
+                    if (dv >= U) dv = kInf;                                   // unreached
                     if (v == root || dv == kInf) { cnt = 0; bs = kInf; }
                     if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
                     o_dist[v] = dv;
@@ -507,32 +493,29 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         // See spf_kernel.cuh phase 3J for the derivation; the first parents are read back
         // from the plane just written.
         // -- hops: sum of HOP flags over (root, v]; the root and unreached vertices are terminals
-        for (uint32_t v = tid; v < V; v += T) {
-            const uint32_t f = __ldcg(&o_fp[v]);
+        for (uint32_t v = tid; v < Vp; v += T) {      // (padding words are terminals: no bounds checks in the rounds)
+            const uint32_t f = (v < V) ? __ldcg(&o_fp[v]) : kInf;
             word[v] = (f == kInf) ? (v << 16) : ((f << 16) | (is_hop(v) ? 1u : 0u));
         }
         __syncthreads();
         uint32_t jump_rounds = 0;     // rounds in which some vertex still moved
         for (;;) {
-            int ch = 0;
-            for (uint32_t v0 = tid; v0 < V; v0 += 4 * T) {
+            uint32_t moved = 0;
+            for (uint32_t v0 = tid; v0 < Vp; v0 += 4 * T) {      // Vp % (4 * T) == 0
                 uint32_t w[4], w2[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { const uint32_t v = v0 + k * T; w[k] = (v < V) ? word[v] : 0u; }
+                for (int k = 0; k < 4; ++k) w[k] = word[v0 + k * T];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t v = v0 + k * T;
                     // w2 is a terminal (points at itself, sum 0) or an ordinary vertex
-                    if (v < V) {
-                        word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
-                        ch |= ((w2[k] ^ w[k]) >> 16) != 0;
-                    }
+                    word[v0 + k * T] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
+                    moved |= w2[k] ^ w[k];
                 }
             }
             if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
-            if (!__syncthreads_or(ch)) break;
+            if (!__syncthreads_or((moved >> 16) != 0)) break;
             if (++jump_rounds > 32u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // depth < 2^32: cannot happen
         }
         for (uint32_t v = tid; v < V; v += T) {
@@ -605,10 +588,12 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         }
         for (uint32_t pass = 0; pass * 16u < n_atoms || pass == 0; ++pass) {
             // terminals (the root, unreached vertices, ECMP vertices) point at themselves
-            for (uint32_t v = tid; v < V; v += T) {
-                const uint32_t f = __ldcg(&o_fp[v]);
-                uint32_t A = (f == kInf) ? v : (hops0(f) ? root : f);
-                if (is_ecmp(v)) A = v;
+            for (uint32_t v = tid; v < Vp; v += T) {
+                uint32_t A = v;
+                if (v < V) {
+                    const uint32_t f = __ldcg(&o_fp[v]);
+                    if (f != kInf && !is_ecmp(v)) A = hops0(f) ? root : f;
+                }
                 word[v] = A << 16;
             }
             __syncthreads();
@@ -616,18 +601,15 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             __syncthreads();
             // the cut tree is no deeper than the first-parent tree: the hop pass's round count suffices
             for (uint32_t r = 0; r < jump_rounds; ++r) {
-                for (uint32_t v0 = tid; v0 < V; v0 += 4 * T) {
+                for (uint32_t v0 = tid; v0 < Vp; v0 += 4 * T) {
                     uint32_t w[4], w2[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { const uint32_t v = v0 + k * T; w[k] = (v < V) ? word[v] : 0u; }
+                    for (int k = 0; k < 4; ++k) w[k] = word[v0 + k * T];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t v = v0 + k * T;
-                        // OR-ing a terminal's own seeds again is harmless (every vertex ORs in its top's set below)
-                        if (v < V) word[v] = (w2[k] & 0xFFFF0000u) | ((w[k] | w2[k]) & 0xFFFFu);
-                    }
+                    for (int k = 0; k < 4; ++k)   // OR-ing a terminal's own seeds again is harmless (every vertex ORs in its top's set below)
+                        word[v0 + k * T] = (w2[k] & 0xFFFF0000u) | ((w[k] | w2[k]) & 0xFFFFu);
                 }
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 14] += 1;
                 __syncthreads();
