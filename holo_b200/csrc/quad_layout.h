@@ -9,17 +9,17 @@
 //
 //  * forward quads (fq): records point at the SLOT of the head vertex = index of the
 //    head's first forward quad.  The tentative distances of the SSSP are indexed by
-//    slot (dist[NQ]); a chain's continuation quads carry a copy of their owner's
-//    distance, refreshed whenever the owner enters the frontier.
+//    slot (dist[NQ]; the entries of continuation quads are unused): a queue entry of the
+//    SSSP names a quad and the first quad of its chain, whose distance it relaxes from.
 //  * in-quads (iq): the transposed adjacency in the same form (records point at the
 //    slot of the source vertex); one thread per in-quad evaluates the ECMP-DAG
 //    predicate, partial results of a chain are combined with warp shuffles.
 //  * chains never straddle a 32-quad boundary (dummy quads pad the gap), so a chain
 //    lives in one word of the frontier bitmaps / one warp of the parents pass.
 //
-// A pad record of forward quad q is (q | 0xFFFF << 16): relaxing the quad's own slot
-// with cost 65535 can never improve it, so the relaxation body needs no validity
-// branch.  A pad record of an in-quad of vertex v is (slot(v) | 0xFFFF << 16):
+// A pad record of a forward quad of vertex v is (slot(v) | 0xFFFF << 16): relaxing the
+// owner's own slot with cost 65535 can never improve it, so the relaxation body needs no
+// validity branch (dummy quads pad with their own index and are never expanded).  A pad record of an in-quad of vertex v is (slot(v) | 0xFFFF << 16):
 // dist[v] + 65535 == dist[v] never holds, so it is never a DAG edge.
 //
 // Reference semantics are unchanged: vertex order (= slot order) is the VertexId order
@@ -85,6 +85,7 @@ inline QuadHost build_quads(uint32_t V, uint32_t E, const uint32_t *row, const u
         for (uint32_t j = 0; j < nq; ++j) {
             Q.vert_of[slot[v] + j] = (uint16_t)v;
             if (j) Q.fcont[(slot[v] + j) >> 5] |= 1u << ((slot[v] + j) & 31);
+            for (int k = 0; k < 4; ++k) Q.fq[(size_t)(slot[v] + j) * 4 + k] = slot[v] | 0xFFFF0000u;   // pad: owner's slot
         }
         for (uint32_t i = 0; i < deg; ++i) {
             const uint32_t e = row[v] + i;

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         const uint32_t sh = kOv ? S.sh : Q.shift;
         {
             // one quad: four relaxations (pad records never improve anything)
-            auto relax = [&](uint32_t q, uint32_t du, const uint4 &r4) {
+            auto relax = [&](uint32_t q, uint32_t first, uint32_t du, const uint4 &r4) {
                 uint32_t hs[4] = {r4.x & 0xFFFFu, r4.y & 0xFFFFu, r4.z & 0xFFFFu, r4.w & 0xFFFFu};
                 uint32_t cs[4] = {r4.x >> 16, r4.y >> 16, r4.z >> 16, r4.w >> 16};
                 if (kOv) {
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if ((fp_ & 3u) == (uint32_t)j) {
-                                if (c == kInf) { hs[j] = q; cs[j] = 0xFFFFu; } else cs[j] = c;
+                                if (c == kInf) { hs[j] = first; cs[j] = 0xFFFFu; } else cs[j] = c;
                             }
                     }
                 }
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
                     if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
                     if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
-                    if (l0) relax(e0 & 0xFFFFu, du0, r0);
-                    if (l1) relax(e1 & 0xFFFFu, du1, r1);
+                    if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
+                    if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
                 }
                 if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
                 __syncthreads();

@@ -44,12 +44,13 @@ def sssp(q, root: int, reject_above: int = 0xFFFFFFFE, qcap: int = 1 << 30):
             if pos > qcap:
                 continue                      # stays in the bitmap for the next round
             bm[w] = 0
+            first = None
             for bit in range(32):
                 if (allb >> bit) & 1:
                     qq = w * 32 + bit
-                    queue.append(qq)
-                    if (C >> bit) & 1:
-                        dist[qq] = dist[qq - 1]
+                    if not (C >> bit) & 1:
+                        first = qq
+                    queue.append((qq, first))
         if not queue:
             empties += 1
             if empties == 4:
@@ -58,8 +59,8 @@ def sssp(q, root: int, reject_above: int = 0xFFFFFFFE, qcap: int = 1 << 30):
             continue
         empties = 0
         rounds += 1
-        for qq in queue:
-            du = int(dist[qq])
+        for qq, first in queue:
+            du = int(dist[first])
             if du == INF or (du >> sh) != cur:
                 continue
             for r in q.fq[qq]:
@@ -144,7 +145,7 @@ def check_image(q, csr):
             assert recs[i] == (int(slot[col[e]]) | (int(cost[e]) << 16)), (v, i)
             assert q.fpos[e] == s * 4 + i
         for i in range(deg, nq * 4):
-            assert recs[i] == ((s + i // 4) | 0xFFFF0000)           # pad: own quad, cost 65535
+            assert recs[i] == (s | 0xFFFF0000)                      # pad: owner's slot, cost 65535
     # every forward edge appears exactly once among the in-quad records, at ipos
     seen = 0
     for e in range(E):
