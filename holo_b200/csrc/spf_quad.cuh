@@ -271,95 +271,116 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
                     if (nd < dh[j]) {      // also rejects nd > reject_above (see U)
-                        // fire-and-forget: nothing below waits on an atomic's result
-                        atomicMin(&dist[hs[j]], nd);
-                        atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
+                        // The mark must not become visible before the distance (another warp may claim
+                        // it at once): it takes the atomic's result as an operand.  A mark is only needed
+                        // when this relaxation was the improvement.
+                        const uint32_t old = atomicMin(&dist[hs[j]], nd);
+                        if (old > nd) atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
                     }
                 }
             };
-            uint32_t cur = 0, empties = 0, p = 0;
-            // defensive bound on the number of rounds (a hang would cost the caller its GPU)
+            // Buckets are processed in order; INSIDE a bucket the warps run asynchronously (label
+            // correcting needs no order): a warp claims a chunk of 32 words of the bucket's bitmap
+            // (atomicExch: marks made meanwhile by other warps are either taken now or stay for a
+            // later visit), queues the quads in its private staging area and expands them, then
+            // moves to the next chunk.  A warp is idle after a full sweep over all chunks that
+            // found nothing; the bucket is finished when every warp is idle at the same time (any
+            // mark was made by a warp that afterwards either saw it or saw it claimed by a warp
+            // that is not idle).  No CTA barrier inside a bucket.
+            constexpr uint32_t kWarps_ = T / 32;
+            const uint32_t warp = tid >> 5;
+            const uint32_t nchunks = (NBWp + 31) >> 5;
+            const uint32_t scap = qcap / kWarps_;                 // staging entries per warp (>= 64)
+            uint32_t *stg = queue + warp * scap;
+            volatile uint32_t *v_idle = &S.cnt[0];
+            uint32_t cur = 0, empties = 0;
             for (uint32_t guard = 0;; ++guard) {
-                if (guard > NQ * 64u) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }
+                if (guard > (1u << 24)) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
                 uint32_t *bm = ring + (cur & 3u);
-                long long t_sub = 0;
-                if (a.prof && tid == 0) t_sub = clock64();
-                // ---- compact the current bucket's bitmap into the queue ------------------
-                // A lane owns two bitmap words.  Emission is by rank: in pass r every lane that
-                // still has a bit queues its r-th one at base + (its rank among such lanes), so
-                // the passes are ballots and popcounts, no per-lane loop and no prefix scan.
-                for (uint32_t d0 = 0; d0 * 2 < NBWp; d0 += T) {
-                    const uint32_t d = d0 + tid;
-                    uint32_t a0 = 0, a1 = 0;
-                    if (d * 2 < NBWp) { a0 = bm[(d * 2) << 2]; a1 = bm[(d * 2 + 1) << 2]; }
-                    if (!__any_sync(0xffffffffu, (a0 | a1) != 0)) continue;
-                    const uint32_t b0 = a0, b1 = a1;
-                    uint32_t C0 = 0, C1 = 0;
-                    if (a0 | a1) {
-                        C0 = cont_s[d * 2]; C1 = cont_s[d * 2 + 1];
-                        uint32_t m = a0;
-                        while ((m = (m << 1) & C0) != 0) a0 |= m;    // the other quads of a multi-quad vertex
-                        m = a1;
-                        while ((m = (m << 1) & C1) != 0) a1 |= m;
-                    }
-                    const uint32_t n = __reduce_add_sync(0xffffffffu, __popc(a0) + __popc(a1));
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&S.cnt[p], n);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base + n > qcap) {
-                        // queue full: these vertices stay in the bitmap for the next round
-                        for (uint32_t i = base + lane; i < qcap; i += 32) queue[i] = 0xFFFFFFFFu;
-                        continue;
-                    }
-                    if (b0) bm[(d * 2) << 2] = 0;
-                    if (b1) bm[(d * 2 + 1) << 2] = 0;
-                    uint32_t first = 0;
-                    const uint32_t qb = d * 64;
-                    for (;;) {
-                        const bool has = (a0 | a1) != 0;
-                        const uint32_t mk = __ballot_sync(0xffffffffu, has);
-                        if (mk == 0) break;
-                        if (has) {
-                            uint32_t bit, q;
-                            bool isc;
-                            if (a0) { bit = __ffs(a0) - 1; a0 &= a0 - 1; q = qb + bit; isc = (C0 >> bit) & 1u; }
-                            else { bit = __ffs(a1) - 1; a1 &= a1 - 1; q = qb + 32 + bit; isc = (C1 >> bit) & 1u; }
-                            if (!isc) first = q;          // bits come in ascending order: a chain's first quad precedes it
-                            queue[base + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
+                uint32_t clean = 0, c = warp % nchunks, spins = 0;
+                bool idle = false, worked = false;
+                for (;;) {
+                    const uint32_t w = c * 32 + lane;
+                    uint32_t bits = (w < NBWp) ? *reinterpret_cast<volatile uint32_t *>(&bm[w << 2]) : 0u;
+                    if (__any_sync(0xffffffffu, bits != 0)) {
+                        if (idle) {                                  // leave the idle set BEFORE claiming
+                            idle = false;
+                            if (lane == 0) atomicSub(&S.cnt[0], 1u);
                         }
-                        base += __popc(mk);
+                        uint32_t C = 0;
+                        if (bits) {
+                            bits = atomicExch(&bm[w << 2], 0u);
+                            C = cont_s[w];
+                            uint32_t m = bits;
+                            while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
+                        }
+                        uint32_t first = 0;
+                        const uint32_t qb = w * 32;
+                        // emission by rank: in a pass every lane that still has a bit queues one, at
+                        // (its rank among such lanes): ballots and popcounts, no per-lane loop
+                        while (__any_sync(0xffffffffu, bits != 0)) {
+                            uint32_t n = 0;
+                            for (;;) {
+                                const bool has = bits != 0;
+                                const uint32_t mk = __ballot_sync(0xffffffffu, has);
+                                const uint32_t k = __popc(mk);
+                                if (k == 0 || n + k > scap) break;
+                                if (has) {
+                                    const uint32_t bit = __ffs(bits) - 1, q = qb + bit;
+                                    bits &= bits - 1;
+                                    if (!((C >> bit) & 1u)) first = q;   // ascending bits: a chain's first quad precedes it
+                                    stg[n + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
+                                }
+                                n += k;
+                            }
+                            __syncwarp();
+                            if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
+                            // ---- expand: one quad per lane, two quads of a lane in flight ------------
+                            for (uint32_t i = lane; i < n; i += 64) {
+                                const uint32_t i1 = i + 32;
+                                const uint32_t e0 = stg[i];
+                                const uint32_t e1 = (i1 < n) ? stg[i1] : 0xFFFFFFFFu;
+                                const uint32_t du0 = dist[e0 >> 16];     // the chain owner's distance
+                                const uint32_t du1 = (i1 < n) ? dist[e1 >> 16] : kInf;
+                                // a mark is stale when the vertex was settled in an earlier bucket
+                                const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
+                                uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                                if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
+                                if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
+                                if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
+                                if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
+                            }
+                            __syncwarp();
+                        }
+                        clean = 0;
+                        worked = true;
+                    } else {
+                        ++clean;
+                    }
+                    c = (c + 1 == nchunks) ? 0u : c + 1;
+                    if (clean >= nchunks) {                            // a full sweep found nothing
+                        if (!idle) {
+                            idle = true;
+                            if (lane == 0) atomicAdd(&S.cnt[0], 1u);
+                        }
+                        uint32_t ni = 0;
+                        if (lane == 0) ni = *v_idle;
+                        ni = __shfl_sync(0xffffffffu, ni, 0);
+                        if (ni == kWarps_) break;
+                        if (++spins > (1u << 22)) { if (lane == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
+                        __nanosleep(64);
                     }
                 }
+                if (worked && lane == 0) S.cnt[1] = 1;
                 __syncthreads();
-                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 8] += n_ - t_sub; t_sub = n_; }
-                const uint32_t n_cur = min(S.cnt[p], qcap);
-                if (n_cur == 0) {
-                    if (++empties == 4) break;
-                    ++cur;
-                    __syncthreads();     // every thread has read S.cnt[p] == 0; the counter is reused as is
-                    continue;
-                }
-                empties = 0;
-                if (tid == 0) { S.cnt[p ^ 1] = 0; if (a.prof) { a.prof[(size_t)blockIdx.x * 16 + 7] += 1; a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; } }
-                // ---- expand: one quad per lane, two quads of a thread in flight -----------------
-                for (uint32_t i = tid; i < n_cur; i += 2 * T) {
-                    const uint32_t i1 = i + T;
-                    const uint32_t e0 = queue[i];
-                    const uint32_t e1 = (i1 < n_cur) ? queue[i1] : 0xFFFFFFFFu;
-                    const uint32_t du0 = (e0 != 0xFFFFFFFFu) ? dist[e0 >> 16] : kInf;     // the chain owner's distance
-                    const uint32_t du1 = (e1 != 0xFFFFFFFFu) ? dist[e1 >> 16] : kInf;
-                    // a mark is stale when the vertex was settled in an earlier bucket
-                    const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
-                    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                    if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
-                    if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
-                    if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
-                    if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
-                }
-                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 9] += n_ - t_sub; t_sub = n_; }
+                const uint32_t any_work = S.cnt[1];
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;
                 __syncthreads();
-                if (a.prof && tid == 0) { const long long n_ = clock64(); a.prof[(size_t)blockIdx.x * 16 + 10] += n_ - t_sub; }
-                p ^= 1;
+                if (tid == 0) { S.cnt[0] = 0; S.cnt[1] = 0; }
+                __syncthreads();
+                if (any_work) empties = 0;
+                else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
+                ++cur;
             }
         }
         HSPF_QMARK(1);   // SSSP
