@@ -97,6 +97,7 @@ inline QuadLayout make_quad_layout(uint32_t V, uint32_t NQ, uint32_t qcap, uint3
 
 struct QSmall {
     uint32_t cnt[2];
+    uint32_t wake;        // epoch: bumped by a working warp that sees plenty of work while others sleep
     uint32_t status;
     uint32_t job;
     uint32_t n_ov, sh;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             S.status = 0;
             S.cnt[0] = 0;
             S.cnt[1] = 0;
+            S.wake = 0;
             S.n_ov = n_ov_raw;
             S.sh = Q.shift;
         }
@@ -286,27 +288,44 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             // moves to the next chunk.  A warp is idle after a full sweep over all chunks that
             // found nothing; the bucket is finished when every warp is idle at the same time (any
             // mark was made by a warp that afterwards either saw it or saw it claimed by a warp
-            // that is not idle).  No CTA barrier inside a bucket.
+            // that is not idle).  An idle warp does not sweep: it sleeps and polls the idle count,
+            // and goes back to work when a busy warp that staged a large batch bumps S.wake (the
+            // small frontiers at the start and the end of a bucket are left to the warps that
+            // found them, so the other CTAs of the SM get the issue slots).  No CTA barrier
+            // inside a bucket.
             constexpr uint32_t kWarps_ = T / 32;
             const uint32_t warp = tid >> 5;
             const uint32_t nchunks = (NBWp + 31) >> 5;
             const uint32_t scap = qcap / kWarps_;                 // staging entries per warp (>= 64)
             uint32_t *stg = queue + warp * scap;
             volatile uint32_t *v_idle = &S.cnt[0];
+            volatile uint32_t *v_wake = &S.wake;
             uint32_t cur = 0, empties = 0;
             for (uint32_t guard = 0;; ++guard) {
                 if (guard > (1u << 24)) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
                 uint32_t *bm = ring + (cur & 3u);
-                uint32_t clean = 0, c = warp % nchunks, spins = 0;
+                uint32_t clean = 0, c = warp % nchunks, spins = 0, seen = 0;
                 bool idle = false, worked = false;
                 for (;;) {
+                    if (idle) {
+                        uint32_t ni = 0, wk = 0;
+                        if (lane == 0) { ni = *v_idle; wk = *v_wake; }
+                        ni = __shfl_sync(0xffffffffu, ni, 0);
+                        wk = __shfl_sync(0xffffffffu, wk, 0);
+                        if (ni == kWarps_) break;
+                        if (wk != seen) {                              // plenty of work somewhere: sweep again
+                            idle = false;
+                            clean = 0;
+                            if (lane == 0) atomicSub(&S.cnt[0], 1u);
+                            continue;
+                        }
+                        if (++spins > (1u << 22)) { if (lane == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
+                        __nanosleep(200);
+                        continue;
+                    }
                     const uint32_t w = c * 32 + lane;
                     uint32_t bits = (w < NBWp) ? *reinterpret_cast<volatile uint32_t *>(&bm[w << 2]) : 0u;
                     if (__any_sync(0xffffffffu, bits != 0)) {
-                        if (idle) {                                  // leave the idle set BEFORE claiming
-                            idle = false;
-                            if (lane == 0) atomicSub(&S.cnt[0], 1u);
-                        }
                         uint32_t C = 0;
                         if (bits) {
                             bits = atomicExch(&bm[w << 2], 0u);
@@ -334,6 +353,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                                 n += k;
                             }
                             __syncwarp();
+                            if (n >= 48 && lane == 0 && *v_idle != 0) atomicAdd(&S.wake, 1u);   // work for the sleepers
                             if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
                             // ---- expand: one quad per lane, two quads of a lane in flight ------------
                             for (uint32_t i = lane; i < n; i += 64) {
@@ -358,17 +378,11 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                         ++clean;
                     }
                     c = (c + 1 == nchunks) ? 0u : c + 1;
-                    if (clean >= nchunks) {                            // a full sweep found nothing
-                        if (!idle) {
-                            idle = true;
-                            if (lane == 0) atomicAdd(&S.cnt[0], 1u);
-                        }
-                        uint32_t ni = 0;
-                        if (lane == 0) ni = *v_idle;
-                        ni = __shfl_sync(0xffffffffu, ni, 0);
-                        if (ni == kWarps_) break;
-                        if (++spins > (1u << 22)) { if (lane == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
-                        __nanosleep(64);
+                    if (clean >= nchunks) {                            // a full sweep found nothing: idle
+                        idle = true;
+                        uint32_t wk = 0;
+                        if (lane == 0) { wk = *v_wake; atomicAdd(&S.cnt[0], 1u); }
+                        seen = __shfl_sync(0xffffffffu, wk, 0);
                     }
                 }
                 if (worked && lane == 0) S.cnt[1] = 1;
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 const uint32_t any_work = S.cnt[1];
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;
                 __syncthreads();
-                if (tid == 0) { S.cnt[0] = 0; S.cnt[1] = 0; }
+                if (tid == 0) { S.cnt[0] = 0; S.cnt[1] = 0; }      // (S.wake keeps counting)
                 __syncthreads();
                 if (any_work) empties = 0;
                 else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
