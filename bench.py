@@ -538,9 +538,11 @@ def main():
                          "(p2p; falls back to nccl if peer memory cannot be mapped), one NCCL all-gather per "
                          "step (nccl), or auto = p2p up to 4 GPUs, nccl above")
     ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
+    ap.add_argument("--jobs", type=int, default=JOBS_PER_GPU, help="SPF roots per GPU per step (tuning; BASELINE: 1000)")
     args = ap.parse_args()
-    global DELTA
+    global DELTA, JOBS_PER_GPU
     DELTA = args.delta
+    JOBS_PER_GPU = args.jobs
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

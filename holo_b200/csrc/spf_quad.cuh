@@ -281,119 +281,81 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     }
                 }
             };
-            // Buckets are processed in order; INSIDE a bucket the warps run asynchronously (label
-            // correcting needs no order): a warp claims a chunk of 32 words of the bucket's bitmap
-            // (atomicExch: marks made meanwhile by other warps are either taken now or stay for a
-            // later visit), queues the quads in its private staging area and expands them, then
-            // moves to the next chunk.  A warp is idle after a full sweep over all chunks that
-            // found nothing; the bucket is finished when every warp is idle at the same time (any
-            // mark was made by a warp that afterwards either saw it or saw it claimed by a warp
-            // that is not idle).  An idle warp does not sweep: it sleeps and polls the idle count,
-            // and goes back to work when a busy warp that staged a large batch bumps S.wake (the
-            // small frontiers at the start and the end of a bucket are left to the warps that
-            // found them, so the other CTAs of the SM get the issue slots).  No CTA barrier
-            // inside a bucket.
+            // Buckets are processed in order; a bucket takes rounds.  In a round every warp claims
+            // its own chunks of the bucket's bitmap (atomicExch: a mark made meanwhile by another
+            // warp is either taken now or stays for the next round), queues the quads in its private
+            // staging area by rank (ballots and popcounts, no per-lane loop, no CTA-wide scan) and
+            // expands them.  One CTA barrier per round; the bucket is finished by a round that
+            // claimed nothing.
             constexpr uint32_t kWarps_ = T / 32;
             const uint32_t warp = tid >> 5;
-            const uint32_t nchunks = (NBWp + 31) >> 5;
+            // chunk = the bitmap words of one claim (one per lane): sized so that every warp owns one
+            const uint32_t cw = min(32u, (NBWp + kWarps_ - 1) / kWarps_);
+            const uint32_t nchunks = (NBWp + cw - 1) / cw;
             const uint32_t scap = qcap / kWarps_;                 // staging entries per warp (>= 64)
             uint32_t *stg = queue + warp * scap;
-            volatile uint32_t *v_idle = &S.cnt[0];
-            volatile uint32_t *v_wake = &S.wake;
             uint32_t cur = 0, empties = 0;
+            bool bucket_work = false;
             for (uint32_t guard = 0;; ++guard) {
                 if (guard > (1u << 24)) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
                 uint32_t *bm = ring + (cur & 3u);
-                uint32_t clean = 0, c = warp % nchunks, spins = 0, seen = 0;
-                bool idle = false, worked = false;
-                for (;;) {
-                    if (idle) {
-                        uint32_t ni = 0, wk = 0;
-                        if (lane == 0) { ni = *v_idle; wk = *v_wake; }
-                        ni = __shfl_sync(0xffffffffu, ni, 0);
-                        wk = __shfl_sync(0xffffffffu, wk, 0);
-                        if (ni == kWarps_) break;
-                        if (wk != seen) {                              // plenty of work somewhere: sweep again
-                            idle = false;
-                            clean = 0;
-                            if (lane == 0) atomicSub(&S.cnt[0], 1u);
-                            continue;
-                        }
-                        if (++spins > (1u << 22)) { if (lane == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
-                        __nanosleep(200);
-                        continue;
+                int claimed = 0;
+                for (uint32_t c = warp; c < nchunks; c += kWarps_) {
+                    const uint32_t w = c * cw + lane;
+                    uint32_t bits = (lane < cw && w < NBWp) ? bm[w << 2] : 0u;
+                    if (!__any_sync(0xffffffffu, bits != 0)) continue;
+                    claimed = 1;
+                    uint32_t C = 0;
+                    if (bits) {
+                        bits = atomicExch(&bm[w << 2], 0u);
+                        C = cont_s[w];
+                        uint32_t m = bits;
+                        while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
                     }
-                    const uint32_t w = c * 32 + lane;
-                    uint32_t bits = (w < NBWp) ? *reinterpret_cast<volatile uint32_t *>(&bm[w << 2]) : 0u;
-                    if (__any_sync(0xffffffffu, bits != 0)) {
-                        uint32_t C = 0;
-                        if (bits) {
-                            bits = atomicExch(&bm[w << 2], 0u);
-                            C = cont_s[w];
-                            uint32_t m = bits;
-                            while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
-                        }
-                        uint32_t first = 0;
-                        const uint32_t qb = w * 32;
+                    uint32_t first = 0;
+                    const uint32_t qb = w * 32;
+                    while (__any_sync(0xffffffffu, bits != 0)) {
                         // emission by rank: in a pass every lane that still has a bit queues one, at
-                        // (its rank among such lanes): ballots and popcounts, no per-lane loop
-                        while (__any_sync(0xffffffffu, bits != 0)) {
-                            uint32_t n = 0;
-                            for (;;) {
-                                const bool has = bits != 0;
-                                const uint32_t mk = __ballot_sync(0xffffffffu, has);
-                                const uint32_t k = __popc(mk);
-                                if (k == 0 || n + k > scap) break;
-                                if (has) {
-                                    const uint32_t bit = __ffs(bits) - 1, q = qb + bit;
-                                    bits &= bits - 1;
-                                    if (!((C >> bit) & 1u)) first = q;   // ascending bits: a chain's first quad precedes it
-                                    stg[n + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
-                                }
-                                n += k;
+                        // (its rank among such lanes)
+                        uint32_t n = 0;
+                        for (;;) {
+                            const bool has = bits != 0;
+                            const uint32_t mk = __ballot_sync(0xffffffffu, has);
+                            const uint32_t k = __popc(mk);
+                            if (k == 0 || n + k > scap) break;
+                            if (has) {
+                                const uint32_t bit = __ffs(bits) - 1, q = qb + bit;
+                                bits &= bits - 1;
+                                if (!((C >> bit) & 1u)) first = q;   // ascending bits: a chain's first quad precedes it
+                                stg[n + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
                             }
-                            __syncwarp();
-                            if (n >= 48 && lane == 0 && *v_idle != 0) atomicAdd(&S.wake, 1u);   // work for the sleepers
-                            if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
-                            // ---- expand: one quad per lane, two quads of a lane in flight ------------
-                            for (uint32_t i = lane; i < n; i += 64) {
-                                const uint32_t i1 = i + 32;
-                                const uint32_t e0 = stg[i];
-                                const uint32_t e1 = (i1 < n) ? stg[i1] : 0xFFFFFFFFu;
-                                const uint32_t du0 = dist[e0 >> 16];     // the chain owner's distance
-                                const uint32_t du1 = (i1 < n) ? dist[e1 >> 16] : kInf;
-                                // a mark is stale when the vertex was settled in an earlier bucket
-                                const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
-                                uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                                if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
-                                if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
-                                if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
-                                if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
-                            }
-                            __syncwarp();
+                            n += k;
                         }
-                        clean = 0;
-                        worked = true;
-                    } else {
-                        ++clean;
-                    }
-                    c = (c + 1 == nchunks) ? 0u : c + 1;
-                    if (clean >= nchunks) {                            // a full sweep found nothing: idle
-                        idle = true;
-                        uint32_t wk = 0;
-                        if (lane == 0) { wk = *v_wake; atomicAdd(&S.cnt[0], 1u); }
-                        seen = __shfl_sync(0xffffffffu, wk, 0);
+                        __syncwarp();
+                        if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
+                        // ---- expand: one quad per lane, two quads of a lane in flight ------------
+                        for (uint32_t i = lane; i < n; i += 64) {
+                            const uint32_t i1 = i + 32;
+                            const uint32_t e0 = stg[i];
+                            const uint32_t e1 = (i1 < n) ? stg[i1] : 0xFFFFFFFFu;
+                            const uint32_t du0 = dist[e0 >> 16];     // the chain owner's distance
+                            const uint32_t du1 = (i1 < n) ? dist[e1 >> 16] : kInf;
+                            // a mark is stale when the vertex was settled in an earlier bucket
+                            const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
+                            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                            if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
+                            if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
+                            if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
+                            if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
+                        }
+                        __syncwarp();
                     }
                 }
-                if (worked && lane == 0) S.cnt[1] = 1;
-                __syncthreads();
-                const uint32_t any_work = S.cnt[1];
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;
-                __syncthreads();
-                if (tid == 0) { S.cnt[0] = 0; S.cnt[1] = 0; }      // (S.wake keeps counting)
-                __syncthreads();
-                if (any_work) empties = 0;
+                if (__syncthreads_or(claimed)) { bucket_work = true; continue; }      // another round of this bucket
+                if (bucket_work) empties = 0;
                 else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
+                bucket_work = false;
                 ++cur;
             }
         }

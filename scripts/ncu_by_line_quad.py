@@ -51,17 +51,17 @@ def find(t):
     return [i + 1 for i, l in enumerate(src) if t in l][0]
 
 
-marks = [("prolog / job fetch / init", "spf_quad_kernel(const QuadArgs"),
+marks = [("prolog / job fetch / init", "spf_quad_kernel(const QuadArgs a)"),
          ("sssp: relax (lambda)", "auto relax = "),
-         ("sssp: emit (lambda)", "auto emit = "),
-         ("sssp: compaction", "compact the current bucket"),
-         ("sssp: round control", "const uint32_t n_cur = min"),
-         ("sssp: expansion loop", "expand: one quad per lane"),
+         ("sssp: bucket loop, chunk claim, emission", "constexpr uint32_t kWarps_"),
+         ("sssp: expansion loop", "expand: one quad per lane, two quads of a lane in flight"),
+         ("sssp: idle / bucket end", "clean = 0;\n"),
          ("h0 / seeds", "hops-0 non-HOP heads of root edges"),
          ("parents", "= phase 2: ECMP parents"),
          ("jump: hops", "= phase 3: pointer jumping ="),
          ("jump: next hops", "// -- next hops."),
          ]
+marks = [m for m in marks if any(m[1] in l for l in src)]
 pos = sorted([(n, find(t)) for n, t in marks], key=lambda x: x[1]) + [("end", len(src) + 1)]
 print("---- by phase")
 for (name, a), (_, b) in zip(pos, pos[1:]):

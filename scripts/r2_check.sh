@@ -16,6 +16,9 @@ done
 for D in ${DELTAS:-128 512}; do
   HSPF_QUAD_T=${TBEST:-512} step "bench T=${TBEST:-512} delta=$D" 120 python scripts/bench_brief.py --steps 10 --warmup 3 --no-cpu-baseline --delta $D
 done
+for J in ${JOBSWEEP:-}; do
+  HSPF_QUAD_T=${TBEST:-512} step "bench T=${TBEST:-512} jobs=$J" 120 python scripts/bench_brief.py --steps 10 --warmup 3 --no-cpu-baseline --jobs $J
+done
 for T in ${TS:-384 512}; do HSPF_QUAD_T=$T step "phase profile T=$T" 100 python scripts/quad_profile.py; done
 if [ -n "$NCU" ]; then
   HSPF_QUAD_T=${TBEST:-512} step ncu 400 ncu --set full --clock-control none --import-source on -k regex:spf_quad_kernel -s 3 -c 1 \
