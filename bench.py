@@ -525,6 +525,7 @@ def run_ours(args):
 
 
 def main():
+    global DELTA, JOBS_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -540,7 +541,6 @@ def main():
     ap.add_argument("--delta", type=int, default=0, help="near/far bucket width (tuning; 0 = library default)")
     ap.add_argument("--jobs", type=int, default=JOBS_PER_GPU, help="SPF roots per GPU per step (tuning; BASELINE: 1000)")
     args = ap.parse_args()
-    global DELTA, JOBS_PER_GPU
     DELTA = args.delta
     JOBS_PER_GPU = args.jobs
     if args.warmup < 3 and args.impl == "ours":
