@@ -273,90 +273,117 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
                     if (nd < dh[j]) {      // also rejects nd > reject_above (see U)
-                        // The mark must not become visible before the distance (another warp may claim
-                        // it at once): it takes the atomic's result as an operand.  A mark is only needed
-                        // when this relaxation was the improvement.
-                        const uint32_t old = atomicMin(&dist[hs[j]], nd);
-                        if (old > nd) atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
+                        // fire-and-forget: nothing below waits on an atomic's result (the round's
+                        // barrier orders distances and marks for the next collect)
+                        atomicMin(&dist[hs[j]], nd);
+                        atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
                     }
                 }
             };
-            // Buckets are processed in order; a bucket takes rounds.  In a round every warp claims
-            // its own chunks of the bucket's bitmap (atomicExch: a mark made meanwhile by another
-            // warp is either taken now or stays for the next round), queues the quads in its private
-            // staging area by rank (ballots and popcounts, no per-lane loop, no CTA-wide scan) and
-            // expands them.  One CTA barrier per round; the bucket is finished by a round that
-            // claimed nothing.
+            // Buckets are processed in order; a bucket takes rounds of (collect, barrier, expand,
+            // barrier).  Collect: every warp claims its own chunk of the bucket's bitmap (one word
+            // per lane), a warp scan of the popcounts gives every quad of the chunk an output index,
+            // and output lane t finds its quad by itself — owner word by binary search over the
+            // scanned counts (shuffles), then the k-th set bit of that word — so all 32 lanes emit
+            // in every pass, whatever the distribution of bits over the words.  The quads go to a
+            // CTA-wide queue (one atomicAdd per warp), so the expansion runs with full warps.
             constexpr uint32_t kWarps_ = T / 32;
             const uint32_t warp = tid >> 5;
             // chunk = the bitmap words of one claim (one per lane): sized so that every warp owns one
             const uint32_t cw = min(32u, (NBWp + kWarps_ - 1) / kWarps_);
             const uint32_t nchunks = (NBWp + cw - 1) / cw;
-            const uint32_t scap = qcap / kWarps_;                 // staging entries per warp (>= 64)
-            uint32_t *stg = queue + warp * scap;
-            uint32_t cur = 0, empties = 0;
+            uint32_t cur = 0, empties = 0, p = 0;
             bool bucket_work = false;
             for (uint32_t guard = 0;; ++guard) {
                 if (guard > (1u << 24)) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
                 uint32_t *bm = ring + (cur & 3u);
-                int claimed = 0;
+                // ---- collect ----------------------------------------------------------------
                 for (uint32_t c = warp; c < nchunks; c += kWarps_) {
                     const uint32_t w = c * cw + lane;
-                    uint32_t bits = (lane < cw && w < NBWp) ? bm[w << 2] : 0u;
+                    const bool mine = lane < cw && w < NBWp;
+                    uint32_t bits = mine ? bm[w << 2] : 0u;
                     if (!__any_sync(0xffffffffu, bits != 0)) continue;
-                    claimed = 1;
+                    const uint32_t orig = bits;
                     uint32_t C = 0;
                     if (bits) {
-                        bits = atomicExch(&bm[w << 2], 0u);
                         C = cont_s[w];
                         uint32_t m = bits;
                         while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
                     }
-                    uint32_t first = 0;
-                    const uint32_t qb = w * 32;
-                    while (__any_sync(0xffffffffu, bits != 0)) {
-                        // emission by rank: in a pass every lane that still has a bit queues one, at
-                        // (its rank among such lanes)
-                        uint32_t n = 0;
-                        for (;;) {
-                            const bool has = bits != 0;
-                            const uint32_t mk = __ballot_sync(0xffffffffu, has);
-                            const uint32_t k = __popc(mk);
-                            if (k == 0 || n + k > scap) break;
-                            if (has) {
-                                const uint32_t bit = __ffs(bits) - 1, q = qb + bit;
-                                bits &= bits - 1;
-                                if (!((C >> bit) & 1u)) first = q;   // ascending bits: a chain's first quad precedes it
-                                stg[n + __popc(mk & ((1u << lane) - 1u))] = q | (first << 16);
-                            }
-                            n += k;
+                    const uint32_t cnt = __popc(bits);
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += t;
+                    }
+                    const uint32_t n = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&S.cnt[p], n);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base + n > qcap) {
+                        // queue full: these vertices stay in the bitmap for the next round
+                        for (uint32_t i = base + lane; i < qcap; i += 32) queue[i] = 0xFFFFFFFFu;
+                        continue;
+                    }
+                    if (orig) bm[w << 2] = 0;      // (no other warp touches the current bucket's bitmap during a collect)
+                    const uint32_t meta = (incl - cnt) | (w << 16);
+                    for (uint32_t t0 = 0; t0 < n; t0 += 32) {
+                        const uint32_t t = t0 + lane;
+                        // owner = number of lanes whose inclusive count is <= t
+                        uint32_t lo = 0;
+#pragma unroll
+                        for (uint32_t step = 16; step >= 1; step >>= 1) {
+                            const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                            if (v <= t) lo += step;
                         }
-                        __syncwarp();
-                        if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
-                        // ---- expand: one quad per lane, two quads of a lane in flight ------------
-                        for (uint32_t i = lane; i < n; i += 64) {
-                            const uint32_t i1 = i + 32;
-                            const uint32_t e0 = stg[i];
-                            const uint32_t e1 = (i1 < n) ? stg[i1] : 0xFFFFFFFFu;
-                            const uint32_t du0 = dist[e0 >> 16];     // the chain owner's distance
-                            const uint32_t du1 = (i1 < n) ? dist[e1 >> 16] : kInf;
-                            // a mark is stale when the vertex was settled in an earlier bucket
-                            const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
-                            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                            if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
-                            if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
-                            if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
-                            if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
+                        const uint32_t ob = __shfl_sync(0xffffffffu, bits, lo);
+                        const uint32_t om = __shfl_sync(0xffffffffu, meta, lo);
+                        const uint32_t oc = __shfl_sync(0xffffffffu, C, lo);
+                        if (t < n) {
+                            // k-th set bit of the owner's word
+                            uint32_t k = t - (om & 0xFFFFu), pos = 0, cc;
+                            cc = __popc(ob & 0xFFFFu); if (k >= cc) { k -= cc; pos = 16; }
+                            cc = __popc((ob >> pos) & 0xFFu); if (k >= cc) { k -= cc; pos += 8; }
+                            cc = __popc((ob >> pos) & 0xFu); if (k >= cc) { k -= cc; pos += 4; }
+                            cc = __popc((ob >> pos) & 0x3u); if (k >= cc) { k -= cc; pos += 2; }
+                            cc = (ob >> pos) & 1u; if (k >= cc) pos += 1;
+                            // first quad of the chain: the nearest bit at or below pos that continues nothing
+                            const uint32_t fb = 31u - __clz(~oc & ((2u << pos) - 1u));
+                            const uint32_t qb = (om >> 16) * 32;
+                            queue[base + t] = (qb + pos) | ((qb + fb) << 16);
                         }
-                        __syncwarp();
                     }
                 }
-                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;
-                if (__syncthreads_or(claimed)) { bucket_work = true; continue; }      // another round of this bucket
-                if (bucket_work) empties = 0;
-                else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
-                bucket_work = false;
-                ++cur;
+                __syncthreads();
+                const uint32_t n_cur = min(S.cnt[p], qcap);
+                if (n_cur == 0) {
+                    __syncthreads();     // every thread has read S.cnt[p] == 0; the counter is reused as is
+                    if (bucket_work) empties = 0;
+                    else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
+                    bucket_work = false;
+                    ++cur;
+                    continue;
+                }
+                bucket_work = true;
+                if (tid == 0) { S.cnt[p ^ 1] = 0; if (a.prof) { a.prof[(size_t)blockIdx.x * 16 + 7] += 1; a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; } }
+                // ---- expand: one quad per lane, two quads of a thread in flight -----------------
+                for (uint32_t i = tid; i < n_cur; i += 2 * T) {
+                    const uint32_t i1 = i + T;
+                    const uint32_t e0 = queue[i];
+                    const uint32_t e1 = (i1 < n_cur) ? queue[i1] : 0xFFFFFFFFu;
+                    const uint32_t du0 = (e0 != 0xFFFFFFFFu) ? dist[e0 >> 16] : kInf;     // the chain owner's distance
+                    const uint32_t du1 = (e1 != 0xFFFFFFFFu) ? dist[e1 >> 16] : kInf;
+                    // a mark is stale when the vertex was settled in an earlier bucket
+                    const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
+                    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                    if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
+                    if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
+                    if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
+                    if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
+                }
+                __syncthreads();
+                p ^= 1;
             }
         }
         HSPF_QMARK(1);   // SSSP
