@@ -157,6 +157,8 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
     a.out_dist = out->dist; a.out_hops = out->hops; a.out_fp = out->first_parent; a.out_npar = out->n_parents;
     a.out_nh = out->nh_mask; a.out_status = out->job_status;
     a.job_counter = ctx->d_counter;
+    a.sub_rounds = 1;
+    if (const char *sr = getenv("HSPF_QUAD_SUB")) { int v = atoi(sr); if (v >= 1 && v <= 8) a.sub_rounds = (uint32_t)v; }   // tuning knob
     const bool ov = jobs->ov_off != nullptr;
     switch (T) {
     case 128: return ov ? launch_quad<128, true>(ctx, a, lay.total, cap) : launch_quad<128, false>(ctx, a, lay.total, cap);

@@ -70,6 +70,7 @@ struct QuadArgs {
     uint64_t *out_nh;
     uint32_t *out_status;
     uint32_t *job_counter;
+    uint32_t sub_rounds;        // visits of a warp to its bitmap chunk per barrier-separated round (>= 1)
     unsigned long long *prof;   // optional [gridDim][16] cycle counters
 };
 
@@ -273,117 +274,109 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t nd = kOv ? sat_add(du, cs[j]) : du + cs[j];
                     if (nd < dh[j]) {      // also rejects nd > reject_above (see U)
-                        // fire-and-forget: nothing below waits on an atomic's result (the round's
-                        // barrier orders distances and marks for the next collect)
-                        atomicMin(&dist[hs[j]], nd);
-                        atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
+                        // The mark must not become visible before the distance (another warp may claim
+                        // it at once): it takes the atomic's result as an operand.  A mark is only needed
+                        // when this relaxation was the improvement.
+                        const uint32_t old = atomicMin(&dist[hs[j]], nd);
+                        if (old > nd) atomicOr(&ring[((hs[j] >> 5) << 2) + ((nd >> sh) & 3u)], 1u << (hs[j] & 31));
                     }
                 }
             };
-            // Buckets are processed in order; a bucket takes rounds of (collect, barrier, expand,
-            // barrier).  Collect: every warp claims its own chunk of the bucket's bitmap (one word
-            // per lane), a warp scan of the popcounts gives every quad of the chunk an output index,
-            // and output lane t finds its quad by itself — owner word by binary search over the
-            // scanned counts (shuffles), then the k-th set bit of that word — so all 32 lanes emit
-            // in every pass, whatever the distribution of bits over the words.  The quads go to a
-            // CTA-wide queue (one atomicAdd per warp), so the expansion runs with full warps.
+            // Buckets are processed in order; a bucket takes rounds.  In a round every warp claims
+            // its own chunk of the bucket's bitmap (one word per lane; atomicExch: a mark made
+            // meanwhile by another warp is either taken now or stays for the next claim).  A warp
+            // scan of the popcounts gives every quad of the chunk an output index, and output lane t
+            // finds its quad by itself — owner word by binary search over the scanned counts
+            // (shuffles), then the k-th set bit of that word — so all lanes work in every pass,
+            // whatever the distribution of bits over the words, and the quad goes straight from the
+            // lane's registers into the relaxation: no queue, no CTA-wide scan.  A warp visits its
+            // chunk `a.sub_rounds` times per round; one CTA barrier per round; the bucket is
+            // finished by a round that claimed nothing.
             constexpr uint32_t kWarps_ = T / 32;
             const uint32_t warp = tid >> 5;
             // chunk = the bitmap words of one claim (one per lane): sized so that every warp owns one
             const uint32_t cw = min(32u, (NBWp + kWarps_ - 1) / kWarps_);
             const uint32_t nchunks = (NBWp + cw - 1) / cw;
-            uint32_t cur = 0, empties = 0, p = 0;
+            const uint32_t sub_rounds = a.sub_rounds;
+            // output index t of a claimed chunk -> queue-less entry (quad | first quad of its chain << 16)
+            auto pick = [&](uint32_t t, uint32_t incl, uint32_t bits, uint32_t meta, uint32_t C) -> uint32_t {
+                uint32_t lo = 0;      // owner = number of lanes whose inclusive count is <= t
+#pragma unroll
+                for (uint32_t step = 16; step >= 1; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                    if (v <= t) lo += step;
+                }
+                lo &= 31u;
+                const uint32_t ob = __shfl_sync(0xffffffffu, bits, lo);
+                const uint32_t om = __shfl_sync(0xffffffffu, meta, lo);
+                const uint32_t oc = __shfl_sync(0xffffffffu, C, lo);
+                // k-th set bit of the owner's word
+                uint32_t k = t - (om & 0xFFFFu), pos = 0, cc;
+                cc = __popc(ob & 0xFFFFu); if (k >= cc) { k -= cc; pos = 16; }
+                cc = __popc((ob >> pos) & 0xFFu); if (k >= cc) { k -= cc; pos += 8; }
+                cc = __popc((ob >> pos) & 0xFu); if (k >= cc) { k -= cc; pos += 4; }
+                cc = __popc((ob >> pos) & 0x3u); if (k >= cc) { k -= cc; pos += 2; }
+                cc = (ob >> pos) & 1u; if (k >= cc) pos += 1;
+                pos &= 31u;
+                // first quad of the chain: the nearest bit at or below pos that continues nothing
+                const uint32_t fb = 31u - __clz((~oc & ((2u << pos) - 1u)) | 1u);
+                const uint32_t qb = (om >> 16) * 32;
+                return (qb + pos) | ((qb + fb) << 16);
+            };
+            uint32_t cur = 0, empties = 0;
             bool bucket_work = false;
             for (uint32_t guard = 0;; ++guard) {
                 if (guard > (1u << 24)) { if (tid == 0) atomicOr(&S.status, kJsInternal); break; }   // defensive
                 uint32_t *bm = ring + (cur & 3u);
-                // ---- collect ----------------------------------------------------------------
-                for (uint32_t c = warp; c < nchunks; c += kWarps_) {
-                    const uint32_t w = c * cw + lane;
-                    const bool mine = lane < cw && w < NBWp;
-                    uint32_t bits = mine ? bm[w << 2] : 0u;
-                    if (!__any_sync(0xffffffffu, bits != 0)) continue;
-                    const uint32_t orig = bits;
-                    uint32_t C = 0;
-                    if (bits) {
-                        C = cont_s[w];
-                        uint32_t m = bits;
-                        while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
-                    }
-                    const uint32_t cnt = __popc(bits);
-                    uint32_t incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ((int)lane >= o) incl += t;
-                    }
-                    const uint32_t n = __shfl_sync(0xffffffffu, incl, 31);
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&S.cnt[p], n);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base + n > qcap) {
-                        // queue full: these vertices stay in the bitmap for the next round
-                        for (uint32_t i = base + lane; i < qcap; i += 32) queue[i] = 0xFFFFFFFFu;
-                        continue;
-                    }
-                    if (orig) bm[w << 2] = 0;      // (no other warp touches the current bucket's bitmap during a collect)
-                    const uint32_t meta = (incl - cnt) | (w << 16);
-                    for (uint32_t t0 = 0; t0 < n; t0 += 32) {
-                        const uint32_t t = t0 + lane;
-                        // owner = number of lanes whose inclusive count is <= t
-                        uint32_t lo = 0;
-#pragma unroll
-                        for (uint32_t step = 16; step >= 1; step >>= 1) {
-                            const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-                            if (v <= t) lo += step;
+                int claimed = 0;
+                for (uint32_t sr = 0; sr < sub_rounds; ++sr) {
+                    for (uint32_t c = warp; c < nchunks; c += kWarps_) {
+                        const uint32_t w = c * cw + lane;
+                        const bool mine = lane < cw && w < NBWp;
+                        uint32_t bits = mine ? *reinterpret_cast<volatile uint32_t *>(&bm[w << 2]) : 0u;
+                        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+                        claimed = 1;
+                        uint32_t C = 0;
+                        if (bits) {
+                            bits = atomicExch(&bm[w << 2], 0u);
+                            C = cont_s[w];
+                            uint32_t m = bits;
+                            while ((m = (m << 1) & C) != 0) bits |= m;      // the other quads of a multi-quad vertex
                         }
-                        const uint32_t ob = __shfl_sync(0xffffffffu, bits, lo);
-                        const uint32_t om = __shfl_sync(0xffffffffu, meta, lo);
-                        const uint32_t oc = __shfl_sync(0xffffffffu, C, lo);
-                        if (t < n) {
-                            // k-th set bit of the owner's word
-                            uint32_t k = t - (om & 0xFFFFu), pos = 0, cc;
-                            cc = __popc(ob & 0xFFFFu); if (k >= cc) { k -= cc; pos = 16; }
-                            cc = __popc((ob >> pos) & 0xFFu); if (k >= cc) { k -= cc; pos += 8; }
-                            cc = __popc((ob >> pos) & 0xFu); if (k >= cc) { k -= cc; pos += 4; }
-                            cc = __popc((ob >> pos) & 0x3u); if (k >= cc) { k -= cc; pos += 2; }
-                            cc = (ob >> pos) & 1u; if (k >= cc) pos += 1;
-                            // first quad of the chain: the nearest bit at or below pos that continues nothing
-                            const uint32_t fb = 31u - __clz(~oc & ((2u << pos) - 1u));
-                            const uint32_t qb = (om >> 16) * 32;
-                            queue[base + t] = (qb + pos) | ((qb + fb) << 16);
+                        const uint32_t cnt = __popc(bits);
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                            if ((int)lane >= o) incl += t;
+                        }
+                        const uint32_t n = __shfl_sync(0xffffffffu, incl, 31);
+                        const uint32_t meta = (incl - cnt) | (w << 16);
+                        if (a.prof && lane == 0) atomicAdd(&a.prof[(size_t)blockIdx.x * 16 + 12], (unsigned long long)n);
+                        // two quads of a lane in flight
+                        for (uint32_t t0 = 0; t0 < n; t0 += 64) {
+                            const uint32_t ta = t0 + lane, tb = ta + 32;
+                            const bool hb = t0 + 32 < n;                       // warp-uniform
+                            const uint32_t e0 = pick(ta, incl, bits, meta, C);
+                            const uint32_t e1 = hb ? pick(tb, incl, bits, meta, C) : 0u;
+                            const uint32_t du0 = (ta < n) ? dist[e0 >> 16] : kInf;     // the chain owner's distance
+                            const uint32_t du1 = (hb && tb < n) ? dist[e1 >> 16] : kInf;
+                            // a mark is stale when the vertex was settled in an earlier bucket
+                            const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
+                            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                            if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
+                            if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
+                            if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
+                            if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
                         }
                     }
                 }
-                __syncthreads();
-                const uint32_t n_cur = min(S.cnt[p], qcap);
-                if (n_cur == 0) {
-                    __syncthreads();     // every thread has read S.cnt[p] == 0; the counter is reused as is
-                    if (bucket_work) empties = 0;
-                    else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
-                    bucket_work = false;
-                    ++cur;
-                    continue;
-                }
-                bucket_work = true;
-                if (tid == 0) { S.cnt[p ^ 1] = 0; if (a.prof) { a.prof[(size_t)blockIdx.x * 16 + 7] += 1; a.prof[(size_t)blockIdx.x * 16 + 12] += n_cur; } }
-                // ---- expand: one quad per lane, two quads of a thread in flight -----------------
-                for (uint32_t i = tid; i < n_cur; i += 2 * T) {
-                    const uint32_t i1 = i + T;
-                    const uint32_t e0 = queue[i];
-                    const uint32_t e1 = (i1 < n_cur) ? queue[i1] : 0xFFFFFFFFu;
-                    const uint32_t du0 = (e0 != 0xFFFFFFFFu) ? dist[e0 >> 16] : kInf;     // the chain owner's distance
-                    const uint32_t du1 = (e1 != 0xFFFFFFFFu) ? dist[e1 >> 16] : kInf;
-                    // a mark is stale when the vertex was settled in an earlier bucket
-                    const bool l0 = (du0 >> sh) == cur, l1 = (du1 >> sh) == cur;
-                    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                    if (l0) r0 = __ldg(&Q.fq[e0 & 0xFFFFu]);
-                    if (l1) r1 = __ldg(&Q.fq[e1 & 0xFFFFu]);
-                    if (l0) relax(e0 & 0xFFFFu, e0 >> 16, du0, r0);
-                    if (l1) relax(e1 & 0xFFFFu, e1 >> 16, du1, r1);
-                }
-                __syncthreads();
-                p ^= 1;
+                if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 7] += 1;
+                if (__syncthreads_or(claimed)) { bucket_work = true; continue; }      // another round of this bucket
+                if (bucket_work) empties = 0;
+                else if (++empties == 4) break;      // bucket width >= a third of the largest cost: gaps span < 4 buckets
+                bucket_work = false;
+                ++cur;
             }
         }
         HSPF_QMARK(1);   // SSSP

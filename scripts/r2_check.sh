@@ -16,6 +16,9 @@ done
 for D in ${DELTAS:-128 512}; do
   HSPF_QUAD_T=${TBEST:-512} step "bench T=${TBEST:-512} delta=$D" 120 python scripts/bench_brief.py --steps 10 --warmup 3 --no-cpu-baseline --delta $D
 done
+for SUB in ${SUBS:-}; do
+  HSPF_QUAD_SUB=$SUB HSPF_QUAD_T=${TBEST:-512} step "bench T=${TBEST:-512} sub_rounds=$SUB delta=${DBEST:-0}" 120 python scripts/bench_brief.py --steps 10 --warmup 3 --no-cpu-baseline --delta ${DBEST:-0}
+done
 for J in ${JOBSWEEP:-}; do
   HSPF_QUAD_T=${TBEST:-512} step "bench T=${TBEST:-512} jobs=$J" 120 python scripts/bench_brief.py --steps 10 --warmup 3 --no-cpu-baseline --jobs $J
 done
