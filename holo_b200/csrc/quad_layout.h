@@ -124,10 +124,11 @@ inline QuadHost build_quads(uint32_t V, uint32_t E, const uint32_t *row, const u
             Q.ipos[ifwd[k]] = islot[v] * 4 + i;
         }
     }
-    // ---- bucket width: a power of two near 4x the mean cost (few buckets, ~1.3x
-    // re-expansion), and at least a third of the largest cost so that a relaxation out
-    // of bucket b lands in b .. b+3, the span of the ring of four frontier bitmaps -------
-    uint64_t want = delta_hint ? delta_hint : (E ? 4 * (cost_sum / E) : 1);
+    // ---- bucket width: a power of two near 2.5x the mean cost (measured on the BASELINE
+    // shapes: ~1.4x re-expansion, a few buckets), and at least a third of the largest cost
+    // so that a relaxation out of bucket b lands in b .. b+3, the span of the ring of four
+    // frontier bitmaps ------------------------------------------------------------------
+    uint64_t want = delta_hint ? delta_hint : (E ? (5 * (cost_sum / E) + 1) / 2 : 1);
     want = std::max<uint64_t>(want, (uint64_t)(max_cost + 2) / 3);
     uint32_t sh = 0;
     while ((1ull << sh) < want) ++sh;

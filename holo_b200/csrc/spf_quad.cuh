@@ -519,16 +519,20 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         for (;;) {
             uint32_t moved = 0;
             for (uint32_t v0 = tid; v0 < Vp; v0 += 4 * T) {      // Vp % (4 * T) == 0
-                uint32_t w[4], w2[4];
+                // two jumps per round (v -> A -> A'): fewer barrier-separated rounds
+                uint32_t w[4], w2[4], w3[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) w[k] = word[v0 + k * T];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
 #pragma unroll
+                for (int k = 0; k < 4; ++k) w3[k] = word[w2[k] >> 16];
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    // w2 is a terminal (points at itself, sum 0) or an ordinary vertex
-                    word[v0 + k * T] = (w2[k] & 0xFFFF0000u) | ((w[k] + w2[k]) & 0xFFFFu);
-                    moved |= w2[k] ^ w[k];
+                    // w2 / w3 are terminals (point at themselves, sum 0: read twice they add nothing)
+                    // or ordinary vertices
+                    word[v0 + k * T] = (w3[k] & 0xFFFF0000u) | ((w[k] + w2[k] + w3[k]) & 0xFFFFu);
+                    moved |= w3[k] ^ w[k];
                 }
             }
             if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 13] += 1;
@@ -619,14 +623,16 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             // the cut tree is no deeper than the first-parent tree: the hop pass's round count suffices
             for (uint32_t r = 0; r < jump_rounds; ++r) {
                 for (uint32_t v0 = tid; v0 < Vp; v0 += 4 * T) {
-                    uint32_t w[4], w2[4];
+                    uint32_t w[4], w2[4], w3[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) w[k] = word[v0 + k * T];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) w2[k] = word[w[k] >> 16];
 #pragma unroll
+                    for (int k = 0; k < 4; ++k) w3[k] = word[w2[k] >> 16];
+#pragma unroll
                     for (int k = 0; k < 4; ++k)   // OR-ing a terminal's own seeds again is harmless (every vertex ORs in its top's set below)
-                        word[v0 + k * T] = (w2[k] & 0xFFFF0000u) | ((w[k] | w2[k]) & 0xFFFFu);
+                        word[v0 + k * T] = (w3[k] & 0xFFFF0000u) | ((w[k] | w2[k] | w3[k]) & 0xFFFFu);
                 }
                 if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + 14] += 1;
                 __syncthreads();
