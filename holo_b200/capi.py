@@ -35,6 +35,8 @@ JS_SATURATED = 0x1
 JS_TOO_MANY_ATOMS = 0x2
 JS_ORDER = 0x4
 JS_INVALID = 0x8
+JS_INTERNAL = 0x10
+JS_NARROW = 0x20
 RUN_DEVICE_PTRS = 0x1
 MAX_OVERRIDES = 8
 
@@ -81,14 +83,26 @@ class ResultStruct(C.Structure):
     ]
 
 
+class Result16Struct(C.Structure):
+    _fields_ = [
+        ("dist", _u16p),
+        ("hops", _u16p),
+        ("first_parent", _u16p),
+        ("n_parents", _u16p),
+        ("nh_mask", _u16p),
+        ("job_status", _u32p),
+    ]
+
+
 EXPORTS = [
     "hspf_version", "hspf_ctx_create", "hspf_ctx_destroy", "hspf_last_error",
     "hspf_graph_upload", "hspf_graph_free", "hspf_run_batch", "hspf_run_batch_async",
     "hspf_sync", "hspf_stream", "hspf_launch_count", "hspf_atom_decode", "hspf_atom_count",
     "hspf_ctx_reserve_sms", "hspf_debug_quad_image", "hspf_debug_phase_profile",
+    "hspf_run_batch16", "hspf_run_batch16_async", "hspf_graph_info",
     "hspf_xchg_create", "hspf_xchg_attach", "hspf_xchg_slot", "hspf_xchg_slot_bytes", "hspf_xchg_acquire",
     "hspf_xchg_push", "hspf_xchg_wait", "hspf_xchg_release", "hspf_xchg_consumer_stream", "hspf_xchg_sync",
-    "hspf_xchg_last_error", "hspf_xchg_destroy",
+    "hspf_xchg_last_error", "hspf_xchg_destroy", "hspf_xchg_attach_ptr", "hspf_xchg_base", "hspf_xchg_set_push_bytes",
 ]
 
 
@@ -134,6 +148,9 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.hspf_debug_quad_image.argtypes = [C.POINTER(CsrStruct), C.POINTER(C.c_uint32), _u32p, _u32p, _u16p, _u16p,
                                           _u32p, _u32p, _u32p, _u32p]
     lib.hspf_debug_phase_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+    lib.hspf_run_batch16.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(JobsStruct), C.POINTER(Result16Struct), C.c_uint32]
+    lib.hspf_run_batch16_async.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(JobsStruct), C.POINTER(Result16Struct)]
+    lib.hspf_graph_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     if path is None:
         _lib = lib
     return lib
@@ -298,6 +315,35 @@ class Context:
         res.status = self._check(rc, allow=(HSPF_E_JOB_STATUS,))
         del keep
         return res
+
+    def run16(self, graph: Graph, roots, overrides=None, planes=("dist", "hops", "first_parent", "n_parents", "nh_mask")):
+        """Host-pointer call with 16-bit planes (hspf_run_batch16); planes not listed are skipped (NULL)."""
+        js, keep = make_jobs(roots, overrides)
+        n, V = js.n_jobs, graph.csr.n_vertices
+        arr = {k: np.empty((n, V), np.uint16) for k in planes}
+        status = np.zeros(n, np.uint32)
+        rs = Result16Struct()
+        for k in ("dist", "hops", "first_parent", "n_parents", "nh_mask"):
+            setattr(rs, k, _ptr(arr.get(k), _u16p))
+        rs.job_status = _ptr(status, _u32p)
+        rc = self.lib.hspf_run_batch16(self.handle, graph.handle, C.byref(js), C.byref(rs), 0)
+        rc = self._check(rc, allow=(HSPF_E_JOB_STATUS,))
+        del keep
+        arr["job_status"] = status
+        arr["status"] = rc
+        return arr
+
+    def run_device16(self, graph: Graph, jobs: JobsStruct, rs: "Result16Struct", sync: bool = True):
+        """Device-pointer call with 16-bit planes."""
+        self._check(self.lib.hspf_run_batch16_async(self.handle, graph.handle, C.byref(jobs), C.byref(rs)))
+        if sync:
+            self._check(self.lib.hspf_sync(self.handle))
+
+    def graph_info(self, graph: Graph) -> dict:
+        info = (C.c_uint32 * 8)()
+        self._check(self.lib.hspf_graph_info(graph.handle, info))
+        return {"fast_path": bool(info[0]), "fwd_quads": info[1], "in_quads": info[2], "bucket_shift": info[3],
+                "V": info[4], "E": info[5], "max_indeg": info[6]}
 
     def run_device(self, graph: Graph, jobs: JobsStruct, rs: ResultStruct, sync: bool = True):
         """Device-pointer call (inputs/outputs already resident in HBM)."""

@@ -105,6 +105,36 @@ int max_ctas_per_sm(size_t smem) {
     return n < 1 ? 1 : n;
 }
 
+// Result planes of either width: hspf_result (dist u32, first_parent u32, nh_mask u64 x nh_words)
+// or hspf_result16 (all planes u16, one next-hop word of 16 atoms).
+struct AnyResult {
+    void *dist = nullptr;
+    uint16_t *hops = nullptr;
+    void *fp = nullptr;
+    uint16_t *npar = nullptr;
+    void *nh = nullptr;
+    uint32_t nh_words = 1;
+    uint32_t *job_status = nullptr;
+    bool narrow = false;
+    size_t dist_b() const { return narrow ? 2 : 4; }
+    size_t fp_b() const { return narrow ? 2 : 4; }
+    size_t nh_b() const { return narrow ? 2 : 8 * (size_t)nh_words; }
+};
+
+AnyResult any_of(const hspf_result *r) {
+    AnyResult a;
+    a.dist = r->dist; a.hops = r->hops; a.fp = r->first_parent; a.npar = r->n_parents; a.nh = r->nh_mask;
+    a.nh_words = r->nh_words; a.job_status = r->job_status; a.narrow = false;
+    return a;
+}
+
+AnyResult any_of(const hspf_result16 *r) {
+    AnyResult a;
+    a.dist = r->dist; a.hops = r->hops; a.fp = r->first_parent; a.npar = r->n_parents; a.nh = r->nh_mask;
+    a.nh_words = 1; a.job_status = r->job_status; a.narrow = true;
+    return a;
+}
+
 template <int T, bool O>
 int launch_quad(hspf_ctx *ctx, const QuadArgs &args, size_t smem, int per_sm_cap) {
     CK(cudaFuncSetAttribute(spf_quad_kernel<T, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -139,7 +169,7 @@ int launch_quad(hspf_ctx *ctx, const QuadArgs &args, size_t smem, int per_sm_cap
 }
 
 // The fast path: quad-space kernel (spf_quad.cuh).  Returns 1 if the batch is not eligible.
-int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult *out) {
     if (!g->has_quads || g->has_leaf || (g->d.flags & HSPF_GF_HOPCOUNT) || out->nh_words != 1) return 1;
     if (getenv("HSPF_NO_QUAD")) return 1;             // tuning knob (experiments only)
     uint32_t qcap = 2048;
@@ -154,8 +184,10 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
     a.g = g->d; a.q = g->q; a.lay = lay;
     a.n_jobs = jobs->n_jobs; a.roots = jobs->roots;
     a.ov_off = jobs->ov_off; a.ov_edge = jobs->ov_edge; a.ov_cost = jobs->ov_cost;
-    a.out_dist = out->dist; a.out_hops = out->hops; a.out_fp = out->first_parent; a.out_npar = out->n_parents;
-    a.out_nh = out->nh_mask; a.out_status = out->job_status;
+    a.out_dist = static_cast<uint32_t *>(out->dist); a.out_hops = out->hops;
+    a.out_fp = static_cast<uint32_t *>(out->fp); a.out_npar = out->npar;
+    a.out_nh = static_cast<uint64_t *>(out->nh); a.out_status = out->job_status;
+    a.narrow = out->narrow ? 1u : 0u;
     a.job_counter = ctx->d_counter;
     a.sub_rounds = 1;
     if (const char *sr = getenv("HSPF_QUAD_SUB")) { int v = atoi(sr); if (v >= 1 && v <= 8) a.sub_rounds = (uint32_t)v; }   // tuning knob
@@ -169,11 +201,14 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
 }
 
 // Enqueue one batch.  All pointers in `jobs`/`out` are device pointers here.
-int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
+int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult *out) {
     {
         const int rq = enqueue_quad(ctx, g, jobs, out);
         if (rq != 1) return rq;
     }
+    if (out->narrow)
+        return fail(ctx, HSPF_E_UNSUPPORTED, "16-bit result planes need the packed fast path (" +
+                    (g->has_quads ? std::string("LEAF flags / hop-count mode") : g->quad_why) + ")");
     const uint32_t V = g->d.V;
     const bool q16 = V <= 0xFFFFu;
     const Layout lay = make_layout(V, g->d.E, q16 ? 2 : 4);
@@ -190,11 +225,11 @@ int enqueue(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hsp
     a.ov_off = jobs->ov_off;
     a.ov_edge = jobs->ov_edge;
     a.ov_cost = jobs->ov_cost;
-    a.out_dist = out->dist;
+    a.out_dist = static_cast<uint32_t *>(out->dist);
     a.out_hops = out->hops;
-    a.out_fp = out->first_parent;
-    a.out_npar = out->n_parents;
-    a.out_nh = out->nh_mask;
+    a.out_fp = static_cast<uint32_t *>(out->fp);
+    a.out_npar = out->npar;
+    a.out_nh = static_cast<uint64_t *>(out->nh);
     a.out_status = out->job_status;
     a.nhw = out->nh_words;
     a.job_counter = ctx->d_counter;
@@ -246,19 +281,168 @@ struct Planes {   // byte sizes of the result planes of a batch
     size_t total() const { return dist + hops + fp + npar + nh + status; }
 };
 
-Planes plane_sizes(uint32_t n_jobs, uint32_t V, uint32_t nhw) {
+Planes plane_sizes(uint32_t n_jobs, uint32_t V, const AnyResult &r) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t n = (size_t)n_jobs * V;
     Planes p;
-    p.dist = al(n * 4); p.hops = al(n * 2); p.fp = al(n * 4); p.npar = al(n * 2);
-    p.nh = al(n * 8 * nhw); p.status = al((size_t)n_jobs * 4);
+    p.dist = al(n * r.dist_b()); p.hops = al(n * 2); p.fp = al(n * r.fp_b()); p.npar = al(n * 2);
+    p.nh = al(n * r.nh_b()); p.status = al((size_t)n_jobs * 4);
     return p;
 }
 
-int check_result_args(hspf_ctx *ctx, const hspf_result *out) {
-    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
-    if (out->nh_words < 1 || out->nh_words > 4) return fail(ctx, HSPF_E_INVAL, "nh_words must be 1..4");
+int check_result_args(hspf_ctx *ctx, const AnyResult &out) {
+    if (out.nh_words < 1 || out.nh_words > 4) return fail(ctx, HSPF_E_INVAL, "nh_words must be 1..4");
     return HSPF_OK;
+}
+
+int run_async_any(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult &out);
+int run_any(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult &out, uint32_t flags);
+
+int run_async_any(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult &out) {
+    int rc = check_result_args(ctx, out);
+    if (rc) return rc;
+    if (jobs->n_jobs == 0) return HSPF_OK;
+    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        // planes the caller skipped still have to exist on the device
+        AnyResult r = out;
+        Planes ps = plane_sizes(jobs->n_jobs, g->d.V, r);
+        size_t need = 0;
+        if (!r.dist) need += ps.dist;
+        if (!r.hops) need += ps.hops;
+        if (!r.fp) need += ps.fp;
+        if (!r.npar) need += ps.npar;
+        if (!r.nh) need += ps.nh;
+        if (!r.job_status) need += ps.status;
+        if (need) {
+            rc = grow(ctx, &ctx->scratch, &ctx->scratch_bytes, need);
+            if (rc) return rc;
+            uint8_t *p = static_cast<uint8_t *>(ctx->scratch);
+            if (!r.dist) { r.dist = p; p += ps.dist; }
+            if (!r.hops) { r.hops = reinterpret_cast<uint16_t *>(p); p += ps.hops; }
+            if (!r.fp) { r.fp = p; p += ps.fp; }
+            if (!r.npar) { r.npar = reinterpret_cast<uint16_t *>(p); p += ps.npar; }
+            if (!r.nh) { r.nh = p; p += ps.nh; }
+            if (!r.job_status) { r.job_status = reinterpret_cast<uint32_t *>(p); p += ps.status; }
+        }
+        return enqueue(ctx, g, jobs, &r);
+    } catch (...) {
+        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+int run_any(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const AnyResult &out, uint32_t flags) {
+    int rc = check_result_args(ctx, out);
+    if (rc) return rc;
+    if (jobs->n_jobs == 0) return HSPF_OK;
+    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const uint32_t n = jobs->n_jobs, V = g->d.V;
+        if (flags & HSPF_RUN_DEVICE_PTRS) {
+            rc = run_async_any(ctx, g, jobs, out);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+            return HSPF_OK;   // job_status stays on the device in this mode
+        }
+        // ---- host-pointer mode: validate, stage in, run, stage out --------------
+        uint32_t n_ov = 0;
+        for (uint32_t j = 0; j < n; ++j)
+            if (jobs->roots[j] >= V) return fail(ctx, HSPF_E_INVAL, "root out of range");
+        if (jobs->ov_off) {
+            if (!jobs->ov_edge || !jobs->ov_cost) {
+                if (jobs->ov_off[n] != 0) return fail(ctx, HSPF_E_INVAL, "null override arrays");
+            }
+            for (uint32_t j = 0; j < n; ++j) {
+                if (jobs->ov_off[j + 1] < jobs->ov_off[j]) return fail(ctx, HSPF_E_INVAL, "ov_off not monotone");
+                if (jobs->ov_off[j + 1] - jobs->ov_off[j] > HSPF_MAX_OVERRIDES)
+                    return fail(ctx, HSPF_E_UNSUPPORTED, "more than HSPF_MAX_OVERRIDES overrides in a job");
+            }
+            n_ov = jobs->ov_off[n];
+            for (uint32_t i = 0; i < n_ov; ++i)
+                if (jobs->ov_edge[i] >= g->d.E) return fail(ctx, HSPF_E_INVAL, "override edge out of range");
+        }
+        auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+        const size_t in_roots = al((size_t)n * 4);
+        const size_t in_off = jobs->ov_off ? al((size_t)(n + 1) * 4) : 0;
+        const size_t in_ove = al((size_t)n_ov * 4 + 4), in_ovc = al((size_t)n_ov * 4 + 4);
+        const size_t in_total = in_roots + in_off + in_ove + in_ovc;
+        Planes ps = plane_sizes(n, V, out);
+        const size_t dev_total = in_total + ps.total();
+        rc = grow(ctx, &ctx->stage, &ctx->stage_bytes, dev_total);
+        if (rc) return rc;
+        rc = grow(ctx, &ctx->h_pin, &ctx->h_pin_bytes, in_total, true);
+        if (rc) return rc;
+        uint8_t *hp = static_cast<uint8_t *>(ctx->h_pin);
+        uint8_t *dp = static_cast<uint8_t *>(ctx->stage);
+        std::memcpy(hp, jobs->roots, (size_t)n * 4);
+        if (jobs->ov_off) {
+            std::memcpy(hp + in_roots, jobs->ov_off, (size_t)(n + 1) * 4);
+            if (n_ov) {
+                std::memcpy(hp + in_roots + in_off, jobs->ov_edge, (size_t)n_ov * 4);
+                std::memcpy(hp + in_roots + in_off + in_ove, jobs->ov_cost, (size_t)n_ov * 4);
+            }
+        }
+        CK(cudaMemcpyAsync(dp, hp, in_total, cudaMemcpyHostToDevice, ctx->stream));
+        hspf_jobs dj{};
+        dj.n_jobs = n;
+        dj.roots = reinterpret_cast<const uint32_t *>(dp);
+        dj.ov_off = jobs->ov_off ? reinterpret_cast<const uint32_t *>(dp + in_roots) : nullptr;
+        dj.ov_edge = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off);
+        dj.ov_cost = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off + in_ove);
+        uint8_t *rp = dp + in_total;
+        AnyResult dr = out;
+        dr.dist = rp; rp += ps.dist;
+        dr.hops = reinterpret_cast<uint16_t *>(rp); rp += ps.hops;
+        dr.fp = rp; rp += ps.fp;
+        dr.npar = reinterpret_cast<uint16_t *>(rp); rp += ps.npar;
+        dr.nh = rp; rp += ps.nh;
+        dr.job_status = reinterpret_cast<uint32_t *>(rp); rp += ps.status;
+        // The batch is launched in chunks; a chunk's planes are copied back on a second stream
+        // while the next chunk computes, so the device-to-host copy (the longer of the two at
+        // the BASELINE batch size) hides the kernels.  HSPF_E2E_CHUNK overrides the chunk size.
+        uint32_t chunk = n >= 256 ? (n + 3) / 4 : n;
+        if (const char *cs = getenv("HSPF_E2E_CHUNK")) { int v = atoi(cs); if (v > 0) chunk = (uint32_t)v; }
+        std::vector<uint32_t> st(n);
+        const size_t db = out.dist_b(), fb = out.fp_b(), nb = out.nh_b();
+        for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint32_t cn = std::min(chunk, n - c0);
+            hspf_jobs cj = dj;
+            cj.n_jobs = cn;
+            cj.roots = dj.roots + c0;
+            if (dj.ov_off) cj.ov_off = dj.ov_off + c0;    // offsets stay absolute into ov_edge/ov_cost
+            AnyResult cr = dr;
+            const size_t o = (size_t)c0 * V;
+            cr.dist = static_cast<uint8_t *>(dr.dist) + o * db; cr.hops = dr.hops + o;
+            cr.fp = static_cast<uint8_t *>(dr.fp) + o * fb; cr.npar = dr.npar + o;
+            cr.nh = static_cast<uint8_t *>(dr.nh) + o * nb;
+            cr.job_status = dr.job_status + c0;
+            rc = enqueue(ctx, g, &cj, &cr);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->chunk_done, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
+            const size_t cv = (size_t)cn * V;
+            cudaStream_t cs = ctx->copy_stream;
+            if (out.dist) CK(cudaMemcpyAsync(static_cast<uint8_t *>(out.dist) + o * db, cr.dist, cv * db, cudaMemcpyDeviceToHost, cs));
+            if (out.hops) CK(cudaMemcpyAsync(out.hops + o, cr.hops, cv * 2, cudaMemcpyDeviceToHost, cs));
+            if (out.fp) CK(cudaMemcpyAsync(static_cast<uint8_t *>(out.fp) + o * fb, cr.fp, cv * fb, cudaMemcpyDeviceToHost, cs));
+            if (out.npar) CK(cudaMemcpyAsync(out.npar + o, cr.npar, cv * 2, cudaMemcpyDeviceToHost, cs));
+            if (out.nh) CK(cudaMemcpyAsync(static_cast<uint8_t *>(out.nh) + o * nb, cr.nh, cv * nb, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(st.data() + c0, cr.job_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+        }
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool any = false;
+        for (uint32_t j = 0; j < n; ++j) any |= (st[j] != 0);
+        if (out.job_status) std::memcpy(out.job_status, st.data(), (size_t)n * 4);
+        if (any) return fail(ctx, HSPF_E_JOB_STATUS, "one or more jobs need the CPU path (see job_status)");
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
 }
 
 }  // namespace
@@ -545,152 +729,36 @@ int hspf_sync(hspf_ctx *ctx) {
 
 int hspf_run_batch_async(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out) {
     if (!ctx || !g || !jobs) return HSPF_E_INVAL;
-    int rc = check_result_args(ctx, out);
-    if (rc) return rc;
-    if (jobs->n_jobs == 0) return HSPF_OK;
-    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
-    try {
-        CK(cudaSetDevice(ctx->device));
-        // planes the caller skipped still have to exist on the device
-        hspf_result r = *out;
-        Planes ps = plane_sizes(jobs->n_jobs, g->d.V, r.nh_words);
-        size_t need = 0;
-        if (!r.dist) need += ps.dist;
-        if (!r.hops) need += ps.hops;
-        if (!r.first_parent) need += ps.fp;
-        if (!r.n_parents) need += ps.npar;
-        if (!r.nh_mask) need += ps.nh;
-        if (!r.job_status) need += ps.status;
-        if (need) {
-            rc = grow(ctx, &ctx->scratch, &ctx->scratch_bytes, need);
-            if (rc) return rc;
-            uint8_t *p = static_cast<uint8_t *>(ctx->scratch);
-            if (!r.dist) { r.dist = reinterpret_cast<uint32_t *>(p); p += ps.dist; }
-            if (!r.hops) { r.hops = reinterpret_cast<uint16_t *>(p); p += ps.hops; }
-            if (!r.first_parent) { r.first_parent = reinterpret_cast<uint32_t *>(p); p += ps.fp; }
-            if (!r.n_parents) { r.n_parents = reinterpret_cast<uint16_t *>(p); p += ps.npar; }
-            if (!r.nh_mask) { r.nh_mask = reinterpret_cast<uint64_t *>(p); p += ps.nh; }
-            if (!r.job_status) { r.job_status = reinterpret_cast<uint32_t *>(p); p += ps.status; }
-        }
-        return enqueue(ctx, g, jobs, &r);
-    } catch (...) {
-        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
-    }
+    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
+    return run_async_any(ctx, g, jobs, any_of(out));
 }
 
 int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result *out, uint32_t flags) {
     if (!ctx || !g || !jobs) return HSPF_E_INVAL;
-    int rc = check_result_args(ctx, out);
-    if (rc) return rc;
-    if (jobs->n_jobs == 0) return HSPF_OK;
-    if (!jobs->roots) return fail(ctx, HSPF_E_INVAL, "null roots");
-    try {
-        CK(cudaSetDevice(ctx->device));
-        const uint32_t n = jobs->n_jobs, V = g->d.V;
-        if (flags & HSPF_RUN_DEVICE_PTRS) {
-            rc = hspf_run_batch_async(ctx, g, jobs, out);
-            if (rc) return rc;
-            CK(cudaStreamSynchronize(ctx->stream));
-            return HSPF_OK;   // job_status stays on the device in this mode
-        }
-        // ---- host-pointer mode: validate, stage in, run, stage out --------------
-        uint32_t n_ov = 0;
-        for (uint32_t j = 0; j < n; ++j)
-            if (jobs->roots[j] >= V) return fail(ctx, HSPF_E_INVAL, "root out of range");
-        if (jobs->ov_off) {
-            if (!jobs->ov_edge || !jobs->ov_cost) {
-                if (jobs->ov_off[n] != 0) return fail(ctx, HSPF_E_INVAL, "null override arrays");
-            }
-            for (uint32_t j = 0; j < n; ++j) {
-                if (jobs->ov_off[j + 1] < jobs->ov_off[j]) return fail(ctx, HSPF_E_INVAL, "ov_off not monotone");
-                if (jobs->ov_off[j + 1] - jobs->ov_off[j] > HSPF_MAX_OVERRIDES)
-                    return fail(ctx, HSPF_E_UNSUPPORTED, "more than HSPF_MAX_OVERRIDES overrides in a job");
-            }
-            n_ov = jobs->ov_off[n];
-            for (uint32_t i = 0; i < n_ov; ++i)
-                if (jobs->ov_edge[i] >= g->d.E) return fail(ctx, HSPF_E_INVAL, "override edge out of range");
-        }
-        auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-        const size_t in_roots = al((size_t)n * 4);
-        const size_t in_off = jobs->ov_off ? al((size_t)(n + 1) * 4) : 0;
-        const size_t in_ove = al((size_t)n_ov * 4 + 4), in_ovc = al((size_t)n_ov * 4 + 4);
-        const size_t in_total = in_roots + in_off + in_ove + in_ovc;
-        Planes ps = plane_sizes(n, V, out->nh_words);
-        const size_t dev_total = in_total + ps.total();
-        rc = grow(ctx, &ctx->stage, &ctx->stage_bytes, dev_total);
-        if (rc) return rc;
-        rc = grow(ctx, &ctx->h_pin, &ctx->h_pin_bytes, in_total, true);
-        if (rc) return rc;
-        uint8_t *hp = static_cast<uint8_t *>(ctx->h_pin);
-        uint8_t *dp = static_cast<uint8_t *>(ctx->stage);
-        std::memcpy(hp, jobs->roots, (size_t)n * 4);
-        if (jobs->ov_off) {
-            std::memcpy(hp + in_roots, jobs->ov_off, (size_t)(n + 1) * 4);
-            if (n_ov) {
-                std::memcpy(hp + in_roots + in_off, jobs->ov_edge, (size_t)n_ov * 4);
-                std::memcpy(hp + in_roots + in_off + in_ove, jobs->ov_cost, (size_t)n_ov * 4);
-            }
-        }
-        CK(cudaMemcpyAsync(dp, hp, in_total, cudaMemcpyHostToDevice, ctx->stream));
-        hspf_jobs dj{};
-        dj.n_jobs = n;
-        dj.roots = reinterpret_cast<const uint32_t *>(dp);
-        dj.ov_off = jobs->ov_off ? reinterpret_cast<const uint32_t *>(dp + in_roots) : nullptr;
-        dj.ov_edge = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off);
-        dj.ov_cost = reinterpret_cast<const uint32_t *>(dp + in_roots + in_off + in_ove);
-        uint8_t *rp = dp + in_total;
-        hspf_result dr{};
-        dr.nh_words = out->nh_words;
-        dr.dist = reinterpret_cast<uint32_t *>(rp); rp += ps.dist;
-        dr.hops = reinterpret_cast<uint16_t *>(rp); rp += ps.hops;
-        dr.first_parent = reinterpret_cast<uint32_t *>(rp); rp += ps.fp;
-        dr.n_parents = reinterpret_cast<uint16_t *>(rp); rp += ps.npar;
-        dr.nh_mask = reinterpret_cast<uint64_t *>(rp); rp += ps.nh;
-        dr.job_status = reinterpret_cast<uint32_t *>(rp); rp += ps.status;
-        // The batch can be launched in chunks, each chunk's planes copied back on a second
-        // stream while the next chunk computes.
-        // (measured on B200/PCIe5: the 200 MB D2H dominates and chunking buys nothing at the
-        // BASELINE batch size, so the default is one chunk; HSPF_E2E_CHUNK overrides)
-        uint32_t chunk = n;
-        if (const char *cs = getenv("HSPF_E2E_CHUNK")) { int v = atoi(cs); if (v > 0) chunk = (uint32_t)v; }
-        std::vector<uint32_t> st(n);
-        for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
-            const uint32_t cn = std::min(chunk, n - c0);
-            hspf_jobs cj = dj;
-            cj.n_jobs = cn;
-            cj.roots = dj.roots + c0;
-            if (dj.ov_off) cj.ov_off = dj.ov_off + c0;    // offsets stay absolute into ov_edge/ov_cost
-            hspf_result cr = dr;
-            const size_t o = (size_t)c0 * V;
-            cr.dist = dr.dist + o; cr.hops = dr.hops + o; cr.first_parent = dr.first_parent + o;
-            cr.n_parents = dr.n_parents + o; cr.nh_mask = dr.nh_mask + o * out->nh_words;
-            cr.job_status = dr.job_status + c0;
-            rc = enqueue(ctx, g, &cj, &cr);
-            if (rc) return rc;
-            CK(cudaEventRecord(ctx->chunk_done, ctx->stream));
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
-            const size_t cv = (size_t)cn * V;
-            cudaStream_t cs = ctx->copy_stream;
-            if (out->dist) CK(cudaMemcpyAsync(out->dist + o, cr.dist, cv * 4, cudaMemcpyDeviceToHost, cs));
-            if (out->hops) CK(cudaMemcpyAsync(out->hops + o, cr.hops, cv * 2, cudaMemcpyDeviceToHost, cs));
-            if (out->first_parent) CK(cudaMemcpyAsync(out->first_parent + o, cr.first_parent, cv * 4, cudaMemcpyDeviceToHost, cs));
-            if (out->n_parents) CK(cudaMemcpyAsync(out->n_parents + o, cr.n_parents, cv * 2, cudaMemcpyDeviceToHost, cs));
-            if (out->nh_mask)
-                CK(cudaMemcpyAsync(out->nh_mask + o * out->nh_words, cr.nh_mask, cv * 8 * out->nh_words, cudaMemcpyDeviceToHost, cs));
-            CK(cudaMemcpyAsync(st.data() + c0, cr.job_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
-        }
-        CK(cudaStreamSynchronize(ctx->copy_stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        bool any = false;
-        for (uint32_t j = 0; j < n; ++j) any |= (st[j] != 0);
-        if (out->job_status) std::memcpy(out->job_status, st.data(), (size_t)n * 4);
-        if (any) return fail(ctx, HSPF_E_JOB_STATUS, "one or more jobs need the CPU path (see job_status)");
-        return HSPF_OK;
-    } catch (const std::bad_alloc &) {
-        return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
-    } catch (...) {
-        return fail(ctx, HSPF_E_INVAL, "unexpected exception");
-    }
+    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
+    return run_any(ctx, g, jobs, any_of(out), flags);
+}
+
+int hspf_run_batch16_async(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result16 *out) {
+    if (!ctx || !g || !jobs) return HSPF_E_INVAL;
+    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
+    return run_async_any(ctx, g, jobs, any_of(out));
+}
+
+int hspf_run_batch16(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const hspf_result16 *out, uint32_t flags) {
+    if (!ctx || !g || !jobs) return HSPF_E_INVAL;
+    if (!out) return fail(ctx, HSPF_E_INVAL, "null result");
+    return run_any(ctx, g, jobs, any_of(out), flags);
+}
+
+int hspf_graph_info(const hspf_graph *g, uint32_t info[8]) {
+    if (!g || !info) return HSPF_E_INVAL;
+    info[0] = g->has_quads && !g->has_leaf && !(g->d.flags & HSPF_GF_HOPCOUNT) ? 1u : 0u;   // fast path / 16-bit planes available
+    info[1] = g->has_quads ? g->q.NQ : 0u;
+    info[2] = g->has_quads ? g->q.NIQ : 0u;
+    info[3] = g->has_quads ? g->q.shift : 0u;
+    info[4] = g->d.V; info[5] = g->d.E; info[6] = g->max_indeg; info[7] = 0;
+    return HSPF_OK;
 }
 
 int hspf_debug_quad_image(const hspf_csr *g, uint32_t hdr[8], uint32_t *fq, uint32_t *fcont, uint16_t *slot_of,

@@ -9,8 +9,11 @@
 //
 // exported with cudaIpcGetMemHandle and opened by every peer.  The batch kernel of rank r
 // writes its result planes straight into slot r of its own buffer k; hspf_xchg_push(k) then
-// copies that slot into slot r of buffer k of every peer with the copy engines and, behind
-// each copy on the same stream, a 4-byte sequence number into the peer's `arrived` flag.
+// copies that slot (or its first push_bytes) into slot r of buffer k of every peer with the copy
+// engines — one stream per peer, so the copies to different peers run on different engines —
+// and, behind each copy on the same stream, a 4-byte sequence number into the peer's `arrived`
+// flag (written into a local staging word with a 32-bit memset, then copied: any 32-bit value,
+// no limit on the number of pushes).
 // No SM is involved, so the persistent batch kernel of the next step runs at full width
 // while the planes travel (an NCCL all-gather needs CTAs, which that kernel does not leave).
 // Consumers wait with stream memory operations (cuStreamWaitValue32), which need no SM
@@ -32,9 +35,8 @@
 
 namespace {
 
-constexpr uint32_t kSeqTable = 1u << 16;   // device table of the values 1..65536 (flag copy sources)
-
 typedef CUresult (*wait_value_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*memset32_fn)(CUdeviceptr, unsigned int, size_t, CUstream);
 
 }  // namespace
 
@@ -44,14 +46,23 @@ struct hspf_xchg {
     size_t slot_bytes = 0, data_bytes = 0, total_bytes = 0;
     uint8_t *local = nullptr;                 // own allocation
     std::vector<uint8_t *> peer;              // [world] mapped base of every rank (own = local)
-    uint32_t *seq_table = nullptr;            // device: 1..kSeqTable
+    std::vector<bool> peer_is_ipc;            // opened with cudaIpcOpenMemHandle (to be closed)
+    uint32_t *stage = nullptr;                // device: [2][n_buffers][world] staging words of the flag copies
     std::vector<uint32_t> seq;                // [n_buffers] pushes done on buffer k
     std::vector<uint32_t> released;           // [n_buffers] releases done on buffer k
+    size_t push_bytes = 0;                    // bytes of the own slot that travel (<= slot_bytes)
     cudaStream_t compute = nullptr;           // the engine's stream (hspf_stream)
-    cudaStream_t push_stream = nullptr, consume_stream = nullptr;
-    std::vector<cudaEvent_t> kernel_done, push_done, consumed;   // [n_buffers]
+    std::vector<cudaStream_t> push_streams;   // [world] one per peer (own: unused)
+    cudaStream_t consume_stream = nullptr;
+    std::vector<cudaEvent_t> kernel_done, consumed;              // [n_buffers]
+    std::vector<cudaEvent_t> push_done;                           // [n_buffers * world]
     wait_value_fn wait_value = nullptr;
+    memset32_fn memset32 = nullptr;
+    unsigned int wait_flags = CU_STREAM_WAIT_VALUE_GEQ;
     std::string err;
+
+    uint32_t *stage_arrived(uint32_t k, uint32_t r) const { return stage + (size_t)k * world + r; }
+    uint32_t *stage_acked(uint32_t k, uint32_t r) const { return stage + (size_t)(n_buffers + k) * world + r; }
 
     uint32_t *arrived(uint8_t *base, uint32_t k, uint32_t r) const {
         return reinterpret_cast<uint32_t *>(base + data_bytes) + (size_t)k * world + r;
@@ -98,24 +109,27 @@ int hspf_xchg_create(hspf_ctx *ctx, int device, uint32_t rank, uint32_t world, s
     if (cudaSetDevice(device) != cudaSuccess) return bail(HSPF_E_CUDA);
     if (cudaMalloc(&x->local, x->total_bytes) != cudaSuccess) return bail(HSPF_E_NOMEM);
     if (cudaMemset(x->local, 0, x->total_bytes) != cudaSuccess) return bail(HSPF_E_CUDA);
-    if (cudaMalloc(&x->seq_table, kSeqTable * sizeof(uint32_t)) != cudaSuccess) return bail(HSPF_E_NOMEM);
-    {
-        std::vector<uint32_t> t(kSeqTable);
-        for (uint32_t i = 0; i < kSeqTable; ++i) t[i] = i + 1;
-        if (cudaMemcpy(x->seq_table, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(HSPF_E_CUDA);
-    }
-    if (cudaStreamCreateWithFlags(&x->push_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HSPF_E_CUDA);
+    x->push_bytes = x->slot_bytes;
+    if (cudaMalloc(&x->stage, (size_t)2 * n_buffers * world * sizeof(uint32_t)) != cudaSuccess) return bail(HSPF_E_NOMEM);
+    x->push_streams.assign(world, nullptr);
+    for (uint32_t r = 0; r < world; ++r)
+        if (r != rank && cudaStreamCreateWithFlags(&x->push_streams[r], cudaStreamNonBlocking) != cudaSuccess)
+            return bail(HSPF_E_CUDA);
     if (cudaStreamCreateWithFlags(&x->consume_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HSPF_E_CUDA);
-    x->kernel_done.resize(n_buffers); x->push_done.resize(n_buffers); x->consumed.resize(n_buffers);
+    x->kernel_done.resize(n_buffers); x->consumed.resize(n_buffers);
+    x->push_done.assign((size_t)n_buffers * world, nullptr);
     for (uint32_t k = 0; k < n_buffers; ++k) {
         if (cudaEventCreateWithFlags(&x->kernel_done[k], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&x->push_done[k], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->consumed[k], cudaEventDisableTiming) != cudaSuccess)
             return bail(HSPF_E_CUDA);
+        for (uint32_t r = 0; r < world; ++r)
+            if (r != rank && cudaEventCreateWithFlags(&x->push_done[(size_t)k * world + r], cudaEventDisableTiming) != cudaSuccess)
+                return bail(HSPF_E_CUDA);
     }
     x->seq.assign(n_buffers, 0);
     x->released.assign(n_buffers, 0);
     x->peer.assign(world, nullptr);
+    x->peer_is_ipc.assign(world, false);
     x->peer[rank] = x->local;
     // stream memory operations through the runtime's driver entry point (libcuda is not linked,
     // so the library still loads on a machine without a driver)
@@ -127,6 +141,19 @@ int hspf_xchg_create(hspf_ctx *ctx, int device, uint32_t rank, uint32_t world, s
         return HSPF_E_UNSUPPORTED;
     }
     x->wait_value = reinterpret_cast<wait_value_fn>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuMemsetD32Async", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) {
+        hspf_xchg_destroy(x);
+        return HSPF_E_UNSUPPORTED;
+    }
+    x->memset32 = reinterpret_cast<memset32_fn>(fn);
+    // A consumer sees a peer's data only through the polled flag.  The design relies on a peer
+    // copy being visible at the destination before the next copy of the same stream (the flag)
+    // lands; where the device can flush remote writes the waits ask for it as well.
+    int can_flush = 0;
+    if (cudaDeviceGetAttribute(&can_flush, cudaDevAttrCanFlushRemoteWrites, device) == cudaSuccess && can_flush)
+        x->wait_flags |= CU_STREAM_WAIT_VALUE_FLUSH;
     cudaIpcMemHandle_t h;
     if (cudaIpcGetMemHandle(&h, x->local) != cudaSuccess) return bail(HSPF_E_CUDA);
     std::memcpy(handle, &h, sizeof(h));
@@ -143,6 +170,28 @@ int hspf_xchg_attach(hspf_xchg *x, uint32_t peer_rank, const uint8_t handle[HSPF
     void *p = nullptr;
     XCK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     x->peer[peer_rank] = static_cast<uint8_t *>(p);
+    x->peer_is_ipc[peer_rank] = true;
+    return HSPF_OK;
+}
+
+/* Attach a peer whose allocation is addressable in THIS process (hspf_xchg_base of an exchange
+ * created by the same process, e.g. two contexts on one device or on two devices with peer
+ * access enabled): tests and single-process deployments. */
+int hspf_xchg_attach_ptr(hspf_xchg *x, uint32_t peer_rank, void *peer_base) {
+    if (!x || !peer_base || peer_rank >= x->world) return HSPF_E_INVAL;
+    if (peer_rank == x->rank) return HSPF_OK;
+    x->peer[peer_rank] = static_cast<uint8_t *>(peer_base);
+    x->peer_is_ipc[peer_rank] = false;
+    return HSPF_OK;
+}
+
+void *hspf_xchg_base(hspf_xchg *x) { return x ? x->local : nullptr; }
+
+/* Only the first `nbytes` of the own slot travel in hspf_xchg_push (e.g. the planes the caller's
+ * Vertex keeps, laid out first).  0 or more than the slot = the whole slot. */
+int hspf_xchg_set_push_bytes(hspf_xchg *x, size_t nbytes) {
+    if (!x) return HSPF_E_INVAL;
+    x->push_bytes = (nbytes == 0 || nbytes > x->slot_bytes) ? x->slot_bytes : nbytes;
     return HSPF_OK;
 }
 
@@ -160,7 +209,9 @@ const char *hspf_xchg_last_error(const hspf_xchg *x) { return x ? x->err.c_str()
  * consumer has released the buffer. */
 int hspf_xchg_acquire(hspf_xchg *x, uint32_t buffer) {
     if (!x || buffer >= x->n_buffers) return HSPF_E_INVAL;
-    if (x->seq[buffer]) XCK(cudaStreamWaitEvent(x->compute, x->push_done[buffer], 0));
+    if (x->seq[buffer])
+        for (uint32_t r = 0; r < x->world; ++r)
+            if (r != x->rank) XCK(cudaStreamWaitEvent(x->compute, x->push_done[(size_t)buffer * x->world + r], 0));
     // ... and until the local consumer has released it (it reads the own slot too)
     if (x->released[buffer]) XCK(cudaStreamWaitEvent(x->compute, x->consumed[buffer], 0));
     return HSPF_OK;
@@ -172,24 +223,27 @@ int hspf_xchg_push(hspf_xchg *x, uint32_t buffer) {
     for (uint32_t r = 0; r < x->world; ++r)
         if (!x->peer[r]) return xfail(x, HSPF_E_INVAL, "hspf_xchg_push before every peer is attached");
     const uint32_t k = buffer, me = x->rank;
-    const uint32_t s = ++x->seq[k];
-    if (s > kSeqTable) return xfail(x, HSPF_E_UNSUPPORTED, "more than 65536 pushes on one buffer");
+    const uint32_t s = x->seq[k] + 1;
     XCK(cudaEventRecord(x->kernel_done[k], x->compute));
-    XCK(cudaStreamWaitEvent(x->push_stream, x->kernel_done[k], 0));
     for (uint32_t d = 1; d < x->world; ++d) {
         const uint32_t r = (me + d) % x->world;      // every rank starts with a different peer
+        cudaStream_t ps = x->push_streams[r];
+        XCK(cudaStreamWaitEvent(ps, x->kernel_done[k], 0));
         if (s > 1) {   // the peer must have released what it read from the previous push
-            CUresult cr = x->wait_value(reinterpret_cast<CUstream>(x->push_stream),
+            CUresult cr = x->wait_value(reinterpret_cast<CUstream>(ps),
                                         reinterpret_cast<CUdeviceptr>(x->acked(x->local, k, r)), s - 1,
                                         CU_STREAM_WAIT_VALUE_GEQ);
             if (cr != CUDA_SUCCESS) return xfail(x, HSPF_E_CUDA, "cuStreamWaitValue32(acked) failed");
         }
-        XCK(cudaMemcpyAsync(x->slot(x->peer[r], k, me), x->slot(x->local, k, me), x->slot_bytes,
-                            cudaMemcpyDeviceToDevice, x->push_stream));
-        XCK(cudaMemcpyAsync(x->arrived(x->peer[r], k, me), x->seq_table + (s - 1), sizeof(uint32_t),
-                            cudaMemcpyDeviceToDevice, x->push_stream));
+        XCK(cudaMemcpyAsync(x->slot(x->peer[r], k, me), x->slot(x->local, k, me), x->push_bytes,
+                            cudaMemcpyDeviceToDevice, ps));
+        if (x->memset32(reinterpret_cast<CUdeviceptr>(x->stage_arrived(k, r)), s, 1, reinterpret_cast<CUstream>(ps)) != CUDA_SUCCESS)
+            return xfail(x, HSPF_E_CUDA, "cuMemsetD32Async(flag) failed");
+        XCK(cudaMemcpyAsync(x->arrived(x->peer[r], k, me), x->stage_arrived(k, r), sizeof(uint32_t),
+                            cudaMemcpyDeviceToDevice, ps));
+        XCK(cudaEventRecord(x->push_done[(size_t)k * x->world + r], ps));
     }
-    XCK(cudaEventRecord(x->push_done[k], x->push_stream));
+    x->seq[k] = s;
     return HSPF_OK;
 }
 
@@ -202,8 +256,7 @@ int hspf_xchg_wait(hspf_xchg *x, uint32_t buffer) {
     for (uint32_t r = 0; r < x->world; ++r) {
         if (r == x->rank) continue;
         CUresult cr = x->wait_value(reinterpret_cast<CUstream>(x->consume_stream),
-                                    reinterpret_cast<CUdeviceptr>(x->arrived(x->local, k, r)), s,
-                                    CU_STREAM_WAIT_VALUE_GEQ);
+                                    reinterpret_cast<CUdeviceptr>(x->arrived(x->local, k, r)), s, x->wait_flags);
         if (cr != CUDA_SUCCESS) return xfail(x, HSPF_E_CUDA, "cuStreamWaitValue32(arrived) failed");
     }
     // own slot: the batch that produced it
@@ -219,7 +272,10 @@ int hspf_xchg_release(hspf_xchg *x, uint32_t buffer) {
     x->released[k] = s;
     for (uint32_t d = 1; d < x->world; ++d) {
         const uint32_t r = (x->rank + d) % x->world;
-        XCK(cudaMemcpyAsync(x->acked(x->peer[r], k, x->rank), x->seq_table + (s - 1), sizeof(uint32_t),
+        if (x->memset32(reinterpret_cast<CUdeviceptr>(x->stage_acked(k, r)), s, 1,
+                        reinterpret_cast<CUstream>(x->consume_stream)) != CUDA_SUCCESS)
+            return xfail(x, HSPF_E_CUDA, "cuMemsetD32Async(ack) failed");
+        XCK(cudaMemcpyAsync(x->acked(x->peer[r], k, x->rank), x->stage_acked(k, r), sizeof(uint32_t),
                             cudaMemcpyDeviceToDevice, x->consume_stream));
     }
     XCK(cudaEventRecord(x->consumed[k], x->consume_stream));
@@ -231,7 +287,8 @@ void *hspf_xchg_consumer_stream(hspf_xchg *x) { return x ? x->consume_stream : n
 /* Block the host until every push and every consumer operation enqueued so far is done. */
 int hspf_xchg_sync(hspf_xchg *x) {
     if (!x) return HSPF_E_INVAL;
-    XCK(cudaStreamSynchronize(x->push_stream));
+    for (cudaStream_t ps : x->push_streams)
+        if (ps) XCK(cudaStreamSynchronize(ps));
     XCK(cudaStreamSynchronize(x->consume_stream));
     return HSPF_OK;
 }
@@ -239,16 +296,16 @@ int hspf_xchg_sync(hspf_xchg *x) {
 int hspf_xchg_destroy(hspf_xchg *x) {
     if (!x) return HSPF_OK;
     cudaSetDevice(x->device);
-    if (x->push_stream) cudaStreamSynchronize(x->push_stream);
+    for (cudaStream_t ps : x->push_streams) if (ps) cudaStreamSynchronize(ps);
     if (x->consume_stream) cudaStreamSynchronize(x->consume_stream);
     for (uint32_t r = 0; r < x->peer.size(); ++r)
-        if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+        if (r != x->rank && x->peer[r] && x->peer_is_ipc[r]) cudaIpcCloseMemHandle(x->peer[r]);
     for (auto e : x->kernel_done) if (e) cudaEventDestroy(e);
     for (auto e : x->push_done) if (e) cudaEventDestroy(e);
     for (auto e : x->consumed) if (e) cudaEventDestroy(e);
-    if (x->push_stream) cudaStreamDestroy(x->push_stream);
+    for (cudaStream_t ps : x->push_streams) if (ps) cudaStreamDestroy(ps);
     if (x->consume_stream) cudaStreamDestroy(x->consume_stream);
-    if (x->seq_table) cudaFree(x->seq_table);
+    if (x->stage) cudaFree(x->stage);
     if (x->local) cudaFree(x->local);
     delete x;
     return HSPF_OK;

@@ -47,7 +47,7 @@ constexpr int kMaxRootDeg = 256;   // non-HOP root neighbours tracked in smem
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kVfHop = 1u, kVfLeaf = 2u, kVfLeafUnlessRoot = 4u;
 constexpr uint32_t kGfNoHopTargetNoNh = 1u, kGfHopCount = 2u;
-constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u;
+constexpr uint32_t kJsSaturated = 1u, kJsTooManyAtoms = 2u, kJsOrder = 4u, kJsBadJob = 8u;   // HSPF_JS_*
 
 struct DevGraph {
     uint32_t V, E;
@@ -295,6 +295,17 @@ __global__ void __launch_bounds__(kThreads, 2) spf_batch_kernel(const BatchArgs 
         const uint32_t job = S.job;
         if (job >= a.n_jobs) break;
         const uint32_t root = a.roots[job];
+        {
+            // device-pointer callers are not validated on the host: a malformed job is flagged and skipped
+            uint32_t n_raw = 0;
+            if (a.ov_off) n_raw = a.ov_off[job + 1] - a.ov_off[job];
+            bool bad = root >= V || n_raw > (uint32_t)kMaxOv;
+            for (uint32_t k = 0; !bad && k < n_raw; ++k) bad = a.ov_edge[a.ov_off[job] + k] >= g.E;
+            if (bad) {
+                if (tid == 0) a.out_status[job] = kJsBadJob;
+                continue;
+            }
+        }
         const size_t jo = (size_t)job * V;
         uint16_t *o_hops = a.out_hops + jo;
         uint32_t *o_fp = a.out_fp + jo;

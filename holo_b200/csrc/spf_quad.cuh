@@ -35,6 +35,7 @@ namespace hspf {
 
 constexpr uint32_t kJsInvalid = 8u;   // HSPF_JS_INVALID
 constexpr uint32_t kJsInternal = 16u; // HSPF_JS_INTERNAL: a loop bound that cannot be reached was reached
+constexpr uint32_t kJsNarrow = 32u;   // HSPF_JS_NARROW: the job's result does not fit 16-bit planes
 constexpr int kQMaxRoot = 64;         // non-HOP root neighbours tracked (>= 64 atoms is refused anyway)
 
 struct QuadDev {
@@ -71,6 +72,7 @@ struct QuadArgs {
     uint32_t *out_status;
     uint32_t *job_counter;
     uint32_t sub_rounds;        // visits of a warp to its bitmap chunk per barrier-separated round (>= 1)
+    uint32_t narrow;            // 1: 16-bit result planes (hspf_result16): out_dist / out_fp / out_nh point at u16 arrays
     unsigned long long *prof;   // optional [gridDim][16] cycle counters
 };
 
@@ -165,11 +167,24 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             continue;
         }
         const size_t jo = (size_t)job * V;
+        const bool narrow = a.narrow != 0;
         uint32_t *o_dist = a.out_dist + jo;
         uint16_t *o_hops = a.out_hops + jo;
         uint32_t *o_fp = a.out_fp + jo;
         uint16_t *o_npar = a.out_npar + jo;
         uint64_t *o_nh = a.out_nh + jo;
+        uint16_t *o_dist16 = reinterpret_cast<uint16_t *>(a.out_dist) + jo;     // narrow planes (hspf_result16)
+        uint16_t *o_fp16 = reinterpret_cast<uint16_t *>(a.out_fp) + jo;
+        uint16_t *o_nh16 = reinterpret_cast<uint16_t *>(a.out_nh) + jo;
+        // the planes just written are read back in phase 3 (first parents, distances of ECMP parents)
+        auto ld_fp = [&](uint32_t v) -> uint32_t {
+            if (narrow) { const uint32_t f = __ldcg(&o_fp16[v]); return f == 0xFFFFu ? kInf : f; }
+            return __ldcg(&o_fp[v]);
+        };
+        auto ld_dist = [&](uint32_t v) -> uint32_t {
+            if (narrow) { const uint32_t d = __ldcg(&o_dist16[v]); return d == 0xFFFFu ? kInf : d; }
+            return __ldcg(&o_dist[v]);
+        };
 
         // ---- per-job init -----------------------------------------------------------
         {
@@ -419,7 +434,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
 
         // ======================= phase 2: ECMP parents, one thread per in-quad =============
         {
-            uint32_t sat_flag = 0;
+            uint32_t sat_flag = 0, narrow_flag = 0;
             const uint32_t NIQ = Q.NIQ, isteps = Q.isteps;
             // DAG predicate on the four records of one in-quad -> (count, best (dist, slot) parent)
             auto pull = [&](uint32_t i, const uint2 &m, const uint4 &r4, uint32_t &dv, uint32_t &cnt, uint32_t &bd, uint32_t &bs) {
@@ -471,8 +486,15 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     if (dv >= U) dv = kInf;                                   // unreached
                     if (v == root || dv == kInf) { cnt = 0; bs = kInf; }
                     if (dv != kInf && g.saturate_at && dv >= g.saturate_at) sat_flag = 1;
-                    o_dist[v] = dv;
-                    o_fp[v] = cnt ? (uint32_t)__ldg(&Q.vert_of[bs]) : kInf;
+                    const uint32_t fpv = cnt ? (uint32_t)__ldg(&Q.vert_of[bs]) : kInf;
+                    if (narrow) {
+                        if (dv != kInf && dv >= 0xFFFFu) narrow_flag = 1;      // does not fit; 0xFFFF means "not on the SPT"
+                        o_dist16[v] = (uint16_t)min(dv, 0xFFFFu);
+                        o_fp16[v] = (uint16_t)min(fpv, 0xFFFFu);
+                    } else {
+                        o_dist[v] = dv;
+                        o_fp[v] = fpv;
+                    }
                     o_npar[v] = (uint16_t)min(cnt, 0xFFFFu);
                     if (cnt >= 2) atomicOr(&ecmpbm[v >> 5], 1u << (v & 31));
                 }
@@ -496,6 +518,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 if (hb) emit_v(mb, dvb, cb, bsb);
             }
             if (sat_flag) atomicOr(&S.status, kJsSaturated);
+            if (narrow_flag) atomicOr(&S.status, kJsNarrow);
         }
         __syncthreads();
         HSPF_QMARK(2);   // parents
@@ -511,7 +534,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         // from the plane just written.
         // -- hops: sum of HOP flags over (root, v]; the root and unreached vertices are terminals
         for (uint32_t v = tid; v < Vp; v += T) {      // (padding words are terminals: no bounds checks in the rounds)
-            const uint32_t f = (v < V) ? __ldcg(&o_fp[v]) : kInf;
+            const uint32_t f = (v < V) ? ld_fp(v) : kInf;
             word[v] = (f == kInf) ? (v << 16) : ((f << 16) | (is_hop(v) ? 1u : 0u));
         }
         __syncthreads();
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         const uint32_t n_e = S.cnt[0];
         // DAG parents of an ECMP vertex are re-derived from the distance plane just written
         auto parents = [&](uint32_t x, auto &&f) {
-            const uint32_t dx = __ldcg(&o_dist[x]);
+            const uint32_t dx = ld_dist(x);
             for (uint32_t j = g.irow[x]; j < g.irow[x + 1]; ++j) {
                 uint32_t u, c;
                 if constexpr (kOv) {
@@ -592,7 +615,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                     const uint32_t r = g.iedge16[j];
                     u = r & 0xFFFFu; c = r >> 16;
                 }
-                const uint32_t du = __ldcg(&o_dist[u]);
+                const uint32_t du = ld_dist(u);
                 if (du != kInf && sat_add(du, c) == dx && !hops0(u)) f(u);
             }
         };
@@ -612,7 +635,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             for (uint32_t v = tid; v < Vp; v += T) {
                 uint32_t A = v;
                 if (v < V) {
-                    const uint32_t f = __ldcg(&o_fp[v]);
+                    const uint32_t f = ld_fp(v);
                     if (f != kInf && !is_ecmp(v)) A = hops0(f) ? root : f;
                 }
                 word[v] = A << 16;
@@ -642,7 +665,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 for (uint32_t i = tid; i < n_e; i += T) {
                     const uint32_t x = elist[i];
                     const uint32_t seeds = word[x] & 0xFFFFu;
-                    const uint32_t f = __ldcg(&o_fp[x]);      // an ECMP vertex has parents
+                    const uint32_t f = ld_fp(x);      // an ECMP vertex has parents
                     uint32_t nw;
                     if (hops0(f)) nw = (root << 16) | seeds;
                     else if (is_ecmp(f)) nw = (f << 16) | seeds;
@@ -681,12 +704,16 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 const uint32_t w = word[v], Tv = w >> 16;
                 uint32_t m = w;
                 if (Tv != root && Tv != v) m |= word[Tv];
-                const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
-                if (pass == 0) o_nh[v] = bits; else o_nh[v] |= bits;
+                if (narrow) {
+                    if (pass == 0) o_nh16[v] = (uint16_t)(m & 0xFFFFu);      // (more than 16 atoms: HSPF_JS_NARROW, set below)
+                } else {
+                    const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
+                    if (pass == 0) o_nh[v] = bits; else o_nh[v] |= bits;
+                }
             }
             __syncthreads();
         }
-        if (tid == 0) a.out_status[job] = S.status;
+        if (tid == 0) a.out_status[job] = S.status | ((narrow && n_atoms > 16u) ? kJsNarrow : 0u);
         HSPF_QMARK(4);   // next hops
     }
 }

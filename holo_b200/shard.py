@@ -96,6 +96,51 @@ class PeerExchange:
             raise RuntimeError(f"hspf_xchg_attach failed on some rank (local rc={rc}: {msg})")
         self.slot_bytes = int(lib.hspf_xchg_slot_bytes(self.handle))
 
+    @classmethod
+    def local_pair(cls, ctxs, device_index: int, slot_bytes: int, n_buffers: int = 2):
+        """Two exchanges of ONE process on one device, attached to each other by pointer
+        (hspf_xchg_attach_ptr): exercises the push / wait / release sequencing on a single GPU."""
+        import ctypes as C
+        xs = []
+        for rank, ctx in enumerate(ctxs):
+            x = cls.__new__(cls)
+            x.C, x.lib, x.rank, x.world, x.n_buffers = C, ctx.lib, rank, len(ctxs), n_buffers
+            lib = x.lib
+            lib.hspf_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32,
+                                             C.POINTER(C.c_void_p), C.c_char_p]
+            lib.hspf_xchg_attach_ptr.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+            lib.hspf_xchg_base.argtypes = [C.c_void_p]
+            lib.hspf_xchg_base.restype = C.c_void_p
+            lib.hspf_xchg_slot.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+            lib.hspf_xchg_slot.restype = C.c_void_p
+            lib.hspf_xchg_slot_bytes.argtypes = [C.c_void_p]
+            lib.hspf_xchg_slot_bytes.restype = C.c_size_t
+            lib.hspf_xchg_set_push_bytes.argtypes = [C.c_void_p, C.c_size_t]
+            for f in ("acquire", "push", "wait", "release"):
+                getattr(lib, "hspf_xchg_" + f).argtypes = [C.c_void_p, C.c_uint32]
+            lib.hspf_xchg_consumer_stream.argtypes = [C.c_void_p]
+            lib.hspf_xchg_consumer_stream.restype = C.c_void_p
+            lib.hspf_xchg_sync.argtypes = [C.c_void_p]
+            lib.hspf_xchg_destroy.argtypes = [C.c_void_p]
+            lib.hspf_xchg_last_error.argtypes = [C.c_void_p]
+            lib.hspf_xchg_last_error.restype = C.c_char_p
+            x.handle = C.c_void_p()
+            rc = lib.hspf_xchg_create(ctx.handle, device_index, rank, len(ctxs), slot_bytes, n_buffers,
+                                      C.byref(x.handle), C.create_string_buffer(64))
+            if rc != 0:
+                raise RuntimeError(f"hspf_xchg_create rc={rc}")
+            x.slot_bytes = int(lib.hspf_xchg_slot_bytes(x.handle))
+            xs.append(x)
+        for x in xs:
+            for y in xs:
+                if x is not y:
+                    x._ck(x.lib.hspf_xchg_attach_ptr(x.handle, y.rank, x.lib.hspf_xchg_base(y.handle)), "attach_ptr")
+        return xs
+
+    def set_push_bytes(self, nbytes: int):
+        self.lib.hspf_xchg_set_push_bytes.argtypes = [self.C.c_void_p, self.C.c_size_t]
+        self._ck(self.lib.hspf_xchg_set_push_bytes(self.handle, nbytes), "set_push_bytes")
+
     def last_error(self) -> str:
         return (self.lib.hspf_xchg_last_error(self.handle) or b"").decode()
 

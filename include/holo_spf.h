@@ -97,6 +97,7 @@ extern "C" {
                                        whose job arrays the host cannot see; host-pointer calls
                                        fail with HSPF_E_INVAL before anything runs            */
 
+#define HSPF_JS_NARROW         0x20u /* hspf_run_batch16 only: the result does not fit 16-bit planes */
 #define HSPF_JS_INTERNAL       0x10u /* a device loop hit a bound that cannot be reached on a
                                         valid graph (defensive; please report): planes undefined */
 
@@ -187,6 +188,28 @@ typedef struct hspf_result {
 
 #define HSPF_RUN_DEVICE_PTRS 0x1u
 
+/*
+ * The same results in 16-bit planes: 10 bytes per vertex instead of 20, or 6 when the
+ * caller skips first_parent / n_parents (holo-ospf keeps neither in its Vertex,
+ * holo-ospf/src/spf.rs:38-46; holo-isis does, spf.rs:76-86).  Half the bytes over PCIe in the
+ * host-pointer call and over NVLink in the multi-GPU exchange.  OSPF always fits: its
+ * distances are u16 (spf.rs:672) and a job whose distances reach 0xFFFF is HSPF_JS_SATURATED
+ * anyway.  Encoding: dist 0xFFFF = not on the SPT, first_parent 0xFFFF = none, nh_mask = atoms
+ * 0..15.  A job whose result does not fit (a distance >= 0xFFFF on a graph without
+ * saturate_at, or more than 16 first-hop atoms) gets HSPF_JS_NARROW and must be re-run through
+ * hspf_run_batch.  Graph requirements: fewer than 65535 vertices, link costs <= 65534, no
+ * HSPF_VF_LEAF* flags, no HSPF_GF_HOPCOUNT (hspf_graph_info tells); otherwise
+ * HSPF_E_UNSUPPORTED.  Any plane pointer may be NULL.
+ */
+typedef struct hspf_result16 {
+    uint16_t *dist;
+    uint16_t *hops;
+    uint16_t *first_parent;
+    uint16_t *n_parents;
+    uint16_t *nh_mask;
+    uint32_t *job_status;
+} hspf_result16;
+
 typedef struct hspf_ctx hspf_ctx;
 typedef struct hspf_graph hspf_graph;
 
@@ -211,6 +234,14 @@ int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs,
 int hspf_run_batch_async(hspf_ctx *ctx, const hspf_graph *g,
                          const hspf_jobs *jobs, const hspf_result *out);
 int hspf_sync(hspf_ctx *ctx);
+/* 16-bit planes (hspf_result16), same contracts as the two calls above. */
+int hspf_run_batch16(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs,
+                     const hspf_result16 *out, uint32_t flags);
+int hspf_run_batch16_async(hspf_ctx *ctx, const hspf_graph *g,
+                           const hspf_jobs *jobs, const hspf_result16 *out);
+/* info = {1 if the packed fast path (and so hspf_run_batch16) serves this graph, forward quads,
+ * in-quads, log2 of the bucket width, n_vertices, n_edges, largest in-degree, 0}. */
+int hspf_graph_info(const hspf_graph *g, uint32_t info[8]);
 /* The ctx's cudaStream_t (as void*) so callers can record CUDA events on it. */
 void *hspf_stream(hspf_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench `gpu_launches`). */
@@ -278,6 +309,13 @@ typedef struct hspf_xchg hspf_xchg;
 int hspf_xchg_create(hspf_ctx *ctx, int device, uint32_t rank, uint32_t world, size_t slot_bytes,
                      uint32_t n_buffers, hspf_xchg **out, uint8_t handle[HSPF_IPC_HANDLE_BYTES]);
 int hspf_xchg_attach(hspf_xchg *x, uint32_t peer_rank, const uint8_t handle[HSPF_IPC_HANDLE_BYTES]);
+/* Same-process peers (two contexts on one device, or devices with peer access): attach by the
+ * base pointer hspf_xchg_base() of the peer's exchange instead of an IPC handle. */
+int hspf_xchg_attach_ptr(hspf_xchg *x, uint32_t peer_rank, void *peer_base);
+void *hspf_xchg_base(hspf_xchg *x);
+/* Only the first nbytes of the own slot travel in hspf_xchg_push (0 = the whole slot): lay the
+ * planes the consumers need first.  Sequence numbers are 32 bits: no limit on the number of pushes. */
+int hspf_xchg_set_push_bytes(hspf_xchg *x, size_t nbytes);
 void *hspf_xchg_slot(hspf_xchg *x, uint32_t buffer, uint32_t slot);   /* device pointer, local copy */
 size_t hspf_xchg_slot_bytes(const hspf_xchg *x);                      /* slot_bytes rounded up to 256 */
 int hspf_xchg_acquire(hspf_xchg *x, uint32_t buffer);

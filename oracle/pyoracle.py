@@ -129,3 +129,58 @@ def isis_compute_routes(inst):
     L = lib()
     L.oracle_isis_compute_routes.argtypes = [C.POINTER(isis.InstanceStruct), C.POINTER(isis.RibStruct)]
     return isis._call_rib(L.oracle_isis_compute_routes, inst)
+
+
+def usable_cores() -> int:
+    """Cores this process may use (affinity mask capped by the cgroup CPU quota)."""
+    return int(lib().oracle_usable_cores())
+
+
+def effective_cores(threads: int = 0) -> float:
+    """Measured parallel throughput of `threads` threads in units of one core (batch_pool.cc)."""
+    L = lib()
+    L.oracle_effective_cores.restype = C.c_double
+    L.oracle_effective_cores.argtypes = [C.c_int]
+    return float(L.oracle_effective_cores(threads if threads > 0 else usable_cores()))
+
+
+def csr_batch(csr, roots, overrides=None, mode: str = "heap", vec_mode: int = 0, threads: int = 0,
+              stop_after_s: float = 0.0, nh_words: int = 1, want_planes: bool = True):
+    """Run a batch on a native thread pool (oracle/batch_pool.cc).  mode: "faithful" | "heap".
+    Returns a dict: planes [n, V] (when want_planes), status [n], jobs_done, seconds, checksum."""
+    L = lib()
+    V = csr.n_vertices
+    roots = np.ascontiguousarray(roots, dtype=np.uint32)
+    n = len(roots)
+    s = csr.as_struct()
+    off = ove = ovc = None
+    if overrides is not None:
+        off = np.zeros(n + 1, np.uint32)
+        ed, co = [], []
+        for j, ov in enumerate(overrides):
+            for e, c in ov:
+                ed.append(e); co.append(c)
+            off[j + 1] = len(ed)
+        ove = np.asarray(ed or [0], np.uint32)
+        ovc = np.asarray(co or [0], np.uint32)
+    out = {}
+    if want_planes:
+        out = dict(dist=np.empty((n, V), np.uint32), hops=np.empty((n, V), np.uint16),
+                   first_parent=np.empty((n, V), np.uint32), n_parents=np.empty((n, V), np.uint16),
+                   nh_mask=np.empty((n, V, nh_words), np.uint64))
+    status = np.zeros(n, np.uint32)
+    done, secs, chk = C.c_uint32(), C.c_double(), C.c_uint64()
+    if threads <= 0:
+        threads = usable_cores()
+    L.oracle_csr_batch.argtypes = [C.c_void_p, C.c_uint32, _u32p, _u32p, _u32p, _u32p, C.c_int, C.c_int, C.c_int,
+                                   C.c_double, C.c_uint32, _u32p, _u16p, _u32p, _u16p, _u64p, _u32p,
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    rc = L.oracle_csr_batch(C.cast(C.byref(s), C.c_void_p), n, _p(roots, _u32p), _p(off, _u32p), _p(ove, _u32p),
+                            _p(ovc, _u32p), 0 if mode == "faithful" else 1, vec_mode, threads, float(stop_after_s),
+                            nh_words, _p(out.get("dist"), _u32p), _p(out.get("hops"), _u16p),
+                            _p(out.get("first_parent"), _u32p), _p(out.get("n_parents"), _u16p),
+                            _p(out.get("nh_mask"), _u64p), _p(status, _u32p), C.byref(done), C.byref(secs), C.byref(chk))
+    if rc != 0:
+        raise RuntimeError(f"oracle_csr_batch rc={rc}")
+    out.update(status=status, jobs_done=done.value, seconds=secs.value, checksum=chk.value, threads=threads)
+    return out

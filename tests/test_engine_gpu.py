@@ -294,3 +294,115 @@ def test_atom_count_selects_the_next_hop_phase_per_job(ctx):
     for j, r in enumerate(roots):
         check(res, j, pyoracle.csr_spf(csr, int(r), nh_words=1))
     g.free()
+
+
+@pytest.mark.parametrize("V,E,seed,kw,isis", [
+    (100, 400, 3, {}, False),
+    (300, 1400, 6, dict(cost_choices=[10, 20], lan_fraction=0.1), False),
+    (3000, 12000, 9, dict(cost_choices=[10, 20, 30], lan_fraction=0.05), True),
+])
+def test_narrow_planes_equal_the_wide_ones(ctx, V, E, seed, kw, isis):
+    """hspf_run_batch16: the same results in 16-bit planes, skipped planes stay untouched."""
+    from holo_b200.capi import JS_NARROW
+    t = synth.random_topology(V, E, synth.SEED_BASE + seed, **kw)
+    csr = synth.topology_csr(t, isis=isis)
+    g = ctx.upload(csr)
+    assert ctx.graph_info(g)["fast_path"]
+    nv = csr.n_vertices
+    roots = np.arange(nv, dtype=np.uint32) if nv <= 300 else np.arange(0, nv, 37, dtype=np.uint32)
+    wide = ctx.run(g, roots, nh_words=1)
+    nar = ctx.run16(g, roots)
+    for j in range(len(roots)):
+        st = int(nar["job_status"][j])
+        if wide.job_status[j] == 0 and (wide.nh_mask[j] >> np.uint64(16)).any():
+            assert st & JS_NARROW          # more than 16 first-hop atoms in use: does not fit
+            continue
+        assert (st & ~JS_NARROW) == wide.job_status[j]
+        if st:
+            continue
+        d = wide.dist[j]
+        assert np.array_equal(nar["dist"][j], np.where(d == DIST_INF, 0xFFFF, d).astype(np.uint16))
+        assert np.array_equal(nar["hops"][j], wide.hops[j])
+        fp = wide.first_parent[j]
+        assert np.array_equal(nar["first_parent"][j], np.where(fp == 0xFFFFFFFF, 0xFFFF, fp).astype(np.uint16))
+        assert np.array_equal(nar["n_parents"][j], wide.n_parents[j])
+        assert np.array_equal(nar["nh_mask"][j], wide.nh_mask[j, :, 0].astype(np.uint16))
+    # OSPF caller: three planes only
+    part = ctx.run16(g, roots, planes=("dist", "hops", "nh_mask"))
+    assert np.array_equal(part["dist"], nar["dist"]) and np.array_equal(part["nh_mask"], nar["nh_mask"])
+    g.free()
+
+
+def test_narrow_planes_refused_off_the_fast_path(ctx):
+    t = synth.random_topology(60, 240, synth.SEED_BASE + 21, cost_lo=70000, cost_hi=70100)
+    csr = synth.topology_csr(t, isis=True)
+    g = ctx.upload(csr)
+    assert not ctx.graph_info(g)["fast_path"]
+    with pytest.raises(HspfError) as ei:
+        ctx.run16(g, np.asarray([0], np.uint32))
+    assert ei.value.code == -5
+    g.free()
+
+
+def test_device_pointer_jobs_are_validated_on_the_device(ctx):
+    """HSPF_RUN_DEVICE_PTRS: the host cannot see the job arrays; a bad root or override edge
+    flags its own job HSPF_JS_INVALID and the other jobs of the batch are unaffected."""
+    import ctypes as C
+    import torch
+    from holo_b200 import capi
+    t = synth.random_topology(200, 900, synth.SEED_BASE + 22)
+    csr = synth.topology_csr(t)
+    V = csr.n_vertices
+    for no_quad in (False, True):
+        import os
+        if no_quad:
+            os.environ["HSPF_NO_QUAD"] = "1"
+        try:
+            g = ctx.upload(csr)
+            roots = torch.tensor([0, V + 7, 5, 0xFFFFFFF], dtype=torch.int32, device="cuda")
+            n = 4
+            bufs = dict(dist=torch.full((n, V), -7, dtype=torch.int32, device="cuda"),
+                        hops=torch.zeros((n, V), dtype=torch.int16, device="cuda"),
+                        fp=torch.zeros((n, V), dtype=torch.int32, device="cuda"),
+                        npar=torch.zeros((n, V), dtype=torch.int16, device="cuda"),
+                        nh=torch.zeros((n, V), dtype=torch.int64, device="cuda"),
+                        st=torch.zeros((n,), dtype=torch.int32, device="cuda"))
+            js = capi.JobsStruct()
+            js.n_jobs = n
+            js.roots = C.cast(roots.data_ptr(), C.POINTER(C.c_uint32))
+            rs = capi.ResultStruct()
+            rs.dist = C.cast(bufs["dist"].data_ptr(), C.POINTER(C.c_uint32))
+            rs.hops = C.cast(bufs["hops"].data_ptr(), C.POINTER(C.c_uint16))
+            rs.first_parent = C.cast(bufs["fp"].data_ptr(), C.POINTER(C.c_uint32))
+            rs.n_parents = C.cast(bufs["npar"].data_ptr(), C.POINTER(C.c_uint16))
+            rs.nh_mask = C.cast(bufs["nh"].data_ptr(), C.POINTER(C.c_uint64))
+            rs.nh_words = 1
+            rs.job_status = C.cast(bufs["st"].data_ptr(), C.POINTER(C.c_uint32))
+            ctx.run_device(g, js, rs)
+            st = bufs["st"].cpu().numpy()
+            assert list(st) == [0, capi.JS_INVALID, 0, capi.JS_INVALID]
+            d = bufs["dist"].cpu().numpy().astype(np.uint32)
+            assert np.array_equal(d[0], pyoracle.csr_spf(csr, 0)["dist"])
+            assert np.array_equal(d[2], pyoracle.csr_spf(csr, 5)["dist"])
+            assert (bufs["dist"][1] == -7).all()          # skipped job: planes untouched
+            g.free()
+        finally:
+            os.environ.pop("HSPF_NO_QUAD", None)
+
+
+def test_reserved_sms_shrink_the_grid_and_small_batches_still_run(ctx):
+    """hspf_ctx_reserve_sms leaves SMs to a concurrent kernel by launching fewer persistent CTAs;
+    batches of 1..4 jobs must still be computed."""
+    t = synth.random_topology(300, 1300, synth.SEED_BASE + 23)
+    csr = synth.topology_csr(t)
+    g = ctx.upload(csr)
+    ctx.reserve_sms(40)
+    try:
+        for n in (1, 2, 3, 4, 300):
+            roots = np.arange(n, dtype=np.uint32)
+            res = ctx.run(g, roots)
+            for j in (0, n - 1):
+                check(res, j, pyoracle.csr_spf(csr, int(roots[j])))
+    finally:
+        ctx.reserve_sms(0)
+    g.free()

@@ -49,3 +49,27 @@ def test_isis_vec_lists():
         for x in a["nhvec"][no[v]:no[v + 1]]:
             s |= 1 << int(x)
         assert s == int(a["nh_mask"][v, 0])
+
+
+def test_native_batch_pool_matches_single_calls(built):
+    """oracle/batch_pool.cc: the thread pool returns the planes of the single-job calls, the
+    bounded sample stops early, and the checksum does not depend on the thread count."""
+    import numpy as np
+    from holo_b200 import synth
+    from oracle import pyoracle
+    t = synth.random_topology(300, 1400, synth.SEED_BASE + 41, lan_fraction=0.1)
+    csr = synth.topology_csr(t)
+    roots = np.arange(0, 300, 7, dtype=np.uint32)
+    a = pyoracle.csr_batch(csr, roots, mode="heap", threads=3)
+    b = pyoracle.csr_batch(csr, roots, mode="faithful", threads=2)
+    assert a["jobs_done"] == len(roots) == b["jobs_done"] and a["checksum"] == b["checksum"]
+    for j, r in enumerate(roots):
+        ref = pyoracle.csr_spf(csr, int(r))
+        for k in ("dist", "hops", "first_parent", "n_parents", "nh_mask"):
+            assert np.array_equal(a[k][j], ref[k]) and np.array_equal(b[k][j], ref[k]), (j, k)
+    c = pyoracle.csr_batch(csr, roots, mode="heap", threads=1, want_planes=False)
+    assert c["checksum"] == a["checksum"]
+    ov = [[(0, 0xFFFFFFFF)] if j % 2 else [] for j in range(len(roots))]
+    d = pyoracle.csr_batch(csr, roots, overrides=ov, mode="heap", threads=2)
+    assert np.array_equal(d["dist"][1], pyoracle.csr_spf_heap(csr, int(roots[1]), overrides=ov[1])["dist"])
+    assert pyoracle.usable_cores() >= 1 and 1.0 <= pyoracle.effective_cores(2) <= 2.0
