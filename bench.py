@@ -341,7 +341,10 @@ def run_ours(args):
     ctx = capi.Context(local_rank)
     graphs = [ctx.upload(w.csr) for w in works]
     fast = all(ctx.graph_info(g)["fast_path"] for g in graphs)
-    narrow = fast and args.planes == "16"
+    # 16-bit next-hop planes hold 16 first-hop atoms: a batch with a root that has more (a router on
+    # several LANs) runs with the 32/64-bit planes
+    max_atoms = max(max(capi.atom_count(w.csr, int(r)) for r in np.unique(w.roots)) for w in works)
+    narrow = fast and args.planes == "16" and max_atoms <= 16
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     al = lambda x: (x + 255) // 256 * 256
     bpv = ({"dist": 2, "hops": 2, "fp": 2, "npar": 2, "nh": 2} if narrow else
