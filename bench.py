@@ -532,7 +532,7 @@ def run_ours(args):
         """which: 'caller16' (what the protocol's caller keeps, 16-bit), 'all16', 'all32'.  Returns
         (SPF/s, h2d bytes, d2h bytes, steps) or None if not applicable."""
         use16 = which != "all32"
-        if use16 and not fast:
+        if use16 and not (fast and max_atoms <= 16):
             return None
         planes = ("dist", "hops", "nh") if (which == "caller16" and is_ospf) else ("dist", "hops", "fp", "npar", "nh")
         hbufs, calls, d2h, h2d = [], [], 0, 0
@@ -661,8 +661,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_main[0], "unit": UNIT, "h2d_bytes_per_step": e2e_main[1],
                     "d2h_bytes_per_step": e2e_main[2], "steps": e2e_main[3],
-                    "planes": ("distance, hops, next-hop set (what holo-ospf's Vertex keeps), 16-bit" if (fast and is_ospf) else
-                               "all five planes, 16-bit" if fast else "all five planes, 32/64-bit"),
+                    "planes": ("distance, hops, next-hop set (what holo-ospf's Vertex keeps), 16-bit" if (fast and is_ospf and max_atoms <= 16) else
+                               "all five planes, 16-bit" if (fast and max_atoms <= 16) else "all five planes, 32/64-bit"),
                     "variants": e2e_extra or None},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
