@@ -486,3 +486,87 @@ def rib_diff(old, new: IsisRib, lib=None, name="hspf_isis_rib_diff"):
     if rc != capi.HSPF_OK:
         raise capi.HspfError(rc, name + " failed")
     return acts[: n.value].copy(), new_routes
+
+
+# ---- L1/L2 routers: summary routes and L1 -> L2 propagation (holo-isis route.rs:189-231, lsdb.rs:1149-1357)
+SUMMARY_DT = np.dtype([("prefix", IP_DT), ("cfg_metric", "<u4"), ("metric", "<u4"), ("len", "u1"),
+                       ("has_cfg_metric", "u1"), ("_pad", "u1", (2,))], align=True)
+ROUTE_SUMMARY = 0x04
+
+
+def summary_cfg(entries) -> np.ndarray:
+    """[(prefix string, metric or None), ...] -> SUMMARY_DT records in prefix order."""
+    import ipaddress
+    from . import ospfv3
+    recs = []
+    for p, m in entries:
+        net = ipaddress.ip_network(p, strict=False)
+        recs.append((ospfv3.ip_rec(net.network_address), 0 if m is None else int(m), 0, net.prefixlen, int(m is not None), (0, 0)))
+    a = np.zeros(len(recs), SUMMARY_DT)
+    for i, r in enumerate(recs):
+        a[i] = r
+    order = sorted(range(len(a)), key=lambda i: (int(a[i]["prefix"]["is_v6"]), bytes(a[i]["prefix"]["bytes"]), int(a[i]["len"])))
+    return a[order] if len(a) else a
+
+
+def summaries(l1_rib, cfg: np.ndarray, lib=None, name="hspf_isis_summaries") -> np.ndarray:
+    """Active summaries of an L1 table (the L1 half of update_rib)."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    keep = []
+    s1 = _rib_struct(l1_rib, keep) if l1_rib is not None else None
+    cfg = np.ascontiguousarray(cfg, dtype=SUMMARY_DT)
+    out = np.zeros(max(len(cfg), 1), SUMMARY_DT)
+    n = C.c_uint32()
+    rc = fn(C.addressof(s1) if s1 is not None else None, cfg.ctypes.data if len(cfg) else None, len(cfg), out.ctypes.data,
+            C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return out[: n.value].copy()
+
+
+def rib_add_summaries(l2_rib, active: np.ndarray, lib=None, name="hspf_isis_rib_add_summaries") -> IsisRib:
+    """The L2 table with the active summaries as next-hop-less ROUTE_SUMMARY routes."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(RibStruct)]
+    keep = []
+    s2 = _rib_struct(l2_rib, keep) if l2_rib is not None else None
+    active = np.ascontiguousarray(active, dtype=SUMMARY_DT)
+    n_r = (len(l2_rib.routes) if l2_rib is not None else 0) + len(active)
+    n_h = len(l2_rib.nexthops) if l2_rib is not None else 0
+    routes, nhs = np.zeros(max(n_r, 1), ROUTE_DT), np.zeros(max(n_h, 1), NEXTHOP_DT)
+    r = RibStruct()
+    r.routes_cap, r.routes = len(routes), routes.ctypes.data
+    r.nexthops_cap, r.nexthops = len(nhs), nhs.ctypes.data
+    rc = fn(C.addressof(s2) if s2 is not None else None, active.ctypes.data if len(active) else None, len(active), C.byref(r))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return IsisRib(routes[: r.n_routes].copy(), nhs[: r.n_nexthops].copy(), rc)
+
+
+def l1_to_l2(level: IsisLevel, local_system_id: int, spt_std: IsisSpt, spt_v6, l1_metric_type: int, l2_metric_type: int,
+             cfg: np.ndarray, active: np.ndarray, up_down=None, lib=None, name="hspf_isis_l1_to_l2") -> np.ndarray:
+    """lsp_propagate_l1_to_l2: the IP reachability entries an L1/L2 router adds to its L2 LSP."""
+    lib = lib or capi.load_library()
+    fn = getattr(lib, name)
+    fn.argtypes = [C.POINTER(LevelStruct), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint8, C.c_uint8,
+                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    ls = level.as_struct()
+    s_std = _spt_struct(spt_std, keep)
+    s_v6 = _spt_struct(spt_v6, keep) if spt_v6 is not None else None
+    cfg = np.ascontiguousarray(cfg, dtype=SUMMARY_DT)
+    active = np.ascontiguousarray(active, dtype=SUMMARY_DT)
+    ud = np.ascontiguousarray(up_down, dtype=np.uint8) if up_down is not None else None
+    cap = len(level.ipreaches) + 3 * len(active) + 1
+    out = np.zeros(cap, IPREACH_DT)
+    n = C.c_uint32()
+    rc = fn(C.byref(ls), ud.ctypes.data if ud is not None else None, local_system_id, C.addressof(s_std),
+            C.addressof(s_v6) if s_v6 is not None else None, l1_metric_type, l2_metric_type,
+            cfg.ctypes.data if len(cfg) else None, len(cfg), active.ctypes.data if len(active) else None, len(active),
+            out.ctypes.data, cap, C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return out[: n.value].copy()

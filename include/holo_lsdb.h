@@ -289,6 +289,8 @@ typedef struct hl_rib_route {
 } hl_rib_route;
 
 #define HL_ROUTE_INSTALLED 0x02u   /* RouteNetFlags::INSTALLED (route.rs:50-55) */
+#define HL_ROUTE_SUMMARY   0x04u   /* holo-isis RouteFlags::SUMMARY (route.rs:40-46): active L1->L2 summary,
+                                      installed as a blackhole route without next hops */
 
 /* One message to the RIB manager produced by update_global_rib (route.rs:833-893). */
 #define HL_RIB_INSTALL        1u   /* ibus route_install of new_rib.routes[route]                   */
@@ -704,6 +706,18 @@ typedef struct hl_isis_route {
     uint32_t n_nh;
     uint32_t sr_label;      /* input label (Route.sr_label) when has_sr_label */
 } hl_isis_route;
+
+/* One configured L1->L2 summary prefix (instance.config.summaries, SummaryCfg:
+ * holo-isis/src/northbound/configuration.rs:225-227), and an ACTIVE summary (SummaryRoute,
+ * route.rs:72-75): `metric` = the lowest metric of the contributing L1 routes. */
+typedef struct hl_isis_summary {
+    hl_ip_addr prefix;
+    uint32_t cfg_metric;    /* SummaryCfg.metric when has_cfg_metric */
+    uint32_t metric;        /* active summaries only: lowest contributing metric */
+    uint8_t  len;
+    uint8_t  has_cfg_metric;
+    uint8_t  _pad[2];
+} hl_isis_summary;
 
 typedef struct hl_isis_rib {
     uint32_t routes_cap,   n_routes;    hl_isis_route *routes;

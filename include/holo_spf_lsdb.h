@@ -170,10 +170,40 @@ int hspf_isis_routes_from_planes(const hl_isis_instance *inst, const uint32_t *d
  * installs / uninstalls for the RIB manager (a route is reinstalled unless metric and the
  * next-hop set — labels included — are unchanged; connected routes and routes without next hops
  * are never installed; hl_isis_route.flags receive HL_ROUTE_INSTALLED).  Either level may be
- * NULL; `old_rib` may be NULL.  Summary (blackhole) routes are not modelled.  Host only. */
+ * NULL; `old_rib` may be NULL.  Summary routes (HL_ROUTE_SUMMARY, no next hops) are installed
+ * (route.rs:284-288).  Host only. */
 int hspf_isis_rib_merge(const hl_isis_rib *l2, const hl_isis_rib *l1, hl_isis_rib *out);
 int hspf_isis_rib_diff(const hl_isis_rib *old_rib, hl_isis_rib *new_rib, hl_rib_action *out, uint32_t cap,
                        uint32_t *n_out);
+
+/* L1/L2 routers: summary routes and the L1 -> L2 propagation that uses the L1 SPT distances
+ * (holo-isis/src/route.rs:189-231, lsdb.rs:1149-1357).  Host only.
+ *
+ *   hspf_isis_summaries        <->  the L1 half of update_rib (route.rs:193-216): every L1 route
+ *       covered by a configured summary (shortest-prefix match, JointPrefixMap::get_spm of the
+ *       prefix-trie crate) makes that summary active; its metric is the lowest covered metric.
+ *       `cfg` in prefix order; `out` (capacity n_cfg) in prefix order.
+ *   hspf_isis_rib_add_summaries <-> the L2 half (route.rs:218-229): the active summaries join the
+ *       L2 table as routes without next hops, flag HL_ROUTE_SUMMARY, type L2 intra-area, metric =
+ *       the configured one if set, else the lowest covered (SummaryRoute::metric).  A summary
+ *       replaces an L2 route of the same prefix (BTreeMap::extend).
+ *   hspf_isis_l1_to_l2         <->  lsp_propagate_l1_to_l2: the IP reachability of the other
+ *       systems' valid non-pseudonode L1 LSPs, metric + L1 SPT distance to the originator
+ *       (saturating; narrow TLVs capped at 63), up/down entries and entries covered by a configured
+ *       summary left out, the lowest total metric kept per prefix and TLV kind, Prefix-SIDs with
+ *       R and P set and E cleared; then one entry per active summary.  `spt_std` / `spt_v6` are
+ *       the L1 SPTs of the standard / IPv6-unicast topology (hspf_isis_compute_spt or
+ *       hspf_isis_spt_from_planes; spt_v6 NULL: no MT); a system that is not on the SPT
+ *       propagates nothing.  `up_down` (may be NULL): one byte per entry of l1->ipreaches, non-zero = the
+ *       entry's up/down bit is set.  Output entries ordered by (kind, prefix). */
+int hspf_isis_summaries(const hl_isis_rib *l1, const hl_isis_summary *cfg, uint32_t n_cfg, hl_isis_summary *out,
+                        uint32_t *n_out);
+int hspf_isis_rib_add_summaries(const hl_isis_rib *l2, const hl_isis_summary *active, uint32_t n_active,
+                                hl_isis_rib *out);
+int hspf_isis_l1_to_l2(const hl_isis_level *l1, const uint8_t *up_down, uint64_t local_system_id,
+                       const hl_isis_spt *spt_std, const hl_isis_spt *spt_v6, uint8_t l1_metric_type, uint8_t l2_metric_type,
+                       const hl_isis_summary *cfg, uint32_t n_cfg, const hl_isis_summary *active, uint32_t n_active,
+                       hl_isis_ipreach *out, uint32_t cap, uint32_t *n_out);
 
 /* ---- IS-IS flooding reduction over the hop-count SPTs of the neighbour batch ------------
  * (holo-isis/src/flooding/manet.rs).  manet::init_cache runs one hop-count

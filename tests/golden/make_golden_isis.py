@@ -25,6 +25,15 @@ def _pfx(lsp, key, metric_of):
             for p in (lsp.get(key) or {}).get("prefixes", [])]
 
 
+def _updown(lsp):
+    """prefixes of this LSP whose up/down bit is set (never propagated L1 -> L2, lsdb.rs:1331)"""
+    out = []
+    for key in ("ipv4-internal-reachability", "ipv4-external-reachability", "extended-ipv4-reachability",
+                "ipv6-reachability", "mt-ipv6-reachability"):
+        out += [f"{p['ip-prefix']}/{p['prefix-len']}" for p in (lsp.get(key) or {}).get("prefixes", []) if p.get("up-down")]
+    return out
+
+
 # Step tests: the state the reference reached after the step (full database, interfaces and
 # adjacencies in <step>/<NN>-output-northbound-state.json) is one more snapshot; the table computed
 # from it, diffed against the table of the topology snapshot, must give the step's ibus output
@@ -53,6 +62,14 @@ ISIS_STEPS = [
     ("pdu-lsp-att-bit1", "topo1-2", "rt7", "02", {}),
     ("pdu-lsp-expiration1", "topo2-1", "rt6", "02", {}),
     ("pdu-lsp-overload1", "topo2-1", "rt6", "02", {}),
+]
+
+# L1 -> L2 summary routes of an L1/L2 router (holo-isis/src/route.rs:189-231): chains of steps, each
+# diffed against the state before it.  (test, topology, router, [(step, configured summaries
+# [[prefix, metric or null]], ...)]).
+ISIS_SUMMARY_CHAINS = [
+    ("nb-config-summary1", "topo1-2", "rt2", [("01", [["1.0.0.0/8", None]]), ("02", [["1.0.0.0/8", 100]]), ("04", [])]),
+    ("nb-config-summary2", "topo1-2", "rt2", [("01", [["1.0.0.0/8", None]]), ("03", [["1.0.0.0/8", None]])]),
 ]
 
 
@@ -91,6 +108,7 @@ def snapshot(rt: Path, state_path: Path, overrides=None):
                 "ext_ipv4": _pfx(l, "extended-ipv4-reachability", lambda x: x["metric"]),
                 "ipv6": _pfx(l, "ipv6-reachability", lambda x: x["metric"]),
                 "mt_ipv6": _pfx(l, "mt-ipv6-reachability", lambda x: x["metric"]),
+                "updown": _updown(l),
             })
         snap["levels"].append({"level": lv["level"], "lsps": lsps})
     for i in o.get("interfaces", {}).get("interface", []):
@@ -161,5 +179,17 @@ def extract_isis(ref: Path):
                 after = snapshot(rt, sd / f"{nn}-output-northbound-state.json", ov)
                 after["ibus"] = ibus_stream(sd / f"{nn}-output-ibus.jsonl")
                 snap["after"][name] = after
+            snap["summary_chains"] = {}
+            for (name, t, r, chain) in ISIS_SUMMARY_CHAINS:
+                if (t, r) != (topo.name, rt.name):
+                    continue
+                sd = ref / "holo-isis/tests/conformance" / name
+                steps = []
+                for nn, summ in chain:
+                    st_ = snapshot(rt, sd / f"{nn}-output-northbound-state.json")
+                    st_["summaries"] = summ
+                    st_["ibus"] = ibus_stream(sd / f"{nn}-output-ibus.jsonl")
+                    steps.append(st_)
+                snap["summary_chains"][name] = steps
             out.append(snap)
     return out
