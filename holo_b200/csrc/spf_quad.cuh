@@ -73,6 +73,8 @@ struct QuadArgs {
     uint32_t *job_counter;
     uint32_t sub_rounds;        // visits of a warp to its bitmap chunk per barrier-separated round (>= 1)
     uint32_t narrow;            // 1: 16-bit result planes (hspf_result16): out_dist / out_fp / out_nh point at u16 arrays
+    uint32_t *done;             // optional: done[job / done_chunk] counts finished jobs (release: planes first), so
+    uint32_t done_chunk;        // that the host call can copy a chunk's planes back while the launch still runs
     unsigned long long *prof;   // optional [gridDim][16] cycle counters
 };
 
@@ -163,7 +165,10 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         uint32_t n_ov_raw = 0;
         if (kOv && a.ov_off) n_ov_raw = a.ov_off[job + 1] - a.ov_off[job];
         if (root >= V || n_ov_raw > (uint32_t)kMaxOv) {      // device-pointer callers are not validated on the host
-            if (tid == 0) a.out_status[job] = kJsInvalid;
+            if (tid == 0) {
+                a.out_status[job] = kJsInvalid;
+                if (a.done) { __threadfence(); atomicAdd(&a.done[job / a.done_chunk], 1u); }
+            }
             continue;
         }
         const size_t jo = (size_t)job * V;
@@ -714,6 +719,12 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             __syncthreads();
         }
         if (tid == 0) a.out_status[job] = S.status | ((narrow && n_atoms > 16u) ? kJsNarrow : 0u);
+        if (a.done) {
+            // every plane of this job is written: publish (barrier: the other threads' stores happen
+            // before thread 0's fence; fence: before the count becomes visible to the copy engine's wait)
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicAdd(&a.done[job / a.done_chunk], 1u); }
+        }
         HSPF_QMARK(4);   // next hops
     }
 }
