@@ -419,7 +419,9 @@ int run_any(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, const Any
         const bool quad_ok = g->has_quads && !g->has_leaf && !(g->d.flags & HSPF_GF_HOPCOUNT) && out.nh_words == 1 &&
                              !getenv("HSPF_NO_QUAD");
         if (quad_ok && ctx->wait_value && n >= 256 && !getenv("HSPF_E2E_CHUNK")) {
-            const uint32_t pchunk = std::max<uint32_t>(64, (n + 15) / 16);
+            uint32_t pieces = 4;       // few, large copies: every cudaMemcpyAsync costs ~10 us here
+            if (const char *pc = getenv("HSPF_E2E_PIECES")) { int v = atoi(pc); if (v >= 1 && v <= 64) pieces = (uint32_t)v; }   // tuning knob
+            const uint32_t pchunk = std::max<uint32_t>(1, (n + pieces - 1) / pieces);
             const uint32_t n_chunks = (n + pchunk - 1) / pchunk;
             CK(cudaMemsetAsync(ctx->d_done, 0, 64 * sizeof(uint32_t), ctx->stream));
             CK(cudaEventRecord(ctx->prog_reset, ctx->stream));
