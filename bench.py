@@ -158,6 +158,10 @@ def build_workload(name: str, rank: int, world: int, jobs: int):
 EXCHANGE_TEXT = {
     "none": "none",
     "nccl": "one NCCL all-gather of the step's result planes per step, overlapped with the next step's kernel",
+    "fused": "fused into the batch kernel: its result writer stores the travelling planes of every job straight into "
+             "this rank's slot on every peer GPU over NVLink while the batch computes (hspf_ctx_set_peer_slots); only "
+             "4-byte sequence flags follow behind the kernel (stream memory-op waits, no collective kernel); checked "
+             "once against an NCCL all-gather before the timed region",
     "p2p": "all-gather of the step's result planes per step by the copy engines over NVLink peer memory "
            "(hspf_xchg_*: one copy stream per peer, sequence flags behind the data, stream memory-op waits, no SM), "
            "overlapped with the next step's kernel; checked once against an NCCL all-gather before the timed region",
@@ -299,7 +303,7 @@ def run_reference(args):
         t_total += r["seconds"]
     value = done / t_total
     sample = f"{done} jobs in {t_total:.1f} s: each step a {step_s:.0f} s sample of the step's batch"
-    exchange = "none" if (args.gpus == 1 or args.config != "C2") else (args.exchange if args.exchange != "auto" else "p2p")
+    exchange = "none" if (args.gpus == 1 or args.config != "C2") else (args.exchange if args.exchange != "auto" else "fused")
     cfg = config_dict(args.gpus, desc, works, exchange, "16-bit" if args.planes == "16" else "32-bit")
     cfg["reference_sample"] = sample
     line = {
@@ -373,10 +377,15 @@ def run_ours(args):
     xchg_bytes = prefix if (len(works) == 1 and is_ospf and args.xchg_planes == "vertex") else tot
     exchange = "none"
     if world > 1 and args.config == "C2":
-        exchange = args.exchange if args.exchange != "auto" else "p2p"
+        exchange = args.exchange
+        if exchange == "auto":
+            # fused: the kernel stores the travelling planes into the peers' slots itself (16-bit vertex planes)
+            exchange = "fused" if (narrow and xchg_bytes == prefix) else "p2p"
+        if exchange == "fused" and not (narrow and xchg_bytes == prefix):
+            raise SystemExit("--exchange fused needs 16-bit planes and --xchg-planes vertex")
     n_buf = 2 if exchange != "none" else 1
     xchg = None
-    if exchange == "p2p":
+    if exchange in ("p2p", "fused"):
         try:
             xchg = shard.PeerExchange(ctx, local_rank, rank, world, tot, n_buf)
         except RuntimeError as e:       # raised on every rank together
@@ -451,6 +460,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    mode = {"x": exchange}
+
     def run_steps(n_steps):
         """No exchange: [flush, kernels] per step, per-step events.  With an exchange: kernels on
         the engine stream, the all-gather beside them, double buffered."""
@@ -460,6 +471,9 @@ def run_ours(args):
             if exchange == "none":
                 with torch.cuda.stream(stream):
                     flush.fill_(1)
+            elif xchg is not None and mode["x"] == "fused":
+                xchg.acquire_direct(b)                 # ... and every peer has released its copy of the slot
+                ctx.set_peer_slots(xchg.peer_deltas(b))
             elif xchg is not None:
                 xchg.acquire(b)                        # own slot of buffer b has left the device
             elif ag_done[b] is not None:
@@ -470,7 +484,11 @@ def run_ours(args):
             launch_all(b)
             ek.record(stream)
             if xchg is not None:
-                xchg.push(b)        # copy engines: slot -> every peer, flags behind the data
+                if mode["x"] == "fused":
+                    ctx.set_peer_slots([])
+                    xchg.publish(b)  # the planes are already there: flags only
+                else:
+                    xchg.push(b)    # copy engines: slot -> every peer, flags behind the data
                 xchg.wait(b)        # consumer stream: all slots of buffer b have arrived
                 xchg.release(b)     # (no consumer work in the bench) peers may reuse buffer b
             elif exchange == "nccl":
@@ -503,7 +521,18 @@ def run_ours(args):
         del ref
         barrier()
         if int(same.item()) != 1:
-            raise SystemExit("bench: peer exchange delivered planes that differ from the NCCL all-gather")
+            if mode["x"] == "fused":
+                # never expected; keep the run valid by measuring the copy-engine exchange instead
+                if rank == 0:
+                    print("bench: fused exchange delivered planes that differ from the NCCL all-gather; "
+                          "falling back to --exchange p2p", file=sys.stderr)
+                mode["x"] = exchange = "p2p"
+                xchg.sync()
+                barrier()
+                run_steps(args.warmup)
+                barrier()
+            else:
+                raise SystemExit("bench: peer exchange delivered planes that differ from the NCCL all-gather")
     st_all = torch.cat([bufs[0][o["status"]: o["status"] + 4 * w.n].view(torch.int32) for o, w in zip(lay, works)])
     assert int(st_all.abs().sum().item()) == 0, "job_status != 0"
 
@@ -703,9 +732,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="time bound of the faithful all-cores CPU sample")
     ap.add_argument("--no-e2e-variants", dest="e2e_variants", action="store_false")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="N>1, C2 only: how the result planes are all-gathered: copy engines over peer memory (p2p; "
-                         "falls back to nccl if peer memory cannot be mapped) or one NCCL all-gather per step; auto = p2p")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "p2p", "nccl"],
+                    help="N>1, C2 only: how the result planes reach the other GPUs: stored by the batch kernel itself "
+                         "into peer memory (fused), copied by the copy engines over peer memory (p2p), or one NCCL "
+                         "all-gather per step; auto = fused for 16-bit vertex planes, else p2p; peer memory that cannot "
+                         "be mapped falls back to nccl")
     ap.add_argument("--xchg-planes", default="vertex", choices=["vertex", "all"],
                     help="N>1, C2: what every GPU receives from every other: the planes holo-ospf's Vertex keeps "
                          "(distance, hops, next-hop set + job status) or all five planes")

@@ -103,6 +103,7 @@ EXPORTS = [
     "hspf_xchg_create", "hspf_xchg_attach", "hspf_xchg_slot", "hspf_xchg_slot_bytes", "hspf_xchg_acquire",
     "hspf_xchg_push", "hspf_xchg_wait", "hspf_xchg_release", "hspf_xchg_consumer_stream", "hspf_xchg_sync",
     "hspf_xchg_last_error", "hspf_xchg_destroy", "hspf_xchg_attach_ptr", "hspf_xchg_base", "hspf_xchg_set_push_bytes",
+    "hspf_xchg_acquire_direct", "hspf_xchg_peer_deltas", "hspf_xchg_publish", "hspf_ctx_set_peer_slots",
 ]
 
 
@@ -353,6 +354,13 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hspf_sync(self.handle))
+
+    def set_peer_slots(self, deltas):
+        """Fused exchange: the next 16-bit launches also store dist / hops / nh_mask / status into the
+        peers' copies of this rank's slot (hspf_xchg_peer_deltas); [] switches it off."""
+        self.lib.hspf_ctx_set_peer_slots.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int64)]
+        arr = (C.c_int64 * max(len(deltas), 1))(*deltas)
+        self._check(self.lib.hspf_ctx_set_peer_slots(self.handle, len(deltas), arr))
 
     def reserve_sms(self, n_sms: int):
         self._check(self.lib.hspf_ctx_reserve_sms(self.handle, n_sms))

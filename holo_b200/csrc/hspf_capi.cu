@@ -56,6 +56,9 @@ struct hspf_ctx {
     uint32_t prog_chunk = 0;
     CUresult (*wait_value)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t prog_reset = nullptr;
+    // fused exchange: peer slots the next 16-bit launches also write (hspf_ctx_set_peer_slots)
+    uint32_t n_peer_slots = 0;
+    long long peer_delta[7] = {0, 0, 0, 0, 0, 0, 0};
     int reserved_sms = 0;     // SMs left free for concurrent kernels (e.g. NCCL), see hspf_ctx_reserve_sms
 };
 
@@ -195,6 +198,8 @@ int enqueue_quad(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs, cons
     a.out_fp = static_cast<uint32_t *>(out->fp); a.out_npar = out->npar;
     a.out_nh = static_cast<uint64_t *>(out->nh); a.out_status = out->job_status;
     a.narrow = out->narrow ? 1u : 0u;
+    a.n_peers = out->narrow ? ctx->n_peer_slots : 0u;
+    for (uint32_t k = 0; k < 7; ++k) a.peer_delta[k] = ctx->peer_delta[k];
     a.done = ctx->prog_done;
     a.done_chunk = ctx->prog_chunk ? ctx->prog_chunk : 1u;
     a.job_counter = ctx->d_counter;
@@ -561,6 +566,13 @@ const char *hspf_last_error(const hspf_ctx *ctx) { return ctx ? ctx->err.c_str()
 void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hspf_ctx_set_peer_slots(hspf_ctx *ctx, uint32_t n_peers, const int64_t *deltas) {
+    if (!ctx || n_peers > 7 || (n_peers && !deltas)) return HSPF_E_INVAL;
+    ctx->n_peer_slots = n_peers;
+    for (uint32_t k = 0; k < n_peers; ++k) ctx->peer_delta[k] = (long long)deltas[k];
+    return HSPF_OK;
+}
 
 int hspf_ctx_reserve_sms(hspf_ctx *ctx, int n_sms) {
     if (!ctx || n_sms < 0 || n_sms >= ctx->sm_count) return HSPF_E_INVAL;

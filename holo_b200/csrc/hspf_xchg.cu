@@ -247,6 +247,60 @@ int hspf_xchg_push(hspf_xchg *x, uint32_t buffer) {
     return HSPF_OK;
 }
 
+/* ---- fused exchange: the batch kernel itself stores into the peers' slots -----------------
+ * hspf_xchg_acquire_direct replaces acquire (the engine's stream also waits until every peer has
+ * released what it read from this rank's slot of `buffer`: the kernel is about to overwrite the
+ * peers' copies), hspf_xchg_peer_deltas gives the address differences for hspf_ctx_set_peer_slots,
+ * hspf_xchg_publish replaces push (flags only, behind the kernel). */
+int hspf_xchg_acquire_direct(hspf_xchg *x, uint32_t buffer) {
+    if (!x || buffer >= x->n_buffers) return HSPF_E_INVAL;
+    int rc = hspf_xchg_acquire(x, buffer);
+    if (rc) return rc;
+    const uint32_t k = buffer, s = x->seq[k] + 1;
+    if (s > 1)
+        for (uint32_t r = 0; r < x->world; ++r) {
+            if (r == x->rank) continue;
+            CUresult cr = x->wait_value(reinterpret_cast<CUstream>(x->compute),
+                                        reinterpret_cast<CUdeviceptr>(x->acked(x->local, k, r)), s - 1,
+                                        CU_STREAM_WAIT_VALUE_GEQ);
+            if (cr != CUDA_SUCCESS) return xfail(x, HSPF_E_CUDA, "cuStreamWaitValue32(acked) failed");
+        }
+    return HSPF_OK;
+}
+
+int hspf_xchg_peer_deltas(hspf_xchg *x, uint32_t buffer, int64_t *deltas, uint32_t *n_peers) {
+    if (!x || buffer >= x->n_buffers || !deltas || !n_peers) return HSPF_E_INVAL;
+    uint32_t n = 0;
+    for (uint32_t d = 1; d < x->world; ++d) {
+        const uint32_t r = (x->rank + d) % x->world;
+        if (!x->peer[r]) return xfail(x, HSPF_E_INVAL, "hspf_xchg_peer_deltas before every peer is attached");
+        deltas[n++] = (int64_t)(x->slot(x->peer[r], buffer, x->rank) - x->slot(x->local, buffer, x->rank));
+    }
+    *n_peers = n;
+    return HSPF_OK;
+}
+
+int hspf_xchg_publish(hspf_xchg *x, uint32_t buffer) {
+    if (!x || buffer >= x->n_buffers) return HSPF_E_INVAL;
+    for (uint32_t r = 0; r < x->world; ++r)
+        if (!x->peer[r]) return xfail(x, HSPF_E_INVAL, "hspf_xchg_publish before every peer is attached");
+    const uint32_t k = buffer, me = x->rank;
+    const uint32_t s = x->seq[k] + 1;
+    XCK(cudaEventRecord(x->kernel_done[k], x->compute));
+    for (uint32_t d = 1; d < x->world; ++d) {
+        const uint32_t r = (me + d) % x->world;
+        cudaStream_t ps = x->push_streams[r];
+        XCK(cudaStreamWaitEvent(ps, x->kernel_done[k], 0));      // the kernel's peer stores are complete
+        if (x->memset32(reinterpret_cast<CUdeviceptr>(x->stage_arrived(k, r)), s, 1, reinterpret_cast<CUstream>(ps)) != CUDA_SUCCESS)
+            return xfail(x, HSPF_E_CUDA, "cuMemsetD32Async(flag) failed");
+        XCK(cudaMemcpyAsync(x->arrived(x->peer[r], k, me), x->stage_arrived(k, r), sizeof(uint32_t),
+                            cudaMemcpyDeviceToDevice, ps));
+        XCK(cudaEventRecord(x->push_done[(size_t)k * x->world + r], ps));
+    }
+    x->seq[k] = s;
+    return HSPF_OK;
+}
+
 /* The consumer stream of the exchange waits until every peer's slot of `buffer` carries the
  * data of this rank's latest push number (ranks step in lockstep), without using an SM. */
 int hspf_xchg_wait(hspf_xchg *x, uint32_t buffer) {

@@ -73,6 +73,11 @@ struct QuadArgs {
     uint32_t *job_counter;
     uint32_t sub_rounds;        // visits of a warp to its bitmap chunk per barrier-separated round (>= 1)
     uint32_t narrow;            // 1: 16-bit result planes (hspf_result16): out_dist / out_fp / out_nh point at u16 arrays
+    // Fused exchange (multi-GPU, 16-bit planes): the result writer also stores the planes the
+    // consumers need (dist, hops, nh_mask, job status) into this rank's slot on every peer GPU,
+    // over NVLink, job by job while the batch computes: peer address = local address + peer_delta[k].
+    uint32_t n_peers;
+    long long peer_delta[7];
     uint32_t *done;             // optional: done[job / done_chunk] counts finished jobs (release: planes first), so
     uint32_t done_chunk;        // that the host call can copy a chunk's planes back while the launch still runs
     unsigned long long *prof;   // optional [gridDim][16] cycle counters
@@ -167,6 +172,8 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         if (root >= V || n_ov_raw > (uint32_t)kMaxOv) {      // device-pointer callers are not validated on the host
             if (tid == 0) {
                 a.out_status[job] = kJsInvalid;
+                for (uint32_t k = 0; k < (a.narrow ? a.n_peers : 0u); ++k)
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&a.out_status[job]) + a.peer_delta[k]) = kJsInvalid;
                 if (a.done) { __threadfence(); atomicAdd(&a.done[job / a.done_chunk], 1u); }
             }
             continue;
@@ -182,6 +189,12 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         uint16_t *o_fp16 = reinterpret_cast<uint16_t *>(a.out_fp) + jo;
         uint16_t *o_nh16 = reinterpret_cast<uint16_t *>(a.out_nh) + jo;
         // the planes just written are read back in phase 3 (first parents, distances of ECMP parents)
+        const uint32_t n_peers = narrow ? a.n_peers : 0u;
+        // one 16-bit value into the same plane position of every peer's copy of this rank's slot
+        auto peer_st16 = [&](uint16_t *p, uint16_t x) {
+            for (uint32_t k = 0; k < n_peers; ++k)
+                *reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(p) + a.peer_delta[k]) = x;
+        };
         auto ld_fp = [&](uint32_t v) -> uint32_t {
             if (narrow) { const uint32_t f = __ldcg(&o_fp16[v]); return f == 0xFFFFu ? kInf : f; }
             return __ldcg(&o_fp[v]);
@@ -496,6 +509,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                         if (dv != kInf && dv >= 0xFFFFu) narrow_flag = 1;      // does not fit; 0xFFFF means "not on the SPT"
                         o_dist16[v] = (uint16_t)min(dv, 0xFFFFu);
                         o_fp16[v] = (uint16_t)min(fpv, 0xFFFFu);
+                        peer_st16(&o_dist16[v], (uint16_t)min(dv, 0xFFFFu));
                     } else {
                         o_dist[v] = dv;
                         o_fp[v] = fpv;
@@ -571,6 +585,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             const uint32_t w = word[v];
             const uint32_t h = (w >> 16) == v ? 0u : (w & 0xFFFFu);
             o_hops[v] = (uint16_t)h;
+            peer_st16(&o_hops[v], (uint16_t)h);
             // a hops-0 vertex that is not a head of a root edge cannot own atoms
             if (h == 0 && v != root && (w >> 16) != v && !hops0(v) && g.row[v + 1] != g.row[v])
                 atomicOr(&S.status, kJsTooManyAtoms);
@@ -710,7 +725,10 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 uint32_t m = w;
                 if (Tv != root && Tv != v) m |= word[Tv];
                 if (narrow) {
-                    if (pass == 0) o_nh16[v] = (uint16_t)(m & 0xFFFFu);      // (more than 16 atoms: HSPF_JS_NARROW, set below)
+                    if (pass == 0) {      // (more than 16 atoms: HSPF_JS_NARROW, set below)
+                        o_nh16[v] = (uint16_t)(m & 0xFFFFu);
+                        peer_st16(&o_nh16[v], (uint16_t)(m & 0xFFFFu));
+                    }
                 } else {
                     const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
                     if (pass == 0) o_nh[v] = bits; else o_nh[v] |= bits;
@@ -718,7 +736,12 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             }
             __syncthreads();
         }
-        if (tid == 0) a.out_status[job] = S.status | ((narrow && n_atoms > 16u) ? kJsNarrow : 0u);
+        if (tid == 0) {
+            const uint32_t st = S.status | ((narrow && n_atoms > 16u) ? kJsNarrow : 0u);
+            a.out_status[job] = st;
+            for (uint32_t k = 0; k < n_peers; ++k)
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&a.out_status[job]) + a.peer_delta[k]) = st;
+        }
         if (a.done) {
             // every plane of this job is written: publish (barrier: the other threads' stores happen
             // before thread 0's fence; fence: before the count becomes visible to the copy engine's wait)

@@ -137,6 +137,23 @@ class PeerExchange:
                     x._ck(x.lib.hspf_xchg_attach_ptr(x.handle, y.rank, x.lib.hspf_xchg_base(y.handle)), "attach_ptr")
         return xs
 
+    def acquire_direct(self, b):
+        self.lib.hspf_xchg_acquire_direct.argtypes = [self.C.c_void_p, self.C.c_uint32]
+        self._ck(self.lib.hspf_xchg_acquire_direct(self.handle, b), "acquire_direct")
+
+    def publish(self, b):
+        self.lib.hspf_xchg_publish.argtypes = [self.C.c_void_p, self.C.c_uint32]
+        self._ck(self.lib.hspf_xchg_publish(self.handle, b), "publish")
+
+    def peer_deltas(self, b):
+        """Address differences (peer copy of this rank's slot - local slot) for hspf_ctx_set_peer_slots."""
+        C = self.C
+        self.lib.hspf_xchg_peer_deltas.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
+        d = (C.c_int64 * 8)()
+        n = C.c_uint32()
+        self._ck(self.lib.hspf_xchg_peer_deltas(self.handle, b, d, C.byref(n)), "peer_deltas")
+        return [int(d[i]) for i in range(n.value)]
+
     def set_push_bytes(self, nbytes: int):
         self.lib.hspf_xchg_set_push_bytes.argtypes = [self.C.c_void_p, self.C.c_size_t]
         self._ck(self.lib.hspf_xchg_set_push_bytes(self.handle, nbytes), "set_push_bytes")

@@ -316,6 +316,20 @@ void *hspf_xchg_base(hspf_xchg *x);
 /* Only the first nbytes of the own slot travel in hspf_xchg_push (0 = the whole slot): lay the
  * planes the consumers need first.  Sequence numbers are 32 bits: no limit on the number of pushes. */
 int hspf_xchg_set_push_bytes(hspf_xchg *x, size_t nbytes);
+/* Fused exchange: the batch kernel stores the planes the consumers need (16-bit dist, hops,
+ * nh_mask; job status) into this rank's slot on every peer while it computes, over NVLink, and
+ * only the sequence flags travel afterwards.  Per step on buffer k:
+ *     hspf_xchg_acquire_direct(x, k);     as acquire, and every peer has released this rank's slot
+ *     hspf_xchg_peer_deltas(x, k, d, &n); hspf_ctx_set_peer_slots(ctx, n, d);
+ *     hspf_run_batch16_async(... planes inside hspf_xchg_slot(x, k, rank) ...);
+ *     hspf_ctx_set_peer_slots(ctx, 0, NULL);
+ *     hspf_xchg_publish(x, k);            flags behind the kernel
+ *     hspf_xchg_wait / consumer work / hspf_xchg_release as before.
+ * deltas[]: room for world - 1 entries; at most 7 peers.  first_parent / n_parents stay local. */
+int hspf_xchg_acquire_direct(hspf_xchg *x, uint32_t buffer);
+int hspf_xchg_peer_deltas(hspf_xchg *x, uint32_t buffer, int64_t *deltas, uint32_t *n_peers);
+int hspf_xchg_publish(hspf_xchg *x, uint32_t buffer);
+int hspf_ctx_set_peer_slots(hspf_ctx *ctx, uint32_t n_peers, const int64_t *deltas);
 void *hspf_xchg_slot(hspf_xchg *x, uint32_t buffer, uint32_t slot);   /* device pointer, local copy */
 size_t hspf_xchg_slot_bytes(const hspf_xchg *x);                      /* slot_bytes rounded up to 256 */
 int hspf_xchg_acquire(hspf_xchg *x, uint32_t buffer);

@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 log=gpurun_out/r2_n${N}.log
 : > $log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+echo "== pytest exchange" >> $log
+timeout 300 python -m pytest tests/test_xchg_gpu.py -x -q -m gpu 2>&1 | tail -4 >> $log
 echo "== selftest" >> $log
 timeout 150 $TR --master-port 29533 scripts/xchg_selftest.py --steps 40 --slot-mb 8 2>&1 | grep -v "OMP_NUM_THREADS\|^\*\*\*" | tail -5 >> $log
 run() {  # name, extra args
@@ -14,9 +16,10 @@ run() {  # name, extra args
   timeout 200 $TR --master-port 295$((40 + RANDOM % 50)) bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline --no-e2e-variants "$@" \
       > gpurun_out/r2_n${N}_$name.json 2> gpurun_out/r2_n${N}_$name.err || { echo "FAILED rc=$?" >> $log; tail -8 gpurun_out/r2_n${N}_$name.err >> $log; }
 }
-run p2p_vertex
-[ -z "$QUICK" ] && run p2p_all --xchg-planes all
-[ -z "$QUICK" ] && run nccl_vertex --exchange nccl
+run fused
+[ -z "$QUICK" ] && run p2p_vertex --exchange p2p
+[ -n "$FULL" ] && run p2p_all --exchange p2p --xchg-planes all
+[ -n "$FULL" ] && run nccl_vertex --exchange nccl
 python - >> $log <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_n${N}_*.json")):

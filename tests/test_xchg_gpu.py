@@ -70,3 +70,76 @@ def test_peer_exchange_loopback_on_one_gpu():
         x.close()
     for c in ctxs:
         c.close()
+
+
+def test_fused_exchange_kernel_stores_into_the_peer_slot_loopback():
+    """Fused exchange on one GPU (two contexts, exchanges attached by pointer): the batch kernel of
+    rank r writes dist / hops / nh_mask / job status of its jobs into its slot of rank 1-r's buffer
+    while it computes; after publish + wait the peer's copy equals the local planes, and the planes
+    that do not travel (first_parent, n_parents) stay untouched there."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from holo_b200 import capi, shard, synth
+    from oracle import pyoracle
+    dev = torch.device("cuda", 0)
+    t = synth.random_topology(400, 1800, synth.SEED_BASE + 61)
+    csr = synth.topology_csr(t)
+    V, n = csr.n_vertices, 96
+    al = lambda x: (x + 255) // 256 * 256
+    off, tot = {}, 0
+    for k, b in (("dist", 2), ("hops", 2), ("nh", 2), ("status", None), ("fp", 2), ("npar", 2)):
+        off[k] = tot
+        tot += al(n * 4 if b is None else n * V * b)
+    ctxs = [capi.Context(0), capi.Context(0)]
+    graphs = [c.upload(csr) for c in ctxs]
+    xs = shard.PeerExchange.local_pair(ctxs, 0, tot, 2)
+    roots = [np.arange(r * n, (r + 1) * n, dtype=np.uint32) % V for r in range(2)]
+    d_roots = [torch.from_numpy(x.astype(np.int64)).to(torch.int32).to(dev) for x in roots]
+    for step in range(3):
+        b = step % 2
+        for r, (c, x) in enumerate(zip(ctxs, xs)):
+            base = x.slot_ptr(b, r)
+            shard.raw_cuda_tensor(base, tot, dev).zero_()
+        torch.cuda.synchronize()
+        for r, (c, x, g) in enumerate(zip(ctxs, xs, graphs)):
+            x.acquire_direct(b)
+            c.set_peer_slots(x.peer_deltas(b))
+            js = capi.JobsStruct()
+            js.n_jobs = n
+            js.roots = C.cast(d_roots[r].data_ptr(), C.POINTER(C.c_uint32))
+            base = x.slot_ptr(b, r)
+            rs = capi.Result16Struct()
+            for k, f in (("dist", "dist"), ("hops", "hops"), ("fp", "first_parent"), ("npar", "n_parents"), ("nh", "nh_mask")):
+                setattr(rs, f, C.cast(base + off[k], C.POINTER(C.c_uint16)))
+            rs.job_status = C.cast(base + off["status"], C.POINTER(C.c_uint32))
+            c.run_device16(g, js, rs, sync=False)
+            c.set_peer_slots([])
+            x.publish(b)
+        for x in xs:
+            x.wait(b)
+        for x in xs:
+            x.sync()
+        torch.cuda.synchronize()
+        for r, x in enumerate(xs):
+            mine = shard.raw_cuda_tensor(x.slot_ptr(b, r), tot, dev).cpu().numpy()
+            theirs = shard.raw_cuda_tensor(xs[1 - r].slot_ptr(b, r), tot, dev).cpu().numpy()   # rank r's slot on the peer
+            for k in ("dist", "hops", "nh"):
+                a0, a1 = off[k], off[k] + n * V * 2
+                assert np.array_equal(mine[a0:a1], theirs[a0:a1]), (step, r, k)
+            assert np.array_equal(mine[off["status"]: off["status"] + 4 * n], theirs[off["status"]: off["status"] + 4 * n])
+            assert not theirs[off["fp"]: off["fp"] + n * V * 2].any()          # does not travel
+            d = mine[off["dist"]: off["dist"] + n * V * 2].view(np.uint16).reshape(n, V)
+            ref = pyoracle.csr_spf(csr, int(roots[r][5]))
+            assert np.array_equal(d[5], ref["dist"].astype(np.uint16))
+        for x in xs:
+            x.release(b)
+    for x in xs:
+        x.sync()
+    torch.cuda.synchronize()
+    for x in xs:
+        x.close()
+    for g in graphs:
+        g.free()
+    for c in ctxs:
+        c.close()
