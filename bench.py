@@ -158,8 +158,9 @@ def build_workload(name: str, rank: int, world: int, jobs: int):
 EXCHANGE_TEXT = {
     "none": "none",
     "nccl": "one NCCL all-gather of the step's result planes per step, overlapped with the next step's kernel",
-    "fused": "fused into the batch kernel: its result writer stores the travelling planes of every job straight into "
-             "this rank's slot on every peer GPU over NVLink while the batch computes (hspf_ctx_set_peer_slots); only "
+    "fused": "fused into the batch kernel: every finished job's rows of the travelling planes are pushed by its CTA straight "
+             "into this rank's slot on every peer GPU over NVLink (16-byte stores) while the batch computes "
+             "(hspf_ctx_set_peer_slots); only "
              "4-byte sequence flags follow behind the kernel (stream memory-op waits, no collective kernel); checked "
              "once against an NCCL all-gather before the timed region",
     "p2p": "all-gather of the step's result planes per step by the copy engines over NVLink peer memory "
@@ -303,7 +304,8 @@ def run_reference(args):
         t_total += r["seconds"]
     value = done / t_total
     sample = f"{done} jobs in {t_total:.1f} s: each step a {step_s:.0f} s sample of the step's batch"
-    exchange = "none" if (args.gpus == 1 or args.config != "C2") else (args.exchange if args.exchange != "auto" else "fused")
+    exchange = "none" if (args.gpus == 1 or args.config != "C2") else (
+        args.exchange if args.exchange != "auto" else ("fused" if args.gpus > 4 else "p2p"))
     cfg = config_dict(args.gpus, desc, works, exchange, "16-bit" if args.planes == "16" else "32-bit")
     cfg["reference_sample"] = sample
     line = {
@@ -379,8 +381,10 @@ def run_ours(args):
     if world > 1 and args.config == "C2":
         exchange = args.exchange
         if exchange == "auto":
-            # fused: the kernel stores the travelling planes into the peers' slots itself (16-bit vertex planes)
-            exchange = "fused" if (narrow and xchg_bytes == prefix) else "p2p"
+            # Measured (profiles/r2_n*_*.json): the copy engines hide the exchange behind the kernel at N=2
+            # (efficiency 0.97) and deliver ~265-285 GB/s per GPU beyond that (N=4: 0.73); with 7 peers the
+            # fused variant (the kernel pushes every finished job's rows into the peers' slots itself) is used.
+            exchange = "fused" if (world > 4 and narrow and xchg_bytes == prefix) else "p2p"
         if exchange == "fused" and not (narrow and xchg_bytes == prefix):
             raise SystemExit("--exchange fused needs 16-bit planes and --xchg-planes vertex")
     n_buf = 2 if exchange != "none" else 1
@@ -735,8 +739,8 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "p2p", "nccl"],
                     help="N>1, C2 only: how the result planes reach the other GPUs: stored by the batch kernel itself "
                          "into peer memory (fused), copied by the copy engines over peer memory (p2p), or one NCCL "
-                         "all-gather per step; auto = fused for 16-bit vertex planes, else p2p; peer memory that cannot "
-                         "be mapped falls back to nccl")
+                         "all-gather per step; auto = p2p up to 4 GPUs, fused above (16-bit vertex planes); peer memory "
+                         "that cannot be mapped falls back to nccl")
     ap.add_argument("--xchg-planes", default="vertex", choices=["vertex", "all"],
                     help="N>1, C2: what every GPU receives from every other: the planes holo-ospf's Vertex keeps "
                          "(distance, hops, next-hop set + job status) or all five planes")

@@ -190,10 +190,26 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
         uint16_t *o_nh16 = reinterpret_cast<uint16_t *>(a.out_nh) + jo;
         // the planes just written are read back in phase 3 (first parents, distances of ECMP parents)
         const uint32_t n_peers = narrow ? a.n_peers : 0u;
-        // one 16-bit value into the same plane position of every peer's copy of this rank's slot
-        auto peer_st16 = [&](uint16_t *p, uint16_t x) {
-            for (uint32_t k = 0; k < n_peers; ++k)
-                *reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(p) + a.peer_delta[k]) = x;
+        // Fused exchange: a finished job's row of a travelling plane goes to the same position of
+        // every peer's copy of this rank's slot, as 16-byte stores (full NVLink write packets; the
+        // row was just written, so the loads hit L2), unaligned ends as 2-byte stores.
+        auto peer_push_row = [&](uint16_t *row) {
+            char *src = reinterpret_cast<char *>(row);
+            const size_t bytes = (size_t)V * 2;
+            const size_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;       // (deltas are multiples of 256)
+            const size_t h = head < bytes ? head : bytes;
+            const size_t n16 = (bytes - h) / 16, tail0 = h + n16 * 16;
+            for (size_t i = tid; i < n16; i += T) {
+                const uint4 val = __ldcg(reinterpret_cast<const uint4 *>(src + h) + i);
+                for (uint32_t k = 0; k < n_peers; ++k)
+                    reinterpret_cast<uint4 *>(src + h + a.peer_delta[k])[i] = val;
+            }
+            auto push16 = [&](size_t o) {
+                const uint16_t val = __ldcg(reinterpret_cast<const uint16_t *>(src + o));
+                for (uint32_t k = 0; k < n_peers; ++k) *reinterpret_cast<uint16_t *>(src + o + a.peer_delta[k]) = val;
+            };
+            for (size_t o = (size_t)tid * 2; o < h; o += (size_t)T * 2) push16(o);
+            for (size_t o = tail0 + (size_t)tid * 2; o < bytes; o += (size_t)T * 2) push16(o);
         };
         auto ld_fp = [&](uint32_t v) -> uint32_t {
             if (narrow) { const uint32_t f = __ldcg(&o_fp16[v]); return f == 0xFFFFu ? kInf : f; }
@@ -509,7 +525,7 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                         if (dv != kInf && dv >= 0xFFFFu) narrow_flag = 1;      // does not fit; 0xFFFF means "not on the SPT"
                         o_dist16[v] = (uint16_t)min(dv, 0xFFFFu);
                         o_fp16[v] = (uint16_t)min(fpv, 0xFFFFu);
-                        peer_st16(&o_dist16[v], (uint16_t)min(dv, 0xFFFFu));
+
                     } else {
                         o_dist[v] = dv;
                         o_fp[v] = fpv;
@@ -585,7 +601,6 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
             const uint32_t w = word[v];
             const uint32_t h = (w >> 16) == v ? 0u : (w & 0xFFFFu);
             o_hops[v] = (uint16_t)h;
-            peer_st16(&o_hops[v], (uint16_t)h);
             // a hops-0 vertex that is not a head of a root edge cannot own atoms
             if (h == 0 && v != root && (w >> 16) != v && !hops0(v) && g.row[v + 1] != g.row[v])
                 atomicOr(&S.status, kJsTooManyAtoms);
@@ -727,7 +742,6 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 if (narrow) {
                     if (pass == 0) {      // (more than 16 atoms: HSPF_JS_NARROW, set below)
                         o_nh16[v] = (uint16_t)(m & 0xFFFFu);
-                        peer_st16(&o_nh16[v], (uint16_t)(m & 0xFFFFu));
                     }
                 } else {
                     const uint64_t bits = (uint64_t)(m & 0xFFFFu) << (16 * pass);
@@ -735,6 +749,12 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
                 }
             }
             __syncthreads();
+        }
+        if (n_peers) {
+            __syncthreads();                      // every plane of this job is written (this CTA wrote them all)
+            peer_push_row(o_dist16);
+            peer_push_row(o_hops);
+            peer_push_row(o_nh16);
         }
         if (tid == 0) {
             const uint32_t st = S.status | ((narrow && n_atoms > 16u) ? kJsNarrow : 0u);

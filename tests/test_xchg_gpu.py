@@ -83,7 +83,7 @@ def test_fused_exchange_kernel_stores_into_the_peer_slot_loopback():
     from holo_b200 import capi, shard, synth
     from oracle import pyoracle
     dev = torch.device("cuda", 0)
-    t = synth.random_topology(400, 1800, synth.SEED_BASE + 61)
+    t = synth.random_topology(403, 1800, synth.SEED_BASE + 61)      # odd row length: unaligned heads and tails
     csr = synth.topology_csr(t)
     V, n = csr.n_vertices, 96
     al = lambda x: (x + 255) // 256 * 256
