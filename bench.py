@@ -679,7 +679,9 @@ def run_ours(args):
         if tjson.exists() and args.config == "C2":
             try:
                 tr = json.loads(tjson.read_text())
-                traffic, traffic_src = tr.get("dram_bytes_per_launch"), tr.get("source")
+                # the capture is of the fast path with 16-bit planes: any other combination has no traffic figure
+                if fast and narrow and str(tr.get("kernel", "")).startswith("spf_quad_kernel"):
+                    traffic, traffic_src = tr.get("dram_bytes_per_launch"), tr.get("source")
             except Exception:
                 traffic = None
         cpu = None if args.no_cpu_baseline else cpu_arms(works, seconds=args.cpu_seconds)
