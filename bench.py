@@ -654,6 +654,39 @@ def run_ours(args):
         route_stage = {"ms_per_root": 1e3 * (time.perf_counter() - t0) / k,
                        "what": "hspf_ospfv2_run_area: flatten + one device SPF + next-hop resolution, router table, "
                                f"intra-area routes with SR labels (host C++ behind the device SPT), LSDB-level call, {k} calls"}
+        # the batched form: SPTs and the intra-area route cells of every root on the device
+        # (hspf_ospfv2_run_area_batch), then the host decode of ONE root (the local router's)
+        flat = ospfv2.Flat(area)
+        rids = flat.ids[works[0].roots].astype(np.uint32)
+        ospfv2.run_area_batch(ctx, area, rids[:8])
+        t0 = time.perf_counter()
+        b = ospfv2.run_area_batch(ctx, area, rids)
+        t_batch = time.perf_counter() - t0
+        rt = ospfv2.RouteTable(flat)
+        j = int(np.nonzero(rids == area.router_id)[0][0]) if (rids == area.router_id).any() else None
+        dec_ms = None
+        if j is not None and b.status[j] == 0:
+            gv, gn = b.gather(j)
+            t0 = time.perf_counter()
+            dec = ospfv2.routes_from_cells(area, rt, b.cells[j], gv, gn)
+            dec_ms = 1e3 * (time.perf_counter() - t0)
+            ref = ospfv2.run_area(ctx, area)
+            keep = [n for n in dec.routes.dtype.names if n != "nh_off"]
+            if dec.rc != 0 or not np.array_equal(dec.routes[keep], ref.routes[keep]):
+                raise SystemExit("route cells of the local root do not decode to hspf_ospfv2_run_area's routes")
+        route_stage["device_batch"] = {
+            "roots": int(len(rids)), "prefixes": int(rt.n_prefixes), "advertisers": int(rt.n_contributors),
+            "refused_roots": int((b.status != 0).sum()),
+            "spt_batch_ms": b.device_ms[0], "route_kernel_ms": b.device_ms[1],
+            "route_kernel_us_per_root": 1e3 * b.device_ms[1] / max(len(rids), 1),
+            "cell_bytes": int(b.cells.nbytes),
+            "route_kernel_GBps": b.cells.nbytes / max(b.device_ms[1], 1e-9) / 1e6,
+            "call_wall_ms": 1e3 * t_batch,
+            "host_decode_ms_one_root": dec_ms,
+            "what": "hspf_ospfv2_run_area_batch: flatten + route table + one SPT batch + one thread per (root, prefix) "
+                    "over the advertisers (update_rib_intra_area, route.rs:343-446) + cells back to pageable host memory; "
+                    "hspf_ospfv2_routes_from_cells decodes one root's cells into interface next hops and SR labels",
+        }
 
     # ---- max over ranks ----------------------------------------------------------------------
     tm = torch.tensor([total_ms, kernel_ms_avg, wall], dtype=torch.float64, device=dev)

@@ -12,12 +12,15 @@
 // 895-942) with SR labels per sr.rs:29-77,127-255.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <new>
+#include <stdexcept>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
 #include "holo_spf_lsdb.h"
+#include "route_cells.h"
 
 namespace {
 
@@ -364,6 +367,7 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
         (uint32_t)sizeof(hl_ospfv3_rib_area), (uint32_t)sizeof(hl_rib_route6), (uint32_t)sizeof(hl_ospfv3_rib),
         (uint32_t)sizeof(hl_rib_action),
         (uint32_t)sizeof(hl_isis_rnl_entry),
+        (uint32_t)sizeof(hl_route_cell),
     };
     static_assert(sizeof(hl_rib_action) == 12, "hl_rib_action layout");
     const uint32_t n = sizeof(v) / sizeof(v[0]);
@@ -664,6 +668,256 @@ int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *a, const uint32_t *dist, 
         if (rit == f.rtr_vertex.end()) return HSPF_OK;
         out->root_found = 1;
         return area_from_planes(f, a, rit->second, dist, hops, nh_mask, nh_words, out);
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
+
+
+/* ---- batched route stage: the table and the per-job decode (route_cells.h) ------------------- */
+
+void hspf_ospfv2_rtable_free(hspf_ospfv2_rtable *rt) {
+    if (!rt) return;
+    hspf_rtable_release_device(rt);
+    delete rt;
+}
+
+int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable **out) {
+    if (!flat || !flat->area || !out) return HSPF_E_INVAL;
+    try {
+        const hspf_ospfv2_flat &f = *flat;
+        const hl_ospfv2_area *a = f.area;
+        const uint32_t V = (uint32_t)f.ids.size();
+        // Extended-Prefix entries by (advertising router, prefix): the first live one in LSDB order
+        // (lsdb iteration + find, sr.rs:29-49), and which routers announce the SPF algorithm
+        struct EKey { uint32_t adv, prefix, plen; bool operator==(const EKey &o) const { return adv == o.adv && prefix == o.prefix && plen == o.plen; } };
+        struct EHash { size_t operator()(const EKey &k) const { return ((size_t)k.adv * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.prefix << 7) ^ k.plen; } };
+        std::unordered_map<EKey, uint32_t, EHash> extp;
+        std::unordered_set<uint32_t> sr_algo;
+        if (a->sr_enabled) {
+            extp.reserve(a->n_ext_prefixes);
+            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+                const auto &e = a->ext_prefixes[i];
+                if (e.age == HL_LSA_MAX_AGE) continue;
+                extp.emplace(EKey{e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)}, i);
+            }
+            for (uint32_t i = 0; i < a->n_ri_lsas; ++i)
+                if (a->ri_lsas[i].age != HL_LSA_MAX_AGE && a->ri_lsas[i].has_sr_algo) sr_algo.insert(a->ri_lsas[i].adv_rtr);
+        }
+        struct Raw { uint32_t prefix, plen, seq; hspf::RouteContrib c; uint8_t otype; uint32_t oadv; int32_t ext; };
+        std::vector<Raw> raw;
+        raw.reserve((size_t)a->n_links + a->n_network_lsas);
+        auto rt = new hspf_ospfv2_rtable();
+        std::unique_ptr<hspf_ospfv2_rtable> guard(rt);
+        rt->t.sids.push_back(hspf::SidDesc{0, 0, 0});
+        std::unordered_map<uint64_t, uint16_t> sid_class;
+        auto add = [&](uint32_t v, uint32_t prefix, uint32_t plen, uint32_t metric, uint8_t otype, uint32_t oadv, uint32_t oid) {
+            Raw r{};
+            r.prefix = prefix; r.plen = plen; r.seq = (uint32_t)raw.size();
+            r.c.vertex = v; r.c.origin_id = oid; r.c.metric = (uint16_t)metric; r.c.is_network = otype == 2;
+            r.otype = otype; r.oadv = oadv; r.ext = -1;
+            if (a->sr_enabled && sr_algo.count(oadv)) {
+                auto it = extp.find(EKey{oadv, prefix, plen});
+                if (it != extp.end()) {
+                    const auto &e = a->ext_prefixes[it->second];
+                    if (e.route_type == 1 && e.has_sid) {
+                        r.ext = (int32_t)it->second;
+                        const uint64_t key = ((uint64_t)e.sid_value << 16) | ((uint64_t)e.sid_flags << 8) | (e.sid_is_label ? 1u : 0u);
+                        auto ins = sid_class.emplace(key, (uint16_t)rt->t.sids.size());
+                        if (ins.second) {
+                            if (rt->t.sids.size() >= 0xFFFFu) throw std::length_error("sid classes");
+                            rt->t.sids.push_back(hspf::SidDesc{e.sid_value, e.sid_flags, (uint8_t)(e.sid_is_label ? 1 : 0)});
+                        }
+                        r.c.sid_class = ins.first->second;
+                    }
+                }
+            }
+            raw.push_back(r);
+        };
+        for (uint32_t v = 0; v < V; ++v) {
+            if (!f.is_router[v]) {
+                const auto &nl = a->network_lsas[f.lsa_of[v]];
+                add(v, nl.lsa_id & nl.mask, (uint32_t)__builtin_popcount(nl.mask), 0, 2, nl.adv_rtr, nl.lsa_id);
+            } else {
+                const auto &rl = a->router_lsas[f.lsa_of[v]];
+                for (uint32_t k = 0; k < rl.n_links; ++k) {
+                    const auto &l = a->links[rl.link_off + k];
+                    if (l.link_type != HL_LINK_STUB) continue;
+                    add(v, l.link_id & l.link_data, (uint32_t)__builtin_popcount(l.link_data), l.metric, 1, rl.adv_rtr, rl.lsa_id);
+                }
+            }
+        }
+        std::sort(raw.begin(), raw.end(), [](const Raw &x, const Raw &y) {
+            if (x.prefix != y.prefix) return x.prefix < y.prefix;
+            if (x.plen != y.plen) return x.plen < y.plen;
+            return x.seq < y.seq;
+        });
+        auto &t = rt->t;
+        t.n_vertices = V;
+        for (size_t i = 0; i < raw.size(); ++i) {
+            if (i == 0 || raw[i].prefix != raw[i - 1].prefix || raw[i].plen != raw[i - 1].plen) {
+                t.prefix.push_back(raw[i].prefix); t.plen.push_back(raw[i].plen); t.off.push_back((uint32_t)i);
+            }
+            t.contribs.push_back(raw[i].c);
+            t.origin_type.push_back(raw[i].otype);
+            t.origin_adv.push_back(raw[i].oadv);
+            rt->ext_of.push_back(raw[i].ext);
+        }
+        t.off.push_back((uint32_t)raw.size());
+        *out = guard.release();
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_UNSUPPORTED;
+    }
+}
+
+uint32_t hspf_ospfv2_rtable_prefixes(const hspf_ospfv2_rtable *rt) { return rt ? (uint32_t)rt->t.prefix.size() : 0; }
+uint32_t hspf_ospfv2_rtable_contributors(const hspf_ospfv2_rtable *rt) { return rt ? (uint32_t)rt->t.contribs.size() : 0; }
+
+int hspf_ospfv2_rtable_arrays(const hspf_ospfv2_rtable *rt, const uint32_t **prefix, const uint32_t **plen,
+                              const uint32_t **off, const void **contribs) {
+    if (!rt) return HSPF_E_INVAL;
+    if (prefix) *prefix = rt->t.prefix.data();
+    if (plen) *plen = rt->t.plen.data();
+    if (off) *off = rt->t.off.data();
+    if (contribs) *contribs = rt->t.contribs.data();
+    return HSPF_OK;
+}
+
+int hspf_ospfv2_routes_from_cells(const hl_ospfv2_area *a, const hspf_ospfv2_rtable *rt, const hl_route_cell *cells,
+                                  const uint32_t *gather_v, const uint64_t *gather_nh, uint32_t n_gather,
+                                  hl_ospfv2_result *out) {
+    if (!a || !rt || !cells || !out || (n_gather && (!gather_v || !gather_nh))) return HSPF_E_INVAL;
+    try {
+        out->n_vertices = out->n_routers = out->n_routes = out->n_nexthops = 0;
+        out->transit_capability = 0;
+        out->root_found = 0;
+        hspf_ospfv2_flat f;
+        int rc = flatten(a, f);
+        if (rc) return rc;
+        const uint32_t V = (uint32_t)f.ids.size();
+        if (V != rt->t.n_vertices) return HSPF_E_INVAL;          // not the LSDB the table was built from
+        auto rit = f.rtr_vertex.find(a->router_id);
+        if (rit == f.rtr_vertex.end()) return HSPF_OK;
+        out->root_found = 1;
+        const uint32_t root = rit->second;
+        // atoms -> next hops: only the transit networks next to the root are ever looked up (Resolver::resolve)
+        std::vector<uint64_t> sparse_nh(V, 0);
+        for (uint32_t i = 0; i < n_gather; ++i) {
+            if (gather_v[i] >= V) return HSPF_E_INVAL;
+            sparse_nh[gather_v[i]] = gather_nh[i];
+        }
+        Resolver rs{f, a, root, sparse_nh.data(), 1, {}, {}, {}};
+        rs.atom_nh.resize(64);
+        rs.atom_done.assign(64, 0);
+        for (uint32_t i = 0; i < a->n_ifaces; ++i)
+            if (a->ifaces[i].n_nbrs > 0) rs.ifaces_with_nbrs.push_back((int)i);
+        // SRGBs per router (area_router_information, ospfv2/spf.rs:617-654)
+        std::unordered_map<uint32_t, RouterInfo> ri_cache;
+        const RouterInfo no_ri;
+        if (a->sr_enabled) {
+            for (uint32_t i = 0; i < a->n_ri_lsas; ++i) {
+                const auto &l = a->ri_lsas[i];
+                if (l.age == HL_LSA_MAX_AGE) continue;
+                RouterInfo &ri = ri_cache[l.adv_rtr];
+                if (l.has_sr_algo) ri.has_sr_algo = true;
+                for (uint32_t k = 0; k < l.n_srgb; ++k) ri.srgb.push_back(&a->srgbs[l.srgb_off + k]);
+            }
+        }
+        auto cached_ri = [&](uint32_t rid) -> const RouterInfo & {
+            auto it = ri_cache.find(rid);
+            return it == ri_cache.end() ? no_ri : it->second;
+        };
+        const RouterInfo &local_ri = cached_ri(a->router_id);
+
+        const auto &t = rt->t;
+        const uint32_t P = (uint32_t)t.prefix.size();
+        uint32_t n_routes = 0, n_nh = 0;
+        std::vector<Nh> set;
+        for (uint32_t p = 0; p < P; ++p) {
+            const hl_route_cell &c = cells[p];
+            if (!(c.flags & HL_CELL_PRESENT)) continue;
+            if (c.flags & HL_CELL_MIXED_SID) return HSPF_E_UNSUPPORTED;
+            if (c.winner < t.off[p] || c.winner >= t.off[p + 1]) return HSPF_E_INVAL;
+            const hspf::RouteContrib &w = t.contribs[c.winner];
+            const hl_ospfv2_ext_prefix *ep = nullptr;
+            if (w.sid_class) {
+                const int32_t e = rt->ext_of[c.winner];
+                if (e < 0 || (uint32_t)e >= a->n_ext_prefixes) return HSPF_E_INVAL;
+                ep = &a->ext_prefixes[e];
+            }
+            const bool local = (c.flags & HL_CELL_CONNECTED) != 0;
+            hl_route_net o{};
+            o.prefix = t.prefix[p]; o.mask = t.plen[p] == 0 ? 0 : 0xFFFFFFFFu << (32 - t.plen[p]);
+            o.metric = c.metric; o.flags = local ? HL_ROUTE_CONNECTED : 0; o.origin_type = t.origin_type[c.winner];
+            o.origin_adv_rtr = t.origin_adv[c.winner]; o.origin_lsa_id = w.origin_id;
+            if (ep) {
+                o.has_prefix_sid = 1; o.prefix_sid_value = ep->sid_value; o.prefix_sid_flags = ep->sid_flags;
+                o.prefix_sid_is_label = ep->sid_is_label;
+                if (!(local && (!(ep->sid_flags & HL_PSID_NP) || (ep->sid_flags & HL_PSID_E)))) {
+                    if (!ep->sid_is_label) {
+                        uint32_t lab;
+                        if (!local_ri.srgb.empty() && index_to_label(ep->sid_value, local_ri.srgb, &lab)) { o.has_sr_label = 1; o.sr_label = lab; }
+                    } else {
+                        o.has_sr_label = 1; o.sr_label = ep->sid_value;
+                    }
+                }
+            }
+            set.clear();
+            uint64_t m = c.nh_mask;
+            while (m) {
+                const uint32_t atom = (uint32_t)__builtin_ctzll(m);
+                m &= m - 1;
+                const bool last_hop = (c.lasthop_mask >> atom) & 1u;
+                for (Nh x : rs.resolve(atom)) {
+                    if (ep && x.has_nbr) {
+                        uint32_t lab = 0; bool ok = false, decided = false;
+                        if (last_hop) {
+                            if (!(ep->sid_flags & HL_PSID_NP)) { lab = 3; ok = decided = true; }
+                            else if (ep->sid_flags & HL_PSID_E) { lab = 0; ok = decided = true; }
+                        }
+                        if (!decided) {
+                            if (!ep->sid_is_label) {
+                                const RouterInfo &nri = cached_ri(x.nbr);
+                                if (!nri.srgb.empty()) ok = index_to_label(ep->sid_value, nri.srgb, &lab);
+                            } else {
+                                lab = last_hop ? ep->sid_value : 3u; ok = true;
+                            }
+                        }
+                        if (ok) { x.has_label = 1; x.label = lab; }
+                    }
+                    auto it = std::lower_bound(set.begin(), set.end(), x, nh_less);
+                    if (it != set.end() && nh_same_key(*it, x)) {
+                        // two atoms, one next hop: the reference keeps whichever advertiser came last; the
+                        // cell cannot tell unless both agree
+                        if (it->iface != x.iface || it->nbr != x.nbr || it->has_nbr != x.has_nbr ||
+                            it->has_label != x.has_label || it->label != x.label) return HSPF_E_UNSUPPORTED;
+                    } else {
+                        set.insert(it, x);
+                    }
+                }
+            }
+            if (set.size() > a->max_paths) set.resize(a->max_paths);
+            o.nh_off = n_nh; o.n_nh = (uint32_t)set.size();
+            if (n_routes < out->routes_cap && n_nh + set.size() <= out->nexthops_cap) {
+                out->routes[n_routes] = o;
+                for (const Nh &x : set) {
+                    hl_nexthop h{};
+                    h.iface = x.iface; h.addr = x.has_addr ? x.addr : 0; h.nbr_router_id = x.has_nbr ? x.nbr : 0;
+                    h.sr_label = x.has_label ? x.label : 0;
+                    h.has_addr = x.has_addr; h.has_nbr = x.has_nbr; h.has_label = x.has_label;
+                    out->nexthops[n_nh + (&x - set.data())] = h;
+                }
+            }
+            ++n_routes; n_nh += (uint32_t)set.size();
+        }
+        out->n_routes = n_routes; out->n_nexthops = n_nh;
+        if (n_routes > out->routes_cap || n_nh > out->nexthops_cap) return HSPF_E_NOMEM;
+        return HSPF_OK;
     } catch (const std::bad_alloc &) {
         return HSPF_E_NOMEM;
     } catch (...) {

@@ -85,7 +85,7 @@ ABI_SIZES = [
 
 def abi_sizes_expected():
     from . import isis, ospf_rib, ospfv3
-    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES + [isis.RNL_DT.itemsize]
+    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES + [isis.RNL_DT.itemsize, CELL_DT.itemsize]
 
 
 def abi_sizes_from_library():
@@ -265,6 +265,145 @@ class Flat:
                 self.handle = None
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------- batched route stage
+CELL_DT = np.dtype([("nh_mask", "<u8"), ("lasthop_mask", "<u8"), ("winner", "<u4"), ("metric", "<u2"),
+                    ("flags", "u1"), ("_pad", "u1")])
+CONTRIB_DT = np.dtype([("vertex", "<u4"), ("origin_id", "<u4"), ("metric", "<u2"), ("sid_class", "<u2"),
+                       ("is_network", "u1"), ("_pad", "u1", (3,))])
+CELL_PRESENT, CELL_CONNECTED, CELL_MIXED_SID = 1, 2, 4
+
+
+class RouteTable:
+    """hspf_ospfv2_rtable: the area's prefixes in route-table order and their advertisers (host);
+    `upload(ctx)` copies it to the device for hspf_ospfv2_routes_batch."""
+
+    def __init__(self, flat: Flat):
+        lib = capi.load_library()
+        lib.hspf_ospfv2_rtable_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.hspf_ospfv2_rtable_free.argtypes = [C.c_void_p]
+        lib.hspf_ospfv2_rtable_free.restype = None
+        lib.hspf_ospfv2_rtable_prefixes.argtypes = [C.c_void_p]
+        lib.hspf_ospfv2_rtable_prefixes.restype = C.c_uint32
+        lib.hspf_ospfv2_rtable_contributors.argtypes = [C.c_void_p]
+        lib.hspf_ospfv2_rtable_contributors.restype = C.c_uint32
+        lib.hspf_ospfv2_rtable_arrays.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),
+                                                  C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_void_p)]
+        lib.hspf_ospfv2_rtable_upload.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib = lib
+        self.flat = flat                      # the table is built from the flat's area image
+        h = C.c_void_p()
+        rc = lib.hspf_ospfv2_rtable_create(flat.handle, C.byref(h))
+        if rc != capi.HSPF_OK:
+            raise capi.HspfError(rc, "hspf_ospfv2_rtable_create failed")
+        self.handle = h
+        self.n_prefixes = int(lib.hspf_ospfv2_rtable_prefixes(h))
+        self.n_contributors = int(lib.hspf_ospfv2_rtable_contributors(h))
+        pp, pl, po, pc = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_void_p()
+        lib.hspf_ospfv2_rtable_arrays(h, C.byref(pp), C.byref(pl), C.byref(po), C.byref(pc))
+        P, K = self.n_prefixes, self.n_contributors
+        as_np = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        self.prefix, self.plen, self.off = as_np(pp, P), as_np(pl, P), as_np(po, P + 1)
+        self.contribs = (np.frombuffer(C.string_at(pc.value, K * CONTRIB_DT.itemsize), CONTRIB_DT).copy()
+                         if K else np.zeros(0, CONTRIB_DT))
+
+    def upload(self, ctx: capi.Context):
+        rc = self.lib.hspf_ospfv2_rtable_upload(ctx.handle, self.handle)
+        if rc != capi.HSPF_OK:
+            raise capi.HspfError(rc, ctx.last_error())
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.hspf_ospfv2_rtable_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+@dataclass
+class BatchRoutes:
+    cells: np.ndarray          # [n_roots, P] CELL_DT
+    status: np.ndarray         # [n_roots] job status words
+    gather_off: np.ndarray     # [n_roots + 1]
+    gather_v: np.ndarray
+    gather_nh: np.ndarray
+    device_ms: tuple           # (SPT batch, route kernel)
+    rc: int = 0
+
+    def gather(self, j):
+        a, b = int(self.gather_off[j]), int(self.gather_off[j + 1])
+        return self.gather_v[a:b], self.gather_nh[a:b]
+
+
+def run_area_batch(ctx: capi.Context, area: Ospfv2Area, root_router_ids, n_prefixes=None) -> BatchRoutes:
+    """hspf_ospfv2_run_area_batch: SPT + intra-area route cells of every listed root router, on the device."""
+    lib = ctx.lib
+    lib.hspf_ospfv2_run_area_batch.argtypes = [C.c_void_p, C.POINTER(AreaStruct), C.POINTER(C.c_uint32), C.c_uint32,
+                                               C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                               C.c_uint32, C.POINTER(C.c_double)]
+    roots = np.ascontiguousarray(root_router_ids, np.uint32)
+    n = len(roots)
+    s = area.as_struct()
+    if n_prefixes is None:
+        n_prefixes = len(area.links) + len(area.network_lsas)       # upper bound
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    for _ in range(2):
+        cells = np.zeros((n, max(n_prefixes, 1)), CELL_DT)
+        status = np.zeros(n, np.uint32)
+        goff = np.zeros(n + 1, np.uint32)
+        gcap = 128 * max(n, 1)
+        gv, gnh = np.zeros(gcap, np.uint32), np.zeros(gcap, np.uint64)
+        P = C.c_uint32()
+        ms = (C.c_double * 2)()
+        rc = lib.hspf_ospfv2_run_area_batch(ctx.handle, C.byref(s), roots.ctypes.data_as(u32p), n, cells.ctypes.data,
+                                            cells.size, C.byref(P), status.ctypes.data_as(u32p), goff.ctypes.data_as(u32p),
+                                            gv.ctypes.data_as(u32p), gnh.ctypes.data_as(u64p), gcap, ms)
+        if rc == capi.HSPF_E_NOMEM and P.value != cells.shape[1]:
+            n_prefixes = P.value
+            continue
+        break
+    if rc not in (capi.HSPF_OK, capi.HSPF_E_JOB_STATUS):
+        raise capi.HspfError(rc, ctx.last_error())
+    if P.value != cells.shape[1]:             # the call wrote rows of P cells into the flat buffer
+        cells = cells.reshape(-1)[: n * P.value].reshape(n, P.value)
+    G = int(goff[n])
+    return BatchRoutes(cells, status, goff, gv[:G].copy(), gnh[:G].copy(), (ms[0], ms[1]), rc)
+
+
+def routes_batch_device(ctx: capi.Context, rt: RouteTable, n_jobs: int, rs, cells_ptr: int, n_gather: int = 0,
+                        gather_job_ptr: int = 0, gather_v_ptr: int = 0, gather_nh_ptr: int = 0):
+    """hspf_ospfv2_routes_batch / _batch16 over DEVICE planes (rs: capi.ResultStruct or capi.Result16Struct
+    holding device pointers); cells_ptr: device buffer of n_jobs * rt.n_prefixes cells.  Enqueued on the ctx
+    stream; the table must have been uploaded."""
+    lib = ctx.lib
+    narrow = isinstance(rs, capi.Result16Struct)
+    fn = lib.hspf_ospfv2_routes_batch16 if narrow else lib.hspf_ospfv2_routes_batch
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = fn(ctx.handle, rt.handle, n_jobs, C.byref(rs), cells_ptr, n_gather, gather_job_ptr or None,
+            gather_v_ptr or None, gather_nh_ptr or None)
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, ctx.last_error())
+
+
+def routes_from_cells(area: Ospfv2Area, rt: RouteTable, cells: np.ndarray, gather_v, gather_nh) -> Ospfv2Result:
+    """hspf_ospfv2_routes_from_cells (host): one job's cells -> routes and next hops as run_area returns them
+    for area.router_id.  rc HSPF_E_UNSUPPORTED is returned in the result (caller: area_from_planes)."""
+    lib = capi.load_library()
+    lib.hspf_ospfv2_routes_from_cells.argtypes = [C.POINTER(AreaStruct), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32),
+                                                  C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(ResultStruct)]
+    cells = np.ascontiguousarray(cells, CELL_DT)
+    assert cells.shape == (rt.n_prefixes,)
+    gv = np.ascontiguousarray(gather_v, np.uint32)
+    gn = np.ascontiguousarray(gather_nh, np.uint64)
+    res = _call_run_area(lib.hspf_ospfv2_routes_from_cells, area, (),
+                         (rt.handle, cells.ctypes.data, gv.ctypes.data_as(C.POINTER(C.c_uint32)),
+                          gn.ctypes.data_as(C.POINTER(C.c_uint64)), len(gv)))
+    if res.rc not in (capi.HSPF_OK, capi.HSPF_E_UNSUPPORTED):
+        raise capi.HspfError(res.rc, "hspf_ospfv2_routes_from_cells failed")
+    return res
 
 
 # ------------------------------------------------------------------------------ synthetic

@@ -220,6 +220,24 @@ typedef struct hl_ospfv2_result {
 } hl_ospfv2_result;
 
 
+/* ------------------------------------------- batched intra-area route cells -- */
+/* One (job, prefix) cell of the device route stage (hspf_ospfv2_routes_batch): what
+ * update_rib_intra_area (route.rs:343-446) leaves for that prefix in the SPT of that job, with the
+ * next hops still as first-hop atoms (include/holo_spf.h).  Prefixes are those of the area's
+ * route table (hspf_ospfv2_rtable_prefixes), in route-table order. */
+#define HL_CELL_PRESENT    0x01u   /* the prefix is reachable in this job                                  */
+#define HL_CELL_CONNECTED  0x02u   /* RouteNetFlags::CONNECTED: the winner's vertex has hops == 0           */
+#define HL_CELL_MIXED_SID  0x04u   /* equal-cost advertisers with different Prefix-SIDs were merged: redo
+                                      this job's routes from its planes (hspf_ospfv2_area_from_planes)       */
+typedef struct hl_route_cell {
+    uint64_t nh_mask;       /* union of the merged advertisers' atom sets                                 */
+    uint64_t lasthop_mask;  /* atoms contributed (last) by an advertiser one hop from the root (PHP rule)   */
+    uint32_t winner;        /* contributor that defines metric / origin / flags / Prefix-SID (table index)  */
+    uint16_t metric;
+    uint8_t  flags;         /* HL_CELL_*                                                                   */
+    uint8_t  _pad;
+} hl_route_cell;
+
 /* ------------------------------------------------ OSPFv2 full routing table -- */
 /* Inputs and output of update_rib_full (holo-ospf/src/route.rs:146-193): the stages that
  * follow the per-area SPF — inter-area networks / routers from Summary-LSAs

@@ -69,6 +69,62 @@ int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *area, const uint32_t *dis
                                  const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv2_result *out);
 
 /*
+ * Batched intra-area route stage on the device (update_rib_intra_area, holo-ospf/src/route.rs:343-446,
+ * for every job of a batch: what-if roots, all routers of an area).
+ *
+ *   hspf_ospfv2_rtable_create   per flattened area: the area's prefixes in route-table order and, per
+ *                               prefix, its advertisers (transit networks, stub links) in the order
+ *                               update_rib_intra_area meets them.  Host only; `flat` and its area image
+ *                               must outlive the call only.
+ *   hspf_ospfv2_rtable_upload   copies the table to the ctx's device.
+ *   hspf_ospfv2_routes_batch    one thread per (job, prefix) over DEVICE planes [n_jobs][V] written by
+ *   hspf_ospfv2_routes_batch16  hspf_run_batch_async / hspf_run_batch16_async with nh_words == 1:
+ *                               cells[n_jobs][P] (device).  `gather_*` (optional) additionally copies
+ *                               nh_mask[job][vertex] of listed vertices: the transit networks next to a
+ *                               job's root, which the host needs to turn atoms into interfaces.
+ *                               Enqueued on the ctx stream behind the batch; no synchronisation.
+ *   hspf_ospfv2_run_area_batch  the whole LSDB-level call for a list of root routers: flatten, upload,
+ *                               one SPT batch, the route kernel, cells (and status words) back to host
+ *                               memory.  cells: [n_roots][P]; P from hspf_ospfv2_rtable_prefixes of a
+ *                               table of the same area (returned through *n_prefixes; HSPF_E_NOMEM if
+ *                               cells_cap is too small).  A job with a non-zero status word has no valid
+ *                               cells (saturation, more than 64 atoms): the caller's single-root path.
+ *   hspf_ospfv2_routes_from_cells   host: one job's cells -> the routes / next hops hspf_ospfv2_run_area
+ *                               returns for area->router_id (out->routes, out->nexthops; vertices and
+ *                               routers are not produced).  `area` carries the root's interface and
+ *                               neighbour state and the same LSDB the table was built from.  gather_v /
+ *                               gather_nh: nh_mask of the transit networks attached to the root.
+ *                               HSPF_E_UNSUPPORTED: a cell is flagged HL_CELL_MIXED_SID, or two atoms
+ *                               resolve to the same next hop with different attributes: use
+ *                               hspf_ospfv2_area_from_planes for this job.
+ */
+typedef struct hspf_ospfv2_rtable hspf_ospfv2_rtable;
+int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable **out);
+void hspf_ospfv2_rtable_free(hspf_ospfv2_rtable *rt);
+uint32_t hspf_ospfv2_rtable_prefixes(const hspf_ospfv2_rtable *rt);
+uint32_t hspf_ospfv2_rtable_contributors(const hspf_ospfv2_rtable *rt);
+/* prefix[P], plen[P], off[P+1]; per contributor: vertex, metric, is_network (any pointer may be NULL) */
+int hspf_ospfv2_rtable_arrays(const hspf_ospfv2_rtable *rt, const uint32_t **prefix, const uint32_t **plen,
+                              const uint32_t **off, const void **contribs /* 16-byte records, route_cells.h */);
+int hspf_ospfv2_rtable_upload(hspf_ctx *ctx, hspf_ospfv2_rtable *rt);
+int hspf_ospfv2_routes_batch(hspf_ctx *ctx, const hspf_ospfv2_rtable *rt, uint32_t n_jobs,
+                             const hspf_result *planes, hl_route_cell *cells,
+                             uint32_t n_gather, const uint32_t *gather_job, const uint32_t *gather_v,
+                             uint64_t *gather_nh);
+int hspf_ospfv2_routes_batch16(hspf_ctx *ctx, const hspf_ospfv2_rtable *rt, uint32_t n_jobs,
+                               const hspf_result16 *planes, hl_route_cell *cells,
+                               uint32_t n_gather, const uint32_t *gather_job, const uint32_t *gather_v,
+                               uint64_t *gather_nh);
+int hspf_ospfv2_run_area_batch(hspf_ctx *ctx, const hl_ospfv2_area *area, const uint32_t *root_router_ids,
+                               uint32_t n_roots, hl_route_cell *cells, uint64_t cells_cap, uint32_t *n_prefixes,
+                               uint32_t *job_status,
+                               uint32_t *gather_off /* [n_roots+1] */, uint32_t *gather_v, uint64_t *gather_nh,
+                               uint32_t gather_cap, double *device_ms /* [2]: SPT batch, route kernel; may be NULL */);
+int hspf_ospfv2_routes_from_cells(const hl_ospfv2_area *area, const hspf_ospfv2_rtable *rt,
+                                  const hl_route_cell *cells, const uint32_t *gather_v, const uint64_t *gather_nh,
+                                  uint32_t n_gather, hl_ospfv2_result *out);
+
+/*
  * The stages of update_rib_full that follow the per-area SPFs (holo-ospf/src/route.rs:146-193):
  * merges the intra-area routes of the attached areas (route_update / route_compare,
  * route.rs:895-971), adds inter-area network routes and inter-area router entries from the

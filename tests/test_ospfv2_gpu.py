@@ -122,3 +122,91 @@ def test_reference_golden_whole_local_rib(ctx, snap):
         g = got[prefix]
         assert (g[0], g[1]) == (metric, rtype), (prefix, g)
         assert [(a or "", b or "") for a, b in g[2]] == [(a or "", b or "") for a, b in nh], (prefix, g[2], nh)
+
+
+# ---- batched route stage on the device (hspf_ospfv2_run_area_batch, csrc/ospfv2_routes.cu) ----------
+def same_routes(res, ref):
+    from holo_b200 import capi
+    assert res.rc == capi.HSPF_OK
+    assert len(res.routes) == len(ref.routes)
+    keep = [n for n in res.routes.dtype.names if n != "nh_off"]
+    assert np.array_equal(res.routes[keep], ref.routes[keep])
+    for a, b in zip(res.routes, ref.routes):
+        assert res.nh(a) == ref.nh(b), (hex(int(a["prefix"])), res.nh(a), ref.nh(b))
+
+
+@pytest.mark.parametrize("V,E,seed,kw", [
+    (100, 400, 1, {}),
+    (300, 1400, 6, dict(cost_choices=[10, 20], lan_fraction=0.1)),          # C5 shape: ECMP, LANs, SR
+])
+def test_run_area_batch_every_root_matches_oracle(ctx, V, E, seed, kw):
+    """One device batch over EVERY router of the area as root: SPTs and the intra-area route cells; each
+    root's cells, decoded with that root's interface state, equal the faithful oracle's run_area routes
+    (prefixes, metrics, origins, flags, Prefix-SIDs, next hops, SR labels)."""
+    t = synth.random_topology(V, E, synth.SEED_BASE + seed, **kw)
+    area0 = ospfv2.synth_area(t, root=0, sr=True)
+    rids = [int(ospfv2.RID_BASE + i) for i in range(V)]
+    b = ospfv2.run_area_batch(ctx, area0, rids)
+    assert b.rc == 0 and not b.status.any()
+    rt = ospfv2.RouteTable(ospfv2.Flat(area0))
+    assert b.cells.shape == (V, rt.n_prefixes)
+    n_ecmp = 0
+    for root in range(V):
+        area = ospfv2.synth_area(t, root=root, sr=True)
+        gv, gn = b.gather(root)
+        res = ospfv2.routes_from_cells(area, rt, b.cells[root], gv, gn)
+        same_routes(res, pyoracle.ospfv2_run_area(area))
+        n_ecmp += int((res.routes["n_nh"] > 1).sum())
+    if kw:
+        assert n_ecmp > 0
+
+
+def test_routes_batch_on_device_planes_wide_and_narrow(ctx):
+    """hspf_ospfv2_routes_batch / _batch16 over planes that never leave the device: both plane widths
+    give the same cells as the one-call batch."""
+    import ctypes as C
+    import torch
+    from holo_b200 import capi
+    V = 200
+    t = synth.random_topology(V, 900, synth.SEED_BASE + 23, cost_choices=[10, 20])
+    area = ospfv2.synth_area(t, root=0, sr=True)
+    flat = ospfv2.Flat(area)
+    rt = ospfv2.RouteTable(flat)
+    rt.upload(ctx)
+    rids = [int(ospfv2.RID_BASE + i) for i in range(V)]
+    want = ospfv2.run_area_batch(ctx, area, rids)
+    roots_v = np.array([flat.router_vertex(r) for r in rids], np.uint32)
+    g = ctx.upload(flat.csr)
+    nv = flat.csr.n_vertices
+    roots = torch.from_numpy(roots_v.astype(np.int32)).cuda()
+    js = capi.JobsStruct()
+    js.n_jobs = V
+    js.roots = C.cast(roots.data_ptr(), C.POINTER(C.c_uint32))
+    P = rt.n_prefixes
+    for narrow in (False, True):
+        dt = torch.int16 if narrow else torch.int32
+        d = torch.zeros((V, nv), dtype=dt, device="cuda")
+        h = torch.zeros((V, nv), dtype=torch.int16, device="cuda")
+        m = torch.zeros((V, nv), dtype=torch.int16 if narrow else torch.int64, device="cuda")
+        st = torch.zeros((V,), dtype=torch.int32, device="cuda")
+        cells = torch.zeros((V * P * ospfv2.CELL_DT.itemsize,), dtype=torch.uint8, device="cuda")
+        if narrow:
+            rs = capi.Result16Struct()
+            rs.dist = C.cast(d.data_ptr(), C.POINTER(C.c_uint16))
+            rs.nh_mask = C.cast(m.data_ptr(), C.POINTER(C.c_uint16))
+        else:
+            rs = capi.ResultStruct()
+            rs.dist = C.cast(d.data_ptr(), C.POINTER(C.c_uint32))
+            rs.nh_mask = C.cast(m.data_ptr(), C.POINTER(C.c_uint64))
+            rs.nh_words = 1
+        rs.hops = C.cast(h.data_ptr(), C.POINTER(C.c_uint16))
+        rs.job_status = C.cast(st.data_ptr(), C.POINTER(C.c_uint32))
+        (ctx.run_device16 if narrow else ctx.run_device)(g, js, rs, sync=False)
+        ospfv2.routes_batch_device(ctx, rt, V, rs, cells.data_ptr())
+        ctx.sync()
+        status = st.cpu().numpy()
+        got = np.frombuffer(cells.cpu().numpy().tobytes(), ospfv2.CELL_DT).reshape(V, P)
+        ok = status == 0                         # a root with more than 16 atoms has no narrow planes
+        assert ok.sum() > V // 2 and (narrow or ok.all())
+        assert got[ok].tobytes() == want.cells[ok].tobytes()
+        assert not (got[~ok]["flags"]).any()     # refused jobs: empty cells
