@@ -166,6 +166,7 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
         Hops hops;
         bool has_label = false;
         uint32_t label = 0;
+        uint32_t origin_id = 0;            // LS origin of an intra-area route
     };
     struct Rtr {
         uint32_t area, metric;
@@ -247,11 +248,21 @@ int rib_full(uint32_t router_id, uint32_t max_paths, const typename T::Area *are
         for (uint32_t i = 0; i < a.spf->n_routes; ++i) {
             const auto &r = a.spf->routes[i];
             const PKey k = T::key(r);
-            if (const Net *cur = find(k))
-                if (r.metric > cur->metric) continue;
+            Net *cur = find(k);
+            if (cur && r.metric > cur->metric) continue;
             Net n{k, r.metric, 0, 0, a.area_id, HL_PATH_INTRA_AREA, r.flags, T::options(r), true, false,
                   hops_of(a, r.nh_off, r.n_nh)};
             T::label_in(n.has_label, n.label, r);
+            n.origin_id = r.origin_lsa_id;
+            if (cur && r.origin_type == 2) {
+                // the areas share one table in the reference: a transit network that maps to a prefix
+                // another area already gave takes the entry over unless its LSA id is lower, and
+                // never merges into it (route.rs:387-397)
+                if (r.origin_lsa_id < cur->origin_id) continue;
+                *cur = std::move(n);
+                clip(cur->hops);
+                continue;
+            }
             offer(std::move(n));
         }
     }

@@ -131,8 +131,11 @@ int hspf_ospfv2_routes_from_cells(const hl_ospfv2_area *area, const hspf_ospfv2_
  * Summary-LSAs (only the backbone's when more than one area is active), re-examines transit
  * areas, and adds AS-external routes through the best ASBR entry.  Pure host table joins over
  * the results of hspf_ospfv2_run_area; no device work.  A prefix that is intra-area in two
- * areas is merged by route_compare; the transit-network overwrite rule (route.rs:388-398)
- * has already been applied inside each area.  Returns HSPF_OK or HSPF_E_NOMEM (counts filled in).
+ * areas is merged by route_compare; the transit-network overwrite rule (route.rs:387-397)
+ * has been applied inside each area and is applied again per route across areas (an area's
+ * route whose LS origin is a transit network stays out when its LSA id is lower than the entry's
+ * origin, otherwise replaces the entry): per route, not per stub link, because the areas' tables
+ * arrive already merged.  Returns HSPF_OK or HSPF_E_NOMEM (counts filled in).
  */
 int hspf_ospfv2_update_rib_full(uint32_t router_id, uint32_t max_paths, const hl_ospfv2_rib_area *areas,
                                 uint32_t n_areas, const hl_ospfv2_external_lsa *ext, uint32_t n_ext,

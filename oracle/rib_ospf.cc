@@ -16,7 +16,9 @@
 //
 // Deviation kept on purpose (documented in include/holo_spf_lsdb.h): the per-area intra-area
 // routes arrive already merged per area, so the shared-table walk of update_rib_intra_area
-// across areas (route.rs:156-160) is applied per route, not per stub link.
+// across areas (route.rs:156-160) is applied per route, not per stub link: an area's route whose
+// LS origin is a transit network meets the table as that network vertex would (route.rs:371-384:
+// kept out when its LSA id is lower than the entry's origin, otherwise it replaces the entry).
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -146,6 +148,7 @@ struct Stage {
         uint8_t prefix_options = 0;
         bool has_label = false;      // sr_label of an intra-area route
         uint32_t label = 0;
+        uint32_t origin_lsa_id = 0;  // origin.lsa_id of an intra-area route
         Nexthops nexthops;
     };
     struct RouteRtr {   // route.rs:57-66
@@ -219,8 +222,13 @@ struct Stage {
                 const Prefix p = V::of(r);
                 auto it = rib.find(p);
                 if (it != rib.end() && r.metric > it->second.metric) continue;   // route.rs:372-376
+                if (it != rib.end() && r.origin_type == 2) {                     // route.rs:387-397
+                    if (r.origin_lsa_id < it->second.origin_lsa_id) continue;
+                    rib.erase(it);
+                }
                 RouteNet n;
                 n.path_type = HL_PATH_INTRA_AREA; n.has_area = true; n.area_id = a.area_id; n.metric = r.metric;
+                n.origin_lsa_id = r.origin_lsa_id;
                 n.flags = r.flags; n.prefix_options = V::opts(r); n.nexthops = lift(a, r.nh_off, r.n_nh);
                 V::label(n.has_label, n.label, r);
                 route_update(rib, p, std::move(n), max_paths);

@@ -67,7 +67,10 @@ def random_instance(seed: int):
         for pi in sorted(rng.choice(len(pool_prefixes) - 1, int(rng.integers(1, 8)), replace=False)):
             p, m = pool_prefixes[int(pi)]
             off, n = hops()
-            routes.append((p, m, int(rng.integers(0, 40)), int(rng.integers(0, 2)), 1, 0, 0, 0, 0, 0, 0, 0, (0, 0), 0, off, n))
+            # LS origin: a router (stub link) or a transit network with a small LSA id, so that the
+            # cross-area transit-network rule (route.rs:387-397) meets equal metrics and both id orders
+            routes.append((p, m, int(rng.choice([5, 5, 10, 20, 33])), int(rng.integers(0, 2)), int(rng.choice([1, 1, 2])),
+                           0, 0, 0, int(rng.integers(1, 6)), 0, 0, 0, (0, 0), 0, off, n))
         res = ospfv2.Ospfv2Result(np.zeros(0, ospfv2.SPT_VERTEX_DT), np.asarray(routers, ospfv2.ROUTE_RTR_DT),
                                   np.asarray(routes, ospfv2.ROUTE_NET_DT), np.asarray(nhs, ospfv2.NEXTHOP_DT)
                                   if nhs else np.zeros(0, ospfv2.NEXTHOP_DT), bool(rng.integers(0, 2)), True)
@@ -184,7 +187,8 @@ def random_instance_v3(seed: int):
         for pi in sorted(rng.choice(len(pool) - 1, int(rng.integers(1, 8)), replace=False)):
             p, ln = pool[int(pi)]
             off, n = hops()
-            routes.append((ospfv3.ip_rec(p), ln, int(rng.integers(0, 2)), 1, 0, int(rng.integers(0, 40)), 0, 0, off, n))
+            routes.append((ospfv3.ip_rec(p), ln, int(rng.integers(0, 2)), int(rng.choice([1, 1, 2])), 0,
+                           int(rng.choice([5, 5, 10, 20, 33])), 0, int(rng.integers(1, 6)), off, n))
         mk = lambda rows, dt: np.asarray(rows, dtype=dt) if rows else np.zeros(0, dt)
         res = ospfv3.Ospfv3Result(np.zeros(0, ospfv3.SPT_VERTEX6_DT), mk(routers, ospfv2.ROUTE_RTR_DT),
                                   mk(routes, ospfv3.ROUTE_NET6_DT), mk(nhs, ospfv3.NEXTHOP6_DT),
@@ -452,3 +456,36 @@ def test_rib_stage_rejects_out_of_range_next_hop_slices():
         broken.routes["n_nh"][0] = 1_000_000
         with pytest.raises(capi.HspfError):
             ospf_rib.rib_diff(None, broken)
+
+
+def _two_area_tables(origin_b, lsa_id_b, metric_b=10):
+    """Area 0 reaches 10.0.0.0/24 through transit network 5 (metric 10, next hop on interface 1);
+    area 1 reaches the same prefix with the given origin (next hop on interface 2)."""
+    def area(aid, sk, origin_type, lsa_id, metric):
+        ifaces = np.zeros(1, ospfv2.IFACE_DT)
+        ifaces[0] = (100 + sk, sk, ospfv2.IF_P2P, (0, 0, 0), 0, 0, 0, 0)
+        nhs = np.asarray([(0, 7, 0x02020200 + sk, 0, 1, 1, 0, 0)], ospfv2.NEXTHOP_DT)
+        routes = np.asarray([(0x0A000000, 0xFFFFFF00, metric, 0, origin_type, 0, 0, 0x02020200 + sk, lsa_id, 0, 0, 0, (0, 0), 0, 0, 1)],
+                            ospfv2.ROUTE_NET_DT)
+        res = ospfv2.Ospfv2Result(np.zeros(0, ospfv2.SPT_VERTEX_DT), np.zeros(0, ospfv2.ROUTE_RTR_DT), routes, nhs, False, True)
+        return ospf_rib.RibArea(aid, res, ifaces, np.zeros(0, ospf_rib.SUMMARY_LSA_DT), True)
+    return [area(0, 1, 2, 5, 10), area(1, 2, origin_b, lsa_id_b, metric_b)]
+
+
+@pytest.mark.parametrize("origin_b,lsa_id_b,metric_b,want", [
+    (2, 7, 10, [2]),        # a transit network with a higher LSA id takes the entry over (route.rs:387-397)
+    (2, 5, 10, [2]),        # ... or an equal one
+    (2, 3, 10, [1]),        # a lower one stays out
+    (1, 3, 10, [1, 2]),     # a stub link merges its next hops (route_update, route.rs:916-932)
+    (2, 7, 11, [1]),        # a longer path never replaces
+    (2, 3, 9, [1]),         # the id rule comes before route_compare: a shorter path with a lower id stays out too
+])
+def test_transit_network_rule_across_areas(origin_b, lsa_id_b, metric_b, want):
+    areas = _two_area_tables(origin_b, lsa_id_b, metric_b)
+    empty = np.zeros(0, ospf_rib.EXTERNAL_LSA_DT)
+    for fn in (ospf_rib.update_rib_full, pyoracle.ospfv2_update_rib_full):
+        rib = fn(0x01010101, 16, areas, empty)
+        assert len(rib.routes) == 1
+        r = rib.routes[0]
+        hops = rib.nexthops[int(r["nh_off"]): int(r["nh_off"]) + int(r["n_nh"])]
+        assert [int(h["iface"]) for h in hops] == want, fn
