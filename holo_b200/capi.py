@@ -104,6 +104,7 @@ EXPORTS = [
     "hspf_xchg_push", "hspf_xchg_wait", "hspf_xchg_release", "hspf_xchg_consumer_stream", "hspf_xchg_sync",
     "hspf_xchg_last_error", "hspf_xchg_destroy", "hspf_xchg_attach_ptr", "hspf_xchg_base", "hspf_xchg_set_push_bytes",
     "hspf_xchg_acquire_direct", "hspf_xchg_peer_deltas", "hspf_xchg_publish", "hspf_ctx_set_peer_slots",
+    "hspf_graph_update_costs",
 ]
 
 
@@ -354,6 +355,14 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hspf_sync(self.handle))
+
+    def update_costs(self, graph: "Graph", edges, costs):
+        """hspf_graph_update_costs: permanent cost change of existing edges, patched in place on the device."""
+        e = np.ascontiguousarray(edges, np.uint32)
+        c = np.ascontiguousarray(costs, np.uint32)
+        assert e.shape == c.shape
+        self.lib.hspf_graph_update_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        self._check(self.lib.hspf_graph_update_costs(self.handle, graph.handle, len(e), e.ctypes.data, c.ctypes.data))
 
     def set_peer_slots(self, deltas):
         """Fused exchange: the next 16-bit launches also store dist / hops / nh_mask / status into the

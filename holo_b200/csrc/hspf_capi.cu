@@ -31,6 +31,9 @@ struct hspf_graph {
     bool has_quads = false;    // quad-space image present (spf_quad_kernel eligible, see quad_layout.h)
     QuadDev q{};
     std::string quad_why;      // why the quad image was not built
+    // host copies hspf_graph_update_costs validates against
+    std::vector<uint32_t> h_row;
+    std::vector<uint8_t> h_vflags;
 };
 
 struct hspf_ctx {
@@ -781,6 +784,8 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         }
         G->d.delta = delta;
         G->max_indeg = max_indeg;
+        G->h_row.assign(g->row_ptr, g->row_ptr + V + 1);
+        G->h_vflags.assign(g->vflags, g->vflags + V);
         for (uint32_t v = 0; v < V; ++v)
             if (g->vflags[v] & (HSPF_VF_LEAF | HSPF_VF_LEAF_UNLESS_ROOT)) G->has_leaf = true;
         *out = G;
@@ -789,6 +794,42 @@ int hspf_graph_upload(hspf_ctx *ctx, const hspf_csr *g, hspf_graph **out) {
         return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
     } catch (...) {
         return fail(ctx, HSPF_E_INVAL, "unexpected exception");
+    }
+}
+
+int hspf_graph_update_costs(hspf_ctx *ctx, hspf_graph *g, uint32_t n, const uint32_t *edges, const uint32_t *costs) {
+    if (!ctx || !g || (n && (!edges || !costs))) return HSPF_E_INVAL;
+    if (n == 0) return HSPF_OK;
+    try {
+        if (g->d.flags & HSPF_GF_HOPCOUNT) return fail(ctx, HSPF_E_UNSUPPORTED, "hop-count graphs have fixed costs");
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t e = edges[i], c = costs[i];
+            if (e >= g->d.E) return fail(ctx, HSPF_E_INVAL, "edge out of range");
+            if (c == HSPF_COST_DISABLED) return fail(ctx, HSPF_E_INVAL, "cost 0xFFFFFFFF is reserved");
+            const uint32_t tail = (uint32_t)(std::upper_bound(g->h_row.begin(), g->h_row.end(), e) - g->h_row.begin()) - 1;
+            if (c == 0 && (g->h_vflags[tail] & HSPF_VF_HOP))
+                return fail(ctx, HSPF_E_NEEDS_ORACLE, "zero-cost link out of a hop-counting vertex");
+            if (g->d.iedge16 && c > 0xFFFFu) return fail(ctx, HSPF_E_UNSUPPORTED, "cost does not fit the packed image");
+            if (g->has_quads && (c > 65534u || (unsigned long long)c > (3ull << g->q.shift)))
+                return fail(ctx, HSPF_E_UNSUPPORTED, "cost outside the bucket ring of the uploaded image");
+        }
+        cudaError_t er = cudaSetDevice(ctx->device);
+        uint32_t *d = nullptr;
+        if (er == cudaSuccess) er = cudaMalloc(&d, (size_t)n * 8);
+        if (er != cudaSuccess) return cuda_fail(ctx, er, "cudaMalloc(cost patch)");
+        er = cudaMemcpyAsync(d, edges, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (er == cudaSuccess) er = cudaMemcpyAsync(d + n, costs, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (er == cudaSuccess) {
+            hspf::patch_costs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g->d, g->q, g->has_quads, n, d, d + n);
+            er = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d);
+        if (er != cudaSuccess) return cuda_fail(ctx, er, "cost patch");
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, HSPF_E_NOMEM, "host allocation failed");
     }
 }
 

@@ -925,4 +925,128 @@ int hspf_ospfv2_routes_from_cells(const hl_ospfv2_area *a, const hspf_ospfv2_rta
     }
 }
 
+
+/* ---- trigger-keyed recomputation (holo_spf_lsdb.h) ---------------------------------------------- */
+
+int hspf_ospfv2_spf_computation_type(const hl_lsa_trigger *tr, uint32_t n, hl_spf_computation *out) {
+    if (!out || (n && !tr)) return HSPF_E_INVAL;
+    out->kind = HL_SPF_PARTIAL;
+    out->n_inter_network = out->n_inter_router = out->n_external = 0;
+    // Router- and Network-LSAs are topology; the SR opaque LSAs are treated the same way (ospfv2/spf.rs:101-121)
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto &t = tr[i];
+        const bool sr_opaque_area = t.lsa_type == 10 && (t.opaque_type == 4 || t.opaque_type == 7 || t.opaque_type == 8);
+        const bool sr_opaque_as = t.lsa_type == 11 && t.opaque_type == 7;
+        if (t.lsa_type == 1 || t.lsa_type == 2 || sr_opaque_area || sr_opaque_as) {
+            out->kind = HL_SPF_FULL;
+            return HSPF_OK;
+        }
+    }
+    try {
+        std::vector<std::pair<uint32_t, uint32_t>> net, ext;      // (address, prefix length): Ipv4Network order
+        std::vector<uint32_t> rtr;
+        for (uint32_t i = 0; i < n; ++i) {
+            const auto &t = tr[i];
+            if (t.lsa_type == 3) net.emplace_back(t.lsa_id, (uint32_t)__builtin_popcount(t.mask));
+            else if (t.lsa_type == 4) rtr.push_back(t.lsa_id);
+            else if (t.lsa_type == 5) ext.emplace_back(t.lsa_id, (uint32_t)__builtin_popcount(t.mask));
+        }
+        auto uniq = [](auto &v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+        uniq(net); uniq(rtr); uniq(ext);
+        out->n_inter_network = (uint32_t)net.size();
+        out->n_inter_router = (uint32_t)rtr.size();
+        out->n_external = (uint32_t)ext.size();
+        if (net.size() > out->cap || rtr.size() > out->cap || ext.size() > out->cap) return HSPF_E_NOMEM;
+        if ((!net.empty() && !out->inter_network) || (!rtr.empty() && !out->inter_router) || (!ext.empty() && !out->external))
+            return HSPF_E_INVAL;
+        auto mask_of = [](uint32_t len) { return len == 0 ? 0u : 0xFFFFFFFFu << (32 - len); };
+        for (size_t i = 0; i < net.size(); ++i) out->inter_network[i] = hl_ipv4_net{net[i].first, mask_of(net[i].second)};
+        for (size_t i = 0; i < rtr.size(); ++i) out->inter_router[i] = rtr[i];
+        for (size_t i = 0; i < ext.size(); ++i) out->external[i] = hl_ipv4_net{ext[i].first, mask_of(ext[i].second)};
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    }
+}
+
+int hspf_ospfv2_flat_update(hspf_ospfv2_flat *flat, const hl_ospfv2_area *na, const hl_lsa_trigger *tr, uint32_t n,
+                            uint32_t *kind, uint32_t *edges, uint32_t *costs, uint32_t cap, uint32_t *n_changed) {
+    if (!flat || !flat->area || !na || !kind || !n_changed || (n && !tr)) return HSPF_E_INVAL;
+    try {
+        *n_changed = 0;
+        hspf_ospfv2_flat &f = *flat;
+        const hl_ospfv2_area *oa = f.area;
+        auto rebuild = [&]() -> int {
+            hspf_ospfv2_flat fresh;
+            const int rc = flatten(na, fresh);
+            if (rc) return rc;
+            f = std::move(fresh);
+            *kind = HSPF_FLAT_REBUILT;
+            return HSPF_OK;
+        };
+        // the shortcuts below index the new image with the old image's LSA and link positions
+        const bool same_layout = oa->n_router_lsas == na->n_router_lsas && oa->n_network_lsas == na->n_network_lsas &&
+                                 oa->n_links == na->n_links && oa->n_attached == na->n_attached;
+        std::vector<uint32_t> cost_rows;       // router vertices whose link metrics may have changed
+        bool graph_trigger = false;
+        for (uint32_t i = 0; i < n; ++i) {
+            const auto &t = tr[i];
+            if (t.lsa_type != 1 && t.lsa_type != 2) continue;   // nothing else bears on the graph
+            graph_trigger = true;
+            if (!same_layout) return rebuild();
+            if (t.lsa_type == 1) {
+                // the LSA at the same index must be this LSA, before and after, with the same links
+                const hl_ospfv2_router_lsa *ol = nullptr, *nl = nullptr;
+                uint32_t idx = 0;
+                for (; idx < oa->n_router_lsas; ++idx)
+                    if (oa->router_lsas[idx].adv_rtr == t.adv_rtr && oa->router_lsas[idx].lsa_id == t.lsa_id) { ol = &oa->router_lsas[idx]; break; }
+                if (!ol) return rebuild();                                      // a new LSA: a vertex may appear
+                nl = &na->router_lsas[idx];
+                if (nl->adv_rtr != t.adv_rtr || nl->lsa_id != t.lsa_id) return rebuild();
+                if ((ol->age == HL_LSA_MAX_AGE) != (nl->age == HL_LSA_MAX_AGE)) return rebuild();
+                if (ol->n_links != nl->n_links || ol->link_off != nl->link_off) return rebuild();
+                for (uint32_t k = 0; k < ol->n_links; ++k) {
+                    const auto &x = oa->links[ol->link_off + k], &y = na->links[nl->link_off + k];
+                    if (x.link_type != y.link_type || x.link_id != y.link_id || x.link_data != y.link_data) return rebuild();
+                }
+                if (t.adv_rtr == t.lsa_id && nl->age != HL_LSA_MAX_AGE) {
+                    auto it = f.rtr_vertex.find(t.adv_rtr);
+                    if (it == f.rtr_vertex.end() || f.lsa_of[it->second] != idx) return rebuild();
+                    cost_rows.push_back(it->second);
+                }
+            } else {
+                const hl_ospfv2_network_lsa *ol = nullptr;
+                uint32_t idx = 0;
+                for (; idx < oa->n_network_lsas; ++idx)
+                    if (oa->network_lsas[idx].adv_rtr == t.adv_rtr && oa->network_lsas[idx].lsa_id == t.lsa_id) { ol = &oa->network_lsas[idx]; break; }
+                if (!ol) return rebuild();
+                const hl_ospfv2_network_lsa *nl = &na->network_lsas[idx];
+                if (nl->adv_rtr != t.adv_rtr || nl->lsa_id != t.lsa_id) return rebuild();
+                if ((ol->age == HL_LSA_MAX_AGE) != (nl->age == HL_LSA_MAX_AGE)) return rebuild();
+                if (ol->n_att != nl->n_att || ol->att_off != nl->att_off) return rebuild();
+                for (uint32_t k = 0; k < ol->n_att; ++k)
+                    if (oa->attached[ol->att_off + k] != na->attached[nl->att_off + k]) return rebuild();
+            }
+        }
+        f.area = na;
+        if (!graph_trigger) { *kind = HSPF_FLAT_UNCHANGED; return HSPF_OK; }
+        uint32_t changed = 0;
+        for (uint32_t v : cost_rows)
+            for (uint32_t e = f.row[v]; e < f.row[v + 1]; ++e) {
+                const uint32_t c = na->links[f.link_index[e]].metric;
+                if (c == f.cost[e]) continue;
+                f.cost[e] = c;
+                if (changed < cap && edges && costs) { edges[changed] = e; costs[changed] = c; }
+                ++changed;
+            }
+        *n_changed = changed;
+        *kind = changed ? HSPF_FLAT_COSTS : HSPF_FLAT_UNCHANGED;
+        return changed > cap ? HSPF_E_NOMEM : HSPF_OK;
+    } catch (const std::bad_alloc &) {
+        return HSPF_E_NOMEM;
+    } catch (...) {
+        return HSPF_E_INVAL;
+    }
+}
+
 }  // extern "C"

@@ -27,31 +27,47 @@ __global__ void __launch_bounds__(256)
 route_cells_kernel(uint32_t n_jobs, uint32_t P, uint32_t V, const uint32_t *__restrict__ off,
                    const RouteContrib *__restrict__ contribs, const D *__restrict__ dist,
                    const uint16_t *__restrict__ hops, const N *__restrict__ nh, const uint32_t *__restrict__ job_status,
-                   hl_route_cell *__restrict__ cells, uint32_t n_gather, const uint32_t *__restrict__ gather_job,
-                   const uint32_t *__restrict__ gather_v, uint64_t *__restrict__ gather_nh) {
+                   hl_route_cell *__restrict__ cells, bool aligned16, uint32_t n_gather,
+                   const uint32_t *__restrict__ gather_job, const uint32_t *__restrict__ gather_v,
+                   uint64_t *__restrict__ gather_nh) {
+    // a warp owns 32 consecutive cells = one contiguous 768-byte span of the output: the cells are staged in
+    // shared memory and leave as 48 16-byte stores (full sectors) instead of 96 scattered 8-byte ones
+    __shared__ __align__(16) uint64_t stage[8][96];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t total = (uint64_t)n_jobs * P;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total + n_gather; idx += stride) {
-        if (idx >= total) {                                   // the few plane values the host decode needs
-            const uint32_t g = (uint32_t)(idx - total);
-            const uint32_t job = gather_job[g], v = gather_v[g];
-            gather_nh[g] = (job < n_jobs && v < V) ? (uint64_t)nh[(size_t)job * V + v] : 0;
-            continue;
-        }
-        const uint32_t job = (uint32_t)(idx / P), p = (uint32_t)(idx - (uint64_t)job * P);
+    const uint64_t n_tiles = (total + 31) / 32;
+    const uint64_t wstride = (uint64_t)gridDim.x * 8;
+    for (uint64_t tile = (uint64_t)blockIdx.x * 8 + wib; tile < n_tiles; tile += wstride) {
+        const uint64_t idx = tile * 32 + lane;
         hl_route_cell c;
-        if (job_status && job_status[job] != 0) {             // planes of a refused job are undefined
-            c.nh_mask = 0; c.lasthop_mask = 0; c.winner = 0xFFFFFFFFu; c.metric = 0; c.flags = 0; c._pad = 0;
-        } else {
-            const size_t base = (size_t)job * V;
-            const Planes pl{dist + base, hops + base, nh + base};
-            c = hspf::route_cell_eval(pl, contribs, off[p], off[p + 1]);
+        c.nh_mask = 0; c.lasthop_mask = 0; c.winner = 0xFFFFFFFFu; c.metric = 0; c.flags = 0; c._pad = 0;
+        if (idx < total) {
+            const uint32_t job = (uint32_t)(idx / P), p = (uint32_t)(idx - (uint64_t)job * P);
+            if (!(job_status && job_status[job] != 0)) {      // planes of a refused job are undefined: empty cells
+                const size_t base = (size_t)job * V;
+                const Planes pl{dist + base, hops + base, nh + base};
+                c = hspf::route_cell_eval(pl, contribs, off[p], off[p + 1]);
+            }
         }
-        // 24-byte cell as three 8-byte stores (the struct is 8-byte aligned)
-        uint64_t *o = reinterpret_cast<uint64_t *>(cells + idx);
-        o[0] = c.nh_mask;
-        o[1] = c.lasthop_mask;
-        o[2] = (uint64_t)c.winner | ((uint64_t)c.metric << 32) | ((uint64_t)c.flags << 48);
+        const uint64_t w2 = (uint64_t)c.winner | ((uint64_t)c.metric << 32) | ((uint64_t)c.flags << 48);
+        if (aligned16 && tile * 32 + 32 <= total) {
+            uint64_t *s = stage[wib];
+            s[lane * 3 + 0] = c.nh_mask; s[lane * 3 + 1] = c.lasthop_mask; s[lane * 3 + 2] = w2;
+            __syncwarp();
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+            uint4 *o4 = reinterpret_cast<uint4 *>(cells + tile * 32);
+            o4[lane] = s4[lane];
+            if (lane < 16) o4[32 + lane] = s4[32 + lane];
+            __syncwarp();
+        } else if (idx < total) {
+            uint64_t *o = reinterpret_cast<uint64_t *>(cells + idx);
+            o[0] = c.nh_mask; o[1] = c.lasthop_mask; o[2] = w2;
+        }
+    }
+    // the few plane values the host decode needs
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_gather; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t job = gather_job[g], v = gather_v[g];
+        gather_nh[g] = (job < n_jobs && v < V) ? (uint64_t)nh[(size_t)job * V + v] : 0;
     }
 }
 static_assert(sizeof(hl_route_cell) == 24, "hl_route_cell layout");
@@ -63,17 +79,18 @@ int launch_cells(hspf_ctx *ctx, const hspf_ospfv2_rtable *rt, uint32_t n_jobs, c
     if (!ctx || !rt || !rt->d_blob || !dist || !hops || !nh || !cells) return HSPF_E_INVAL;
     if (n_gather && (!gather_job || !gather_v || !gather_nh)) return HSPF_E_INVAL;
     const uint32_t P = (uint32_t)rt->t.prefix.size();
-    const uint64_t total = (uint64_t)n_jobs * P + n_gather;
-    if (total == 0) return HSPF_OK;
+    const uint64_t total = (uint64_t)n_jobs * P;
+    if (total + n_gather == 0) return HSPF_OK;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return HSPF_E_CUDA;
-    // one resident wave (8 blocks of 256 per SM), grid-stride beyond that
-    const uint64_t want = (total + 255) / 256;
+    // one resident wave (8 blocks of 256 per SM), warp-tile-stride beyond that
+    const uint64_t want = std::max<uint64_t>((total + 255) / 256, 1);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 8);
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(cells) & 15u) == 0;
     cudaStream_t st = static_cast<cudaStream_t>(hspf_stream(ctx));
     route_cells_kernel<Planes, D, N><<<blocks, 256, 0, st>>>(n_jobs, P, rt->t.n_vertices, rt->d_off, rt->d_contribs, dist, hops,
-                                                             nh, status, cells, n_gather, gather_job, gather_v, gather_nh);
+                                                             nh, status, cells, aligned16, n_gather, gather_job, gather_v, gather_nh);
     if (cudaGetLastError() != cudaSuccess) return HSPF_E_CUDA;
     hspf_note_launches(ctx, 1);
     return HSPF_OK;

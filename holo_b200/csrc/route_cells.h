@@ -26,7 +26,7 @@
 namespace hspf {
 
 // One (vertex, prefix) advertisement, in the order update_rib_intra_area meets them.
-struct RouteContrib {
+struct alignas(16) RouteContrib {
     uint32_t vertex;      // SPT vertex (flattener order)
     uint32_t origin_id;   // LSA id of the vertex's LSA (route.origin, route.rs:356-360)
     uint16_t metric;      // stub link metric; 0 for a transit network's own prefix
@@ -67,6 +67,19 @@ struct PlanesNarrow {
     HSPF_HD uint64_t n(uint32_t v) const { return nh[v]; }
 };
 
+// one 16-byte record, one load
+HSPF_HD RouteContrib load_contrib(const RouteContrib *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    RouteContrib k;
+    k.vertex = r.x; k.origin_id = r.y; k.metric = (uint16_t)(r.z & 0xFFFFu); k.sid_class = (uint16_t)(r.z >> 16);
+    k.is_network = (uint8_t)(r.w & 0xFFu); k._pad[0] = k._pad[1] = k._pad[2] = 0;
+    return k;
+#else
+    return *p;
+#endif
+}
+
 // The walk of one prefix's contributors = the sequence of route_update calls update_rib_intra_area
 // makes for that prefix (route.rs:362-443):
 //   * a contributor off the SPT adds nothing;
@@ -84,7 +97,7 @@ HSPF_HD hl_route_cell route_cell_eval(const Planes &pl, const RouteContrib *cont
     c.nh_mask = 0; c.lasthop_mask = 0; c.winner = 0xFFFFFFFFu; c.metric = 0; c.flags = 0; c._pad = 0;
     uint32_t cur_origin = 0, cur_class = 0;
     for (uint32_t i = begin; i < end; ++i) {
-        const RouteContrib k = contribs[i];
+        const RouteContrib k = load_contrib(contribs + i);
         if (!pl.reached(k.vertex)) continue;
         uint32_t m = pl.d(k.vertex) + k.metric;
         if (m > 0xFFFFu) m = 0xFFFFu;

@@ -772,4 +772,37 @@ __global__ void __launch_bounds__(T, 3) spf_quad_kernel(const QuadArgs a) {
     }
 }
 
+// Permanent cost change of listed forward edges (hspf_graph_update_costs): every copy of an edge's cost in
+// the device image — CSR edge, transposed edge (found by its forward index among the head's in-edges),
+// their packed twins, the quad-padded in-edge rows of spf_batch_kernel and the two quad-space records
+// (QuadHost::fpos / ipos) — is rewritten by one thread per edge.  Runs alone on the ctx stream.
+__global__ void patch_costs_kernel(DevGraph g, QuadDev q, bool has_quads, uint32_t n, const uint32_t *edges,
+                                   const uint32_t *costs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = edges[i], c = costs[i];
+    uint2 *edge = const_cast<uint2 *>(g.edge);
+    const uint32_t v = edge[e].x;
+    edge[e].y = c;
+    if (g.edge16) const_cast<uint32_t *>(g.edge16)[e] = v | (c << 16);
+    uint4 *iedge = const_cast<uint4 *>(g.iedge);
+    for (uint32_t k = g.irow[v]; k < g.irow[v + 1]; ++k) {
+        if (iedge[k].z != e) continue;
+        iedge[k].y = c;
+        if (g.iedge16) {
+            const uint32_t rec = iedge[k].x | (c << 16);
+            const_cast<uint32_t *>(g.iedge16)[k] = rec;
+            if (g.iquad) reinterpret_cast<uint32_t *>(const_cast<uint4 *>(g.iquad))[(size_t)g.iquad_row[v] * 4 + (k - g.irow[v])] = rec;
+        }
+        break;
+    }
+    if (has_quads) {
+        uint32_t *fq = reinterpret_cast<uint32_t *>(const_cast<uint4 *>(q.fq));
+        uint32_t *iq = reinterpret_cast<uint32_t *>(const_cast<uint4 *>(q.iq));
+        const uint32_t fp = q.fpos[e], ip = q.ipos[e];
+        fq[fp] = (fq[fp] & 0xFFFFu) | (c << 16);
+        iq[ip] = (iq[ip] & 0xFFFFu) | (c << 16);
+    }
+}
+
 }  // namespace hspf

@@ -236,6 +236,10 @@ class Flat:
         if rc != capi.HSPF_OK:
             raise capi.HspfError(rc, "hspf_ospfv2_flatten failed")
         self.handle = h
+        self._load()
+
+    def _load(self):
+        lib, h = self.lib, self.handle
         cs = capi.CsrStruct()
         lib.hspf_ospfv2_flat_csr(h, C.byref(cs))
         V, E = cs.n_vertices, cs.n_edges
@@ -265,6 +269,54 @@ class Flat:
                 self.handle = None
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------- trigger-keyed recomputation
+TRIGGER_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("mask", "<u4"), ("lsa_type", "u1"), ("opaque_type", "u1"),
+                       ("_pad", "u1", (2,))])
+SPF_FULL, SPF_PARTIAL = 1, 2
+FLAT_UNCHANGED, FLAT_COSTS, FLAT_REBUILT = 0, 1, 2
+
+
+class SpfComputationStruct(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("n_inter_network", C.c_uint32), ("n_inter_router", C.c_uint32),
+                ("n_external", C.c_uint32), ("cap", C.c_uint32), ("inter_network", C.c_void_p),
+                ("inter_router", C.c_void_p), ("external", C.c_void_p)]
+
+
+def spf_computation_type(triggers, fn=None):
+    """hspf_ospfv2_spf_computation_type -> (kind, inter_network [(addr, mask)], inter_router [id], external)."""
+    tr = np.ascontiguousarray(triggers, TRIGGER_DT)
+    if fn is None:
+        fn = capi.load_library().hspf_ospfv2_spf_computation_type
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SpfComputationStruct)]
+    cap = max(len(tr), 1)
+    net, rtr, ext = np.zeros(cap, IPV4_NET_DT), np.zeros(cap, np.uint32), np.zeros(cap, IPV4_NET_DT)
+    s = SpfComputationStruct(0, 0, 0, 0, cap, net.ctypes.data, rtr.ctypes.data, ext.ctypes.data)
+    rc = fn(tr.ctypes.data, len(tr), C.byref(s))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "spf_computation_type failed")
+    pairs = lambda a, k: [(int(x["addr"]), int(x["mask"])) for x in a[:k]]
+    return s.kind, pairs(net, s.n_inter_network), [int(x) for x in rtr[: s.n_inter_router]], pairs(ext, s.n_external)
+
+
+def flat_update(flat: "Flat", new_area: Ospfv2Area, triggers):
+    """hspf_ospfv2_flat_update: returns (kind, edges, costs); the Flat object's numpy views are refreshed."""
+    lib = flat.lib
+    lib.hspf_ospfv2_flat_update.argtypes = [C.c_void_p, C.POINTER(AreaStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                            C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    tr = np.ascontiguousarray(triggers, TRIGGER_DT)
+    cap = max(int(flat.csr.n_edges), 1)
+    edges, costs = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    kind, n = C.c_uint32(), C.c_uint32()
+    s = new_area.as_struct()
+    rc = lib.hspf_ospfv2_flat_update(flat.handle, C.byref(s), tr.ctypes.data, len(tr), C.byref(kind), edges.ctypes.data,
+                                     costs.ctypes.data, cap, C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "hspf_ospfv2_flat_update failed")
+    flat.area, flat._s = new_area, s            # the native flat now refers to the new image
+    flat._load()
+    return kind.value, edges[: n.value].copy(), costs[: n.value].copy()
 
 
 # ------------------------------------------------------------------- batched route stage

@@ -220,6 +220,35 @@ typedef struct hl_ospfv2_result {
 } hl_ospfv2_result;
 
 
+/* ----------------------------------------------------------- SPF triggers -- */
+/* One LSA whose change scheduled the SPF run (SpfTriggerLsa, holo-ospf/src/spf.rs:115-120): the key and
+ * type of `new`.  lsa_type: 1 router, 2 network, 3 summary (network), 4 summary (ASBR), 5 AS-external,
+ * 10 area-scope opaque, 11 AS-scope opaque; opaque_type (types 10 / 11): 4 Router-Information,
+ * 7 Extended-Prefix, 8 Extended-Link; mask: the body's network mask (types 3 and 5). */
+typedef struct hl_lsa_trigger {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t mask;
+    uint8_t  lsa_type;
+    uint8_t  opaque_type;
+    uint8_t  _pad[2];
+} hl_lsa_trigger;
+
+/* SpfComputation (spf.rs:123-140, ospfv2/spf.rs:98-171) */
+#define HL_SPF_FULL     1u   /* a topological (or SR) change: every area's SPT and the whole table            */
+#define HL_SPF_PARTIAL  2u   /* only summary / external LSAs changed: the SPTs stand, the listed destinations
+                                are re-examined (update_rib_partial, route.rs:196-340)                        */
+typedef struct hl_spf_computation {
+    uint32_t kind;                 /* HL_SPF_*                                                               */
+    uint32_t n_inter_network;      /* prefixes of changed type-3 LSAs (with_netmask(lsa_id, mask), host bits kept) */
+    uint32_t n_inter_router;       /* ASBR ids of changed type-4 LSAs                                          */
+    uint32_t n_external;           /* prefixes of changed type-5 LSAs                                          */
+    uint32_t cap;                  /* capacity of each of the three arrays below                              */
+    hl_ipv4_net *inter_network;    /* sorted, unique (BTreeSet)                                               */
+    uint32_t    *inter_router;
+    hl_ipv4_net *external;
+} hl_spf_computation;
+
 /* ------------------------------------------- batched intra-area route cells -- */
 /* One (job, prefix) cell of the device route stage (hspf_ospfv2_routes_batch): what
  * update_rib_intra_area (route.rs:343-446) leaves for that prefix in the SPT of that job, with the

@@ -229,6 +229,14 @@ void hspf_graph_free(hspf_ctx *ctx, hspf_graph *g);
 int hspf_run_batch(hspf_ctx *ctx, const hspf_graph *g, const hspf_jobs *jobs,
                    const hspf_result *out, uint32_t flags);
 
+/* Permanent cost change of existing edges of an uploaded graph (an interface cost change: the structure
+ * stands).  Every cost-bearing array of the device image is patched in place on the ctx stream, behind
+ * batches already enqueued; the call returns when the patch is done.  edges[]: forward CSR edge indices,
+ * costs[]: their new costs.  HSPF_E_UNSUPPORTED when a cost does not fit the image as uploaded (16-bit
+ * packing, bucket ring of the fast path, hop-count graphs): free the graph and upload the new CSR.
+ * HSPF_E_NEEDS_ORACLE: zero cost out of a HOP vertex.  Nothing is changed on an error. */
+int hspf_graph_update_costs(hspf_ctx *ctx, hspf_graph *g, uint32_t n, const uint32_t *edges, const uint32_t *costs);
+
 /* Asynchronous variant used by the benchmark: enqueue on the ctx stream and
  * return; requires HSPF_RUN_DEVICE_PTRS.  hspf_sync() waits for completion. */
 int hspf_run_batch_async(hspf_ctx *ctx, const hspf_graph *g,

@@ -69,6 +69,34 @@ int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *area, const uint32_t *dis
                                  const uint64_t *nh_mask, uint32_t nh_words, hl_ospfv2_result *out);
 
 /*
+ * Trigger-keyed recomputation (incremental flattener).
+ *
+ *   hspf_ospfv2_spf_computation_type   Ospfv2::spf_computation_type (holo-ospf/src/ospfv2/spf.rs:98-171):
+ *       which work a set of trigger LSAs asks for.  HSPF_E_NOMEM when a set does not fit `cap` (counts filled in).
+ *   hspf_ospfv2_flat_update   brings a flattened area up to date with `new_area`, the LSDB image after the
+ *       trigger LSAs were installed, touching only what the triggers can have changed:
+ *         HSPF_FLAT_UNCHANGED  no trigger bears on the graph (summary / external / opaque LSAs, a refreshed
+ *                              Router- or Network-LSA with the same links): the uploaded graph stands;
+ *         HSPF_FLAT_COSTS      Router-LSAs changed in link metrics only (an interface cost change): the
+ *                              flat's costs are patched in place and edges[] / costs[] list the forward
+ *                              CSR edges to hand to hspf_graph_update_costs — nothing else is re-uploaded;
+ *         HSPF_FLAT_REBUILT    links appeared or disappeared, a vertex came or went, or the image is laid out
+ *                              differently: the flat was rebuilt from scratch; upload it again.
+ *       The cost-only shortcut requires new_area to keep the LSAs and links of the old image at the same
+ *       indices (same counts, same order), which is what replacing an LSA's body in place gives.  The flat
+ *       refers to new_area afterwards (it must outlive the flat's use).  Stub-link metrics and SR data do
+ *       not touch the graph: rebuild the route table (hspf_ospfv2_rtable_create) after any FULL trigger.
+ *       HSPF_E_NOMEM: more changed edges than `cap` (n_changed filled in; the flat is already updated).
+ */
+#define HSPF_FLAT_UNCHANGED 0u
+#define HSPF_FLAT_COSTS     1u
+#define HSPF_FLAT_REBUILT   2u
+int hspf_ospfv2_spf_computation_type(const hl_lsa_trigger *triggers, uint32_t n_triggers, hl_spf_computation *out);
+int hspf_ospfv2_flat_update(hspf_ospfv2_flat *flat, const hl_ospfv2_area *new_area, const hl_lsa_trigger *triggers,
+                            uint32_t n_triggers, uint32_t *kind, uint32_t *edges, uint32_t *costs, uint32_t cap,
+                            uint32_t *n_changed);
+
+/*
  * Batched intra-area route stage on the device (update_rib_intra_area, holo-ospf/src/route.rs:343-446,
  * for every job of a batch: what-if roots, all routers of an area).
  *

@@ -93,6 +93,12 @@ def ospfv2_run_area(area):
     return ospfv2._call_run_area(L.oracle_ospfv2_run_area, area)
 
 
+def ospfv2_spf_computation_type(triggers):
+    """Restatement of Ospfv2::spf_computation_type (oracle/spf_ospfv2.cc)."""
+    from holo_b200 import ospfv2
+    return ospfv2.spf_computation_type(triggers, fn=lib().oracle_ospfv2_spf_computation_type)
+
+
 def ospfv2_update_rib_full(router_id: int, max_paths: int, areas: list, externals=None):
     """Reference-faithful update_rib_full stages after the per-area SPFs (oracle/rib_ospfv2.cc)."""
     from holo_b200 import ospf_rib

@@ -466,3 +466,34 @@ extern "C" int oracle_ospfv2_run_area(const hl_ospfv2_area *a, hl_ospfv2_result 
     }
     return 0;
 }
+
+// Restates Ospfv2::spf_computation_type (holo-ospf/src/ospfv2/spf.rs:98-171): any Router-LSA, Network-LSA,
+// area-scope Router-Information / Extended-Prefix / Extended-Link opaque LSA or AS-scope Extended-Prefix
+// opaque LSA among the triggers asks for a full run; otherwise the run is partial over the prefixes of the
+// changed type-3 and type-5 LSAs (Ipv4Network::with_netmask(lsa_id, mask), host bits kept) and the ASBR ids
+// of the changed type-4 LSAs, each a BTreeSet.  PARITY UNPINNED: no reference test records this value.
+#include <set>
+extern "C" int oracle_ospfv2_spf_computation_type(const hl_lsa_trigger *tr, uint32_t n, hl_spf_computation *out) {
+    bool full = false;
+    std::set<std::pair<uint32_t, uint8_t>> inter_network, external;   // Ipv4Network Ord: address, then length
+    std::set<uint32_t> inter_router;
+    for (uint32_t i = 0; i < n; ++i) {
+        switch (tr[i].lsa_type) {
+        case 1: case 2: full = true; break;
+        case 10: if (tr[i].opaque_type == 4 || tr[i].opaque_type == 7 || tr[i].opaque_type == 8) full = true; break;
+        case 11: if (tr[i].opaque_type == 7) full = true; break;
+        case 3: inter_network.insert({tr[i].lsa_id, (uint8_t)__builtin_popcount(tr[i].mask)}); break;
+        case 4: inter_router.insert(tr[i].lsa_id); break;
+        case 5: external.insert({tr[i].lsa_id, (uint8_t)__builtin_popcount(tr[i].mask)}); break;
+        default: break;
+        }
+    }
+    out->n_inter_network = out->n_inter_router = out->n_external = 0;
+    if (full) { out->kind = HL_SPF_FULL; return 0; }
+    out->kind = HL_SPF_PARTIAL;
+    auto mask = [](uint8_t len) { return len ? 0xFFFFFFFFu << (32 - len) : 0u; };
+    for (auto &p : inter_network) out->inter_network[out->n_inter_network++] = hl_ipv4_net{p.first, mask(p.second)};
+    for (uint32_t r : inter_router) out->inter_router[out->n_inter_router++] = r;
+    for (auto &p : external) out->external[out->n_external++] = hl_ipv4_net{p.first, mask(p.second)};
+    return 0;
+}

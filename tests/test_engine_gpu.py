@@ -406,3 +406,58 @@ def test_reserved_sms_shrink_the_grid_and_small_batches_still_run(ctx):
     finally:
         ctx.reserve_sms(0)
     g.free()
+
+
+@pytest.mark.parametrize("shape", ["fast", "wide_costs", "lans"])
+def test_update_costs_in_place_equals_a_fresh_upload(ctx, shape):
+    """hspf_graph_update_costs patches every cost-bearing array of the device image (CSR, transpose, packed
+    twins, quad-space records): a batch on the patched graph gives the planes of a fresh upload of the
+    modified CSR, on the fast path, on the general path (u32 costs) and with transit networks."""
+    import os
+    from holo_b200 import capi
+    kw = dict(lans=dict(lan_fraction=0.1)).get(shape, {})
+    t = synth.random_topology(400, 1800, synth.SEED_BASE + 61, **kw)
+    # wide_costs: IS-IS-style u32 arithmetic (no OSPF saturation), costs that do not pack: general kernel
+    csr = synth.topology_csr(t, isis=(shape == "wide_costs"), saturate_at=0 if shape == "wide_costs" else 0xFFFF)
+    hop = (csr.vflags & 1).astype(bool)
+    tails = np.repeat(np.arange(csr.n_vertices), np.diff(csr.row_ptr.astype(np.int64)))
+    cand = np.nonzero(hop[tails])[0]                            # edges out of routers carry the costs
+    if shape == "wide_costs":
+        csr.cost[cand[::7]] = 70000 + (csr.cost[cand[::7]] % 50)
+    rng = np.random.default_rng(5)
+    L = len(t.lans)
+    roots = rng.choice(np.arange(L, csr.n_vertices), 40, replace=False).astype(np.uint32)
+    g = ctx.upload(csr)
+    assert ctx.graph_info(g)["fast_path"] == (shape != "wide_costs")
+    edges = rng.choice(cand, 60, replace=False).astype(np.uint32)
+    new = rng.integers(1, 250 if shape != "wide_costs" else 90000, len(edges)).astype(np.uint32)
+    ctx.update_costs(g, edges, new)
+    csr2 = capi.Csr(csr.row_ptr.copy(), csr.col.copy(), csr.cost.copy(), csr.vflags.copy(), reject_above=csr.reject_above,
+                    saturate_at=csr.saturate_at, flags=csr.flags, delta=csr.delta)
+    csr2.cost[edges] = new
+    got = ctx.run(g, roots)
+    g2 = ctx.upload(csr2)
+    want = ctx.run(g2, roots)
+    for name in ("dist", "hops", "first_parent", "n_parents", "nh_mask", "job_status"):
+        assert np.array_equal(getattr(got, name), getattr(want, name)), name
+    for j in (0, 17, 39):
+        ref = pyoracle.csr_spf_heap(csr2, int(roots[j]), nh_words=1)
+        assert np.array_equal(got.dist[j], ref["dist"]) and np.array_equal(got.nh_mask[j].reshape(-1), ref["nh_mask"].reshape(-1))
+    os.environ["HSPF_NO_QUAD"] = "1"                            # the general kernel reads the other copies
+    try:
+        alt = ctx.run(g, roots)
+    finally:
+        del os.environ["HSPF_NO_QUAD"]
+    for name in ("dist", "hops", "first_parent", "n_parents", "nh_mask"):
+        assert np.array_equal(getattr(alt, name), getattr(want, name)), name
+    # refusals leave the graph as it is
+    if shape == "fast":
+        with pytest.raises(capi.HspfError):
+            ctx.update_costs(g, edges[:1], [70000])             # does not fit the packed image
+        with pytest.raises(capi.HspfError):
+            ctx.update_costs(g, edges[:1], [0])                 # zero cost out of a router
+        with pytest.raises(capi.HspfError):
+            ctx.update_costs(g, [csr.n_edges], [5])
+        again = ctx.run(g, roots)
+        assert np.array_equal(again.dist, want.dist)
+    g.free(); g2.free()

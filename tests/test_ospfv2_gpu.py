@@ -210,3 +210,34 @@ def test_routes_batch_on_device_planes_wide_and_narrow(ctx):
         assert ok.sum() > V // 2 and (narrow or ok.all())
         assert got[ok].tobytes() == want.cells[ok].tobytes()
         assert not (got[~ok]["flags"]).any()     # refused jobs: empty cells
+
+
+def test_interface_cost_change_reuses_the_uploaded_graph(ctx):
+    """SURVEY 8f f2 end to end: a Router-LSA comes back with other link metrics; hspf_ospfv2_flat_update names
+    the changed CSR edges, hspf_graph_update_costs patches the device image in place, and the SPT + routes of
+    the patched graph equal the oracle's on the new LSDB."""
+    import copy
+    t = synth.random_topology(300, 1400, synth.SEED_BASE + 6, cost_choices=[10, 20], lan_fraction=0.1)
+    area = ospfv2.synth_area(t, root=5, sr=True)
+    flat = ospfv2.Flat(area)
+    g = ctx.upload(flat.csr)
+    new = copy.deepcopy(area)
+    rids = [int(ospfv2.RID_BASE + i) for i in (5, 6, 40)]
+    for rid in rids:
+        i = int(np.nonzero(new.router_lsas["adv_rtr"] == rid)[0][0])
+        lo, n = int(new.router_lsas["link_off"][i]), int(new.router_lsas["n_links"][i])
+        for k in range(lo, lo + n):
+            if new.links["link_type"][k] != ospfv2.LINK_STUB:
+                new.links["metric"][k] = 7 + 3 * (k % 5)
+    kind, edges, costs = ospfv2.flat_update(flat, new, [(r, r, 0, 1, 0, (0, 0)) for r in rids])
+    assert kind == ospfv2.FLAT_COSTS and len(edges) > 0
+    ctx.update_costs(g, edges, costs)
+    root = flat.router_vertex(new.router_id)
+
+    def planes(csr, r, nhw):
+        res = ctx.run(g, [r], nh_words=nhw)
+        return res.dist[0], res.hops[0], res.nh_mask[0]
+    res = ospfv2.area_from_planes(new, planes)
+    assert_same(res, pyoracle.ospfv2_run_area(new))
+    assert_same(ospfv2.run_area(ctx, new), res)          # and the full re-flatten + upload path agrees
+    g.free()
