@@ -178,3 +178,71 @@ def test_table_shape_and_order():
     # every p2p /30 is advertised by both ends, every LAN prefix by its transit network
     assert rt.n_contributors > rt.n_prefixes
     assert int(rt.contribs["is_network"].sum()) == len(area.network_lsas)
+
+
+FUZZ_STATS = {}
+
+
+def collide(area, rng):
+    """Make prefixes meet: stub links of several routers re-pointed at a small pool of prefixes (with few
+    distinct metrics, so ties are common), some of them a transit network's own prefix; transit networks
+    widened to /16 so that several map to one prefix; Prefix-SIDs for some of the new (router, prefix) pairs,
+    equal or different; per-router SRGBs of different bases; a few PHP / explicit-null flag variants."""
+    links, rl = area.links, area.router_lsas
+    nets = area.network_lsas
+    pool = [(0xC6336400 + (i << 8), 0xFFFFFF00) for i in range(4)]
+    if len(nets):
+        for j in rng.choice(len(nets), min(len(nets), 3), replace=False):
+            if rng.random() < 0.5:
+                nets["mask"][j] = 0xFFFF0000                       # several LANs -> one /16
+            pool.append((int(nets["lsa_id"][j]) & int(nets["mask"][j]), int(nets["mask"][j])))
+    ext = list(area.ext_prefixes) if area.sr_enabled else []
+    for i in rng.choice(len(rl), min(len(rl), 14), replace=False):
+        lo, n = int(rl["link_off"][i]), int(rl["n_links"][i])
+        stubs = [k for k in range(lo, lo + n) if links["link_type"][k] == ospfv2.LINK_STUB and int(links["link_data"][k]) != 0xFFFFFFFF]
+        if not stubs:
+            continue
+        k = int(rng.choice(stubs))
+        p, m = pool[int(rng.integers(0, len(pool)))]
+        links["link_id"][k], links["link_data"][k], links["metric"][k] = p, m, int(rng.choice([0, 5, 5, 10]))
+        if area.sr_enabled and rng.random() < 0.7:
+            flags = int(rng.choice([ospfv2.PSID_NP, ospfv2.PSID_NP, 0, ospfv2.PSID_NP | ospfv2.PSID_E]))
+            ext.append((int(rl["adv_rtr"][i]), p, m, 1, 1, 1, flags, 0, (0, 0), int(rng.choice([900, 900, 901]))))
+    if area.sr_enabled:
+        area.ext_prefixes = np.asarray(ext, ospfv2.EXT_PREFIX_DT)
+        area.ext_prefixes = area.ext_prefixes[np.lexsort((area.ext_prefixes["prefix"], area.ext_prefixes["adv_rtr"]))]
+        for i in range(len(area.srgbs)):
+            area.srgbs["first"][i] = 16000 + 1000 * (i % 5)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_colliding_prefixes_fuzz(harness, seed):
+    """Every way two advertisers can meet on one prefix (stub / stub, stub / transit network, network /
+    network, equal and unequal metrics, equal and different Prefix-SIDs): the decoded cells equal the
+    faithful oracle's routes, or the decode refuses the job (different SIDs merged) — never a wrong route."""
+    rng = np.random.default_rng(500 + seed)
+    V = int(rng.integers(30, 90))
+    t = synth.random_topology(V, int(V * rng.uniform(2.5, 5)), synth.SEED_BASE + 70 + seed,
+                              cost_choices=[int(x) for x in rng.choice([5, 10, 10, 20], 2)], lan_fraction=float(rng.uniform(0.1, 0.35)))
+    sr = bool(rng.random() < 0.75)
+    mp = int(rng.choice([1, 2, 16]))
+    mut_seed = int(rng.integers(0, 1 << 30))
+    n_ok = n_refused = n_multi = 0
+    for root in rng.choice(V, 8, replace=False):
+        area, rt, cells, res, ref = check_root(harness, t, int(root), sr=sr, max_paths=mp,
+                                               mutate=lambda ar: collide(ar, np.random.default_rng(mut_seed)))
+        n_multi += int((np.diff(rt.off.astype(np.int64)) > 2).sum())
+        if res.rc == capi.HSPF_E_UNSUPPORTED:
+            assert sr and (cells["flags"] & ospfv2.CELL_MIXED_SID).any()
+            n_refused += 1
+            continue
+        same_routes(res, ref)
+        n_ok += 1
+    FUZZ_STATS[seed] = (n_ok, n_refused)
+    assert n_ok + n_refused == 8 and n_multi > 0
+
+
+def test_colliding_prefixes_fuzz_covers_both_outcomes():
+    if len(FUZZ_STATS) < 12:
+        pytest.skip("runs after the whole fuzz")
+    assert sum(a for a, _ in FUZZ_STATS.values()) >= 40 and sum(b for _, b in FUZZ_STATS.values()) >= 8
