@@ -28,11 +28,32 @@ NVCC_FLAGS = [
 ]
 
 
-def _newer(target: Path, sources) -> bool:
-    if not target.exists():
-        return False
-    t = target.stat().st_mtime
-    return all(Path(s).stat().st_mtime <= t for s in sources)
+def _fingerprint(tool: str, flags, deps) -> str:
+    """What the library was built from: compiler identity, flags and the bytes of every source and header.
+    (Not mtimes: a prebuilt .so that travels to another box, or sources restored by a checkout, must neither
+    be trusted when something differs nor rebuilt when nothing does.)"""
+    import hashlib
+    h = hashlib.sha256()
+    try:
+        ver = subprocess.run([tool, "--version"], capture_output=True, text=True).stdout
+    except OSError:
+        ver = "missing"
+    h.update(ver.encode())
+    # paths relative to the checkout: the same tree under another root is the same build
+    h.update("\0".join(str(f).replace(str(ROOT), ".") for f in flags).encode())
+    for d in sorted(Path(x).resolve() for x in deps):
+        h.update(str(d.relative_to(ROOT)).encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
+def _up_to_date(target: Path, fp: str) -> bool:
+    stamp = target.with_suffix(target.suffix + ".stamp")
+    return target.exists() and stamp.exists() and stamp.read_text().strip() == fp
+
+
+def _write_stamp(target: Path, fp: str):
+    target.with_suffix(target.suffix + ".stamp").write_text(fp + "\n")
 
 
 def _run(cmd):
@@ -50,15 +71,17 @@ def product_sources():
 def build_product(force: bool = False, verbose: bool = False) -> Path:
     srcs = product_sources()
     deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((ROOT / "include").glob("*.h"))
-    if not force and _newer(PRODUCT_LIB, deps):
-        return PRODUCT_LIB
     nvcc = os.environ.get("NVCC", "nvcc")
+    fp = _fingerprint(nvcc, NVCC_FLAGS, deps)
+    if not force and _up_to_date(PRODUCT_LIB, fp):
+        return PRODUCT_LIB
     LIBDIR.mkdir(parents=True, exist_ok=True)
     cmd = [nvcc, *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(PRODUCT_LIB), *map(str, srcs)]
     out = _run(cmd)
+    _write_stamp(PRODUCT_LIB, fp)
     if verbose:
         print(out)
     return PRODUCT_LIB
@@ -71,12 +94,13 @@ def oracle_sources():
 def build_oracle(force: bool = False) -> Path:
     srcs = oracle_sources()
     deps = srcs + list(ORACLE_DIR.glob("*.h")) + list((ROOT / "include").glob("*.h"))
-    if not force and _newer(ORACLE_LIB, deps):
+    flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", "-I", str(ROOT / "include")]
+    fp = _fingerprint("g++", flags, deps)
+    if not force and _up_to_date(ORACLE_LIB, fp):
         return ORACLE_LIB
     ORACLE_LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread",
-           "-I", str(ROOT / "include"), "-o", str(ORACLE_LIB), *map(str, srcs)]
-    _run(cmd)
+    _run(["g++", *flags, "-o", str(ORACLE_LIB), *map(str, srcs)])
+    _write_stamp(ORACLE_LIB, fp)
     return ORACLE_LIB
 
 

@@ -61,3 +61,18 @@ def test_atom_decode_host_only(built):
     assert len(seen) == n
     with pytest.raises(capi.HspfError):
         capi.atom_decode(csr, root, n)
+
+
+def test_build_fingerprint_covers_flags_sources_and_not_the_checkout_root(tmp_path, built):
+    """A prebuilt library is reused only when compiler, flags and every source byte are the ones it was built
+    from (holo_b200/build.py); the same tree under another root is the same build."""
+    from holo_b200 import build
+    src = sorted(build.CSRC.glob("*.h"))[:2]
+    a = build._fingerprint("g++", ["-O2", "-I", str(build.ROOT / "include")], src)
+    assert a == build._fingerprint("g++", ["-O2", "-I", str(build.ROOT / "include")], src)
+    assert a != build._fingerprint("g++", ["-O3", "-I", str(build.ROOT / "include")], src)
+    assert a != build._fingerprint("g++", ["-O2", "-I", str(build.ROOT / "include")], src[:1])
+    assert a != build._fingerprint("nvcc", ["-O2", "-I", str(build.ROOT / "include")], src)
+    stamp = built[0].with_suffix(".so.stamp")
+    assert stamp.exists() and build._up_to_date(built[0], stamp.read_text().strip())
+    assert not build._up_to_date(built[0], "0" * 64)
