@@ -101,3 +101,48 @@ if which == 'ospf':
                 if getattr(got3,name).tobytes()!=getattr(ref3,name).tobytes(): bad+=1; print('MISMATCH v3',name,V,E,kw,int(root),flush=True); break
     print('fuzzed',n,'areas; mismatches',bad,'skipped',skipped)
 
+
+
+if which == 'cells':
+    # route_cell_eval (the device route kernel's body, run on the CPU through tests/native/route_cells_harness.cc)
+    # + hspf_ospfv2_routes_from_cells against the faithful oracle's run_area routes, on LSDBs whose prefixes
+    # collide in every way tests/test_ospfv2_route_cells.py::collide knows (round 2: 56 k roots, 19 k refused as
+    # mixed-SID, 0 mismatches)
+    import ctypes as C, subprocess, time, numpy as np
+    import test_ospfv2_route_cells as T
+    from holo_b200 import capi, synth
+    from holo_b200.build import build_all
+    build_all()
+    so = os.path.join(ROOT, 'tests', '_build', 'libroute_cells_harness.so')
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I', os.path.join(ROOT, 'include'), '-o', so,
+                    os.path.join(ROOT, 'tests', 'native', 'route_cells_harness.cc')], check=True)
+    lib = C.CDLL(so)
+    lib.harness_route_cells.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.harness_route_cells16.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    t_end = time.time() + float(sys.argv[1]); seed = 10000; n = bad = refused = 0
+    while time.time() < t_end:
+        seed += 1
+        rng = np.random.default_rng(seed)
+        V = int(rng.integers(12, 120))
+        try:
+            t = synth.random_topology(V, int(V * rng.uniform(1.5, 6)), seed, cost_choices=[int(x) for x in rng.choice([1, 5, 10, 10, 20], 2)],
+                                      lan_fraction=float(rng.uniform(0.0, 0.5)))
+        except Exception:
+            continue
+        sr = bool(rng.random() < 0.75); mp = int(rng.choice([1, 2, 3, 16])); ms = int(rng.integers(0, 1 << 30))
+        for root in rng.choice(V, min(V, 5), replace=False):
+            try:
+                area, rt, cells, res, ref = T.check_root(lib, t, int(root), sr=sr, max_paths=mp,
+                                                         mutate=lambda ar: T.collide(ar, np.random.default_rng(ms)))
+            except AssertionError:
+                continue      # the oracle refused the root (more than 64 atoms)
+            n += 1
+            if res.rc == capi.HSPF_E_UNSUPPORTED:
+                refused += 1
+                continue
+            try:
+                T.same_routes(res, ref)
+            except AssertionError as e:
+                bad += 1; print('MISMATCH', seed, int(root), str(e)[:300], flush=True)
+    print('fuzzed', n, 'roots; refused', refused, 'mismatches', bad)
