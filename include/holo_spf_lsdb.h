@@ -123,8 +123,9 @@ int hspf_ospfv2_flat_update(hspf_ospfv2_flat *flat, const hl_ospfv2_area *new_ar
  *                               neighbour state and the same LSDB the table was built from.  gather_v /
  *                               gather_nh: nh_mask of the transit networks attached to the root.
  *                               HSPF_E_UNSUPPORTED: a cell is flagged HL_CELL_MIXED_SID, or two atoms
- *                               resolve to the same next hop with different attributes: use
- *                               hspf_ospfv2_area_from_planes for this job.
+ *                               resolve to the same next hop with different attributes: the cells cannot
+ *                               say which advertiser's label a next hop keeps — take this root through
+ *                               hspf_ospfv2_run_area (or hspf_ospfv2_area_from_planes over its planes).
  */
 typedef struct hspf_ospfv2_rtable hspf_ospfv2_rtable;
 int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable **out);
