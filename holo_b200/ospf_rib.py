@@ -210,3 +210,107 @@ def call_rib_diff(fn, old, new: Rib, v3: bool = False):
 def rib_diff(old, new: Rib, v3: bool = False):
     lib = capi.load_library()
     return call_rib_diff(lib.hspf_ospfv3_rib_diff if v3 else lib.hspf_ospfv2_rib_diff, old, new, v3)
+
+
+# ---- partial runs (update_rib_partial, holo-ospf/src/route.rs:196-340), OSPFv2 ---------------------------
+RIB_RTR_DT = np.dtype([("area_id", "<u4"), ("router_id", "<u4"), ("metric", "<u4"), ("path_type", "u1"), ("flags", "u1"),
+                       ("_pad", "u1", (2,)), ("nh_off", "<u4"), ("n_nh", "<u4")], align=True)
+
+
+class RtrTablesStruct(C.Structure):
+    _fields_ = [("rtrs_cap", C.c_uint32), ("n_rtrs", C.c_uint32), ("rtrs", C.c_void_p),
+                ("nexthops_cap", C.c_uint32), ("n_nexthops", C.c_uint32), ("nexthops", C.c_void_p)]
+
+
+@dataclass
+class RtrTables:
+    rtrs: np.ndarray
+    nexthops: np.ndarray
+
+
+def _area_array(areas: list, keep: list, with_results: bool):
+    arr = (RibAreaStruct * max(len(areas), 1))()
+    for i, a in enumerate(areas):
+        ifs = np.ascontiguousarray(a.ifaces, dtype=ospfv2.IFACE_DT)
+        sm = np.ascontiguousarray(a.summaries, dtype=SUMMARY_LSA_DT)
+        keep += [ifs, sm]
+        arr[i].area_id, arr[i].n_summaries = a.area_id, len(sm)
+        if with_results:
+            rs = _result_struct(a.result, keep)
+            keep.append(rs)
+            arr[i].spf = C.addressof(rs)
+        arr[i].ifaces = ifs.ctypes.data if len(ifs) else None
+        arr[i].summaries = sm.ctypes.data if len(sm) else None
+        arr[i].n_ifaces, arr[i].active = len(ifs), int(a.active)
+    return arr
+
+
+def _tables_out(cap_r, cap_h, keep):
+    rt, nh = np.zeros(max(cap_r, 1), RIB_RTR_DT), np.zeros(max(cap_h, 1), ospfv2.NEXTHOP_DT)
+    keep += [rt, nh]
+    s = RtrTablesStruct(len(rt), 0, rt.ctypes.data, len(nh), 0, nh.ctypes.data)
+    return s, rt, nh
+
+
+def router_tables(router_id: int, areas: list, fn=None) -> RtrTables:
+    """hspf_ospfv2_rib_router_tables: area.state.routers of every area after a full run."""
+    if fn is None:
+        fn = capi.load_library().hspf_ospfv2_rib_router_tables
+    fn.argtypes = [C.c_uint32, C.POINTER(RibAreaStruct), C.c_uint32, C.POINTER(RtrTablesStruct)]
+    keep = []
+    arr = _area_array(areas, keep, True)
+    caps = [64, 256]
+    for _ in range(3):
+        s, rt, nh = _tables_out(caps[0], caps[1], keep)
+        rc = fn(router_id, arr, len(areas), C.byref(s))
+        if rc == capi.HSPF_E_NOMEM:
+            caps = [max(caps[0], s.n_rtrs), max(caps[1], s.n_nexthops)]
+            continue
+        break
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "rib_router_tables failed")
+    return RtrTables(rt[: s.n_rtrs].copy(), nh[: s.n_nexthops].copy())
+
+
+def update_rib_partial(router_id: int, max_paths: int, areas: list, externals, triggers_or_sets, prev_rib: Rib,
+                       prev_rtrs: RtrTables, fn=None):
+    """hspf_ospfv2_update_rib_partial -> (new Rib, new RtrTables, actions).  `triggers_or_sets`: the
+    (inter_network [(addr, mask)], inter_router [id], external [(addr, mask)]) sets of a PARTIAL computation."""
+    if fn is None:
+        fn = capi.load_library().hspf_ospfv2_update_rib_partial
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(RibAreaStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                   C.POINTER(ospfv2.SpfComputationStruct), C.POINTER(RibStruct), C.POINTER(RtrTablesStruct),
+                   C.POINTER(RibStruct), C.POINTER(RtrTablesStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    keep = []
+    arr = _area_array(areas, keep, False)
+    transit = np.asarray([int(a.result.transit_capability) for a in areas] or [0], np.uint8)
+    ext = np.ascontiguousarray(externals if externals is not None else np.zeros(0, EXTERNAL_LSA_DT), dtype=EXTERNAL_LSA_DT)
+    net, rtr, xt = triggers_or_sets
+    netA = np.asarray(net or [(0, 0)], ospfv2.IPV4_NET_DT)
+    rtrA = np.asarray(rtr or [0], np.uint32)
+    xtA = np.asarray(xt or [(0, 0)], ospfv2.IPV4_NET_DT)
+    pc = ospfv2.SpfComputationStruct(ospfv2.SPF_PARTIAL, len(net), len(rtr), len(xt), max(len(net), len(rtr), len(xt), 1),
+                                     netA.ctypes.data, rtrA.ctypes.data, xtA.ctypes.data)
+    prs = _rib_struct(prev_rib, keep, RIB_ROUTE_DT, ospfv2.NEXTHOP_DT)
+    prt = np.ascontiguousarray(prev_rtrs.rtrs, RIB_RTR_DT)
+    pnh = np.ascontiguousarray(prev_rtrs.nexthops, ospfv2.NEXTHOP_DT)
+    pts = RtrTablesStruct(len(prt), len(prt), prt.ctypes.data if len(prt) else None, len(pnh), len(pnh),
+                          pnh.ctypes.data if len(pnh) else None)
+    caps = [len(prev_rib.routes) + 64, len(prev_rib.nexthops) + 512, len(prt) + 64, len(pnh) + 512, len(prev_rib.routes) + 128]
+    for _ in range(3):
+        routes, nhs = np.zeros(caps[0], RIB_ROUTE_DT), np.zeros(caps[1], ospfv2.NEXTHOP_DT)
+        out = RibStruct(caps[0], 0, routes.ctypes.data, caps[1], 0, nhs.ctypes.data)
+        ts, rt, tnh = _tables_out(caps[2], caps[3], keep)
+        acts = np.zeros(caps[4], ACTION_DT)
+        n = C.c_uint32()
+        rc = fn(router_id, max_paths, arr, transit.ctypes.data, len(areas), ext.ctypes.data if len(ext) else None, len(ext),
+                C.byref(pc), C.byref(prs), C.byref(pts), C.byref(out), C.byref(ts), acts.ctypes.data, caps[4], C.byref(n))
+        if rc == capi.HSPF_E_NOMEM:
+            caps = [max(caps[0], out.n_routes), max(caps[1], out.n_nexthops), max(caps[2], ts.n_rtrs), max(caps[3], ts.n_nexthops),
+                    max(caps[4], n.value)]
+            continue
+        break
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "update_rib_partial failed")
+    return (Rib(routes[: out.n_routes].copy(), nhs[: out.n_nexthops].copy()), RtrTables(rt[: ts.n_rtrs].copy(), tnh[: ts.n_nexthops].copy()),
+            acts[: n.value].copy())

@@ -357,6 +357,25 @@ typedef struct hl_ospfv2_rib {
 } hl_ospfv2_rib;
 
 
+/* Per-area router tables (area.state.routers, RouteRtr, route.rs:57-66) as update_rib_full leaves them:
+ * intra-area entries of the SPF plus inter-area entries from type-4 LSAs.  State carried between a full
+ * run and the partial runs that follow it.  Entries in (area order of the call, router id) order; next hops
+ * name interfaces by sort key, in NexthopKey order. */
+typedef struct hl_rib_rtr {
+    uint32_t area_id;
+    uint32_t router_id;
+    uint32_t metric;
+    uint8_t  path_type;    /* HL_PATH_INTRA_AREA / HL_PATH_INTER_AREA */
+    uint8_t  flags;        /* HL_RTR_FLAG_* */
+    uint8_t  _pad[2];
+    uint32_t nh_off;
+    uint32_t n_nh;
+} hl_rib_rtr;
+typedef struct hl_ospfv2_rtr_tables {
+    uint32_t rtrs_cap,     n_rtrs;       hl_rib_rtr *rtrs;
+    uint32_t nexthops_cap, n_nexthops;   hl_nexthop *nexthops;
+} hl_ospfv2_rtr_tables;
+
 /* ------------------------------------------------------------------ OSPFv3 -- */
 
 /* Router-LSA link (holo-ospf/src/ospfv3/packet/lsa.rs LsaRouterLink); link_type uses

@@ -97,6 +97,31 @@ int hspf_ospfv2_flat_update(hspf_ospfv2_flat *flat, const hl_ospfv2_area *new_ar
                             uint32_t *n_changed);
 
 /*
+ * Partial runs (HL_SPF_PARTIAL): update_rib_partial, holo-ospf/src/route.rs:196-340, OSPFv2.
+ *   hspf_ospfv2_rib_router_tables   the per-area router tables a FULL run leaves behind (the same inputs as
+ *                                   hspf_ospfv2_update_rib_full): the state the partial runs start from.
+ *   hspf_ospfv2_update_rib_partial  only summary / external LSAs changed: the SPTs stand.  The routes of the
+ *       named destinations are taken out of the previous table and recomputed from the LSAs into a side table
+ *       (inter-area networks, then inter-area routers in the per-area tables, then — when a type-4 LSA changed —
+ *       every external route, else the named ones), transit areas are re-examined on the routes that stayed,
+ *       update_global_rib runs over the side table against the routes taken out, and the side table is laid over
+ *       the previous one.  Like the reference, the recomputed routes do not see the routes that stayed (an
+ *       inter-area route recomputed for a prefix that is also intra-area replaces it).
+ *       `areas[i].spf` is not read (no SPF ran); `areas[i].summaries`, `.active`, `.area_id`, and
+ *       `transit_capability[i]` (area.state.transit_capability of the last SPF) are.
+ *       out_rib / out_rtrs: the new state; actions: route indices of out_rib (INSTALL, UNINSTALL) or of prev_rib
+ *       (UNINSTALL_OLD).  HSPF_E_NOMEM with the counts filled in when an output is too small.
+ */
+int hspf_ospfv2_rib_router_tables(uint32_t router_id, const hl_ospfv2_rib_area *areas, uint32_t n_areas,
+                                  hl_ospfv2_rtr_tables *out);
+int hspf_ospfv2_update_rib_partial(uint32_t router_id, uint32_t max_paths, const hl_ospfv2_rib_area *areas,
+                                   const uint8_t *transit_capability, uint32_t n_areas,
+                                   const hl_ospfv2_external_lsa *ext, uint32_t n_ext, const hl_spf_computation *partial,
+                                   const hl_ospfv2_rib *prev_rib, const hl_ospfv2_rtr_tables *prev_rtrs,
+                                   hl_ospfv2_rib *out_rib, hl_ospfv2_rtr_tables *out_rtrs,
+                                   hl_rib_action *actions, uint32_t actions_cap, uint32_t *n_actions);
+
+/*
  * Batched intra-area route stage on the device (update_rib_intra_area, holo-ospf/src/route.rs:343-446,
  * for every job of a batch: what-if roots, all routers of an area).
  *

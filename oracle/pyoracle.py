@@ -105,6 +105,18 @@ def ospfv2_update_rib_full(router_id: int, max_paths: int, areas: list, external
     return ospf_rib.call_update_rib_full(lib().oracle_ospfv2_update_rib_full, router_id, max_paths, areas, externals)
 
 
+def ospfv2_rib_router_tables(router_id: int, areas: list):
+    from holo_b200 import ospf_rib
+    return ospf_rib.router_tables(router_id, areas, fn=lib().oracle_ospfv2_rib_router_tables)
+
+
+def ospfv2_update_rib_partial(router_id, max_paths, areas, externals, sets, prev_rib, prev_rtrs):
+    """Restatement of update_rib_partial (oracle/rib_partial.cc)."""
+    from holo_b200 import ospf_rib
+    return ospf_rib.update_rib_partial(router_id, max_paths, areas, externals, sets, prev_rib, prev_rtrs,
+                                       fn=lib().oracle_ospfv2_update_rib_partial)
+
+
 def ospfv3_update_rib_full(router_id: int, max_paths: int, areas: list, externals=None):
     from holo_b200 import ospf_rib
     return ospf_rib.call_update_rib_full(lib().oracle_ospfv3_update_rib_full, router_id, max_paths, areas, externals,
