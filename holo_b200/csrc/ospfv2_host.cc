@@ -368,6 +368,8 @@ int hspf_abi_sizes(uint32_t *out, uint32_t cap) {
         (uint32_t)sizeof(hl_rib_action),
         (uint32_t)sizeof(hl_isis_rnl_entry),
         (uint32_t)sizeof(hl_route_cell),
+        (uint32_t)sizeof(hl_lsa_trigger), (uint32_t)sizeof(hl_spf_computation), (uint32_t)sizeof(hl_rib_rtr),
+        (uint32_t)sizeof(hl_ospfv2_rtr_tables),
     };
     static_assert(sizeof(hl_rib_action) == 12, "hl_rib_action layout");
     const uint32_t n = sizeof(v) / sizeof(v[0]);

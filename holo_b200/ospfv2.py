@@ -85,13 +85,15 @@ ABI_SIZES = [
 
 def abi_sizes_expected():
     from . import isis, ospf_rib, ospfv3
-    return ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES + [isis.RNL_DT.itemsize, CELL_DT.itemsize]
+    return (ABI_SIZES + isis.ABI_SIZES + ospfv3.ABI_SIZES + ospf_rib.ABI_SIZES +
+            [isis.RNL_DT.itemsize, CELL_DT.itemsize, TRIGGER_DT.itemsize, C.sizeof(SpfComputationStruct),
+             ospf_rib.RIB_RTR_DT.itemsize, C.sizeof(ospf_rib.RtrTablesStruct)])
 
 
 def abi_sizes_from_library():
     lib = capi.load_library()
-    out = (C.c_uint32 * 64)()
-    n = lib.hspf_abi_sizes(out, 64)
+    out = (C.c_uint32 * 128)()
+    n = lib.hspf_abi_sizes(out, 128)
     return [int(out[i]) for i in range(n)]
 
 
