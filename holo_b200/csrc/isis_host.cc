@@ -287,6 +287,69 @@ int hspf_isis_flat_csr(const hspf_isis_flat *flat, hspf_csr *out) {
     return HSPF_OK;
 }
 
+int hspf_isis_spf_type(const hl_isis_level *ol, const hl_isis_level *nl, const hl_isis_lsp_trigger *tr, uint32_t n,
+                       uint32_t *spf_type) {
+    if (!ol || !nl || !spf_type || (n && !tr)) return HSPF_E_INVAL;
+    auto find = [](const hl_isis_level *l, hl_lan_id id, uint8_t frag) -> const hl_isis_lsp * {
+        for (uint32_t i = 0; i < l->n_lsps; ++i)
+            if (l->lsps[i].lan_id == id && l->lsps[i].fragment == frag) return &l->lsps[i];
+        return nullptr;
+    };
+    // the IS-reachability entries of one TLV kind, in TLV order
+    auto same_kind = [](const hl_isis_level *a, const hl_isis_lsp *x, const hl_isis_level *b, const hl_isis_lsp *y, uint8_t kind) {
+        uint32_t i = 0, j = 0;
+        for (;;) {
+            while (i < x->n_reach && a->reaches[x->reach_off + i].kind != kind) ++i;
+            while (j < y->n_reach && b->reaches[y->reach_off + j].kind != kind) ++j;
+            if (i == x->n_reach || j == y->n_reach) return i == x->n_reach && j == y->n_reach;
+            const hl_isis_reach &p = a->reaches[x->reach_off + i], &q = b->reaches[y->reach_off + j];
+            if (p.neighbor != q.neighbor || p.metric != q.metric) return false;
+            ++i; ++j;
+        }
+    };
+    *spf_type = HL_ISIS_SPF_ROUTE_ONLY;
+    for (uint32_t k = 0; k < n; ++k) {
+        const hl_isis_lsp *x = find(ol, tr[k].lan_id, tr[k].fragment), *y = find(nl, tr[k].lan_id, tr[k].fragment);
+        if (!y) return HSPF_E_INVAL;                         // a trigger is an LSP that was just installed
+        bool topology_change = true;
+        if (x && (x->rem_lifetime == 0) == (y->rem_lifetime == 0) && x->flags == y->flags &&
+            same_kind(ol, x, nl, y, HL_ISIS_REACH_LEGACY) && same_kind(ol, x, nl, y, HL_ISIS_REACH_EXT))
+            topology_change = false;
+        if (topology_change) { *spf_type = HL_ISIS_SPF_FULL; break; }
+    }
+    return HSPF_OK;
+}
+
+int hspf_isis_flat_update(hspf_isis_flat *flat, const hl_isis_level *nl, uint32_t *kind, uint32_t *edges, uint32_t *costs,
+                          uint32_t cap, uint32_t *n_changed) {
+    if (!flat || !nl || !kind || !n_changed) return HSPF_E_INVAL;
+    try {
+        *n_changed = 0;
+        hspf_isis_flat fresh;
+        const int rc = flatten(nl, fresh);
+        if (rc) return rc;
+        hspf_isis_flat &f = *flat;
+        const bool same_graph = f.ids == fresh.ids && f.row == fresh.row && f.col == fresh.col && f.vflags == fresh.vflags &&
+                                f.reject_above == fresh.reject_above && f.gflags == fresh.gflags;
+        if (!same_graph) {
+            f = std::move(fresh);
+            *kind = HSPF_FLAT_REBUILT;
+            return HSPF_OK;
+        }
+        uint32_t changed = 0;
+        for (uint32_t e = 0; e < (uint32_t)f.cost.size(); ++e) {
+            if (f.cost[e] == fresh.cost[e]) continue;
+            if (changed < cap && edges && costs) { edges[changed] = e; costs[changed] = fresh.cost[e]; }
+            ++changed;
+        }
+        f.cost = std::move(fresh.cost);
+        f.lvl = nl;
+        *n_changed = changed;
+        *kind = changed ? HSPF_FLAT_COSTS : HSPF_FLAT_UNCHANGED;
+        return changed > cap ? HSPF_E_NOMEM : HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
 int hspf_isis_flat_vertices(const hspf_isis_flat *flat, const uint64_t **lan_ids, uint32_t *n_vertices) {
     if (!flat) return HSPF_E_INVAL;
     if (lan_ids) *lan_ids = flat->ids.data();

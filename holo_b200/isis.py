@@ -185,6 +185,10 @@ class Flat:
         if rc != capi.HSPF_OK:
             raise capi.HspfError(rc, "hspf_isis_flatten failed")
         self.handle = h
+        self._load()
+
+    def _load(self):
+        h = self.handle
         cs = capi.CsrStruct()
         self.lib.hspf_isis_flat_csr(h, C.byref(cs))
         V, E = cs.n_vertices, cs.n_edges
@@ -218,6 +222,43 @@ class Flat:
                 self.handle = None
         except Exception:
             pass
+
+
+LSP_TRIGGER_DT = np.dtype([("lan_id", "<u8"), ("fragment", "u1"), ("_pad", "u1", (7,))], align=True)
+SPF_FULL, SPF_ROUTE_ONLY = 1, 2
+FLAT_UNCHANGED, FLAT_COSTS, FLAT_REBUILT = 0, 1, 2
+
+
+def spf_type(old_level: IsisLevel, new_level: IsisLevel, triggers, lib=None, name="hspf_isis_spf_type") -> int:
+    """hspf_isis_spf_type: SPF_FULL or SPF_ROUTE_ONLY for the LSPs [(lan_id, fragment)] that were just installed."""
+    fn = getattr(lib or capi.load_library(), name)
+    fn.argtypes = [C.POINTER(LevelStruct), C.POINTER(LevelStruct), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    tr = np.zeros(len(triggers), LSP_TRIGGER_DT)
+    for i, (lan_id, frag) in enumerate(triggers):
+        tr[i]["lan_id"], tr[i]["fragment"] = lan_id, frag
+    so, sn = old_level.as_struct(), new_level.as_struct()
+    out = C.c_uint32()
+    rc = fn(C.byref(so), C.byref(sn), tr.ctypes.data if len(tr) else None, len(tr), C.byref(out))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, name + " failed")
+    return out.value
+
+
+def flat_update(flat: "Flat", new_level: IsisLevel):
+    """hspf_isis_flat_update -> (kind, edges, costs); the Flat's numpy views are refreshed."""
+    lib = flat.lib
+    lib.hspf_isis_flat_update.argtypes = [C.c_void_p, C.POINTER(LevelStruct), C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p,
+                                          C.c_uint32, C.POINTER(C.c_uint32)]
+    cap = max(int(flat.csr.n_edges), 1)
+    edges, costs = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    kind, n = C.c_uint32(), C.c_uint32()
+    s = new_level.as_struct()
+    rc = lib.hspf_isis_flat_update(flat.handle, C.byref(s), C.byref(kind), edges.ctypes.data, costs.ctypes.data, cap, C.byref(n))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "hspf_isis_flat_update failed")
+    flat.level, flat._s = new_level, s
+    flat._load()
+    return kind.value, edges[: n.value].copy(), costs[: n.value].copy()
 
 
 # ------------------------------------------------------------------------------ synthetic

@@ -675,6 +675,15 @@ typedef struct hl_isis_ipreach {
 #define HL_ISIS_MODE_NORMAL   0u     /* MetricMode::Normal   */
 #define HL_ISIS_MODE_HOPCOUNT 1u     /* MetricMode::HopCount (flooding/manet.rs:59) */
 
+/* An LSP whose installation scheduled the SPF run (spf_sched.trigger_lsps, holo-isis/src/lsdb.rs:1525-1531). */
+typedef struct hl_isis_lsp_trigger {
+    hl_lan_id lan_id;
+    uint8_t   fragment;
+    uint8_t   _pad[7];
+} hl_isis_lsp_trigger;
+#define HL_ISIS_SPF_FULL       1u   /* SpfType::Full (holo-isis/src/spf.rs:148-154): SPTs, flooding cache, routes */
+#define HL_ISIS_SPF_ROUTE_ONLY 2u   /* SpfType::RouteOnly: compute_routes over the standing SPTs              */
+
 /* One level's LSDB plus the compute_spt() parameters (spf.rs:525-535). */
 typedef struct hl_isis_level {
     uint8_t  metric_type;

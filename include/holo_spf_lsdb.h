@@ -261,6 +261,25 @@ int hspf_isis_spt_from_planes(const hspf_isis_flat *flat, uint32_t root_vertex, 
 /* One SPT for `root_system_id` (48-bit system id). */
 int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root_system_id, hl_isis_spt *out);
 
+/*
+ * Trigger-keyed recomputation for IS-IS.
+ *   hspf_isis_spf_type     the decision lsp_install makes per installed LSP (holo-isis/src/lsdb.rs:1450-1465,
+ *                          1525-1531): a run is FULL when any trigger LSP differs from its previous instance in
+ *                          expiry, flags or its IS-reachability / extended-IS-reachability entries (a new LSP
+ *                          always does); otherwise ROUTE_ONLY — compute_routes over the standing SPTs
+ *                          (hspf_isis_routes_from_planes with the planes of the last full run).  As in the
+ *                          reference, MT IS-reachability (TLV 222) entries are not part of the comparison.
+ *   hspf_isis_flat_update  brings a flattened level up to date with `new_lvl` and says what to upload:
+ *                          HSPF_FLAT_UNCHANGED / HSPF_FLAT_COSTS (same vertices, edges and flags: only metrics
+ *                          moved; edges[] / costs[] for hspf_graph_update_costs) / HSPF_FLAT_REBUILT.  The level
+ *                          is re-walked (linear in the LSDB); what is saved is the graph upload.  The flat refers
+ *                          to new_lvl afterwards.  HSPF_E_NOMEM: more changed edges than `cap` (n_changed set).
+ */
+int hspf_isis_spf_type(const hl_isis_level *old_lvl, const hl_isis_level *new_lvl, const hl_isis_lsp_trigger *triggers,
+                       uint32_t n_triggers, uint32_t *spf_type);
+int hspf_isis_flat_update(hspf_isis_flat *flat, const hl_isis_level *new_lvl, uint32_t *kind, uint32_t *edges,
+                          uint32_t *costs, uint32_t cap, uint32_t *n_changed);
+
 /* Route path of one level (compute_spf, holo-isis/src/spf.rs:742-799): for every enabled
  * topology an SPT with `local = true` next-hop resolution (spf.rs:948-1002), then
  * compute_routes (spf.rs:838-941) into one RIB (prefix order). */

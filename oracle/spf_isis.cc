@@ -569,3 +569,43 @@ extern "C" int oracle_isis_compute_routes(const hl_isis_instance *in, hl_isis_ri
     }
     return 0;
 }
+
+// Restates the SPF-type decision of lsp_install (holo-isis/src/lsdb.rs:1450-1465, 1525-1531): the run is Full as
+// soon as one installed LSP has no previous instance, or differs from it in `is_expired()`, `flags`, or in the
+// `is_reach()` / `ext_is_reach()` iterators (TLV 2 and TLV 22 entries in TLV order; TLV 222 is not looked at);
+// otherwise RouteOnly.  PARITY UNPINNED: no reference fixture records the SPF type.
+extern "C" int oracle_isis_spf_type(const hl_isis_level *old_lvl, const hl_isis_level *new_lvl,
+                                    const hl_isis_lsp_trigger *tr, uint32_t n, uint32_t *spf_type) {
+    auto lookup = [](const hl_isis_level *l, uint64_t lan_id, uint8_t fragment) {
+        int at = -1;
+        for (uint32_t i = 0; i < l->n_lsps && at < 0; ++i)
+            if (l->lsps[i].lan_id == lan_id && l->lsps[i].fragment == fragment) at = (int)i;
+        return at;
+    };
+    auto reach_of = [](const hl_isis_level *l, int at, uint8_t kind) {
+        std::vector<std::pair<uint64_t, uint32_t>> v;
+        const hl_isis_lsp &p = l->lsps[at];
+        for (uint32_t k = 0; k < p.n_reach; ++k) {
+            const hl_isis_reach &r = l->reaches[p.reach_off + k];
+            if (r.kind == kind) v.emplace_back(r.neighbor, r.metric);
+        }
+        return v;
+    };
+    bool full = false;
+    for (uint32_t k = 0; k < n; ++k) {
+        const int o = lookup(old_lvl, tr[k].lan_id, tr[k].fragment), w = lookup(new_lvl, tr[k].lan_id, tr[k].fragment);
+        if (w < 0) return -1;
+        bool topology_change = true;
+        if (o >= 0) {
+            const hl_isis_lsp &a = old_lvl->lsps[o], &b = new_lvl->lsps[w];
+            const bool a_expired = a.rem_lifetime == 0, b_expired = b.rem_lifetime == 0;
+            if (a_expired == b_expired && a.flags == b.flags &&
+                reach_of(old_lvl, o, HL_ISIS_REACH_LEGACY) == reach_of(new_lvl, w, HL_ISIS_REACH_LEGACY) &&
+                reach_of(old_lvl, o, HL_ISIS_REACH_EXT) == reach_of(new_lvl, w, HL_ISIS_REACH_EXT))
+                topology_change = false;
+        }
+        full = full || topology_change;
+    }
+    *spf_type = full ? HL_ISIS_SPF_FULL : HL_ISIS_SPF_ROUTE_ONLY;
+    return 0;
+}
