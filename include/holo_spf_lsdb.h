@@ -83,8 +83,9 @@ int hspf_ospfv2_area_from_planes(const hl_ospfv2_area *area, const uint32_t *dis
  *         HSPF_FLAT_REBUILT    links appeared or disappeared, a vertex came or went, or the image is laid out
  *                              differently: the flat was rebuilt from scratch; upload it again.
  *       The cost-only shortcut requires new_area to keep the LSAs and links of the old image at the same
- *       indices (same counts, same order), which is what replacing an LSA's body in place gives.  The flat
- *       refers to new_area afterwards (it must outlive the flat's use).  Stub-link metrics and SR data do
+ *       indices (same counts, same order), which is what replacing an LSA's body in place gives.  The image
+ *       the flat was built from is read during the call (it must still be alive); the flat refers to new_area
+ *       afterwards (which must outlive the flat's use).  Stub-link metrics and SR data do
  *       not touch the graph: rebuild the route table (hspf_ospfv2_rtable_create) after any FULL trigger.
  *       HSPF_E_NOMEM: more changed edges than `cap` (n_changed filled in; the flat is already updated).
  */
