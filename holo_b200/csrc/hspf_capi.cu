@@ -571,6 +571,7 @@ void *hspf_stream(hspf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t hspf_launch_count(const hspf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 /* kernels other translation units of the library enqueue on the ctx stream (route_cells.h) */
 void hspf_note_launches(hspf_ctx *ctx, uint32_t n) { if (ctx) ctx->launches += n; }
+int hspf_ctx_device(const hspf_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 int hspf_ctx_set_peer_slots(hspf_ctx *ctx, uint32_t n_peers, const int64_t *deltas) {
     if (!ctx || n_peers > 7 || (n_peers && !deltas)) return HSPF_E_INVAL;

@@ -81,8 +81,10 @@ int launch_cells(hspf_ctx *ctx, const hspf_ospfv2_rtable *rt, uint32_t n_jobs, c
     const uint32_t P = (uint32_t)rt->t.prefix.size();
     const uint64_t total = (uint64_t)n_jobs * P;
     if (total + n_gather == 0) return HSPF_OK;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    const int dev = hspf_ctx_device(ctx);
+    if (rt->device != dev) return HSPF_E_INVAL;               // the table was uploaded to another device
+    int sms = 0;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return HSPF_E_CUDA;
     // one resident wave (8 blocks of 256 per SM), warp-tile-stride beyond that
     const uint64_t want = std::max<uint64_t>((total + 255) / 256, 1);
@@ -117,6 +119,7 @@ extern "C" {
 int hspf_ospfv2_rtable_upload(hspf_ctx *ctx, hspf_ospfv2_rtable *rt) {
     if (!ctx || !rt) return HSPF_E_INVAL;
     hspf_rtable_release_device(rt);
+    if (cudaSetDevice(hspf_ctx_device(ctx)) != cudaSuccess) return HSPF_E_CUDA;
     const size_t off_bytes = (rt->t.off.size() * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t con_bytes = rt->t.contribs.size() * sizeof(RouteContrib);
     void *blob = nullptr;
@@ -128,6 +131,7 @@ int hspf_ospfv2_rtable_upload(hspf_ctx *ctx, hspf_ospfv2_rtable *rt) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the host vectors may go away after the call
     if (e != cudaSuccess) { cudaFree(blob); return HSPF_E_CUDA; }
     rt->d_blob = blob;
+    rt->device = hspf_ctx_device(ctx);
     rt->d_off = static_cast<const uint32_t *>(blob);
     rt->d_contribs = reinterpret_cast<const RouteContrib *>(static_cast<char *>(blob) + off_bytes);
     return HSPF_OK;
@@ -198,6 +202,7 @@ int hspf_ospfv2_run_area_batch(hspf_ctx *ctx, const hl_ospfv2_area *area, const 
             gather_off[j + 1] = (uint32_t)gv.size();
         }
         const uint32_t G = (uint32_t)gv.size();
+        if (cudaSetDevice(hspf_ctx_device(ctx)) != cudaSuccess) return HSPF_E_CUDA;
         if (G > gather_cap || (G && (!gather_v || !gather_nh))) return HSPF_E_NOMEM;
         rc = hspf_graph_upload(ctx, &csr, &g);
         if (rc) return rc;

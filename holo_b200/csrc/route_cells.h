@@ -144,3 +144,4 @@ void hspf_rtable_release_device(hspf_ospfv2_rtable *rt);
 // counts kernels this translation unit enqueues on the ctx stream (hspf_capi.cu, hspf_launch_count)
 struct hspf_ctx;
 extern "C" void hspf_note_launches(hspf_ctx *ctx, uint32_t n);
+extern "C" int hspf_ctx_device(const hspf_ctx *ctx);     // the CUDA device the ctx and its stream belong to
