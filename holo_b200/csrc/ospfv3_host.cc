@@ -268,6 +268,36 @@ int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out) {
 
 void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat) { delete flat; }
 
+int hspf_ospfv3_flat_update(hspf_ospfv3_flat *flat, const hl_ospfv3_area *na, uint32_t *kind, uint32_t *edges,
+                            uint32_t *costs, uint32_t cap, uint32_t *n_changed) {
+    if (!flat || !na || !kind || !n_changed) return HSPF_E_INVAL;
+    try {
+        *n_changed = 0;
+        hspf_ospfv3_flat fresh;
+        const int rc = flatten(na, fresh);
+        if (rc) return rc;
+        hspf_ospfv3_flat &f = *flat;
+        // same vertices, same edges between them, same per-edge link records: only metrics can differ
+        const bool same_graph = f.rid == fresh.rid && f.ifid == fresh.ifid && f.is_router == fresh.is_router && f.row == fresh.row &&
+                                f.col == fresh.col && f.vflags == fresh.vflags;
+        if (!same_graph) {
+            f = std::move(fresh);
+            *kind = HSPF_FLAT_REBUILT;
+            return HSPF_OK;
+        }
+        uint32_t changed = 0;
+        for (uint32_t e = 0; e < (uint32_t)f.cost.size(); ++e) {
+            if (f.cost[e] == fresh.cost[e]) continue;
+            if (changed < cap && edges && costs) { edges[changed] = e; costs[changed] = fresh.cost[e]; }
+            ++changed;
+        }
+        f = std::move(fresh);                    // LSA / link indices of the new image
+        *n_changed = changed;
+        *kind = changed ? HSPF_FLAT_COSTS : HSPF_FLAT_UNCHANGED;
+        return changed > cap ? HSPF_E_NOMEM : HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
 int hspf_ospfv3_flat_csr(const hspf_ospfv3_flat *flat, hspf_csr *out) {
     if (!flat || !out) return HSPF_E_INVAL;
     fill_csr(*flat, out);

@@ -205,6 +205,10 @@ class Flat:
         if rc != capi.HSPF_OK:
             raise capi.HspfError(rc, "hspf_ospfv3_flatten failed")
         self.handle = h
+        self._load()
+
+    def _load(self):
+        lib, h = self.lib, self.handle
         cs = capi.CsrStruct()
         lib.hspf_ospfv3_flat_csr(h, C.byref(cs))
         V, E = cs.n_vertices, cs.n_edges
@@ -220,6 +224,22 @@ class Flat:
 
     def router_vertex(self, router_id: int) -> int:
         return int(self.lib.hspf_ospfv3_flat_router_vertex(self.handle, router_id))
+
+    def update(self, new_area: "Ospfv3Area"):
+        """hspf_ospfv3_flat_update -> (kind, edges, costs) with kind 0 unchanged / 1 costs / 2 rebuilt."""
+        self.lib.hspf_ospfv3_flat_update.argtypes = [C.c_void_p, C.POINTER(AreaStruct), C.POINTER(C.c_uint32), C.c_void_p,
+                                                     C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        cap = max(int(self.csr.n_edges), 1)
+        edges, costs = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        kind, n = C.c_uint32(), C.c_uint32()
+        s = new_area.as_struct()
+        rc = self.lib.hspf_ospfv3_flat_update(self.handle, C.byref(s), C.byref(kind), edges.ctypes.data, costs.ctypes.data, cap,
+                                              C.byref(n))
+        if rc != capi.HSPF_OK:
+            raise capi.HspfError(rc, "hspf_ospfv3_flat_update failed")
+        self.area, self._s = new_area, s
+        self._load()
+        return kind.value, edges[: n.value].copy(), costs[: n.value].copy()
 
     def __del__(self):
         try:

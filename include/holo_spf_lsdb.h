@@ -226,6 +226,10 @@ typedef struct hspf_ospfv3_flat hspf_ospfv3_flat;
 int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out);
 void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat);
 int hspf_ospfv3_flat_csr(const hspf_ospfv3_flat *flat, hspf_csr *out);
+/* As hspf_isis_flat_update: the area is re-walked (linear), the flat then describes new_area, and `kind` says what
+ * to upload — nothing, the listed edge costs (hspf_graph_update_costs: an interface cost change), or everything. */
+int hspf_ospfv3_flat_update(hspf_ospfv3_flat *flat, const hl_ospfv3_area *new_area, uint32_t *kind, uint32_t *edges,
+                            uint32_t *costs, uint32_t cap, uint32_t *n_changed);
 int hspf_ospfv3_flat_vertices(const hspf_ospfv3_flat *flat, const uint32_t **router_ids, const uint32_t **iface_ids,
                               const uint8_t **is_router, uint32_t *n_vertices);
 uint32_t hspf_ospfv3_flat_router_vertex(const hspf_ospfv3_flat *flat, uint32_t router_id);
