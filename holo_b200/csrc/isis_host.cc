@@ -312,7 +312,10 @@ int hspf_isis_spf_type(const hl_isis_level *ol, const hl_isis_level *nl, const h
         const hl_isis_lsp *x = find(ol, tr[k].lan_id, tr[k].fragment), *y = find(nl, tr[k].lan_id, tr[k].fragment);
         if (!y) return HSPF_E_INVAL;                         // a trigger is an LSP that was just installed
         bool topology_change = true;
-        if (x && (x->rem_lifetime == 0) == (y->rem_lifetime == 0) && x->flags == y->flags &&
+        // lsp.flags (LspFlags: the image carries its OL and ATT bits; the other image flags come from TLVs, which the
+        // reference does not compare here)
+        const uint8_t hdr_bits = HL_LSPF_OL | HL_LSPF_ATT;
+        if (x && (x->rem_lifetime == 0) == (y->rem_lifetime == 0) && (x->flags & hdr_bits) == (y->flags & hdr_bits) &&
             same_kind(ol, x, nl, y, HL_ISIS_REACH_LEGACY) && same_kind(ol, x, nl, y, HL_ISIS_REACH_EXT))
             topology_change = false;
         if (topology_change) { *spf_type = HL_ISIS_SPF_FULL; break; }

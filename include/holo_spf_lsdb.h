@@ -270,8 +270,8 @@ int hspf_isis_compute_spt(hspf_ctx *ctx, const hl_isis_level *lvl, uint64_t root
  * Trigger-keyed recomputation for IS-IS.
  *   hspf_isis_spf_type     the decision lsp_install makes per installed LSP (holo-isis/src/lsdb.rs:1450-1465,
  *                          1525-1531): a run is FULL when any trigger LSP differs from its previous instance in
- *                          expiry, flags or its IS-reachability / extended-IS-reachability entries (a new LSP
- *                          always does); otherwise ROUTE_ONLY — compute_routes over the standing SPTs
+ *                          expiry, LSP flags (the image's OL and ATT bits) or its IS-reachability / extended-IS-
+ *                          reachability entries (a new LSP always does); otherwise ROUTE_ONLY — compute_routes over the standing SPTs
  *                          (hspf_isis_routes_from_planes with the planes of the last full run).  As in the
  *                          reference, MT IS-reachability (TLV 222) entries are not part of the comparison.
  *   hspf_isis_flat_update  brings a flattened level up to date with `new_lvl` and says what to upload:

@@ -599,7 +599,9 @@ extern "C" int oracle_isis_spf_type(const hl_isis_level *old_lvl, const hl_isis_
         if (o >= 0) {
             const hl_isis_lsp &a = old_lvl->lsps[o], &b = new_lvl->lsps[w];
             const bool a_expired = a.rem_lifetime == 0, b_expired = b.rem_lifetime == 0;
-            if (a_expired == b_expired && a.flags == b.flags &&
+            // LspFlags bits present in the image: overload and attached
+            const bool same_flags = ((a.flags ^ b.flags) & (HL_LSPF_OL | HL_LSPF_ATT)) == 0;
+            if (a_expired == b_expired && same_flags &&
                 reach_of(old_lvl, o, HL_ISIS_REACH_LEGACY) == reach_of(new_lvl, w, HL_ISIS_REACH_LEGACY) &&
                 reach_of(old_lvl, o, HL_ISIS_REACH_EXT) == reach_of(new_lvl, w, HL_ISIS_REACH_EXT))
                 topology_change = false;

@@ -83,6 +83,11 @@ def test_structural_changes_rebuild_and_ip_changes_do_not_touch_the_graph():
     flat = isis.Flat(lv)
     assert isis.flat_update(flat, new) [0] == isis.FLAT_UNCHANGED
     assert isis.spf_type(lv, new, [(isis.sysid(9) << 8, 0)]) == isis.SPF_ROUTE_ONLY
+    # Protocols-Supported changes (a TLV, not an LSP flag) are not compared by the reference: RouteOnly,
+    # although the flattener's transit gate reads them (the caller of a RouteOnly run keeps its SPT)
+    new = copy.deepcopy(lv)
+    new.lsps["flags"][i] = int(new.lsps["flags"][i]) & (0xFF ^ isis.LSPF_NLPID_IPV4)
+    assert isis.spf_type(lv, new, [(isis.sysid(9) << 8, 0)]) == isis.SPF_ROUTE_ONLY
     # a brand-new LSP is always a topology change
     newer = copy.deepcopy(lv)
     keep = np.ones(len(lv.lsps), bool)
@@ -107,7 +112,7 @@ def test_spf_type_matches_restatement(seed):
         if what < 0.25 and n:
             new.reaches["metric"][lo + int(rng.integers(0, n))] += 1
         elif what < 0.4:
-            new.lsps["flags"][i] ^= isis.LSPF_ATT
+            new.lsps["flags"][i] ^= int(rng.choice([isis.LSPF_ATT, isis.LSPF_OL, isis.LSPF_HAS_PROTOCOLS]))
         elif what < 0.5:
             new.lsps["rem_lifetime"][i] = 0
         elif what < 0.6 and n:
