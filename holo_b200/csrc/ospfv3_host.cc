@@ -16,6 +16,9 @@
 #include <new>
 #include <unordered_map>
 #include <unordered_set>
+#include <array>
+#include <set>
+#include <tuple>
 #include <vector>
 
 #include "holo_spf_lsdb.h"
@@ -267,6 +270,47 @@ int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out) {
 }
 
 void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat) { delete flat; }
+
+int hspf_ospfv3_spf_computation_type(const hl_lsa_trigger6 *tr, uint32_t n, const hl_ip_prefix *prefixes, uint32_t n_prefixes,
+                                     hl_spf_computation6 *out) {
+    if (!out || (n && !tr) || (n_prefixes && !prefixes)) return HSPF_E_INVAL;
+    out->kind = HL_SPF_PARTIAL;
+    out->n_intra = out->n_inter_network = out->n_inter_router = out->n_external = 0;
+    auto normalized = [](uint16_t c) -> uint16_t { return (c >= 33 && c <= 41) ? (uint16_t)(c - 32) : c; };   // Ext* -> legacy code
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint16_t c = normalized(tr[i].function_code);
+        if (c == 1 || c == 2 || c == 8 || c == 12) { out->kind = HL_SPF_FULL; return HSPF_OK; }
+        if ((uint64_t)tr[i].prefix_off + tr[i].n_prefixes > n_prefixes) return HSPF_E_INVAL;
+    }
+    try {
+        using Key = std::tuple<uint8_t, std::array<uint8_t, 16>, uint8_t>;      // IpNetwork Ord: family, address, length
+        auto key = [](const hl_ip_prefix &p) { std::array<uint8_t, 16> b; std::memcpy(b.data(), p.addr.bytes, 16); return Key{p.addr.is_v6, b, p.len}; };
+        std::map<Key, hl_ip_prefix> intra, inter, ext;
+        std::set<uint32_t> rtr;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint16_t c = normalized(tr[i].function_code);
+            const hl_ip_prefix *p = prefixes + tr[i].prefix_off;
+            if (c == 9) for (uint32_t k = 0; k < tr[i].n_prefixes; ++k) intra.emplace(key(p[k]), p[k]);
+            else if (c == 3) { if (tr[i].n_prefixes) inter.emplace(key(p[0]), p[0]); }
+            else if (c == 4) rtr.insert(tr[i].router_id);
+            else if (c == 5) { if (tr[i].n_prefixes) ext.emplace(key(p[0]), p[0]); }
+        }
+        out->n_intra = (uint32_t)intra.size(); out->n_inter_network = (uint32_t)inter.size();
+        out->n_inter_router = (uint32_t)rtr.size(); out->n_external = (uint32_t)ext.size();
+        if (intra.size() > out->cap || inter.size() > out->cap || rtr.size() > out->cap || ext.size() > out->cap) return HSPF_E_NOMEM;
+        if ((!intra.empty() && !out->intra) || (!inter.empty() && !out->inter_network) || (!rtr.empty() && !out->inter_router) ||
+            (!ext.empty() && !out->external)) return HSPF_E_INVAL;
+        uint32_t k = 0;
+        for (auto &kv : intra) out->intra[k++] = kv.second;
+        k = 0;
+        for (auto &kv : inter) out->inter_network[k++] = kv.second;
+        k = 0;
+        for (uint32_t r : rtr) out->inter_router[k++] = r;
+        k = 0;
+        for (auto &kv : ext) out->external[k++] = kv.second;
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; }
+}
 
 int hspf_ospfv3_flat_update(hspf_ospfv3_flat *flat, const hl_ospfv3_area *na, uint32_t *kind, uint32_t *edges,
                             uint32_t *costs, uint32_t cap, uint32_t *n_changed) {

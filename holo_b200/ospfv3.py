@@ -186,6 +186,39 @@ def area_from_planes(area: Ospfv3Area, spf) -> Ospfv3Result:
     return res
 
 
+IP_PREFIX_DT = np.dtype([("addr", IP_DT), ("len", "u1"), ("_pad", "u1", (3,))], align=True)
+TRIGGER6_DT = np.dtype([("adv_rtr", "<u4"), ("lsa_id", "<u4"), ("router_id", "<u4"), ("prefix_off", "<u4"), ("n_prefixes", "<u4"),
+                        ("function_code", "<u2"), ("_pad", "u1", (2,))], align=True)
+
+
+class SpfComputation6Struct(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("n_intra", C.c_uint32), ("n_inter_network", C.c_uint32), ("n_inter_router", C.c_uint32),
+                ("n_external", C.c_uint32), ("cap", C.c_uint32), ("intra", C.c_void_p), ("inter_network", C.c_void_p),
+                ("inter_router", C.c_void_p), ("external", C.c_void_p)]
+
+
+def spf_computation_type(triggers, fn=None):
+    """hspf_ospfv3_spf_computation_type.  triggers: [(function_code, adv_rtr, lsa_id, router_id, [(addr, len), ...])]
+    -> (kind, intra, inter_network, inter_router, external) with prefixes as (addr string, len)."""
+    if fn is None:
+        fn = capi.load_library().hspf_ospfv3_spf_computation_type
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SpfComputation6Struct)]
+    tr = np.zeros(len(triggers), TRIGGER6_DT)
+    pf = []
+    for i, (code, adv, lsa_id, router_id, prefixes) in enumerate(triggers):
+        tr[i] = (adv, lsa_id, router_id, len(pf), len(prefixes), code, (0, 0))
+        pf += [(ip_rec(a), ln, (0, 0, 0)) for a, ln in prefixes]
+    pfa = np.asarray(pf, IP_PREFIX_DT) if pf else np.zeros(0, IP_PREFIX_DT)
+    cap = max(len(pfa), len(tr), 1)
+    a, b, c, d = np.zeros(cap, IP_PREFIX_DT), np.zeros(cap, IP_PREFIX_DT), np.zeros(cap, np.uint32), np.zeros(cap, IP_PREFIX_DT)
+    s = SpfComputation6Struct(0, 0, 0, 0, 0, cap, a.ctypes.data, b.ctypes.data, c.ctypes.data, d.ctypes.data)
+    rc = fn(tr.ctypes.data if len(tr) else None, len(tr), pfa.ctypes.data if len(pfa) else None, len(pfa), C.byref(s))
+    if rc != capi.HSPF_OK:
+        raise capi.HspfError(rc, "ospfv3 spf_computation_type failed")
+    out = lambda arr, k: [(ip_str(x["addr"]), int(x["len"])) for x in arr[:k]]
+    return s.kind, out(a, s.n_intra), out(b, s.n_inter_network), [int(x) for x in c[: s.n_inter_router]], out(d, s.n_external)
+
+
 class Flat:
     def __init__(self, area: Ospfv3Area):
         lib = capi.load_library()

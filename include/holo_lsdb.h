@@ -426,6 +426,31 @@ typedef struct hl_ospfv3_prefix {
     uint16_t metric;
 } hl_ospfv3_prefix;
 
+/* SPF triggers of OSPFv3 (SpfTriggerLsa, spf.rs:115-120; Ospfv3::spf_computation_type, ospfv3/spf.rs:96-162).
+ * function_code: LsaFunctionCode of `new` — legacy or extended (1/33 router, 2/34 network, 3/35 inter-area-prefix,
+ * 4/36 inter-area-router, 5/37 AS-external, 8/40 link, 9/41 intra-area-prefix, 11 grace, 12 router-information).
+ * prefixes[prefix_off .. +n_prefixes]: intra-area-prefix: the prefixes of the new AND of the old instance;
+ * inter-area-prefix / AS-external: the LSA's prefix.  router_id: inter-area-router: the destination router. */
+typedef struct hl_ip_prefix { hl_ip_addr addr; uint8_t len; uint8_t _pad[3]; } hl_ip_prefix;
+typedef struct hl_lsa_trigger6 {
+    uint32_t adv_rtr;
+    uint32_t lsa_id;
+    uint32_t router_id;
+    uint32_t prefix_off;
+    uint32_t n_prefixes;
+    uint16_t function_code;
+    uint8_t  _pad[2];
+} hl_lsa_trigger6;
+typedef struct hl_spf_computation6 {
+    uint32_t kind;                 /* HL_SPF_FULL / HL_SPF_PARTIAL                              */
+    uint32_t n_intra, n_inter_network, n_inter_router, n_external;
+    uint32_t cap;                  /* capacity of each array below                               */
+    hl_ip_prefix *intra;           /* sorted, unique (BTreeSet<IpNetwork>: family, address, length) */
+    hl_ip_prefix *inter_network;
+    uint32_t     *inter_router;
+    hl_ip_prefix *external;
+} hl_spf_computation6;
+
 /* Intra-Area-Prefix-LSAs in LsaKey order (ospfv3/spf.rs:420-477). */
 #define HL_V3_REF_ROUTER  1u
 #define HL_V3_REF_NETWORK 2u

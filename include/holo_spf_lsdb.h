@@ -226,6 +226,12 @@ typedef struct hspf_ospfv3_flat hspf_ospfv3_flat;
 int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out);
 void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat);
 int hspf_ospfv3_flat_csr(const hspf_ospfv3_flat *flat, hspf_csr *out);
+/* Ospfv3::spf_computation_type (holo-ospf/src/ospfv3/spf.rs:96-162): Router-, Network-, Link- and Router-Information
+ * LSAs ask for a full run; otherwise the run is partial over the prefixes of the changed Intra-Area-Prefix (old and
+ * new instance), Inter-Area-Prefix and AS-external LSAs and the routers of the changed Inter-Area-Router LSAs.
+ * HSPF_E_NOMEM when a set does not fit `cap` (counts filled in). */
+int hspf_ospfv3_spf_computation_type(const hl_lsa_trigger6 *triggers, uint32_t n_triggers, const hl_ip_prefix *prefixes,
+                                     uint32_t n_prefixes, hl_spf_computation6 *out);
 /* As hspf_isis_flat_update: the area is re-walked (linear), the flat then describes new_area, and `kind` says what
  * to upload — nothing, the listed edge costs (hspf_graph_update_costs: an interface cost change), or everything. */
 int hspf_ospfv3_flat_update(hspf_ospfv3_flat *flat, const hl_ospfv3_area *new_area, uint32_t *kind, uint32_t *edges,

@@ -340,3 +340,51 @@ extern "C" int oracle_ospfv3_run_area(const hl_ospfv3_area *a, hl_ospfv3_result 
     }
     return 0;
 }
+
+// Restates Ospfv3::spf_computation_type (holo-ospf/src/ospfv3/spf.rs:96-162): a Router-, Network-, Link- or
+// Router-Information LSA among the triggers (function code normalised: extended LSAs count as their legacy twins)
+// asks for a full run; otherwise partial, with BTreeSets of the prefixes of the changed Intra-Area-Prefix LSAs (new
+// and old instance), Inter-Area-Prefix LSAs and AS-external LSAs, and of the routers of the Inter-Area-Router LSAs.
+// PARITY UNPINNED: no reference test records this value.
+#include <algorithm>
+extern "C" int oracle_ospfv3_spf_computation_type(const hl_lsa_trigger6 *tr, uint32_t n, const hl_ip_prefix *prefixes,
+                                                  uint32_t /*n_prefixes*/, hl_spf_computation6 *out) {
+    auto code = [](uint16_t c) {
+        switch (c) { case 33: return 1; case 34: return 2; case 35: return 3; case 36: return 4; case 37: return 5; case 40: return 8;
+                     case 41: return 9; default: return (int)c; }
+    };
+    auto less = [](const hl_ip_prefix &a, const hl_ip_prefix &b) {
+        if (a.addr.is_v6 != b.addr.is_v6) return a.addr.is_v6 < b.addr.is_v6;
+        const int c = std::memcmp(a.addr.bytes, b.addr.bytes, 16);
+        return c != 0 ? c < 0 : a.len < b.len;
+    };
+    auto same = [&](const hl_ip_prefix &a, const hl_ip_prefix &b) { return !less(a, b) && !less(b, a); };
+    out->n_intra = out->n_inter_network = out->n_inter_router = out->n_external = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const int c = code(tr[i].function_code);
+        if (c == 1 || c == 2 || c == 8 || c == 12) { out->kind = HL_SPF_FULL; return 0; }
+    }
+    out->kind = HL_SPF_PARTIAL;
+    std::vector<hl_ip_prefix> intra, inter, ext;
+    std::vector<uint32_t> rtr;
+    for (uint32_t i = 0; i < n; ++i) {
+        const int c = code(tr[i].function_code);
+        const hl_ip_prefix *p = prefixes + tr[i].prefix_off;
+        if (c == 9) intra.insert(intra.end(), p, p + tr[i].n_prefixes);
+        if (c == 3 && tr[i].n_prefixes) inter.push_back(p[0]);
+        if (c == 4) rtr.push_back(tr[i].router_id);
+        if (c == 5 && tr[i].n_prefixes) ext.push_back(p[0]);
+    }
+    auto set_of = [&](std::vector<hl_ip_prefix> &v) {
+        std::sort(v.begin(), v.end(), less);
+        v.erase(std::unique(v.begin(), v.end(), same), v.end());
+    };
+    set_of(intra); set_of(inter); set_of(ext);
+    std::sort(rtr.begin(), rtr.end());
+    rtr.erase(std::unique(rtr.begin(), rtr.end()), rtr.end());
+    for (auto &p : intra) out->intra[out->n_intra++] = p;
+    for (auto &p : inter) out->inter_network[out->n_inter_network++] = p;
+    for (uint32_t r : rtr) out->inter_router[out->n_inter_router++] = r;
+    for (auto &p : ext) out->external[out->n_external++] = p;
+    return 0;
+}

@@ -63,3 +63,38 @@ def test_structural_change_rebuilds_and_refresh_is_a_no_op():
     new2.router_lsas["age"][i] = 3600                                      # the fragment ages out
     assert flat.update(new2)[0] == 2
     same_flat(flat, ospfv3.Flat(new2))
+
+
+ROUTER, NETWORK, INTER_PREFIX, INTER_ROUTER, EXTERNAL, LINK, INTRA_PREFIX, GRACE, ROUTER_INFO = 1, 2, 3, 4, 5, 8, 9, 11, 12
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_spf_computation_type_matches_restatement(seed):
+    rng = np.random.default_rng(900 + seed)
+    pool = [("2001:db8:%x::" % i, 64) for i in range(5)] + [("2001:db8::%x" % i, 128) for i in range(3)] + [("10.0.%d.0" % i, 24) for i in range(3)]
+    codes = [INTER_PREFIX, INTER_ROUTER, EXTERNAL, INTRA_PREFIX, GRACE, 35, 36, 37, 41] + ([ROUTER, NETWORK, LINK, ROUTER_INFO, 33, 40] if rng.random() < 0.25 else [])
+    tr = []
+    for _ in range(int(rng.integers(0, 9))):
+        c = int(rng.choice(codes))
+        k = int(rng.integers(0, 4)) if c in (INTRA_PREFIX, 41) else 1
+        pf = [pool[int(j)] for j in rng.integers(0, len(pool), k)]
+        tr.append((c, int(rng.integers(1, 4)), int(rng.integers(0, 3)), int(rng.choice([0x01010101, 0x02020202])), pf))
+    a = ospfv3.spf_computation_type(tr)
+    b = ospfv3.spf_computation_type(tr, fn=pyoracle.lib().oracle_ospfv3_spf_computation_type)
+    assert a == b
+
+
+def test_spf_computation_type_cases():
+    p1, p2, v4 = ("2001:db8:1::", 64), ("2001:db8:2::", 64), ("10.0.0.0", 24)
+    FULL, PARTIAL = 1, 2
+    assert ospfv3.spf_computation_type([(INTER_PREFIX, 1, 1, 0, [p1]), (LINK, 1, 2, 0, [])])[0] == FULL
+    assert ospfv3.spf_computation_type([(33, 1, 0, 0, [])])[0] == FULL                       # E-Router-LSA
+    assert ospfv3.spf_computation_type([(ROUTER_INFO, 1, 0, 0, [])])[0] == FULL
+    kind, intra, inter, rtr, ext = ospfv3.spf_computation_type([
+        (INTRA_PREFIX, 1, 0, 0, [p2, p1, v4]),          # prefixes of the new and of the old instance
+        (41, 2, 0, 0, [p1]),                            # E-Intra-Area-Prefix-LSA
+        (INTER_PREFIX, 1, 5, 0, [p2]), (INTER_ROUTER, 1, 6, 0x09090909, []), (EXTERNAL, 3, 7, 0, [p1]), (GRACE, 1, 0, 0, [])])
+    assert kind == PARTIAL
+    assert intra == [("10.0.0.0", 24), ("2001:db8:1::", 64), ("2001:db8:2::", 64)]            # IPv4 before IPv6, unique
+    assert inter == [p2] and rtr == [0x09090909] and ext == [p1]
+    assert ospfv3.spf_computation_type([]) == (PARTIAL, [], [], [], [])
