@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Long-running CPU fuzzes of the product's host stages against the oracle's restatements:
-  python scripts/fuzz_host_stages.py {rib|isis|ospf} <seconds>
+  python scripts/fuzz_host_stages.py {rib|isis|ospf|cells} <seconds>
 rib : hspf_ospfv{2,3}_update_rib_full + rib_diff on random multi-area tables
 isis: hspf_isis_routes_from_planes (with SR) on random levels
 ospf: hspf_ospfv{2,3}_area_from_planes on random areas
-(round 1: 261 k / 149 k / 146 k instances without a mismatch)."""
+cells: the device route kernel's body on the CPU + hspf_ospfv2_routes_from_cells on colliding prefixes
+(round 1: 261 k / 149 k / 146 k instances without a mismatch; round 2: 70 k / 91 k / 88 k / 72 k roots, none)."""
 import os
 import sys
 
