@@ -246,3 +246,16 @@ def test_colliding_prefixes_fuzz_covers_both_outcomes():
     if len(FUZZ_STATS) < 12:
         pytest.skip("runs after the whole fuzz")
     assert sum(a for a, _ in FUZZ_STATS.values()) >= 40 and sum(b for _, b in FUZZ_STATS.values()) >= 8
+
+
+def test_c5_size_lsdb(harness):
+    """BASELINE C5 shape at full size (10 000 routers, 5 % of the adjacencies on LANs, costs {10, 20}, Prefix-SIDs):
+    29 213 prefixes, 48 212 advertisers; the cells of three roots — the bench's local router, a LAN's designated
+    router, a router in the middle — decode to the faithful oracle's route tables."""
+    t = synth.random_topology(10000, 40000, synth.SEED_BASE + 5, cost_choices=[10, 20], lan_fraction=0.05)
+    for root in (0, int(t.lans[0][0][0]), 5000):
+        area, rt, cells, res, ref = check_root(harness, t, root)
+        same_routes(res, ref)
+        assert rt.n_prefixes == 29213 and rt.n_contributors == 48212
+        assert len(res.routes) == rt.n_prefixes and int((res.routes["n_nh"] > 1).sum()) > 1000
+        assert int(res.routes["has_sr_label"].sum()) >= 9999
