@@ -19,9 +19,11 @@
 #include <array>
 #include <set>
 #include <tuple>
+#include <memory>
 #include <vector>
 
 #include "holo_spf_lsdb.h"
+#include "route_cells.h"
 
 namespace {
 
@@ -555,6 +557,155 @@ int hspf_ospfv3_area_from_planes(const hl_ospfv3_area *a, const uint32_t *dist, 
     } catch (...) {
         return HSPF_E_INVAL;
     }
+}
+
+
+/* ---- batched route stage: table and per-job decode for OSPFv3 areas (route_cells.h) ---------------------- */
+
+int hspf_ospfv3_rtable_create(const hspf_ospfv3_flat *flat, hspf_ospfv2_rtable **out) {
+    if (!flat || !flat->area || !out) return HSPF_E_INVAL;
+    try {
+        const hspf_ospfv3_flat &f = *flat;
+        const hl_ospfv3_area *a = f.area;
+        // update_rib_intra_area meets the advertisements LSA by LSA in LsaKey order (ospfv3/spf.rs:420-477)
+        std::vector<uint32_t> iord(a->n_iap_lsas);
+        for (uint32_t i = 0; i < a->n_iap_lsas; ++i) iord[i] = i;
+        std::stable_sort(iord.begin(), iord.end(), [&](uint32_t x, uint32_t y) {
+            const auto &p = a->iap_lsas[x], &q = a->iap_lsas[y];
+            return p.adv_rtr != q.adv_rtr ? p.adv_rtr < q.adv_rtr : p.lsa_id < q.lsa_id;
+        });
+        struct Raw { PKey key; uint32_t seq; hspf::RouteContrib c; uint8_t otype, options; uint32_t oadv; };
+        std::vector<Raw> raw;
+        for (uint32_t i : iord) {
+            const auto &l = a->iap_lsas[i];
+            if (l.age == HL_LSA_MAX_AGE) continue;
+            uint32_t v = kNone;
+            if (l.ref_type == HL_V3_REF_ROUTER) {
+                if (l.ref_lsa_id != 0) continue;
+                auto it = f.rtr_vertex.find(l.ref_adv_rtr);
+                if (it != f.rtr_vertex.end()) v = it->second;
+            } else if (l.ref_type == HL_V3_REF_NETWORK) {
+                auto it = f.net_vertex.find(((uint64_t)l.ref_adv_rtr << 32) | l.ref_lsa_id);
+                if (it != f.net_vertex.end()) v = it->second;
+            }
+            if (v == kNone) continue;
+            uint8_t otype; uint32_t oadv, oid;
+            if (f.is_router[v]) { const auto &r = a->router_lsas[f.first_lsa[v]]; otype = 1; oadv = r.adv_rtr; oid = r.lsa_id; }
+            else { const auto &n = a->network_lsas[f.first_lsa[v]]; otype = 2; oadv = n.adv_rtr; oid = n.lsa_id; }
+            for (uint32_t k = 0; k < l.n_prefixes; ++k) {
+                const auto &px = a->prefixes[l.prefix_off + k];
+                if (px.options & HL_PFX_OPT_NU) continue;
+                Raw r{};
+                r.key = PKey{px.addr, px.len}; r.seq = (uint32_t)raw.size();
+                r.c.vertex = v; r.c.origin_id = oid; r.c.metric = px.metric; r.c.sid_class = 0; r.c.is_network = otype == 2;
+                r.otype = otype; r.options = px.options; r.oadv = oadv;
+                raw.push_back(r);
+            }
+        }
+        std::sort(raw.begin(), raw.end(), [](const Raw &x, const Raw &y) {
+            if (x.key < y.key) return true;
+            if (y.key < x.key) return false;
+            return x.seq < y.seq;
+        });
+        auto rt = std::make_unique<hspf_ospfv2_rtable>();
+        auto &t = rt->t;
+        t.v3 = true;
+        t.n_vertices = (uint32_t)f.rid.size();
+        t.sids.push_back(hspf::SidDesc{0, 0, 0});
+        for (size_t i = 0; i < raw.size(); ++i) {
+            if (i == 0 || raw[i - 1].key < raw[i].key) {
+                t.prefix6.push_back(raw[i].key.a); t.prefix.push_back(0); t.plen.push_back(raw[i].key.len); t.off.push_back((uint32_t)i);
+            }
+            t.contribs.push_back(raw[i].c);
+            t.origin_type.push_back(raw[i].otype);
+            t.origin_adv.push_back(raw[i].oadv);
+            t.options6.push_back(raw[i].options);
+            rt->ext_of.push_back(-1);
+        }
+        t.off.push_back((uint32_t)raw.size());
+        *out = rt.release();
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
+}
+
+int hspf_ospfv3_rtable_prefixes6(const hspf_ospfv2_rtable *rt, const hl_ip_addr **prefixes, const uint32_t **lens) {
+    if (!rt || !rt->t.v3) return HSPF_E_INVAL;
+    if (prefixes) *prefixes = rt->t.prefix6.data();
+    if (lens) *lens = rt->t.plen.data();
+    return HSPF_OK;
+}
+
+int hspf_ospfv3_routes_from_cells(const hl_ospfv3_area *a, const hspf_ospfv2_rtable *rt, const hl_route_cell *cells,
+                                  const uint32_t *gather_v, const uint64_t *gather_nh, uint32_t n_gather, hl_ospfv3_result *out) {
+    if (!a || !rt || !rt->t.v3 || !cells || !out || (n_gather && (!gather_v || !gather_nh))) return HSPF_E_INVAL;
+    try {
+        out->n_vertices = out->n_routers = out->n_routes = out->n_nexthops = 0;
+        out->transit_capability = 0;
+        out->root_found = 0;
+        hspf_ospfv3_flat f;
+        int rc = flatten(a, f);
+        if (rc) return rc;
+        const uint32_t V = (uint32_t)f.rid.size();
+        if (V != rt->t.n_vertices) return HSPF_E_INVAL;                   // not the LSDB the table was built from
+        auto rit = f.rtr_vertex.find(a->router_id);
+        if (rit == f.rtr_vertex.end()) return HSPF_OK;
+        out->root_found = 1;
+        std::vector<uint64_t> sparse_nh(V, 0);                             // only the transit networks next to the root are read
+        for (uint32_t i = 0; i < n_gather; ++i) {
+            if (gather_v[i] >= V) return HSPF_E_INVAL;
+            sparse_nh[gather_v[i]] = gather_nh[i];
+        }
+        Resolver rs{f, a, rit->second, sparse_nh.data(), 1, {}, {}};
+        rs.atom_nh.resize(64);
+        rs.atom_done.assign(64, 0);
+        const auto &t = rt->t;
+        const uint32_t P = (uint32_t)t.prefix6.size();
+        uint32_t n_routes = 0, n_nh = 0;
+        std::vector<Nh6> set;
+        for (uint32_t p = 0; p < P; ++p) {
+            const hl_route_cell &c = cells[p];
+            if (!(c.flags & HL_CELL_PRESENT)) continue;
+            if (c.flags & HL_CELL_MIXED_SID) return HSPF_E_UNSUPPORTED;
+            if (c.winner < t.off[p] || c.winner >= t.off[p + 1]) return HSPF_E_INVAL;
+            hl_route_net6 o{};
+            o.prefix = t.prefix6[p]; o.len = (uint8_t)t.plen[p];
+            o.flags = (c.flags & HL_CELL_CONNECTED) ? HL_ROUTE_CONNECTED : 0;
+            o.origin_type = t.origin_type[c.winner]; o.prefix_options = t.options6[c.winner]; o.metric = c.metric;
+            o.origin_adv_rtr = t.origin_adv[c.winner]; o.origin_lsa_id = t.contribs[c.winner].origin_id;
+            set.clear();
+            uint64_t m = c.nh_mask;
+            while (m) {
+                const uint32_t atom = (uint32_t)__builtin_ctzll(m);
+                m &= m - 1;
+                for (const Nh6 &x : rs.resolve(atom)) {
+                    auto it = std::lower_bound(set.begin(), set.end(), x, nh_less);
+                    if (it != set.end() && nh_same(*it, x)) {
+                        // same NexthopKey from another atom: the reference keeps the later advertiser's; both must agree
+                        if (it->iface != x.iface || it->has_nbr != x.has_nbr || (x.has_nbr && it->nbr != x.nbr)) return HSPF_E_UNSUPPORTED;
+                    } else {
+                        set.insert(it, x);
+                    }
+                }
+            }
+            if (set.size() > a->max_paths) set.resize(a->max_paths);
+            o.nh_off = n_nh; o.n_nh = (uint32_t)set.size();
+            if (n_routes < out->routes_cap && n_nh + set.size() <= out->nexthops_cap) {
+                out->routes[n_routes] = o;
+                uint32_t h = n_nh;
+                for (const Nh6 &x : set) {
+                    hl_nexthop6 q{};
+                    q.iface = x.iface; q.nbr_router_id = x.has_nbr ? x.nbr : 0;
+                    if (x.has_addr) q.addr = x.addr;
+                    q.has_addr = x.has_addr; q.has_nbr = x.has_nbr;
+                    out->nexthops[h++] = q;
+                }
+            }
+            ++n_routes; n_nh += (uint32_t)set.size();
+        }
+        out->n_routes = n_routes; out->n_nexthops = n_nh;
+        if (n_routes > out->routes_cap || n_nh > out->nexthops_cap) return HSPF_E_NOMEM;
+        return HSPF_OK;
+    } catch (const std::bad_alloc &) { return HSPF_E_NOMEM; } catch (...) { return HSPF_E_INVAL; }
 }
 
 }  // extern "C"

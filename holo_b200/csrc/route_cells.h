@@ -49,6 +49,11 @@ struct RouteTable {
     std::vector<uint32_t> origin_adv;
     std::vector<SidDesc> sids;               // [0] unused
     uint32_t n_vertices = 0;
+    // OSPFv3 tables (hspf_ospfv3_rtable_create): the prefixes proper; `prefix` is then zero-filled and `plen`
+    // repeats len6, so that every consumer of the common part (kernel launch, harness) sees P entries
+    std::vector<hl_ip_addr> prefix6;
+    std::vector<uint8_t> options6;           // per contributor: prefix options of its advertisement
+    bool v3 = false;
 };
 
 // Normalised view of one job's planes (32/64-bit or 16-bit planes).

@@ -226,6 +226,17 @@ typedef struct hspf_ospfv3_flat hspf_ospfv3_flat;
 int hspf_ospfv3_flatten(const hl_ospfv3_area *area, hspf_ospfv3_flat **out);
 void hspf_ospfv3_flat_free(hspf_ospfv3_flat *flat);
 int hspf_ospfv3_flat_csr(const hspf_ospfv3_flat *flat, hspf_csr *out);
+/* The batched route stage for OSPFv3 areas (see "Batched intra-area route stage" above): the table of an OSPFv3
+ * area — prefixes of the Intra-Area-Prefix-LSAs in route-table order, advertisers in the order update_rib_intra_area
+ * meets them (LSAs in LsaKey order, ospfv3/spf.rs:420-477) — is the same object; upload it with
+ * hspf_ospfv2_rtable_upload and run hspf_ospfv2_routes_batch[16] behind hspf_run_batch[16]_async over the area's
+ * graph.  hspf_ospfv3_routes_from_cells decodes one job's cells into the routes hspf_ospfv3_run_area returns for
+ * area->router_id (out->routes, out->nexthops).  hspf_ospfv3_rtable_prefixes6: the table's prefixes / lengths. */
+int hspf_ospfv3_rtable_create(const hspf_ospfv3_flat *flat, hspf_ospfv2_rtable **out);
+int hspf_ospfv3_rtable_prefixes6(const hspf_ospfv2_rtable *rt, const hl_ip_addr **prefixes, const uint32_t **lens);
+int hspf_ospfv3_routes_from_cells(const hl_ospfv3_area *area, const hspf_ospfv2_rtable *rt, const hl_route_cell *cells,
+                                  const uint32_t *gather_v, const uint64_t *gather_nh, uint32_t n_gather,
+                                  hl_ospfv3_result *out);
 /* Ospfv3::spf_computation_type (holo-ospf/src/ospfv3/spf.rs:96-162): Router-, Network-, Link- and Router-Information
  * LSAs ask for a full run; otherwise the run is partial over the prefixes of the changed Intra-Area-Prefix (old and
  * new instance), Inter-Area-Prefix and AS-external LSAs and the routers of the changed Inter-Area-Router LSAs.
