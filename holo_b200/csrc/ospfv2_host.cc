@@ -136,24 +136,28 @@ int flatten(const hl_ospfv2_area *a, hspf_ospfv2_flat &f) {
         }
     }
     // ---- mutual-link filter: keep u->v iff v has any raw link to u -----------------
-    std::unordered_set<uint64_t> have;
-    have.reserve(raw.size() * 2);
-    for (auto &e : raw) have.insert(((uint64_t)e.u << 32) | e.v);
-    f.row.assign(V + 1, 0);
-    for (auto &e : raw) {
+    // raw is grouped by u (vertices were walked in order): "v links back to u" is a scan of v's few raw links
+    std::vector<uint32_t> rrow(V + 1, 0);
+    for (auto &e : raw) rrow[e.u + 1]++;
+    for (uint32_t v = 0; v < V; ++v) rrow[v + 1] += rrow[v];
+    std::vector<uint8_t> keep(raw.size(), 0);
+    for (size_t i = 0; i < raw.size(); ++i) {
+        const Raw &e = raw[i];
         if (e.u == e.v) continue;   // a link to oneself is skipped by `spt.contains_key`
-        if (!have.count(((uint64_t)e.v << 32) | e.u)) continue;
-        f.row[e.u + 1]++;
+        for (uint32_t k = rrow[e.v]; k < rrow[e.v + 1]; ++k)
+            if (raw[k].v == e.u) { keep[i] = 1; break; }
     }
+    f.row.assign(V + 1, 0);
+    for (size_t i = 0; i < raw.size(); ++i) if (keep[i]) f.row[raw[i].u + 1]++;
     for (uint32_t v = 0; v < V; ++v) f.row[v + 1] += f.row[v];
     const uint32_t E = f.row[V];
     f.col.resize(E); f.cost.resize(E); f.link_index.resize(E); f.link_pos.resize(E);
-    std::vector<uint32_t> fill(f.row.begin(), f.row.end() - 1);
-    for (auto &e : raw) {   // raw is already grouped by u in link order
-        if (e.u == e.v) continue;
-        if (!have.count(((uint64_t)e.v << 32) | e.u)) continue;
-        const uint32_t k = fill[e.u]++;
+    uint32_t k = 0;
+    for (size_t i = 0; i < raw.size(); ++i) {   // grouped by u in link order: edges come out in CSR order
+        if (!keep[i]) continue;
+        const Raw &e = raw[i];
         f.col[k] = e.v; f.cost[k] = e.cost; f.link_index[k] = e.link; f.link_pos[k] = e.pos;
+        ++k;
     }
     return HSPF_OK;
 }
@@ -275,13 +279,45 @@ bool index_to_label(uint32_t index, const std::vector<const hl_srgb *> &srgbs, u
     return false;
 }
 
+// open-addressing u64 -> u32 table sized once (the tables below know their bound): a find is a multiply and a probe
+struct FlatMap64 {
+    static constexpr uint64_t kEmpty = ~0ull;
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> vals;
+    uint64_t mask = 0;
+    void init(size_t n) {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        keys.assign(cap, kEmpty);
+        vals.assign(cap, 0);
+        mask = cap - 1;
+    }
+    static uint64_t mix(uint64_t k) { k ^= k >> 29; k *= 0x9E3779B97F4A7C15ull; return k ^ (k >> 32); }
+    uint32_t *find(uint64_t k) {
+        for (uint64_t i = mix(k) & mask;; i = (i + 1) & mask) {
+            if (keys[i] == k) return &vals[i];
+            if (keys[i] == kEmpty) return nullptr;
+        }
+    }
+    // inserts when absent; returns the slot's value either way
+    uint32_t &at(uint64_t k, uint32_t v_if_new, bool *inserted) {
+        for (uint64_t i = mix(k) & mask;; i = (i + 1) & mask) {
+            if (keys[i] == k) { *inserted = false; return vals[i]; }
+            if (keys[i] == kEmpty) { keys[i] = k; vals[i] = v_if_new; *inserted = true; return vals[i]; }
+        }
+    }
+};
+
 struct Route {
     uint32_t prefix, plen, metric;
     uint8_t flags, origin_type;
     uint32_t origin_adv, origin_id;
     bool has_sid = false; uint32_t sid_value = 0; uint8_t sid_flags = 0; bool sid_is_label = false;
     bool has_label = false; uint32_t label = 0;
-    std::vector<Nh> nh;
+    std::vector<Nh> nh;                          // owned next hops (labelled, merged or truncated) ...
+    const std::vector<Nh> *shared = nullptr;     // ... or the vertex's own set, untouched (most routes)
+    const std::vector<Nh> &hops() const { return shared ? *shared : nh; }
+    void own() { if (shared) { nh = *shared; shared = nullptr; } }
 };
 
 inline uint64_t pkey(uint32_t prefix, uint32_t plen) { return ((uint64_t)prefix << 8) | plen; }
@@ -403,21 +439,23 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
     for (uint32_t v : spt) vnh[v] = rs.vertex_nexthops(v);
 
     // ---- intra-area routes (update_rib_intra_area) ------------------------------------
-    std::unordered_map<uint64_t, const hl_ospfv2_ext_prefix *> extp;   // (adv_rtr, prefix/len) first wins
+    FlatMap64 extp;                      // (adv_rtr, prefix/len) -> index of the first live entry
     auto ekey = [](uint32_t adv, uint32_t prefix, uint32_t plen) {
-        return ((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen;
+        return (((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen) & 0x7FFFFFFFFFFFFFFFull;
     };
     if (a->sr_enabled) {
+        extp.init(a->n_ext_prefixes);
         for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
             const auto &e = a->ext_prefixes[i];
             if (e.age == HL_LSA_MAX_AGE) continue;
-            extp.emplace(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), &e);
+            bool fresh;
+            extp.at(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), i, &fresh);
         }
     }
     auto ext_find = [&](uint32_t adv, uint32_t prefix, uint32_t plen) -> const hl_ospfv2_ext_prefix * {
-        auto it = extp.find(ekey(adv, prefix, plen));
-        if (it == extp.end()) return nullptr;
-        const auto *e = it->second;
+        const uint32_t *slot = extp.find(ekey(adv, prefix, plen));
+        if (!slot) return nullptr;
+        const auto *e = &a->ext_prefixes[*slot];
         if (e->adv_rtr == adv && e->prefix == prefix && (uint32_t)__builtin_popcount(e->mask) == plen) return e;
         // hash-key collision: fall back to a scan (first match in LSDB order)
         for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
@@ -427,12 +465,12 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
         }
         return nullptr;
     };
-    std::unordered_map<uint64_t, uint32_t> rib_idx;
+    FlatMap64 rib_idx;
     std::vector<Route> rib;
     std::vector<uint8_t> rib_live;
     {   // at most one entry per stub link / network vertex: no rehash, no vector regrowth
         const size_t cap = (size_t)a->n_links + a->n_network_lsas + 1;
-        rib_idx.reserve(cap);
+        rib_idx.init(cap);
         rib.reserve(cap);
         rib_live.reserve(cap);
     }
@@ -457,29 +495,38 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
         return it->second;
     };
 
+    // the neighbours that next hops name are the root's few: remember their entries
+    std::vector<std::pair<uint32_t, const RouterInfo *>> nbr_memo;
+    auto nbr_ri = [&](uint32_t rid) -> const RouterInfo & {
+        for (auto &kv : nbr_memo) if (kv.first == rid) return *kv.second;
+        const RouterInfo &ri = cached_ri(rid);
+        if (nbr_memo.size() < 64) nbr_memo.emplace_back(rid, &ri);
+        return ri;
+    };
     auto add_stub = [&](uint32_t v, uint32_t prefix, uint32_t plen, uint32_t stub_metric, uint32_t adv_rtr) {
         uint32_t m = dist[v] + stub_metric;
         if (m > 0xFFFF) m = 0xFFFF;
         const uint64_t key = pkey(prefix, plen);
-        auto it = rib_idx.find(key);
-        Route *cur = (it != rib_idx.end() && rib_live[it->second]) ? &rib[it->second] : nullptr;
+        const uint32_t *slot = rib_idx.find(key);
+        Route *cur = (slot && rib_live[*slot]) ? &rib[*slot] : nullptr;
         if (cur && m > cur->metric) return;
         uint8_t otype; uint32_t oadv, oid;
         if (f.is_router[v]) { const auto &l = a->router_lsas[f.lsa_of[v]]; otype = 1; oadv = l.adv_rtr; oid = l.lsa_id; }
         else { const auto &l = a->network_lsas[f.lsa_of[v]]; otype = 2; oadv = l.adv_rtr; oid = l.lsa_id; }
         if (!f.is_router[v] && cur) {
             if (m > cur->metric || oid < cur->origin_id) return;
-            rib_live[it->second] = 0;   // o.remove()
+            rib_live[*slot] = 0;        // o.remove()
             cur = nullptr;
         }
         Route nr;
         nr.prefix = prefix; nr.plen = plen; nr.metric = m;
         nr.flags = hops[v] == 0 ? HL_ROUTE_CONNECTED : 0;
         nr.origin_type = otype; nr.origin_adv = oadv; nr.origin_id = oid;
-        nr.nh = vnh[v];
+        nr.shared = &vnh[v];
         if (a->sr_enabled) {
             const hl_ospfv2_ext_prefix *ep = ext_find(adv_rtr, prefix, plen);
             if (ep && ep->route_type == 1 && ep->has_sid && cached_ri(oadv).has_sr_algo) {
+                nr.own();                        // per-route labels on the next hops
                 const bool local = hops[v] == 0, last_hop = hops[v] == 1;
                 nr.has_sid = true; nr.sid_value = ep->sid_value; nr.sid_flags = ep->sid_flags;
                 nr.sid_is_label = ep->sid_is_label;
@@ -503,7 +550,7 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
                     }
                     if (!decided) {
                         if (!ep->sid_is_label) {
-                            const RouterInfo &nri = cached_ri(x.nbr);
+                            const RouterInfo &nri = nbr_ri(x.nbr);
                             if (!nri.srgb.empty()) ok = index_to_label(ep->sid_value, nri.srgb, &lab);
                         } else {
                             lab = last_hop ? ep->sid_value : 3u; ok = true;
@@ -517,13 +564,17 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
         Route *route;
         if (cur) {
             if (nr.metric < cur->metric) *cur = std::move(nr);
-            else if (nr.metric == cur->metric) for (const Nh &x : nr.nh) nh_insert(cur->nh, x);
+            else if (nr.metric == cur->metric) { cur->own(); for (const Nh &x : nr.hops()) nh_insert(cur->nh, x); }
             route = cur;
         } else {
-            if (it != rib_idx.end()) { rib[it->second] = std::move(nr); rib_live[it->second] = 1; route = &rib[it->second]; }
-            else { rib_idx.emplace(key, (uint32_t)rib.size()); rib.push_back(std::move(nr)); rib_live.push_back(1); route = &rib.back(); }
+            if (slot) { rib[*slot] = std::move(nr); rib_live[*slot] = 1; route = &rib[*slot]; }
+            else {
+                bool fresh;
+                rib_idx.at(key, (uint32_t)rib.size(), &fresh);
+                rib.push_back(std::move(nr)); rib_live.push_back(1); route = &rib.back();
+            }
         }
-        if (route->nh.size() > a->max_paths) route->nh.resize(a->max_paths);
+        if (route->hops().size() > a->max_paths) { route->own(); route->nh.resize(a->max_paths); }
     };
     for (uint32_t v : spt) {
         if (!f.is_router[v]) {
@@ -540,14 +591,16 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
     }
 
     // ---- export ---------------------------------------------------------------------------
+    std::vector<std::pair<uint64_t, uint32_t>> order;      // (prefix, length) key next to the index: a flat sort
+    order.reserve(rib.size());
+    for (uint32_t i = 0; i < rib.size(); ++i) if (rib_live[i]) order.emplace_back(pkey(rib[i].prefix, rib[i].plen), i);
+    std::sort(order.begin(), order.end());
     std::vector<uint32_t> live;
-    for (uint32_t i = 0; i < rib.size(); ++i) if (rib_live[i]) live.push_back(i);
-    std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
-        return rib[x].prefix != rib[y].prefix ? rib[x].prefix < rib[y].prefix : rib[x].plen < rib[y].plen;
-    });
+    live.reserve(order.size());
+    for (auto &kv : order) live.push_back(kv.second);
     uint32_t n_rtr_in_spt = 0, need_h = 0;
     for (uint32_t v : spt) { need_h += (uint32_t)vnh[v].size(); if (f.is_router[v]) { ++n_rtr_in_spt; need_h += (uint32_t)vnh[v].size(); } }
-    for (uint32_t i : live) need_h += (uint32_t)rib[i].nh.size();
+    for (uint32_t i : live) need_h += (uint32_t)rib[i].hops().size();
     out->n_vertices = (uint32_t)spt.size();
     out->n_routers = n_rtr_in_spt;
     out->n_routes = (uint32_t)live.size();
@@ -597,8 +650,8 @@ int area_from_planes(const hspf_ospfv2_flat &f, const hl_ospfv2_area *a, uint32_
         o.has_prefix_sid = r.has_sid; o.prefix_sid_value = r.sid_value; o.prefix_sid_flags = r.sid_flags;
         o.prefix_sid_is_label = r.sid_is_label;
         o.has_sr_label = r.has_label; o.sr_label = r.has_label ? r.label : 0;
-        o.nh_off = h; o.n_nh = (uint32_t)r.nh.size();
-        put(r.nh);
+        o.nh_off = h; o.n_nh = (uint32_t)r.hops().size();
+        put(r.hops());
         out->routes[i++] = o;
     }
     return HSPF_OK;
