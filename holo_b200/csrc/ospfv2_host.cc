@@ -749,16 +749,32 @@ int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable *
         const uint32_t V = (uint32_t)f.ids.size();
         // Extended-Prefix entries by (advertising router, prefix): the first live one in LSDB order
         // (lsdb iteration + find, sr.rs:29-49), and which routers announce the SPF algorithm
-        struct EKey { uint32_t adv, prefix, plen; bool operator==(const EKey &o) const { return adv == o.adv && prefix == o.prefix && plen == o.plen; } };
-        struct EHash { size_t operator()(const EKey &k) const { return ((size_t)k.adv * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.prefix << 7) ^ k.plen; } };
-        std::unordered_map<EKey, uint32_t, EHash> extp;
+        // (advertising router, prefix) -> first live Extended-Prefix entry in LSDB order (lsdb iteration + find,
+        // sr.rs:29-49): a flat table on a folded key, verified on the entry, with a scan behind a false hit
+        FlatMap64 extp;
+        auto ekey = [](uint32_t adv, uint32_t prefix, uint32_t plen) {
+            return (((uint64_t)adv << 38) ^ ((uint64_t)prefix << 6) ^ plen) & 0x7FFFFFFFFFFFFFFFull;
+        };
+        auto ext_lookup = [&](uint32_t adv, uint32_t prefix, uint32_t plen) -> int32_t {
+            const uint32_t *slot = extp.find(ekey(adv, prefix, plen));
+            if (!slot) return -1;
+            const auto &e = a->ext_prefixes[*slot];
+            if (e.adv_rtr == adv && e.prefix == prefix && (uint32_t)__builtin_popcount(e.mask) == plen) return (int32_t)*slot;
+            for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
+                const auto &x = a->ext_prefixes[i];
+                if (x.age != HL_LSA_MAX_AGE && x.adv_rtr == adv && x.prefix == prefix && (uint32_t)__builtin_popcount(x.mask) == plen)
+                    return (int32_t)i;
+            }
+            return -1;
+        };
         std::unordered_set<uint32_t> sr_algo;
         if (a->sr_enabled) {
-            extp.reserve(a->n_ext_prefixes);
+            extp.init(a->n_ext_prefixes);
             for (uint32_t i = 0; i < a->n_ext_prefixes; ++i) {
                 const auto &e = a->ext_prefixes[i];
                 if (e.age == HL_LSA_MAX_AGE) continue;
-                extp.emplace(EKey{e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)}, i);
+                bool fresh;
+                extp.at(ekey(e.adv_rtr, e.prefix, (uint32_t)__builtin_popcount(e.mask)), i, &fresh);
             }
             for (uint32_t i = 0; i < a->n_ri_lsas; ++i)
                 if (a->ri_lsas[i].age != HL_LSA_MAX_AGE && a->ri_lsas[i].has_sr_algo) sr_algo.insert(a->ri_lsas[i].adv_rtr);
@@ -776,11 +792,11 @@ int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable *
             r.c.vertex = v; r.c.origin_id = oid; r.c.metric = (uint16_t)metric; r.c.is_network = otype == 2;
             r.otype = otype; r.oadv = oadv; r.ext = -1;
             if (a->sr_enabled && sr_algo.count(oadv)) {
-                auto it = extp.find(EKey{oadv, prefix, plen});
-                if (it != extp.end()) {
-                    const auto &e = a->ext_prefixes[it->second];
+                const int32_t ei = ext_lookup(oadv, prefix, plen);
+                if (ei >= 0) {
+                    const auto &e = a->ext_prefixes[ei];
                     if (e.route_type == 1 && e.has_sid) {
-                        r.ext = (int32_t)it->second;
+                        r.ext = ei;
                         const uint64_t key = ((uint64_t)e.sid_value << 16) | ((uint64_t)e.sid_flags << 8) | (e.sid_is_label ? 1u : 0u);
                         auto ins = sid_class.emplace(key, (uint16_t)rt->t.sids.size());
                         if (ins.second) {
@@ -806,11 +822,15 @@ int hspf_ospfv2_rtable_create(const hspf_ospfv2_flat *flat, hspf_ospfv2_rtable *
                 }
             }
         }
-        std::sort(raw.begin(), raw.end(), [](const Raw &x, const Raw &y) {
-            if (x.prefix != y.prefix) return x.prefix < y.prefix;
-            if (x.plen != y.plen) return x.plen < y.plen;
-            return x.seq < y.seq;
-        });
+        {   // (prefix, length, order of appearance): sort flat keys, then gather the records
+            std::vector<std::pair<uint64_t, uint32_t>> order(raw.size());
+            for (size_t i = 0; i < raw.size(); ++i) order[i] = {pkey(raw[i].prefix, raw[i].plen), raw[i].seq};
+            std::sort(order.begin(), order.end());
+            std::vector<Raw> sorted;
+            sorted.reserve(raw.size());
+            for (auto &kv : order) sorted.push_back(raw[kv.second]);
+            raw.swap(sorted);
+        }
         auto &t = rt->t;
         t.n_vertices = V;
         for (size_t i = 0; i < raw.size(); ++i) {
