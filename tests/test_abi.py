@@ -76,3 +76,15 @@ def test_build_fingerprint_covers_flags_sources_and_not_the_checkout_root(tmp_pa
     stamp = built[0].with_suffix(".so.stamp")
     assert stamp.exists() and build._up_to_date(built[0], stamp.read_text().strip())
     assert not build._up_to_date(built[0], "0" * 64)
+
+
+def test_integration_doc_names_only_declared_entry_points():
+    """Every `hspf_*` function INTEGRATION.md binds or calls is declared in include/*.h (and so exported)."""
+    text = (ROOT / "INTEGRATION.md").read_text()
+    named = set(re.findall(r"\b(hspf_[a-z0-9_]+)\s*\(", text))
+    declared = set(declared_symbols())
+    # shorthand the text uses for families of calls
+    named = {n for n in named if not n.endswith("_")}
+    missing = sorted(n for n in named if n not in declared)
+    assert not missing, missing
+    assert len(named) > 30
